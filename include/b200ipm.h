@@ -1,0 +1,165 @@
+/*
+ * b200ipm.h -- C ABI of libb200ipm.so: the B200-native (sm_100a) Newton-step engine that replaces the
+ * per-iteration hot path of jkaardal/pyipm (reference: /root/reference/pyipm.py @ ccc74da).
+ *
+ * The reference has no FFI: its "operator interface" is the set of compiled-callable slots that
+ * IPM.compile() assigns (pyipm.py:855-954) and IPM.solve() consumes (pyipm.py:1658-1814).  Each entry point
+ * below names the slot / code region it replaces.  INTEGRATION.md shows the ctypes binding a maintainer of
+ * the reference would add (pyipm_b200/_lib.py is that binding, in full).
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error (b200ipm_last_error() has the text); no exceptions
+ *     and no C++/torch types cross this boundary;
+ *   - a handle owns ALL its device memory and one CUDA stream (the one given at create time, or its own);
+ *     a handle is not thread-safe, distinct handles are independent;
+ *   - all host arrays are caller-owned, C-order float64, copied in/out;  `on_device != 0` on the bind/set
+ *     calls means the pointers are device pointers on the handle's device (copied device-to-device);
+ *   - vector ordering is the reference's: z = [x (D) | s (N) | lda_e (M) | lda_i (N)]  (pyipm.py:655-668),
+ *     Jacobians are D x M / D x N ("transposed", pyipm.py:117,138,223-225), lda = [lda_e | lda_i];
+ *   - the product never falls back to the CPU: if no CUDA device is present create() fails.
+ */
+#ifndef B200IPM_H
+#define B200IPM_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200IPM_VERSION 100
+
+typedef struct b200ipm_engine* b200ipm_handle;
+typedef struct b200ipm_ldlt*   b200ipm_ldlt_handle;
+
+/* Solver constants: IPM.__init__ kwargs (pyipm.py:311-314, defaults :161-212) + engine knobs. */
+typedef struct b200ipm_params {
+    double mu, nu, rho, tau, eta, beta;   /* pyipm.py:338-343 */
+    double Xtol, Ktol;                    /* pyipm.py:346-350 */
+    double eps;                           /* np.finfo(float64).eps, pyipm.py:336 */
+    double reg_coef;                      /* sqrt(eps) = delta0, pyipm.py:353,372 */
+    int    nrefine;                       /* iterative-refinement sweeps against the UNREDUCED KKT residual */
+    int    ls_batch;                      /* speculative line-search trials evaluated per launch */
+    int    max_reg_retries;               /* cap on the delta*=10 loop (pyipm.py:1399-1403 has none) */
+    int    reserved;
+} b200ipm_params;
+
+/* Everything one inner iteration (pyipm.py:1714-1754) reports back. */
+typedef struct b200ipm_step_info {
+    double kkt_norm[4];      /* 2-norms of (kkt1, kkt2, kkt3, kkt4) at the NEW point (pyipm.py:1754, 958-991) */
+    double fval;             /* f at the new x (pyipm.py:1758,1778) */
+    double delta;            /* diagonal shift after reghess (pyipm.py:1390-1402) */
+    double mu, nu;           /* barrier / merit parameters after the step (nu: pyipm.py:1727-1735) */
+    double alpha_smax, alpha_lmax;   /* fraction-to-the-boundary limits (pyipm.py:1739-1742) */
+    double alpha_s, alpha_l;         /* accepted step lengths (pyipm.py:1507-1510,1553-1562) */
+    double alpha_corr;               /* second-order-correction scaling, 0 if none */
+    double phi0, dphi0;              /* merit value / directional derivative at the old point */
+    double rcond;                    /* reciprocal-condition estimate used for the pyipm.py:1381 test */
+    double resid;                    /* || b - K dz ||_inf of the unreduced system after refinement */
+    double con_l1;                   /* ||con||_1 at the old point (pyipm.py:1732) */
+    int    n_neg, n_zero;            /* inertia of the accepted condensed KKT matrix */
+    int    n_factor;                 /* factorisations this step (= eigvalsh calls in the reference) */
+    int    n_backtracks;             /* tau-multiplications in search() (pyipm.py:1492-1505) */
+    int    soc_tried, soc_accepted;  /* pyipm.py:1464-1489 / 1516-1536 */
+    int    signal;                   /* 0 ok, -2 bad direction (pyipm.py:1502,1548) */
+    int    eq_reg;                   /* 1 if the eq-multiplier block was regularised (pyipm.py:1383-1389) */
+    float  ms_eval, ms_assemble, ms_factor, ms_solve, ms_search, ms_total;   /* CUDA-event phase times */
+    float  ms_hess_kernel, ms_condense_kernel;   /* the two SYRK-shaped fp64 contractions, per launch */
+} b200ipm_step_info;
+
+int         b200ipm_version(void);
+const char* b200ipm_last_error(void);
+/* number of kernels this library has launched in this process (bench.py's "gpu_launches") */
+long long   b200ipm_launch_count(void);
+
+/* ---- lifecycle ----------------------------------------------------------------------------------- */
+/* Replaces IPM.__init__/compile() workspace setup (pyipm.py:311-376, 410-467).  `stream` is a cudaStream_t
+ * (NULL => the handle creates its own non-blocking stream). */
+int b200ipm_create(int D, int M, int N, const b200ipm_params* p, int device, void* stream, b200ipm_handle* out);
+int b200ipm_destroy(b200ipm_handle h);
+int b200ipm_set_params(b200ipm_handle h, const b200ipm_params* p);
+int b200ipm_sync(b200ipm_handle h);
+
+/* ---- problem binding: replaces symbolic autodiff of f/ce/ci (pyipm.py:473-509) ------------------- */
+/* Dense synthetic family (BASELINE.json configs 2/3/5): f = 1/2 x'Qx + c'x + q4/4 sum x^4,
+ * ce = A x + 1/2 (U x)^2 - b, ci = G x - 1/2 (V x)^2 + r.  At/Ut are D x M, Gt/Vt are D x N (row-major);
+ * Ut, Vt may be NULL. */
+int b200ipm_bind_quad(b200ipm_handle h, const double* Q, const double* c, double q4,
+                      const double* At, const double* Ut, const double* b,
+                      const double* Gt, const double* Vt, const double* r, int on_device);
+/* Sparse-polynomial lowering (the ten example problems, pyipm.py:1920-2131): CSR monomial table, row 0 = f,
+ * rows 1..M = ce, rows M+1..M+N = ci; optional xlogx_coeff * sum x*log(x + xlogx_shift) added to f. */
+int b200ipm_bind_poly(b200ipm_handle h, int nterms, const int* term_row, const double* term_coeff,
+                      const int* term_ptr, const int* fac_var, const int* fac_pow,
+                      double xlogx_coeff, double xlogx_shift);
+/* User-callable mode: the caller evaluated f, df (D), ce (M), ci (N), J = [dce | dci] (D x (M+N)) and
+ * d2L = d2f - d2ce - d2ci (D x D; only its upper triangle is used, pyipm.py:785,827) at the current state. */
+int b200ipm_set_derivs(b200ipm_handle h, double fval, const double* df, const double* ce, const double* ci,
+                       const double* J, const double* d2L, int on_device);
+
+/* ---- state: (x, s, lda) and the hidden shared scalars mu_dev / nu_dev / delta (pyipm.py:363-364,1628) */
+int b200ipm_set_state(b200ipm_handle h, const double* x, const double* s, const double* lda,
+                      double mu, double nu, double delta);
+int b200ipm_get_state(b200ipm_handle h, double* x, double* s, double* lda,
+                      double* mu, double* nu, double* delta);
+int b200ipm_set_mu_host(b200ipm_handle h, double mu_host);   /* pyipm.py:1603/1606 (reghess uses mu_host) */
+
+/* ---- operator slots -------------------------------------------------------------------------------- */
+/* cost(x), pyipm.py:855-857 */
+int b200ipm_cost(b200ipm_handle h, double* fval);
+/* grad(x,s,lda), pyipm.py:610-668,865-869: g (K = D+2N+M, may be NULL) and the four KKT 2-norms with
+ * kkt2 = g_s * s (pyipm.py:958-991).  One pass over J. */
+int b200ipm_residual(b200ipm_handle h, double* g, double kkt_norm[4]);
+/* KKT(x,s,lda), pyipm.py:958-991: the four condition vectors themselves (D, N, M, N). */
+int b200ipm_kkt(b200ipm_handle h, double* kkt1, double* kkt2, double* kkt3, double* kkt4);
+/* con(x,s) pyipm.py:564-579 (M+N) and jaco(x)[:D,:] pyipm.py:581-607 (D x (M+N)); either may be NULL. */
+int b200ipm_con_jac(b200ipm_handle h, double* con, double* J);
+/* hess(x,s,lda), pyipm.py:768-844: the reference's FULL K x K symmetric KKT matrix (drop-in slot and parity
+ * check; the hot path never forms it).  H is K*K doubles on the host. */
+int b200ipm_hess_full(b200ipm_handle h, double* H);
+/* Lagrangian Hessian d2L (D x D, symmetrised from its upper triangle). */
+int b200ipm_d2L(b200ipm_handle h, double* W);
+/* phi(x,s) / dphi(x,s,dz[:D+N]), pyipm.py:670-721,890-904 at the current state (dz from the last solve). */
+int b200ipm_merit(b200ipm_handle h, double* phi, double* dphi);
+/* init_slack / init_lambda, pyipm.py:723-744,1596-1621: sets s and/or lda in the state. */
+int b200ipm_init_slack(b200ipm_handle h);
+int b200ipm_init_lambda(b200ipm_handle h);
+/* barrier update, pyipm.py:1804-1814: returns the new mu (caller stores it via set_state/set_mu_host). */
+int b200ipm_update_mu(b200ipm_handle h, double* mu_new);
+
+/* reghess + sym_solve_cmp, pyipm.py:1373-1406,1718-1725: condensed KKT formation, inertia-corrected LDL^T,
+ * solve + refinement, multiplier sign flip.  dz (K, may be NULL) is in the reference ordering. */
+int b200ipm_direction(b200ipm_handle h, double* dz, b200ipm_step_info* info);
+/* step(), pyipm.py:1408-1436 (closed-form ratio test; equals the golden-section bracket to ~1e-15). */
+int b200ipm_step_max(b200ipm_handle h, double* alpha_smax, double* alpha_lmax);
+/* One full inner iteration, pyipm.py:1714-1754: grad, hess, reghess, solve, nu update, step rules, line
+ * search (+ second-order correction), state update, KKT at the new point. */
+int b200ipm_newton_step(b200ipm_handle h, b200ipm_step_info* info);
+
+/* ---- generic dense symmetric-indefinite factor/solve (sym_solve_cmp slot, pyipm.py:911-914; config 4) -- */
+/* A is n x n (leading dimension lda) symmetric, lower triangle referenced; factored in a private copy. */
+int b200ipm_ldlt_create(int n, int device, void* stream, b200ipm_ldlt_handle* out);
+int b200ipm_ldlt_destroy(b200ipm_ldlt_handle h);
+int b200ipm_ldlt_factor(b200ipm_ldlt_handle h, const double* A, int lda, int on_device,
+                        int inertia[3] /* pos, neg, zero */, double* rcond_est);
+/* B is n x nrhs column-major-by-rhs (rhs r occupies B[r*n .. r*n+n)); solved in place; nrefine sweeps of
+ * iterative refinement against the original A. */
+int b200ipm_ldlt_solve(b200ipm_ldlt_handle h, double* B, int nrhs, int nrefine, int on_device);
+/* Tile-level building blocks used by the multi-GPU 2-D block-cyclic driver (pyipm_b200/dist_ldlt.py). */
+int b200ipm_ldlt_tile_factor(b200ipm_ldlt_handle h, double* tile_dev, int ld, int nb,
+                             double* linv_dev, double* dblk_dev, int* perm_dev, int counts[3]);
+int b200ipm_ldlt_panel(b200ipm_ldlt_handle h, double* panel_dev, int ld, int rows, const double* linv_dev,
+                       const double* dblk_dev, const int* perm_dev, double* w_dev);
+int b200ipm_gemm_nt_update(b200ipm_ldlt_handle h, double* C_dev, int ldc, int rows, int cols,
+                           const double* A_dev, int lda, const double* B_dev, int ldb, int k, int lower_only);
+
+/* ---- test hooks: individual kernels against the oracle (tests/test_gpu_kernels.py) ---------------- */
+/* C (n x n, symmetric, mirrored) = beta*sym(triu(Cin)) + diag(dadd) + shift*I + sum_t alpha_t A_t diag(w_t) A_t'.
+ * Host arrays; A_t is n x K_t row-major.  force_simple != 0 runs the scalar reference kernel. */
+int b200ipm_test_syrk(int n, const double* Cin, double beta, const double* dadd, double shift,
+                      int nterms, const double* const* A, const double* const* w, const int* K,
+                      const double* alpha, double* C, int force_simple, float* ms);
+int b200ipm_test_gemv(int rows, int cols, const double* A, const double* v, double* y, int transpose);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200IPM_H */

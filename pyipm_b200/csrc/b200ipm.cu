@@ -1,0 +1,1162 @@
+// b200ipm.cu -- engine + C ABI (include/b200ipm.h).  One translation unit; kernels live in the .cuh files.
+//
+// One inner iteration of the primal-dual interior-point method (pyipm.py:1714-1754) on the device:
+//   evaluate f/ce/ci derivatives (lowered problem forms) -> residual g and KKT norms (one pass over J)
+//   -> Lagrangian Hessian W (DMMA SYRK) -> condensed KKT matrix  [W + delta I + dci S dci', dce; dce', -reg I]
+//   -> tile-pivoted LDL^T with inertia, delta/reg retry loop of reghess (pyipm.py:1373-1406)
+//   -> solve + iterative refinement against the UNREDUCED KKT system -> nu rule, fraction-to-the-boundary,
+//   Armijo backtracking with speculative batched trials (+ second-order correction) -> state update.
+// Host code only sequences kernels and takes the scalar branch decisions the reference takes in Python.
+#include "../../include/b200ipm.h"
+#include "common.cuh"
+#include "vec.cuh"
+#include "gemm_nt.cuh"
+#include "ldlt.cuh"
+#include "engine_kernels.cuh"
+
+#include <vector>
+#include <algorithm>
+
+namespace b200 {
+thread_local std::string g_last_error;
+std::atomic<long long> g_launches{0};
+}  // namespace b200
+using namespace b200;
+
+enum { KIND_NONE = 0, KIND_QUAD = 1, KIND_POLY = 2, KIND_CALLABLE = 3 };
+enum { EV_START = 0, EV_EVAL, EV_ASSEMBLE, EV_FACTOR, EV_SOLVE, EV_SEARCH, EV_HESS0, EV_HESS1, EV_COND0, EV_COND1, EV_N };
+
+struct b200ipm_engine {
+    int D = 0, M = 0, N = 0, K = 0, Kc = 0, C = 0, ldJ = 0, ldW = 0;
+    int device = 0;
+    cudaStream_t st = nullptr;
+    bool own_stream = false;
+    b200ipm_params p{};
+    double mu = 0, nu = 0, delta = 0, mu_host = 0;
+    int kind = KIND_NONE;
+    // state
+    double *x = nullptr, *s = nullptr, *lam = nullptr;
+    // derivatives at the state
+    double *fval = nullptr, *df = nullptr, *ce = nullptr, *ci = nullptr, *J = nullptr, *W = nullptr;
+    bool eval_valid = false, resid_valid = false;
+    // residual / direction
+    double *g = nullptr, *sigma = nullptr, *bvec = nullptr, *tvec = nullptr, *rhs = nullptr, *sol = nullptr;
+    double *ycur = nullptr, *ycor = nullptr, *rho = nullptr, *dz = nullptr, *wx = nullptr, *jt = nullptr;
+    double *Hb = nullptr;   // W + dci S dci'  (D x ldW), without delta
+    double reg_cur = 0, delta_eff = 0;
+    LdltWs F;               // condensed KKT factorisation (order Kc)
+    LdltWs F2;              // pseudo-inverse / second-order-correction systems (lazy)
+    bool F2_ready = false;
+    int F2_n = 0;
+    double *Jt = nullptr;   // (M+N) x D transposed Jacobian for the SOC normal equations (lazy)
+    // scratch
+    double *scr = nullptr, *part = nullptr, *red = nullptr, *trial = nullptr, *xt = nullptr, *st_ = nullptr;
+    double *pvec = nullptr, *cnew = nullptr, *uvec = nullptr;
+    double *h_red = nullptr;   // pinned
+    int max_batch = 512;
+    // QUAD
+    double *Q = nullptr, *qc = nullptr, *At = nullptr, *Ut = nullptr, *qb = nullptr, *Gt = nullptr, *Vt = nullptr,
+           *qr = nullptr, *xdiag = nullptr;
+    double q4 = 0;
+    double *qx = nullptr, *ax = nullptr, *ux = nullptr, *gx = nullptr, *vx = nullptr;
+    double *qd = nullptr, *ad = nullptr, *ud = nullptr, *gd = nullptr, *vd = nullptr;
+    // POLY
+    int *p_rowptr = nullptr, *p_ptr = nullptr, *p_fvar = nullptr, *p_fpow = nullptr;
+    double* p_coeff = nullptr;
+    PolyData poly{};
+    cudaEvent_t ev[EV_N];
+    double last_red[8];     // host copy of the residual reductions at the current state
+};
+typedef b200ipm_engine Eng;
+
+struct b200ipm_ldlt {
+    LdltWs F;
+    double *A0 = nullptr, *b = nullptr, *x = nullptr, *r = nullptr, *c = nullptr;
+    int device = 0;
+    cudaStream_t st = nullptr;
+    bool own_stream = false;
+    bool factored = false;
+};
+
+template <typename T>
+static int dalloc(T** p, size_t n) {
+    CU(cudaMalloc(p, sizeof(T) * std::max<size_t>(n, 1)));
+    return 0;
+}
+static int up(Eng* h, double* dst, const double* src, size_t n, int on_device) {
+    if (n == 0 || src == nullptr) return 0;
+    CU(cudaMemcpyAsync(dst, src, sizeof(double) * n, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->st));
+    return 0;
+}
+static int down(Eng* h, double* dst, const double* src, size_t n) {
+    if (n == 0 || dst == nullptr) return 0;
+    CU(cudaMemcpyAsync(dst, src, sizeof(double) * n, cudaMemcpyDeviceToHost, h->st));
+    return 0;
+}
+static int fetch_red(Eng* h, const double* dsrc, int n) {
+    CU(cudaMemcpyAsync(h->h_red, dsrc, sizeof(double) * n, cudaMemcpyDeviceToHost, h->st));
+    CU(cudaStreamSynchronize(h->st));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ evaluation
+static QuadData quad_data(Eng* h) {
+    return QuadData{h->Q, h->qc, h->At, h->Ut, h->qb, h->Gt, h->Vt, h->qr, h->q4};
+}
+// linear images of a vector v (length D):  Q v, A v, U v, G v, V v
+static int quad_images(Eng* h, const double* v, double* qv, double* av, double* uv, double* gv, double* vv) {
+    const int D = h->D, M = h->M, N = h->N;
+    RET(gemv_n(h->st, h->Q, D, D, D, v, nullptr, 0.0, 1.0, qv));
+    if (M) {
+        RET(gemv_t(h->st, h->At, M, D, M, v, nullptr, 0.0, 1.0, av, h->scr));
+        if (h->Ut) RET(gemv_t(h->st, h->Ut, M, D, M, v, nullptr, 0.0, 1.0, uv, h->scr));
+    }
+    if (N) {
+        RET(gemv_t(h->st, h->Gt, N, D, N, v, nullptr, 0.0, 1.0, gv, h->scr));
+        if (h->Vt) RET(gemv_t(h->st, h->Vt, N, D, N, v, nullptr, 0.0, 1.0, vv, h->scr));
+    }
+    return 0;
+}
+
+// f, df, ce, ci, J and W = d2L at the current (x, lda)
+static int eval_derivs(Eng* h) {
+    if (h->eval_valid) return 0;
+    const int D = h->D, M = h->M, N = h->N;
+    if (h->kind == KIND_QUAD) {
+        RET(quad_images(h, h->x, h->qx, h->ax, h->ux, h->gx, h->vx));
+        quad_point_kernel<<<1, 1024, 0, h->st>>>(D, M, N, quad_data(h), h->x, h->qx, h->ax, h->ux, h->gx, h->vx, h->df,
+                                                 h->xdiag, h->ce, h->ci, h->fval);
+        LAUNCHED();
+        if (h->C) {
+            quad_jac_kernel<<<std::min(cdiv(D * h->C, 256), 148 * 16), 256, 0, h->st>>>(D, M, N, quad_data(h), h->ux, h->vx,
+                                                                                         h->J, h->ldJ);
+            LAUNCHED();
+        }
+        // W = Q + 3 q4 diag(x^2) - Ut diag(lda_e) Ut' + Vt diag(lda_i) Vt'      (a3; DMMA SYRK)
+        GemmArgs a{};
+        a.C = h->W; a.ldc = h->ldW; a.Cin = h->Q; a.ldcin = D; a.dadd = h->xdiag; a.n = D; a.m = D; a.beta = 1.0;
+        a.shift = 0.0; a.mode = GEMM_UPPER_MIRROR; a.nterms = 0;
+        if (M && h->Ut) a.t[a.nterms++] = GemmTerm{h->Ut, h->Ut, h->lam, M, M, M, -1.0};
+        if (N && h->Vt) a.t[a.nterms++] = GemmTerm{h->Vt, h->Vt, h->lam + M, N, N, N, 1.0};
+        CU(cudaEventRecord(h->ev[EV_HESS0], h->st));
+        RET(gemm_nt(h->st, a));
+        CU(cudaEventRecord(h->ev[EV_HESS1], h->st));
+    } else if (h->kind == KIND_POLY) {
+        poly_eval_kernel<<<1, 256, 0, h->st>>>(D, M, N, h->poly, h->x, h->fval, h->df, h->ce, h->ci, h->J, h->ldJ);
+        LAUNCHED();
+        poly_hess_kernel<<<cdiv(D * D, 256), 256, 0, h->st>>>(D, M, N, h->poly, h->x, h->lam, h->W, h->ldW);
+        LAUNCHED();
+        CU(cudaEventRecord(h->ev[EV_HESS0], h->st));
+        CU(cudaEventRecord(h->ev[EV_HESS1], h->st));
+    } else if (h->kind == KIND_CALLABLE) {
+        return fail_msg("callable mode: b200ipm_set_derivs must be called after every state change");
+    } else {
+        return fail_msg("no problem bound (b200ipm_bind_quad / b200ipm_bind_poly / b200ipm_set_derivs)");
+    }
+    h->eval_valid = true;
+    h->resid_valid = false;
+    return 0;
+}
+
+// g, sigma, KKT norms, ||con||_1 at the current state  (a1, a10)
+static int residual(Eng* h) {
+    RET(eval_derivs(h));
+    if (h->resid_valid) return 0;
+    const int D = h->D, M = h->M, N = h->N;
+    int npart = 0;
+    if (h->C) {
+        // g_x = df - J * lda   (the headline HBM-bound kernel: one pass over J), squared norm fused
+        RET(gemv_n(h->st, h->J, h->ldJ, D, h->C, h->lam, h->df, 1.0, -1.0, h->g, h->part));
+        npart = gemv_n_blocks(D);
+    } else {
+        npart = cdiv(D, 256);
+        copy_sq_kernel<<<npart, 256, 0, h->st>>>(D, h->df, h->g, h->part);   // unconstrained: g_x = df
+        LAUNCHED();
+    }
+    residual_tail_kernel<<<1, 1024, 0, h->st>>>(D, M, N, h->s, h->lam, h->ce, h->ci, h->mu, h->p.eps, h->g, h->sigma,
+                                                h->part, npart, h->fval, h->red);
+    LAUNCHED();
+    RET(fetch_red(h, h->red, 6));
+    for (int i = 0; i < 6; i++) h->last_red[i] = h->h_red[i];
+    h->resid_valid = true;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ KKT formation
+// Hb = W + dci diag(sigma) dci'      (condensation, a3/a4; DMMA SYRK)
+static int condense(Eng* h) {
+    const int D = h->D, M = h->M, N = h->N;
+    GemmArgs a{};
+    a.C = h->Hb; a.ldc = h->ldW; a.Cin = h->W; a.ldcin = h->ldW; a.dadd = nullptr; a.n = D; a.m = D; a.beta = 1.0;
+    a.shift = 0.0; a.mode = GEMM_UPPER_MIRROR; a.nterms = 0;
+    if (N) a.t[a.nterms++] = GemmTerm{h->J + M, h->J + M, h->sigma, h->ldJ, h->ldJ, N, 1.0};
+    CU(cudaEventRecord(h->ev[EV_COND0], h->st));
+    RET(gemm_nt(h->st, a));
+    CU(cudaEventRecord(h->ev[EV_COND1], h->st));
+    return 0;
+}
+// Kc = [[Hb + delta I, .], [dce', -reg I]]  (lower triangle is what the factorisation reads)
+static int build_kc(Eng* h, double delta, double reg) {
+    const int D = h->D, M = h->M;
+    kc_xx_kernel<<<std::min(cdiv(D * D, 256), 148 * 32), 256, 0, h->st>>>(h->Hb, h->ldW, D, delta, h->F.A, h->F.ld);
+    LAUNCHED();
+    if (M) {
+        RET(transpose(h->st, h->J, h->ldJ, D, M, h->F.A + (size_t)D * h->F.ld, h->F.ld));
+        kc_ee_kernel<<<cdiv(M * M, 256), 256, 0, h->st>>>(h->F.A, h->F.ld, D, M, reg);
+        LAUNCHED();
+    }
+    h->delta_eff = delta;
+    h->reg_cur = reg;
+    return 0;
+}
+static int factor_once(Eng* h, double delta, double reg, int* n_neg, int* n_zero, double* rcond) {
+    RET(build_kc(h, delta, reg));
+    RET(ldlt_factor(h->F));
+    int cnt[4];
+    double ds[2];
+    CU(cudaMemcpyAsync(cnt, h->F.counts, sizeof(int) * 4, cudaMemcpyDeviceToHost, h->st));
+    CU(cudaMemcpyAsync(ds, h->F.dstat, sizeof(double) * 2, cudaMemcpyDeviceToHost, h->st));
+    CU(cudaStreamSynchronize(h->st));
+    *n_neg = cnt[0];
+    *n_zero = cnt[1];
+    *rcond = (cnt[1] > 0 || !(ds[1] > 0.0)) ? 0.0 : ds[0] / ds[1];
+    return 0;
+}
+// reghess (pyipm.py:1373-1406) on the condensed matrix: full-K inertia (D+N, M+N, 0)  <=>  condensed has
+// exactly M negative pivots (Haynsworth).
+static int factor_regularised(Eng* h, b200ipm_step_info* info) {
+    const int M = h->M;
+    int n_neg = 0, n_zero = 0, nfac = 0;
+    double rcond = 0.0;
+    RET(factor_once(h, 0.0, 0.0, &n_neg, &n_zero, &rcond));
+    nfac++;
+    const double rcond0 = rcond;
+    int eq_reg = 0;
+    if (rcond <= h->p.eps || n_neg != M) {
+        double reg = 0.0;
+        if (rcond <= h->p.eps && M) {
+            reg = h->p.reg_coef * h->p.eta * pow(h->mu_host, h->p.beta);
+            eq_reg = 1;
+        }
+        if (h->delta == 0.0) h->delta = h->p.reg_coef;
+        else h->delta = std::max(h->delta / 2.0, h->p.reg_coef);
+        RET(factor_once(h, h->delta, reg, &n_neg, &n_zero, &rcond));
+        nfac++;
+        int guard = 0;
+        while (n_neg != M) {
+            if (++guard > h->p.max_reg_retries) return fail_msg("reghess: inertia correction did not converge");
+            h->delta *= 10.0;
+            RET(factor_once(h, h->delta, reg, &n_neg, &n_zero, &rcond));
+            nfac++;
+        }
+    }
+    if (info) {
+        info->n_neg = n_neg; info->n_zero = n_zero; info->n_factor = nfac; info->rcond = rcond0; info->eq_reg = eq_reg;
+        info->delta = h->delta;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ solve
+// K y for the unreduced system -> rho = b - K y, returns ||rho||_inf in h->red[0] (device)
+static int kkt_residual_vec(Eng* h, const double* b, const double* y, double* rho) {
+    const int D = h->D, M = h->M, N = h->N, K = h->K;
+    if (h->C) {
+        RET(gemv_n(h->st, h->J, h->ldJ, D, h->C, y + D + N, nullptr, 0.0, 1.0, h->wx));           // J [y_e; y_i]
+        RET(gemv_n(h->st, h->W, h->ldW, D, D, y, h->wx, 1.0, 1.0, h->wx));                        // + W dx
+        RET(gemv_t(h->st, h->J, h->ldJ, D, h->C, y, nullptr, 0.0, 1.0, h->jt, h->scr));           // J' dx
+    } else {
+        RET(gemv_n(h->st, h->W, h->ldW, D, D, y, nullptr, 0.0, 1.0, h->wx));
+    }
+    const int nb = cdiv(K, 256);
+    kkt_resid_kernel<<<nb, 256, 0, h->st>>>(D, M, N, h->sigma, h->delta_eff, h->reg_cur, b, y, h->wx, h->jt, rho, h->part);
+    LAUNCHED();
+    max_partials_kernel<<<1, 256, 0, h->st>>>(h->part, nb, h->red + 8);
+    LAUNCHED();
+    return 0;
+}
+// generic condensed solve of  K y = b  (b, y in reference ordering, y with the internal multiplier sign)
+static int condensed_solve(Eng* h, const double* b, double* y) {
+    const int D = h->D, M = h->M, N = h->N;
+    if (N) {
+        cond_t_kernel<<<cdiv(N, 256), 256, 0, h->st>>>(D, M, N, h->sigma, b, h->tvec);
+        LAUNCHED();
+        RET(gemv_n(h->st, h->J + M, h->ldJ, D, N, h->tvec, b, 1.0, 1.0, h->rhs));   // b_x + dci t
+    } else {
+        CU(cudaMemcpyAsync(h->rhs, b, sizeof(double) * D, cudaMemcpyDeviceToDevice, h->st));
+    }
+    if (M) CU(cudaMemcpyAsync(h->rhs + D, b + D + N, sizeof(double) * M, cudaMemcpyDeviceToDevice, h->st));
+    RET(ldlt_solve(h->F, h->rhs, h->sol));
+    if (N) RET(gemv_t(h->st, h->J, h->ldJ, D, h->C, h->sol, nullptr, 0.0, 1.0, h->jt, h->scr));
+    expand_kernel<<<cdiv(std::max(D, std::max(M, N)), 256), 256, 0, h->st>>>(D, M, N, h->sigma, b, h->sol, h->jt, y);
+    LAUNCHED();
+    return 0;
+}
+static int solve_direction(Eng* h, b200ipm_step_info* info) {
+    const int K = h->K;
+    axpby_kernel<<<cdiv(K, 256), 256, 0, h->st>>>(K, -1.0, h->g, 0.0, nullptr, h->bvec);   // b = -g (pyipm.py:1717)
+    LAUNCHED();
+    RET(condensed_solve(h, h->bvec, h->ycur));
+    for (int it = 0; it < h->p.nrefine; it++) {
+        RET(kkt_residual_vec(h, h->bvec, h->ycur, h->rho));
+        RET(condensed_solve(h, h->rho, h->ycor));
+        axpby_kernel<<<cdiv(K, 256), 256, 0, h->st>>>(K, 1.0, h->ycur, 1.0, h->ycor, h->ycur);
+        LAUNCHED();
+    }
+    RET(kkt_residual_vec(h, h->bvec, h->ycur, h->rho));   // final residual (reported)
+    flip_kernel<<<cdiv(K, 256), 256, 0, h->st>>>(h->D, h->N, K, h->ycur, h->dz);
+    LAUNCHED();
+    (void)info;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ merit at a point
+// (f, ||con||_1, sum log s) at an explicit point (xt, st) -> h->trial[0..2] (device)
+static int merit_pieces_at(Eng* h, const double* xt, const double* st) {
+    const int D = h->D, M = h->M, N = h->N;
+    if (h->kind == KIND_POLY) {
+        poly_point_merit_kernel<<<1, 256, 0, h->st>>>(D, M, N, h->poly, xt, st, h->trial);
+        LAUNCHED();
+    } else if (h->kind == KIND_QUAD) {
+        // images of xt into the direction slots, then a k=0 "trial" with alpha = 0 around (xt, st)
+        RET(quad_images(h, xt, h->qd, h->ad, h->ud, h->gd, h->vd));
+        QuadImages im{h->qd, h->ad, h->ud, h->gd, h->vd, h->qd, h->ad, h->ud, h->gd, h->vd};
+        quad_trial_kernel<<<1, 256, 0, h->st>>>(D, M, N, quad_data(h), im, xt, st, xt, st, 0.0, 1.0, 0, h->trial);
+        LAUNCHED();
+    } else {
+        return fail_msg("merit evaluation needs a lowered problem (quad / poly)");
+    }
+    return 0;
+}
+// trials alpha0 * tau^(k0 + k), k = 0..nb-1 along the current dz -> h->trial (3 per trial), copied to host
+static int merit_trials(Eng* h, double alpha0, int k0, int nb, std::vector<double>& out) {
+    const int D = h->D, M = h->M, N = h->N;
+    if (h->kind == KIND_POLY) {
+        if (sizeof(double) * (D + N) > 40 * 1024) return fail_msg("polynomial lowering supports D + N <= 5120");
+        poly_trial_kernel<<<nb, 256, sizeof(double) * (D + N), h->st>>>(D, M, N, h->poly, h->x, h->s, h->dz, h->dz + D,
+                                                                         alpha0, h->p.tau, k0, h->trial);
+        LAUNCHED();
+    } else if (h->kind == KIND_QUAD) {
+        QuadImages im{h->qx, h->ax, h->ux, h->gx, h->vx, h->qd, h->ad, h->ud, h->gd, h->vd};
+        quad_trial_kernel<<<nb, 256, 0, h->st>>>(D, M, N, quad_data(h), im, h->x, h->s, h->dz, h->dz + D, alpha0, h->p.tau,
+                                                 k0, h->trial);
+        LAUNCHED();
+    } else {
+        return fail_msg("line search needs a lowered problem (quad / poly)");
+    }
+    out.resize((size_t)3 * nb);
+    CU(cudaMemcpyAsync(out.data(), h->trial, sizeof(double) * 3 * nb, cudaMemcpyDeviceToHost, h->st));
+    CU(cudaStreamSynchronize(h->st));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ F2 helpers
+static int ensure_F2(Eng* h, int n) {
+    if (h->F2_ready && h->F2_n == n) return 0;
+    if (h->F2_ready) ldlt_free(h->F2);
+    RET(ldlt_alloc(h->F2, n, h->st));
+    h->F2_ready = true;
+    h->F2_n = n;
+    return 0;
+}
+static int max_row_sqnorm(Eng* h, const double* Mx, int ld, int rows, int cols, double* out) {
+    const int nb = std::min(rows, 296);
+    row_sqnorm_max_kernel<<<nb, 256, 0, h->st>>>(Mx, ld, rows, cols, h->part);
+    LAUNCHED();
+    max_partials_kernel<<<1, 256, 0, h->st>>>(h->part, nb, h->red + 9);
+    LAUNCHED();
+    RET(fetch_red(h, h->red + 9, 1));
+    *out = h->h_red[0];
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ second-order correction
+// dz_p = -lstsq(A, c_new) with A = jaco(x0)' (pyipm.py:1468-1477, 1520-1529): minimum-norm solution through the
+// normal equations  z = A' (A A' + eps I)^-1 c  with iterated-Tikhonov sweeps,  A A' = J'J + diag(0_M, I_N).
+static int soc_direction(Eng* h, const double* cnew /* device, M+N */, double* pz /* device, D+N */) {
+    const int D = h->D, M = h->M, N = h->N, C = h->C;
+    if (!h->Jt) RET(dalloc(&h->Jt, (size_t)C * rup(D, 16)));
+    const int ldt = (int)rup(D, 16);
+    RET(transpose(h->st, h->J, h->ldJ, D, C, h->Jt, ldt));
+    RET(ensure_F2(h, C));
+    double scale = 0.0;
+    RET(max_row_sqnorm(h, h->Jt, ldt, C, D, &scale));
+    scale += 1.0;
+    const double tik = 1e-10 * scale;
+    // G = Jt Jt' + diag(0, I) + tik I : build SYRK into F2.A then add the slack identity on the diagonal
+    GemmArgs a{};
+    a.C = h->F2.A; a.ldc = h->F2.ld; a.Cin = nullptr; a.n = C; a.m = C; a.beta = 0.0; a.shift = tik; a.dadd = nullptr;
+    a.mode = GEMM_UPPER_MIRROR; a.nterms = 1;
+    a.t[0] = GemmTerm{h->Jt, h->Jt, nullptr, ldt, ldt, D, 1.0};
+    // dadd: ones on the inequality rows
+    CU(cudaMemsetAsync(h->uvec, 0, sizeof(double) * C, h->st));
+    if (N) {
+        fill_kernel<<<cdiv(N, 256), 256, 0, h->st>>>(N, 1.0, h->uvec + M);
+        LAUNCHED();
+    }
+    a.dadd = h->uvec;
+    RET(gemm_nt(h->st, a));
+    RET(ldlt_factor(h->F2));
+    // iterated Tikhonov: z_{k+1} = z_k + A'(G)^-1 (c - A z_k);   A z = [J' z_x]_e, [J' z_x]_i - z_s
+    CU(cudaMemsetAsync(pz, 0, sizeof(double) * (D + N), h->st));
+    for (int it = 0; it < 3; it++) {
+        // r = c - A z  -> h->cnew-sized scratch h->tvec? use h->ycor (length K >= C)
+        if (it == 0) {
+            CU(cudaMemcpyAsync(h->ycor, cnew, sizeof(double) * C, cudaMemcpyDeviceToDevice, h->st));
+        } else {
+            RET(gemv_t(h->st, h->J, h->ldJ, D, C, pz, nullptr, 0.0, 1.0, h->jt, h->scr));   // J' z_x
+            axpby_kernel<<<cdiv(C, 256), 256, 0, h->st>>>(C, 1.0, cnew, -1.0, h->jt, h->ycor);
+            LAUNCHED();
+            if (N) {
+                axpby_kernel<<<cdiv(N, 256), 256, 0, h->st>>>(N, 1.0, h->ycor + M, 1.0, pz + D, h->ycor + M);
+                LAUNCHED();
+            }
+        }
+        RET(ldlt_solve(h->F2, h->ycor, h->rho));                                            // u = G^-1 r
+        // z_x += J u ; z_s += -u_i
+        RET(gemv_n(h->st, h->J, h->ldJ, D, C, h->rho, pz, 1.0, 1.0, pz));
+        if (N) {
+            axpby_kernel<<<cdiv(N, 256), 256, 0, h->st>>>(N, 1.0, pz + D, -1.0, h->rho + M, pz + D);
+            LAUNCHED();
+        }
+    }
+    // dz_p = -z
+    axpby_kernel<<<cdiv(D + N, 256), 256, 0, h->st>>>(D + N, -1.0, pz, 0.0, nullptr, pz);
+    LAUNCHED();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ line search
+// search() (pyipm.py:1438-1565).  Scalars and branch decisions on the host, every vector operation on the device.
+static int line_search(Eng* h, b200ipm_step_info* info, const double* stats /* host dir stats */) {
+    const int D = h->D, M = h->M, N = h->N;
+    const double eta = h->p.eta, tau = h->p.tau, eps = h->p.eps;
+    const bool con = (M + N) > 0;
+    const double f0 = h->last_red[5], c1_old = h->last_red[4];
+    const double logs0 = stats[3];
+    double phi0 = f0;
+    if (con) phi0 += h->nu * c1_old;
+    if (N) phi0 -= h->mu * logs0;
+    double dphi0 = stats[1];
+    if (con) dphi0 -= h->nu * c1_old;
+    if (N) dphi0 -= stats[2];
+    const double ndx = sqrt(stats[4]), nds = sqrt(stats[5]);
+    double a_s = N ? stats[6] : 1.0, a_l = N ? stats[7] : 1.0;
+    if (!con) a_l = 0.0;
+    info->alpha_smax = a_s;
+    info->alpha_lmax = a_l;
+    info->phi0 = phi0;
+    info->dphi0 = dphi0;
+    info->n_backtracks = 0;
+    info->soc_tried = info->soc_accepted = 0;
+    info->alpha_corr = 0.0;
+    info->signal = 0;
+
+    if (h->kind == KIND_QUAD) RET(quad_images(h, h->dz, h->qd, h->ad, h->ud, h->gd, h->vd));
+    auto phi_of = [&](const double* t) {
+        double v = t[0];
+        if (con) v += h->nu * t[1];
+        if (N) v -= h->mu * t[2];
+        return v;
+    };
+    std::vector<double> tr;
+    RET(merit_trials(h, a_s, 0, 1, tr));
+    bool correction = false;
+    double alpha_corr = 0.0;
+    if (phi_of(tr.data()) > phi0 + a_s * eta * dphi0) {
+        const double c1_new = tr[1];
+        if (con && c1_new > c1_old) {
+            // second-order correction (pyipm.py:1464-1489 / 1516-1536)
+            info->soc_tried = 1;
+            // c_new = con(x0 + a_s dx, s0 + a_s ds): evaluate through the explicit-point path
+            trial_point_kernel<<<cdiv(std::max(D, N), 256), 256, 0, h->st>>>(D, N, h->x, h->s, h->dz, a_s, nullptr, 0.0, 1.0,
+                                                                            h->xt, h->st_);
+            LAUNCHED();
+            // con at the trial point: reuse the evaluation kernels on (xt, st)
+            if (h->kind == KIND_POLY) {
+                poly_eval_kernel<<<1, 256, 0, h->st>>>(D, M, N, h->poly, h->xt, h->trial, nullptr, h->cnew, h->cnew + M,
+                                                       nullptr, 0);
+                LAUNCHED();
+            } else {
+                RET(quad_images(h, h->xt, h->qd, h->ad, h->ud, h->gd, h->vd));
+                quad_point_kernel<<<1, 1024, 0, h->st>>>(D, M, N, quad_data(h), h->xt, h->qd, h->ad, h->ud, h->gd, h->vd,
+                                                         nullptr, nullptr, h->cnew, h->cnew + M, h->trial);
+                LAUNCHED();
+            }
+            if (N) {
+                axpby_kernel<<<cdiv(N, 256), 256, 0, h->st>>>(N, 1.0, h->cnew + M, -1.0, h->st_, h->cnew + M);
+                LAUNCHED();
+            }
+            RET(soc_direction(h, h->cnew, h->pvec));
+            // phi(x0 + a_s dx + p_x, s0 + a_s ds + p_s)
+            trial_point_kernel<<<cdiv(std::max(D, N), 256), 256, 0, h->st>>>(D, N, h->x, h->s, h->dz, a_s, h->pvec, 1.0, 1.0,
+                                                                            h->xt, h->st_);
+            LAUNCHED();
+            RET(merit_pieces_at(h, h->xt, h->st_));
+            RET(fetch_red(h, h->trial, 3));
+            double t3[3] = {h->h_red[0], h->h_red[1], h->h_red[2]};
+            if (phi_of(t3) <= phi0 + a_s * eta * dphi0) {
+                if (N) {
+                    // alpha_corr = step(s0, a_s ds + p_s)
+                    axpby_kernel<<<cdiv(N, 256), 256, 0, h->st>>>(N, a_s, h->dz + D, 1.0, h->pvec + D, h->uvec);
+                    LAUNCHED();
+                    ftb_kernel<<<1, 1024, 0, h->st>>>(N, h->s, h->uvec, tau, h->red + 10);
+                    LAUNCHED();
+                    RET(fetch_red(h, h->red + 10, 1));
+                    alpha_corr = h->h_red[0];
+                    trial_point_kernel<<<cdiv(std::max(D, N), 256), 256, 0, h->st>>>(D, N, h->x, h->s, h->dz, a_s, h->pvec,
+                                                                                    1.0, alpha_corr, h->xt, h->st_);
+                    LAUNCHED();
+                    RET(merit_pieces_at(h, h->xt, h->st_));
+                    RET(fetch_red(h, h->trial, 3));
+                    double t4[3] = {h->h_red[0], h->h_red[1], h->h_red[2]};
+                    if (phi_of(t4) <= phi0 + a_s * eta * dphi0) correction = true;
+                } else {
+                    alpha_corr = 1.0;
+                    correction = true;
+                }
+            }
+            if (h->kind == KIND_QUAD && !correction)   // direction images were clobbered by the explicit-point path
+                RET(quad_images(h, h->dz, h->qd, h->ad, h->ud, h->gd, h->vd));
+        }
+        if (!correction) {
+            // backtracking (pyipm.py:1490-1505 / 1537-1551): alpha <- tau * alpha until Armijo holds
+            const double a0_s = a_s, a0_l = a_l;
+            int k = 1;   // trial index: alpha = a0 * tau^k
+            a_s *= tau;
+            a_l *= tau;
+            info->n_backtracks = 1;
+            int batch = std::max(1, h->p.ls_batch);
+            bool done = false;
+            while (!done) {
+                const int nb = std::min(batch, h->max_batch);
+                RET(merit_trials(h, a0_s, k, nb, tr));
+                for (int q = 0; q < nb; q++) {
+                    // a_s, a_l already correspond to trial k+q
+                    if (!(phi_of(&tr[3 * q]) > phi0 + a_s * eta * dphi0)) { done = true; break; }
+                    const double nrm = N ? sqrt((a_s * ndx) * (a_s * ndx) + (a_l * nds) * (a_l * nds)) : a_s * ndx;
+                    if (nrm < eps) {
+                        info->signal = -2;   // pyipm.py:1502 / 1548: state left untouched
+                        info->alpha_s = info->alpha_l = 0.0;
+                        return 0;
+                    }
+                    a_s *= tau;
+                    a_l *= tau;
+                    info->n_backtracks++;
+                }
+                k += nb;
+                batch *= 2;
+            }
+            (void)a0_l;
+        }
+    }
+    info->soc_accepted = correction ? 1 : 0;
+    info->alpha_corr = alpha_corr;
+    info->alpha_s = a_s;
+    info->alpha_l = a_l;
+    // state update
+    if (correction) {
+        // x = x0 + alpha_corr (a_s dx + p_x), s likewise, lda = lda0 + a_l dl
+        trial_point_kernel<<<cdiv(std::max(D, N), 256), 256, 0, h->st>>>(D, N, h->x, h->s, h->dz, a_s, h->pvec, 1.0, alpha_corr,
+                                                                        h->xt, h->st_);
+        LAUNCHED();
+        CU(cudaMemcpyAsync(h->x, h->xt, sizeof(double) * D, cudaMemcpyDeviceToDevice, h->st));
+        if (N) CU(cudaMemcpyAsync(h->s, h->st_, sizeof(double) * N, cudaMemcpyDeviceToDevice, h->st));
+        if (con) {
+            axpby_kernel<<<cdiv(M + N, 256), 256, 0, h->st>>>(M + N, 1.0, h->lam, a_l, h->dz + D + N, h->lam);
+            LAUNCHED();
+        }
+    } else {
+        update_state_kernel<<<cdiv(std::max(D, M + N), 256), 256, 0, h->st>>>(D, M, N, a_s, a_l, h->dz, h->x, h->s, h->lam);
+        LAUNCHED();
+    }
+    h->eval_valid = false;
+    h->resid_valid = false;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ direction + step
+static int compute_direction(Eng* h, b200ipm_step_info* info) {
+    RET(residual(h));
+    CU(cudaEventRecord(h->ev[EV_EVAL], h->st));
+    RET(condense(h));
+    CU(cudaEventRecord(h->ev[EV_ASSEMBLE], h->st));
+    RET(factor_regularised(h, info));
+    CU(cudaEventRecord(h->ev[EV_FACTOR], h->st));
+    RET(solve_direction(h, info));
+    CU(cudaEventRecord(h->ev[EV_SOLVE], h->st));
+    return 0;
+}
+static int dir_stats(Eng* h, double* stats) {
+    dir_stats_kernel<<<1, 1024, 0, h->st>>>(h->D, h->M, h->N, h->df, h->s, h->lam, h->dz, h->mu, h->p.eps, h->p.tau, h->red);
+    LAUNCHED();
+    RET(fetch_red(h, h->red, 9));
+    for (int i = 0; i < 9; i++) stats[i] = h->h_red[i];
+    return 0;
+}
+static void fill_times(Eng* h, b200ipm_step_info* info) {
+    float t;
+    auto el = [&](int a, int b) { t = 0.f; cudaEventElapsedTime(&t, h->ev[a], h->ev[b]); return t; };
+    info->ms_eval = el(EV_START, EV_EVAL);
+    info->ms_assemble = el(EV_EVAL, EV_ASSEMBLE);
+    info->ms_factor = el(EV_ASSEMBLE, EV_FACTOR);
+    info->ms_solve = el(EV_FACTOR, EV_SOLVE);
+    info->ms_search = el(EV_SOLVE, EV_SEARCH);
+    info->ms_total = el(EV_START, EV_SEARCH);
+    info->ms_hess_kernel = el(EV_HESS0, EV_HESS1);
+    info->ms_condense_kernel = el(EV_COND0, EV_COND1);
+}
+
+// =========================================================================================== C ABI
+extern "C" {
+
+int b200ipm_version(void) { return B200IPM_VERSION; }
+const char* b200ipm_last_error(void) { return g_last_error.c_str(); }
+long long b200ipm_launch_count(void) { return g_launches.load(); }
+
+int b200ipm_create(int D, int M, int N, const b200ipm_params* p, int device, void* stream, b200ipm_handle* out) {
+    if (!out || !p || D <= 0 || M < 0 || N < 0) return fail_msg("b200ipm_create: bad arguments");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail_msg("b200ipm_create: no CUDA device available (this library has no CPU fallback)");
+    CU(cudaSetDevice(device));
+    Eng* h = new Eng();
+    h->D = D; h->M = M; h->N = N; h->C = M + N; h->K = D + 2 * N + M; h->Kc = D + M;
+    h->ldJ = (int)rup(std::max(h->C, 1), 16);
+    h->ldW = (int)rup(D, 16);
+    h->device = device;
+    h->p = *p;
+    h->mu = p->mu; h->nu = p->nu; h->delta = 0.0; h->mu_host = p->mu;
+    if (stream) { h->st = (cudaStream_t)stream; h->own_stream = false; }
+    else { CU(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking)); h->own_stream = true; }
+    for (int i = 0; i < EV_N; i++) CU(cudaEventCreate(&h->ev[i]));
+    RET(ldlt_init_attrs());
+    RET(ldlt_init_solve_attrs());
+    const int K = h->K, C = h->C;
+    RET(dalloc(&h->x, D)); RET(dalloc(&h->s, N)); RET(dalloc(&h->lam, C));
+    RET(dalloc(&h->fval, 8)); RET(dalloc(&h->df, D)); RET(dalloc(&h->ce, M)); RET(dalloc(&h->ci, N));
+    RET(dalloc(&h->J, (size_t)D * h->ldJ)); RET(dalloc(&h->W, (size_t)D * h->ldW)); RET(dalloc(&h->Hb, (size_t)D * h->ldW));
+    CU(cudaMemsetAsync(h->J, 0, sizeof(double) * (size_t)D * h->ldJ, h->st));
+    RET(dalloc(&h->g, K)); RET(dalloc(&h->sigma, N)); RET(dalloc(&h->bvec, K)); RET(dalloc(&h->tvec, N));
+    RET(dalloc(&h->rhs, h->Kc)); RET(dalloc(&h->sol, h->Kc)); RET(dalloc(&h->ycur, K)); RET(dalloc(&h->ycor, K));
+    RET(dalloc(&h->rho, K)); RET(dalloc(&h->dz, K)); RET(dalloc(&h->wx, D)); RET(dalloc(&h->jt, std::max(C, 1)));
+    CU(cudaMemsetAsync(h->jt, 0, sizeof(double) * std::max(C, 1), h->st));
+    const size_t scr = std::max(gemv_t_scratch_doubles(D, std::max(C, 1)), gemv_t_scratch_doubles(D, D));
+    RET(dalloc(&h->scr, scr));
+    RET(dalloc(&h->part, std::max<size_t>(4096, (size_t)cdiv(K, 8) + 64)));
+    RET(dalloc(&h->red, 32));
+    RET(dalloc(&h->trial, (size_t)3 * h->max_batch));
+    RET(dalloc(&h->xt, D)); RET(dalloc(&h->st_, N)); RET(dalloc(&h->pvec, D + N)); RET(dalloc(&h->cnew, C));
+    RET(dalloc(&h->uvec, std::max(C, D)));
+    RET(dalloc(&h->xdiag, D));
+    RET(dalloc(&h->qx, D)); RET(dalloc(&h->ax, M)); RET(dalloc(&h->ux, M)); RET(dalloc(&h->gx, N)); RET(dalloc(&h->vx, N));
+    RET(dalloc(&h->qd, D)); RET(dalloc(&h->ad, M)); RET(dalloc(&h->ud, M)); RET(dalloc(&h->gd, N)); RET(dalloc(&h->vd, N));
+    CU(cudaMallocHost(&h->h_red, sizeof(double) * 64));
+    RET(ldlt_alloc(h->F, h->Kc, h->st));
+    CU(cudaStreamSynchronize(h->st));
+    *out = h;
+    return 0;
+}
+
+int b200ipm_destroy(b200ipm_handle h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->st);
+    double* bufs[] = {h->x, h->s, h->lam, h->fval, h->df, h->ce, h->ci, h->J, h->W, h->Hb, h->g, h->sigma, h->bvec, h->tvec,
+                      h->rhs, h->sol, h->ycur, h->ycor, h->rho, h->dz, h->wx, h->jt, h->scr, h->part, h->red, h->trial,
+                      h->xt, h->st_, h->pvec, h->cnew, h->uvec, h->xdiag, h->qx, h->ax, h->ux, h->gx, h->vx, h->qd, h->ad,
+                      h->ud, h->gd, h->vd, h->Q, h->qc, h->At, h->Ut, h->qb, h->Gt, h->Vt, h->qr, h->Jt, h->p_coeff};
+    for (double* b : bufs) cudaFree(b);
+    cudaFree(h->p_rowptr); cudaFree(h->p_ptr); cudaFree(h->p_fvar); cudaFree(h->p_fpow);
+    cudaFreeHost(h->h_red);
+    ldlt_free(h->F);
+    if (h->F2_ready) ldlt_free(h->F2);
+    for (int i = 0; i < EV_N; i++) cudaEventDestroy(h->ev[i]);
+    if (h->own_stream) cudaStreamDestroy(h->st);
+    delete h;
+    return 0;
+}
+
+int b200ipm_set_params(b200ipm_handle h, const b200ipm_params* p) {
+    if (!h || !p) return fail_msg("null argument");
+    h->p = *p;
+    return 0;
+}
+int b200ipm_sync(b200ipm_handle h) {
+    CU(cudaStreamSynchronize(h->st));
+    return 0;
+}
+
+int b200ipm_bind_quad(b200ipm_handle h, const double* Q, const double* c, double q4, const double* At, const double* Ut,
+                      const double* b, const double* Gt, const double* Vt, const double* r, int on_device) {
+    if (!h || !Q || !c) return fail_msg("bind_quad: Q and c are required");
+    CU(cudaSetDevice(h->device));
+    const size_t D = h->D, M = h->M, N = h->N;
+    if (M && (!At || !b)) return fail_msg("bind_quad: At and b are required when M > 0");
+    if (N && (!Gt || !r)) return fail_msg("bind_quad: Gt and r are required when N > 0");
+    if (!h->Q) { RET(dalloc(&h->Q, D * D)); RET(dalloc(&h->qc, D)); }
+    RET(up(h, h->Q, Q, D * D, on_device)); RET(up(h, h->qc, c, D, on_device));
+    h->q4 = q4;
+    if (M) {
+        if (!h->At) { RET(dalloc(&h->At, D * M)); RET(dalloc(&h->qb, M)); }
+        RET(up(h, h->At, At, D * M, on_device)); RET(up(h, h->qb, b, M, on_device));
+        if (Ut) { if (!h->Ut) RET(dalloc(&h->Ut, D * M)); RET(up(h, h->Ut, Ut, D * M, on_device)); }
+        else if (h->Ut) { cudaFree(h->Ut); h->Ut = nullptr; }
+    }
+    if (N) {
+        if (!h->Gt) { RET(dalloc(&h->Gt, D * N)); RET(dalloc(&h->qr, N)); }
+        RET(up(h, h->Gt, Gt, D * N, on_device)); RET(up(h, h->qr, r, N, on_device));
+        if (Vt) { if (!h->Vt) RET(dalloc(&h->Vt, D * N)); RET(up(h, h->Vt, Vt, D * N, on_device)); }
+        else if (h->Vt) { cudaFree(h->Vt); h->Vt = nullptr; }
+    }
+    CU(cudaStreamSynchronize(h->st));
+    h->kind = KIND_QUAD;
+    h->eval_valid = h->resid_valid = false;
+    return 0;
+}
+
+int b200ipm_bind_poly(b200ipm_handle h, int nterms, const int* term_row, const double* term_coeff, const int* term_ptr,
+                      const int* fac_var, const int* fac_pow, double xlogx_coeff, double xlogx_shift) {
+    if (!h || nterms < 0) return fail_msg("bind_poly: bad arguments");
+    CU(cudaSetDevice(h->device));
+    const int R = 1 + h->M + h->N;
+    std::vector<int> rowptr(R + 1, 0);
+    for (int t = 0; t < nterms; t++) {
+        if (term_row[t] < 0 || term_row[t] >= R) return fail_msg("bind_poly: term_row out of range");
+        if (t > 0 && term_row[t] < term_row[t - 1]) return fail_msg("bind_poly: terms must be sorted by row");
+        rowptr[term_row[t] + 1]++;
+    }
+    for (int r = 0; r < R; r++) rowptr[r + 1] += rowptr[r];
+    const int nfac = nterms ? term_ptr[nterms] : 0;
+    for (int a = 0; a < nfac; a++)
+        if (fac_var[a] < 0 || fac_var[a] >= h->D || fac_pow[a] < 1) return fail_msg("bind_poly: bad factor");
+    cudaFree(h->p_rowptr); cudaFree(h->p_ptr); cudaFree(h->p_fvar); cudaFree(h->p_fpow); cudaFree(h->p_coeff);
+    RET(dalloc(&h->p_rowptr, R + 1)); RET(dalloc(&h->p_ptr, nterms + 1)); RET(dalloc(&h->p_fvar, nfac));
+    RET(dalloc(&h->p_fpow, nfac)); RET(dalloc(&h->p_coeff, nterms));
+    CU(cudaMemcpyAsync(h->p_rowptr, rowptr.data(), sizeof(int) * (R + 1), cudaMemcpyHostToDevice, h->st));
+    std::vector<int> tp(nterms + 1, 0);
+    for (int t = 0; t <= nterms; t++) tp[t] = nterms ? term_ptr[t] : 0;
+    CU(cudaMemcpyAsync(h->p_ptr, tp.data(), sizeof(int) * (nterms + 1), cudaMemcpyHostToDevice, h->st));
+    if (nfac) {
+        CU(cudaMemcpyAsync(h->p_fvar, fac_var, sizeof(int) * nfac, cudaMemcpyHostToDevice, h->st));
+        CU(cudaMemcpyAsync(h->p_fpow, fac_pow, sizeof(int) * nfac, cudaMemcpyHostToDevice, h->st));
+    }
+    if (nterms) CU(cudaMemcpyAsync(h->p_coeff, term_coeff, sizeof(double) * nterms, cudaMemcpyHostToDevice, h->st));
+    CU(cudaStreamSynchronize(h->st));
+    h->poly = PolyData{nterms, R, h->p_rowptr, h->p_coeff, h->p_ptr, h->p_fvar, h->p_fpow, xlogx_coeff, xlogx_shift};
+    h->kind = KIND_POLY;
+    h->eval_valid = h->resid_valid = false;
+    return 0;
+}
+
+int b200ipm_set_derivs(b200ipm_handle h, double fval, const double* df, const double* ce, const double* ci, const double* J,
+                       const double* d2L, int on_device) {
+    if (!h || !df || !d2L) return fail_msg("set_derivs: df and d2L are required");
+    CU(cudaSetDevice(h->device));
+    const int D = h->D, M = h->M, N = h->N, C = h->C;
+    if (C && !J) return fail_msg("set_derivs: J is required when there are constraints");
+    const cudaMemcpyKind kd = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    CU(cudaMemcpyAsync(h->fval, &fval, sizeof(double), cudaMemcpyHostToDevice, h->st));
+    RET(up(h, h->df, df, D, on_device));
+    if (M) RET(up(h, h->ce, ce, M, on_device));
+    if (N) RET(up(h, h->ci, ci, N, on_device));
+    if (C) CU(cudaMemcpy2DAsync(h->J, sizeof(double) * h->ldJ, J, sizeof(double) * C, sizeof(double) * C, D, kd, h->st));
+    CU(cudaMemcpy2DAsync(h->W, sizeof(double) * h->ldW, d2L, sizeof(double) * D, sizeof(double) * D, D, kd, h->st));
+    dim3 blk(32, 8), grid(cdiv(D, 32), cdiv(D, 8));
+    sym_from_upper_kernel<<<grid, blk, 0, h->st>>>(h->W, h->ldW, D);
+    LAUNCHED();
+    CU(cudaStreamSynchronize(h->st));   // fval lives on the caller's stack
+    if (h->kind == KIND_NONE) h->kind = KIND_CALLABLE;
+    h->eval_valid = true;
+    h->resid_valid = false;
+    return 0;
+}
+
+int b200ipm_set_state(b200ipm_handle h, const double* x, const double* s, const double* lda, double mu, double nu,
+                      double delta) {
+    if (!h) return fail_msg("null handle");
+    CU(cudaSetDevice(h->device));
+    if (x) RET(up(h, h->x, x, h->D, 0));
+    if (s) RET(up(h, h->s, s, h->N, 0));
+    if (lda) RET(up(h, h->lam, lda, h->C, 0));
+    CU(cudaStreamSynchronize(h->st));
+    h->mu = mu; h->nu = nu; h->delta = delta;
+    if (x || lda) h->eval_valid = false;   // W, J, df depend on (x, lda) only
+    h->resid_valid = false;
+    return 0;
+}
+int b200ipm_get_state(b200ipm_handle h, double* x, double* s, double* lda, double* mu, double* nu, double* delta) {
+    if (!h) return fail_msg("null handle");
+    CU(cudaSetDevice(h->device));
+    RET(down(h, x, h->x, h->D)); RET(down(h, s, h->s, h->N)); RET(down(h, lda, h->lam, h->C));
+    CU(cudaStreamSynchronize(h->st));
+    if (mu) *mu = h->mu;
+    if (nu) *nu = h->nu;
+    if (delta) *delta = h->delta;
+    return 0;
+}
+int b200ipm_set_mu_host(b200ipm_handle h, double mu_host) {
+    h->mu_host = mu_host;
+    return 0;
+}
+
+int b200ipm_cost(b200ipm_handle h, double* fval) {
+    CU(cudaSetDevice(h->device));
+    RET(residual(h));
+    *fval = h->last_red[5];
+    return 0;
+}
+int b200ipm_residual(b200ipm_handle h, double* g, double kkt_norm[4]) {
+    CU(cudaSetDevice(h->device));
+    RET(residual(h));
+    if (g) { RET(down(h, g, h->g, h->K)); CU(cudaStreamSynchronize(h->st)); }
+    if (kkt_norm) for (int i = 0; i < 4; i++) kkt_norm[i] = h->last_red[i];
+    return 0;
+}
+int b200ipm_kkt(b200ipm_handle h, double* kkt1, double* kkt2, double* kkt3, double* kkt4) {
+    CU(cudaSetDevice(h->device));
+    RET(residual(h));
+    const int D = h->D, M = h->M, N = h->N;
+    RET(down(h, kkt1, h->g, D));
+    if (N && kkt2) {
+        // kkt2 = g_s * s (pyipm.py:972)
+        mul_kernel<<<cdiv(N, 256), 256, 0, h->st>>>(N, h->g + D, h->s, h->tvec);
+        LAUNCHED();
+        RET(down(h, kkt2, h->tvec, N));
+    }
+    if (M) RET(down(h, kkt3, h->g + D + N, M));
+    if (N) RET(down(h, kkt4, h->g + D + N + M, N));
+    CU(cudaStreamSynchronize(h->st));
+    return 0;
+}
+int b200ipm_con_jac(b200ipm_handle h, double* con, double* J) {
+    CU(cudaSetDevice(h->device));
+    RET(residual(h));
+    const int D = h->D, N = h->N, C = h->C;
+    if (con && C) RET(down(h, con, h->g + D + N, C));
+    if (J && C)
+        CU(cudaMemcpy2DAsync(J, sizeof(double) * C, h->J, sizeof(double) * h->ldJ, sizeof(double) * C, D,
+                             cudaMemcpyDeviceToHost, h->st));
+    CU(cudaStreamSynchronize(h->st));
+    return 0;
+}
+int b200ipm_hess_full(b200ipm_handle h, double* H) {
+    CU(cudaSetDevice(h->device));
+    RET(residual(h));
+    const size_t K = h->K;
+    double* dH = nullptr;
+    RET(dalloc(&dH, K * K));
+    full_kkt_kernel<<<(int)std::min<size_t>((K * K + 255) / 256, 148 * 32), 256, 0, h->st>>>(h->D, h->M, h->N, h->W, h->ldW,
+                                                                                             h->J, h->ldJ, h->sigma, dH);
+    LAUNCHED();
+    CU(cudaMemcpyAsync(H, dH, sizeof(double) * K * K, cudaMemcpyDeviceToHost, h->st));
+    CU(cudaStreamSynchronize(h->st));
+    cudaFree(dH);
+    return 0;
+}
+int b200ipm_d2L(b200ipm_handle h, double* W) {
+    CU(cudaSetDevice(h->device));
+    RET(eval_derivs(h));
+    CU(cudaMemcpy2DAsync(W, sizeof(double) * h->D, h->W, sizeof(double) * h->ldW, sizeof(double) * h->D, h->D,
+                         cudaMemcpyDeviceToHost, h->st));
+    CU(cudaStreamSynchronize(h->st));
+    return 0;
+}
+int b200ipm_merit(b200ipm_handle h, double* phi, double* dphi) {
+    CU(cudaSetDevice(h->device));
+    RET(residual(h));
+    double stats[9];
+    RET(dir_stats(h, stats));
+    const bool con = h->C > 0;
+    double p0 = h->last_red[5];
+    if (con) p0 += h->nu * h->last_red[4];
+    if (h->N) p0 -= h->mu * stats[3];
+    double d0 = stats[1];
+    if (con) d0 -= h->nu * h->last_red[4];
+    if (h->N) d0 -= stats[2];
+    if (phi) *phi = p0;
+    if (dphi) *dphi = d0;
+    return 0;
+}
+int b200ipm_init_slack(b200ipm_handle h) {
+    CU(cudaSetDevice(h->device));
+    if (!h->N) return 0;
+    RET(eval_derivs(h));
+    init_slack_kernel<<<cdiv(h->N, 256), 256, 0, h->st>>>(h->N, h->ci, h->p.Ktol, h->s);
+    LAUNCHED();
+    h->resid_valid = false;
+    return 0;
+}
+// lda0 = pinv(J) df (pyipm.py:723-730): minimum-norm least squares through (J J' + eps I), iterated Tikhonov
+int b200ipm_init_lambda(b200ipm_handle h) {
+    CU(cudaSetDevice(h->device));
+    const int D = h->D, M = h->M, N = h->N, C = h->C;
+    if (!C) return 0;
+    RET(eval_derivs(h));
+    RET(ensure_F2(h, D));
+    double scale = 0.0;
+    RET(max_row_sqnorm(h, h->J, h->ldJ, D, C, &scale));
+    const double tik = 1e-10 * (scale > 0.0 ? scale : 1.0);
+    GemmArgs a{};
+    a.C = h->F2.A; a.ldc = h->F2.ld; a.Cin = nullptr; a.dadd = nullptr; a.n = D; a.m = D; a.beta = 0.0; a.shift = tik;
+    a.mode = GEMM_UPPER_MIRROR; a.nterms = 1;
+    a.t[0] = GemmTerm{h->J, h->J, nullptr, h->ldJ, h->ldJ, C, 1.0};
+    RET(gemm_nt(h->st, a));
+    RET(ldlt_factor(h->F2));
+    CU(cudaMemsetAsync(h->lam, 0, sizeof(double) * C, h->st));
+    for (int it = 0; it < 3; it++) {
+        // r = df - J lda ; u = G^-1 r ; lda += J' u
+        RET(gemv_n(h->st, h->J, h->ldJ, D, C, h->lam, h->df, 1.0, -1.0, h->wx));
+        RET(ldlt_solve(h->F2, h->wx, h->xt));
+        RET(gemv_t(h->st, h->J, h->ldJ, D, C, h->xt, h->lam, 1.0, 1.0, h->lam, h->scr));
+    }
+    if (N) {
+        fix_lambda_kernel<<<cdiv(N, 256), 256, 0, h->st>>>(M, N, h->p.Ktol, h->lam);
+        LAUNCHED();
+    }
+    h->eval_valid = false;   // W depends on lda
+    h->resid_valid = false;
+    return 0;
+}
+int b200ipm_update_mu(b200ipm_handle h, double* mu_new) {
+    CU(cudaSetDevice(h->device));
+    const int N = h->N;
+    if (!N) { *mu_new = h->mu; return 0; }
+    mu_stats_kernel<<<1, 1024, 0, h->st>>>(h->M, N, h->s, h->lam, h->red + 12);
+    LAUNCHED();
+    RET(fetch_red(h, h->red + 12, 2));
+    const double mn = h->h_red[0], dot = h->h_red[1], eps = h->p.eps;
+    const double xi = N * mn / (dot + eps);                         // pyipm.py:1806-1808
+    const double t = std::min(0.05 * (1.0 - xi) / (xi + eps), 2.0);
+    double mu = 0.1 * (t * t * t) * dot / N;                        // pyipm.py:1809-1810
+    if (mu < 0.0) mu = 0.0;
+    *mu_new = mu;
+    return 0;
+}
+
+int b200ipm_direction(b200ipm_handle h, double* dz, b200ipm_step_info* info) {
+    if (!h) return fail_msg("null handle");
+    CU(cudaSetDevice(h->device));
+    b200ipm_step_info tmp{};
+    if (!info) info = &tmp;
+    CU(cudaEventRecord(h->ev[EV_START], h->st));
+    RET(compute_direction(h, info));
+    RET(fetch_red(h, h->red + 8, 1));
+    info->resid = h->h_red[0];
+    if (dz) { RET(down(h, dz, h->dz, h->K)); CU(cudaStreamSynchronize(h->st)); }
+    info->mu = h->mu; info->nu = h->nu;
+    return 0;
+}
+int b200ipm_step_max(b200ipm_handle h, double* alpha_smax, double* alpha_lmax) {
+    CU(cudaSetDevice(h->device));
+    double stats[9];
+    RET(dir_stats(h, stats));
+    if (alpha_smax) *alpha_smax = h->N ? stats[6] : 1.0;
+    if (alpha_lmax) *alpha_lmax = h->N ? stats[7] : 1.0;
+    return 0;
+}
+
+int b200ipm_newton_step(b200ipm_handle h, b200ipm_step_info* info) {
+    if (!h || !info) return fail_msg("null argument");
+    CU(cudaSetDevice(h->device));
+    memset(info, 0, sizeof(*info));
+    CU(cudaEventRecord(h->ev[EV_START], h->st));
+    RET(compute_direction(h, info));
+    double stats[9];
+    RET(dir_stats(h, stats));
+    info->resid = h->h_red[8];
+    info->con_l1 = h->last_red[4];
+    if (h->C) {
+        // merit parameter update (pyipm.py:1727-1735); IEEE semantics for ||con||_1 == 0 are the reference's
+        const double nu_thres = stats[0] / (1.0 - h->p.rho) / h->last_red[4];
+        if (h->nu < nu_thres) h->nu = nu_thres;
+    }
+    RET(line_search(h, info, stats));
+    CU(cudaEventRecord(h->ev[EV_SEARCH], h->st));
+    // KKT conditions at the new point (pyipm.py:1754); doubles as the residual of the next step
+    if (h->kind != KIND_CALLABLE) {
+        RET(residual(h));
+        for (int i = 0; i < 4; i++) info->kkt_norm[i] = h->last_red[i];
+        info->fval = h->last_red[5];
+    }
+    info->mu = h->mu; info->nu = h->nu; info->delta = h->delta;
+    CU(cudaStreamSynchronize(h->st));
+    fill_times(h, info);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ generic LDL^T
+int b200ipm_ldlt_create(int n, int device, void* stream, b200ipm_ldlt_handle* out) {
+    if (!out || n <= 0) return fail_msg("ldlt_create: bad arguments");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail_msg("b200ipm_ldlt_create: no CUDA device available (this library has no CPU fallback)");
+    CU(cudaSetDevice(device));
+    b200ipm_ldlt* h = new b200ipm_ldlt();
+    h->device = device;
+    if (stream) { h->st = (cudaStream_t)stream; } else { CU(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking)); h->own_stream = true; }
+    RET(ldlt_init_attrs());
+    RET(ldlt_init_solve_attrs());
+    RET(ldlt_alloc(h->F, n, h->st));
+    RET(dalloc(&h->A0, (size_t)n * h->F.ld));
+    RET(dalloc(&h->b, n)); RET(dalloc(&h->x, n)); RET(dalloc(&h->r, n)); RET(dalloc(&h->c, n));
+    *out = h;
+    return 0;
+}
+int b200ipm_ldlt_destroy(b200ipm_ldlt_handle h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->st);
+    ldlt_free(h->F);
+    cudaFree(h->A0); cudaFree(h->b); cudaFree(h->x); cudaFree(h->r); cudaFree(h->c);
+    if (h->own_stream) cudaStreamDestroy(h->st);
+    delete h;
+    return 0;
+}
+int b200ipm_ldlt_factor(b200ipm_ldlt_handle h, const double* A, int lda, int on_device, int inertia[3], double* rcond_est) {
+    if (!h || !A) return fail_msg("null argument");
+    CU(cudaSetDevice(h->device));
+    const int n = h->F.n, ld = h->F.ld;
+    CU(cudaMemcpy2DAsync(h->A0, sizeof(double) * ld, A, sizeof(double) * lda, sizeof(double) * n, n,
+                         on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->st));
+    dim3 blk(32, 8), grid(cdiv(n, 32), cdiv(n, 8));
+    sym_from_lower_kernel<<<grid, blk, 0, h->st>>>(h->A0, ld, n);
+    LAUNCHED();
+    CU(cudaMemcpyAsync(h->F.A, h->A0, sizeof(double) * (size_t)n * ld, cudaMemcpyDeviceToDevice, h->st));
+    RET(ldlt_factor(h->F));
+    int cnt[4];
+    double ds[2];
+    CU(cudaMemcpyAsync(cnt, h->F.counts, sizeof(int) * 4, cudaMemcpyDeviceToHost, h->st));
+    CU(cudaMemcpyAsync(ds, h->F.dstat, sizeof(double) * 2, cudaMemcpyDeviceToHost, h->st));
+    CU(cudaStreamSynchronize(h->st));
+    if (inertia) { inertia[0] = cnt[2]; inertia[1] = cnt[0]; inertia[2] = cnt[1]; }
+    if (rcond_est) *rcond_est = (cnt[1] > 0 || !(ds[1] > 0.0)) ? 0.0 : ds[0] / ds[1];
+    h->factored = true;
+    return 0;
+}
+int b200ipm_ldlt_solve(b200ipm_ldlt_handle h, double* B, int nrhs, int nrefine, int on_device) {
+    if (!h || !B) return fail_msg("null argument");
+    if (!h->factored) return fail_msg("ldlt_solve: factor first");
+    CU(cudaSetDevice(h->device));
+    const int n = h->F.n, ld = h->F.ld;
+    const cudaMemcpyKind kin = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    const cudaMemcpyKind kout = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    for (int r = 0; r < nrhs; r++) {
+        CU(cudaMemcpyAsync(h->b, B + (size_t)r * n, sizeof(double) * n, kin, h->st));
+        RET(ldlt_solve(h->F, h->b, h->x));
+        for (int it = 0; it < nrefine; it++) {
+            RET(gemv_n(h->st, h->A0, ld, n, n, h->x, h->b, 1.0, -1.0, h->r));   // r = b - A x
+            RET(ldlt_solve(h->F, h->r, h->c));
+            axpby_kernel<<<cdiv(n, 256), 256, 0, h->st>>>(n, 1.0, h->x, 1.0, h->c, h->x);
+            LAUNCHED();
+        }
+        CU(cudaMemcpyAsync(B + (size_t)r * n, h->x, sizeof(double) * n, kout, h->st));
+    }
+    CU(cudaStreamSynchronize(h->st));
+    return 0;
+}
+int b200ipm_ldlt_tile_factor(b200ipm_ldlt_handle h, double* tile_dev, int ld, int nb, double* linv_dev, double* dblk_dev,
+                             int* perm_dev, int counts[3]) {
+    if (!h || !tile_dev || !linv_dev || !dblk_dev || nb <= 0 || nb > NB) return fail_msg("tile_factor: bad arguments");
+    CU(cudaSetDevice(h->device));
+    ldlt_reset_kernel<<<1, 1, 0, h->st>>>(h->F.counts, h->F.dstat, h->F.ticket);
+    LAUNCHED();
+    // dblk_dev layout: [dinv_a (NB) | dinv_b (NB) | d_a (NB) | d_b (NB)] followed by NB ints of `kind`
+    int* kind = reinterpret_cast<int*>(dblk_dev + 4 * NB);
+    ldlt_tile_kernel<<<1, 256, TILE_SMEM, h->st>>>(tile_dev, ld, nb, linv_dev, dblk_dev, dblk_dev + NB, dblk_dev + 2 * NB,
+                                                   dblk_dev + 3 * NB, kind, perm_dev, h->F.counts, h->F.dstat);
+    LAUNCHED();
+    if (counts) {
+        int cnt[4];
+        CU(cudaMemcpyAsync(cnt, h->F.counts, sizeof(int) * 4, cudaMemcpyDeviceToHost, h->st));
+        CU(cudaStreamSynchronize(h->st));
+        counts[0] = cnt[2]; counts[1] = cnt[0]; counts[2] = cnt[1];
+    }
+    return 0;
+}
+int b200ipm_ldlt_panel(b200ipm_ldlt_handle h, double* panel_dev, int ld, int rows, const double* linv_dev,
+                       const double* dblk_dev, const int* perm_dev, double* w_dev) {
+    (void)perm_dev;
+    if (!h || !panel_dev || !w_dev) return fail_msg("panel: bad arguments");
+    if (rows <= 0) return 0;
+    CU(cudaSetDevice(h->device));
+    GemmArgs g{};
+    g.C = w_dev; g.ldc = NB; g.n = rows; g.m = NB; g.mode = GEMM_FULL; g.nterms = 1;
+    g.t[0] = GemmTerm{panel_dev, linv_dev, nullptr, ld, NB, NB, 1.0};
+    RET(gemm_nt(h->st, g));
+    const int* kind = reinterpret_cast<const int*>(dblk_dev + 4 * NB);
+    ldlt_scale_kernel<<<cdiv(rows * NB, 256), 256, 0, h->st>>>(w_dev, rows, panel_dev, ld, dblk_dev, dblk_dev + NB, kind);
+    LAUNCHED();
+    return 0;
+}
+int b200ipm_gemm_nt_update(b200ipm_ldlt_handle h, double* C_dev, int ldc, int rows, int cols, const double* A_dev, int lda,
+                           const double* B_dev, int ldb, int k, int lower_only) {
+    if (!h || !C_dev || !A_dev || !B_dev) return fail_msg("gemm_nt_update: bad arguments");
+    if (rows <= 0 || cols <= 0) return 0;
+    CU(cudaSetDevice(h->device));
+    GemmArgs u{};
+    u.C = C_dev; u.ldc = ldc; u.Cin = C_dev; u.ldcin = ldc; u.n = rows; u.m = cols; u.beta = 1.0;
+    u.mode = lower_only ? GEMM_LOWER_ONLY : GEMM_FULL; u.nterms = 1;
+    u.t[0] = GemmTerm{A_dev, B_dev, nullptr, lda, ldb, k, -1.0};
+    RET(gemm_nt(h->st, u));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ test hooks
+int b200ipm_test_syrk(int n, const double* Cin, double beta, const double* dadd, double shift, int nterms,
+                      const double* const* A, const double* const* w, const int* K, const double* alpha, double* C,
+                      int force_simple, float* ms) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail_msg("no CUDA device available");
+    if (nterms < 0 || nterms > 3) return fail_msg("test_syrk: 0..3 terms");
+    RET(ldlt_init_attrs());
+    cudaStream_t st = nullptr;
+    double *dC = nullptr, *dCin = nullptr, *dd = nullptr, *dA[3] = {nullptr, nullptr, nullptr}, *dw[3] = {nullptr, nullptr, nullptr};
+    const int ld = (int)rup(n, 16);
+    RET(dalloc(&dC, (size_t)n * ld));
+    GemmArgs a{};
+    a.C = dC; a.ldc = ld; a.n = n; a.m = n; a.beta = beta; a.shift = shift; a.mode = GEMM_UPPER_MIRROR; a.nterms = nterms;
+    if (Cin) {
+        RET(dalloc(&dCin, (size_t)n * ld));
+        CU(cudaMemcpy2D(dCin, sizeof(double) * ld, Cin, sizeof(double) * n, sizeof(double) * n, n, cudaMemcpyHostToDevice));
+        a.Cin = dCin; a.ldcin = ld;
+    }
+    if (dadd) { RET(dalloc(&dd, n)); CU(cudaMemcpy(dd, dadd, sizeof(double) * n, cudaMemcpyHostToDevice)); a.dadd = dd; }
+    for (int t = 0; t < nterms; t++) {
+        const int ldk = (int)rup(K[t], 16);
+        RET(dalloc(&dA[t], (size_t)n * ldk));
+        CU(cudaMemcpy2D(dA[t], sizeof(double) * ldk, A[t], sizeof(double) * K[t], sizeof(double) * K[t], n, cudaMemcpyHostToDevice));
+        if (w && w[t]) { RET(dalloc(&dw[t], K[t])); CU(cudaMemcpy(dw[t], w[t], sizeof(double) * K[t], cudaMemcpyHostToDevice)); }
+        a.t[t] = GemmTerm{dA[t], dA[t], dw[t], ldk, ldk, K[t], alpha[t]};
+    }
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    RET(gemm_nt(st, a, force_simple != 0));   // warm-up
+    CU(cudaEventRecord(e0, st));
+    RET(gemm_nt(st, a, force_simple != 0));
+    CU(cudaEventRecord(e1, st));
+    CU(cudaEventSynchronize(e1));
+    if (ms) CU(cudaEventElapsedTime(ms, e0, e1));
+    CU(cudaMemcpy2D(C, sizeof(double) * n, dC, sizeof(double) * ld, sizeof(double) * n, n, cudaMemcpyDeviceToHost));
+    cudaFree(dC); cudaFree(dCin); cudaFree(dd);
+    for (int t = 0; t < 3; t++) { cudaFree(dA[t]); cudaFree(dw[t]); }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return 0;
+}
+int b200ipm_test_gemv(int rows, int cols, const double* A, const double* v, double* y, int transpose_) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail_msg("no CUDA device available");
+    double *dA = nullptr, *dv = nullptr, *dy = nullptr, *scr = nullptr;
+    const int nin = transpose_ ? rows : cols, nout = transpose_ ? cols : rows;
+    RET(dalloc(&dA, (size_t)rows * cols)); RET(dalloc(&dv, nin)); RET(dalloc(&dy, nout));
+    RET(dalloc(&scr, gemv_t_scratch_doubles(rows, cols)));
+    CU(cudaMemcpy(dA, A, sizeof(double) * rows * cols, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dv, v, sizeof(double) * nin, cudaMemcpyHostToDevice));
+    if (transpose_) RET(gemv_t(nullptr, dA, cols, rows, cols, dv, nullptr, 0.0, 1.0, dy, scr));
+    else RET(gemv_n(nullptr, dA, cols, rows, cols, dv, nullptr, 0.0, 1.0, dy));
+    CU(cudaMemcpy(y, dy, sizeof(double) * nout, cudaMemcpyDeviceToHost));
+    cudaFree(dA); cudaFree(dv); cudaFree(dy); cudaFree(scr);
+    return 0;
+}
+
+}  // extern "C"

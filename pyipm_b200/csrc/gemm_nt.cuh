@@ -1,0 +1,244 @@
+// gemm_nt.cuh -- fp64 "A * diag(w) * B^T" contraction on the tensor cores (DMMA.8x8x4 on sm_100a).
+//
+//   C[i, j] = beta * Cin[i, j] + [i == j] * (dadd[i] + shift) + sum_t alpha_t * sum_k A_t[i, k] * w_t[k] * B_t[j, k]
+//
+// Both operands are row-major with the contraction index contiguous (K-major), which is exactly the layout of
+// the reference's transposed Jacobians (dci is D x N, pyipm.py:138): the Lagrangian-Hessian terms
+// Ut diag(lda_e) Ut', Vt diag(lda_i) Vt', the condensation dci diag(sigma) dci' and the LDL^T trailing update
+// W L' all map onto this one kernel.
+//
+// Modes
+//   GEMM_UPPER_MIRROR: C is n x n symmetric.  Only tiles on/above the diagonal are computed, only elements
+//                      i <= j are authoritative, each is mirrored to (j, i) => bitwise symmetric output, and
+//                      Cin is read from its UPPER triangle only (the reference symmetrises triu(d2L),
+//                      pyipm.py:785,827,843).
+//   GEMM_LOWER_ONLY:   tiles on/below the diagonal, no mirror (LDL^T trailing update).
+//   GEMM_FULL:         all tiles of an n x m result.
+//
+// Tiling: 128 x 128 x 16 CTA tile, 8 warps (2 x 4), 64 x 32 warp tile = 8 x 4 DMMA fragments, 4-stage cp.async
+// pipeline (16-byte LDGSTS, zero-filled edges), smem row stride 20 doubles => every fragment LDS.64 is the
+// minimum two wavefronts.  Algorithmic FLOPs per launch: 2 * (#computed tile elements) * sum_t K_t.
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+enum { GEMM_UPPER_MIRROR = 0, GEMM_LOWER_ONLY = 1, GEMM_FULL = 2 };
+
+struct GemmTerm {
+    const double* A;
+    const double* B;
+    const double* w;   // may be null (all ones)
+    int lda, ldb, K;
+    double alpha;
+};
+struct GemmArgs {
+    double* C;
+    const double* Cin;    // may be null
+    const double* dadd;   // may be null
+    int ldc, ldcin;
+    int n, m;             // rows, cols of C
+    double beta, shift;
+    int mode, nterms;
+    GemmTerm t[3];
+};
+
+constexpr int G_BM = 128, G_BN = 128, G_BK = 16, G_LDS = 20, G_STAGES = 4;
+constexpr int G_SMEM = G_STAGES * (G_BM + G_BN) * G_LDS * 8;
+
+__device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc, int bytes) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gsrc), "r"(bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// one operand tile: 128 rows x 16 doubles, 1024 16-byte chunks, 4 per thread; rows/k beyond the edge zero-fill
+__device__ __forceinline__ void g_load_tile(double* sdst, const double* __restrict__ G, int ld, int row0, int nrows,
+                                            int k0, int K, int tid) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int c = tid + 256 * i;
+        const int row = c >> 3, kc = (c & 7) * 2;
+        const int gr = row0 + row, gk = k0 + kc;
+        int bytes = 0;
+        const double* src = G;
+        if (gr < nrows && gk < K) {
+            bytes = min(16, (K - gk) * 8);
+            src = G + (size_t)gr * ld + gk;
+        }
+        cp_async16(sdst + row * G_LDS + kc, src, bytes);
+    }
+}
+
+__global__ void __launch_bounds__(256, 1) gemm_nt_dmma_kernel(const GemmArgs a) {
+    extern __shared__ __align__(16) double g_smem[];
+    const int ti = blockIdx.y, tj = blockIdx.x;
+    if (a.mode == GEMM_UPPER_MIRROR && ti > tj) return;
+    if (a.mode == GEMM_LOWER_ONLY && ti < tj) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp >> 2, wn = warp & 3;
+    const int g = lane >> 2, tg = lane & 3;
+    const int row0 = ti * G_BM, col0 = tj * G_BN;
+    double* As = g_smem;
+    double* Bs = g_smem + G_STAGES * G_BM * G_LDS;
+
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    for (int t = 0; t < a.nterms; t++) {
+        const GemmTerm T = a.t[t];
+        const int nk = (T.K + G_BK - 1) / G_BK;
+        // prologue
+#pragma unroll
+        for (int s = 0; s < G_STAGES - 1; s++) {
+            if (s < nk) {
+                g_load_tile(As + s * G_BM * G_LDS, T.A, T.lda, row0, a.n, s * G_BK, T.K, tid);
+                g_load_tile(Bs + s * G_BN * G_LDS, T.B, T.ldb, col0, a.m, s * G_BK, T.K, tid);
+            }
+            cp_async_commit();
+        }
+        double wv[4];
+#pragma unroll
+        for (int kk = 0; kk < 4; kk++) {
+            const int k = kk * 4 + tg;
+            wv[kk] = (k < T.K) ? T.alpha * (T.w ? __ldg(T.w + k) : 1.0) : 0.0;
+        }
+        for (int kt = 0; kt < nk; kt++) {
+            cp_async_wait<G_STAGES - 2>();
+            __syncthreads();
+            {   // refill the stage consumed at iteration kt-1
+                const int kn = kt + G_STAGES - 1;
+                if (kn < nk) {
+                    const int s = kn % G_STAGES;
+                    g_load_tile(As + s * G_BM * G_LDS, T.A, T.lda, row0, a.n, kn * G_BK, T.K, tid);
+                    g_load_tile(Bs + s * G_BN * G_LDS, T.B, T.ldb, col0, a.m, kn * G_BK, T.K, tid);
+                }
+                cp_async_commit();
+            }
+            // prefetch next tile's weights
+            double wn_[4];
+#pragma unroll
+            for (int kk = 0; kk < 4; kk++) {
+                const int k = (kt + 1) * G_BK + kk * 4 + tg;
+                wn_[kk] = (k < T.K) ? T.alpha * (T.w ? __ldg(T.w + k) : 1.0) : 0.0;
+            }
+            const int s = kt % G_STAGES;
+            const double* as = As + s * G_BM * G_LDS + (wm * 64 + g) * G_LDS + tg;
+            const double* bs = Bs + s * G_BN * G_LDS + (wn * 32 + g) * G_LDS + tg;
+#pragma unroll
+            for (int kk = 0; kk < 4; kk++) {
+                double af[8], bf[4];
+#pragma unroll
+                for (int mt = 0; mt < 8; mt++) af[mt] = as[mt * 8 * G_LDS + kk * 4];
+#pragma unroll
+                for (int nt = 0; nt < 4; nt++) bf[nt] = bs[nt * 8 * G_LDS + kk * 4] * wv[kk];
+#pragma unroll
+                for (int mt = 0; mt < 8; mt++)
+#pragma unroll
+                    for (int nt = 0; nt < 4; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
+            }
+#pragma unroll
+            for (int kk = 0; kk < 4; kk++) wv[kk] = wn_[kk];
+        }
+        cp_async_wait<0>();
+        __syncthreads();
+    }
+
+    // epilogue
+    const bool diag_tile = (ti == tj);
+#pragma unroll
+    for (int mt = 0; mt < 8; mt++) {
+        const int i = row0 + wm * 64 + mt * 8 + g;
+        if (i >= a.n) continue;
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++) {
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const int j = col0 + wn * 32 + nt * 8 + tg * 2 + e;
+                if (j >= a.m) continue;
+                if (a.mode == GEMM_UPPER_MIRROR && diag_tile && i > j) continue;
+                double v = acc[mt][nt][e];
+                if (a.Cin) v += a.beta * a.Cin[(size_t)i * a.ldcin + j];
+                if (i == j) v += a.shift + (a.dadd ? a.dadd[i] : 0.0);
+                a.C[(size_t)i * a.ldc + j] = v;
+                if (a.mode == GEMM_UPPER_MIRROR && i != j) a.C[(size_t)j * a.ldc + i] = v;
+            }
+        }
+    }
+}
+
+// scalar reference kernel: any size / alignment (tiny problems, odd leading dimensions, test cross-check)
+__global__ void gemm_nt_simple_kernel(const GemmArgs a) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= a.n || j >= a.m) return;
+    if (a.mode == GEMM_UPPER_MIRROR && i > j) return;
+    if (a.mode == GEMM_LOWER_ONLY && i < j) return;
+    double v = 0.0;
+    for (int t = 0; t < a.nterms; t++) {
+        const GemmTerm T = a.t[t];
+        const double* pa = T.A + (size_t)i * T.lda;
+        const double* pb = T.B + (size_t)j * T.ldb;
+        double s = 0.0;
+        if (T.w)
+            for (int k = 0; k < T.K; k++) s += pa[k] * (pb[k] * T.w[k]);
+        else
+            for (int k = 0; k < T.K; k++) s += pa[k] * pb[k];
+        v += T.alpha * s;
+    }
+    if (a.Cin) v += a.beta * a.Cin[(size_t)i * a.ldcin + j];
+    if (i == j) v += a.shift + (a.dadd ? a.dadd[i] : 0.0);
+    a.C[(size_t)i * a.ldc + j] = v;
+    if (a.mode == GEMM_UPPER_MIRROR && i != j) a.C[(size_t)j * a.ldc + i] = v;
+}
+
+inline bool gemm_nt_can_dmma(const GemmArgs& a) {
+    for (int t = 0; t < a.nterms; t++) {
+        const GemmTerm& T = a.t[t];
+        if ((T.lda & 1) || (T.ldb & 1)) return false;
+        if ((reinterpret_cast<uintptr_t>(T.A) & 15) || (reinterpret_cast<uintptr_t>(T.B) & 15)) return false;
+    }
+    return true;
+}
+
+inline int gemm_nt(cudaStream_t st, const GemmArgs& a, bool force_simple = false) {
+    if (a.n <= 0 || a.m <= 0) return 0;
+    static bool attr_set = false;
+    const bool big = (a.n >= 48 && a.m >= 48);
+    if (!force_simple && big && gemm_nt_can_dmma(a)) {
+        if (!attr_set) {
+            CU(cudaFuncSetAttribute(gemm_nt_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM));
+            attr_set = true;
+        }
+        dim3 grid(cdiv(a.m, G_BN), cdiv(a.n, G_BM));
+        gemm_nt_dmma_kernel<<<grid, 256, G_SMEM, st>>>(a);
+        LAUNCHED();
+    } else {
+        dim3 blk(32, 8), grid(cdiv(a.m, 32), cdiv(a.n, 8));
+        gemm_nt_simple_kernel<<<grid, blk, 0, st>>>(a);
+        LAUNCHED();
+    }
+    return 0;
+}
+
+// computed tile elements x 2 x sum K  (what one launch is credited with in the roofline)
+inline double gemm_nt_flops(const GemmArgs& a) {
+    double ksum = 0;
+    for (int t = 0; t < a.nterms; t++) ksum += a.t[t].K;
+    double elems = (a.mode == GEMM_FULL) ? (double)a.n * a.m : 0.5 * (double)a.n * ((double)a.n + 1.0);
+    return 2.0 * elems * ksum;
+}
+
+}  // namespace b200

@@ -1,0 +1,512 @@
+// ldlt.cuh -- dense symmetric-INDEFINITE factorisation  A = Lhat * D * Lhat^T  with inertia, on the device.
+//
+// Replaces the reference's  eigvalsh(K, I)  inertia test (pyipm.py:906-909, 1378-1403; >= 90 % of its Newton
+// step) and its general-LU solve (pyipm.py:18-20, 911-914, 1720).
+//
+// Algorithm: right-looking blocked LDL^T, block size NB = 64, Bunch-Kaufman (1x1 / 2x2) pivoting restricted to
+// the diagonal tile ("tile pivoting": no pivot search touches HBM outside the 64 x 64 tile, so the only
+// serial part of a panel step is one CTA working out of shared memory).  Per panel k (rows/cols k0..k1):
+//   1. ldlt_tile_kernel   P T P^T = L D L^T  of the diagonal tile in smem, fused Gauss-Jordan accumulation of
+//                         X = L^-1; emits LinvP = X * P (so nobody downstream needs the permutation),
+//                         D^-1 blocks, inertia counts and |D| extremes.
+//   2. gemm_nt (DMMA)     W = B * LinvP^T            (W = Lpanel * D, rows below the tile)
+//   3. ldlt_scale_kernel  Lpanel = W * D^-1          (overwrites B in place)
+//   4. gemm_nt (DMMA)     A22 -= W * Lpanel^T        (lower tiles only)  -- Kc^3/3 FLOPs total, the tensor work
+// Sylvester's law of inertia makes #negative eigenvalues = #negative 1x1 pivots + #2x2 blocks with det < 0
+// (+ 2 for negative-definite 2x2 blocks), which is what pyipm.py:1381,1399 tests.
+//
+// Solves are ONE launch per direction: CTA i owns block-row i, spins on per-block epoch flags published by the
+// CTAs of earlier block rows (tickets guarantee forward progress), and applies LinvP_i as a 64 x 64 GEMV.
+#pragma once
+#include "common.cuh"
+#include "gemm_nt.cuh"
+#include "vec.cuh"
+
+namespace b200 {
+
+constexpr int NB = 64;
+constexpr int NBP = NB + 1;   // padded smem row
+constexpr int TILE_SMEM = 2 * NB * NBP * 8;
+
+struct LdltWs {
+    int n = 0, ld = 0, nblk = 0;
+    double* A = nullptr;       // n x ld, factored in place (strictly-lower part holds Lhat panels)
+    double* Wp = nullptr;      // n x NB   panel scratch (L * D)
+    double* LinvP = nullptr;   // nblk x NB x NB
+    double* dinfo = nullptr;   // 4 x n: [dinv_a | dinv_b | d_a | d_b]
+    int* kind = nullptr;       // n: 0 = 1x1, 1 = first of 2x2, 2 = second of 2x2
+    int* counts = nullptr;     // [neg, zero, pos]
+    double* dstat = nullptr;   // [min |eig(D)|, max |eig(D)|]
+    unsigned* flags = nullptr; // 2 x nblk epoch flags (forward, backward)
+    unsigned* ticket = nullptr;
+    double *yv = nullptr, *zv = nullptr, *xv = nullptr;
+    unsigned epoch = 0;
+    cudaStream_t st = nullptr;
+};
+
+inline int ldlt_alloc(LdltWs& w, int n, cudaStream_t st) {
+    w.n = n;
+    w.ld = (int)rup(n, 16);
+    w.nblk = cdiv(n, NB);
+    w.st = st;
+    w.epoch = 0;
+    const size_t npad = (size_t)w.nblk * NB;
+    CU(cudaMalloc(&w.A, sizeof(double) * (size_t)npad * w.ld));
+    CU(cudaMalloc(&w.Wp, sizeof(double) * npad * NB));
+    CU(cudaMalloc(&w.LinvP, sizeof(double) * (size_t)w.nblk * NB * NB));
+    CU(cudaMalloc(&w.dinfo, sizeof(double) * 4 * npad));
+    CU(cudaMalloc(&w.kind, sizeof(int) * npad));
+    CU(cudaMalloc(&w.counts, sizeof(int) * 4));
+    CU(cudaMalloc(&w.dstat, sizeof(double) * 2));
+    CU(cudaMalloc(&w.flags, sizeof(unsigned) * 2 * w.nblk));
+    CU(cudaMalloc(&w.ticket, sizeof(unsigned) * 2));
+    CU(cudaMalloc(&w.yv, sizeof(double) * npad));
+    CU(cudaMalloc(&w.zv, sizeof(double) * npad));
+    CU(cudaMalloc(&w.xv, sizeof(double) * npad));
+    CU(cudaMemsetAsync(w.flags, 0, sizeof(unsigned) * 2 * w.nblk, st));
+    CU(cudaMemsetAsync(w.A, 0, sizeof(double) * (size_t)npad * w.ld, st));
+    return 0;
+}
+inline void ldlt_free(LdltWs& w) {
+    cudaFree(w.A); cudaFree(w.Wp); cudaFree(w.LinvP); cudaFree(w.dinfo); cudaFree(w.kind); cudaFree(w.counts);
+    cudaFree(w.dstat); cudaFree(w.flags); cudaFree(w.ticket); cudaFree(w.yv); cudaFree(w.zv); cudaFree(w.xv);
+    w = LdltWs();
+}
+
+// ------------------------------------------------------------------------------------------- tile kernel
+// One CTA (256 threads).  T (symmetric, both triangles kept bitwise equal) and X (running L^-1) live in smem.
+__global__ void __launch_bounds__(256) ldlt_tile_kernel(double* __restrict__ A, int ld, int nb, double* __restrict__ LinvP,
+                                                        double* __restrict__ dinv_a, double* __restrict__ dinv_b,
+                                                        double* __restrict__ d_a, double* __restrict__ d_b,
+                                                        int* __restrict__ kind, int* __restrict__ perm_out,
+                                                        int* __restrict__ counts, double* __restrict__ dstat) {
+    extern __shared__ __align__(16) double tsm[];
+    double(*T)[NBP] = reinterpret_cast<double(*)[NBP]>(tsm);
+    double(*X)[NBP] = reinterpret_cast<double(*)[NBP]>(tsm + NB * NBP);
+    __shared__ double colu[NB], colv[NB], sda[NB], sdb[NB];
+    __shared__ int sperm[NB], skind[NB];
+    __shared__ int s_kp, s_kstep;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double BK_ALPHA = 0.6403882032022076;   // (1 + sqrt(17)) / 8
+
+    // load the tile from its LOWER triangle, mirror, identity-pad to NB
+    for (int idx = tid; idx < NB * NB; idx += 256) {
+        const int i = idx / NB, j = idx % NB;
+        double v;
+        if (i < nb && j < nb) {
+            v = (i >= j) ? A[(size_t)i * ld + j] : A[(size_t)j * ld + i];
+        } else {
+            v = (i == j) ? 1.0 : 0.0;
+        }
+        T[i][j] = v;
+        X[i][j] = (i == j) ? 1.0 : 0.0;
+    }
+    if (tid < NB) {
+        sperm[tid] = tid;
+        skind[tid] = 0;
+        sda[tid] = 1.0;
+        sdb[tid] = 0.0;
+    }
+    __syncthreads();
+
+    int j = 0;
+    while (j < nb) {
+        // ---- pivot selection (warp 0), LAPACK dsytf2 logic restricted to the tile
+        if (warp == 0) {
+            const double absakk = fabs(T[j][j]);
+            double cm = -1.0;
+            int r = j;
+            for (int i = j + 1 + lane; i < nb; i += 32) {
+                const double v = fabs(T[i][j]);
+                if (v > cm) { cm = v; r = i; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ocm = __shfl_xor_sync(0xffffffffu, cm, o);
+                const int orr = __shfl_xor_sync(0xffffffffu, r, o);
+                if (ocm > cm || (ocm == cm && orr < r)) { cm = ocm; r = orr; }
+            }
+            const double colmax = (cm < 0.0) ? 0.0 : cm;
+            int kp = j, kstep = 1;
+            if (!(fmax(absakk, colmax) == 0.0) && absakk < BK_ALPHA * colmax) {
+                double rm = 0.0;
+                for (int i = j + lane; i < nb; i += 32)
+                    if (i != r) rm = fmax(rm, fabs(T[i][r]));
+                rm = warp_max(rm);
+                if (absakk * rm >= BK_ALPHA * colmax * colmax) {
+                    kp = j;
+                } else if (fabs(T[r][r]) >= BK_ALPHA * rm) {
+                    kp = r;
+                } else {
+                    kp = r;
+                    kstep = 2;
+                }
+            }
+            if (lane == 0) { s_kp = kp; s_kstep = kstep; }
+        }
+        __syncthreads();
+        const int kp = s_kp, kstep = s_kstep;
+        const int kk = j + kstep - 1;
+        // ---- symmetric interchange kk <-> kp on T and X (rows, then columns)
+        if (kp != kk) {
+            if (tid < NB) {
+                double t0 = T[kk][tid]; T[kk][tid] = T[kp][tid]; T[kp][tid] = t0;
+                double x0 = X[kk][tid]; X[kk][tid] = X[kp][tid]; X[kp][tid] = x0;
+            }
+            __syncthreads();
+            if (tid < NB) {
+                double t0 = T[tid][kk]; T[tid][kk] = T[tid][kp]; T[tid][kp] = t0;
+                double x0 = X[tid][kk]; X[tid][kk] = X[tid][kp]; X[tid][kp] = x0;
+            }
+            if (tid == 0) { int p = sperm[kk]; sperm[kk] = sperm[kp]; sperm[kp] = p; }
+            __syncthreads();
+        }
+        // ---- elimination
+        if (kstep == 1) {
+            const double d = T[j][j];
+            if (tid < NB) colu[tid] = (tid > j) ? T[tid][j] : 0.0;
+            if (tid == 0) { sda[j] = d; sdb[j] = 0.0; skind[j] = 0; }
+            __syncthreads();
+            if (d != 0.0) {
+                const double dinv = 1.0 / d;
+                for (int i = j + 1 + warp; i < nb; i += 8) {
+                    const double li = colu[i] * dinv;
+                    // trailing update, lower part + mirror
+                    for (int m = j + 1 + lane; m <= i; m += 32) {
+                        const double v = T[i][m] - li * colu[m];
+                        T[i][m] = v;
+                        T[m][i] = v;
+                    }
+                    // Gauss-Jordan: X[i][0..j] -= l_i * X[j][0..j]
+                    for (int c = lane; c <= j; c += 32) X[i][c] -= li * X[j][c];
+                    if (lane == 0) T[i][j] = li;
+                }
+            }
+        } else {
+            const double a11 = T[j][j], a21 = T[j + 1][j], a22 = T[j + 1][j + 1];
+            if (tid < NB) {
+                colu[tid] = (tid > j + 1) ? T[tid][j] : 0.0;
+                colv[tid] = (tid > j + 1) ? T[tid][j + 1] : 0.0;
+            }
+            if (tid == 0) {
+                sda[j] = a11; sdb[j] = a21; sda[j + 1] = a22; sdb[j + 1] = 0.0;
+                skind[j] = 1; skind[j + 1] = 2;
+            }
+            __syncthreads();
+            // LAPACK's scaled 2x2 inverse (dsytf2): robust against overflow of the determinant
+            const double d11 = a22 / a21, d22 = a11 / a21;
+            const double tt = 1.0 / (d11 * d22 - 1.0);
+            const double d21i = tt / a21;
+            for (int i = j + 2 + warp; i < nb; i += 8) {
+                const double u = colu[i], v = colv[i];
+                const double l1 = d21i * (d11 * u - v);
+                const double l2 = d21i * (d22 * v - u);
+                for (int m = j + 2 + lane; m <= i; m += 32) {
+                    const double val = T[i][m] - (l1 * colu[m] + l2 * colv[m]);
+                    T[i][m] = val;
+                    T[m][i] = val;
+                }
+                for (int c = lane; c <= j + 1; c += 32) X[i][c] -= l1 * X[j][c] + l2 * X[j + 1][c];
+                if (lane == 0) { T[i][j] = l1; T[i][j + 1] = l2; }
+            }
+            if (tid == 0) T[j + 1][j] = 0.0;
+        }
+        __syncthreads();
+        j += kstep;
+    }
+
+    // ---- outputs
+    // LinvP[r][perm[m]] = X[r][m]   (column scatter folds the permutation into the inverse)
+    for (int idx = tid; idx < NB * NB; idx += 256) {
+        const int r = idx / NB, m = idx % NB;
+        LinvP[r * NB + sperm[m]] = (m <= r) ? X[r][m] : 0.0;
+    }
+    // L back into the strictly-lower part of the tile, D on the diagonal (diagnostics / tests)
+    for (int idx = tid; idx < nb * nb; idx += 256) {
+        const int i = idx / nb, jj = idx % nb;
+        if (i > jj) A[(size_t)i * ld + jj] = T[i][jj];
+        else if (i == jj) A[(size_t)i * ld + jj] = sda[i];
+    }
+    if (tid < NB) {
+        const int p = tid;
+        double ia = 0.0, ib = 0.0;
+        if (p < nb) {
+            if (skind[p] == 0) {
+                ia = (sda[p] != 0.0) ? 1.0 / sda[p] : 0.0;
+            } else {
+                const int p0 = (skind[p] == 1) ? p : p - 1;
+                const double a11 = sda[p0], a21 = sdb[p0], a22 = sda[p0 + 1];
+                const double d11 = a22 / a21, d22 = a11 / a21;
+                const double tt = 1.0 / (d11 * d22 - 1.0);
+                const double d21i = tt / a21;
+                // D^-1 = d21i * [[d11, -1], [-1, d22]]
+                ia = (skind[p] == 1) ? d21i * d11 : d21i * d22;
+                ib = (skind[p] == 1) ? -d21i : 0.0;
+            }
+        } else {
+            ia = 1.0;
+        }
+        dinv_a[p] = ia;
+        dinv_b[p] = ib;
+        d_a[p] = sda[p];
+        d_b[p] = sdb[p];
+        kind[p] = (p < nb) ? skind[p] : 0;
+        if (perm_out) perm_out[p] = sperm[p];
+    }
+    if (tid == 0) {
+        int neg = 0, zero = 0, pos = 0;
+        double mn = dstat[0], mx = dstat[1];
+        for (int p = 0; p < nb; p++) {
+            if (skind[p] == 0) {
+                const double d = sda[p];
+                if (d > 0.0) pos++; else if (d < 0.0) neg++; else zero++;
+                mn = fmin(mn, fabs(d)); mx = fmax(mx, fabs(d));
+            } else if (skind[p] == 1) {
+                const double a = sda[p], b = sdb[p], c = sda[p + 1];
+                const double hm = 0.5 * (a + c), hd = 0.5 * (a - c);
+                const double rad = sqrt(hd * hd + b * b);
+                const double e1 = hm + rad, e2 = hm - rad;
+                if (e1 > 0.0) pos++; else if (e1 < 0.0) neg++; else zero++;
+                if (e2 > 0.0) pos++; else if (e2 < 0.0) neg++; else zero++;
+                mn = fmin(mn, fmin(fabs(e1), fabs(e2))); mx = fmax(mx, fmax(fabs(e1), fabs(e2)));
+            }
+        }
+        counts[0] += neg; counts[1] += zero; counts[2] += pos;
+        dstat[0] = mn; dstat[1] = mx;
+    }
+}
+
+// Lpanel = W * D^-1 (block diagonal), rows x NB; W has leading dimension NB, L is written into A's panel
+__global__ void ldlt_scale_kernel(const double* __restrict__ W, int rows, double* __restrict__ L, int ld,
+                                  const double* __restrict__ dinv_a, const double* __restrict__ dinv_b,
+                                  const int* __restrict__ kind) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * NB) return;
+    const int r = idx / NB, j = idx % NB;
+    const double* w = W + (size_t)r * NB;
+    const int k = kind[j];
+    double v = w[j] * dinv_a[j];
+    if (k == 1) v += w[j + 1] * dinv_b[j];
+    else if (k == 2) v += w[j - 1] * dinv_b[j - 1];
+    L[(size_t)r * ld + j] = v;
+}
+
+__global__ void ldlt_reset_kernel(int* counts, double* dstat, unsigned* ticket) {
+    counts[0] = counts[1] = counts[2] = counts[3] = 0;
+    dstat[0] = INFINITY;
+    dstat[1] = 0.0;
+    ticket[0] = ticket[1] = 0;
+}
+
+inline int ldlt_init_attrs() {
+    CU(cudaFuncSetAttribute(ldlt_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM));
+    CU(cudaFuncSetAttribute(gemm_nt_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM));
+    return 0;
+}
+
+// Factor w.A in place.  Results stay on the device (counts/dstat); the caller reads them back when it needs the
+// inertia decision.
+inline int ldlt_factor(LdltWs& w) {
+    cudaStream_t st = w.st;
+    const int n = w.n, ld = w.ld;
+    const size_t npad = (size_t)w.nblk * NB;
+    double *ia = w.dinfo, *ib = w.dinfo + npad, *da = w.dinfo + 2 * npad, *db = w.dinfo + 3 * npad;
+    ldlt_reset_kernel<<<1, 1, 0, st>>>(w.counts, w.dstat, w.ticket);
+    LAUNCHED();
+    for (int k = 0; k < w.nblk; k++) {
+        const int k0 = k * NB, nb = min(NB, n - k0), k1 = k0 + nb;
+        double* Akk = w.A + (size_t)k0 * ld + k0;
+        double* Lk = w.LinvP + (size_t)k * NB * NB;
+        ldlt_tile_kernel<<<1, 256, TILE_SMEM, st>>>(Akk, ld, nb, Lk, ia + k0, ib + k0, da + k0, db + k0, w.kind + k0,
+                                                    nullptr, w.counts, w.dstat);
+        LAUNCHED();
+        const int rows = n - k1;
+        if (rows <= 0) break;
+        double* B = w.A + (size_t)k1 * ld + k0;
+        // W = B * LinvP^T
+        GemmArgs g{};
+        g.C = w.Wp; g.ldc = NB; g.Cin = nullptr; g.dadd = nullptr; g.n = rows; g.m = NB; g.beta = 0.0; g.shift = 0.0;
+        g.mode = GEMM_FULL; g.nterms = 1;
+        g.t[0] = GemmTerm{B, Lk, nullptr, ld, NB, NB, 1.0};
+        RET(gemm_nt(st, g));
+        ldlt_scale_kernel<<<cdiv(rows * NB, 256), 256, 0, st>>>(w.Wp, rows, B, ld, ia + k0, ib + k0, w.kind + k0);
+        LAUNCHED();
+        // A22 -= W * L^T   (lower tiles only)
+        GemmArgs u{};
+        u.C = w.A + (size_t)k1 * ld + k1; u.ldc = ld; u.Cin = u.C; u.ldcin = ld; u.dadd = nullptr; u.n = rows; u.m = rows;
+        u.beta = 1.0; u.shift = 0.0; u.mode = GEMM_LOWER_ONLY; u.nterms = 1;
+        u.t[0] = GemmTerm{w.Wp, B, nullptr, NB, ld, NB, -1.0};
+        RET(gemm_nt(st, u));
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------- solve kernels
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+
+// forward:  y_i = LinvP_i * (b_i - sum_{j<i} L_ij y_j),  z_i = D_i^-1 y_i
+__global__ void __launch_bounds__(256) ldlt_fwd_kernel(const double* __restrict__ A, int ld, int n, int nblk,
+                                                       const double* __restrict__ LinvP, const double* __restrict__ dinv_a,
+                                                       const double* __restrict__ dinv_b, const int* __restrict__ kind,
+                                                       const double* __restrict__ b, double* yv, double* __restrict__ zv,
+                                                       unsigned* flags, unsigned epoch, unsigned* ticket) {
+    __shared__ double Ls[NB][NB];   // LinvP_i
+    __shared__ double accv[NB], ys[NB];
+    __shared__ int s_i;
+    const int tid = threadIdx.x;
+    if (tid == 0) s_i = (int)atomicAdd(ticket, 1u);
+    __syncthreads();
+    const int i = s_i;
+    const int r0 = i * NB;
+    const int r = tid >> 2, q = tid & 3;
+    const bool rowok = (r0 + r) < n;
+    {   // stage LinvP_i while earlier block rows are still being solved
+        const double* src = LinvP + (size_t)i * NB * NB;
+        for (int idx = tid; idx < NB * NB; idx += 256) Ls[idx / NB][idx % NB] = src[idx];
+    }
+    double part = 0.0;
+    const double* arow = A + (size_t)(r0 + r) * ld + q * 16;
+    for (int j = 0; j < i; j++) {
+        double lv[16];
+        if (rowok) {
+            const double2* p2 = reinterpret_cast<const double2*>(arow + (size_t)j * NB);
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                const double2 t = __ldg(p2 + c);
+                lv[2 * c] = t.x;
+                lv[2 * c + 1] = t.y;
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < 16; c++) lv[c] = 0.0;
+        }
+        if (tid == 0) {
+            while (ld_acquire_u32(flags + j) != epoch) __nanosleep(32);
+        }
+        __syncthreads();
+        const double* yj = yv + (size_t)j * NB + q * 16;
+#pragma unroll
+        for (int c = 0; c < 16; c++) part += lv[c] * __ldcg(yj + c);
+    }
+    part += __shfl_xor_sync(0xffffffffu, part, 1);
+    part += __shfl_xor_sync(0xffffffffu, part, 2);
+    if (q == 0) accv[r] = rowok ? (b[r0 + r] - part) : 0.0;
+    __syncthreads();
+    double yp = 0.0;
+#pragma unroll
+    for (int c = 0; c < 16; c++) yp += Ls[r][q * 16 + c] * accv[q * 16 + c];
+    yp += __shfl_xor_sync(0xffffffffu, yp, 1);
+    yp += __shfl_xor_sync(0xffffffffu, yp, 2);
+    if (q == 0) {
+        ys[r] = yp;
+        if (rowok) yv[r0 + r] = yp;
+    }
+    __syncthreads();
+    if (q == 0 && rowok) {
+        const int gidx = r0 + r;
+        const int k = kind[gidx];
+        double z = dinv_a[gidx] * ys[r];
+        if (k == 1) z += dinv_b[gidx] * ys[r + 1];
+        else if (k == 2) z += dinv_b[gidx - 1] * ys[r - 1];
+        zv[gidx] = z;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) st_release_u32(flags + i, epoch);
+}
+
+// backward:  x_i = LinvP_i^T * (z_i - sum_{j>i} L_ji^T x_j)
+__global__ void __launch_bounds__(256) ldlt_bwd_kernel(const double* __restrict__ A, int ld, int n, int nblk,
+                                                       const double* __restrict__ LinvP, const double* __restrict__ zv,
+                                                       double* xv, unsigned* flags, unsigned epoch, unsigned* ticket) {
+    extern __shared__ __align__(16) double bsm[];
+    double(*P)[NBP] = reinterpret_cast<double(*)[NBP]>(bsm);          // partial sums [row r][col c]
+    double(*Ls)[NBP] = reinterpret_cast<double(*)[NBP]>(bsm + NB * NBP);
+    __shared__ double tv[NB];
+    __shared__ int s_i;
+    const int tid = threadIdx.x;
+    if (tid == 0) s_i = nblk - 1 - (int)atomicAdd(ticket, 1u);
+    __syncthreads();
+    const int i = s_i;
+    const int c0 = i * NB;
+    const int r = tid >> 2, q = tid & 3;
+    {
+        const double* src = LinvP + (size_t)i * NB * NB;
+        for (int idx = tid; idx < NB * NB; idx += 256) Ls[idx / NB][idx % NB] = src[idx];
+    }
+    double pacc[16];
+#pragma unroll
+    for (int c = 0; c < 16; c++) pacc[c] = 0.0;
+    for (int j = nblk - 1; j > i; j--) {
+        const int gr = j * NB + r;
+        const bool rowok = gr < n;
+        double lv[16];
+        if (rowok) {
+            const double2* p2 = reinterpret_cast<const double2*>(A + (size_t)gr * ld + c0 + q * 16);
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                const double2 t = __ldg(p2 + c);
+                lv[2 * c] = t.x;
+                lv[2 * c + 1] = t.y;
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < 16; c++) lv[c] = 0.0;
+        }
+        if (tid == 0) {
+            while (ld_acquire_u32(flags + j) != epoch) __nanosleep(32);
+        }
+        __syncthreads();
+        const double xr = rowok ? __ldcg(xv + gr) : 0.0;
+#pragma unroll
+        for (int c = 0; c < 16; c++) pacc[c] += lv[c] * xr;
+    }
+#pragma unroll
+    for (int c = 0; c < 16; c++) P[r][q * 16 + c] = pacc[c];
+    __syncthreads();
+    if (tid < NB) {
+        double s = 0.0;
+        for (int rr = 0; rr < NB; rr++) s += P[rr][tid];
+        tv[tid] = ((c0 + tid) < n ? zv[c0 + tid] : 0.0) - s;
+    }
+    __syncthreads();
+    if (tid < NB) {
+        double s = 0.0;
+        for (int rr = 0; rr < NB; rr++) s += Ls[rr][tid] * tv[rr];
+        if (c0 + tid < n) xv[c0 + tid] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) st_release_u32(flags + i, epoch);
+}
+
+inline int ldlt_init_solve_attrs() {
+    CU(cudaFuncSetAttribute(ldlt_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM));
+    return 0;
+}
+
+// x = A^-1 b using the factorisation in w; b and x are device vectors of length n (may alias)
+inline int ldlt_solve(LdltWs& w, const double* b, double* x) {
+    cudaStream_t st = w.st;
+    const size_t npad = (size_t)w.nblk * NB;
+    double *ia = w.dinfo, *ib = w.dinfo + npad;
+    w.epoch++;
+    CU(cudaMemsetAsync(w.ticket, 0, sizeof(unsigned) * 2, st));
+    ldlt_fwd_kernel<<<w.nblk, 256, 0, st>>>(w.A, w.ld, w.n, w.nblk, w.LinvP, ia, ib, w.kind, b, w.yv, w.zv, w.flags,
+                                            w.epoch, w.ticket);
+    LAUNCHED();
+    ldlt_bwd_kernel<<<w.nblk, 256, TILE_SMEM, st>>>(w.A, w.ld, w.n, w.nblk, w.LinvP, w.zv, w.xv, w.flags + w.nblk,
+                                                    w.epoch, w.ticket + 1);
+    LAUNCHED();
+    CU(cudaMemcpyAsync(x, w.xv, sizeof(double) * w.n, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+}  // namespace b200

@@ -1,0 +1,449 @@
+"""Drop-in replacement for ``pyipm.IPM`` (reference: /root/reference/pyipm.py:23-1863) whose per-iteration hot
+path runs on a B200 through libb200ipm.so.
+
+Same constructor keywords (pyipm.py:311-314), same ``solve() -> (x, s, lda, fval, kkt)`` (pyipm.py:1567, 1863),
+same ``KKT()``, ``validate()``, ``compile()``, the same progress messages and ``signal`` codes.  What changed:
+
+* Aesara is gone.  ``f`` is either a *lowerable problem description* (``problems.PolyProblem`` /
+  ``problems.QuadProblem``: derivatives are generated and evaluated on the device -- this replaces symbolic
+  autodiff, pyipm.py:473-509) or a set of plain Python callables ``f, df, d2f, ce, dce, d2ce, ci, dci, d2ci``
+  with the reference's "precompiled function" conventions (pyipm.py:216-231).  ``x_dev`` / ``lambda_dev`` are
+  accepted and ignored.
+* ``lbfgs`` must be False (the L-BFGS branch is outside the hot path this package replaces).
+* The callable slots of the reference (``cost, grad, hess, con, jaco, phi, dphi, init_lambda, init_slack``)
+  exist with the same signatures and run on the device for lowered problems.
+
+There is no CPU fallback: constructing the engine without libb200ipm.so or without a CUDA device raises.
+"""
+from __future__ import print_function
+
+import numpy as np
+
+from . import _lib
+from . import problems as _problems
+
+
+class IPM(object):
+    def __init__(self, x0=None, x_dev=None, f=None, df=None, d2f=None, ce=None, dce=None, d2ce=None, ci=None, dci=None,
+                 d2ci=None, lda0=None, lambda_dev=None, s0=None, mu=0.2, nu=10.0, rho=0.1, tau=0.995, eta=1.0E-4,
+                 beta=0.4, miter=20, niter=10, Xtol=None, Ktol=1.0E-4, Ftol=None, lbfgs=False, lbfgs_zeta=None,
+                 float_dtype=np.float64, verbosity=1, device=0, stream=None, nrefine=2):
+        # pyipm.py:316-376
+        self.x0 = x0
+        self.x_dev = x_dev            # ignored (no symbolic graph)
+        self.lda0 = lda0
+        self.lambda_dev = lambda_dev  # ignored
+        self.s0 = s0
+        self.problem = f if isinstance(f, (_problems.PolyProblem, _problems.QuadProblem)) else None
+        self.f, self.df, self.d2f = f, df, d2f
+        self.ce, self.dce, self.d2ce = ce, dce, d2ce
+        self.ci, self.dci, self.d2ci = ci, dci, d2ci
+        self.nvar = self.neq = self.nineq = None
+        self.eps = np.finfo(float_dtype).eps
+        self.mu, self.nu, self.rho, self.tau, self.eta, self.beta = mu, nu, rho, tau, eta, beta
+        self.miter, self.niter = miter, niter
+        self.Xtol = Xtol if Xtol else self.eps
+        self.Ktol, self.Ftol = Ktol, Ftol
+        self.reg_coef = float_dtype(np.sqrt(self.eps))
+        self.lbfgs, self.lbfgs_zeta = lbfgs, lbfgs_zeta
+        self.float_dtype = float_dtype
+        # the reference's two shared scalars (pyipm.py:363-364)
+        self.nu_dev = float(nu)
+        self.mu_dev = float(mu)
+        self.verbosity = verbosity
+        self.delta0 = self.reg_coef
+        self.compiled = False
+        self.device, self.stream, self.nrefine = device, stream, nrefine
+        self.engine = None
+        self.delta = 0.0
+        self.mu_host = mu
+        self.signal = 0
+        self.step_log = []   # one dict per Newton step (timings, inertia, alphas) for benchmarking/tests
+
+    # ------------------------------------------------------------------ validate / compile
+    def validate(self):
+        """pyipm.py:385-408."""
+        assert self.f is not None
+        if self.problem is None:
+            assert (self.ce is not None) or (self.ce is None and self.dce is None and self.d2ce is None)
+            assert (self.ci is not None) or (self.ci is None and self.dci is None and self.d2ci is None)
+        assert self.mu > 0.0
+        assert self.nu > 0.0
+        assert 0.0 < self.eta < 1.0
+        assert 0.0 < self.rho < 1.0
+        assert 0.0 < self.tau < 1.0
+        assert self.beta < 1.0
+        assert self.miter >= 0 and isinstance(self.miter, int)
+        assert self.niter >= 0 and isinstance(self.miter, int)
+        assert self.Xtol >= self.eps
+        assert self.Ktol >= self.eps
+        assert self.Ftol is None or self.Ftol >= 0.0
+        assert not self.lbfgs, 'pyipm_b200 implements the exact-Hessian path only (lbfgs=False)'
+        assert self.float_dtype == np.float64, 'pyipm_b200 computes in float64'
+
+    def compile(self, nvar=None, neq=None, nineq=None):
+        """Size discovery (pyipm.py:414-467), device workspace allocation and problem binding."""
+        if nvar is not None:
+            self.nvar = nvar
+        if self.problem is not None:
+            self.nvar, self.neq, self.nineq = self.problem.nvar, self.problem.neq, self.problem.nineq
+        else:
+            self.neq = neq
+            self.nineq = nineq
+            if self.ce is not None and self.neq is None:
+                self.neq = np.asarray(self.ce(self.x0)).size
+            elif neq is None:
+                self.neq = 0
+            if self.ci is not None and self.nineq is None:
+                self.nineq = np.asarray(self.ci(self.x0)).size
+            elif nineq is None:
+                self.nineq = 0
+            for name in ('df', 'd2f') + (('dce', 'd2ce') if self.neq else ()) + (('dci', 'd2ci') if self.nineq else ()):
+                assert getattr(self, name) is not None, \
+                    'callable mode needs %s (no symbolic autodiff; pass a PolyProblem/QuadProblem to have ' \
+                    'derivatives generated on the device)' % name
+        params = _lib.default_params(mu=self.mu, nu=self.nu, rho=self.rho, tau=self.tau, eta=self.eta, beta=self.beta,
+                                     Xtol=self.Xtol, Ktol=self.Ktol, nrefine=self.nrefine)
+        if self.engine is not None:
+            self.engine.close()
+        self.engine = _lib.Engine(self.nvar, self.neq, self.nineq, params, device=self.device, stream=self.stream)
+        if self.problem is not None:
+            self.engine.bind(self.problem)
+        self.compiled = True
+
+    # ------------------------------------------------------------------ state plumbing
+    def _push(self, x, s, lda):
+        self.engine.set_state(x, s if self.nineq else None, lda if (self.neq + self.nineq) else None,
+                              self.mu_dev, self.nu_dev, self.delta)
+        self.engine.set_mu_host(self.mu_host)
+        if self.problem is None:
+            self._upload_derivs(np.asarray(x, dtype=np.float64), np.asarray(lda, dtype=np.float64))
+
+    def _upload_derivs(self, x, lda):
+        D, M, N = self.nvar, self.neq, self.nineq
+        fval = float(self.f(x))
+        df = np.asarray(self.df(x), dtype=np.float64).reshape(D)
+        W = np.array(self.d2f(x), dtype=np.float64).reshape(D, D)
+        ce = ci = None
+        blocks = []
+        if M:
+            ce = np.asarray(self.ce(x), dtype=np.float64).reshape(M)
+            blocks.append(np.asarray(self.dce(x), dtype=np.float64).reshape(D, M))
+            W = W - np.asarray(self.d2ce(x, lda), dtype=np.float64).reshape(D, D)
+        if N:
+            ci = np.asarray(self.ci(x), dtype=np.float64).reshape(N)
+            blocks.append(np.asarray(self.dci(x), dtype=np.float64).reshape(D, N))
+            W = W - np.asarray(self.d2ci(x, lda), dtype=np.float64).reshape(D, D)
+        J = np.concatenate(blocks, axis=1) if blocks else None
+        self.engine.set_derivs(fval, df, ce, ci, J, W)
+
+    # ------------------------------------------------------------------ operator slots (pyipm.py:855-954)
+    def _at(self, x, s=None, lda=None):
+        s = np.zeros(self.nineq) if s is None else s
+        lda = np.zeros(self.neq + self.nineq) if lda is None else lda
+        self._push(np.asarray(x, dtype=np.float64), np.asarray(s, dtype=np.float64), np.asarray(lda, dtype=np.float64))
+
+    def cost(self, x):
+        self._at(x, np.ones(self.nineq))
+        return self.engine.cost()
+
+    def grad(self, x, s, lda):
+        self._at(x, s, lda)
+        return self.engine.residual()[0]
+
+    def hess(self, x, s, lda):
+        self._at(x, s, lda)
+        return self.engine.hess_full()
+
+    def con(self, x, s):
+        self._at(x, s)
+        return self.engine.con_jac()[0]
+
+    def jaco(self, x):
+        self._at(x, np.ones(self.nineq))
+        D, M, N = self.nvar, self.neq, self.nineq
+        top = self.engine.con_jac()[1]
+        if not N:
+            return top
+        bottom = np.concatenate([np.zeros((N, M)), -np.eye(N)], axis=1)
+        return np.concatenate([top, bottom], axis=0)
+
+    def KKT(self, x, s, lda):
+        """pyipm.py:958-991 (absent conditions are scalar 0.0; returns a tuple)."""
+        self._at(x, s, lda)
+        k1, k2, k3, k4 = self.engine.kkt()
+        z = self.float_dtype(0.0)
+        return k1, (k2 if self.nineq else z), (k3 if self.neq else z), (k4 if self.nineq else z)
+
+    # ------------------------------------------------------------------ solve
+    def solve(self, x0=None, s0=None, lda0=None, force_recompile=False):
+        """pyipm.py:1567-1863 with the inner-iteration body (pyipm.py:1714-1754) executed by
+        ``b200ipm_newton_step`` on the device."""
+        if x0 is not None:
+            self.x0 = x0
+        if s0 is not None:
+            self.s0 = s0
+        if lda0 is not None:
+            self.lda0 = lda0
+        assert (self.x0 is not None) and (self.x0.size > 0)
+        assert self.x0.size == self.x0.shape[0]
+        self.nvar = self.x0.size
+        self.x0 = self.float_dtype(self.x0)
+        self.validate()
+        if not self.compiled or force_recompile:
+            self.compile()
+        D, M, N = self.nvar, self.neq, self.nineq
+        eng = self.engine
+        lowered = self.problem is not None
+        self.step_log = []
+
+        # initialise weights, slacks and multipliers (pyipm.py:1596-1625)
+        x = np.array(self.x0, dtype=np.float64)
+        self.delta = 0.0
+        if N:
+            self.mu_host = self.mu               # quirk xi: mu_dev is NOT reset (pyipm.py:1603)
+        else:
+            self.mu_host = self.Ktol             # pyipm.py:1606-1607
+            self.mu_dev = float(self.mu_host)
+        if M or N:
+            self.nu_host = self.nu
+            self.nu_dev = float(self.nu_host)
+        s = np.zeros(N)
+        lda = np.zeros(M + N)
+        if N and self.s0 is not None:
+            s = np.asarray(self.s0, dtype=np.float64)
+        if (M or N) and self.lda0 is not None:
+            lda = np.asarray(self.lda0, dtype=np.float64)
+        self._push(x, s if (not N or self.s0 is not None) else np.ones(N), lda)
+        if N and self.s0 is None:
+            if lowered:
+                eng.init_slack()
+            else:
+                s = np.maximum(np.asarray(self.ci(x), dtype=np.float64).reshape(N), self.Ktol)
+                self._push(x, s, lda)
+        if (M or N) and self.lda0 is None:
+            eng.init_lambda()
+        x, s, lda, _, _, _ = eng.get_state()
+        if not lowered:
+            self._push(x, s, lda)
+
+        _, nrm = eng.residual(want_g=False)
+        iter_count = 0
+        if self.Ftol is not None:
+            f_past = eng.cost()
+        Ktol_converged = False
+        Ftol_converged = False
+        self.signal = 0
+        if self.verbosity > 0:
+            print('Searching for a feasible local minimizer using the exact Hessian.')
+        outer = inner = 0
+
+        for outer in range(self.niter):
+            if all(nrm <= self.Ktol):
+                self.signal = 1
+                Ktol_converged = True
+                break
+            if self.verbosity > 0 and N:
+                print('OUTER ITERATION {}'.format(outer + 1))
+
+            for inner in range(self.miter):
+                muTol = np.max([self.Ktol, self.mu_host])
+                if all(nrm <= muTol):
+                    if not M and not N:
+                        self.signal = 1
+                        Ktol_converged = True
+                    break
+
+                if self.verbosity > 0:
+                    msg = []
+                    if N:
+                        msg.append('* INNER ITERATION {}'.format(inner + 1))
+                    else:
+                        msg.append('ITERATION {}'.format(iter_count + 1))
+                    if self.verbosity > 1:
+                        msg.append('f(x) = {}'.format(eng.cost()))
+                    if self.verbosity > 2:
+                        msg.append('|dL/dx| = {}'.format(nrm[0]))
+                        msg.append('|dL/ds| = {}'.format(nrm[1]))
+                        msg.append('|ce| = {}'.format(nrm[2]))
+                        msg.append('|ci-s| = {}'.format(nrm[3]))
+                    print(', '.join(msg))
+
+                # ---- one Newton step on the device (pyipm.py:1714-1754)
+                if lowered:
+                    info = eng.newton_step()
+                    nrm = np.array(list(info.kkt_norm))
+                    f_new_dev = info.fval
+                else:
+                    info, nrm, f_new_dev = self._callable_step()
+                self.nu_dev = self.nu_host = info.nu
+                self.delta = info.delta
+                if info.signal == -2:
+                    self.signal = -2
+                    if self.verbosity > 2:
+                        print('Search direction is unreliable to machine precision.')
+                if info.soc_accepted and self.verbosity > 2:
+                    print('Second-order feasibility correction accepted')
+                self.step_log.append(info.asdict())
+                iter_count += 1
+
+                if all([self.Ftol is not None, not N, self.signal != -2]):
+                    f_new = f_new_dev
+                    if np.abs(f_past - f_new) <= np.abs(self.Ftol):
+                        self.signal = 2
+                        Ftol_converged = True
+                        break
+                    else:
+                        f_past = f_new
+                if self.signal == -2:
+                    break
+                if inner >= self.miter - 1:
+                    if self.verbosity > 0 and N:
+                        print('MAXIMUM INNER ITERATIONS EXCEEDED')
+
+            if all([self.Ftol is not None, N, self.signal != -2]):
+                f_new = eng.cost()
+                if np.abs(f_past - f_new) <= np.abs(self.Ftol):
+                    self.signal = 2
+                    Ftol_converged = True
+                else:
+                    f_past = f_new
+            if self.Ftol is not None and Ftol_converged:
+                break
+            if self.signal == -2:
+                break
+            if outer >= self.niter - 1:
+                self.signal = -1
+                if self.verbosity > 0:
+                    print('MAXIMUM OUTER ITERATIONS EXCEEDED' if N else 'MAXIMUM ITERATIONS EXCEEDED')
+                break
+
+            if N:
+                # barrier parameter update (pyipm.py:1804-1814)
+                self.mu_host = float(eng.update_mu())
+                self.mu_dev = self.mu_host
+                xs, ss, ls, _, nu_, dl_ = eng.get_state()
+                eng.set_state(None, None, None, self.mu_dev, nu_, dl_)
+                eng.set_mu_host(self.mu_host)
+                if not lowered:
+                    self._push(xs, ss, ls)
+                _, nrm = eng.residual(want_g=False)
+
+        x, s, lda, _, _, _ = eng.get_state()
+        self.x, self.s, self.lda = x, s, lda
+        if not lowered:
+            self._push(x, s, lda)
+        self.kkt = self.KKT(x, s, lda)
+        self.fval = eng.cost()
+        kn = [np.linalg.norm(k) for k in self.kkt]
+
+        if self.verbosity >= 0:
+            msg = []
+            if self.signal == -2:
+                msg.append('Terminated due to bad direction in backtracking line search')
+            elif all(k <= self.Ktol for k in kn):
+                msg.append('Converged to Ktol tolerance')
+            elif self.Ftol is not None and Ftol_converged:
+                msg.append('Converged to Ftol tolerance')
+            else:
+                msg.append('Maximum iterations reached')
+                outer = self.niter
+                inner = 0
+            if N:
+                if outer > 1:
+                    msg.append('after {} outer'.format(outer - 1))
+                    msg.append('iterations' if outer > 2 else 'iteration')
+                    msg.append('and')
+                else:
+                    msg.append('after')
+                msg.append('{} inner'.format(inner))
+                msg.append('iterations' if inner > 1 else 'iteration')
+                msg.append('({} total).'.format(iter_count))
+            else:
+                msg.append('after {}'.format(iter_count))
+                msg.append('iterations.' if iter_count > 1 else 'iteration.')
+            print(' '.join(msg))
+            if self.verbosity > 1:
+                msg = ['FINAL: f(x) = {}'.format(self.fval)]
+                if self.verbosity > 2:
+                    msg.append('|dL/dx| = {}'.format(kn[0]))
+                    msg.append('|dL/ds| = {}'.format(kn[1]))
+                    msg.append('|ce| = {}'.format(kn[2]))
+                    msg.append('|ci-s| = {}'.format(kn[3]))
+                print(', '.join(msg))
+        self.iter_count = iter_count
+        return self.x, self.s, self.lda, self.fval, self.kkt
+
+    # ------------------------------------------------------------------ callable mode
+    def _callable_step(self):
+        """One inner iteration when f/ce/ci are opaque host callables: derivatives are evaluated by the user's
+        functions and uploaded; residual, KKT formation, inertia-corrected factorisation, solve, nu rule and the
+        fraction-to-the-boundary rule run on the device; the Armijo loop has to call the user's host functions
+        for every trial point, so its scalar bookkeeping (pyipm.py:1457-1505) stays on the host.  The
+        second-order correction is not attempted in this mode."""
+        eng = self.engine
+        D, M, N = self.nvar, self.neq, self.nineq
+        x, s, lda, _, _, _ = eng.get_state()
+        dz, info = eng.direction()
+        _, nrm0 = eng.residual(want_g=False)
+        con_l1 = 0.0
+        if M:
+            con_l1 += np.sum(np.abs(np.asarray(self.ce(x)).reshape(M)))
+        if N:
+            con_l1 += np.sum(np.abs(np.asarray(self.ci(x)).reshape(N) - s))
+        df = np.asarray(self.df(x), dtype=np.float64).reshape(D)
+        if M or N:
+            bcg = np.concatenate([df, -self.mu_dev / (s + self.eps)]) if N else df
+            nu_thres = np.dot(bcg, dz[:D + N]) / (1 - self.rho) / con_l1
+            if self.nu_dev < nu_thres:
+                self.nu_dev = float(nu_thres)
+        eng.set_state(None, None, None, self.mu_dev, self.nu_dev, info.delta)
+        a_s, a_l = eng.step_max() if N else (1.0, 1.0)
+        if not (M or N):
+            a_l = 0.0
+        dx, ds, dl = dz[:D], dz[D:D + N], dz[D + N:]
+
+        def phi(xx, ss):
+            v = float(self.f(xx))
+            c1 = 0.0
+            if M:
+                c1 += np.sum(np.abs(np.asarray(self.ce(xx)).reshape(M)))
+            if N:
+                c1 += np.sum(np.abs(np.asarray(self.ci(xx)).reshape(N) - ss))
+            if M or N:
+                v += self.nu_dev * c1
+            if N:
+                v -= self.mu_dev * np.sum(np.log(ss))
+            return v
+
+        phi0 = phi(x, s)
+        dphi0 = np.dot(df, dx)
+        if M or N:
+            dphi0 -= self.nu_dev * con_l1
+        if N:
+            dphi0 -= np.dot(self.mu_dev / (s + self.eps), ds)
+        info.alpha_smax, info.alpha_lmax = a_s, a_l
+        nb = 0
+        with np.errstate(all='ignore'):
+            if phi(x + a_s * dx, s + a_s * ds) > phi0 + a_s * self.eta * dphi0:
+                a_s *= self.tau
+                a_l *= self.tau
+                nb = 1
+                while phi(x + a_s * dx, s + a_s * ds) > phi0 + a_s * self.eta * dphi0:
+                    nrm_step = (np.sqrt(np.linalg.norm(a_s * dx) ** 2 + np.linalg.norm(a_l * ds) ** 2) if N
+                                else np.linalg.norm(a_s * dx))
+                    if nrm_step < self.eps:
+                        info.signal = -2
+                        break
+                    a_s *= self.tau
+                    a_l *= self.tau
+                    nb += 1
+        info.n_backtracks = nb
+        if info.signal != -2:
+            x = x + a_s * dx
+            s = s + a_s * ds
+            lda = lda + a_l * dl if (M or N) else lda
+        info.alpha_s, info.alpha_l, info.nu = a_s, a_l, self.nu_dev
+        self._push(x, s, lda)
+        _, nrm = eng.residual(want_g=False)
+        return info, nrm, float(self.f(x))

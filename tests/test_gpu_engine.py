@@ -1,0 +1,188 @@
+"""Engine parity on the B200, through the C ABI, against the CPU oracle and the reference-generated fixtures.
+
+Teacher-forced single Newton steps start from oracle states (tight tolerances: same inertia decision, same
+delta, same number of backtracks); full solves are compared at 1e-6 and against the reference's known answers.
+Tolerances follow SURVEY.md section 8(c)."""
+import numpy as np
+import pytest
+
+from oracle.pyipm_numpy import OracleIPM
+from pyipm_b200 import IPM, _lib, problems
+from tests.util import ALL_GOLDEN, EXAMPLES, get_problem, load_golden
+
+pytestmark = pytest.mark.gpu
+
+DZ_RTOL = 1e-9
+
+
+def oracle_trace(prob, x0, **kw):
+    tr = []
+    o = OracleIPM(x0=np.array(x0), Ftol=1.0E-8, verbosity=-1, trace=tr, **prob.callables(), **kw)
+    with np.errstate(all='ignore'):
+        o.solve()
+    return o, tr
+
+
+def make_engine(prob, **kw):
+    eng = _lib.Engine(prob.nvar, prob.neq, prob.nineq, _lib.default_params(**kw))
+    eng.bind(prob)
+    return eng
+
+
+def relinf(a, b):
+    return np.max(np.abs(np.asarray(a) - np.asarray(b))) / max(np.max(np.abs(b)), 1e-300)
+
+
+@pytest.mark.parametrize('name', ALL_GOLDEN)
+def test_residual_and_full_kkt_matrix(name):
+    """a1/a10/a3: grad(), KKT norms and the reference's full K x K hess() at every state of the reference run."""
+    g = load_golden(name)
+    prob, x0, _ = get_problem(name)
+    eng = make_engine(prob)
+    for k in range(int(g['nsteps'])):
+        eng.set_state(g['st_x'][k], g['st_s'][k], g['st_lda'][k], g['st_mu'][k], g['st_nu_before'][k],
+                      g['st_delta_before'][k])
+        gv, nrm = eng.residual()
+        ref = -g['st_g'][k]
+        assert relinf(gv, ref) < 1e-12
+        if 'st_Hfull' in g.files:
+            H = eng.hess_full()
+            Href = g['st_Hfull'][k]
+            assert np.array_equal(H, H.T)
+            assert np.max(np.abs(H - Href)) <= 1e-12 * max(1.0, np.max(np.abs(Href)))
+    eng.close()
+
+
+@pytest.mark.parametrize('name', ALL_GOLDEN)
+def test_teacher_forced_newton_steps(name):
+    """a3-a9: one device Newton step from each oracle state: dz, delta, #factorisations (= eigvalsh calls),
+    step limits, number of backtracks, accepted point."""
+    prob, x0, _ = get_problem(name)
+    o, tr = oracle_trace(prob, x0)
+    g = load_golden(name)
+    eng = make_engine(prob)
+    for k, st in enumerate(tr):
+        eng.set_state(st['x'], st['s'], st['lda'], st['mu'], g['st_nu_before'][k], g['st_delta_before'][k])
+        eng.set_mu_host(st['mu_host'])
+        dz, dinfo = eng.direction()
+        assert relinf(dz, st['dz']) < DZ_RTOL, (k, relinf(dz, st['dz']))
+        assert dinfo.delta == st['delta'], (k, dinfo.delta, st['delta'])
+        assert dinfo.n_factor == st['reg']['n_eig'], (k, dinfo.n_factor, st['reg']['n_eig'])
+        assert dinfo.n_neg == prob.neq
+        assert dinfo.resid < 1e-9 * max(1.0, np.max(np.abs(st['g'])))
+        # the full step from the same state
+        eng.set_state(st['x'], st['s'], st['lda'], st['mu'], g['st_nu_before'][k], g['st_delta_before'][k])
+        info = eng.newton_step()
+        x, s, lda, mu, nu, delta = eng.get_state()
+        assert abs(nu - st['nu_after']) <= 1e-9 * abs(st['nu_after']), k
+        if prob.nineq:
+            assert abs(info.alpha_smax - st['alpha_smax']) < 1e-12
+            assert abs(info.alpha_lmax - st['alpha_lmax']) < 1e-12
+        sr = st['search']
+        assert info.soc_tried == int(sr['soc_tried']), k
+        assert info.soc_accepted == int(sr['soc_accepted']), k
+        assert info.n_backtracks == sr['n_backtracks'], (k, info.n_backtracks, sr['n_backtracks'])
+        tol = 1e-8 if not sr['soc_accepted'] else 1e-6
+        assert relinf(x, st['x_new']) < tol, (k, relinf(x, st['x_new']))
+        if prob.nineq:
+            assert relinf(s, st['s_new']) < tol
+        if prob.neq + prob.nineq:
+            assert relinf(lda, st['lda_new']) < tol
+        np.testing.assert_allclose(np.array(list(info.kkt_norm)), st['kkt_norms'], rtol=1e-6, atol=1e-10)
+    eng.close()
+
+
+@pytest.mark.parametrize('name', ALL_GOLDEN)
+def test_full_solve_matches_reference(name):
+    """IPM(...).solve() drop-in: final (x, s, lda, fval, kkt), signal and iteration count vs the reference run."""
+    g = load_golden(name)
+    prob, x0, gts = get_problem(name)
+    p = IPM(x0=np.array(x0), f=prob, Ftol=1.0E-8, verbosity=-1)
+    x, s, lda, fval, kkt = p.solve()
+    assert p.signal == int(g['sol0_signal'])
+    assert p.iter_count == int(g['sol0_nsteps'])
+    for a, key in ((x, 'x'), (s, 's'), (lda, 'lda')):
+        ref = g['sol0_' + key]
+        assert np.linalg.norm(a - ref) <= 1e-6 * (1.0 + np.linalg.norm(ref)), key
+    assert abs(fval - float(g['sol0_fval'])) <= 1e-8 * (1.0 + abs(float(g['sol0_fval'])))
+    if gts is not None:
+        assert min(np.linalg.norm(x - gt) for gt in gts) <= 1.0E-3    # unit_tests.py:51,405-409
+
+
+def test_second_solve_quirk_mu_dev_not_reset():
+    """Quirk xi (pyipm.py:1603 vs 1607): a second solve() starts from the stale mu_dev."""
+    g = load_golden('example7')
+    prob, x0, _ = get_problem('example7')
+    p = IPM(x0=np.array(x0), f=prob, Ftol=1.0E-8, verbosity=-1)
+    p.solve()
+    x, s, lda, fval, kkt = p.solve()
+    assert np.linalg.norm(x - g['sol1_x']) <= 1e-6
+    assert np.linalg.norm(lda - g['sol1_lda']) <= 1e-6
+
+
+def test_init_slack_and_lambda():
+    """a12: s0 = max(ci, Ktol), lda0 = pinv(J) df with negative inequality multipliers -> Ktol."""
+    for name in ('example7', 'example5', 'example8', 'qp_small', 'nlp_mid', 'nlp_eqonly'):
+        prob, x0, _ = get_problem(name)
+        o = OracleIPM(x0=np.array(x0), verbosity=-1, **prob.callables())
+        o.nvar = prob.nvar
+        o.compile()
+        eng = make_engine(prob)
+        eng.set_state(x0, np.ones(prob.nineq), np.zeros(prob.neq + prob.nineq), 0.2, 10.0, 0.0)
+        if prob.nineq:
+            eng.init_slack()
+        eng.init_lambda()
+        x, s, lda, _, _, _ = eng.get_state()
+        lref = o.init_lambda(np.array(x0))
+        if prob.nineq:
+            np.testing.assert_allclose(s, o.init_slack(np.array(x0)), rtol=1e-13)
+            li = lref[prob.neq:]
+            li[li < 0] = 1e-4
+        assert relinf(lda, lref) < 1e-7, (name, relinf(lda, lref))
+        eng.close()
+
+
+def test_callable_mode_matches_lowered_mode():
+    """Opaque host callables (the reference's precompiled-function input mode) through set_derivs."""
+    for name in ('example1', 'example5', 'example7', 'qp_small'):
+        prob, x0, gts = get_problem(name)
+        g = load_golden(name)
+        p = IPM(x0=np.array(x0), Ftol=1.0E-8, verbosity=-1, **prob.callables())
+        x, s, lda, fval, kkt = p.solve()
+        assert np.linalg.norm(x - g['sol0_x']) <= 1e-6 * (1 + np.linalg.norm(g['sol0_x'])), name
+        assert p.signal == int(g['sol0_signal'])
+
+
+def test_mid_size_steps_vs_oracle():
+    """Teacher-forced steps on problems large enough to use the DMMA kernels and several LDL^T panels."""
+    for prob in (problems.make_qp(D=320, M=80, nbox=160, seed=21), problems.make_nlp(D=256, M=48, N=256, seed=22)):
+        o, tr = oracle_trace(prob, prob.x0, niter=2, miter=3)
+        eng = make_engine(prob)
+        nu_b, de_b = 10.0, 0.0
+        for k, st in enumerate(tr):
+            eng.set_state(st['x'], st['s'], st['lda'], st['mu'], nu_b, de_b)
+            eng.set_mu_host(st['mu_host'])
+            dz, dinfo = eng.direction()
+            assert dinfo.n_factor == st['reg']['n_eig'], (prob.name, k)
+            assert dinfo.delta == st['delta']
+            assert relinf(dz, st['dz']) < 1e-8, (prob.name, k, relinf(dz, st['dz']))
+            nu_b, de_b = st['nu_after'], st['delta']
+        eng.close()
+
+
+def test_config3_size_properties():
+    """BASELINE config 3 (D=4096, M=512, N=4096) at full size: properties that do not need the (hours-long) CPU
+    oracle -- exact inertia of the accepted matrix, unreduced KKT residual of the direction, a descent
+    direction for the merit function, and monotone decrease of the KKT norms over a few steps."""
+    prob = problems.make_nlp()
+    p = IPM(x0=prob.x0, f=prob, verbosity=-1, niter=1, miter=3)
+    p.solve()
+    assert len(p.step_log) == 3
+    for st in p.step_log:
+        assert st['n_neg'] == prob.neq and st['n_zero'] == 0
+        assert st['resid'] < 1e-8
+        assert st['dphi0'] < 0.0
+        assert st['signal'] == 0
+    k0 = np.array(p.step_log[0]['kkt_norm'])
+    k2 = np.array(p.step_log[-1]['kkt_norm'])
+    assert k2[2] < k0[2] and k2[3] < k0[3]       # feasibility improves

@@ -1,0 +1,136 @@
+"""Kernel-level parity on the B200 (through the C ABI): GEMV, the DMMA A*diag(w)*A' contraction and the
+tile-pivoted LDL^T (factor, inertia, solve) against NumPy/SciPy on the same seeded inputs."""
+import numpy as np
+import pytest
+import scipy.linalg
+
+from pyipm_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('rows,cols', [(3, 4), (17, 33), (128, 130), (1000, 257), (512, 2048)])
+@pytest.mark.parametrize('transpose', [False, True])
+def test_gemv(rows, cols, transpose):
+    rng = np.random.default_rng(rows * 1000 + cols)
+    A = rng.standard_normal((rows, cols))
+    v = rng.standard_normal(rows if transpose else cols)
+    y = _lib.test_gemv(A, v, transpose)
+    ref = A.T @ v if transpose else A @ v
+    np.testing.assert_allclose(y, ref, rtol=1e-12, atol=1e-12 * np.abs(ref).max())
+
+
+def _syrk_ref(n, Cin, beta, dadd, shift, terms):
+    C = np.zeros((n, n))
+    if Cin is not None:
+        U = np.triu(Cin)
+        C += beta * (U + np.triu(U, 1).T)       # reference quirk: only triu(d2L) is used (pyipm.py:785,843)
+    if dadd is not None:
+        C += np.diag(dadd)
+    C += shift * np.eye(n)
+    for A, w, alpha in terms:
+        C += alpha * (A * (1.0 if w is None else w)[None, :]) @ A.T
+    return C
+
+
+@pytest.mark.parametrize('n,Ks,force_simple', [(5, [3], False), (64, [20], False), (130, [70, 33], False),
+                                               (130, [70, 33], True), (257, [64], False), (512, [256, 512, 100], False),
+                                               (1000, [1000], False)])
+def test_syrk_adat(n, Ks, force_simple):
+    rng = np.random.default_rng(n + sum(Ks))
+    Cin = rng.standard_normal((n, n))            # deliberately NOT symmetric
+    dadd = rng.standard_normal(n)
+    terms = []
+    for i, K in enumerate(Ks):
+        w = None if i == 2 else 10.0 ** rng.uniform(-3, 3, K)
+        terms.append((rng.standard_normal((n, K)), w, [-1.0, 1.0, 0.5][i]))
+    C, ms = _lib.test_syrk(n, Cin, 1.0, dadd, 0.25, terms, force_simple=force_simple)
+    ref = _syrk_ref(n, Cin, 1.0, dadd, 0.25, terms)
+    scale = sum(np.abs(A) @ (np.abs(A) * (1.0 if w is None else w)).T for A, w, _ in terms) + np.abs(ref) + 1.0
+    assert np.array_equal(C, C.T), 'output must be bitwise symmetric'
+    assert np.max(np.abs(C - ref) / scale) < 1e-14 * max(Ks)
+
+
+def _check_ldlt(A, nrhs=2, tol=1e-10, expect_inertia=True):
+    n = A.shape[0]
+    rng = np.random.default_rng(n)
+    F = _lib.DenseLDLT(n)
+    (pos, neg, zero), rcond = F.factor(A)
+    w = np.linalg.eigvalsh(A)
+    if expect_inertia:
+        assert (pos, neg, zero) == (int(np.sum(w > 0)), int(np.sum(w < 0)), 0)
+    B = rng.standard_normal((n, nrhs))
+    X = F.solve(B, nrefine=2)
+    Xref = np.linalg.solve(A, B)
+    err = np.max(np.abs(X - Xref)) / np.max(np.abs(Xref))
+    res = np.max(np.abs(A @ X - B)) / (np.max(np.abs(A)) * np.max(np.abs(X)) * n)
+    F.close()
+    assert res < 1e-14, res
+    assert err < tol, err
+    return rcond
+
+
+@pytest.mark.parametrize('n', [1, 2, 7, 64, 65, 100, 257, 640, 1000])
+def test_ldlt_spd(n):
+    rng = np.random.default_rng(n)
+    B = rng.standard_normal((n, n))
+    A = B @ B.T / n + np.eye(n)
+    _check_ldlt(A)
+
+
+@pytest.mark.parametrize('n', [2, 10, 64, 100, 300, 777])
+def test_ldlt_indefinite_random(n):
+    rng = np.random.default_rng(100 + n)
+    B = rng.standard_normal((n, n))
+    A = (B + B.T) / np.sqrt(n)
+    _check_ldlt(A, tol=1e-8)
+
+
+@pytest.mark.parametrize('D,M', [(3, 1), (2, 1), (40, 10), (100, 28), (300, 64), (900, 124)])
+def test_ldlt_saddle_point_inertia(D, M):
+    """Condensed-KKT structure [[H, A], [A', 0]] with an indefinite H whose reduced Hessian is positive
+    definite: inertia must be exactly (D, M, 0) -- the acceptance test of reghess (pyipm.py:1381)."""
+    rng = np.random.default_rng(D * 7 + M)
+    Aj = rng.standard_normal((D, M))
+    Q, _ = np.linalg.qr(np.concatenate([Aj, rng.standard_normal((D, D - M))], axis=1))
+    Z = Q[:, M:]                                   # null-space basis of Aj'
+    Y = Q[:, :M]
+    S = rng.standard_normal((D - M, D - M))
+    H = Z @ (S @ S.T / D + np.eye(D - M)) @ Z.T - 0.5 * Y @ Y.T    # negative curvature only in range(Aj)
+    K = np.zeros((D + M, D + M))
+    K[:D, :D] = (H + H.T) / 2
+    K[:D, D:] = Aj
+    K[D:, :D] = Aj.T
+    n = D + M
+    F = _lib.DenseLDLT(n)
+    (pos, neg, zero), _ = F.factor(K)
+    assert (pos, neg, zero) == (D, M, 0)
+    b = rng.standard_normal(n)
+    x = F.solve(b, nrefine=2)
+    F.close()
+    xref = np.linalg.solve(K, b)
+    assert np.max(np.abs(x - xref)) / np.max(np.abs(xref)) < 1e-9
+
+
+def test_ldlt_zero_diagonal_tile():
+    """Example-8-like structure (linear objective): H has exact zeros on the diagonal; inside one tile the
+    Bunch-Kaufman 2x2 pivots must handle it."""
+    K = np.array([[0.0, 0, 0, 2, 1.0], [0, 0, 0, -1, 2.0], [0, 0, 0, -1, 0.0], [2, -1, -1, 0, 0.0], [1, 2, 0, 0, 0.0]])
+    K[0, 0] = K[1, 1] = -0.7
+    F = _lib.DenseLDLT(5)
+    (pos, neg, zero), _ = F.factor(K)
+    w = np.linalg.eigvalsh(K)
+    assert (pos, neg, zero) == (int(np.sum(w > 0)), int(np.sum(w < 0)), 0)
+    b = np.arange(1.0, 6.0)
+    np.testing.assert_allclose(F.solve(b), np.linalg.solve(K, b), rtol=1e-11)
+    F.close()
+
+
+def test_ldlt_singular_reports_zero_pivot():
+    K = np.zeros((4, 4))
+    K[0, 0] = 1.0
+    K[1, 1] = 2.0
+    F = _lib.DenseLDLT(4)
+    (pos, neg, zero), rcond = F.factor(K)
+    F.close()
+    assert zero == 2 and pos == 2 and rcond == 0.0
