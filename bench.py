@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py -- Newton steps/s and ms per KKT-solve of the interior-point hot path at BASELINE.json's headline
+configuration (config 3: synthetic nonconvex NLP, n = 4096 dense, 512 eq + 4096 ineq, fp64).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's B200 path
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU arithmetic (oracle port)
+
+One "step" = one inner iteration of the reference (pyipm.py:1714-1754): gradient/KKT residual, Lagrangian
+Hessian, KKT formation, inertia-corrected factorisation (reghess), solve, nu rule, step rules, line search,
+KKT conditions at the new point -- teacher-forced from a fixed state a few iterations into the real solve, so
+every timed step does identical work.
+
+N > 1 (torchrun, one rank per GPU): the Newton step at n = 4096 does not shard (SURVEY.md section 8e,
+DESIGN.md "replicas only"): every rank steps an independent replica, no data-path collective, `scaling: weak`.
+
+Prints ONE JSON line (rank 0).  See DESIGN.md section "Measurement" for every field.
+"""
+from __future__ import print_function
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = 'config3: synthetic nonconvex NLP n=4096, 512 eq + 4096 ineq, dense d2L, fp64 (problems.make_nlp())'
+D3, M3, N3 = 4096, 512, 4096
+K3 = D3 + 2 * N3 + M3
+PRE_STEPS = 3   # real Newton steps taken from x0 before the teacher-forced state is snapshotted
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get('hbm_gbs', 6650.0), d.get('bf16_tflops', 1590.0), 'measured'
+    return 6650.0, 1590.0, 'fallback'
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, universal_newlines=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+                for name, col in (('hw_slowdown', 5), ('hw_thermal_slowdown', 6), ('sw_thermal_slowdown', 7),
+                                  ('sw_power_cap', 8)):
+                    if r[col].lower().startswith('active'):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': mx, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+# ------------------------------------------------------------------------------------------- reference arm
+def oracle_sample_step(D=1024, M=128, N=1024, seed=7):
+    """One Newton step of the CPU oracle on a bounded sample of the workload: the SAME problem family at
+    n = 1024 (K = 3200 instead of 12800), teacher-forced a few iterations in with delta already active so the
+    step does the typical two inertia tests (delta = 0 fails, delta/2 passes) + one LU.  A config-3-size step is
+    >= 4 minutes (eigvalsh(12800) = 235 s + LU 17 s on 8 cores) and several times that when the
+    delta loop escalates, so it cannot be a bench step; the measured n=1024 time is scaled by the cubic
+    work law (K3/K)^3 = 64 of the dense eigen/LU kernels that make up > 95 % of it."""
+    from oracle.pyipm_numpy import OracleIPM
+    from pyipm_b200 import problems
+    prob = problems.make_nlp(D=D, M=M, N=N, seed=seed)
+    o = OracleIPM(x0=prob.x0.copy(), verbosity=-1, **prob.callables())
+    o.nvar = D
+    o.compile()
+    rng = np.random.default_rng(seed)
+    x = prob.x0.copy()
+    s = np.maximum(prob.ci(x), 1e-4)
+    lda = np.concatenate([0.1 * rng.standard_normal(M), 0.2 / s])
+    o.mu_host = 0.2
+    o.mu_dev = np.float64(0.2)
+    o.nu_host = 10.0
+    o.nu_dev = np.float64(10.0)
+    o.signal = 0
+    return o, prob, (x, s, lda)
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return 0
+    os.environ.setdefault('OPENBLAS_NUM_THREADS', str(os.cpu_count()))
+    cores = os.cpu_count()
+    o, prob, (x, s, lda) = oracle_sample_step()
+    K = prob.nvar + 2 * prob.nineq + prob.neq
+    scale = (float(K3) / K) ** 3
+    times = []
+    delta_warm = None
+    with np.errstate(all='ignore'):
+        for it in range(args.warmup + args.steps):
+            # the first (warm-up) step finds delta from scratch; timed steps start from delta_found*2 so that
+            # reghess halves it back and does its typical two inertia tests
+            o.delta = np.float64(0.0) if delta_warm is None else np.float64(2.0 * delta_warm)
+            o.timers = {}
+            t0 = time.perf_counter()
+            o.newton_step(x.copy(), s.copy(), lda.copy())
+            dt = time.perf_counter() - t0
+            if delta_warm is None:
+                delta_warm = float(o.delta)
+            if it >= args.warmup:
+                times.append(dt)
+    t_sample = float(np.mean(times))
+    t_c3 = t_sample * scale
+    value = 1.0 / t_c3
+    sample = ('oracle Newton step (pyipm.py:1714-1754 restated) on the same NLP family at n=1024 (K=%d), mean of %d '
+              'steps = %.2f s, %d eigvalsh + 1 LU per step; scaled to config 3 by (K3/K)^3 = %.0f'
+              % (K, len(times), t_sample, o.last_reg['n_eig'], scale))
+    line = {
+        'impl': 'reference', 'metric': 'newton_steps_per_sec', 'value': value, 'unit': 'steps/s', 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * t_c3, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'D': D3, 'M': M3, 'N': N3, 'K_full': K3},
+        'cpu_baseline': {'value': value, 'unit': 'steps/s', 'cores': cores, 'kind': 'port', 'sample': sample,
+                         'split_s': {k: v for k, v in o.timers.items() if k != 'steps'}},
+        'e2e': {'value': value, 'unit': 'steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'ms_per_kkt_solve': 1e3 * scale * (o.timers.get('reghess', 0.0) + o.timers.get('solve', 0.0)),
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------- B200 arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from pyipm_b200 import _lib, problems
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device (the B200 arm has no CPU fallback; use --impl reference)')
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    hbm_gbs, bf16_tf, peak_kind = measured_peaks()
+    prob = problems.make_nlp(D3, M3, N3)       # same seed on every rank: independent replicas of config 3
+    stream = torch.cuda.current_stream().cuda_stream
+    eng = _lib.Engine(D3, M3, N3, _lib.default_params(), device=local, stream=stream)
+    eng.bind(prob)
+    eng.set_state(prob.x0, np.ones(N3), np.zeros(M3 + N3), 0.2, 10.0, 0.0)
+    eng.set_mu_host(0.2)
+    eng.init_slack()
+    eng.init_lambda()
+    pre = [eng.newton_step().asdict() for _ in range(PRE_STEPS)]
+    eng.state_save()
+    x_h, s_h, l_h, mu, nu, delta = eng.get_state()
+    pin = [torch.from_numpy(a).pin_memory() for a in (x_h, s_h, l_h)]
+    out = [torch.empty_like(t).pin_memory() for t in pin]
+
+    def step_resident():
+        eng.state_restore()
+        return eng.newton_step()
+
+    def step_e2e():
+        # host buffers in, host buffers out: the call a user of the C ABI makes per iteration
+        _lib.check(eng.lib.b200ipm_set_state(eng.h, pin[0].data_ptr(), pin[1].data_ptr(), pin[2].data_ptr(), mu, nu, delta))
+        info = eng.newton_step()
+        _lib.check(eng.lib.b200ipm_get_state(eng.h, out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), None, None, None))
+        return info
+
+    # fp64 contraction peak on THIS box (MEASURED_PEAKS.json only carries bf16 + HBM): cuBLAS DGEMM 4096^3
+    a = torch.randn(4096, 4096, dtype=torch.float64, device='cuda')
+    b = torch.randn(4096, 4096, dtype=torch.float64, device='cuda')
+    torch.matmul(a, b)
+    best = 1e9
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); torch.matmul(a, b); e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    fp64_peak_tf = 2 * 4096 ** 3 / best * 1e-9
+    del a, b
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        n0 = _lib.launch_count()
+        sampler = ClockSampler(local)
+        sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        infos = [fn() for _ in range(steps)]
+        e1.record()
+        barrier()
+        clocks = sampler.stop()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device='cuda', dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, infos, _lib.launch_count() - n0, clocks
+
+    ms_res, infos, launches, clocks = timed(step_resident, args.steps, args.warmup)
+    ms_e2e, infos_e, _, _ = timed(step_e2e, args.steps, max(args.warmup, 3))
+    per_step = ms_res / args.steps
+    value = world * args.steps / (ms_res * 1e-3)
+    e2e_value = world * args.steps / (ms_e2e * 1e-3)
+    last = infos[-1].asdict()
+    kkt_ms = float(np.mean([i.ms_factor + i.ms_solve for i in infos]))
+    nfac = float(np.mean([i.n_factor for i in infos]))
+
+    line = {
+        'metric': 'newton_steps_per_sec', 'value': value, 'unit': 'steps/s', 'n_gpus': world, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': per_step, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'D': D3, 'M': M3, 'N': N3, 'K_full': K3, 'K_condensed': D3 + M3,
+                   'parallelism': 'replicas x%d (one independent Newton step per GPU, no collective)' % world,
+                   'state': 'teacher-forced from the state after %d real Newton steps from x0' % PRE_STEPS,
+                   'factorisations_per_step': nfac, 'refinement_sweeps': 2,
+                   'l2': 'working set (J 151 MB, Vt/Gt/Q 134 MB each, KKT 170 MB) exceeds the 126 MB L2; no flush'},
+        'clocks': clocks,
+        'e2e': {'value': e2e_value, 'unit': 'steps/s', 'h2d_bytes_per_step': int(8 * (D3 + N3 + M3 + N3)),
+                'd2h_bytes_per_step': int(8 * (D3 + N3 + M3 + N3)), 'ms_per_step': ms_e2e / args.steps,
+                'note': 'b200ipm_set_state(host) + b200ipm_newton_step + b200ipm_get_state(host) per step; problem '
+                        'matrices are bound once (they are the problem definition, like the reference\'s compiled '
+                        'functions), the per-step inputs/outputs are the iterate (x, s, lda)'},
+        'gpu_launches': int(launches),
+        'ms_per_kkt_solve': kkt_ms,
+        'kkt_residual_inf': last['resid'],
+        'phase_ms': {k: float(np.mean([getattr(i, k) for i in infos])) for k in
+                     ('ms_eval', 'ms_assemble', 'ms_factor', 'ms_solve', 'ms_search', 'ms_total')},
+    }
+    if rank == 0:
+        # roofline legs: the dominant kernel (fp64 DMMA contraction) and the HBM-bound residual GEMV, each timed
+        # alone with CUDA events on the launching stream
+        eng.state_restore()
+        kern = {}
+        for which, name, kind in ((1, 'hess_syrk', 'flop'), (2, 'condense_syrk', 'flop'), (3, 'ldlt_factor', 'flop'),
+                                  (0, 'residual_gemv', 'byte'), (5, 'jt_gemv', 'byte'), (4, 'ldlt_solve', 'byte')):
+            ms, work = eng.profile_kernel(which, reps=5)
+            kern[name] = {'ms': ms, ('tflops' if kind == 'flop' else 'gbs'): work / ms * (1e-9 if kind == 'flop' else 1e-6),
+                          'work': work}
+        dom = kern['hess_syrk']
+        line['roofline'] = {
+            'kernel': 'gemm_nt_dmma_kernel (Lagrangian-Hessian SYRK: Ut diag(lda_e) Ut\' + Vt diag(lda_i) Vt\', fp64 DMMA)',
+            'bound': 'tensor', 'achieved': dom['tflops'], 'peak': fp64_peak_tf, 'unit': 'TFLOP/s',
+            'frac': dom['tflops'] / fp64_peak_tf, 'traffic': None,
+            'peak_source': 'cuBLAS DGEMM 4096^3 measured in this run (fp64 tensor pipe; MEASURED_PEAKS.json has no fp64 '
+                           'entry: its bf16 figure %.0f TF/s (%s) is a different pipe -- tcgen05 has no f64 kind)'
+                           % (bf16_tf, peak_kind),
+            'flops_per_launch': dom['work'],
+        }
+        res = kern['residual_gemv']
+        line['roofline_hbm'] = {'kernel': 'gemv_n_kernel (g_x = df - J*lda, fused KKT norm)', 'bound': 'hbm',
+                                'achieved': res['gbs'], 'peak': hbm_gbs, 'unit': 'GB/s', 'frac': res['gbs'] / hbm_gbs,
+                                'traffic': None, 'peak_source': 'MEASURED_PEAKS.json hbm_gbs (%s)' % peak_kind,
+                                'bytes_per_launch': res['work']}
+        line['kernels'] = kern
+        if world == 1 and not args.no_cpu_baseline:
+            os.environ.setdefault('OPENBLAS_NUM_THREADS', str(os.cpu_count()))
+            o, sprob, (x, s, lda) = oracle_sample_step()
+            K = sprob.nvar + 2 * sprob.nineq + sprob.neq
+            scale = (float(K3) / K) ** 3
+            with np.errstate(all='ignore'):
+                o.delta = np.float64(0.0)
+                o.newton_step(x.copy(), s.copy(), lda.copy())          # finds delta (untimed)
+                o.delta = np.float64(2.0 * float(o.delta))
+                o.timers = {}
+                t0 = time.perf_counter()
+                o.newton_step(x.copy(), s.copy(), lda.copy())
+                t_sample = time.perf_counter() - t0
+            line['cpu_baseline'] = {
+                'value': 1.0 / (t_sample * scale), 'unit': 'steps/s', 'cores': os.cpu_count(), 'kind': 'port',
+                'sample': 'one oracle Newton step on the same NLP family at n=1024 (K=%d): %.2f s (%d eigvalsh + 1 LU), '
+                          'scaled to config 3 by (K3/K)^3 = %.0f' % (K, t_sample, o.last_reg['n_eig'], scale),
+                'split_s': {k: v for k, v in o.timers.items() if k != 'steps'}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        if args.steps > 4:
+            args.steps = 4      # each reference step is a ~10-30 s bounded CPU sample
+        args.warmup = min(args.warmup, 1)
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+    return run_b200(args)
+
+
+if __name__ == '__main__':
+    sys.exit(main())

@@ -101,6 +101,10 @@ int b200ipm_set_state(b200ipm_handle h, const double* x, const double* s, const 
 int b200ipm_get_state(b200ipm_handle h, double* x, double* s, double* lda,
                       double* mu, double* nu, double* delta);
 int b200ipm_set_mu_host(b200ipm_handle h, double mu_host);   /* pyipm.py:1603/1606 (reghess uses mu_host) */
+/* Device-resident snapshot of (x, s, lda, mu, nu, delta, mu_host): warm start / teacher forcing without any
+ * host<->device traffic (solve(x0, s0, lda0) warm start, pyipm.py:1567-1578). */
+int b200ipm_state_save(b200ipm_handle h);
+int b200ipm_state_restore(b200ipm_handle h);
 
 /* ---- operator slots -------------------------------------------------------------------------------- */
 /* cost(x), pyipm.py:855-857 */
@@ -150,6 +154,14 @@ int b200ipm_ldlt_panel(b200ipm_ldlt_handle h, double* panel_dev, int ld, int row
                        const double* dblk_dev, const int* perm_dev, double* w_dev);
 int b200ipm_gemm_nt_update(b200ipm_ldlt_handle h, double* C_dev, int ldc, int rows, int cols,
                            const double* A_dev, int lda, const double* B_dev, int ldb, int k, int lower_only);
+
+/* ---- measurement hook (bench.py roofline legs, ncu captures) -------------------------------------- */
+/* Re-launches ONE hot kernel `reps` times on the handle's stream between two CUDA events at the current state
+ * and returns the mean milliseconds per launch plus its algorithmic work (FLOPs or bytes):
+ *   which = 0 residual GEMV g_x = df - J*lda (HBM)      1 Lagrangian-Hessian SYRK (fp64 tensor)
+ *           2 condensation SYRK dci*S*dci' (fp64 tensor) 3 one LDL^T factorisation of the condensed KKT matrix
+ *           4 one forward+backward triangular solve      5 J'*dx GEMV (HBM) */
+int b200ipm_profile_kernel(b200ipm_handle h, int which, int reps, float* ms_per_launch, double* work);
 
 /* ---- test hooks: individual kernels against the oracle (tests/test_gpu_kernels.py) ---------------- */
 /* C (n x n, symmetric, mirrored) = beta*sym(triu(Cin)) + diag(dadd) + shift*I + sum_t alpha_t A_t diag(w_t) A_t'.

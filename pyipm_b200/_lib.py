@@ -50,7 +50,8 @@ class StepInfo(C.Structure):
 SYMBOLS = [
     'b200ipm_version', 'b200ipm_last_error', 'b200ipm_launch_count', 'b200ipm_create', 'b200ipm_destroy',
     'b200ipm_set_params', 'b200ipm_sync', 'b200ipm_bind_quad', 'b200ipm_bind_poly', 'b200ipm_set_derivs',
-    'b200ipm_set_state', 'b200ipm_get_state', 'b200ipm_set_mu_host', 'b200ipm_cost', 'b200ipm_residual',
+    'b200ipm_set_state', 'b200ipm_get_state', 'b200ipm_set_mu_host', 'b200ipm_state_save', 'b200ipm_state_restore',
+    'b200ipm_profile_kernel', 'b200ipm_cost', 'b200ipm_residual',
     'b200ipm_kkt', 'b200ipm_con_jac', 'b200ipm_hess_full', 'b200ipm_d2L', 'b200ipm_merit', 'b200ipm_init_slack',
     'b200ipm_init_lambda', 'b200ipm_update_mu', 'b200ipm_direction', 'b200ipm_step_max', 'b200ipm_newton_step',
     'b200ipm_ldlt_create', 'b200ipm_ldlt_destroy', 'b200ipm_ldlt_factor', 'b200ipm_ldlt_solve',
@@ -90,6 +91,9 @@ def load():
         'b200ipm_set_state': (i, [vp, vp, vp, vp, d, d, d]),
         'b200ipm_get_state': (i, [vp, vp, vp, vp, dp, dp, dp]),
         'b200ipm_set_mu_host': (i, [vp, d]),
+        'b200ipm_state_save': (i, [vp]),
+        'b200ipm_state_restore': (i, [vp]),
+        'b200ipm_profile_kernel': (i, [vp, i, i, C.POINTER(C.c_float), dp]),
         'b200ipm_cost': (i, [vp, dp]),
         'b200ipm_residual': (i, [vp, vp, dp]),
         'b200ipm_kkt': (i, [vp, vp, vp, vp, vp]),
@@ -277,6 +281,18 @@ class Engine(object):
     def sync(self):
         check(self.lib.b200ipm_sync(self.h))
 
+    def state_save(self):
+        check(self.lib.b200ipm_state_save(self.h))
+
+    def state_restore(self):
+        check(self.lib.b200ipm_state_restore(self.h))
+
+    def profile_kernel(self, which, reps=10):
+        """-> (ms per launch, algorithmic work per launch [FLOPs or bytes])"""
+        ms, wk = C.c_float(), C.c_double()
+        check(self.lib.b200ipm_profile_kernel(self.h, int(which), int(reps), C.byref(ms), C.byref(wk)))
+        return ms.value, wk.value
+
 
 class DenseLDLT(object):
     """Generic dense symmetric-indefinite factor/solve (sym_solve_cmp slot; BASELINE config 4 building block)."""
@@ -310,7 +326,7 @@ class DenseLDLT(object):
         """B: (n,) or (n, nrhs); returns the solution with the same shape."""
         B = np.asarray(B, dtype=np.float64)
         one = (B.ndim == 1)
-        Bt = np.ascontiguousarray(B.reshape(self.n, -1).T)   # rhs-major
+        Bt = np.array(B.reshape(self.n, -1).T, dtype=np.float64, order='C', copy=True)   # rhs-major private copy
         check(self.lib.b200ipm_ldlt_solve(self.h, ptr(Bt), Bt.shape[0], int(nrefine), 0))
         X = Bt.T
         return X[:, 0].copy() if one else np.ascontiguousarray(X)

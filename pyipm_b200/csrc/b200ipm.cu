@@ -66,6 +66,10 @@ struct b200ipm_engine {
     PolyData poly{};
     cudaEvent_t ev[EV_N];
     double last_red[8];     // host copy of the residual reductions at the current state
+    // device-resident snapshot
+    double *sv_x = nullptr, *sv_s = nullptr, *sv_lam = nullptr;
+    double sv_mu = 0, sv_nu = 0, sv_delta = 0, sv_mu_host = 0;
+    bool sv_valid = false;
 };
 typedef b200ipm_engine Eng;
 
@@ -382,7 +386,7 @@ static int soc_direction(Eng* h, const double* cnew /* device, M+N */, double* p
     double scale = 0.0;
     RET(max_row_sqnorm(h, h->Jt, ldt, C, D, &scale));
     scale += 1.0;
-    const double tik = 1e-10 * scale;
+    const double tik = 1e-7 * scale;
     // G = Jt Jt' + diag(0, I) + tik I : build SYRK into F2.A then add the slack identity on the diagonal
     GemmArgs a{};
     a.C = h->F2.A; a.ldc = h->F2.ld; a.Cin = nullptr; a.n = C; a.m = C; a.beta = 0.0; a.shift = tik; a.dadd = nullptr;
@@ -399,7 +403,7 @@ static int soc_direction(Eng* h, const double* cnew /* device, M+N */, double* p
     RET(ldlt_factor(h->F2));
     // iterated Tikhonov: z_{k+1} = z_k + A'(G)^-1 (c - A z_k);   A z = [J' z_x]_e, [J' z_x]_i - z_s
     CU(cudaMemsetAsync(pz, 0, sizeof(double) * (D + N), h->st));
-    for (int it = 0; it < 3; it++) {
+    for (int it = 0; it < 6; it++) {
         // r = c - A z  -> h->cnew-sized scratch h->tvec? use h->ycor (length K >= C)
         if (it == 0) {
             CU(cudaMemcpyAsync(h->ycor, cnew, sizeof(double) * C, cudaMemcpyDeviceToDevice, h->st));
@@ -665,7 +669,8 @@ int b200ipm_destroy(b200ipm_handle h) {
     double* bufs[] = {h->x, h->s, h->lam, h->fval, h->df, h->ce, h->ci, h->J, h->W, h->Hb, h->g, h->sigma, h->bvec, h->tvec,
                       h->rhs, h->sol, h->ycur, h->ycor, h->rho, h->dz, h->wx, h->jt, h->scr, h->part, h->red, h->trial,
                       h->xt, h->st_, h->pvec, h->cnew, h->uvec, h->xdiag, h->qx, h->ax, h->ux, h->gx, h->vx, h->qd, h->ad,
-                      h->ud, h->gd, h->vd, h->Q, h->qc, h->At, h->Ut, h->qb, h->Gt, h->Vt, h->qr, h->Jt, h->p_coeff};
+                      h->ud, h->gd, h->vd, h->Q, h->qc, h->At, h->Ut, h->qb, h->Gt, h->Vt, h->qr, h->Jt, h->p_coeff, h->sv_x,
+                      h->sv_s, h->sv_lam};
     for (double* b : bufs) cudaFree(b);
     cudaFree(h->p_rowptr); cudaFree(h->p_ptr); cudaFree(h->p_fvar); cudaFree(h->p_fpow);
     cudaFreeHost(h->h_red);
@@ -800,6 +805,93 @@ int b200ipm_set_mu_host(b200ipm_handle h, double mu_host) {
     return 0;
 }
 
+int b200ipm_state_save(b200ipm_handle h) {
+    if (!h) return fail_msg("null handle");
+    CU(cudaSetDevice(h->device));
+    if (!h->sv_x) { RET(dalloc(&h->sv_x, h->D)); RET(dalloc(&h->sv_s, h->N)); RET(dalloc(&h->sv_lam, h->C)); }
+    CU(cudaMemcpyAsync(h->sv_x, h->x, sizeof(double) * h->D, cudaMemcpyDeviceToDevice, h->st));
+    if (h->N) CU(cudaMemcpyAsync(h->sv_s, h->s, sizeof(double) * h->N, cudaMemcpyDeviceToDevice, h->st));
+    if (h->C) CU(cudaMemcpyAsync(h->sv_lam, h->lam, sizeof(double) * h->C, cudaMemcpyDeviceToDevice, h->st));
+    h->sv_mu = h->mu; h->sv_nu = h->nu; h->sv_delta = h->delta; h->sv_mu_host = h->mu_host;
+    h->sv_valid = true;
+    return 0;
+}
+int b200ipm_state_restore(b200ipm_handle h) {
+    if (!h || !h->sv_valid) return fail_msg("state_restore: nothing saved");
+    CU(cudaSetDevice(h->device));
+    CU(cudaMemcpyAsync(h->x, h->sv_x, sizeof(double) * h->D, cudaMemcpyDeviceToDevice, h->st));
+    if (h->N) CU(cudaMemcpyAsync(h->s, h->sv_s, sizeof(double) * h->N, cudaMemcpyDeviceToDevice, h->st));
+    if (h->C) CU(cudaMemcpyAsync(h->lam, h->sv_lam, sizeof(double) * h->C, cudaMemcpyDeviceToDevice, h->st));
+    h->mu = h->sv_mu; h->nu = h->sv_nu; h->delta = h->sv_delta; h->mu_host = h->sv_mu_host;
+    h->eval_valid = false;
+    h->resid_valid = false;
+    return 0;
+}
+
+int b200ipm_profile_kernel(b200ipm_handle h, int which, int reps, float* ms_per_launch, double* work) {
+    if (!h || reps <= 0) return fail_msg("profile_kernel: bad arguments");
+    CU(cudaSetDevice(h->device));
+    RET(residual(h));
+    const int D = h->D, M = h->M, N = h->N, C = h->C;
+    double wk = 0.0;
+    if (which >= 2) RET(condense(h));
+    if (which >= 4) { RET(build_kc(h, h->delta, 0.0)); RET(ldlt_factor(h->F)); }
+    CU(cudaStreamSynchronize(h->st));
+    CU(cudaEventRecord(h->ev[EV_START], h->st));
+    for (int r = 0; r < reps; r++) {
+        switch (which) {
+            case 0:
+                RET(gemv_n(h->st, h->J, h->ldJ, D, C, h->lam, h->df, 1.0, -1.0, h->g, h->part));
+                wk = 8.0 * ((double)D * C + 2.0 * D + C);
+                break;
+            case 1: {
+                GemmArgs a{};
+                a.C = h->W; a.ldc = h->ldW; a.Cin = h->Q; a.ldcin = D; a.dadd = h->xdiag; a.n = D; a.m = D; a.beta = 1.0;
+                a.mode = GEMM_UPPER_MIRROR; a.nterms = 0;
+                if (h->kind != KIND_QUAD) return fail_msg("profile_kernel(1) needs a bound quad problem");
+                if (M && h->Ut) a.t[a.nterms++] = GemmTerm{h->Ut, h->Ut, h->lam, M, M, M, -1.0};
+                if (N && h->Vt) a.t[a.nterms++] = GemmTerm{h->Vt, h->Vt, h->lam + M, N, N, N, 1.0};
+                RET(gemm_nt(h->st, a));
+                wk = gemm_nt_flops(a);
+                break;
+            }
+            case 2: {
+                GemmArgs a{};
+                a.C = h->Hb; a.ldc = h->ldW; a.Cin = h->W; a.ldcin = h->ldW; a.n = D; a.m = D; a.beta = 1.0;
+                a.mode = GEMM_UPPER_MIRROR; a.nterms = 0;
+                if (N) a.t[a.nterms++] = GemmTerm{h->J + M, h->J + M, h->sigma, h->ldJ, h->ldJ, N, 1.0};
+                RET(gemm_nt(h->st, a));
+                wk = gemm_nt_flops(a);
+                break;
+            }
+            case 3:
+                RET(build_kc(h, h->delta, 0.0));
+                RET(ldlt_factor(h->F));
+                wk = (double)h->Kc * h->Kc * h->Kc / 3.0;
+                break;
+            case 4:
+                RET(ldlt_solve(h->F, h->rhs, h->sol));
+                wk = 8.0 * (double)h->Kc * h->Kc;   // bytes: both triangular sweeps read the factor once each (half matrix x2)
+                break;
+            case 5:
+                RET(gemv_t(h->st, h->J, h->ldJ, D, C, h->x, nullptr, 0.0, 1.0, h->jt, h->scr));
+                wk = 8.0 * ((double)D * C + D + C);
+                break;
+            default:
+                return fail_msg("profile_kernel: unknown kernel id");
+        }
+    }
+    CU(cudaEventRecord(h->ev[EV_SEARCH], h->st));
+    CU(cudaEventSynchronize(h->ev[EV_SEARCH]));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, h->ev[EV_START], h->ev[EV_SEARCH]));
+    if (ms_per_launch) *ms_per_launch = ms / reps;
+    if (work) *work = wk;
+    h->eval_valid = false;   // W / Hb / g were rewritten with the same values; keep the cache honest anyway
+    h->resid_valid = false;
+    return 0;
+}
+
 int b200ipm_cost(b200ipm_handle h, double* fval) {
     CU(cudaSetDevice(h->device));
     RET(residual(h));
@@ -896,7 +988,7 @@ int b200ipm_init_lambda(b200ipm_handle h) {
     RET(ensure_F2(h, D));
     double scale = 0.0;
     RET(max_row_sqnorm(h, h->J, h->ldJ, D, C, &scale));
-    const double tik = 1e-10 * (scale > 0.0 ? scale : 1.0);
+    const double tik = 1e-7 * (scale > 0.0 ? scale : 1.0);
     GemmArgs a{};
     a.C = h->F2.A; a.ldc = h->F2.ld; a.Cin = nullptr; a.dadd = nullptr; a.n = D; a.m = D; a.beta = 0.0; a.shift = tik;
     a.mode = GEMM_UPPER_MIRROR; a.nterms = 1;
@@ -904,7 +996,7 @@ int b200ipm_init_lambda(b200ipm_handle h) {
     RET(gemm_nt(h->st, a));
     RET(ldlt_factor(h->F2));
     CU(cudaMemsetAsync(h->lam, 0, sizeof(double) * C, h->st));
-    for (int it = 0; it < 3; it++) {
+    for (int it = 0; it < 6; it++) {
         // r = df - J lda ; u = G^-1 r ; lda += J' u
         RET(gemv_n(h->st, h->J, h->ldJ, D, C, h->lam, h->df, 1.0, -1.0, h->wx));
         RET(ldlt_solve(h->F2, h->wx, h->xt));
@@ -1080,12 +1172,9 @@ int b200ipm_ldlt_panel(b200ipm_ldlt_handle h, double* panel_dev, int ld, int row
     if (!h || !panel_dev || !w_dev) return fail_msg("panel: bad arguments");
     if (rows <= 0) return 0;
     CU(cudaSetDevice(h->device));
-    GemmArgs g{};
-    g.C = w_dev; g.ldc = NB; g.n = rows; g.m = NB; g.mode = GEMM_FULL; g.nterms = 1;
-    g.t[0] = GemmTerm{panel_dev, linv_dev, nullptr, ld, NB, NB, 1.0};
-    RET(gemm_nt(h->st, g));
     const int* kind = reinterpret_cast<const int*>(dblk_dev + 4 * NB);
-    ldlt_scale_kernel<<<cdiv(rows * NB, 256), 256, 0, h->st>>>(w_dev, rows, panel_dev, ld, dblk_dev, dblk_dev + NB, kind);
+    ldlt_panel_kernel<<<cdiv(rows, NB), 128, PANEL_SMEM, h->st>>>(panel_dev, ld, rows, linv_dev, dblk_dev, dblk_dev + NB,
+                                                                   kind, w_dev, NB);
     LAUNCHED();
     return 0;
 }

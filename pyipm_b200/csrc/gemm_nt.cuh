@@ -44,11 +44,15 @@ struct GemmArgs {
 };
 
 constexpr int G_BM = 128, G_BN = 128, G_BK = 16, G_LDS = 20, G_STAGES = 4;
-constexpr int G_SMEM = G_STAGES * (G_BM + G_BN) * G_LDS * 8;
+constexpr int G_SMEM = G_STAGES * ((G_BM + G_BN) * G_LDS + G_BK) * 8;
 
 __device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc, int bytes) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gsrc), "r"(bytes));
+}
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc, int bytes) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gsrc), "r"(bytes));
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
@@ -78,6 +82,15 @@ __device__ __forceinline__ void g_load_tile(double* sdst, const double* __restri
         cp_async16(sdst + row * G_LDS + kc, src, bytes);
     }
 }
+// the diagonal weights of one k-tile (16 doubles) ride the same cp.async pipeline as the operands, so the main
+// loop never waits on a global load (8-byte copies: w only needs natural alignment)
+__device__ __forceinline__ void g_load_w(double* sdst, const double* __restrict__ w, int k0, int K, int tid) {
+    if (tid < G_BK) {
+        const int k = k0 + tid;
+        const bool ok = k < K;
+        cp_async8(sdst + tid, ok ? w + k : w, ok ? 8 : 0);
+    }
+}
 
 __global__ void __launch_bounds__(256, 1) gemm_nt_dmma_kernel(const GemmArgs a) {
     extern __shared__ __align__(16) double g_smem[];
@@ -90,6 +103,7 @@ __global__ void __launch_bounds__(256, 1) gemm_nt_dmma_kernel(const GemmArgs a) 
     const int row0 = ti * G_BM, col0 = tj * G_BN;
     double* As = g_smem;
     double* Bs = g_smem + G_STAGES * G_BM * G_LDS;
+    double* Wsm = g_smem + G_STAGES * (G_BM + G_BN) * G_LDS;
 
     double acc[8][4][2];
 #pragma unroll
@@ -106,14 +120,9 @@ __global__ void __launch_bounds__(256, 1) gemm_nt_dmma_kernel(const GemmArgs a) 
             if (s < nk) {
                 g_load_tile(As + s * G_BM * G_LDS, T.A, T.lda, row0, a.n, s * G_BK, T.K, tid);
                 g_load_tile(Bs + s * G_BN * G_LDS, T.B, T.ldb, col0, a.m, s * G_BK, T.K, tid);
+                if (T.w) g_load_w(Wsm + s * G_BK, T.w, s * G_BK, T.K, tid);
             }
             cp_async_commit();
-        }
-        double wv[4];
-#pragma unroll
-        for (int kk = 0; kk < 4; kk++) {
-            const int k = kk * 4 + tg;
-            wv[kk] = (k < T.K) ? T.alpha * (T.w ? __ldg(T.w + k) : 1.0) : 0.0;
         }
         for (int kt = 0; kt < nk; kt++) {
             cp_async_wait<G_STAGES - 2>();
@@ -124,17 +133,12 @@ __global__ void __launch_bounds__(256, 1) gemm_nt_dmma_kernel(const GemmArgs a) 
                     const int s = kn % G_STAGES;
                     g_load_tile(As + s * G_BM * G_LDS, T.A, T.lda, row0, a.n, kn * G_BK, T.K, tid);
                     g_load_tile(Bs + s * G_BN * G_LDS, T.B, T.ldb, col0, a.m, kn * G_BK, T.K, tid);
+                    if (T.w) g_load_w(Wsm + s * G_BK, T.w, kn * G_BK, T.K, tid);
                 }
                 cp_async_commit();
             }
-            // prefetch next tile's weights
-            double wn_[4];
-#pragma unroll
-            for (int kk = 0; kk < 4; kk++) {
-                const int k = (kt + 1) * G_BK + kk * 4 + tg;
-                wn_[kk] = (k < T.K) ? T.alpha * (T.w ? __ldg(T.w + k) : 1.0) : 0.0;
-            }
             const int s = kt % G_STAGES;
+            const double* ws = Wsm + s * G_BK + tg;
             const double* as = As + s * G_BM * G_LDS + (wm * 64 + g) * G_LDS + tg;
             const double* bs = Bs + s * G_BN * G_LDS + (wn * 32 + g) * G_LDS + tg;
 #pragma unroll
@@ -142,15 +146,14 @@ __global__ void __launch_bounds__(256, 1) gemm_nt_dmma_kernel(const GemmArgs a) 
                 double af[8], bf[4];
 #pragma unroll
                 for (int mt = 0; mt < 8; mt++) af[mt] = as[mt * 8 * G_LDS + kk * 4];
+                const double wk = T.w ? ws[kk * 4] * T.alpha : T.alpha;
 #pragma unroll
-                for (int nt = 0; nt < 4; nt++) bf[nt] = bs[nt * 8 * G_LDS + kk * 4] * wv[kk];
+                for (int nt = 0; nt < 4; nt++) bf[nt] = bs[nt * 8 * G_LDS + kk * 4] * wk;
 #pragma unroll
                 for (int mt = 0; mt < 8; mt++)
 #pragma unroll
                     for (int nt = 0; nt < 4; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
             }
-#pragma unroll
-            for (int kk = 0; kk < 4; kk++) wv[kk] = wn_[kk];
         }
         cp_async_wait<0>();
         __syncthreads();
@@ -215,13 +218,8 @@ inline bool gemm_nt_can_dmma(const GemmArgs& a) {
 
 inline int gemm_nt(cudaStream_t st, const GemmArgs& a, bool force_simple = false) {
     if (a.n <= 0 || a.m <= 0) return 0;
-    static bool attr_set = false;
     const bool big = (a.n >= 48 && a.m >= 48);
     if (!force_simple && big && gemm_nt_can_dmma(a)) {
-        if (!attr_set) {
-            CU(cudaFuncSetAttribute(gemm_nt_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM));
-            attr_set = true;
-        }
         dim3 grid(cdiv(a.m, G_BN), cdiv(a.n, G_BM));
         gemm_nt_dmma_kernel<<<grid, 256, G_SMEM, st>>>(a);
         LAUNCHED();

@@ -31,7 +31,7 @@ constexpr int TILE_SMEM = 2 * NB * NBP * 8;
 struct LdltWs {
     int n = 0, ld = 0, nblk = 0;
     double* A = nullptr;       // n x ld, factored in place (strictly-lower part holds Lhat panels)
-    double* Wp = nullptr;      // n x NB   panel scratch (L * D)
+    double* Wp = nullptr;      // n x NBO  outer-panel scratch (L * D)
     double* LinvP = nullptr;   // nblk x NB x NB
     double* dinfo = nullptr;   // 4 x n: [dinv_a | dinv_b | d_a | d_b]
     int* kind = nullptr;       // n: 0 = 1x1, 1 = first of 2x2, 2 = second of 2x2
@@ -52,7 +52,7 @@ inline int ldlt_alloc(LdltWs& w, int n, cudaStream_t st) {
     w.epoch = 0;
     const size_t npad = (size_t)w.nblk * NB;
     CU(cudaMalloc(&w.A, sizeof(double) * (size_t)npad * w.ld));
-    CU(cudaMalloc(&w.Wp, sizeof(double) * npad * NB));
+    CU(cudaMalloc(&w.Wp, sizeof(double) * npad * 256));
     CU(cudaMalloc(&w.LinvP, sizeof(double) * (size_t)w.nblk * NB * NB));
     CU(cudaMalloc(&w.dinfo, sizeof(double) * 4 * npad));
     CU(cudaMalloc(&w.kind, sizeof(int) * npad));
@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(256) ldlt_tile_kernel(double* __restrict__ A, 
     extern __shared__ __align__(16) double tsm[];
     double(*T)[NBP] = reinterpret_cast<double(*)[NBP]>(tsm);
     double(*X)[NBP] = reinterpret_cast<double(*)[NBP]>(tsm + NB * NBP);
-    __shared__ double colu[NB], colv[NB], sda[NB], sdb[NB];
+    __shared__ double sda[NB], sdb[NB];
     __shared__ int sperm[NB], skind[NB];
     __shared__ int s_kp, s_kstep;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -161,55 +161,61 @@ __global__ void __launch_bounds__(256) ldlt_tile_kernel(double* __restrict__ A, 
             if (tid == 0) { int p = sperm[kk]; sperm[kk] = sperm[kp]; sperm[kp] = p; }
             __syncthreads();
         }
-        // ---- elimination
+        // ---- elimination.  Fixed ownership: warp w owns rows w, w+8, ...; lanes own columns lane, lane+32.
+        // Everybody reads the pivot ROW(s) j (, j+1), which stay intact during the step (the multipliers are
+        // written into COLUMN j), so no staging buffer and no barrier is needed inside the step.  Products are
+        // formed as (u_i*u_m)*dinv so T stays bitwise symmetric.
         if (kstep == 1) {
             const double d = T[j][j];
-            if (tid < NB) colu[tid] = (tid > j) ? T[tid][j] : 0.0;
             if (tid == 0) { sda[j] = d; sdb[j] = 0.0; skind[j] = 0; }
-            __syncthreads();
             if (d != 0.0) {
                 const double dinv = 1.0 / d;
-                for (int i = j + 1 + warp; i < nb; i += 8) {
-                    const double li = colu[i] * dinv;
-                    // trailing update, lower part + mirror
-                    for (int m = j + 1 + lane; m <= i; m += 32) {
-                        const double v = T[i][m] - li * colu[m];
-                        T[i][m] = v;
-                        T[m][i] = v;
+#pragma unroll
+                for (int rr = 0; rr < 8; rr++) {
+                    const int i = warp + 8 * rr;
+                    if (i > j && i < nb) {
+                        const double ui = T[j][i];
+                        const double li = ui * dinv;
+#pragma unroll
+                        for (int hh = 0; hh < 2; hh++) {
+                            const int m = lane + 32 * hh;
+                            if (m > j && m < nb) T[i][m] -= (ui * T[j][m]) * dinv;
+                            if (m <= j) X[i][m] -= li * X[j][m];
+                        }
+                        if (lane == 0) T[i][j] = li;
                     }
-                    // Gauss-Jordan: X[i][0..j] -= l_i * X[j][0..j]
-                    for (int c = lane; c <= j; c += 32) X[i][c] -= li * X[j][c];
-                    if (lane == 0) T[i][j] = li;
                 }
             }
         } else {
             const double a11 = T[j][j], a21 = T[j + 1][j], a22 = T[j + 1][j + 1];
-            if (tid < NB) {
-                colu[tid] = (tid > j + 1) ? T[tid][j] : 0.0;
-                colv[tid] = (tid > j + 1) ? T[tid][j + 1] : 0.0;
-            }
             if (tid == 0) {
                 sda[j] = a11; sdb[j] = a21; sda[j + 1] = a22; sdb[j + 1] = 0.0;
                 skind[j] = 1; skind[j + 1] = 2;
             }
-            __syncthreads();
             // LAPACK's scaled 2x2 inverse (dsytf2): robust against overflow of the determinant
             const double d11 = a22 / a21, d22 = a11 / a21;
             const double tt = 1.0 / (d11 * d22 - 1.0);
             const double d21i = tt / a21;
-            for (int i = j + 2 + warp; i < nb; i += 8) {
-                const double u = colu[i], v = colv[i];
-                const double l1 = d21i * (d11 * u - v);
-                const double l2 = d21i * (d22 * v - u);
-                for (int m = j + 2 + lane; m <= i; m += 32) {
-                    const double val = T[i][m] - (l1 * colu[m] + l2 * colv[m]);
-                    T[i][m] = val;
-                    T[m][i] = val;
+#pragma unroll
+            for (int rr = 0; rr < 8; rr++) {
+                const int i = warp + 8 * rr;
+                if (i > j + 1 && i < nb) {
+                    const double u = T[j][i], v = T[j + 1][i];
+                    const double l1 = d21i * (d11 * u - v);
+                    const double l2 = d21i * (d22 * v - u);
+#pragma unroll
+                    for (int hh = 0; hh < 2; hh++) {
+                        const int m = lane + 32 * hh;
+                        if (m > j + 1 && m < nb) {
+                            const double um = T[j][m], vm = T[j + 1][m];
+                            T[i][m] -= d21i * ((d11 * (u * um) + d22 * (v * vm)) - (v * um + u * vm));
+                        }
+                        if (m <= j + 1) X[i][m] -= l1 * X[j][m] + l2 * X[j + 1][m];
+                    }
+                    if (lane == 0) { T[i][j] = l1; T[i][j + 1] = l2; }
                 }
-                for (int c = lane; c <= j + 1; c += 32) X[i][c] -= l1 * X[j][c] + l2 * X[j + 1][c];
-                if (lane == 0) { T[i][j] = l1; T[i][j + 1] = l2; }
             }
-            if (tid == 0) T[j + 1][j] = 0.0;
+            // (T[j+1][j] keeps a21 until the output stage: other warps may still be reading it)
         }
         __syncthreads();
         j += kstep;
@@ -224,7 +230,7 @@ __global__ void __launch_bounds__(256) ldlt_tile_kernel(double* __restrict__ A, 
     // L back into the strictly-lower part of the tile, D on the diagonal (diagnostics / tests)
     for (int idx = tid; idx < nb * nb; idx += 256) {
         const int i = idx / nb, jj = idx % nb;
-        if (i > jj) A[(size_t)i * ld + jj] = T[i][jj];
+        if (i > jj) A[(size_t)i * ld + jj] = (skind[jj] == 1 && i == jj + 1) ? 0.0 : T[i][jj];
         else if (i == jj) A[(size_t)i * ld + jj] = sda[i];
     }
     if (tid < NB) {
@@ -276,19 +282,79 @@ __global__ void __launch_bounds__(256) ldlt_tile_kernel(double* __restrict__ A, 
     }
 }
 
-// Lpanel = W * D^-1 (block diagonal), rows x NB; W has leading dimension NB, L is written into A's panel
-__global__ void ldlt_scale_kernel(const double* __restrict__ W, int rows, double* __restrict__ L, int ld,
-                                  const double* __restrict__ dinv_a, const double* __restrict__ dinv_b,
-                                  const int* __restrict__ kind) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= rows * NB) return;
-    const int r = idx / NB, j = idx % NB;
-    const double* w = W + (size_t)r * NB;
-    const int k = kind[j];
-    double v = w[j] * dinv_a[j];
-    if (k == 1) v += w[j + 1] * dinv_b[j];
-    else if (k == 2) v += w[j - 1] * dinv_b[j - 1];
-    L[(size_t)r * ld + j] = v;
+// Fused panel step for 64 rows per CTA (4 warps, DMMA):  W = B * LinvP^T  (W = Lpanel * D) and
+// Lpanel = W * D^-1 (block diagonal, 1x1 / 2x2).  B (rows x 64, leading dimension ld) is overwritten with Lpanel,
+// W goes to Wout (leading dimension ldw).  Both operands are staged whole in smem (K = 64), row stride 68 doubles
+// keeps the fragment loads at the minimum two wavefronts.
+constexpr int P_LDS = 68;
+constexpr int PANEL_SMEM = 2 * NB * P_LDS * 8;
+__global__ void __launch_bounds__(128) ldlt_panel_kernel(double* __restrict__ B, int ld, int rows,
+                                                         const double* __restrict__ LinvP,
+                                                         const double* __restrict__ dinv_a,
+                                                         const double* __restrict__ dinv_b, const int* __restrict__ kind,
+                                                         double* __restrict__ Wout, int ldw) {
+    extern __shared__ __align__(16) double psm[];
+    double* As = psm;
+    double* Bs = psm + NB * P_LDS;
+    __shared__ double sia[NB], sib[NB];
+    __shared__ int skd[NB];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, tg = lane & 3;
+    const int r0 = blockIdx.x * NB;
+    if (tid < NB) { sia[tid] = dinv_a[tid]; sib[tid] = dinv_b[tid]; skd[tid] = kind[tid]; }
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const int c = tid + 128 * i;
+        const int row = c >> 5, kc = (c & 31) * 2;
+        const bool ok = (r0 + row) < rows;
+        cp_async16(As + row * P_LDS + kc, ok ? B + (size_t)(r0 + row) * ld + kc : B, ok ? 16 : 0);
+        cp_async16(Bs + row * P_LDS + kc, LinvP + row * NB + kc, 16);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    double acc[2][8][2];
+#pragma unroll
+    for (int a = 0; a < 2; a++)
+#pragma unroll
+        for (int b = 0; b < 8; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
+    const double* as = As + (warp * 16 + g) * P_LDS + tg;
+    const double* bs = Bs + g * P_LDS + tg;
+#pragma unroll
+    for (int kk = 0; kk < 16; kk++) {
+        double af[2], bf[8];
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++) af[mt] = as[mt * 8 * P_LDS + kk * 4];
+#pragma unroll
+        for (int nt = 0; nt < 8; nt++) bf[nt] = bs[nt * 8 * P_LDS + kk * 4];
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+            for (int nt = 0; nt < 8; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
+    }
+    __syncthreads();   // everybody is done reading As: reuse it for the W tile
+#pragma unroll
+    for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+        for (int nt = 0; nt < 8; nt++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) As[(warp * 16 + mt * 8 + g) * P_LDS + nt * 8 + tg * 2 + e] = acc[mt][nt][e];
+    __syncthreads();
+    const int col = tid & 63;
+    const int k = skd[col];
+    const double ia = sia[col];
+    const double ibn = (k == 1) ? sib[col] : ((k == 2) ? sib[col - 1] : 0.0);
+    const int nbr = (k == 1) ? col + 1 : ((k == 2) ? col - 1 : col);
+#pragma unroll 4
+    for (int i = 0; i < 32; i++) {
+        const int r = (tid >> 6) + 2 * i;
+        const int gr = r0 + r;
+        if (gr < rows) {
+            const double wv = As[r * P_LDS + col];
+            Wout[(size_t)gr * ldw + col] = wv;
+            B[(size_t)gr * ld + col] = wv * ia + As[r * P_LDS + nbr] * ibn;
+        }
+    }
 }
 
 __global__ void ldlt_reset_kernel(int* counts, double* dstat, unsigned* ticket) {
@@ -300,12 +366,16 @@ __global__ void ldlt_reset_kernel(int* counts, double* dstat, unsigned* ticket) 
 
 inline int ldlt_init_attrs() {
     CU(cudaFuncSetAttribute(ldlt_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM));
+    CU(cudaFuncSetAttribute(ldlt_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM));
     CU(cudaFuncSetAttribute(gemm_nt_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM));
     return 0;
 }
 
-// Factor w.A in place.  Results stay on the device (counts/dstat); the caller reads them back when it needs the
-// inertia decision.
+// Factor w.A in place (two-level blocking).  Outer panels of NBO = 256 columns: inside a panel the 64-wide tile
+// steps update only the panel's own remaining columns (K = 64, small), the trailing matrix is updated ONCE per
+// outer panel with K = 256 -- 4x less read-modify-write traffic on A22 and a contraction long enough to keep the
+// DMMA pipeline full.  Results stay on the device (counts/dstat) until the caller needs the inertia decision.
+constexpr int NBO = 256;
 inline int ldlt_factor(LdltWs& w) {
     cudaStream_t st = w.st;
     const int n = w.n, ld = w.ld;
@@ -313,29 +383,37 @@ inline int ldlt_factor(LdltWs& w) {
     double *ia = w.dinfo, *ib = w.dinfo + npad, *da = w.dinfo + 2 * npad, *db = w.dinfo + 3 * npad;
     ldlt_reset_kernel<<<1, 1, 0, st>>>(w.counts, w.dstat, w.ticket);
     LAUNCHED();
-    for (int k = 0; k < w.nblk; k++) {
-        const int k0 = k * NB, nb = min(NB, n - k0), k1 = k0 + nb;
-        double* Akk = w.A + (size_t)k0 * ld + k0;
-        double* Lk = w.LinvP + (size_t)k * NB * NB;
-        ldlt_tile_kernel<<<1, 256, TILE_SMEM, st>>>(Akk, ld, nb, Lk, ia + k0, ib + k0, da + k0, db + k0, w.kind + k0,
-                                                    nullptr, w.counts, w.dstat);
-        LAUNCHED();
-        const int rows = n - k1;
-        if (rows <= 0) break;
-        double* B = w.A + (size_t)k1 * ld + k0;
-        // W = B * LinvP^T
-        GemmArgs g{};
-        g.C = w.Wp; g.ldc = NB; g.Cin = nullptr; g.dadd = nullptr; g.n = rows; g.m = NB; g.beta = 0.0; g.shift = 0.0;
-        g.mode = GEMM_FULL; g.nterms = 1;
-        g.t[0] = GemmTerm{B, Lk, nullptr, ld, NB, NB, 1.0};
-        RET(gemm_nt(st, g));
-        ldlt_scale_kernel<<<cdiv(rows * NB, 256), 256, 0, st>>>(w.Wp, rows, B, ld, ia + k0, ib + k0, w.kind + k0);
-        LAUNCHED();
-        // A22 -= W * L^T   (lower tiles only)
+    for (int c0 = 0; c0 < n; c0 += NBO) {
+        const int c1 = min(c0 + NBO, n);
+        for (int k0 = c0; k0 < c1; k0 += NB) {
+            const int k = k0 / NB, nb = min(NB, n - k0), k1 = k0 + nb;
+            double* Akk = w.A + (size_t)k0 * ld + k0;
+            double* Lk = w.LinvP + (size_t)k * NB * NB;
+            ldlt_tile_kernel<<<1, 256, TILE_SMEM, st>>>(Akk, ld, nb, Lk, ia + k0, ib + k0, da + k0, db + k0, w.kind + k0,
+                                                        nullptr, w.counts, w.dstat);
+            LAUNCHED();
+            const int rows = n - k1;
+            if (rows <= 0) break;
+            double* B = w.A + (size_t)k1 * ld + k0;                      // rows below the tile
+            double* Wt = w.Wp + (size_t)k1 * NBO + (k0 - c0);           // W = L * D for this tile step
+            ldlt_panel_kernel<<<cdiv(rows, NB), 128, PANEL_SMEM, st>>>(B, ld, rows, Lk, ia + k0, ib + k0, w.kind + k0, Wt, NBO);
+            LAUNCHED();
+            const int mcols = c1 - k1;                                   // remaining columns of this outer panel
+            if (mcols > 0) {
+                GemmArgs u{};
+                u.C = w.A + (size_t)k1 * ld + k1; u.ldc = ld; u.Cin = u.C; u.ldcin = ld; u.n = rows; u.m = mcols;
+                u.beta = 1.0; u.mode = GEMM_FULL; u.nterms = 1;
+                u.t[0] = GemmTerm{Wt, B, nullptr, NBO, ld, NB, -1.0};
+                RET(gemm_nt(st, u));
+            }
+        }
+        const int rows2 = n - c1;
+        if (rows2 <= 0) break;
+        // A22 -= W_panel * L_panel^T   (lower tiles only, K = c1 - c0)
         GemmArgs u{};
-        u.C = w.A + (size_t)k1 * ld + k1; u.ldc = ld; u.Cin = u.C; u.ldcin = ld; u.dadd = nullptr; u.n = rows; u.m = rows;
-        u.beta = 1.0; u.shift = 0.0; u.mode = GEMM_LOWER_ONLY; u.nterms = 1;
-        u.t[0] = GemmTerm{w.Wp, B, nullptr, NB, ld, NB, -1.0};
+        u.C = w.A + (size_t)c1 * ld + c1; u.ldc = ld; u.Cin = u.C; u.ldcin = ld; u.n = rows2; u.m = rows2;
+        u.beta = 1.0; u.mode = GEMM_LOWER_ONLY; u.nterms = 1;
+        u.t[0] = GemmTerm{w.Wp + (size_t)c1 * NBO, w.A + (size_t)c1 * ld + c0, nullptr, NBO, ld, c1 - c0, -1.0};
         RET(gemm_nt(st, u));
     }
     return 0;

@@ -29,7 +29,7 @@ def _syrk_ref(n, Cin, beta, dadd, shift, terms):
         C += np.diag(dadd)
     C += shift * np.eye(n)
     for A, w, alpha in terms:
-        C += alpha * (A * (1.0 if w is None else w)[None, :]) @ A.T
+        C += alpha * (A if w is None else A * w[None, :]) @ A.T
     return C
 
 
@@ -46,7 +46,7 @@ def test_syrk_adat(n, Ks, force_simple):
         terms.append((rng.standard_normal((n, K)), w, [-1.0, 1.0, 0.5][i]))
     C, ms = _lib.test_syrk(n, Cin, 1.0, dadd, 0.25, terms, force_simple=force_simple)
     ref = _syrk_ref(n, Cin, 1.0, dadd, 0.25, terms)
-    scale = sum(np.abs(A) @ (np.abs(A) * (1.0 if w is None else w)).T for A, w, _ in terms) + np.abs(ref) + 1.0
+    scale = sum(np.abs(A) @ (np.abs(A) if w is None else np.abs(A) * w).T for A, w, _ in terms) + np.abs(ref) + 1.0
     assert np.array_equal(C, C.T), 'output must be bitwise symmetric'
     assert np.max(np.abs(C - ref) / scale) < 1e-14 * max(Ks)
 

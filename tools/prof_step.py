@@ -1,0 +1,16 @@
+"""One teacher-forced Newton step at BASELINE config 3 for ncu captures (test/measurement infrastructure)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from pyipm_b200 import _lib, problems
+D, M, N = (int(a) for a in (sys.argv[1:4] if len(sys.argv) > 3 else (4096, 512, 4096)))
+prob = problems.make_nlp(D, M, N)
+eng = _lib.Engine(D, M, N, _lib.default_params())
+eng.bind(prob)
+rng = np.random.default_rng(0)
+s = np.maximum(prob.ci(prob.x0), 1e-4)
+lda = np.concatenate([0.1 * rng.standard_normal(M), 0.2 / s])
+eng.set_state(prob.x0, s, lda, 0.2, 10.0, 2 * 1.4901161193847656)   # delta already active: 2 factorisations
+eng.set_mu_host(0.2)
+info = eng.newton_step()
+print(info.asdict())
