@@ -1155,7 +1155,7 @@ int b200ipm_ldlt_tile_factor(b200ipm_ldlt_handle h, double* tile_dev, int ld, in
     LAUNCHED();
     // dblk_dev layout: [dinv_a (NB) | dinv_b (NB) | d_a (NB) | d_b (NB)] followed by NB ints of `kind`
     int* kind = reinterpret_cast<int*>(dblk_dev + 4 * NB);
-    ldlt_tile_kernel<<<1, 256, TILE_SMEM, h->st>>>(tile_dev, ld, nb, linv_dev, dblk_dev, dblk_dev + NB, dblk_dev + 2 * NB,
+    ldlt_tile_kernel<<<1, TILE_THREADS, TILE_SMEM, h->st>>>(tile_dev, ld, nb, linv_dev, dblk_dev, dblk_dev + NB, dblk_dev + 2 * NB,
                                                    dblk_dev + 3 * NB, kind, perm_dev, h->F.counts, h->F.dstat);
     LAUNCHED();
     if (counts) {

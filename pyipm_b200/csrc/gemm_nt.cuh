@@ -159,12 +159,52 @@ __global__ void __launch_bounds__(256, 1) gemm_nt_dmma_kernel(const GemmArgs a) 
         __syncthreads();
     }
 
-    // epilogue
+    // epilogue.  Per 8-row fragment group the Cin values are fetched first (4 independent 16-byte loads in flight
+    // per thread), then combined and stored: the short-K launches of the LDL^T are epilogue-bound otherwise.
     const bool diag_tile = (ti == tj);
+    const bool vec_ok = ((a.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(a.C) & 15) == 0) &&
+                        (a.Cin == nullptr || (((a.ldcin & 1) == 0) && ((reinterpret_cast<uintptr_t>(a.Cin) & 15) == 0)));
+    const bool interior = vec_ok && !diag_tile && (row0 + G_BM <= a.n) && (col0 + G_BN <= a.m);
+    if (interior) {
+#pragma unroll
+        for (int mt = 0; mt < 8; mt++) {
+            const int i = row0 + wm * 64 + mt * 8 + g;
+            const int jb = col0 + wn * 32 + tg * 2;
+            double2 cin[4];
+            if (a.Cin) {
+#pragma unroll
+                for (int nt = 0; nt < 4; nt++)
+                    cin[nt] = *reinterpret_cast<const double2*>(a.Cin + (size_t)i * a.ldcin + jb + nt * 8);
+            }
+#pragma unroll
+            for (int nt = 0; nt < 4; nt++) {
+                double2 v = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+                if (a.Cin) { v.x += a.beta * cin[nt].x; v.y += a.beta * cin[nt].y; }
+                const int j = jb + nt * 8;
+                *reinterpret_cast<double2*>(a.C + (size_t)i * a.ldc + j) = v;
+                if (a.mode == GEMM_UPPER_MIRROR) {
+                    a.C[(size_t)j * a.ldc + i] = v.x;
+                    a.C[(size_t)(j + 1) * a.ldc + i] = v.y;
+                }
+            }
+        }
+        return;
+    }
 #pragma unroll
     for (int mt = 0; mt < 8; mt++) {
         const int i = row0 + wm * 64 + mt * 8 + g;
         if (i >= a.n) continue;
+        double cin[4][2];
+        if (a.Cin) {
+#pragma unroll
+            for (int nt = 0; nt < 4; nt++)
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const int j = col0 + wn * 32 + nt * 8 + tg * 2 + e;
+                    const bool need = (j < a.m) && !(a.mode == GEMM_UPPER_MIRROR && diag_tile && i > j);
+                    cin[nt][e] = need ? a.Cin[(size_t)i * a.ldcin + j] : 0.0;
+                }
+        }
 #pragma unroll
         for (int nt = 0; nt < 4; nt++) {
 #pragma unroll
@@ -173,7 +213,7 @@ __global__ void __launch_bounds__(256, 1) gemm_nt_dmma_kernel(const GemmArgs a) 
                 if (j >= a.m) continue;
                 if (a.mode == GEMM_UPPER_MIRROR && diag_tile && i > j) continue;
                 double v = acc[mt][nt][e];
-                if (a.Cin) v += a.beta * a.Cin[(size_t)i * a.ldcin + j];
+                if (a.Cin) v += a.beta * cin[nt][e];
                 if (i == j) v += a.shift + (a.dadd ? a.dadd[i] : 0.0);
                 a.C[(size_t)i * a.ldc + j] = v;
                 if (a.mode == GEMM_UPPER_MIRROR && i != j) a.C[(size_t)j * a.ldc + i] = v;

@@ -74,23 +74,31 @@ inline void ldlt_free(LdltWs& w) {
 }
 
 // ------------------------------------------------------------------------------------------- tile kernel
-// One CTA (256 threads).  T (symmetric, both triangles kept bitwise equal) and X (running L^-1) live in smem.
-__global__ void __launch_bounds__(256) ldlt_tile_kernel(double* __restrict__ A, int ld, int nb, double* __restrict__ LinvP,
-                                                        double* __restrict__ dinv_a, double* __restrict__ dinv_b,
-                                                        double* __restrict__ d_a, double* __restrict__ d_b,
-                                                        int* __restrict__ kind, int* __restrict__ perm_out,
-                                                        int* __restrict__ counts, double* __restrict__ dstat) {
+// One CTA, 1024 threads.  T (symmetric, both triangles kept bitwise equal) and X (running L^-1) live in smem.
+// The 64 pivot steps are a serial chain, so the kernel is organised for latency, not throughput:
+//   * 32 warps, warp w owns rows w and w+32, lanes own columns lane and lane+32 (per-warp work per step is ~60
+//     instructions, 8 warps per scheduler hide the LDS/DFMA latencies);
+//   * EVERY warp runs the (cheap) pivot search redundantly, so a step needs ONE barrier, not two;
+//   * the column arg-max runs on the IEEE bit pattern of |v| with three redux.sync instead of a shuffle tree;
+//   * updates read the pivot ROW(s), which stay intact during the step (multipliers go to COLUMN j): no
+//     staging buffer, all smem loads are issued before the first store.
+constexpr int TILE_THREADS = 1024;
+__global__ void __launch_bounds__(TILE_THREADS) ldlt_tile_kernel(double* __restrict__ A, int ld, int nb,
+                                                                 double* __restrict__ LinvP, double* __restrict__ dinv_a,
+                                                                 double* __restrict__ dinv_b, double* __restrict__ d_a,
+                                                                 double* __restrict__ d_b, int* __restrict__ kind,
+                                                                 int* __restrict__ perm_out, int* __restrict__ counts,
+                                                                 double* __restrict__ dstat) {
     extern __shared__ __align__(16) double tsm[];
     double(*T)[NBP] = reinterpret_cast<double(*)[NBP]>(tsm);
     double(*X)[NBP] = reinterpret_cast<double(*)[NBP]>(tsm + NB * NBP);
     __shared__ double sda[NB], sdb[NB];
     __shared__ int sperm[NB], skind[NB];
-    __shared__ int s_kp, s_kstep;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double BK_ALPHA = 0.6403882032022076;   // (1 + sqrt(17)) / 8
 
     // load the tile from its LOWER triangle, mirror, identity-pad to NB
-    for (int idx = tid; idx < NB * NB; idx += 256) {
+    for (int idx = tid; idx < NB * NB; idx += TILE_THREADS) {
         const int i = idx / NB, j = idx % NB;
         double v;
         if (i < nb && j < nb) {
@@ -109,46 +117,56 @@ __global__ void __launch_bounds__(256) ldlt_tile_kernel(double* __restrict__ A, 
     }
     __syncthreads();
 
+    const int m0 = lane, m1 = lane + 32;
+    const int ra = warp, rb = warp + 32;
     int j = 0;
     while (j < nb) {
-        // ---- pivot selection (warp 0), LAPACK dsytf2 logic restricted to the tile
-        if (warp == 0) {
+        // ---- pivot selection, LAPACK dsytf2 logic restricted to the tile (identical in every warp)
+        int kp = j, kstep = 1;
+        {
             const double absakk = fabs(T[j][j]);
+            const int i0 = j + 1 + lane, i1 = i0 + 32;
             double cm = -1.0;
             int r = j;
-            for (int i = j + 1 + lane; i < nb; i += 32) {
-                const double v = fabs(T[i][j]);
-                if (v > cm) { cm = v; r = i; }
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const double ocm = __shfl_xor_sync(0xffffffffu, cm, o);
-                const int orr = __shfl_xor_sync(0xffffffffu, r, o);
-                if (ocm > cm || (ocm == cm && orr < r)) { cm = ocm; r = orr; }
-            }
-            const double colmax = (cm < 0.0) ? 0.0 : cm;
-            int kp = j, kstep = 1;
+            // column j is read through ROW j (T is bitwise symmetric): row j is never written during the step, so
+            // a warp that is still searching cannot see another warp's update
+            if (i0 < nb) { cm = fabs(T[j][i0]); r = i0; }
+            if (i1 < nb) { const double v = fabs(T[j][i1]); if (v > cm) { cm = v; r = i1; } }
+            const bool have = (cm >= 0.0);
+            const unsigned long long bits = have ? (unsigned long long)__double_as_longlong(cm) : 0ull;
+            const unsigned hi = (unsigned)(bits >> 32), lo = (unsigned)bits;
+            const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+            const unsigned ml = __reduce_max_sync(0xffffffffu, (hi == mh) ? lo : 0u);
+            const unsigned cand = (have && hi == mh && lo == ml) ? (unsigned)r : 0xffffu;
+            const unsigned rsel = __reduce_min_sync(0xffffffffu, cand);
+            const double colmax = __longlong_as_double((long long)(((unsigned long long)mh << 32) | ml));
+            r = (rsel == 0xffffu) ? j : (int)rsel;
             if (!(fmax(absakk, colmax) == 0.0) && absakk < BK_ALPHA * colmax) {
                 double rm = 0.0;
-                for (int i = j + lane; i < nb; i += 32)
-                    if (i != r) rm = fmax(rm, fabs(T[i][r]));
-                rm = warp_max(rm);
+                const int a0 = j + lane, a1 = a0 + 32;
+                if (a0 < nb && a0 != r) rm = fabs(T[r][a0]);
+                if (a1 < nb && a1 != r) rm = fmax(rm, fabs(T[r][a1]));
+                const double arr = fabs(T[r][r]);
+                __syncthreads();   // row r IS written by the update: nobody may start updating before all have read it
+                const unsigned long long rbits = (unsigned long long)__double_as_longlong(rm);
+                const unsigned rh = (unsigned)(rbits >> 32), rl = (unsigned)rbits;
+                const unsigned xh = __reduce_max_sync(0xffffffffu, rh);
+                const unsigned xl = __reduce_max_sync(0xffffffffu, (rh == xh) ? rl : 0u);
+                rm = __longlong_as_double((long long)(((unsigned long long)xh << 32) | xl));
                 if (absakk * rm >= BK_ALPHA * colmax * colmax) {
                     kp = j;
-                } else if (fabs(T[r][r]) >= BK_ALPHA * rm) {
+                } else if (arr >= BK_ALPHA * rm) {
                     kp = r;
                 } else {
                     kp = r;
                     kstep = 2;
                 }
             }
-            if (lane == 0) { s_kp = kp; s_kstep = kstep; }
         }
-        __syncthreads();
-        const int kp = s_kp, kstep = s_kstep;
         const int kk = j + kstep - 1;
-        // ---- symmetric interchange kk <-> kp on T and X (rows, then columns)
+        // ---- symmetric interchange kk <-> kp on T and X (rows, then columns); rare on IPM matrices
         if (kp != kk) {
+            __syncthreads();   // every warp finished reading the unswapped tile for its pivot search
             if (tid < NB) {
                 double t0 = T[kk][tid]; T[kk][tid] = T[kp][tid]; T[kp][tid] = t0;
                 double x0 = X[kk][tid]; X[kk][tid] = X[kp][tid]; X[kp][tid] = x0;
@@ -161,29 +179,29 @@ __global__ void __launch_bounds__(256) ldlt_tile_kernel(double* __restrict__ A, 
             if (tid == 0) { int p = sperm[kk]; sperm[kk] = sperm[kp]; sperm[kp] = p; }
             __syncthreads();
         }
-        // ---- elimination.  Fixed ownership: warp w owns rows w, w+8, ...; lanes own columns lane, lane+32.
-        // Everybody reads the pivot ROW(s) j (, j+1), which stay intact during the step (the multipliers are
-        // written into COLUMN j), so no staging buffer and no barrier is needed inside the step.  Products are
-        // formed as (u_i*u_m)*dinv so T stays bitwise symmetric.
+        // ---- elimination
         if (kstep == 1) {
             const double d = T[j][j];
             if (tid == 0) { sda[j] = d; sdb[j] = 0.0; skind[j] = 0; }
-            if (d != 0.0) {
+            if (d != 0.0 && rb > j) {
                 const double dinv = 1.0 / d;
-#pragma unroll
-                for (int rr = 0; rr < 8; rr++) {
-                    const int i = warp + 8 * rr;
-                    if (i > j && i < nb) {
-                        const double ui = T[j][i];
-                        const double li = ui * dinv;
-#pragma unroll
-                        for (int hh = 0; hh < 2; hh++) {
-                            const int m = lane + 32 * hh;
-                            if (m > j && m < nb) T[i][m] -= (ui * T[j][m]) * dinv;
-                            if (m <= j) X[i][m] -= li * X[j][m];
-                        }
-                        if (lane == 0) T[i][j] = li;
-                    }
+                const double tj0 = T[j][m0], tj1 = T[j][m1], xj0 = X[j][m0], xj1 = X[j][m1];
+                const double ua = T[j][ra], ub = T[j][rb];
+                const double ta0 = T[ra][m0], ta1 = T[ra][m1], xa0 = X[ra][m0], xa1 = X[ra][m1];
+                const double tb0 = T[rb][m0], tb1 = T[rb][m1], xb0 = X[rb][m0], xb1 = X[rb][m1];
+                if (ra > j && ra < nb) {
+                    const double li = ua * dinv;
+                    if (m0 > j) { if (m0 < nb) T[ra][m0] = ta0 - (ua * tj0) * dinv; }
+                    else { X[ra][m0] = xa0 - li * xj0; if (m0 == j) T[ra][m0] = li; }
+                    if (m1 > j) { if (m1 < nb) T[ra][m1] = ta1 - (ua * tj1) * dinv; }
+                    else { X[ra][m1] = xa1 - li * xj1; if (m1 == j) T[ra][m1] = li; }
+                }
+                if (rb < nb) {
+                    const double li = ub * dinv;
+                    if (m0 > j) { if (m0 < nb) T[rb][m0] = tb0 - (ub * tj0) * dinv; }
+                    else { X[rb][m0] = xb0 - li * xj0; if (m0 == j) T[rb][m0] = li; }
+                    if (m1 > j) { if (m1 < nb) T[rb][m1] = tb1 - (ub * tj1) * dinv; }
+                    else { X[rb][m1] = xb1 - li * xj1; if (m1 == j) T[rb][m1] = li; }
                 }
             }
         } else {
@@ -192,27 +210,39 @@ __global__ void __launch_bounds__(256) ldlt_tile_kernel(double* __restrict__ A, 
                 sda[j] = a11; sdb[j] = a21; sda[j + 1] = a22; sdb[j + 1] = 0.0;
                 skind[j] = 1; skind[j + 1] = 2;
             }
-            // LAPACK's scaled 2x2 inverse (dsytf2): robust against overflow of the determinant
-            const double d11 = a22 / a21, d22 = a11 / a21;
-            const double tt = 1.0 / (d11 * d22 - 1.0);
-            const double d21i = tt / a21;
+            if (rb > j + 1) {
+                // LAPACK's scaled 2x2 inverse (dsytf2): robust against overflow of the determinant
+                const double d11 = a22 / a21, d22 = a11 / a21;
+                const double tt = 1.0 / (d11 * d22 - 1.0);
+                const double d21i = tt / a21;
+                const double tj0 = T[j][m0], tj1 = T[j][m1], tk0 = T[j + 1][m0], tk1 = T[j + 1][m1];
+                const double xj0 = X[j][m0], xj1 = X[j][m1], xk0 = X[j + 1][m0], xk1 = X[j + 1][m1];
+                const double ua = T[j][ra], va = T[j + 1][ra], ub = T[j][rb], vb = T[j + 1][rb];
+                const double ta0 = T[ra][m0], ta1 = T[ra][m1], xa0 = X[ra][m0], xa1 = X[ra][m1];
+                const double tb0 = T[rb][m0], tb1 = T[rb][m1], xb0 = X[rb][m0], xb1 = X[rb][m1];
 #pragma unroll
-            for (int rr = 0; rr < 8; rr++) {
-                const int i = warp + 8 * rr;
-                if (i > j + 1 && i < nb) {
-                    const double u = T[j][i], v = T[j + 1][i];
-                    const double l1 = d21i * (d11 * u - v);
-                    const double l2 = d21i * (d22 * v - u);
-#pragma unroll
-                    for (int hh = 0; hh < 2; hh++) {
-                        const int m = lane + 32 * hh;
-                        if (m > j + 1 && m < nb) {
-                            const double um = T[j][m], vm = T[j + 1][m];
-                            T[i][m] -= d21i * ((d11 * (u * um) + d22 * (v * vm)) - (v * um + u * vm));
+                for (int half = 0; half < 2; half++) {
+                    const int i = half ? rb : ra;
+                    const double u = half ? ub : ua, v = half ? vb : va;
+                    const double t0 = half ? tb0 : ta0, t1 = half ? tb1 : ta1, x0 = half ? xb0 : xa0, x1 = half ? xb1 : xa1;
+                    if (i > j + 1 && i < nb) {
+                        const double l1 = d21i * (d11 * u - v);
+                        const double l2 = d21i * (d22 * v - u);
+                        if (m0 > j + 1) {
+                            if (m0 < nb) T[i][m0] = t0 - d21i * ((d11 * (u * tj0) + d22 * (v * tk0)) - (v * tj0 + u * tk0));
+                        } else {
+                            X[i][m0] = x0 - (l1 * xj0 + l2 * xk0);
+                            if (m0 == j) T[i][m0] = l1;
+                            if (m0 == j + 1) T[i][m0] = l2;
                         }
-                        if (m <= j + 1) X[i][m] -= l1 * X[j][m] + l2 * X[j + 1][m];
+                        if (m1 > j + 1) {
+                            if (m1 < nb) T[i][m1] = t1 - d21i * ((d11 * (u * tj1) + d22 * (v * tk1)) - (v * tj1 + u * tk1));
+                        } else {
+                            X[i][m1] = x1 - (l1 * xj1 + l2 * xk1);
+                            if (m1 == j) T[i][m1] = l1;
+                            if (m1 == j + 1) T[i][m1] = l2;
+                        }
                     }
-                    if (lane == 0) { T[i][j] = l1; T[i][j + 1] = l2; }
                 }
             }
             // (T[j+1][j] keeps a21 until the output stage: other warps may still be reading it)
@@ -223,12 +253,12 @@ __global__ void __launch_bounds__(256) ldlt_tile_kernel(double* __restrict__ A, 
 
     // ---- outputs
     // LinvP[r][perm[m]] = X[r][m]   (column scatter folds the permutation into the inverse)
-    for (int idx = tid; idx < NB * NB; idx += 256) {
+    for (int idx = tid; idx < NB * NB; idx += TILE_THREADS) {
         const int r = idx / NB, m = idx % NB;
         LinvP[r * NB + sperm[m]] = (m <= r) ? X[r][m] : 0.0;
     }
     // L back into the strictly-lower part of the tile, D on the diagonal (diagnostics / tests)
-    for (int idx = tid; idx < nb * nb; idx += 256) {
+    for (int idx = tid; idx < nb * nb; idx += TILE_THREADS) {
         const int i = idx / nb, jj = idx % nb;
         if (i > jj) A[(size_t)i * ld + jj] = (skind[jj] == 1 && i == jj + 1) ? 0.0 : T[i][jj];
         else if (i == jj) A[(size_t)i * ld + jj] = sda[i];
@@ -259,10 +289,11 @@ __global__ void __launch_bounds__(256) ldlt_tile_kernel(double* __restrict__ A, 
         kind[p] = (p < nb) ? skind[p] : 0;
         if (perm_out) perm_out[p] = sperm[p];
     }
-    if (tid == 0) {
+    // inertia and |eig(D)| extremes: one warp, two positions per lane
+    if (warp == 0) {
         int neg = 0, zero = 0, pos = 0;
-        double mn = dstat[0], mx = dstat[1];
-        for (int p = 0; p < nb; p++) {
+        double mn = INFINITY, mx = 0.0;
+        for (int p = lane; p < nb; p += 32) {
             if (skind[p] == 0) {
                 const double d = sda[p];
                 if (d > 0.0) pos++; else if (d < 0.0) neg++; else zero++;
@@ -277,8 +308,15 @@ __global__ void __launch_bounds__(256) ldlt_tile_kernel(double* __restrict__ A, 
                 mn = fmin(mn, fmin(fabs(e1), fabs(e2))); mx = fmax(mx, fmax(fabs(e1), fabs(e2)));
             }
         }
-        counts[0] += neg; counts[1] += zero; counts[2] += pos;
-        dstat[0] = mn; dstat[1] = mx;
+        neg = __reduce_add_sync(0xffffffffu, neg);
+        zero = __reduce_add_sync(0xffffffffu, zero);
+        pos = __reduce_add_sync(0xffffffffu, pos);
+        mn = warp_min(mn);
+        mx = warp_max(mx);
+        if (lane == 0) {
+            counts[0] += neg; counts[1] += zero; counts[2] += pos;
+            dstat[0] = fmin(dstat[0], mn); dstat[1] = fmax(dstat[1], mx);
+        }
     }
 }
 
@@ -389,7 +427,7 @@ inline int ldlt_factor(LdltWs& w) {
             const int k = k0 / NB, nb = min(NB, n - k0), k1 = k0 + nb;
             double* Akk = w.A + (size_t)k0 * ld + k0;
             double* Lk = w.LinvP + (size_t)k * NB * NB;
-            ldlt_tile_kernel<<<1, 256, TILE_SMEM, st>>>(Akk, ld, nb, Lk, ia + k0, ib + k0, da + k0, db + k0, w.kind + k0,
+            ldlt_tile_kernel<<<1, TILE_THREADS, TILE_SMEM, st>>>(Akk, ld, nb, Lk, ia + k0, ib + k0, da + k0, db + k0, w.kind + k0,
                                                         nullptr, w.counts, w.dstat);
             LAUNCHED();
             const int rows = n - k1;
