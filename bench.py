@@ -34,6 +34,10 @@ WORKLOAD = 'config3: synthetic nonconvex NLP n=4096, 512 eq + 4096 ineq, dense d
 D3, M3, N3 = 4096, 512, 4096
 K3 = D3 + 2 * N3 + M3
 PRE_STEPS = 3   # real Newton steps taken from x0 before the teacher-forced state is snapshotted
+# diagonal shift reghess settles on for the CPU sample state below (found once with the oracle itself: 10 eigvalsh
+# calls, delta0 * 10^8); starting the sample at 2x this value makes every sampled step do the typical mid-solve
+# work of two inertia tests (delta = 0 rejected, delta/2 accepted) instead of the 10-test discovery.
+DELTA_SAMPLE = 1.4901161193847656
 
 
 def measured_peaks():
@@ -122,18 +126,13 @@ def run_reference(args):
     K = prob.nvar + 2 * prob.nineq + prob.neq
     scale = (float(K3) / K) ** 3
     times = []
-    delta_warm = None
     with np.errstate(all='ignore'):
         for it in range(args.warmup + args.steps):
-            # the first (warm-up) step finds delta from scratch; timed steps start from delta_found*2 so that
-            # reghess halves it back and does its typical two inertia tests
-            o.delta = np.float64(0.0) if delta_warm is None else np.float64(2.0 * delta_warm)
+            o.delta = np.float64(2.0 * DELTA_SAMPLE)
             o.timers = {}
             t0 = time.perf_counter()
             o.newton_step(x.copy(), s.copy(), lda.copy())
             dt = time.perf_counter() - t0
-            if delta_warm is None:
-                delta_warm = float(o.delta)
             if it >= args.warmup:
                 times.append(dt)
     t_sample = float(np.mean(times))
@@ -296,17 +295,18 @@ def run_b200(args):
             K = sprob.nvar + 2 * sprob.nineq + sprob.neq
             scale = (float(K3) / K) ** 3
             with np.errstate(all='ignore'):
-                o.delta = np.float64(0.0)
-                o.newton_step(x.copy(), s.copy(), lda.copy())          # finds delta (untimed)
-                o.delta = np.float64(2.0 * float(o.delta))
-                o.timers = {}
-                t0 = time.perf_counter()
-                o.newton_step(x.copy(), s.copy(), lda.copy())
-                t_sample = time.perf_counter() - t0
+                ts = []
+                for _ in range(3):
+                    o.delta = np.float64(2.0 * DELTA_SAMPLE)
+                    o.timers = {}
+                    t0 = time.perf_counter()
+                    o.newton_step(x.copy(), s.copy(), lda.copy())
+                    ts.append(time.perf_counter() - t0)
+                t_sample = float(np.median(ts))
             line['cpu_baseline'] = {
                 'value': 1.0 / (t_sample * scale), 'unit': 'steps/s', 'cores': os.cpu_count(), 'kind': 'port',
-                'sample': 'one oracle Newton step on the same NLP family at n=1024 (K=%d): %.2f s (%d eigvalsh + 1 LU), '
-                          'scaled to config 3 by (K3/K)^3 = %.0f' % (K, t_sample, o.last_reg['n_eig'], scale),
+                'sample': 'oracle Newton step on the same NLP family at n=1024 (K=%d): median of 3 = %.2f s (%d eigvalsh + '
+                          '1 LU each), scaled to config 3 by (K3/K)^3 = %.0f' % (K, t_sample, o.last_reg['n_eig'], scale),
                 'split_s': {k: v for k, v in o.timers.items() if k != 'steps'}}
         print(json.dumps(line))
     if world > 1:
@@ -324,10 +324,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':
-        if args.steps > 4:
-            args.steps = 4      # each reference step is a ~10-30 s bounded CPU sample
-        args.warmup = min(args.warmup, 1)
-        return run_reference(args)
+        return run_reference(args)    # each step is a ~3-6 s bounded CPU sample (see oracle_sample_step)
     args.warmup = max(args.warmup, 3)
     return run_b200(args)
 

@@ -75,14 +75,53 @@ inline void ldlt_free(LdltWs& w) {
 
 // ------------------------------------------------------------------------------------------- tile kernel
 // One CTA, 1024 threads.  T (symmetric, both triangles kept bitwise equal) and X (running L^-1) live in smem.
-// The 64 pivot steps are a serial chain, so the kernel is organised for latency, not throughput:
-//   * 32 warps, warp w owns rows w and w+32, lanes own columns lane and lane+32 (per-warp work per step is ~60
-//     instructions, 8 warps per scheduler hide the LDS/DFMA latencies);
-//   * EVERY warp runs the (cheap) pivot search redundantly, so a step needs ONE barrier, not two;
-//   * the column arg-max runs on the IEEE bit pattern of |v| with three redux.sync instead of a shuffle tree;
-//   * updates read the pivot ROW(s), which stay intact during the step (multipliers go to COLUMN j): no
-//     staging buffer, all smem loads are issued before the first store.
+// The 64 pivot steps are a serial chain, so the kernel is organised for latency and instruction count:
+//   * 32 warps, warp w owns rows w and w+32, lanes own columns lane and lane+32;
+//   * for column m a step touches EITHER T (m beyond the pivot) OR X (m up to the pivot), never both, so the
+//     update is one fused pass over the augmented matrix [X | T] with a per-lane base pointer;
+//   * updates read the pivot ROW(s), which stay intact during the step (multipliers go to COLUMN j): no staging,
+//     all smem loads are issued before the first store;
+//   * software pipeline: the warp that owns the NEXT pivot row runs the Bunch-Kaufman search on the freshly
+//     updated values it still holds in registers (three redux.sync on the IEEE bit pattern of |v|) and
+//     publishes the decision (and 1/d) while the other warps are still updating => ONE barrier per step.
+//     Only the rare second-level test (needs row r, owned by another warp) costs two extra barriers.
 constexpr int TILE_THREADS = 1024;
+struct TileDec { int kp, kstep, need2, r; double absakk, colmax, dinv; };
+
+__device__ __forceinline__ double warp_absmax_bits(double v) {   // max of non-negative doubles via redux.sync
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    const unsigned h = (unsigned)(b >> 32), l = (unsigned)b;
+    const unsigned mh = __reduce_max_sync(0xffffffffu, h);
+    const unsigned ml = __reduce_max_sync(0xffffffffu, (h == mh) ? l : 0u);
+    return __longlong_as_double((long long)(((unsigned long long)mh << 32) | ml));
+}
+// First-level Bunch-Kaufman test for pivot row jn, executed by ONE warp.  v0/v1 are T[jn][lane], T[jn][lane+32].
+__device__ __forceinline__ void tile_search(int jn, int nb, int lane, double v0, double v1, TileDec* out) {
+    const double BK_ALPHA = 0.6403882032022076;   // (1 + sqrt(17)) / 8
+    const double djj = __shfl_sync(0xffffffffu, (jn < 32) ? v0 : v1, jn & 31);
+    const double absakk = fabs(djj);
+    const int c0 = lane, c1 = lane + 32;
+    double cm = -1.0;
+    int r = jn;
+    if (c0 > jn && c0 < nb) { cm = fabs(v0); r = c0; }
+    if (c1 > jn && c1 < nb) { const double v = fabs(v1); if (v > cm) { cm = v; r = c1; } }
+    const bool have = (cm >= 0.0);
+    const unsigned long long bits = have ? (unsigned long long)__double_as_longlong(cm) : 0ull;
+    const unsigned hi = (unsigned)(bits >> 32), lo = (unsigned)bits;
+    const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned ml = __reduce_max_sync(0xffffffffu, (hi == mh) ? lo : 0u);
+    const unsigned cand = (have && hi == mh && lo == ml) ? (unsigned)r : 0xffffu;
+    const unsigned rsel = __reduce_min_sync(0xffffffffu, cand);
+    const double colmax = __longlong_as_double((long long)(((unsigned long long)mh << 32) | ml));
+    if (lane == 0) {
+        TileDec d;
+        d.kp = jn; d.kstep = 1; d.need2 = 0; d.r = (rsel == 0xffffu) ? jn : (int)rsel;
+        d.absakk = absakk; d.colmax = colmax; d.dinv = (djj != 0.0) ? 1.0 / djj : 0.0;
+        if (!(fmax(absakk, colmax) == 0.0) && absakk < BK_ALPHA * colmax) d.need2 = 1;
+        *out = d;
+    }
+}
+
 __global__ void __launch_bounds__(TILE_THREADS) ldlt_tile_kernel(double* __restrict__ A, int ld, int nb,
                                                                  double* __restrict__ LinvP, double* __restrict__ dinv_a,
                                                                  double* __restrict__ dinv_b, double* __restrict__ d_a,
@@ -90,12 +129,14 @@ __global__ void __launch_bounds__(TILE_THREADS) ldlt_tile_kernel(double* __restr
                                                                  int* __restrict__ perm_out, int* __restrict__ counts,
                                                                  double* __restrict__ dstat) {
     extern __shared__ __align__(16) double tsm[];
-    double(*T)[NBP] = reinterpret_cast<double(*)[NBP]>(tsm);
-    double(*X)[NBP] = reinterpret_cast<double(*)[NBP]>(tsm + NB * NBP);
+    double* Tf = tsm;                 // T[i][m] = Tf[i * NBP + m]
+    double* Xf = tsm + NB * NBP;      // X[i][m] = Xf[i * NBP + m]
     __shared__ double sda[NB], sdb[NB];
     __shared__ int sperm[NB], skind[NB];
+    __shared__ TileDec sdec[2];
+    __shared__ TileDec sdec2;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const double BK_ALPHA = 0.6403882032022076;   // (1 + sqrt(17)) / 8
+    const double BK_ALPHA = 0.6403882032022076;
 
     // load the tile from its LOWER triangle, mirror, identity-pad to NB
     for (int idx = tid; idx < NB * NB; idx += TILE_THREADS) {
@@ -106,8 +147,8 @@ __global__ void __launch_bounds__(TILE_THREADS) ldlt_tile_kernel(double* __restr
         } else {
             v = (i == j) ? 1.0 : 0.0;
         }
-        T[i][j] = v;
-        X[i][j] = (i == j) ? 1.0 : 0.0;
+        Tf[i * NBP + j] = v;
+        Xf[i * NBP + j] = (i == j) ? 1.0 : 0.0;
     }
     if (tid < NB) {
         sperm[tid] = tid;
@@ -116,151 +157,132 @@ __global__ void __launch_bounds__(TILE_THREADS) ldlt_tile_kernel(double* __restr
         sdb[tid] = 0.0;
     }
     __syncthreads();
-
     const int m0 = lane, m1 = lane + 32;
     const int ra = warp, rb = warp + 32;
-    int j = 0;
+    if (warp == 0) tile_search(0, nb, lane, Tf[m0], Tf[m1], &sdec[0]);
+    __syncthreads();
+
+    int j = 0, par = 0;
     while (j < nb) {
-        // ---- pivot selection, LAPACK dsytf2 logic restricted to the tile (identical in every warp)
-        int kp = j, kstep = 1;
-        {
-            const double absakk = fabs(T[j][j]);
-            const int i0 = j + 1 + lane, i1 = i0 + 32;
-            double cm = -1.0;
-            int r = j;
-            // column j is read through ROW j (T is bitwise symmetric): row j is never written during the step, so
-            // a warp that is still searching cannot see another warp's update
-            if (i0 < nb) { cm = fabs(T[j][i0]); r = i0; }
-            if (i1 < nb) { const double v = fabs(T[j][i1]); if (v > cm) { cm = v; r = i1; } }
-            const bool have = (cm >= 0.0);
-            const unsigned long long bits = have ? (unsigned long long)__double_as_longlong(cm) : 0ull;
-            const unsigned hi = (unsigned)(bits >> 32), lo = (unsigned)bits;
-            const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
-            const unsigned ml = __reduce_max_sync(0xffffffffu, (hi == mh) ? lo : 0u);
-            const unsigned cand = (have && hi == mh && lo == ml) ? (unsigned)r : 0xffffu;
-            const unsigned rsel = __reduce_min_sync(0xffffffffu, cand);
-            const double colmax = __longlong_as_double((long long)(((unsigned long long)mh << 32) | ml));
-            r = (rsel == 0xffffu) ? j : (int)rsel;
-            if (!(fmax(absakk, colmax) == 0.0) && absakk < BK_ALPHA * colmax) {
-                double rm = 0.0;
+        TileDec dec = sdec[par];
+        if (dec.need2) {
+            // second-level test (LAPACK dsytf2): needs row r, which is stable now (we are right after a barrier)
+            if (warp == 0) {
+                const int r = dec.r;
                 const int a0 = j + lane, a1 = a0 + 32;
-                if (a0 < nb && a0 != r) rm = fabs(T[r][a0]);
-                if (a1 < nb && a1 != r) rm = fmax(rm, fabs(T[r][a1]));
-                const double arr = fabs(T[r][r]);
-                __syncthreads();   // row r IS written by the update: nobody may start updating before all have read it
-                const unsigned long long rbits = (unsigned long long)__double_as_longlong(rm);
-                const unsigned rh = (unsigned)(rbits >> 32), rl = (unsigned)rbits;
-                const unsigned xh = __reduce_max_sync(0xffffffffu, rh);
-                const unsigned xl = __reduce_max_sync(0xffffffffu, (rh == xh) ? rl : 0u);
-                rm = __longlong_as_double((long long)(((unsigned long long)xh << 32) | xl));
-                if (absakk * rm >= BK_ALPHA * colmax * colmax) {
-                    kp = j;
-                } else if (arr >= BK_ALPHA * rm) {
-                    kp = r;
-                } else {
-                    kp = r;
-                    kstep = 2;
+                double rm = 0.0;
+                if (a0 < nb && a0 != r) rm = fabs(Tf[r * NBP + a0]);
+                if (a1 < nb && a1 != r) rm = fmax(rm, fabs(Tf[r * NBP + a1]));
+                rm = warp_absmax_bits(rm);
+                if (lane == 0) {
+                    TileDec d2 = dec;
+                    d2.need2 = 0;
+                    if (dec.absakk * rm >= BK_ALPHA * dec.colmax * dec.colmax) { d2.kp = j; d2.kstep = 1; }
+                    else if (fabs(Tf[r * NBP + r]) >= BK_ALPHA * rm) { d2.kp = r; d2.kstep = 1; }
+                    else { d2.kp = r; d2.kstep = 2; }
+                    sdec2 = d2;
                 }
             }
+            __syncthreads();
+            dec = sdec2;
         }
+        const int kp = dec.kp, kstep = dec.kstep;
         const int kk = j + kstep - 1;
         // ---- symmetric interchange kk <-> kp on T and X (rows, then columns); rare on IPM matrices
         if (kp != kk) {
-            __syncthreads();   // every warp finished reading the unswapped tile for its pivot search
+            __syncthreads();
             if (tid < NB) {
-                double t0 = T[kk][tid]; T[kk][tid] = T[kp][tid]; T[kp][tid] = t0;
-                double x0 = X[kk][tid]; X[kk][tid] = X[kp][tid]; X[kp][tid] = x0;
+                double t0 = Tf[kk * NBP + tid]; Tf[kk * NBP + tid] = Tf[kp * NBP + tid]; Tf[kp * NBP + tid] = t0;
+                double x0 = Xf[kk * NBP + tid]; Xf[kk * NBP + tid] = Xf[kp * NBP + tid]; Xf[kp * NBP + tid] = x0;
             }
             __syncthreads();
             if (tid < NB) {
-                double t0 = T[tid][kk]; T[tid][kk] = T[tid][kp]; T[tid][kp] = t0;
-                double x0 = X[tid][kk]; X[tid][kk] = X[tid][kp]; X[tid][kp] = x0;
+                double t0 = Tf[tid * NBP + kk]; Tf[tid * NBP + kk] = Tf[tid * NBP + kp]; Tf[tid * NBP + kp] = t0;
+                double x0 = Xf[tid * NBP + kk]; Xf[tid * NBP + kk] = Xf[tid * NBP + kp]; Xf[tid * NBP + kp] = x0;
             }
             if (tid == 0) { int p = sperm[kk]; sperm[kk] = sperm[kp]; sperm[kp] = p; }
             __syncthreads();
         }
-        // ---- elimination
+        const int jn = j + kstep;                                  // next pivot row
+        // per-lane base pointers into the augmented matrix [X | T]
+        double* P0 = (m0 > kk) ? Tf : Xf;
+        double* P1 = (m1 > kk) ? Tf : Xf;
+        double na0, na1, nb0, nb1;                                 // new values of this warp's rows
         if (kstep == 1) {
-            const double d = T[j][j];
+            const double d = Tf[j * NBP + j];
+            const double dinv = (kp == j) ? dec.dinv : ((d != 0.0) ? 1.0 / d : 0.0);
             if (tid == 0) { sda[j] = d; sdb[j] = 0.0; skind[j] = 0; }
-            if (d != 0.0 && rb > j) {
-                const double dinv = 1.0 / d;
-                const double tj0 = T[j][m0], tj1 = T[j][m1], xj0 = X[j][m0], xj1 = X[j][m1];
-                const double ua = T[j][ra], ub = T[j][rb];
-                const double ta0 = T[ra][m0], ta1 = T[ra][m1], xa0 = X[ra][m0], xa1 = X[ra][m1];
-                const double tb0 = T[rb][m0], tb1 = T[rb][m1], xb0 = X[rb][m0], xb1 = X[rb][m1];
+            const double pj0 = P0[j * NBP + m0], pj1 = P1[j * NBP + m1];
+            const double ua = Tf[j * NBP + ra], ub = Tf[j * NBP + rb];
+            na0 = P0[ra * NBP + m0]; na1 = P1[ra * NBP + m1];
+            nb0 = P0[rb * NBP + m0]; nb1 = P1[rb * NBP + m1];
+            if (d != 0.0) {
                 if (ra > j && ra < nb) {
-                    const double li = ua * dinv;
-                    if (m0 > j) { if (m0 < nb) T[ra][m0] = ta0 - (ua * tj0) * dinv; }
-                    else { X[ra][m0] = xa0 - li * xj0; if (m0 == j) T[ra][m0] = li; }
-                    if (m1 > j) { if (m1 < nb) T[ra][m1] = ta1 - (ua * tj1) * dinv; }
-                    else { X[ra][m1] = xa1 - li * xj1; if (m1 == j) T[ra][m1] = li; }
+                    na0 -= (ua * pj0) * dinv; na1 -= (ua * pj1) * dinv;
+                    P0[ra * NBP + m0] = na0; P1[ra * NBP + m1] = na1;
+                    if (m0 == j) Tf[ra * NBP + j] = ua * dinv;
+                    if (m1 == j) Tf[ra * NBP + j] = ua * dinv;
                 }
-                if (rb < nb) {
-                    const double li = ub * dinv;
-                    if (m0 > j) { if (m0 < nb) T[rb][m0] = tb0 - (ub * tj0) * dinv; }
-                    else { X[rb][m0] = xb0 - li * xj0; if (m0 == j) T[rb][m0] = li; }
-                    if (m1 > j) { if (m1 < nb) T[rb][m1] = tb1 - (ub * tj1) * dinv; }
-                    else { X[rb][m1] = xb1 - li * xj1; if (m1 == j) T[rb][m1] = li; }
+                if (rb > j && rb < nb) {
+                    nb0 -= (ub * pj0) * dinv; nb1 -= (ub * pj1) * dinv;
+                    P0[rb * NBP + m0] = nb0; P1[rb * NBP + m1] = nb1;
+                    if (m0 == j) Tf[rb * NBP + j] = ub * dinv;
+                    if (m1 == j) Tf[rb * NBP + j] = ub * dinv;
                 }
             }
         } else {
-            const double a11 = T[j][j], a21 = T[j + 1][j], a22 = T[j + 1][j + 1];
+            const double a11 = Tf[j * NBP + j], a21 = Tf[(j + 1) * NBP + j], a22 = Tf[(j + 1) * NBP + j + 1];
             if (tid == 0) {
                 sda[j] = a11; sdb[j] = a21; sda[j + 1] = a22; sdb[j + 1] = 0.0;
                 skind[j] = 1; skind[j + 1] = 2;
             }
-            if (rb > j + 1) {
-                // LAPACK's scaled 2x2 inverse (dsytf2): robust against overflow of the determinant
-                const double d11 = a22 / a21, d22 = a11 / a21;
-                const double tt = 1.0 / (d11 * d22 - 1.0);
-                const double d21i = tt / a21;
-                const double tj0 = T[j][m0], tj1 = T[j][m1], tk0 = T[j + 1][m0], tk1 = T[j + 1][m1];
-                const double xj0 = X[j][m0], xj1 = X[j][m1], xk0 = X[j + 1][m0], xk1 = X[j + 1][m1];
-                const double ua = T[j][ra], va = T[j + 1][ra], ub = T[j][rb], vb = T[j + 1][rb];
-                const double ta0 = T[ra][m0], ta1 = T[ra][m1], xa0 = X[ra][m0], xa1 = X[ra][m1];
-                const double tb0 = T[rb][m0], tb1 = T[rb][m1], xb0 = X[rb][m0], xb1 = X[rb][m1];
-#pragma unroll
-                for (int half = 0; half < 2; half++) {
-                    const int i = half ? rb : ra;
-                    const double u = half ? ub : ua, v = half ? vb : va;
-                    const double t0 = half ? tb0 : ta0, t1 = half ? tb1 : ta1, x0 = half ? xb0 : xa0, x1 = half ? xb1 : xa1;
-                    if (i > j + 1 && i < nb) {
-                        const double l1 = d21i * (d11 * u - v);
-                        const double l2 = d21i * (d22 * v - u);
-                        if (m0 > j + 1) {
-                            if (m0 < nb) T[i][m0] = t0 - d21i * ((d11 * (u * tj0) + d22 * (v * tk0)) - (v * tj0 + u * tk0));
-                        } else {
-                            X[i][m0] = x0 - (l1 * xj0 + l2 * xk0);
-                            if (m0 == j) T[i][m0] = l1;
-                            if (m0 == j + 1) T[i][m0] = l2;
-                        }
-                        if (m1 > j + 1) {
-                            if (m1 < nb) T[i][m1] = t1 - d21i * ((d11 * (u * tj1) + d22 * (v * tk1)) - (v * tj1 + u * tk1));
-                        } else {
-                            X[i][m1] = x1 - (l1 * xj1 + l2 * xk1);
-                            if (m1 == j) T[i][m1] = l1;
-                            if (m1 == j + 1) T[i][m1] = l2;
-                        }
-                    }
-                }
+            // LAPACK's scaled 2x2 inverse (dsytf2): robust against overflow of the determinant
+            const double d11 = a22 / a21, d22 = a11 / a21;
+            const double tt = 1.0 / (d11 * d22 - 1.0);
+            const double d21i = tt / a21;
+            const double pj0 = P0[j * NBP + m0], pj1 = P1[j * NBP + m1];
+            const double pk0 = P0[(j + 1) * NBP + m0], pk1 = P1[(j + 1) * NBP + m1];
+            const double ua = Tf[j * NBP + ra], va = Tf[(j + 1) * NBP + ra];
+            const double ub = Tf[j * NBP + rb], vb = Tf[(j + 1) * NBP + rb];
+            na0 = P0[ra * NBP + m0]; na1 = P1[ra * NBP + m1];
+            nb0 = P0[rb * NBP + m0]; nb1 = P1[rb * NBP + m1];
+            if (ra > kk && ra < nb) {
+                na0 -= d21i * ((d11 * (ua * pj0) + d22 * (va * pk0)) - (va * pj0 + ua * pk0));
+                na1 -= d21i * ((d11 * (ua * pj1) + d22 * (va * pk1)) - (va * pj1 + ua * pk1));
+                P0[ra * NBP + m0] = na0; P1[ra * NBP + m1] = na1;
+                if (m0 == j || m1 == j) Tf[ra * NBP + j] = d21i * (d11 * ua - va);
+                if (m0 == j + 1 || m1 == j + 1) Tf[ra * NBP + j + 1] = d21i * (d22 * va - ua);
+            }
+            if (rb > kk && rb < nb) {
+                nb0 -= d21i * ((d11 * (ub * pj0) + d22 * (vb * pk0)) - (vb * pj0 + ub * pk0));
+                nb1 -= d21i * ((d11 * (ub * pj1) + d22 * (vb * pk1)) - (vb * pj1 + ub * pk1));
+                P0[rb * NBP + m0] = nb0; P1[rb * NBP + m1] = nb1;
+                if (m0 == j || m1 == j) Tf[rb * NBP + j] = d21i * (d11 * ub - vb);
+                if (m0 == j + 1 || m1 == j + 1) Tf[rb * NBP + j + 1] = d21i * (d22 * vb - ub);
             }
             // (T[j+1][j] keeps a21 until the output stage: other warps may still be reading it)
         }
+        // ---- pipelined pivot search for the next step by the warp that owns row jn (values still in registers;
+        //      lanes whose column is <= kk hold X values there, the search only looks at columns > jn > kk)
+        if (jn < nb) {
+            if (ra == jn) tile_search(jn, nb, lane, na0, na1, &sdec[par ^ 1]);
+            else if (rb == jn) tile_search(jn, nb, lane, nb0, nb1, &sdec[par ^ 1]);
+        }
         __syncthreads();
-        j += kstep;
+        j = jn;
+        par ^= 1;
     }
 
     // ---- outputs
     // LinvP[r][perm[m]] = X[r][m]   (column scatter folds the permutation into the inverse)
     for (int idx = tid; idx < NB * NB; idx += TILE_THREADS) {
         const int r = idx / NB, m = idx % NB;
-        LinvP[r * NB + sperm[m]] = (m <= r) ? X[r][m] : 0.0;
+        LinvP[r * NB + sperm[m]] = (m <= r) ? Xf[r * NBP + m] : 0.0;
     }
     // L back into the strictly-lower part of the tile, D on the diagonal (diagnostics / tests)
     for (int idx = tid; idx < nb * nb; idx += TILE_THREADS) {
         const int i = idx / nb, jj = idx % nb;
-        if (i > jj) A[(size_t)i * ld + jj] = (skind[jj] == 1 && i == jj + 1) ? 0.0 : T[i][jj];
+        if (i > jj) A[(size_t)i * ld + jj] = (skind[jj] == 1 && i == jj + 1) ? 0.0 : Tf[i * NBP + jj];
         else if (i == jj) A[(size_t)i * ld + jj] = sda[i];
     }
     if (tid < NB) {

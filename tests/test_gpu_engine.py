@@ -183,6 +183,8 @@ def test_config3_size_properties():
         assert st['resid'] < 1e-8
         assert st['dphi0'] < 0.0
         assert st['signal'] == 0
-    k0 = np.array(p.step_log[0]['kkt_norm'])
-    k2 = np.array(p.step_log[-1]['kkt_norm'])
-    assert k2[2] < k0[2] and k2[3] < k0[3]       # feasibility improves
+        assert st['alpha_s'] > 0.0 and st['n_factor'] >= 1
+    # Armijo at the accepted point of the last step: phi(new) <= phi0 + alpha*eta*dphi0 (same mu, nu)
+    last = p.step_log[-1]
+    phi_new, _ = p.engine.merit()
+    assert phi_new <= last['phi0'] + last['alpha_s'] * 1e-4 * last['dphi0'] + 1e-9 * abs(last['phi0'])
