@@ -188,3 +188,48 @@ def test_config3_size_properties():
     last = p.step_log[-1]
     phi_new, _ = p.engine.merit()
     assert phi_new <= last['phi0'] + last['alpha_s'] * 1e-4 * last['dphi0'] + 1e-9 * abs(last['phi0'])
+
+
+@pytest.mark.parametrize('mu', [1e-1, 1e-2, 1e-4, 1e-6, 1e-8, 1e-10])
+def test_config5_mu_sweep_vs_oracle(mu):
+    """BASELINE config 5 (ill-conditioned barrier sweep) on a size the CPU oracle can handle: s_i*lda_i = mu with
+    25% active rows s_i = mu^0.9, so Sigma = lda/s spans up to ~1e8.  One teacher-forced step per mu: same
+    delta / inertia decisions as the reference's eigvalsh test, dz to 1e-6 relative, and the
+    UNREDUCED KKT residual of the refined direction small relative to the right-hand side."""
+    prob = problems.make_nlp(D=192, M=32, N=192, seed=31)
+    x, s, lda = problems.mu_sweep_state(prob, mu)
+    o = OracleIPM(x0=x.copy(), verbosity=-1, mu=mu, **prob.callables())
+    o.nvar = prob.nvar
+    o.compile()
+    o.mu_host, o.mu_dev, o.nu_host, o.nu_dev, o.delta, o.signal = mu, np.float64(mu), 10.0, np.float64(10.0), np.float64(0.0), 0
+    tr = []
+    o.trace = tr
+    with np.errstate(all='ignore'):
+        o.newton_step(x.copy(), s.copy(), lda.copy())
+    st = tr[0]
+    eng = make_engine(prob, mu=mu)
+    eng.set_state(x, s, lda, mu, 10.0, 0.0)
+    eng.set_mu_host(mu)
+    dz, info = eng.direction()
+    assert info.n_factor == st['reg']['n_eig'], (info.n_factor, st['reg']['n_eig'])
+    assert info.delta == st['delta']
+    assert info.n_neg == prob.neq and info.n_zero == 0
+    assert relinf(dz, st['dz']) < 1e-6, relinf(dz, st['dz'])
+    assert info.resid <= 1e-10 * max(1.0, np.max(np.abs(st['g'])))
+    eng.close()
+
+
+def test_config5_mu_sweep_full_size_properties():
+    """Config 5 at the full config-3 size (no CPU oracle possible): for every mu the accepted condensed matrix has
+    exactly M negative pivots and the refined direction satisfies the unreduced KKT system."""
+    prob = problems.make_nlp()
+    eng = make_engine(prob)
+    for mu in (1e-1, 1e-4, 1e-7, 1e-10):
+        x, s, lda = problems.mu_sweep_state(prob, mu)
+        eng.set_state(x, s, lda, mu, 10.0, 0.0)
+        eng.set_mu_host(mu)
+        g, _ = eng.residual()
+        dz, info = eng.direction(want_dz=False)
+        assert info.n_neg == prob.neq and info.n_zero == 0, mu
+        assert info.resid <= 1e-9 * max(1.0, np.max(np.abs(g))), (mu, info.resid)
+    eng.close()
