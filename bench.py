@@ -155,6 +155,74 @@ def run_reference(args):
     return 0
 
 
+# ------------------------------------------------------------------------------------------- config 4 (multi-GPU LDL^T)
+def run_c4(args):
+    """BASELINE config 4: dense symmetric quasi-definite KKT of order 16384, 2-D block-cyclic LDL^T over the GPUs of
+    one node (pyipm_b200/dist_ldlt.py), 8 right-hand sides.  Prints its own JSON line (not the headline metric)."""
+    import torch
+    import torch.distributed as dist
+    from pyipm_b200.dist_ldlt import BlockCyclicLDLT, CudaTileOps, choose_grid
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    n, m = args.c4_n, args.c4_n // 8
+    nh = n - m
+    g = torch.Generator(device='cuda')
+    g.manual_seed(16384)
+    W = torch.randn(nh, nh, dtype=torch.float64, device='cuda', generator=g)
+    K = torch.zeros(n, n, dtype=torch.float64, device='cuda')
+    K[:nh, :nh] = W @ W.t() / nh
+    del W
+    K[:nh, :nh].diagonal().add_(10.0 ** (8.0 * torch.rand(nh, dtype=torch.float64, device='cuda', generator=g) - 4.0))
+    J = torch.randn(nh, m, dtype=torch.float64, device='cuda', generator=g)
+    K[:nh, nh:] = J
+    K[nh:, :nh] = J.t()
+    K[nh:, nh:].diagonal().fill_(-1e-8)
+    rhs = torch.randn(8, n, dtype=torch.float64, device='cuda', generator=g)
+    grid = choose_grid(world)
+    F = BlockCyclicLDLT(n, grid, CudaTileOps(local), block=256)
+    F.load_device(K)
+    xref_res = None
+    times_f, times_s = [], []
+    for it in range(args.warmup + args.steps):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record()
+        inertia = F.factor()
+        e1.record()
+        X = F.solve_device(rhs, nrefine=1)
+        e2.record()
+        torch.cuda.synchronize()
+        tf, ts = e0.elapsed_time(e1), e1.elapsed_time(e2)
+        if world > 1:
+            t = torch.tensor([tf, ts], device='cuda', dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            tf, ts = float(t[0]), float(t[1])
+        if it >= args.warmup:
+            times_f.append(tf)
+            times_s.append(ts)
+    R = rhs - F.matvec(X)
+    resid = float(R.abs().max() / (K.abs().max() * X.abs().max()))
+    if rank == 0:
+        tf, ts = float(np.mean(times_f)), float(np.mean(times_s))
+        print(json.dumps({
+            'metric': 'kkt_factor_solve_ms', 'value': tf + ts, 'unit': 'ms', 'n_gpus': world, 'higher_is_better': False,
+            'steps': args.steps, 'warmup': args.warmup, 'scaling': 'strong', 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': 'config4: dense symmetric quasi-definite KKT order %d (%d + %d), 8 RHS, 2-D block-cyclic '
+                                   'LDL^T, grid %dx%d, block 256' % (n, nh, m, grid[0], grid[1])},
+            'factor_ms': tf, 'solve_ms_8rhs_1refine': ts, 'factor_tflops': n ** 3 / 3.0 / tf * 1e-9,
+            'inertia': list(inertia), 'inertia_expected': [nh, m, 0], 'scaled_residual_inf': resid}))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
 # ------------------------------------------------------------------------------------------- B200 arm
 def run_b200(args):
     import torch
@@ -177,7 +245,7 @@ def run_b200(args):
 
     hbm_gbs, bf16_tf, peak_kind = measured_peaks()
     prob = problems.make_nlp(D3, M3, N3)       # same seed on every rank: independent replicas of config 3
-    stream = torch.cuda.current_stream().cuda_stream
+    stream = _lib.torch_stream_handle()
     eng = _lib.Engine(D3, M3, N3, _lib.default_params(), device=local, stream=stream)
     eng.bind(prob)
     eng.set_state(prob.x0, np.ones(N3), np.zeros(M3 + N3), 0.2, 10.0, 0.0)
@@ -322,7 +390,11 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--workload', default='c3', choices=['c3', 'c4'])
+    ap.add_argument('--c4-n', type=int, default=16384)
     args = ap.parse_args()
+    if args.workload == 'c4':
+        return run_c4(args)
     if args.impl == 'reference':
         return run_reference(args)    # each step is a ~3-6 s bounded CPU sample (see oracle_sample_step)
     args.warmup = max(args.warmup, 3)

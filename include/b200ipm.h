@@ -150,8 +150,16 @@ int b200ipm_ldlt_solve(b200ipm_ldlt_handle h, double* B, int nrhs, int nrefine, 
 /* Tile-level building blocks used by the multi-GPU 2-D block-cyclic driver (pyipm_b200/dist_ldlt.py). */
 int b200ipm_ldlt_tile_factor(b200ipm_ldlt_handle h, double* tile_dev, int ld, int nb,
                              double* linv_dev, double* dblk_dev, int* perm_dev, int counts[3]);
+/* panel_dev (rows x 64, leading dimension ld) <- L = W * D^-1, w_dev (leading dimension ldw) <- W = B * LinvP^T */
 int b200ipm_ldlt_panel(b200ipm_ldlt_handle h, double* panel_dev, int ld, int rows, const double* linv_dev,
-                       const double* dblk_dev, const int* perm_dev, double* w_dev);
+                       const double* dblk_dev, const int* perm_dev, double* w_dev, int ldw);
+/* Adopt a factorisation assembled elsewhere (the replicated factor of the multi-GPU driver): A_dev holds the L
+ * panels in its strictly-lower part (n x n, leading dimension lda), linvp_dev the per-tile inverses
+ * (ceil(n/64) x 64 x 64), dinfo_dev the four D arrays [dinv_a | dinv_b | d_a | d_b] each of length
+ * 64*ceil(n/64), kind_dev the pivot kinds.  All device pointers.  Afterwards b200ipm_ldlt_solve(nrefine = 0)
+ * works on this handle. */
+int b200ipm_ldlt_import(b200ipm_ldlt_handle h, const double* A_dev, int lda, const double* linvp_dev,
+                        const double* dinfo_dev, const int* kind_dev);
 int b200ipm_gemm_nt_update(b200ipm_ldlt_handle h, double* C_dev, int ldc, int rows, int cols,
                            const double* A_dev, int lda, const double* B_dev, int ldb, int k, int lower_only);
 

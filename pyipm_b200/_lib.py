@@ -55,7 +55,7 @@ SYMBOLS = [
     'b200ipm_kkt', 'b200ipm_con_jac', 'b200ipm_hess_full', 'b200ipm_d2L', 'b200ipm_merit', 'b200ipm_init_slack',
     'b200ipm_init_lambda', 'b200ipm_update_mu', 'b200ipm_direction', 'b200ipm_step_max', 'b200ipm_newton_step',
     'b200ipm_ldlt_create', 'b200ipm_ldlt_destroy', 'b200ipm_ldlt_factor', 'b200ipm_ldlt_solve',
-    'b200ipm_ldlt_tile_factor', 'b200ipm_ldlt_panel', 'b200ipm_gemm_nt_update', 'b200ipm_test_syrk',
+    'b200ipm_ldlt_tile_factor', 'b200ipm_ldlt_panel', 'b200ipm_ldlt_import', 'b200ipm_gemm_nt_update', 'b200ipm_test_syrk',
     'b200ipm_test_gemv',
 ]
 
@@ -112,7 +112,8 @@ def load():
         'b200ipm_ldlt_factor': (i, [vp, vp, i, i, ip, dp]),
         'b200ipm_ldlt_solve': (i, [vp, vp, i, i, i]),
         'b200ipm_ldlt_tile_factor': (i, [vp, vp, i, i, vp, vp, vp, ip]),
-        'b200ipm_ldlt_panel': (i, [vp, vp, i, i, vp, vp, vp, vp]),
+        'b200ipm_ldlt_panel': (i, [vp, vp, i, i, vp, vp, vp, vp, i]),
+        'b200ipm_ldlt_import': (i, [vp, vp, i, vp, vp, vp]),
         'b200ipm_gemm_nt_update': (i, [vp, vp, i, i, i, vp, i, vp, i, i, i]),
         'b200ipm_test_syrk': (i, [i, vp, d, vp, d, i, C.POINTER(vp), C.POINTER(vp), ip, dp, vp, i,
                                   C.POINTER(C.c_float)]),
@@ -139,6 +140,15 @@ def ptr(a):
 
 def f64(a):
     return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+
+
+def torch_stream_handle(device=None):
+    """cudaStream_t of torch's CURRENT stream for the C ABI.  The legacy default stream has handle 0, which the
+    ABI reads as 'create a private stream', so it is passed as cudaStreamLegacy (0x1) instead: kernels of this
+    library are then ordered with torch ops / NCCL collectives issued on the same stream."""
+    import torch
+    h = torch.cuda.current_stream(device).cuda_stream
+    return h if h else 1
 
 
 def default_params(mu=0.2, nu=10.0, rho=0.1, tau=0.995, eta=1.0E-4, beta=0.4, Xtol=None, Ktol=1.0E-4, nrefine=2,

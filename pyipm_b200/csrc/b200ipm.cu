@@ -1167,15 +1167,30 @@ int b200ipm_ldlt_tile_factor(b200ipm_ldlt_handle h, double* tile_dev, int ld, in
     return 0;
 }
 int b200ipm_ldlt_panel(b200ipm_ldlt_handle h, double* panel_dev, int ld, int rows, const double* linv_dev,
-                       const double* dblk_dev, const int* perm_dev, double* w_dev) {
+                       const double* dblk_dev, const int* perm_dev, double* w_dev, int ldw) {
     (void)perm_dev;
     if (!h || !panel_dev || !w_dev) return fail_msg("panel: bad arguments");
     if (rows <= 0) return 0;
     CU(cudaSetDevice(h->device));
     const int* kind = reinterpret_cast<const int*>(dblk_dev + 4 * NB);
     ldlt_panel_kernel<<<cdiv(rows, NB), 128, PANEL_SMEM, h->st>>>(panel_dev, ld, rows, linv_dev, dblk_dev, dblk_dev + NB,
-                                                                   kind, w_dev, NB);
+                                                                   kind, w_dev, ldw);
     LAUNCHED();
+    return 0;
+}
+int b200ipm_ldlt_import(b200ipm_ldlt_handle h, const double* A_dev, int lda, const double* linvp_dev,
+                        const double* dinfo_dev, const int* kind_dev) {
+    if (!h || !A_dev || !linvp_dev || !dinfo_dev || !kind_dev) return fail_msg("ldlt_import: null argument");
+    CU(cudaSetDevice(h->device));
+    const int n = h->F.n, ld = h->F.ld;
+    const size_t npad = (size_t)h->F.nblk * NB;
+    CU(cudaMemcpy2DAsync(h->F.A, sizeof(double) * ld, A_dev, sizeof(double) * lda, sizeof(double) * n, n,
+                         cudaMemcpyDeviceToDevice, h->st));
+    CU(cudaMemcpyAsync(h->F.LinvP, linvp_dev, sizeof(double) * (size_t)h->F.nblk * NB * NB, cudaMemcpyDeviceToDevice, h->st));
+    CU(cudaMemcpyAsync(h->F.dinfo, dinfo_dev, sizeof(double) * 4 * npad, cudaMemcpyDeviceToDevice, h->st));
+    CU(cudaMemcpyAsync(h->F.kind, kind_dev, sizeof(int) * npad, cudaMemcpyDeviceToDevice, h->st));
+    CU(cudaStreamSynchronize(h->st));
+    h->factored = true;
     return 0;
 }
 int b200ipm_gemm_nt_update(b200ipm_ldlt_handle h, double* C_dev, int ldc, int rows, int cols, const double* A_dev, int lda,

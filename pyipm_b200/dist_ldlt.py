@@ -1,0 +1,288 @@
+"""2-D block-cyclic LDL^T of a dense symmetric (quasi-definite / KKT) matrix across the GPUs of one node.
+
+BASELINE.json config 4 / SURVEY.md section 8(e): the dense KKT solve shards only when the matrix order makes a
+panel factorisation natural (Kc >~ 16k).  One process per GPU, `torch.distributed` (NCCL over NVLink/NVSwitch)
+for the plumbing, the compute is this repo's own kernels through the C ABI (tile-pivoted Bunch-Kaufman tile
+factorisation, fused DMMA panel kernel, DMMA trailing update) -- the same building blocks as the single-GPU
+factorisation (`pyipm_b200/csrc/ldlt.cuh`), so pivoting stays inside 64 x 64 diagonal tiles and no pivot search
+ever crosses a GPU boundary.
+
+Layout: blocks of `b = 256` rows/cols; block (I, J) lives on rank (I mod P, J mod Q) of a P x Q process grid
+(rank = p * Q + q).  Every rank keeps the original local blocks (for the refinement residual) and a working copy.
+
+Per block column k:
+  1. the owner of (k, k) factors the diagonal block (4 tile steps) and broadcasts its factor data (L_kk, the
+     per-tile L^-1 P, D^-1 blocks: 0.66 MB);
+  2. the ranks of process column k mod Q turn their row blocks of the panel into L (in place) and W = L * D;
+  3. the panel (L and W, <= 67 MB at n = 16384) is broadcast from its P owners to every rank -- NVSwitch gives each
+     GPU full bandwidth to every peer, so the panel is simply replicated instead of routed along grid rows/cols;
+  4. every rank updates its own trailing blocks  A[I, J] -= W[I] * L[J]^T  (I >= J) with K = 256 DMMA launches.
+Inertia = sum of the diagonal-block counts.  The O(n^2) triangular solves are latency bound, so they are not
+distributed: the factor is already replicated by step 3, each rank adopts it (`b200ipm_ldlt_import`) and runs the
+single-launch flag-synchronised solves locally; iterative refinement uses the distributed original matrix
+(local mat-vec + one all-reduce).
+
+The tile arithmetic is behind a small `ops` object so that the block-cyclic indexing / collective logic can be
+exercised on CPU (gloo, world_size 2) with a reference implementation (tests/test_dist_ldlt_cpu.py).
+"""
+from __future__ import print_function
+
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+NB = 64
+
+
+class CudaTileOps(object):
+    """Tile arithmetic on the local GPU through libb200ipm.so (device pointers of torch tensors)."""
+
+    def __init__(self, device, block=256):
+        from . import _lib
+        assert block % NB == 0
+        self._lib = _lib
+        self.lib = _lib.load()
+        self.b = block
+        self.nt = block // NB
+        self.device = torch.device('cuda', device)
+        stream = _lib.torch_stream_handle(self.device)
+        self.ctx = _lib.DenseLDLT(NB, device=device, stream=stream)     # carries device + stream for the tile calls
+        self.tile_doubles = NB * NB + 4 * NB + NB // 2                   # LinvP + [dinv_a|dinv_b|d_a|d_b] + kind (ints)
+        self.diag_size = self.b * self.b + self.nt * self.tile_doubles + 3
+        self.perm = torch.empty(NB, dtype=torch.int32, device=self.device)
+        self.wdiag = torch.empty((self.b, self.b), dtype=torch.float64, device=self.device)
+
+    def empty(self, *shape):
+        return torch.empty(shape, dtype=torch.float64, device=self.device)
+
+    def zeros(self, *shape):
+        return torch.zeros(shape, dtype=torch.float64, device=self.device)
+
+    def _tile(self, diag, t):
+        off = self.b * self.b + t * self.tile_doubles
+        return diag[off:off + NB * NB], diag[off + NB * NB:off + self.tile_doubles]
+
+    def factor_diag(self, Akk, diag):
+        """Akk: b x b view (row stride ld) of the working matrix; factored in place; fills `diag`."""
+        b, ld = self.b, Akk.stride(0)
+        es = 8
+        base = Akk.data_ptr()
+        counts = np.zeros(3, dtype=np.int64)
+        cnt = (C.c_int * 3)()
+        for t in range(self.nt):
+            k0 = t * NB
+            linv, dblk = self._tile(diag, t)
+            self._lib.check(self.lib.b200ipm_ldlt_tile_factor(self.ctx.h, base + es * (k0 * ld + k0), ld, NB, linv.data_ptr(),
+                                                              dblk.data_ptr(), self.perm.data_ptr(), cnt))
+            counts += np.array(list(cnt))
+            rows = b - k0 - NB
+            if rows > 0:
+                pptr = base + es * ((k0 + NB) * ld + k0)
+                wptr = self.wdiag.data_ptr() + es * ((k0 + NB) * b + k0)
+                self._lib.check(self.lib.b200ipm_ldlt_panel(self.ctx.h, pptr, ld, rows, linv.data_ptr(), dblk.data_ptr(),
+                                                            None, wptr, b))
+                cptr = base + es * ((k0 + NB) * ld + (k0 + NB))
+                self._lib.check(self.lib.b200ipm_gemm_nt_update(self.ctx.h, cptr, ld, rows, rows, wptr, b, pptr, ld, NB, 1))
+        diag[:b * b].view(b, b).copy_(Akk)
+        diag[-3:] = torch.tensor(counts.astype(np.float64), device=self.device)
+
+    def panel(self, Bblk, diag):
+        """Bblk: rows x b view (row stride ld) -> overwritten with L; returns W = L * D (rows x b, contiguous)."""
+        b, ld, rows = self.b, Bblk.stride(0), Bblk.shape[0]
+        es = 8
+        W = self.empty(rows, b)
+        base, wbase, lkk = Bblk.data_ptr(), W.data_ptr(), diag.data_ptr()
+        for t in range(self.nt):
+            k0 = t * NB
+            linv, dblk = self._tile(diag, t)
+            self._lib.check(self.lib.b200ipm_ldlt_panel(self.ctx.h, base + es * k0, ld, rows, linv.data_ptr(), dblk.data_ptr(),
+                                                        None, wbase + es * k0, b))
+            cols = b - k0 - NB
+            if cols > 0:   # remaining columns of this block column: B[:, k0+64:] -= W_t * L_kk[k0+64:, k0:k0+64]^T
+                self._lib.check(self.lib.b200ipm_gemm_nt_update(self.ctx.h, base + es * (k0 + NB), ld, rows, cols,
+                                                                wbase + es * k0, b, lkk + es * ((k0 + NB) * b + k0), b, NB, 0))
+        return W
+
+    def update(self, Cv, W, L):
+        """Cv (rows x cols view, row stride ldc) -= W (rows x b) @ L (cols x b)^T"""
+        rows, cols = Cv.shape
+        if rows == 0 or cols == 0:
+            return
+        self._lib.check(self.lib.b200ipm_gemm_nt_update(self.ctx.h, Cv.data_ptr(), Cv.stride(0), rows, cols, W.data_ptr(),
+                                                        W.stride(0), L.data_ptr(), L.stride(0), self.b, 0))
+
+    def counts(self, diag):
+        return [int(v) for v in diag[-3:].tolist()]
+
+    # ---- replicated solve on the gathered factor
+    def make_solver(self, n, diags, panels):
+        b, nt = self.b, self.nt
+        nblk = n // NB
+        A = self.zeros(n, n)
+        linvp = self.empty(nblk, NB, NB)
+        dinfo = self.zeros(4, n)
+        kind = torch.zeros(n, dtype=torch.int32, device=self.device)
+        for k, diag in enumerate(diags):
+            r0 = k * b
+            A[r0:r0 + b, r0:r0 + b] = diag[:b * b].view(b, b)
+            if panels[k] is not None:
+                A[r0 + b:, r0:r0 + b] = panels[k]
+            for t in range(nt):
+                linv, dblk = self._tile(diag, t)
+                g0 = r0 + t * NB
+                linvp[g0 // NB] = linv.view(NB, NB)
+                dinfo[:, g0:g0 + NB] = dblk[:4 * NB].view(4, NB)
+                kind[g0:g0 + NB] = dblk[4 * NB:].view(torch.int32)[:NB]
+        stream = self._lib.torch_stream_handle(self.device)
+        F = self._lib.DenseLDLT(n, device=self.device.index, stream=stream)
+        self._lib.check(self.lib.b200ipm_ldlt_import(F.h, A.data_ptr(), n, linvp.data_ptr(), dinfo.data_ptr(), kind.data_ptr()))
+        del A
+        lib, chk = self.lib, self._lib.check
+
+        def solve(Bt):   # Bt: nrhs x n contiguous device tensor, solved in place
+            chk(lib.b200ipm_ldlt_solve(F.h, Bt.data_ptr(), Bt.shape[0], 0, 1))
+            return Bt
+        solve.keepalive = F
+        return solve
+
+
+class BlockCyclicLDLT(object):
+    def __init__(self, n, grid, ops, block=256, group=None):
+        self.n, self.b, self.ops, self.group = int(n), int(block), ops, group
+        self.P, self.Q = grid
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        assert self.P * self.Q == self.world, 'grid does not match the world size'
+        assert self.n % self.b == 0
+        self.nbk = self.n // self.b
+        self.p, self.q = divmod(self.rank, self.Q)
+        self.rows_blk = [I for I in range(self.nbk) if I % self.P == self.p]     # my global block rows
+        self.cols_blk = [J for J in range(self.nbk) if J % self.Q == self.q]     # my global block cols
+        self.A0 = None
+        self.diags, self.panels, self.inertia = [], [], None
+
+    # ---- helpers
+    def _rank_of(self, p, q):
+        return p * self.Q + q
+
+    def _idx(self, blocks):
+        b = self.b
+        if not blocks:
+            return np.zeros(0, dtype=np.int64)
+        return np.concatenate([np.arange(I * b, (I + 1) * b) for I in blocks])
+
+    def _bcast(self, t, src):
+        if self.world > 1:
+            dist.broadcast(t, src=src, group=self.group)
+
+    def load(self, A):
+        """A: full n x n symmetric matrix (NumPy, same on every rank).  Keeps the local blocks of BOTH triangles
+        (the refinement mat-vec uses them); the factorisation touches blocks I >= J of a working copy."""
+        ri, ci = self._idx(self.rows_blk), self._idx(self.cols_blk)
+        loc = np.ascontiguousarray(A[np.ix_(ri, ci)])
+        self.A0 = self.ops.empty(*loc.shape)
+        self.A0.copy_(torch.from_numpy(loc))
+        self.ri = torch.from_numpy(ri).to(self.A0.device)
+        self.ci = torch.from_numpy(ci).to(self.A0.device)
+
+    def load_device(self, A):
+        """A: full n x n symmetric matrix as a device tensor (identical on every rank, e.g. generated from the
+        same seed).  Only the local blocks are kept."""
+        ri = torch.from_numpy(self._idx(self.rows_blk)).to(A.device)
+        ci = torch.from_numpy(self._idx(self.cols_blk)).to(A.device)
+        self.A0 = A.index_select(0, ri).index_select(1, ci).contiguous()
+        self.ri, self.ci = ri, ci
+
+    def factor(self):
+        """-> inertia (pos, neg, zero).  Collective: every rank must call it."""
+        ops, b, P, Q = self.ops, self.b, self.P, self.Q
+        work = self.A0.clone()
+        self.diags, self.panels = [], []
+        tot = np.zeros(3, dtype=np.int64)
+        for k in range(self.nbk):
+            pk, qk = k % P, k % Q
+            # 1. diagonal block
+            diag = ops.empty(ops.diag_size)
+            if (self.p, self.q) == (pk, qk):
+                li, lj = self.rows_blk.index(k), self.cols_blk.index(k)
+                ops.factor_diag(work[li * b:(li + 1) * b, lj * b:(lj + 1) * b], diag)
+            self._bcast(diag, self._rank_of(pk, qk))
+            tot += np.array(ops.counts(diag))
+            self.diags.append(diag)
+            nbelow = self.nbk - (k + 1)
+            if nbelow == 0:
+                self.panels.append(None)
+                break
+            # 2. my part of the panel (process column qk only)
+            mine = [I for I in self.rows_blk if I > k]
+            Wloc = None
+            if self.q == qk and mine:
+                li0, lj = self.rows_blk.index(mine[0]), self.cols_blk.index(k)
+                Bv = work[li0 * b:, lj * b:(lj + 1) * b]
+                Wloc = ops.panel(Bv, diag)
+            # 3. replicate the panel: owners (psrc, qk) broadcast [L | W] of their row blocks
+            Lfull = ops.empty(nbelow * b, b)
+            Wfull = ops.empty(nbelow * b, b)
+            for psrc in range(P):
+                blks = [I for I in range(k + 1, self.nbk) if I % P == psrc]
+                if not blks:
+                    continue
+                buf = ops.empty(2, len(blks) * b, b)
+                if self.p == psrc and self.q == qk:
+                    buf[0].copy_(Bv)
+                    buf[1].copy_(Wloc)
+                self._bcast(buf, self._rank_of(psrc, qk))
+                pos = torch.from_numpy(self._idx([I - (k + 1) for I in blks])).to(buf.device)
+                Lfull.index_copy_(0, pos, buf[0])
+                Wfull.index_copy_(0, pos, buf[1])
+            self.panels.append(Lfull)
+            # 4. trailing update of my blocks: A[I, J] -= W[I] L[J]^T for J > k, I >= J
+            if mine:
+                pos = torch.from_numpy(self._idx([I - (k + 1) for I in mine])).to(Wfull.device)
+                Wmine = Wfull.index_select(0, pos)                     # rows of my block rows > k, in local order
+                li0 = self.rows_blk.index(mine[0])
+                for lj, J in enumerate(self.cols_blk):
+                    if J <= k:
+                        continue
+                    rows_ge = [I for I in mine if I >= J]
+                    if not rows_ge:
+                        continue
+                    lis = self.rows_blk.index(rows_ge[0])
+                    Cv = work[lis * b:, lj * b:(lj + 1) * b]
+                    Lj = Lfull[(J - k - 1) * b:(J - k) * b]
+                    ops.update(Cv, Wmine[(lis - li0) * b:], Lj)
+        self.inertia = tuple(int(v) for v in tot)
+        self._solver = None
+        return self.inertia
+
+    def matvec(self, Xt):
+        """Y = A X for nrhs x n device tensors (distributed original matrix: local product + all-reduce)."""
+        part = torch.matmul(Xt[:, self.ci], self.A0.t())               # nrhs x (my rows)
+        Y = torch.zeros_like(Xt)
+        Y[:, self.ri] = part
+        if self.world > 1:
+            dist.all_reduce(Y, group=self.group)
+        return Y
+
+    def solve_device(self, Bt, nrefine=1):
+        """Bt: nrhs x n device tensor -> X (nrhs x n device tensor)."""
+        if self._solver is None:
+            self._solver = self.ops.make_solver(self.n, self.diags, self.panels)
+        X = self._solver(Bt.clone())
+        for _ in range(nrefine):
+            R = Bt - self.matvec(X)
+            X = X + self._solver(R)
+        return X
+
+    def solve(self, B, nrefine=1):
+        """B: n x nrhs (NumPy) -> X (NumPy).  Replicated triangular solves on the gathered factor + distributed
+        iterative refinement."""
+        Bt = self.ops.empty(B.shape[1], self.n)
+        Bt.copy_(torch.from_numpy(np.ascontiguousarray(B.T)))
+        return self.solve_device(Bt, nrefine).t().contiguous().cpu().numpy()
+
+
+def choose_grid(world):
+    return {1: (1, 1), 2: (1, 2), 4: (2, 2), 8: (2, 4)}.get(world, (1, world))
