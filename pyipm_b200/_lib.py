@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libb200ipm.so')
+LIB_PATH = os.environ.get('B200IPM_LIB', os.path.join(_HERE, 'libb200ipm.so'))   # override: profiling builds
 
 c_double_p = C.POINTER(C.c_double)
 c_int_p = C.POINTER(C.c_int)

@@ -38,7 +38,7 @@ struct b200ipm_engine {
     double *x = nullptr, *s = nullptr, *lam = nullptr;
     // derivatives at the state
     double *fval = nullptr, *df = nullptr, *ce = nullptr, *ci = nullptr, *J = nullptr, *W = nullptr;
-    bool eval_valid = false, resid_valid = false;
+    bool eval_valid = false, hess_valid = false, resid_valid = false;
     // residual / direction
     double *g = nullptr, *sigma = nullptr, *bvec = nullptr, *tvec = nullptr, *rhs = nullptr, *sol = nullptr;
     double *ycur = nullptr, *ycor = nullptr, *rho = nullptr, *dz = nullptr, *wx = nullptr, *jt = nullptr;
@@ -122,7 +122,7 @@ static int quad_images(Eng* h, const double* v, double* qv, double* av, double* 
     return 0;
 }
 
-// f, df, ce, ci, J and W = d2L at the current (x, lda)
+// f, df, ce, ci, J at the current x (first-order quantities: all the KKT conditions need)
 static int eval_derivs(Eng* h) {
     if (h->eval_valid) return 0;
     const int D = h->D, M = h->M, N = h->N;
@@ -136,29 +136,39 @@ static int eval_derivs(Eng* h) {
                                                                                          h->J, h->ldJ);
             LAUNCHED();
         }
-        // W = Q + 3 q4 diag(x^2) - Ut diag(lda_e) Ut' + Vt diag(lda_i) Vt'      (a3; DMMA SYRK)
-        GemmArgs a{};
-        a.C = h->W; a.ldc = h->ldW; a.Cin = h->Q; a.ldcin = D; a.dadd = h->xdiag; a.n = D; a.m = D; a.beta = 1.0;
-        a.shift = 0.0; a.mode = GEMM_UPPER_MIRROR; a.nterms = 0;
-        if (M && h->Ut) a.t[a.nterms++] = GemmTerm{h->Ut, h->Ut, h->lam, M, M, M, -1.0};
-        if (N && h->Vt) a.t[a.nterms++] = GemmTerm{h->Vt, h->Vt, h->lam + M, N, N, N, 1.0};
-        CU(cudaEventRecord(h->ev[EV_HESS0], h->st));
-        RET(gemm_nt(h->st, a));
-        CU(cudaEventRecord(h->ev[EV_HESS1], h->st));
     } else if (h->kind == KIND_POLY) {
         poly_eval_kernel<<<1, 256, 0, h->st>>>(D, M, N, h->poly, h->x, h->fval, h->df, h->ce, h->ci, h->J, h->ldJ);
         LAUNCHED();
-        poly_hess_kernel<<<cdiv(D * D, 256), 256, 0, h->st>>>(D, M, N, h->poly, h->x, h->lam, h->W, h->ldW);
-        LAUNCHED();
-        CU(cudaEventRecord(h->ev[EV_HESS0], h->st));
-        CU(cudaEventRecord(h->ev[EV_HESS1], h->st));
     } else if (h->kind == KIND_CALLABLE) {
         return fail_msg("callable mode: b200ipm_set_derivs must be called after every state change");
     } else {
         return fail_msg("no problem bound (b200ipm_bind_quad / b200ipm_bind_poly / b200ipm_set_derivs)");
     }
     h->eval_valid = true;
+    h->hess_valid = false;
     h->resid_valid = false;
+    return 0;
+}
+// W = d2L at the current (x, lda): only needed when a search direction is computed (a3)
+static int eval_hessian(Eng* h) {
+    RET(eval_derivs(h));
+    if (h->hess_valid) return 0;
+    const int D = h->D, M = h->M, N = h->N;
+    CU(cudaEventRecord(h->ev[EV_HESS0], h->st));
+    if (h->kind == KIND_QUAD) {
+        // W = Q + 3 q4 diag(x^2) - Ut diag(lda_e) Ut' + Vt diag(lda_i) Vt'      (DMMA SYRK)
+        GemmArgs a{};
+        a.C = h->W; a.ldc = h->ldW; a.Cin = h->Q; a.ldcin = D; a.dadd = h->xdiag; a.n = D; a.m = D; a.beta = 1.0;
+        a.shift = 0.0; a.mode = GEMM_UPPER_MIRROR; a.nterms = 0;
+        if (M && h->Ut) a.t[a.nterms++] = GemmTerm{h->Ut, h->Ut, h->lam, M, M, M, -1.0};
+        if (N && h->Vt) a.t[a.nterms++] = GemmTerm{h->Vt, h->Vt, h->lam + M, N, N, N, 1.0};
+        RET(gemm_nt(h->st, a));
+    } else if (h->kind == KIND_POLY) {
+        poly_hess_kernel<<<cdiv(D * D, 256), 256, 0, h->st>>>(D, M, N, h->poly, h->x, h->lam, h->W, h->ldW);
+        LAUNCHED();
+    }   // KIND_CALLABLE: W was uploaded by set_derivs
+    CU(cudaEventRecord(h->ev[EV_HESS1], h->st));
+    h->hess_valid = true;
     return 0;
 }
 
@@ -301,13 +311,20 @@ static int solve_direction(Eng* h, b200ipm_step_info* info) {
     axpby_kernel<<<cdiv(K, 256), 256, 0, h->st>>>(K, -1.0, h->g, 0.0, nullptr, h->bvec);   // b = -g (pyipm.py:1717)
     LAUNCHED();
     RET(condensed_solve(h, h->bvec, h->ycur));
-    for (int it = 0; it < h->p.nrefine; it++) {
+    // iterative refinement against the UNREDUCED system; stop as soon as the residual is at rounding level
+    // relative to the right-hand side (typically after one sweep), at most nrefine sweeps
+    double bnorm = 0.0;
+    for (int i = 0; i < 4; i++) bnorm = std::max(bnorm, h->last_red[i]);
+    const double tol = 1e-14 * std::max(1.0, bnorm);
+    for (int it = 0;; it++) {
         RET(kkt_residual_vec(h, h->bvec, h->ycur, h->rho));
+        if (it >= h->p.nrefine) break;
+        RET(fetch_red(h, h->red + 8, 1));
+        if (h->h_red[0] <= tol) break;
         RET(condensed_solve(h, h->rho, h->ycor));
         axpby_kernel<<<cdiv(K, 256), 256, 0, h->st>>>(K, 1.0, h->ycur, 1.0, h->ycor, h->ycur);
         LAUNCHED();
     }
-    RET(kkt_residual_vec(h, h->bvec, h->ycur, h->rho));   // final residual (reported)
     flip_kernel<<<cdiv(K, 256), 256, 0, h->st>>>(h->D, h->N, K, h->ycur, h->dz);
     LAUNCHED();
     (void)info;
@@ -575,6 +592,7 @@ static int line_search(Eng* h, b200ipm_step_info* info, const double* stats /* h
         LAUNCHED();
     }
     h->eval_valid = false;
+    h->hess_valid = false;
     h->resid_valid = false;
     return 0;
 }
@@ -582,6 +600,7 @@ static int line_search(Eng* h, b200ipm_step_info* info, const double* stats /* h
 // ------------------------------------------------------------------------------------------ direction + step
 static int compute_direction(Eng* h, b200ipm_step_info* info) {
     RET(residual(h));
+    RET(eval_hessian(h));
     CU(cudaEventRecord(h->ev[EV_EVAL], h->st));
     RET(condense(h));
     CU(cudaEventRecord(h->ev[EV_ASSEMBLE], h->st));
@@ -716,7 +735,7 @@ int b200ipm_bind_quad(b200ipm_handle h, const double* Q, const double* c, double
     }
     CU(cudaStreamSynchronize(h->st));
     h->kind = KIND_QUAD;
-    h->eval_valid = h->resid_valid = false;
+    h->eval_valid = h->hess_valid = h->resid_valid = false;
     return 0;
 }
 
@@ -750,7 +769,7 @@ int b200ipm_bind_poly(b200ipm_handle h, int nterms, const int* term_row, const d
     CU(cudaStreamSynchronize(h->st));
     h->poly = PolyData{nterms, R, h->p_rowptr, h->p_coeff, h->p_ptr, h->p_fvar, h->p_fpow, xlogx_coeff, xlogx_shift};
     h->kind = KIND_POLY;
-    h->eval_valid = h->resid_valid = false;
+    h->eval_valid = h->hess_valid = h->resid_valid = false;
     return 0;
 }
 
@@ -773,6 +792,7 @@ int b200ipm_set_derivs(b200ipm_handle h, double fval, const double* df, const do
     CU(cudaStreamSynchronize(h->st));   // fval lives on the caller's stack
     if (h->kind == KIND_NONE) h->kind = KIND_CALLABLE;
     h->eval_valid = true;
+    h->hess_valid = true;
     h->resid_valid = false;
     return 0;
 }
@@ -786,7 +806,8 @@ int b200ipm_set_state(b200ipm_handle h, const double* x, const double* s, const 
     if (lda) RET(up(h, h->lam, lda, h->C, 0));
     CU(cudaStreamSynchronize(h->st));
     h->mu = mu; h->nu = nu; h->delta = delta;
-    if (x || lda) h->eval_valid = false;   // W, J, df depend on (x, lda) only
+    if (x) h->eval_valid = false;            // f, df, ce, ci, J depend on x only
+    if (x || lda) h->hess_valid = false;     // W depends on (x, lda)
     h->resid_valid = false;
     return 0;
 }
@@ -824,6 +845,7 @@ int b200ipm_state_restore(b200ipm_handle h) {
     if (h->C) CU(cudaMemcpyAsync(h->lam, h->sv_lam, sizeof(double) * h->C, cudaMemcpyDeviceToDevice, h->st));
     h->mu = h->sv_mu; h->nu = h->sv_nu; h->delta = h->sv_delta; h->mu_host = h->sv_mu_host;
     h->eval_valid = false;
+    h->hess_valid = false;
     h->resid_valid = false;
     return 0;
 }
@@ -832,6 +854,7 @@ int b200ipm_profile_kernel(b200ipm_handle h, int which, int reps, float* ms_per_
     if (!h || reps <= 0) return fail_msg("profile_kernel: bad arguments");
     CU(cudaSetDevice(h->device));
     RET(residual(h));
+    RET(eval_hessian(h));
     const int D = h->D, M = h->M, N = h->N, C = h->C;
     double wk = 0.0;
     if (which >= 2) RET(condense(h));
@@ -888,6 +911,7 @@ int b200ipm_profile_kernel(b200ipm_handle h, int which, int reps, float* ms_per_
     if (ms_per_launch) *ms_per_launch = ms / reps;
     if (work) *work = wk;
     h->eval_valid = false;   // W / Hb / g were rewritten with the same values; keep the cache honest anyway
+    h->hess_valid = false;
     h->resid_valid = false;
     return 0;
 }
@@ -935,6 +959,7 @@ int b200ipm_con_jac(b200ipm_handle h, double* con, double* J) {
 int b200ipm_hess_full(b200ipm_handle h, double* H) {
     CU(cudaSetDevice(h->device));
     RET(residual(h));
+    RET(eval_hessian(h));
     const size_t K = h->K;
     double* dH = nullptr;
     RET(dalloc(&dH, K * K));
@@ -948,7 +973,7 @@ int b200ipm_hess_full(b200ipm_handle h, double* H) {
 }
 int b200ipm_d2L(b200ipm_handle h, double* W) {
     CU(cudaSetDevice(h->device));
-    RET(eval_derivs(h));
+    RET(eval_hessian(h));
     CU(cudaMemcpy2DAsync(W, sizeof(double) * h->D, h->W, sizeof(double) * h->ldW, sizeof(double) * h->D, h->D,
                          cudaMemcpyDeviceToHost, h->st));
     CU(cudaStreamSynchronize(h->st));
@@ -1006,7 +1031,7 @@ int b200ipm_init_lambda(b200ipm_handle h) {
         fix_lambda_kernel<<<cdiv(N, 256), 256, 0, h->st>>>(M, N, h->p.Ktol, h->lam);
         LAUNCHED();
     }
-    h->eval_valid = false;   // W depends on lda
+    h->hess_valid = false;   // W depends on lda
     h->resid_valid = false;
     return 0;
 }

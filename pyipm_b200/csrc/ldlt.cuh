@@ -74,19 +74,23 @@ inline void ldlt_free(LdltWs& w) {
 }
 
 // ------------------------------------------------------------------------------------------- tile kernel
-// One CTA, 1024 threads.  T (symmetric, both triangles kept bitwise equal) and X (running L^-1) live in smem.
-// The 64 pivot steps are a serial chain, so the kernel is organised for latency and instruction count:
-//   * 32 warps, warp w owns rows w and w+32, lanes own columns lane and lane+32;
-//   * for column m a step touches EITHER T (m beyond the pivot) OR X (m up to the pivot), never both, so the
-//     update is one fused pass over the augmented matrix [X | T] with a per-lane base pointer;
-//   * updates read the pivot ROW(s), which stay intact during the step (multipliers go to COLUMN j): no staging,
-//     all smem loads are issued before the first store;
-//   * software pipeline: the warp that owns the NEXT pivot row runs the Bunch-Kaufman search on the freshly
-//     updated values it still holds in registers (three redux.sync on the IEEE bit pattern of |v|) and
-//     publishes the decision (and 1/d) while the other warps are still updating => ONE barrier per step.
-//     Only the rare second-level test (needs row r, owned by another warp) costs two extra barriers.
-constexpr int TILE_THREADS = 1024;
-struct TileDec { int kp, kstep, need2, r; double absakk, colmax, dinv; };
+// One CTA, 256 threads: P T P^T = L D L^T of one 64 x 64 diagonal tile with Bunch-Kaufman pivoting, fused with the
+// Gauss-Jordan accumulation of X = L^-1.  The 64 pivot steps are a serial chain (measured: the chain, not the
+// arithmetic, is the cost), so the kernel is organised for latency:
+//   * warp w owns rows w, w+8, ..., w+56, lanes own columns lane and lane+32: every thread keeps its 8 x 2 slab of
+//     T and of X in REGISTERS for the whole factorisation (statically indexed, fully unrolled);
+//   * for column m a step touches EITHER T (m beyond the pivot) OR X (m up to the pivot), never both;
+//   * the only shared-memory traffic of a step is the pivot row (T and X parts), published one step ahead into a
+//     double-buffered row by the warp that owns it;
+//   * software pipeline: in the unrolled row loop the next pivot row is the first ACTIVE row of its owner, so that
+//     warp updates it, runs the first-level Bunch-Kaufman test on the values it holds in registers (ONE vote.any in
+//     the common case; redux.sync arg-max only when the test fails) and publishes the decision together with d and
+//     1/d (rcp.approx + two Newton steps) while everybody else is still updating => one barrier per step;
+//   * anything else (second-level test, interchange, 2x2 pivot -- rare on barrier-regularised KKT matrices) takes a
+//     slow step: registers are spilled to the smem copy of T/X, the step runs there, registers are reloaded.
+constexpr int TILE_THREADS = 256;
+constexpr int TILE_RPW = 8;   // rows per warp
+struct TileDec { int code; int r; double d, dinv, absakk, colmax; };   // code = need2 | kstep << 1 | kp << 8
 
 __device__ __forceinline__ double warp_absmax_bits(double v) {   // max of non-negative doubles via redux.sync
     const unsigned long long b = (unsigned long long)__double_as_longlong(v);
@@ -95,16 +99,39 @@ __device__ __forceinline__ double warp_absmax_bits(double v) {   // max of non-n
     const unsigned ml = __reduce_max_sync(0xffffffffu, (h == mh) ? l : 0u);
     return __longlong_as_double((long long)(((unsigned long long)mh << 32) | ml));
 }
+__device__ __forceinline__ double fast_rcp(double x) {
+    const double ax = fabs(x);
+    if (!(ax > 1e-290 && ax < 1e290)) return 1.0 / x;
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
 // First-level Bunch-Kaufman test for pivot row jn, executed by ONE warp.  v0/v1 are T[jn][lane], T[jn][lane+32].
 __device__ __forceinline__ void tile_search(int jn, int nb, int lane, double v0, double v1, TileDec* out) {
     const double BK_ALPHA = 0.6403882032022076;   // (1 + sqrt(17)) / 8
     const double djj = __shfl_sync(0xffffffffu, (jn < 32) ? v0 : v1, jn & 31);
     const double absakk = fabs(djj);
     const int c0 = lane, c1 = lane + 32;
+    const bool in0 = (c0 > jn && c0 < nb), in1 = (c1 > jn && c1 < nb);
+    // need2  <=>  absakk < alpha * colmax  <=>  some |v_m| * alpha exceeds absakk   (both-zero case: false)
+    const bool viol = (in0 && BK_ALPHA * fabs(v0) > absakk) || (in1 && BK_ALPHA * fabs(v1) > absakk);
+    const double rinv = (djj != 0.0) ? fast_rcp(djj) : 0.0;   // independent of the vote: overlaps its latency
+    if (!__any_sync(0xffffffffu, viol)) {
+        if (lane == 0) {
+            out->code = (1 << 1) | (jn << 8);
+            out->d = djj;
+            out->dinv = rinv;
+        }
+        return;
+    }
     double cm = -1.0;
     int r = jn;
-    if (c0 > jn && c0 < nb) { cm = fabs(v0); r = c0; }
-    if (c1 > jn && c1 < nb) { const double v = fabs(v1); if (v > cm) { cm = v; r = c1; } }
+    if (in0) { cm = fabs(v0); r = c0; }
+    if (in1) { const double v = fabs(v1); if (v > cm) { cm = v; r = c1; } }
     const bool have = (cm >= 0.0);
     const unsigned long long bits = have ? (unsigned long long)__double_as_longlong(cm) : 0ull;
     const unsigned hi = (unsigned)(bits >> 32), lo = (unsigned)bits;
@@ -112,13 +139,78 @@ __device__ __forceinline__ void tile_search(int jn, int nb, int lane, double v0,
     const unsigned ml = __reduce_max_sync(0xffffffffu, (hi == mh) ? lo : 0u);
     const unsigned cand = (have && hi == mh && lo == ml) ? (unsigned)r : 0xffffu;
     const unsigned rsel = __reduce_min_sync(0xffffffffu, cand);
-    const double colmax = __longlong_as_double((long long)(((unsigned long long)mh << 32) | ml));
     if (lane == 0) {
-        TileDec d;
-        d.kp = jn; d.kstep = 1; d.need2 = 0; d.r = (rsel == 0xffffu) ? jn : (int)rsel;
-        d.absakk = absakk; d.colmax = colmax; d.dinv = (djj != 0.0) ? 1.0 / djj : 0.0;
-        if (!(fmax(absakk, colmax) == 0.0) && absakk < BK_ALPHA * colmax) d.need2 = 1;
-        *out = d;
+        out->code = 1 | (1 << 1) | (jn << 8);
+        out->r = (rsel == 0xffffu) ? jn : (int)rsel;
+        out->d = djj;
+        out->dinv = 0.0;
+        out->absakk = absakk;
+        out->colmax = __longlong_as_double((long long)(((unsigned long long)mh << 32) | ml));
+    }
+}
+
+// Eight consecutive unpivoted elimination steps j = 8*JB .. 8*JB+7 of the fast attempt (see ldlt_tile_kernel).
+// Ownership here is TRANSPOSED with respect to the pivoting loop: lane l owns rows l and l+32, warp w owns columns
+// w, w+8, ..., w+56 (register b[k][h] = element (l + 32h, w + 8k)).  A step then is, per warp: 11 LDS (pivot-row
+// entries), 2 row masks, 16 FMAs; the column that switches from T-type to X-type is a warp-uniform reset of
+// b[JB][*] (static index), its L entries are two stores per lane, and the next pivot row is published by the one
+// lane per warp that holds it.  The kernel is bound by the number of warp-instructions per step (each SMSP pipe
+// needs ~2 cycles per instruction), hence the effort to keep the step at ~65 instructions per warp.
+template <int JB>
+__device__ __forceinline__ void tile_fast_block(double (&b)[TILE_RPW][2], int nb, int lane, int warp, int tid,
+                                                double* __restrict__ Tf, double* __restrict__ prow0,
+                                                double* __restrict__ pdiag, double* __restrict__ sda,
+                                                int& viol, bool& allpos, bool& allneg) {
+    const double BK_ALPHA = 0.6403882032022076;
+    if (JB * 8 >= nb) return;
+    const int r0 = lane, r1 = lane + 32;
+    for (int w8 = 0; w8 < 8; w8++) {
+        const int j = JB * 8 + w8;
+        if (j >= nb) break;
+        const int par = j & 1;
+        const double* pr = prow0 + par * NB;
+        const double d = pdiag[par * 2], dinv = pdiag[par * 2 + 1];
+        const double u0 = pr[r0], u1 = pr[r1];
+        double q[TILE_RPW];
+#pragma unroll
+        for (int k = 0; k < TILE_RPW; k++) q[k] = pr[warp + 8 * k];
+        const bool act0 = (r0 > j) && (r0 < nb), act1 = (r1 > j) && (r1 < nb);
+        const double g0 = act0 ? u0 * dinv : 0.0;      // L[r0][j]; zero for finished / padded rows => unchanged
+        const double g1 = act1 ? u1 * dinv : 0.0;
+        if (warp == 0) {   // sticky first-level Bunch-Kaufman check on the pivot column (= pivot row by symmetry)
+            const double thr = fabs(d);
+            viol |= ((act0 && BK_ALPHA * fabs(u0) > thr) || (act1 && BK_ALPHA * fabs(u1) > thr)) ? 1 : 0;
+        }
+        allpos = allpos && (d > 0.0);
+        allneg = allneg && (d < 0.0);
+        if (warp == w8) {  // column j switches to X-type: L entries out, registers restart from e_j
+            if (act0) Tf[r0 * NBP + j] = g0;
+            if (act1) Tf[r1 * NBP + j] = g1;
+            b[JB][0] = (r0 == j) ? 1.0 : 0.0;
+            b[JB][1] = (r1 == j) ? 1.0 : 0.0;
+            if (lane == 0) sda[j] = d;
+        }
+#pragma unroll
+        for (int k = 0; k < TILE_RPW; k++) {
+            b[k][0] = fma(-g0, q[k], b[k][0]);
+            b[k][1] = fma(-g1, q[k], b[k][1]);
+        }
+        // ---- publish the next pivot row: in every warp, the lane that holds row jn writes its 8 columns
+        const int jn = j + 1;
+        if (jn < nb && lane == (jn & 31)) {
+            double* pw = prow0 + (par ^ 1) * NB;
+            const bool hi = (JB > 3) || (JB == 3 && w8 == 7);     // row jn lives in the upper half (rows >= 32)
+#pragma unroll
+            for (int k = 0; k < TILE_RPW; k++) pw[warp + 8 * k] = hi ? b[k][1] : b[k][0];
+            if (warp == (jn & 7)) {   // this lane also holds the diagonal T[jn][jn]
+                constexpr int KN = (JB + 1 < TILE_RPW) ? JB + 1 : JB;
+                const double dn = (w8 < 7) ? (hi ? b[JB][1] : b[JB][0]) : (hi ? b[KN][1] : b[KN][0]);
+                pw[jn] = 1.0;
+                pdiag[(par ^ 1) * 2] = dn;
+                pdiag[(par ^ 1) * 2 + 1] = (dn != 0.0) ? fast_rcp(dn) : 0.0;
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -129,26 +221,40 @@ __global__ void __launch_bounds__(TILE_THREADS) ldlt_tile_kernel(double* __restr
                                                                  int* __restrict__ perm_out, int* __restrict__ counts,
                                                                  double* __restrict__ dstat) {
     extern __shared__ __align__(16) double tsm[];
-    double* Tf = tsm;                 // T[i][m] = Tf[i * NBP + m]
+    double* Tf = tsm;                 // T[i][m] = Tf[i * NBP + m]   (authoritative only inside slow steps / at the ends)
     double* Xf = tsm + NB * NBP;      // X[i][m] = Xf[i * NBP + m]
     __shared__ double sda[NB], sdb[NB];
+    __shared__ double prowT[2][NB];   // unified pivot row (T part right of the pivot, X part left of it), double buffered
     __shared__ int sperm[NB], skind[NB];
     __shared__ TileDec sdec[2];
-    __shared__ TileDec sdec2;
+    __shared__ int s_kp2, s_kstep2;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double BK_ALPHA = 0.6403882032022076;
+#ifdef TILE_PROF
+    long long tp0 = clock64(), tp1 = 0, tp2 = 0, tp3 = 0;
+    int nslow = 0;
+#endif
 
-    // load the tile from its LOWER triangle, mirror, identity-pad to NB
-    for (int idx = tid; idx < NB * NB; idx += TILE_THREADS) {
-        const int i = idx / NB, j = idx % NB;
-        double v;
-        if (i < nb && j < nb) {
-            v = (i >= j) ? A[(size_t)i * ld + j] : A[(size_t)j * ld + i];
-        } else {
-            v = (i == j) ? 1.0 : 0.0;
+    // load the tile from its LOWER triangle (coalesced rows, all 16 loads of a thread in flight at once), mirror
+    // through shared memory, identity-pad to NB
+    {
+        double v[NB * NB / TILE_THREADS];
+#pragma unroll
+        for (int it = 0; it < NB * NB / TILE_THREADS; it++) {
+            const int idx = tid + it * TILE_THREADS;
+            const int i = idx / NB, j = idx % NB;
+            v[it] = (i < nb && j <= i) ? A[(size_t)i * ld + j] : ((i == j) ? 1.0 : 0.0);
         }
-        Tf[i * NBP + j] = v;
-        Xf[i * NBP + j] = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+        for (int it = 0; it < NB * NB / TILE_THREADS; it++) {
+            const int idx = tid + it * TILE_THREADS;
+            const int i = idx / NB, j = idx % NB;
+            if (j <= i) {
+                Tf[i * NBP + j] = v[it];
+                Tf[j * NBP + i] = v[it];
+            }
+            Xf[i * NBP + j] = (i == j) ? 1.0 : 0.0;
+        }
     }
     if (tid < NB) {
         sperm[tid] = tid;
@@ -158,120 +264,282 @@ __global__ void __launch_bounds__(TILE_THREADS) ldlt_tile_kernel(double* __restr
     }
     __syncthreads();
     const int m0 = lane, m1 = lane + 32;
-    const int ra = warp, rb = warp + 32;
-    if (warp == 0) tile_search(0, nb, lane, Tf[m0], Tf[m1], &sdec[0]);
-    __syncthreads();
+    // ONE register per (row, column): column m is "T-type" (trailing matrix) until pivot step m and "X-type" (L^-1)
+    // afterwards.  At its switch step the L entries of the column are written to Tf once and the registers restart
+    // from the X initial values; Xf keeps the identity for columns that have not switched yet.
+    double a[TILE_RPW][2];
+#pragma unroll
+    for (int k = 0; k < TILE_RPW; k++) {
+        const int row = warp + 8 * k;
+        a[k][0] = Tf[row * NBP + m0]; a[k][1] = Tf[row * NBP + m1];
+    }
+    double* prow0 = &prowT[0][0];     // unified pivot row, double buffered: prow[par][m]
+    __shared__ double pdiag[4];   // [parity][d, 1/d] of the published pivot
 
-    int j = 0, par = 0;
-    while (j < nb) {
-        TileDec dec = sdec[par];
-        if (dec.need2) {
-            // second-level test (LAPACK dsytf2): needs row r, which is stable now (we are right after a barrier)
+    // =====================================================================================================
+    // FAST ATTEMPT: no pivot search on the critical path.  The tile is eliminated in natural order (what
+    // Bunch-Kaufman does whenever its first-level test |d_j| >= alpha * max_i |T[i][j]| holds); every lane checks
+    // that test on the pivot-row entries it reads anyway and keeps a sticky flag.  The attempt is accepted if no
+    // test failed, or if all pivots came out with the same sign (the tile was definite, so the unpivoted
+    // elimination is unconditionally stable).  Otherwise the tile is reloaded and the pivoting loop below runs.
+    // Per step the serial chain is: barrier -> LDS pivot row -> rcp -> 2 FMA on the next pivot row -> STS.
+    // =====================================================================================================
+    int fast_ok = 0;
+    {
+        double b[TILE_RPW][2];     // transposed ownership: rows lane / lane+32, columns warp + 8k
+#pragma unroll
+        for (int k = 0; k < TILE_RPW; k++) {
+            b[k][0] = Tf[lane * NBP + warp + 8 * k];
+            b[k][1] = Tf[(lane + 32) * NBP + warp + 8 * k];
+        }
+        if (lane == 0) {           // row 0 is the first pivot row
+#pragma unroll
+            for (int k = 0; k < TILE_RPW; k++) prow0[warp + 8 * k] = b[k][0];
             if (warp == 0) {
-                const int r = dec.r;
-                const int a0 = j + lane, a1 = a0 + 32;
-                double rm = 0.0;
-                if (a0 < nb && a0 != r) rm = fabs(Tf[r * NBP + a0]);
-                if (a1 < nb && a1 != r) rm = fmax(rm, fabs(Tf[r * NBP + a1]));
-                rm = warp_absmax_bits(rm);
-                if (lane == 0) {
-                    TileDec d2 = dec;
-                    d2.need2 = 0;
-                    if (dec.absakk * rm >= BK_ALPHA * dec.colmax * dec.colmax) { d2.kp = j; d2.kstep = 1; }
-                    else if (fabs(Tf[r * NBP + r]) >= BK_ALPHA * rm) { d2.kp = r; d2.kstep = 1; }
-                    else { d2.kp = r; d2.kstep = 2; }
-                    sdec2 = d2;
+                prow0[0] = 1.0;
+                pdiag[0] = b[0][0];
+                pdiag[1] = (b[0][0] != 0.0) ? fast_rcp(b[0][0]) : 0.0;
+            }
+        }
+        __syncthreads();
+        int viol = 0;
+        bool allpos = true, allneg = true;
+        tile_fast_block<0>(b, nb, lane, warp, tid, Tf, prow0, pdiag, sda, viol, allpos, allneg);
+        tile_fast_block<1>(b, nb, lane, warp, tid, Tf, prow0, pdiag, sda, viol, allpos, allneg);
+        tile_fast_block<2>(b, nb, lane, warp, tid, Tf, prow0, pdiag, sda, viol, allpos, allneg);
+        tile_fast_block<3>(b, nb, lane, warp, tid, Tf, prow0, pdiag, sda, viol, allpos, allneg);
+        tile_fast_block<4>(b, nb, lane, warp, tid, Tf, prow0, pdiag, sda, viol, allpos, allneg);
+        tile_fast_block<5>(b, nb, lane, warp, tid, Tf, prow0, pdiag, sda, viol, allpos, allneg);
+        tile_fast_block<6>(b, nb, lane, warp, tid, Tf, prow0, pdiag, sda, viol, allpos, allneg);
+        tile_fast_block<7>(b, nb, lane, warp, tid, Tf, prow0, pdiag, sda, viol, allpos, allneg);
+        const int anyviol = __syncthreads_or(viol);
+        // accept: no first-level violation anywhere, or a definite tile (all pivots of one sign, none zero)
+        fast_ok = ((!anyviol) || allpos || allneg) ? 1 : 0;
+        if (!(allpos || allneg)) {   // mixed signs are fine without violations, zero pivots are not
+            bool haszero = false;
+            for (int p2 = 0; p2 < nb; p2++) haszero = haszero || (sda[p2] == 0.0);
+            if (haszero) fast_ok = 0;
+        }
+        if (fast_ok) {
+            // all columns < nb have switched: the registers hold X; hand over to the common output stage
+#pragma unroll
+            for (int k = 0; k < TILE_RPW; k++) {
+                const int c = warp + 8 * k;
+                if (c < nb) {
+                    Xf[lane * NBP + c] = b[k][0];
+                    Xf[(lane + 32) * NBP + c] = b[k][1];
                 }
             }
-            __syncthreads();
-            dec = sdec2;
+            if (tid < NB) { sdb[tid] = 0.0; skind[tid] = 0; }
         }
-        const int kp = dec.kp, kstep = dec.kstep;
-        const int kk = j + kstep - 1;
-        // ---- symmetric interchange kk <-> kp on T and X (rows, then columns); rare on IPM matrices
-        if (kp != kk) {
-            __syncthreads();
-            if (tid < NB) {
-                double t0 = Tf[kk * NBP + tid]; Tf[kk * NBP + tid] = Tf[kp * NBP + tid]; Tf[kp * NBP + tid] = t0;
-                double x0 = Xf[kk * NBP + tid]; Xf[kk * NBP + tid] = Xf[kp * NBP + tid]; Xf[kp * NBP + tid] = x0;
+    }
+    if (!fast_ok) {
+        // reload the tile and the bookkeeping, then fall through to the pivoting loop
+        __syncthreads();
+        for (int idx = tid; idx < NB * NB; idx += TILE_THREADS) {
+            const int i = idx / NB, jj = idx % NB;
+            if (jj <= i) {
+                const double v = (i < nb) ? A[(size_t)i * ld + jj] : ((i == jj) ? 1.0 : 0.0);
+                Tf[i * NBP + jj] = v;
+                Tf[jj * NBP + i] = v;
             }
-            __syncthreads();
-            if (tid < NB) {
-                double t0 = Tf[tid * NBP + kk]; Tf[tid * NBP + kk] = Tf[tid * NBP + kp]; Tf[tid * NBP + kp] = t0;
-                double x0 = Xf[tid * NBP + kk]; Xf[tid * NBP + kk] = Xf[tid * NBP + kp]; Xf[tid * NBP + kp] = x0;
-            }
-            if (tid == 0) { int p = sperm[kk]; sperm[kk] = sperm[kp]; sperm[kp] = p; }
-            __syncthreads();
+            Xf[i * NBP + jj] = (i == jj) ? 1.0 : 0.0;
         }
-        const int jn = j + kstep;                                  // next pivot row
-        // per-lane base pointers into the augmented matrix [X | T]
-        double* P0 = (m0 > kk) ? Tf : Xf;
-        double* P1 = (m1 > kk) ? Tf : Xf;
-        double na0, na1, nb0, nb1;                                 // new values of this warp's rows
-        if (kstep == 1) {
-            const double d = Tf[j * NBP + j];
-            const double dinv = (kp == j) ? dec.dinv : ((d != 0.0) ? 1.0 / d : 0.0);
+        if (tid < NB) { sperm[tid] = tid; skind[tid] = 0; sda[tid] = 1.0; sdb[tid] = 0.0; }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < TILE_RPW; k++) {
+            const int row = warp + 8 * k;
+            a[k][0] = Tf[row * NBP + m0]; a[k][1] = Tf[row * NBP + m1];
+        }
+        if (warp == 0) {
+            prow0[m0] = (m0 == 0) ? 1.0 : a[0][0]; prow0[m1] = a[0][1];
+            tile_search(0, nb, lane, a[0][0], a[0][1], &sdec[0]);
+        }
+        __syncthreads();
+    }
+#ifdef TILE_PROF
+    tp1 = clock64();
+#endif
+
+    int j = fast_ok ? nb : 0, par = 0;
+    while (j < nb) {
+        const int code = sdec[par].code;
+        int jn;
+        if (code == ((1 << 1) | (j << 8))) {
+            // ================= fast step: 1x1 pivot on the diagonal, no interchange =================
+            const double* pr = prow0 + par * NB;
+            const double d = sdec[par].d, dinv = sdec[par].dinv;
+            const double q0 = pr[m0], q1 = pr[m1];
+            double ua[TILE_RPW];
+#pragma unroll
+            for (int k = 0; k < TILE_RPW; k++) ua[k] = pr[warp + 8 * k];      // all smem loads of the step up front
             if (tid == 0) { sda[j] = d; sdb[j] = 0.0; skind[j] = 0; }
-            const double pj0 = P0[j * NBP + m0], pj1 = P1[j * NBP + m1];
-            const double ua = Tf[j * NBP + ra], ub = Tf[j * NBP + rb];
-            na0 = P0[ra * NBP + m0]; na1 = P1[ra * NBP + m1];
-            nb0 = P0[rb * NBP + m0]; nb1 = P1[rb * NBP + m1];
-            if (d != 0.0) {
-                if (ra > j && ra < nb) {
-                    na0 -= (ua * pj0) * dinv; na1 -= (ua * pj1) * dinv;
-                    P0[ra * NBP + m0] = na0; P1[ra * NBP + m1] = na1;
-                    if (m0 == j) Tf[ra * NBP + j] = ua * dinv;
-                    if (m1 == j) Tf[ra * NBP + j] = ua * dinv;
+            const bool sw0 = (m0 == j), sw1 = (m1 == j);
+            jn = j + 1;
+            // ---- phase A (owner of the next pivot row only): update THAT row, publish it, first-level test
+            const bool ownerA = (jn < nb) && ((jn & 7) == warp);
+            if (ownerA) {
+#pragma unroll
+                for (int k = 0; k < TILE_RPW; k++) {
+                    if ((jn >> 3) == k) {
+                        const double uu = ua[k];
+                        a[k][0] = fma(-(uu * q0), dinv, a[k][0]);
+                        a[k][1] = fma(-(uu * q1), dinv, a[k][1]);
+                        if (sw0 || sw1) {
+                            const double lij = uu * dinv;
+                            Tf[jn * NBP + j] = lij;
+                            if (sw0) a[k][0] = -lij; else a[k][1] = -lij;
+                        }
+                        double* pw = prow0 + (par ^ 1) * NB;
+                        pw[m0] = (m0 == jn) ? 1.0 : a[k][0];
+                        pw[m1] = (m1 == jn) ? 1.0 : a[k][1];
+                        tile_search(jn, nb, lane, a[k][0], a[k][1], &sdec[par ^ 1]);
+                    }
                 }
-                if (rb > j && rb < nb) {
-                    nb0 -= (ub * pj0) * dinv; nb1 -= (ub * pj1) * dinv;
-                    P0[rb * NBP + m0] = nb0; P1[rb * NBP + m1] = nb1;
-                    if (m0 == j) Tf[rb * NBP + j] = ub * dinv;
-                    if (m1 == j) Tf[rb * NBP + j] = ub * dinv;
+            }
+            // ---- phase B (everybody): the remaining active rows; inactive rows get a zero multiplier
+#pragma unroll
+            for (int k = 0; k < TILE_RPW; k++) {
+                const int row = warp + 8 * k;
+                const bool act = (row > j) && (row < nb) && !(ownerA && row == jn);
+                const double uu = act ? ua[k] : 0.0;
+                a[k][0] = fma(-(uu * q0), dinv, a[k][0]);
+                a[k][1] = fma(-(uu * q1), dinv, a[k][1]);
+            }
+            // ---- the column that switches from T-type to X-type at this step (one lane per warp)
+            if (sw0 || sw1) {
+#pragma unroll
+                for (int k = 0; k < TILE_RPW; k++) {
+                    const int row = warp + 8 * k;
+                    if (!(ownerA && row == jn)) {
+                        const bool act = (row > j) && (row < nb);
+                        const double lij = act ? ua[k] * dinv : 0.0;
+                        if (act) Tf[row * NBP + j] = lij;
+                        const double xi = act ? -lij : ((row == j) ? 1.0 : 0.0);   // X[row][j] after this step
+                        if (sw0) a[k][0] = xi; else a[k][1] = xi;
+                    }
                 }
             }
         } else {
-            const double a11 = Tf[j * NBP + j], a21 = Tf[(j + 1) * NBP + j], a22 = Tf[(j + 1) * NBP + j + 1];
-            if (tid == 0) {
-                sda[j] = a11; sdb[j] = a21; sda[j + 1] = a22; sdb[j + 1] = 0.0;
-                skind[j] = 1; skind[j + 1] = 2;
+            // ================= slow step: second-level test / interchange / 2x2 pivot, in shared memory ==========
+#ifdef TILE_PROF
+            nslow++;
+#endif
+#pragma unroll
+            for (int k = 0; k < TILE_RPW; k++) {
+                const int row = warp + 8 * k;
+                if (m0 >= j) Tf[row * NBP + m0] = a[k][0]; else Xf[row * NBP + m0] = a[k][0];
+                if (m1 >= j) Tf[row * NBP + m1] = a[k][1]; else Xf[row * NBP + m1] = a[k][1];
             }
-            // LAPACK's scaled 2x2 inverse (dsytf2): robust against overflow of the determinant
-            const double d11 = a22 / a21, d22 = a11 / a21;
-            const double tt = 1.0 / (d11 * d22 - 1.0);
-            const double d21i = tt / a21;
-            const double pj0 = P0[j * NBP + m0], pj1 = P1[j * NBP + m1];
-            const double pk0 = P0[(j + 1) * NBP + m0], pk1 = P1[(j + 1) * NBP + m1];
-            const double ua = Tf[j * NBP + ra], va = Tf[(j + 1) * NBP + ra];
-            const double ub = Tf[j * NBP + rb], vb = Tf[(j + 1) * NBP + rb];
-            na0 = P0[ra * NBP + m0]; na1 = P1[ra * NBP + m1];
-            nb0 = P0[rb * NBP + m0]; nb1 = P1[rb * NBP + m1];
-            if (ra > kk && ra < nb) {
-                na0 -= d21i * ((d11 * (ua * pj0) + d22 * (va * pk0)) - (va * pj0 + ua * pk0));
-                na1 -= d21i * ((d11 * (ua * pj1) + d22 * (va * pk1)) - (va * pj1 + ua * pk1));
-                P0[ra * NBP + m0] = na0; P1[ra * NBP + m1] = na1;
-                if (m0 == j || m1 == j) Tf[ra * NBP + j] = d21i * (d11 * ua - va);
-                if (m0 == j + 1 || m1 == j + 1) Tf[ra * NBP + j + 1] = d21i * (d22 * va - ua);
+            __syncthreads();
+            if (warp == 0) {
+                // second-level test of LAPACK dsytf2 (needs row r)
+                const TileDec dec = sdec[par];
+                int kp = j, kstep = 1;
+                if (dec.code & 1) {
+                    const int r = dec.r;
+                    const int a0 = j + lane, a1 = a0 + 32;
+                    double rm = 0.0;
+                    if (a0 < nb && a0 != r) rm = fabs(Tf[r * NBP + a0]);
+                    if (a1 < nb && a1 != r) rm = fmax(rm, fabs(Tf[r * NBP + a1]));
+                    rm = warp_absmax_bits(rm);
+                    if (dec.absakk * rm >= BK_ALPHA * dec.colmax * dec.colmax) { kp = j; kstep = 1; }
+                    else if (fabs(Tf[r * NBP + r]) >= BK_ALPHA * rm) { kp = r; kstep = 1; }
+                    else { kp = r; kstep = 2; }
+                }
+                if (lane == 0) { s_kp2 = kp; s_kstep2 = kstep; }
             }
-            if (rb > kk && rb < nb) {
-                nb0 -= d21i * ((d11 * (ub * pj0) + d22 * (vb * pk0)) - (vb * pj0 + ub * pk0));
-                nb1 -= d21i * ((d11 * (ub * pj1) + d22 * (vb * pk1)) - (vb * pj1 + ub * pk1));
-                P0[rb * NBP + m0] = nb0; P1[rb * NBP + m1] = nb1;
-                if (m0 == j || m1 == j) Tf[rb * NBP + j] = d21i * (d11 * ub - vb);
-                if (m0 == j + 1 || m1 == j + 1) Tf[rb * NBP + j + 1] = d21i * (d22 * vb - ub);
+            __syncthreads();
+            const int kp = s_kp2, kstep = s_kstep2;
+            const int kk = j + kstep - 1;
+            if (kp != kk) {   // symmetric interchange kk <-> kp on T and X (rows, then columns)
+                if (tid < NB) {
+                    double t0 = Tf[kk * NBP + tid]; Tf[kk * NBP + tid] = Tf[kp * NBP + tid]; Tf[kp * NBP + tid] = t0;
+                    double x0 = Xf[kk * NBP + tid]; Xf[kk * NBP + tid] = Xf[kp * NBP + tid]; Xf[kp * NBP + tid] = x0;
+                }
+                __syncthreads();
+                if (tid < NB) {
+                    double t0 = Tf[tid * NBP + kk]; Tf[tid * NBP + kk] = Tf[tid * NBP + kp]; Tf[tid * NBP + kp] = t0;
+                    double x0 = Xf[tid * NBP + kk]; Xf[tid * NBP + kk] = Xf[tid * NBP + kp]; Xf[tid * NBP + kp] = x0;
+                }
+                if (tid == 0) { int p = sperm[kk]; sperm[kk] = sperm[kp]; sperm[kp] = p; }
+                __syncthreads();
             }
-            // (T[j+1][j] keeps a21 until the output stage: other warps may still be reading it)
-        }
-        // ---- pipelined pivot search for the next step by the warp that owns row jn (values still in registers;
-        //      lanes whose column is <= kk hold X values there, the search only looks at columns > jn > kk)
-        if (jn < nb) {
-            if (ra == jn) tile_search(jn, nb, lane, na0, na1, &sdec[par ^ 1]);
-            else if (rb == jn) tile_search(jn, nb, lane, nb0, nb1, &sdec[par ^ 1]);
+            double* P0 = (m0 > kk) ? Tf : Xf;
+            double* P1 = (m1 > kk) ? Tf : Xf;
+            if (kstep == 1) {
+                const double d = Tf[j * NBP + j];
+                const double dinv = (d != 0.0) ? 1.0 / d : 0.0;
+                if (tid == 0) { sda[j] = d; sdb[j] = 0.0; skind[j] = 0; }
+                const double pj0 = P0[j * NBP + m0], pj1 = P1[j * NBP + m1];
+#pragma unroll
+                for (int k = 0; k < TILE_RPW; k++) {
+                    const int row = warp + 8 * k;
+                    if (row > j && row < nb && d != 0.0) {
+                        const double ur = Tf[j * NBP + row];
+                        P0[row * NBP + m0] = fma(-(ur * pj0), dinv, P0[row * NBP + m0]);
+                        P1[row * NBP + m1] = fma(-(ur * pj1), dinv, P1[row * NBP + m1]);
+                        if (m0 == j || m1 == j) Tf[row * NBP + j] = ur * dinv;
+                    }
+                }
+            } else {
+                const double a11 = Tf[j * NBP + j], a21 = Tf[(j + 1) * NBP + j], a22 = Tf[(j + 1) * NBP + j + 1];
+                if (tid == 0) {
+                    sda[j] = a11; sdb[j] = a21; sda[j + 1] = a22; sdb[j + 1] = 0.0;
+                    skind[j] = 1; skind[j + 1] = 2;
+                }
+                // LAPACK's scaled 2x2 inverse (dsytf2): robust against overflow of the determinant
+                const double d11 = a22 / a21, d22 = a11 / a21;
+                const double tt = 1.0 / (d11 * d22 - 1.0);
+                const double d21i = tt / a21;
+                const double pj0 = P0[j * NBP + m0], pj1 = P1[j * NBP + m1];
+                const double pk0 = P0[(j + 1) * NBP + m0], pk1 = P1[(j + 1) * NBP + m1];
+#pragma unroll
+                for (int k = 0; k < TILE_RPW; k++) {
+                    const int row = warp + 8 * k;
+                    if (row > kk && row < nb) {
+                        const double u = Tf[j * NBP + row], v = Tf[(j + 1) * NBP + row];
+                        P0[row * NBP + m0] -= d21i * ((d11 * (u * pj0) + d22 * (v * pk0)) - (v * pj0 + u * pk0));
+                        P1[row * NBP + m1] -= d21i * ((d11 * (u * pj1) + d22 * (v * pk1)) - (v * pj1 + u * pk1));
+                        if (m0 == j || m1 == j) Tf[row * NBP + j] = d21i * (d11 * u - v);
+                        if (m0 == j + 1 || m1 == j + 1) Tf[row * NBP + j + 1] = d21i * (d22 * v - u);
+                    }
+                }
+                // (T[j+1][j] keeps a21 until the output stage)
+            }
+            __syncthreads();
+            jn = j + kstep;
+#pragma unroll
+            for (int k = 0; k < TILE_RPW; k++) {
+                const int row = warp + 8 * k;
+                a[k][0] = (m0 >= jn) ? Tf[row * NBP + m0] : Xf[row * NBP + m0];
+                a[k][1] = (m1 >= jn) ? Tf[row * NBP + m1] : Xf[row * NBP + m1];
+                if (row == jn && jn < nb) {
+                    double* pw = prow0 + (par ^ 1) * NB;
+                    pw[m0] = (m0 == jn) ? 1.0 : a[k][0];
+                    pw[m1] = (m1 == jn) ? 1.0 : a[k][1];
+                    tile_search(jn, nb, lane, a[k][0], a[k][1], &sdec[par ^ 1]);
+                }
+            }
         }
         __syncthreads();
         j = jn;
         par ^= 1;
     }
+    // pivoting loop: all columns < nb have switched, the registers hold X
+    if (!fast_ok) {
+#pragma unroll
+        for (int k = 0; k < TILE_RPW; k++) {
+            const int row = warp + 8 * k;
+            if (m0 < nb) Xf[row * NBP + m0] = a[k][0];
+            if (m1 < nb) Xf[row * NBP + m1] = a[k][1];
+        }
+    }
+    __syncthreads();
+#ifdef TILE_PROF
+    tp2 = clock64();
+#endif
 
     // ---- outputs
     // LinvP[r][perm[m]] = X[r][m]   (column scatter folds the permutation into the inverse)
@@ -279,12 +547,7 @@ __global__ void __launch_bounds__(TILE_THREADS) ldlt_tile_kernel(double* __restr
         const int r = idx / NB, m = idx % NB;
         LinvP[r * NB + sperm[m]] = (m <= r) ? Xf[r * NBP + m] : 0.0;
     }
-    // L back into the strictly-lower part of the tile, D on the diagonal (diagnostics / tests)
-    for (int idx = tid; idx < nb * nb; idx += TILE_THREADS) {
-        const int i = idx / nb, jj = idx % nb;
-        if (i > jj) A[(size_t)i * ld + jj] = (skind[jj] == 1 && i == jj + 1) ? 0.0 : Tf[i * NBP + jj];
-        else if (i == jj) A[(size_t)i * ld + jj] = sda[i];
-    }
+    // (the tile's own L is not written back: every consumer of a diagonal tile uses LinvP and the D^-1 blocks)
     if (tid < NB) {
         const int p = tid;
         double ia = 0.0, ib = 0.0;
@@ -340,6 +603,11 @@ __global__ void __launch_bounds__(TILE_THREADS) ldlt_tile_kernel(double* __restr
             dstat[0] = fmin(dstat[0], mn); dstat[1] = fmax(dstat[1], mx);
         }
     }
+#ifdef TILE_PROF
+    __syncthreads();
+    tp3 = clock64();
+    if (tid == 0) printf("TILE_PROF nb=%d load=%lld loop=%lld out=%lld slow_steps=%d fast_ok=%d\n", nb, tp1 - tp0, tp2 - tp1, tp3 - tp2, nslow, fast_ok);
+#endif
 }
 
 // Fused panel step for 64 rows per CTA (4 warps, DMMA):  W = B * LinvP^T  (W = Lpanel * D) and
