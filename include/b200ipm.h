@@ -61,6 +61,7 @@ typedef struct b200ipm_step_info {
     int    soc_tried, soc_accepted;  /* pyipm.py:1464-1489 / 1516-1536 */
     int    signal;                   /* 0 ok, -2 bad direction (pyipm.py:1502,1548) */
     int    eq_reg;                   /* 1 if the eq-multiplier block was regularised (pyipm.py:1383-1389) */
+    int    n_neg_first, n_zero_first;/* inertia of the FIRST (delta = 0) attempt, i.e. what pyipm.py:1381 tests */
     float  ms_eval, ms_assemble, ms_factor, ms_solve, ms_search, ms_total;   /* CUDA-event phase times */
     float  ms_hess_kernel, ms_condense_kernel;   /* the two SYRK-shaped fp64 contractions, per launch */
 } b200ipm_step_info;

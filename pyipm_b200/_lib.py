@@ -34,6 +34,7 @@ class StepInfo(C.Structure):
                 ('rcond', C.c_double), ('resid', C.c_double), ('con_l1', C.c_double),
                 ('n_neg', C.c_int), ('n_zero', C.c_int), ('n_factor', C.c_int), ('n_backtracks', C.c_int),
                 ('soc_tried', C.c_int), ('soc_accepted', C.c_int), ('signal', C.c_int), ('eq_reg', C.c_int),
+                ('n_neg_first', C.c_int), ('n_zero_first', C.c_int),
                 ('ms_eval', C.c_float), ('ms_assemble', C.c_float), ('ms_factor', C.c_float), ('ms_solve', C.c_float),
                 ('ms_search', C.c_float), ('ms_total', C.c_float), ('ms_hess_kernel', C.c_float),
                 ('ms_condense_kernel', C.c_float)]

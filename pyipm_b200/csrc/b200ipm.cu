@@ -44,6 +44,8 @@ struct b200ipm_engine {
     double *ycur = nullptr, *ycor = nullptr, *rho = nullptr, *dz = nullptr, *wx = nullptr, *jt = nullptr;
     double *Hb = nullptr;   // W + dci S dci'  (D x ldW), without delta
     double reg_cur = 0, delta_eff = 0;
+    bool strict_retry = false;
+    int n_strict = 0;        // number of strict re-factorisations triggered by a poor residual
     LdltWs F;               // condensed KKT factorisation (order Kc)
     LdltWs F2;              // pseudo-inverse / second-order-correction systems (lazy)
     bool F2_ready = false;
@@ -245,6 +247,7 @@ static int factor_regularised(Eng* h, b200ipm_step_info* info) {
     RET(factor_once(h, 0.0, 0.0, &n_neg, &n_zero, &rcond));
     nfac++;
     const double rcond0 = rcond;
+    if (info) { info->n_neg_first = n_neg; info->n_zero_first = n_zero; }
     int eq_reg = 0;
     if (rcond <= h->p.eps || n_neg != M) {
         double reg = 0.0;
@@ -324,6 +327,21 @@ static int solve_direction(Eng* h, b200ipm_step_info* info) {
         RET(condensed_solve(h, h->rho, h->ycor));
         axpby_kernel<<<cdiv(K, 256), 256, 0, h->st>>>(K, 1.0, h->ycur, 1.0, h->ycor, h->ycur);
         LAUNCHED();
+    }
+    // safety net for the relaxed pivot threshold: a poor refined residual triggers ONE strict (Bunch-Kaufman
+    // threshold) re-factorisation of the same matrix and a fresh solve
+    RET(fetch_red(h, h->red + 8, 1));
+    if (!(h->h_red[0] <= 1e-7 * std::max(1.0, bnorm)) && h->F.pivot_u < 0.64 && !h->strict_retry) {
+        const double u_save = h->F.pivot_u;
+        h->F.pivot_u = 0.6403882032022076;
+        h->strict_retry = true;
+        RET(build_kc(h, h->delta_eff, h->reg_cur));
+        RET(ldlt_factor(h->F));
+        int r = solve_direction(h, info);
+        h->strict_retry = false;
+        h->F.pivot_u = u_save;
+        h->n_strict++;
+        return r;
     }
     flip_kernel<<<cdiv(K, 256), 256, 0, h->st>>>(h->D, h->N, K, h->ycur, h->dz);
     LAUNCHED();
@@ -1181,7 +1199,7 @@ int b200ipm_ldlt_tile_factor(b200ipm_ldlt_handle h, double* tile_dev, int ld, in
     // dblk_dev layout: [dinv_a (NB) | dinv_b (NB) | d_a (NB) | d_b (NB)] followed by NB ints of `kind`
     int* kind = reinterpret_cast<int*>(dblk_dev + 4 * NB);
     ldlt_tile_kernel<<<1, TILE_THREADS, TILE_SMEM, h->st>>>(tile_dev, ld, nb, linv_dev, dblk_dev, dblk_dev + NB, dblk_dev + 2 * NB,
-                                                   dblk_dev + 3 * NB, kind, perm_dev, h->F.counts, h->F.dstat);
+                                                   dblk_dev + 3 * NB, kind, perm_dev, h->F.counts, h->F.dstat, h->F.pivot_u);
     LAUNCHED();
     if (counts) {
         int cnt[4];

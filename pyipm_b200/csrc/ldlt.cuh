@@ -42,6 +42,7 @@ struct LdltWs {
     double *yv = nullptr, *zv = nullptr, *xv = nullptr;
     unsigned epoch = 0;
     cudaStream_t st = nullptr;
+    double pivot_u = 0.01;     // threshold of the fast (unpivoted) tile attempt: accept step j iff |d_j| >= u * max_i |T[i][j]|
 };
 
 inline int ldlt_alloc(LdltWs& w, int n, cudaStream_t st) {
@@ -160,8 +161,7 @@ template <int JB>
 __device__ __forceinline__ void tile_fast_block(double (&b)[TILE_RPW][2], int nb, int lane, int warp, int tid,
                                                 double* __restrict__ Tf, double* __restrict__ prow0,
                                                 double* __restrict__ pdiag, double* __restrict__ sda,
-                                                int& viol, bool& allpos, bool& allneg) {
-    const double BK_ALPHA = 0.6403882032022076;
+                                                int& viol, bool& allpos, bool& allneg, const double pivot_u) {
     if (JB * 8 >= nb) return;
     const int r0 = lane, r1 = lane + 32;
     for (int w8 = 0; w8 < 8; w8++) {
@@ -179,7 +179,7 @@ __device__ __forceinline__ void tile_fast_block(double (&b)[TILE_RPW][2], int nb
         const double g1 = act1 ? u1 * dinv : 0.0;
         if (warp == 0) {   // sticky first-level Bunch-Kaufman check on the pivot column (= pivot row by symmetry)
             const double thr = fabs(d);
-            viol |= ((act0 && BK_ALPHA * fabs(u0) > thr) || (act1 && BK_ALPHA * fabs(u1) > thr)) ? 1 : 0;
+            viol |= ((act0 && pivot_u * fabs(u0) > thr) || (act1 && pivot_u * fabs(u1) > thr)) ? 1 : 0;
         }
         allpos = allpos && (d > 0.0);
         allneg = allneg && (d < 0.0);
@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(TILE_THREADS) ldlt_tile_kernel(double* __restr
                                                                  double* __restrict__ dinv_b, double* __restrict__ d_a,
                                                                  double* __restrict__ d_b, int* __restrict__ kind,
                                                                  int* __restrict__ perm_out, int* __restrict__ counts,
-                                                                 double* __restrict__ dstat) {
+                                                                 double* __restrict__ dstat, const double pivot_u) {
     extern __shared__ __align__(16) double tsm[];
     double* Tf = tsm;                 // T[i][m] = Tf[i * NBP + m]   (authoritative only inside slow steps / at the ends)
     double* Xf = tsm + NB * NBP;      // X[i][m] = Xf[i * NBP + m]
@@ -277,11 +277,15 @@ __global__ void __launch_bounds__(TILE_THREADS) ldlt_tile_kernel(double* __restr
     __shared__ double pdiag[4];   // [parity][d, 1/d] of the published pivot
 
     // =====================================================================================================
-    // FAST ATTEMPT: no pivot search on the critical path.  The tile is eliminated in natural order (what
-    // Bunch-Kaufman does whenever its first-level test |d_j| >= alpha * max_i |T[i][j]| holds); every lane checks
-    // that test on the pivot-row entries it reads anyway and keeps a sticky flag.  The attempt is accepted if no
-    // test failed, or if all pivots came out with the same sign (the tile was definite, so the unpivoted
-    // elimination is unconditionally stable).  Otherwise the tile is reloaded and the pivoting loop below runs.
+    // FAST ATTEMPT: no pivot search on the critical path.  The tile is eliminated in natural order with THRESHOLD
+    // pivoting: step j is acceptable iff |d_j| >= u * max_i |T[i][j]| (u = pivot_u, default 0.01 as in the
+    // multifrontal codes interior-point solvers use; u = 0.64 would be Bunch-Kaufman's first-level test).  Every
+    // lane checks the test on the pivot-column entries it reads anyway and keeps a sticky flag.  The attempt is
+    // accepted if no test failed, or if all pivots came out with the same sign (the tile was definite, so the
+    // unpivoted elimination is unconditionally stable).  Otherwise the tile is reloaded and the full
+    // Bunch-Kaufman loop below runs.  Element growth is bounded by (1 + 1/u) per accepted step; accuracy is
+    // restored by the iterative refinement against the unreduced KKT system, and the engine re-factors with
+    // u = 0.64 if the refined residual is ever poor.
     // Per step the serial chain is: barrier -> LDS pivot row -> rcp -> 2 FMA on the next pivot row -> STS.
     // =====================================================================================================
     int fast_ok = 0;
@@ -304,14 +308,14 @@ __global__ void __launch_bounds__(TILE_THREADS) ldlt_tile_kernel(double* __restr
         __syncthreads();
         int viol = 0;
         bool allpos = true, allneg = true;
-        tile_fast_block<0>(b, nb, lane, warp, tid, Tf, prow0, pdiag, sda, viol, allpos, allneg);
-        tile_fast_block<1>(b, nb, lane, warp, tid, Tf, prow0, pdiag, sda, viol, allpos, allneg);
-        tile_fast_block<2>(b, nb, lane, warp, tid, Tf, prow0, pdiag, sda, viol, allpos, allneg);
-        tile_fast_block<3>(b, nb, lane, warp, tid, Tf, prow0, pdiag, sda, viol, allpos, allneg);
-        tile_fast_block<4>(b, nb, lane, warp, tid, Tf, prow0, pdiag, sda, viol, allpos, allneg);
-        tile_fast_block<5>(b, nb, lane, warp, tid, Tf, prow0, pdiag, sda, viol, allpos, allneg);
-        tile_fast_block<6>(b, nb, lane, warp, tid, Tf, prow0, pdiag, sda, viol, allpos, allneg);
-        tile_fast_block<7>(b, nb, lane, warp, tid, Tf, prow0, pdiag, sda, viol, allpos, allneg);
+        tile_fast_block<0>(b, nb, lane, warp, tid, Tf, prow0, pdiag, sda, viol, allpos, allneg, pivot_u);
+        tile_fast_block<1>(b, nb, lane, warp, tid, Tf, prow0, pdiag, sda, viol, allpos, allneg, pivot_u);
+        tile_fast_block<2>(b, nb, lane, warp, tid, Tf, prow0, pdiag, sda, viol, allpos, allneg, pivot_u);
+        tile_fast_block<3>(b, nb, lane, warp, tid, Tf, prow0, pdiag, sda, viol, allpos, allneg, pivot_u);
+        tile_fast_block<4>(b, nb, lane, warp, tid, Tf, prow0, pdiag, sda, viol, allpos, allneg, pivot_u);
+        tile_fast_block<5>(b, nb, lane, warp, tid, Tf, prow0, pdiag, sda, viol, allpos, allneg, pivot_u);
+        tile_fast_block<6>(b, nb, lane, warp, tid, Tf, prow0, pdiag, sda, viol, allpos, allneg, pivot_u);
+        tile_fast_block<7>(b, nb, lane, warp, tid, Tf, prow0, pdiag, sda, viol, allpos, allneg, pivot_u);
         const int anyviol = __syncthreads_or(viol);
         // accept: no first-level violation anywhere, or a definite tile (all pivots of one sign, none zero)
         fast_ok = ((!anyviol) || allpos || allneg) ? 1 : 0;
@@ -718,7 +722,7 @@ inline int ldlt_factor(LdltWs& w) {
             double* Akk = w.A + (size_t)k0 * ld + k0;
             double* Lk = w.LinvP + (size_t)k * NB * NB;
             ldlt_tile_kernel<<<1, TILE_THREADS, TILE_SMEM, st>>>(Akk, ld, nb, Lk, ia + k0, ib + k0, da + k0, db + k0, w.kind + k0,
-                                                        nullptr, w.counts, w.dstat);
+                                                        nullptr, w.counts, w.dstat, w.pivot_u);
             LAUNCHED();
             const int rows = n - k1;
             if (rows <= 0) break;

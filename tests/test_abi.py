@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     # sizes implied by include/b200ipm.h (10 doubles + 4 ints; 18 doubles + 8 ints + 8 floats)
     assert ctypes.sizeof(_lib.Params) == 10 * 8 + 4 * 4
-    assert ctypes.sizeof(_lib.StepInfo) == 18 * 8 + 8 * 4 + 8 * 4
+    assert ctypes.sizeof(_lib.StepInfo) == 18 * 8 + 10 * 4 + 8 * 4
 
 
 def test_no_cpu_fallback():
