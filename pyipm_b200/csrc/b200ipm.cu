@@ -1241,6 +1241,7 @@ int b200ipm_gemm_nt_update(b200ipm_ldlt_handle h, double* C_dev, int ldc, int ro
     if (!h || !C_dev || !A_dev || !B_dev) return fail_msg("gemm_nt_update: bad arguments");
     if (rows <= 0 || cols <= 0) return 0;
     CU(cudaSetDevice(h->device));
+    if (!lower_only && cols <= 512) return gemm_nt_sub(h->st, C_dev, ldc, rows, cols, A_dev, lda, B_dev, ldb, k);
     GemmArgs u{};
     u.C = C_dev; u.ldc = ldc; u.Cin = C_dev; u.ldcin = ldc; u.n = rows; u.m = cols; u.beta = 1.0;
     u.mode = lower_only ? GEMM_LOWER_ONLY : GEMM_FULL; u.nterms = 1;

@@ -271,6 +271,128 @@ inline int gemm_nt(cudaStream_t st, const GemmArgs& a, bool force_simple = false
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Small-tile variant for the skinny updates on the LDL^T critical path:  C -= A * B^T  in place, C is rows x cols
+// with cols <= a few hundred (the remaining columns of an outer panel, K = 64, or the next panel's 256 columns,
+// K = 256).  With 128 x 128 tiles those launches have fewer CTAs than the GPU has SMs and every CTA is long;
+// 64 x 64 tiles (128 threads, 4 warps x (16 x 64), 3-stage cp.async over K-chunks of 32, two CTAs per SM) spread
+// the same work over all SMs and cut the per-launch latency ~3x.
+constexpr int S_BM = 64, S_BN = 64, S_BK = 32, S_LDS = 36, S_STAGES = 3;
+constexpr int S_SMEM = S_STAGES * (S_BM + S_BN) * S_LDS * 8;
+
+__device__ __forceinline__ void s_load_tile(double* sdst, const double* __restrict__ G, int ld, int row0, int nrows,
+                                            int k0, int K, int tid) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int c = tid + 128 * i;
+        const int row = c >> 4, kc = (c & 15) * 2;
+        const int gr = row0 + row, gk = k0 + kc;
+        int bytes = 0;
+        const double* src = G;
+        if (gr < nrows && gk < K) {
+            bytes = min(16, (K - gk) * 8);
+            src = G + (size_t)gr * ld + gk;
+        }
+        cp_async16(sdst + row * S_LDS + kc, src, bytes);
+    }
+}
+
+__global__ void __launch_bounds__(128, 2) gemm_nt_sub64_kernel(double* __restrict__ C, int ldc, int rows, int cols,
+                                                               const double* __restrict__ A, int lda,
+                                                               const double* __restrict__ B, int ldb, int K) {
+    extern __shared__ __align__(16) double s_smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, tg = lane & 3;
+    const int row0 = blockIdx.y * S_BM, col0 = blockIdx.x * S_BN;
+    double* As = s_smem;
+    double* Bs = s_smem + S_STAGES * S_BM * S_LDS;
+    double acc[2][8][2];
+#pragma unroll
+    for (int a = 0; a < 2; a++)
+#pragma unroll
+        for (int b = 0; b < 8; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
+    const int nk = (K + S_BK - 1) / S_BK;
+#pragma unroll
+    for (int s = 0; s < S_STAGES - 1; s++) {
+        if (s < nk) {
+            s_load_tile(As + s * S_BM * S_LDS, A, lda, row0, rows, s * S_BK, K, tid);
+            s_load_tile(Bs + s * S_BN * S_LDS, B, ldb, col0, cols, s * S_BK, K, tid);
+        }
+        cp_async_commit();
+    }
+    for (int kt = 0; kt < nk; kt++) {
+        cp_async_wait<S_STAGES - 2>();
+        __syncthreads();
+        {
+            const int kn = kt + S_STAGES - 1;
+            if (kn < nk) {
+                const int s = kn % S_STAGES;
+                s_load_tile(As + s * S_BM * S_LDS, A, lda, row0, rows, kn * S_BK, K, tid);
+                s_load_tile(Bs + s * S_BN * S_LDS, B, ldb, col0, cols, kn * S_BK, K, tid);
+            }
+            cp_async_commit();
+        }
+        const int s = kt % S_STAGES;
+        const double* as = As + s * S_BM * S_LDS + (warp * 16 + g) * S_LDS + tg;
+        const double* bs = Bs + s * S_BN * S_LDS + g * S_LDS + tg;
+#pragma unroll
+        for (int kk = 0; kk < S_BK / 4; kk++) {
+            double af[2], bf[8];
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++) af[mt] = as[mt * 8 * S_LDS + kk * 4];
+#pragma unroll
+            for (int nt = 0; nt < 8; nt++) bf[nt] = bs[nt * 8 * S_LDS + kk * 4];
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                for (int nt = 0; nt < 8; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
+        }
+    }
+    cp_async_wait<0>();
+    const bool interior = (row0 + S_BM <= rows) && (col0 + S_BN <= cols) && ((ldc & 1) == 0) &&
+                          ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+#pragma unroll
+    for (int mt = 0; mt < 2; mt++) {
+        const int i = row0 + warp * 16 + mt * 8 + g;
+        if (interior) {
+            double2 cin[8];
+#pragma unroll
+            for (int nt = 0; nt < 8; nt++) cin[nt] = *reinterpret_cast<const double2*>(C + (size_t)i * ldc + col0 + nt * 8 + tg * 2);
+#pragma unroll
+            for (int nt = 0; nt < 8; nt++) {
+                cin[nt].x -= acc[mt][nt][0];
+                cin[nt].y -= acc[mt][nt][1];
+                *reinterpret_cast<double2*>(C + (size_t)i * ldc + col0 + nt * 8 + tg * 2) = cin[nt];
+            }
+        } else if (i < rows) {
+#pragma unroll
+            for (int nt = 0; nt < 8; nt++)
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const int j = col0 + nt * 8 + tg * 2 + e;
+                    if (j < cols) C[(size_t)i * ldc + j] -= acc[mt][nt][e];
+                }
+        }
+    }
+}
+
+// C (rows x cols, in place) -= A (rows x K) * B (cols x K)^T
+inline int gemm_nt_sub(cudaStream_t st, double* C, int ldc, int rows, int cols, const double* A, int lda, const double* B,
+                       int ldb, int K) {
+    if (rows <= 0 || cols <= 0) return 0;
+    const bool ok = !(lda & 1) && !(ldb & 1) && !(reinterpret_cast<uintptr_t>(A) & 15) && !(reinterpret_cast<uintptr_t>(B) & 15);
+    if (ok && rows >= 48) {
+        dim3 grid(cdiv(cols, S_BN), cdiv(rows, S_BM));
+        gemm_nt_sub64_kernel<<<grid, 128, S_SMEM, st>>>(C, ldc, rows, cols, A, lda, B, ldb, K);
+        LAUNCHED();
+        return 0;
+    }
+    GemmArgs u{};
+    u.C = C; u.ldc = ldc; u.Cin = C; u.ldcin = ldc; u.n = rows; u.m = cols; u.beta = 1.0; u.mode = GEMM_FULL; u.nterms = 1;
+    u.t[0] = GemmTerm{A, B, nullptr, lda, ldb, K, -1.0};
+    return gemm_nt(st, u);
+}
+
 // computed tile elements x 2 x sum K  (what one launch is credited with in the roofline)
 inline double gemm_nt_flops(const GemmArgs& a) {
     double ksum = 0;

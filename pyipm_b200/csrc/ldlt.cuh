@@ -42,6 +42,9 @@ struct LdltWs {
     double *yv = nullptr, *zv = nullptr, *xv = nullptr;
     unsigned epoch = 0;
     cudaStream_t st = nullptr;
+    double* Wp2 = nullptr;     // second outer-panel scratch (look-ahead double buffering)
+    cudaStream_t side = nullptr;   // trailing updates beyond the next panel run here, overlapped with the next panel
+    cudaEvent_t ev_panel[2] = {nullptr, nullptr}, ev_upd[2] = {nullptr, nullptr};
     double pivot_u = 0.01;     // threshold of the fast (unpivoted) tile attempt: accept step j iff |d_j| >= u * max_i |T[i][j]|
 };
 
@@ -54,6 +57,12 @@ inline int ldlt_alloc(LdltWs& w, int n, cudaStream_t st) {
     const size_t npad = (size_t)w.nblk * NB;
     CU(cudaMalloc(&w.A, sizeof(double) * (size_t)npad * w.ld));
     CU(cudaMalloc(&w.Wp, sizeof(double) * npad * 256));
+    CU(cudaMalloc(&w.Wp2, sizeof(double) * npad * 256));
+    CU(cudaStreamCreateWithFlags(&w.side, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+        CU(cudaEventCreateWithFlags(&w.ev_panel[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&w.ev_upd[i], cudaEventDisableTiming));
+    }
     CU(cudaMalloc(&w.LinvP, sizeof(double) * (size_t)w.nblk * NB * NB));
     CU(cudaMalloc(&w.dinfo, sizeof(double) * 4 * npad));
     CU(cudaMalloc(&w.kind, sizeof(int) * npad));
@@ -69,7 +78,10 @@ inline int ldlt_alloc(LdltWs& w, int n, cudaStream_t st) {
     return 0;
 }
 inline void ldlt_free(LdltWs& w) {
-    cudaFree(w.A); cudaFree(w.Wp); cudaFree(w.LinvP); cudaFree(w.dinfo); cudaFree(w.kind); cudaFree(w.counts);
+    cudaFree(w.A); cudaFree(w.Wp); cudaFree(w.Wp2);
+    if (w.side) cudaStreamDestroy(w.side);
+    for (int i = 0; i < 2; i++) { if (w.ev_panel[i]) cudaEventDestroy(w.ev_panel[i]); if (w.ev_upd[i]) cudaEventDestroy(w.ev_upd[i]); }
+    cudaFree(w.LinvP); cudaFree(w.dinfo); cudaFree(w.kind); cudaFree(w.counts);
     cudaFree(w.dstat); cudaFree(w.flags); cudaFree(w.ticket); cudaFree(w.yv); cudaFree(w.zv); cudaFree(w.xv);
     w = LdltWs();
 }
@@ -700,23 +712,30 @@ inline int ldlt_init_attrs() {
     CU(cudaFuncSetAttribute(ldlt_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM));
     CU(cudaFuncSetAttribute(ldlt_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM));
     CU(cudaFuncSetAttribute(gemm_nt_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM));
+    CU(cudaFuncSetAttribute(gemm_nt_sub64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S_SMEM));
     return 0;
 }
 
-// Factor w.A in place (two-level blocking).  Outer panels of NBO = 256 columns: inside a panel the 64-wide tile
-// steps update only the panel's own remaining columns (K = 64, small), the trailing matrix is updated ONCE per
-// outer panel with K = 256 -- 4x less read-modify-write traffic on A22 and a contraction long enough to keep the
-// DMMA pipeline full.  Results stay on the device (counts/dstat) until the caller needs the inertia decision.
+// Factor w.A in place (two-level blocking with look-ahead).  Outer panels of NBO = 256 columns: inside a panel the
+// 64-wide tile steps update only the panel's own remaining columns (K = 64, small); the trailing matrix is updated
+// ONCE per outer panel with K = 256 -- 4x less read-modify-write traffic on A22 and a contraction long enough to keep
+// the DMMA pipeline full.  The serial chain is the 72 tile steps, so the trailing update is split: the next
+// panel's 256 columns are updated on the main stream (the chain needs them), everything to the right of them on a
+// side stream, overlapped with the next panel's tile steps (W is double buffered).  Results stay on the device
+// (counts/dstat) until the caller needs the inertia decision.
 constexpr int NBO = 256;
 inline int ldlt_factor(LdltWs& w) {
-    cudaStream_t st = w.st;
+    cudaStream_t st = w.st, sd = w.side;
     const int n = w.n, ld = w.ld;
     const size_t npad = (size_t)w.nblk * NB;
     double *ia = w.dinfo, *ib = w.dinfo + npad, *da = w.dinfo + 2 * npad, *db = w.dinfo + 3 * npad;
     ldlt_reset_kernel<<<1, 1, 0, st>>>(w.counts, w.dstat, w.ticket);
     LAUNCHED();
-    for (int c0 = 0; c0 < n; c0 += NBO) {
+    int p = 0;
+    bool side_used = false;
+    for (int c0 = 0; c0 < n; c0 += NBO, p++) {
         const int c1 = min(c0 + NBO, n);
+        double* Wb = (p & 1) ? w.Wp2 : w.Wp;
         for (int k0 = c0; k0 < c1; k0 += NB) {
             const int k = k0 / NB, nb = min(NB, n - k0), k1 = k0 + nb;
             double* Akk = w.A + (size_t)k0 * ld + k0;
@@ -727,27 +746,38 @@ inline int ldlt_factor(LdltWs& w) {
             const int rows = n - k1;
             if (rows <= 0) break;
             double* B = w.A + (size_t)k1 * ld + k0;                      // rows below the tile
-            double* Wt = w.Wp + (size_t)k1 * NBO + (k0 - c0);           // W = L * D for this tile step
+            double* Wt = Wb + (size_t)k1 * NBO + (k0 - c0);             // W = L * D for this tile step
             ldlt_panel_kernel<<<cdiv(rows, NB), 128, PANEL_SMEM, st>>>(B, ld, rows, Lk, ia + k0, ib + k0, w.kind + k0, Wt, NBO);
             LAUNCHED();
             const int mcols = c1 - k1;                                   // remaining columns of this outer panel
-            if (mcols > 0) {
-                GemmArgs u{};
-                u.C = w.A + (size_t)k1 * ld + k1; u.ldc = ld; u.Cin = u.C; u.ldcin = ld; u.n = rows; u.m = mcols;
-                u.beta = 1.0; u.mode = GEMM_FULL; u.nterms = 1;
-                u.t[0] = GemmTerm{Wt, B, nullptr, NBO, ld, NB, -1.0};
-                RET(gemm_nt(st, u));
-            }
+            if (mcols > 0) RET(gemm_nt_sub(st, w.A + (size_t)k1 * ld + k1, ld, rows, mcols, Wt, NBO, B, ld, NB));
         }
         const int rows2 = n - c1;
         if (rows2 <= 0) break;
-        // A22 -= W_panel * L_panel^T   (lower tiles only, K = c1 - c0)
-        GemmArgs u{};
-        u.C = w.A + (size_t)c1 * ld + c1; u.ldc = ld; u.Cin = u.C; u.ldcin = ld; u.n = rows2; u.m = rows2;
-        u.beta = 1.0; u.mode = GEMM_LOWER_ONLY; u.nterms = 1;
-        u.t[0] = GemmTerm{w.Wp + (size_t)c1 * NBO, w.A + (size_t)c1 * ld + c0, nullptr, NBO, ld, c1 - c0, -1.0};
-        RET(gemm_nt(st, u));
+        const int kw = c1 - c0;
+        const double* Wpan = Wb + (size_t)c1 * NBO;                      // W rows c1..n of this outer panel
+        const double* Lpan = w.A + (size_t)c1 * ld + c0;                 // L rows c1..n
+        const int na = min(NBO, rows2);                                  // width of the next outer panel
+        // (a) next panel's columns, main stream: A[c1:, c1:c1+na] -= W L[c1:c1+na]^T.  The side-stream update of the
+        // PREVIOUS panel read-modify-wrote the same columns, so it has to be complete first (this wait also protects
+        // the W buffer panel p+1 is about to overwrite: it was read by that same side-stream update).
+        if (p >= 1 && side_used) CU(cudaStreamWaitEvent(st, w.ev_upd[(p - 1) & 1], 0));
+        RET(gemm_nt_sub(st, w.A + (size_t)c1 * ld + c1, ld, rows2, na, Wpan, NBO, Lpan, ld, kw));
+        // (b) everything to the right of the next panel, side stream (lower tiles only), overlapped with panel p+1
+        const int rows3 = rows2 - na;
+        if (rows3 > 0) {
+            CU(cudaEventRecord(w.ev_panel[p & 1], st));
+            CU(cudaStreamWaitEvent(sd, w.ev_panel[p & 1], 0));
+            GemmArgs u{};
+            u.C = w.A + (size_t)(c1 + na) * ld + (c1 + na); u.ldc = ld; u.Cin = u.C; u.ldcin = ld; u.n = rows3; u.m = rows3;
+            u.beta = 1.0; u.mode = GEMM_LOWER_ONLY; u.nterms = 1;
+            u.t[0] = GemmTerm{Wpan + (size_t)na * NBO, Lpan + (size_t)na * ld, nullptr, NBO, ld, kw, -1.0};
+            RET(gemm_nt(sd, u));
+            CU(cudaEventRecord(w.ev_upd[p & 1], sd));
+            side_used = true;
+        }
     }
+    if (side_used) CU(cudaStreamWaitEvent(st, w.ev_upd[(p - 1) & 1], 0));   // join (no-op if already waited)
     return 0;
 }
 
