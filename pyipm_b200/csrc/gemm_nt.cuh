@@ -43,7 +43,7 @@ struct GemmArgs {
     GemmTerm t[3];
 };
 
-constexpr int G_BM = 128, G_BN = 128, G_BK = 16, G_LDS = 20, G_STAGES = 4;
+constexpr int G_BM = 128, G_BN = 128, G_BK = 32, G_LDS = 36, G_STAGES = 3;
 constexpr int G_SMEM = G_STAGES * ((G_BM + G_BN) * G_LDS + G_BK) * 8;
 
 __device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc, int bytes) {
@@ -65,13 +65,15 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                  : "d"(a), "d"(b));
 }
 
-// one operand tile: 128 rows x 16 doubles, 1024 16-byte chunks, 4 per thread; rows/k beyond the edge zero-fill
+// one operand tile: 128 rows x 16 doubles, 1024 16-byte chunks spread over the CTA; rows/k beyond the edge zero-fill
+template <int THREADS>
 __device__ __forceinline__ void g_load_tile(double* sdst, const double* __restrict__ G, int ld, int row0, int nrows,
                                             int k0, int K, int tid) {
+    constexpr int CPR = G_BK / 2;                      // 16-byte chunks per row
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const int c = tid + 256 * i;
-        const int row = c >> 3, kc = (c & 7) * 2;
+    for (int i = 0; i < G_BM * CPR / THREADS; i++) {
+        const int c = tid + THREADS * i;
+        const int row = c / CPR, kc = (c % CPR) * 2;
         const int gr = row0 + row, gk = k0 + kc;
         int bytes = 0;
         const double* src = G;
@@ -92,24 +94,29 @@ __device__ __forceinline__ void g_load_w(double* sdst, const double* __restrict_
     }
 }
 
-__global__ void __launch_bounds__(256, 1) gemm_nt_dmma_kernel(const GemmArgs a) {
+// Warp layout NWM x NWN over the 128 x 128 CTA tile (warp tile = (128/NWM) x (128/NWN)).  Measured on B200 at config 3:
+// 2 x 4 (256 threads, 64 x 32 warp tiles) 26.0 TF/s, 4 x 4 (512 threads, 32 x 32 warp tiles) 24.3 TF/s.
+constexpr int G_NWM = 2, G_NWN = 4, G_THREADS = 32 * G_NWM * G_NWN;
+constexpr int G_MT = G_BM / (8 * G_NWM), G_NT = G_BN / (8 * G_NWN);
+__global__ void __launch_bounds__(G_THREADS, 1) gemm_nt_dmma_kernel(const GemmArgs a) {
     extern __shared__ __align__(16) double g_smem[];
     const int ti = blockIdx.y, tj = blockIdx.x;
     if (a.mode == GEMM_UPPER_MIRROR && ti > tj) return;
     if (a.mode == GEMM_LOWER_ONLY && ti < tj) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = warp >> 2, wn = warp & 3;
+    const int wm = warp / G_NWN, wn = warp % G_NWN;
+    constexpr int WTM = G_BM / G_NWM, WTN = G_BN / G_NWN;
     const int g = lane >> 2, tg = lane & 3;
     const int row0 = ti * G_BM, col0 = tj * G_BN;
     double* As = g_smem;
     double* Bs = g_smem + G_STAGES * G_BM * G_LDS;
     double* Wsm = g_smem + G_STAGES * (G_BM + G_BN) * G_LDS;
 
-    double acc[8][4][2];
+    double acc[G_MT][G_NT][2];
 #pragma unroll
-    for (int i = 0; i < 8; i++)
+    for (int i = 0; i < G_MT; i++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int j = 0; j < G_NT; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
     for (int t = 0; t < a.nterms; t++) {
         const GemmTerm T = a.t[t];
@@ -118,8 +125,8 @@ __global__ void __launch_bounds__(256, 1) gemm_nt_dmma_kernel(const GemmArgs a) 
 #pragma unroll
         for (int s = 0; s < G_STAGES - 1; s++) {
             if (s < nk) {
-                g_load_tile(As + s * G_BM * G_LDS, T.A, T.lda, row0, a.n, s * G_BK, T.K, tid);
-                g_load_tile(Bs + s * G_BN * G_LDS, T.B, T.ldb, col0, a.m, s * G_BK, T.K, tid);
+                g_load_tile<G_THREADS>(As + s * G_BM * G_LDS, T.A, T.lda, row0, a.n, s * G_BK, T.K, tid);
+                g_load_tile<G_THREADS>(Bs + s * G_BN * G_LDS, T.B, T.ldb, col0, a.m, s * G_BK, T.K, tid);
                 if (T.w) g_load_w(Wsm + s * G_BK, T.w, s * G_BK, T.K, tid);
             }
             cp_async_commit();
@@ -131,28 +138,28 @@ __global__ void __launch_bounds__(256, 1) gemm_nt_dmma_kernel(const GemmArgs a) 
                 const int kn = kt + G_STAGES - 1;
                 if (kn < nk) {
                     const int s = kn % G_STAGES;
-                    g_load_tile(As + s * G_BM * G_LDS, T.A, T.lda, row0, a.n, kn * G_BK, T.K, tid);
-                    g_load_tile(Bs + s * G_BN * G_LDS, T.B, T.ldb, col0, a.m, kn * G_BK, T.K, tid);
+                    g_load_tile<G_THREADS>(As + s * G_BM * G_LDS, T.A, T.lda, row0, a.n, kn * G_BK, T.K, tid);
+                    g_load_tile<G_THREADS>(Bs + s * G_BN * G_LDS, T.B, T.ldb, col0, a.m, kn * G_BK, T.K, tid);
                     if (T.w) g_load_w(Wsm + s * G_BK, T.w, kn * G_BK, T.K, tid);
                 }
                 cp_async_commit();
             }
             const int s = kt % G_STAGES;
             const double* ws = Wsm + s * G_BK + tg;
-            const double* as = As + s * G_BM * G_LDS + (wm * 64 + g) * G_LDS + tg;
-            const double* bs = Bs + s * G_BN * G_LDS + (wn * 32 + g) * G_LDS + tg;
+            const double* as = As + s * G_BM * G_LDS + (wm * WTM + g) * G_LDS + tg;
+            const double* bs = Bs + s * G_BN * G_LDS + (wn * WTN + g) * G_LDS + tg;
 #pragma unroll
-            for (int kk = 0; kk < 4; kk++) {
-                double af[8], bf[4];
+            for (int kk = 0; kk < G_BK / 4; kk++) {
+                double af[G_MT], bf[G_NT];
 #pragma unroll
-                for (int mt = 0; mt < 8; mt++) af[mt] = as[mt * 8 * G_LDS + kk * 4];
+                for (int mt = 0; mt < G_MT; mt++) af[mt] = as[mt * 8 * G_LDS + kk * 4];
                 const double wk = T.w ? ws[kk * 4] * T.alpha : T.alpha;
 #pragma unroll
-                for (int nt = 0; nt < 4; nt++) bf[nt] = bs[nt * 8 * G_LDS + kk * 4] * wk;
+                for (int nt = 0; nt < G_NT; nt++) bf[nt] = bs[nt * 8 * G_LDS + kk * 4] * wk;
 #pragma unroll
-                for (int mt = 0; mt < 8; mt++)
+                for (int mt = 0; mt < G_MT; mt++)
 #pragma unroll
-                    for (int nt = 0; nt < 4; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
+                    for (int nt = 0; nt < G_NT; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
             }
         }
         cp_async_wait<0>();
@@ -167,17 +174,17 @@ __global__ void __launch_bounds__(256, 1) gemm_nt_dmma_kernel(const GemmArgs a) 
     const bool interior = vec_ok && !diag_tile && (row0 + G_BM <= a.n) && (col0 + G_BN <= a.m);
     if (interior) {
 #pragma unroll
-        for (int mt = 0; mt < 8; mt++) {
-            const int i = row0 + wm * 64 + mt * 8 + g;
-            const int jb = col0 + wn * 32 + tg * 2;
-            double2 cin[4];
+        for (int mt = 0; mt < G_MT; mt++) {
+            const int i = row0 + wm * WTM + mt * 8 + g;
+            const int jb = col0 + wn * WTN + tg * 2;
+            double2 cin[G_NT];
             if (a.Cin) {
 #pragma unroll
-                for (int nt = 0; nt < 4; nt++)
+                for (int nt = 0; nt < G_NT; nt++)
                     cin[nt] = *reinterpret_cast<const double2*>(a.Cin + (size_t)i * a.ldcin + jb + nt * 8);
             }
 #pragma unroll
-            for (int nt = 0; nt < 4; nt++) {
+            for (int nt = 0; nt < G_NT; nt++) {
                 double2 v = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
                 if (a.Cin) { v.x += a.beta * cin[nt].x; v.y += a.beta * cin[nt].y; }
                 const int j = jb + nt * 8;
@@ -191,25 +198,25 @@ __global__ void __launch_bounds__(256, 1) gemm_nt_dmma_kernel(const GemmArgs a) 
         return;
     }
 #pragma unroll
-    for (int mt = 0; mt < 8; mt++) {
-        const int i = row0 + wm * 64 + mt * 8 + g;
+    for (int mt = 0; mt < G_MT; mt++) {
+        const int i = row0 + wm * WTM + mt * 8 + g;
         if (i >= a.n) continue;
-        double cin[4][2];
+        double cin[G_NT][2];
         if (a.Cin) {
 #pragma unroll
-            for (int nt = 0; nt < 4; nt++)
+            for (int nt = 0; nt < G_NT; nt++)
 #pragma unroll
                 for (int e = 0; e < 2; e++) {
-                    const int j = col0 + wn * 32 + nt * 8 + tg * 2 + e;
+                    const int j = col0 + wn * WTN + nt * 8 + tg * 2 + e;
                     const bool need = (j < a.m) && !(a.mode == GEMM_UPPER_MIRROR && diag_tile && i > j);
                     cin[nt][e] = need ? a.Cin[(size_t)i * a.ldcin + j] : 0.0;
                 }
         }
 #pragma unroll
-        for (int nt = 0; nt < 4; nt++) {
+        for (int nt = 0; nt < G_NT; nt++) {
 #pragma unroll
             for (int e = 0; e < 2; e++) {
-                const int j = col0 + wn * 32 + nt * 8 + tg * 2 + e;
+                const int j = col0 + wn * WTN + nt * 8 + tg * 2 + e;
                 if (j >= a.m) continue;
                 if (a.mode == GEMM_UPPER_MIRROR && diag_tile && i > j) continue;
                 double v = acc[mt][nt][e];
@@ -261,7 +268,7 @@ inline int gemm_nt(cudaStream_t st, const GemmArgs& a, bool force_simple = false
     const bool big = (a.n >= 48 && a.m >= 48);
     if (!force_simple && big && gemm_nt_can_dmma(a)) {
         dim3 grid(cdiv(a.m, G_BN), cdiv(a.n, G_BM));
-        gemm_nt_dmma_kernel<<<grid, 256, G_SMEM, st>>>(a);
+        gemm_nt_dmma_kernel<<<grid, G_THREADS, G_SMEM, st>>>(a);
         LAUNCHED();
     } else {
         dim3 blk(32, 8), grid(cdiv(a.m, 32), cdiv(a.n, 8));

@@ -45,6 +45,11 @@ struct LdltWs {
     double* Wp2 = nullptr;     // second outer-panel scratch (look-ahead double buffering)
     cudaStream_t side = nullptr;   // trailing updates beyond the next panel run here, overlapped with the next panel
     cudaEvent_t ev_panel[2] = {nullptr, nullptr}, ev_upd[2] = {nullptr, nullptr};
+    cudaStream_t cap = nullptr;    // internal capture-origin stream (the caller's stream may be the legacy default one)
+    cudaGraphExec_t gexec = nullptr;
+    double graph_u = -1.0;         // pivot_u the captured graph was built with
+    int graph_nodes = 0;
+    int graph_state = 0;           // 0 = not tried, 1 = usable, -1 = capture failed: direct launches
     double pivot_u = 0.01;     // threshold of the fast (unpivoted) tile attempt: accept step j iff |d_j| >= u * max_i |T[i][j]|
 };
 
@@ -59,6 +64,7 @@ inline int ldlt_alloc(LdltWs& w, int n, cudaStream_t st) {
     CU(cudaMalloc(&w.Wp, sizeof(double) * npad * 256));
     CU(cudaMalloc(&w.Wp2, sizeof(double) * npad * 256));
     CU(cudaStreamCreateWithFlags(&w.side, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&w.cap, cudaStreamNonBlocking));
     for (int i = 0; i < 2; i++) {
         CU(cudaEventCreateWithFlags(&w.ev_panel[i], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&w.ev_upd[i], cudaEventDisableTiming));
@@ -79,7 +85,9 @@ inline int ldlt_alloc(LdltWs& w, int n, cudaStream_t st) {
 }
 inline void ldlt_free(LdltWs& w) {
     cudaFree(w.A); cudaFree(w.Wp); cudaFree(w.Wp2);
+    if (w.gexec) cudaGraphExecDestroy(w.gexec);
     if (w.side) cudaStreamDestroy(w.side);
+    if (w.cap) cudaStreamDestroy(w.cap);
     for (int i = 0; i < 2; i++) { if (w.ev_panel[i]) cudaEventDestroy(w.ev_panel[i]); if (w.ev_upd[i]) cudaEventDestroy(w.ev_upd[i]); }
     cudaFree(w.LinvP); cudaFree(w.dinfo); cudaFree(w.kind); cudaFree(w.counts);
     cudaFree(w.dstat); cudaFree(w.flags); cudaFree(w.ticket); cudaFree(w.yv); cudaFree(w.zv); cudaFree(w.xv);
@@ -724,8 +732,8 @@ inline int ldlt_init_attrs() {
 // side stream, overlapped with the next panel's tile steps (W is double buffered).  Results stay on the device
 // (counts/dstat) until the caller needs the inertia decision.
 constexpr int NBO = 256;
-inline int ldlt_factor(LdltWs& w) {
-    cudaStream_t st = w.st, sd = w.side;
+inline int ldlt_factor_launch(LdltWs& w, cudaStream_t st) {
+    cudaStream_t sd = w.side;
     const int n = w.n, ld = w.ld;
     const size_t npad = (size_t)w.nblk * NB;
     double *ia = w.dinfo, *ib = w.dinfo + npad, *da = w.dinfo + 2 * npad, *db = w.dinfo + 3 * npad;
@@ -779,6 +787,42 @@ inline int ldlt_factor(LdltWs& w) {
     }
     if (side_used) CU(cudaStreamWaitEvent(st, w.ev_upd[(p - 1) & 1], 0));   // join (no-op if already waited)
     return 0;
+}
+// The ~230 short, mutually dependent launches of one factorisation are captured ONCE per workspace into a CUDA graph
+// (both streams; fork/join through the events) and replayed: the matrix lives in the same buffers every time, so
+// only the launch overhead changes.  Falls back to direct launches if capture is not possible.
+inline int ldlt_factor(LdltWs& w) {
+    if (w.graph_state == 1 && w.graph_u != w.pivot_u) {   // parameters baked into the graph changed: rebuild
+        cudaGraphExecDestroy(w.gexec);
+        w.gexec = nullptr;
+        w.graph_state = 0;
+    }
+    if (w.graph_state == 0) {
+        w.graph_state = -1;
+        cudaGraph_t graph = nullptr;
+        if (cudaStreamBeginCapture(w.cap, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            const long long before = g_launches.load();
+            const int rc = ldlt_factor_launch(w, w.cap);
+            g_launches.store(before);               // captured launches are counted when the graph is replayed
+            const cudaError_t e = cudaStreamEndCapture(w.cap, &graph);
+            if (rc == 0 && e == cudaSuccess && graph != nullptr &&
+                cudaGraphInstantiate(&w.gexec, graph, 0) == cudaSuccess) {
+                w.graph_state = 1;
+                w.graph_u = w.pivot_u;
+                size_t nn = 0;
+                cudaGraphGetNodes(graph, nullptr, &nn);
+                w.graph_nodes = (int)nn;
+            }
+            if (graph) cudaGraphDestroy(graph);
+        }
+        cudaGetLastError();   // clear any capture error; direct launches still work
+    }
+    if (w.graph_state == 1) {
+        CU(cudaGraphLaunch(w.gexec, w.st));
+        g_launches.fetch_add(w.graph_nodes, std::memory_order_relaxed);
+        return 0;
+    }
+    return ldlt_factor_launch(w, w.st);
 }
 
 // ------------------------------------------------------------------------------------------- solve kernels
