@@ -148,7 +148,10 @@ int b200ipm_ldlt_factor(b200ipm_ldlt_handle h, const double* A, int lda, int on_
 /* B is n x nrhs column-major-by-rhs (rhs r occupies B[r*n .. r*n+n)); solved in place; nrefine sweeps of
  * iterative refinement against the original A. */
 int b200ipm_ldlt_solve(b200ipm_ldlt_handle h, double* B, int nrhs, int nrefine, int on_device);
-/* Tile-level building blocks used by the multi-GPU 2-D block-cyclic driver (pyipm_b200/dist_ldlt.py). */
+/* Tile-level building blocks used by the multi-GPU 2-D block-cyclic driver (pyipm_b200/dist_ldlt.py).  All
+ * pointers are device pointers; calls are asynchronous on the handle's stream.  tile_factor accumulates the
+ * inertia counts (pos, neg, zero) on the device; a non-NULL `counts` returns the totals since the previous such call
+ * (one synchronisation) and resets them. */
 int b200ipm_ldlt_tile_factor(b200ipm_ldlt_handle h, double* tile_dev, int ld, int nb,
                              double* linv_dev, double* dblk_dev, int* perm_dev, int counts[3]);
 /* panel_dev (rows x 64, leading dimension ld) <- L = W * D^-1, w_dev (leading dimension ldw) <- W = B * LinvP^T */
@@ -163,6 +166,12 @@ int b200ipm_ldlt_import(b200ipm_ldlt_handle h, const double* A_dev, int lda, con
                         const double* dinfo_dev, const int* kind_dev);
 int b200ipm_gemm_nt_update(b200ipm_ldlt_handle h, double* C_dev, int ldc, int rows, int cols,
                            const double* A_dev, int lda, const double* B_dev, int ldb, int k, int lower_only);
+/* Trailing update of a rank's local piece of a 2-D block-cyclic matrix in ONE launch: C (rows x cols, local
+ * storage, origin at local block (li0, lj0)) -= A B^T on every 128 x 128 tile whose global block row
+ * (li*P + p) >= its global block column (lj*Q + q); block must be a multiple of 128. */
+int b200ipm_gemm_nt_update_bc(b200ipm_ldlt_handle h, double* C_dev, int ldc, int rows, int cols,
+                              const double* A_dev, int lda, const double* B_dev, int ldb, int k,
+                              int block, int P, int Q, int p, int q, int li0, int lj0);
 
 /* ---- measurement hook (bench.py roofline legs, ncu captures) -------------------------------------- */
 /* Re-launches ONE hot kernel `reps` times on the handle's stream between two CUDA events at the current state

@@ -56,7 +56,7 @@ SYMBOLS = [
     'b200ipm_kkt', 'b200ipm_con_jac', 'b200ipm_hess_full', 'b200ipm_d2L', 'b200ipm_merit', 'b200ipm_init_slack',
     'b200ipm_init_lambda', 'b200ipm_update_mu', 'b200ipm_direction', 'b200ipm_step_max', 'b200ipm_newton_step',
     'b200ipm_ldlt_create', 'b200ipm_ldlt_destroy', 'b200ipm_ldlt_factor', 'b200ipm_ldlt_solve',
-    'b200ipm_ldlt_tile_factor', 'b200ipm_ldlt_panel', 'b200ipm_ldlt_import', 'b200ipm_gemm_nt_update', 'b200ipm_test_syrk',
+    'b200ipm_ldlt_tile_factor', 'b200ipm_ldlt_panel', 'b200ipm_ldlt_import', 'b200ipm_gemm_nt_update', 'b200ipm_gemm_nt_update_bc', 'b200ipm_test_syrk',
     'b200ipm_test_gemv',
 ]
 
@@ -116,6 +116,7 @@ def load():
         'b200ipm_ldlt_panel': (i, [vp, vp, i, i, vp, vp, vp, vp, i]),
         'b200ipm_ldlt_import': (i, [vp, vp, i, vp, vp, vp]),
         'b200ipm_gemm_nt_update': (i, [vp, vp, i, i, i, vp, i, vp, i, i, i]),
+        'b200ipm_gemm_nt_update_bc': (i, [vp, vp, i, i, i, vp, i, vp, i, i, i, i, i, i, i, i, i]),
         'b200ipm_test_syrk': (i, [i, vp, d, vp, d, i, C.POINTER(vp), C.POINTER(vp), ip, dp, vp, i,
                                   C.POINTER(C.c_float)]),
         'b200ipm_test_gemv': (i, [i, i, vp, vp, vp, i]),

@@ -82,6 +82,7 @@ struct b200ipm_ldlt {
     cudaStream_t st = nullptr;
     bool own_stream = false;
     bool factored = false;
+    bool tile_counts_live = false;
 };
 
 template <typename T>
@@ -1194,10 +1195,15 @@ int b200ipm_ldlt_tile_factor(b200ipm_ldlt_handle h, double* tile_dev, int ld, in
                              int* perm_dev, int counts[3]) {
     if (!h || !tile_dev || !linv_dev || !dblk_dev || nb <= 0 || nb > NB) return fail_msg("tile_factor: bad arguments");
     CU(cudaSetDevice(h->device));
-    ldlt_reset_kernel<<<1, 1, 0, h->st>>>(h->F.counts, h->F.dstat, h->F.ticket);
-    LAUNCHED();
-    // dblk_dev layout: [dinv_a (NB) | dinv_b (NB) | d_a (NB) | d_b (NB)] followed by NB ints of `kind`
+    // dblk_dev layout: [dinv_a (NB) | dinv_b (NB) | d_a (NB) | d_b (NB)] followed by NB ints of `kind`.
+    // The inertia counts ACCUMULATE in the handle (device side, no synchronisation) until a call passes a non-NULL
+    // `counts`, which returns the totals since the previous such call and resets them.
     int* kind = reinterpret_cast<int*>(dblk_dev + 4 * NB);
+    if (!h->tile_counts_live) {
+        ldlt_reset_kernel<<<1, 1, 0, h->st>>>(h->F.counts, h->F.dstat, h->F.ticket);
+        LAUNCHED();
+        h->tile_counts_live = true;
+    }
     ldlt_tile_kernel<<<1, TILE_THREADS, TILE_SMEM, h->st>>>(tile_dev, ld, nb, linv_dev, dblk_dev, dblk_dev + NB, dblk_dev + 2 * NB,
                                                    dblk_dev + 3 * NB, kind, perm_dev, h->F.counts, h->F.dstat, h->F.pivot_u);
     LAUNCHED();
@@ -1206,6 +1212,7 @@ int b200ipm_ldlt_tile_factor(b200ipm_ldlt_handle h, double* tile_dev, int ld, in
         CU(cudaMemcpyAsync(cnt, h->F.counts, sizeof(int) * 4, cudaMemcpyDeviceToHost, h->st));
         CU(cudaStreamSynchronize(h->st));
         counts[0] = cnt[2]; counts[1] = cnt[0]; counts[2] = cnt[1];
+        h->tile_counts_live = false;
     }
     return 0;
 }
@@ -1246,6 +1253,21 @@ int b200ipm_gemm_nt_update(b200ipm_ldlt_handle h, double* C_dev, int ldc, int ro
     u.C = C_dev; u.ldc = ldc; u.Cin = C_dev; u.ldcin = ldc; u.n = rows; u.m = cols; u.beta = 1.0;
     u.mode = lower_only ? GEMM_LOWER_ONLY : GEMM_FULL; u.nterms = 1;
     u.t[0] = GemmTerm{A_dev, B_dev, nullptr, lda, ldb, k, -1.0};
+    RET(gemm_nt(h->st, u));
+    return 0;
+}
+
+int b200ipm_gemm_nt_update_bc(b200ipm_ldlt_handle h, double* C_dev, int ldc, int rows, int cols, const double* A_dev,
+                              int lda, const double* B_dev, int ldb, int k, int block, int P, int Q, int p, int q, int li0,
+                              int lj0) {
+    if (!h || !C_dev || !A_dev || !B_dev || block <= 0 || (block % G_BM) != 0) return fail_msg("gemm_nt_update_bc: bad arguments");
+    if (rows <= 0 || cols <= 0) return 0;
+    CU(cudaSetDevice(h->device));
+    GemmArgs u{};
+    u.C = C_dev; u.ldc = ldc; u.Cin = C_dev; u.ldcin = ldc; u.n = rows; u.m = cols; u.beta = 1.0;
+    u.mode = GEMM_BC_LOWER; u.nterms = 1;
+    u.t[0] = GemmTerm{A_dev, B_dev, nullptr, lda, ldb, k, -1.0};
+    u.bc_b = block; u.bc_P = P; u.bc_Q = Q; u.bc_p = p; u.bc_q = q; u.bc_li0 = li0; u.bc_lj0 = lj0;
     RET(gemm_nt(h->st, u));
     return 0;
 }

@@ -23,7 +23,7 @@
 
 namespace b200 {
 
-enum { GEMM_UPPER_MIRROR = 0, GEMM_LOWER_ONLY = 1, GEMM_FULL = 2 };
+enum { GEMM_UPPER_MIRROR = 0, GEMM_LOWER_ONLY = 1, GEMM_FULL = 2, GEMM_BC_LOWER = 3 };
 
 struct GemmTerm {
     const double* A;
@@ -41,6 +41,10 @@ struct GemmArgs {
     double beta, shift;
     int mode, nterms;
     GemmTerm t[3];
+    // GEMM_BC_LOWER: C is a local piece of a 2-D block-cyclic matrix (block bc_b, grid bc_P x bc_Q, this rank at
+    // (bc_p, bc_q), local block offsets bc_li0 / bc_lj0 of C's origin): a tile is computed iff its global block row >=
+    // its global block column (tiles never straddle blocks: bc_b is a multiple of the tile size).
+    int bc_b, bc_P, bc_Q, bc_p, bc_q, bc_li0, bc_lj0;
 };
 
 constexpr int G_BM = 128, G_BN = 128, G_BK = 32, G_LDS = 36, G_STAGES = 3;
@@ -103,6 +107,11 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_nt_dmma_kernel(const GemmAr
     const int ti = blockIdx.y, tj = blockIdx.x;
     if (a.mode == GEMM_UPPER_MIRROR && ti > tj) return;
     if (a.mode == GEMM_LOWER_ONLY && ti < tj) return;
+    if (a.mode == GEMM_BC_LOWER) {
+        const int I = (a.bc_li0 + (ti * G_BM) / a.bc_b) * a.bc_P + a.bc_p;
+        const int J = (a.bc_lj0 + (tj * G_BN) / a.bc_b) * a.bc_Q + a.bc_q;
+        if (I < J) return;
+    }
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp / G_NWN, wn = warp % G_NWN;
     constexpr int WTM = G_BM / G_NWM, WTN = G_BN / G_NWN;
@@ -168,7 +177,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_nt_dmma_kernel(const GemmAr
 
     // epilogue.  Per 8-row fragment group the Cin values are fetched first (4 independent 16-byte loads in flight
     // per thread), then combined and stored: the short-K launches of the LDL^T are epilogue-bound otherwise.
-    const bool diag_tile = (ti == tj);
+    const bool diag_tile = (ti == tj) && (a.mode == GEMM_UPPER_MIRROR || a.mode == GEMM_LOWER_ONLY);
     const bool vec_ok = ((a.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(a.C) & 15) == 0) &&
                         (a.Cin == nullptr || (((a.ldcin & 1) == 0) && ((reinterpret_cast<uintptr_t>(a.Cin) & 15) == 0)));
     const bool interior = vec_ok && !diag_tile && (row0 + G_BM <= a.n) && (col0 + G_BN <= a.m);
@@ -236,6 +245,10 @@ __global__ void gemm_nt_simple_kernel(const GemmArgs a) {
     if (i >= a.n || j >= a.m) return;
     if (a.mode == GEMM_UPPER_MIRROR && i > j) return;
     if (a.mode == GEMM_LOWER_ONLY && i < j) return;
+    if (a.mode == GEMM_BC_LOWER) {
+        const int I = (a.bc_li0 + i / a.bc_b) * a.bc_P + a.bc_p, J = (a.bc_lj0 + j / a.bc_b) * a.bc_Q + a.bc_q;
+        if (I < J) return;
+    }
     double v = 0.0;
     for (int t = 0; t < a.nterms; t++) {
         const GemmTerm T = a.t[t];

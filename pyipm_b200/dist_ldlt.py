@@ -53,6 +53,7 @@ class CudaTileOps(object):
         self.diag_size = self.b * self.b + self.nt * self.tile_doubles + 3
         self.perm = torch.empty(NB, dtype=torch.int32, device=self.device)
         self.wdiag = torch.empty((self.b, self.b), dtype=torch.float64, device=self.device)
+        self._idx_cache = {}
 
     def empty(self, *shape):
         return torch.empty(shape, dtype=torch.float64, device=self.device)
@@ -69,14 +70,11 @@ class CudaTileOps(object):
         b, ld = self.b, Akk.stride(0)
         es = 8
         base = Akk.data_ptr()
-        counts = np.zeros(3, dtype=np.int64)
-        cnt = (C.c_int * 3)()
         for t in range(self.nt):
             k0 = t * NB
             linv, dblk = self._tile(diag, t)
             self._lib.check(self.lib.b200ipm_ldlt_tile_factor(self.ctx.h, base + es * (k0 * ld + k0), ld, NB, linv.data_ptr(),
-                                                              dblk.data_ptr(), self.perm.data_ptr(), cnt))
-            counts += np.array(list(cnt))
+                                                              dblk.data_ptr(), self.perm.data_ptr(), None))
             rows = b - k0 - NB
             if rows > 0:
                 pptr = base + es * ((k0 + NB) * ld + k0)
@@ -86,7 +84,24 @@ class CudaTileOps(object):
                 cptr = base + es * ((k0 + NB) * ld + (k0 + NB))
                 self._lib.check(self.lib.b200ipm_gemm_nt_update(self.ctx.h, cptr, ld, rows, rows, wptr, b, pptr, ld, NB, 1))
         diag[:b * b].view(b, b).copy_(Akk)
-        diag[-3:] = torch.tensor(counts.astype(np.float64), device=self.device)
+        # inertia: signs of the D blocks, computed on the device (no host synchronisation)
+        pos = neg = zero = 0
+        for t in range(self.nt):
+            _, dblk = self._tile(diag, t)
+            da, db = dblk[2 * NB:3 * NB], dblk[3 * NB:4 * NB]
+            kind = dblk[4 * NB:].view(torch.int32)[:NB]
+            one = (kind == 0)
+            pos = pos + (one & (da > 0)).sum()
+            neg = neg + (one & (da < 0)).sum()
+            zero = zero + (one & (da == 0)).sum()
+            first = (kind == 1)
+            c = torch.roll(da, -1)                       # second diagonal entry of a 2x2 block
+            det = da * c - db * db
+            tr = da + c
+            pos = pos + (first & (det > 0) & (tr > 0)).sum() * 2 + (first & (det < 0)).sum()
+            neg = neg + (first & (det > 0) & (tr < 0)).sum() * 2 + (first & (det < 0)).sum()
+            zero = zero + (first & (det == 0)).sum()
+        diag[-3:] = torch.stack([pos, neg, zero]).to(torch.float64)
 
     def panel(self, Bblk, diag):
         """Bblk: rows x b view (row stride ld) -> overwritten with L; returns W = L * D (rows x b, contiguous)."""
@@ -113,8 +128,27 @@ class CudaTileOps(object):
         self._lib.check(self.lib.b200ipm_gemm_nt_update(self.ctx.h, Cv.data_ptr(), Cv.stride(0), rows, cols, W.data_ptr(),
                                                         W.stride(0), L.data_ptr(), L.stride(0), self.b, 0))
 
+    def update_bc(self, Cv, W, L, grid, coord, li0, lj0):
+        """One launch: Cv (local rows x local cols from local block (li0, lj0)) -= W @ L^T on the tiles whose global
+        block row >= global block column."""
+        rows, cols = Cv.shape
+        if rows == 0 or cols == 0:
+            return
+        self._lib.check(self.lib.b200ipm_gemm_nt_update_bc(self.ctx.h, Cv.data_ptr(), Cv.stride(0), rows, cols, W.data_ptr(),
+                                                           W.stride(0), L.data_ptr(), L.stride(0), self.b, self.b, grid[0],
+                                                           grid[1], coord[0], coord[1], li0, lj0))
+
     def counts(self, diag):
         return [int(v) for v in diag[-3:].tolist()]
+
+    def index(self, idx):
+        """device index tensor (int64) from a NumPy index array, cached: no per-panel host-to-device copies"""
+        key = (idx.size, int(idx[0]) if idx.size else -1, int(idx[-1]) if idx.size else -1)
+        t = self._idx_cache.get(key)
+        if t is None:
+            t = torch.from_numpy(idx).to(self.device)
+            self._idx_cache[key] = t
+        return t
 
     # ---- replicated solve on the gathered factor
     def make_solver(self, n, diags, panels):
@@ -209,7 +243,6 @@ class BlockCyclicLDLT(object):
                 li, lj = self.rows_blk.index(k), self.cols_blk.index(k)
                 ops.factor_diag(work[li * b:(li + 1) * b, lj * b:(lj + 1) * b], diag)
             self._bcast(diag, self._rank_of(pk, qk))
-            tot += np.array(ops.counts(diag))
             self.diags.append(diag)
             nbelow = self.nbk - (k + 1)
             if nbelow == 0:
@@ -234,25 +267,19 @@ class BlockCyclicLDLT(object):
                     buf[0].copy_(Bv)
                     buf[1].copy_(Wloc)
                 self._bcast(buf, self._rank_of(psrc, qk))
-                pos = torch.from_numpy(self._idx([I - (k + 1) for I in blks])).to(buf.device)
+                pos = ops.index(self._idx([I - (k + 1) for I in blks]))
                 Lfull.index_copy_(0, pos, buf[0])
                 Wfull.index_copy_(0, pos, buf[1])
             self.panels.append(Lfull)
-            # 4. trailing update of my blocks: A[I, J] -= W[I] L[J]^T for J > k, I >= J
-            if mine:
-                pos = torch.from_numpy(self._idx([I - (k + 1) for I in mine])).to(Wfull.device)
-                Wmine = Wfull.index_select(0, pos)                     # rows of my block rows > k, in local order
-                li0 = self.rows_blk.index(mine[0])
-                for lj, J in enumerate(self.cols_blk):
-                    if J <= k:
-                        continue
-                    rows_ge = [I for I in mine if I >= J]
-                    if not rows_ge:
-                        continue
-                    lis = self.rows_blk.index(rows_ge[0])
-                    Cv = work[lis * b:, lj * b:(lj + 1) * b]
-                    Lj = Lfull[(J - k - 1) * b:(J - k) * b]
-                    ops.update(Cv, Wmine[(lis - li0) * b:], Lj)
+            # 4. trailing update of my blocks: A[I, J] -= W[I] L[J]^T for J > k, I >= J -- one launch per rank
+            mycols = [J for J in self.cols_blk if J > k]
+            if mine and mycols:
+                Wmine = Wfull.index_select(0, ops.index(self._idx([I - (k + 1) for I in mine])))   # my block rows, local order
+                Lmine = Lfull.index_select(0, ops.index(self._idx([J - (k + 1) for J in mycols])))  # L rows of my block cols
+                li0, lj0 = self.rows_blk.index(mine[0]), self.cols_blk.index(mycols[0])
+                ops.update_bc(work[li0 * b:, lj0 * b:], Wmine, Lmine, (P, Q), (self.p, self.q), li0, lj0)
+        for diag in self.diags:      # one synchronisation at the very end
+            tot += np.array(ops.counts(diag))
         self.inertia = tuple(int(v) for v in tot)
         self._solver = None
         return self.inertia

@@ -43,8 +43,19 @@ class RefTileOps(object):
     def update(self, Cv, W, L):
         Cv.sub_(W @ L.t())
 
+    def update_bc(self, Cv, W, L, grid, coord, li0, lj0):
+        b, (P, Q), (p, q) = self.b, grid, coord
+        full = W @ L.t()
+        for bi in range(Cv.shape[0] // b):
+            for bj in range(Cv.shape[1] // b):
+                if (li0 + bi) * P + p >= (lj0 + bj) * Q + q:
+                    Cv[bi * b:(bi + 1) * b, bj * b:(bj + 1) * b] -= full[bi * b:(bi + 1) * b, bj * b:(bj + 1) * b]
+
     def counts(self, diag):
         return [int(v) for v in diag[-3:].tolist()]
+
+    def index(self, idx):
+        return torch.from_numpy(idx)
 
     def make_solver(self, n, diags, panels):
         b = self.b
