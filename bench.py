@@ -357,6 +357,31 @@ def run_b200(args):
                                 'traffic': None, 'peak_source': 'MEASURED_PEAKS.json hbm_gbs (%s)' % peak_kind,
                                 'bytes_per_launch': res['work']}
         line['kernels'] = kern
+        # "KKT-residual match vs CPU ref": one teacher-forced Newton step of a small instance of the same NLP
+        # family on this GPU against the CPU oracle (the full parity suite is tests/test_gpu_engine.py)
+        try:
+            from oracle.pyipm_numpy import OracleIPM
+            sp = problems.make_nlp(D=192, M=32, N=192, seed=3)
+            tr = []
+            oq = OracleIPM(x0=sp.x0.copy(), verbosity=-1, niter=1, miter=2, trace=tr, **sp.callables())
+            with np.errstate(all='ignore'):
+                oq.solve()
+            e2 = _lib.Engine(sp.nvar, sp.neq, sp.nineq, _lib.default_params(), device=local)
+            e2.bind(sp)
+            stq = tr[1]
+            e2.set_state(stq['x'], stq['s'], stq['lda'], stq['mu'], tr[0]['nu_after'], tr[0]['delta'])
+            e2.set_mu_host(stq['mu_host'])
+            dzq, iq = e2.direction()
+            e2.set_state(stq['x'], stq['s'], stq['lda'], stq['mu'], tr[0]['nu_after'], tr[0]['delta'])
+            i2 = e2.newton_step()
+            line['parity_check'] = {
+                'problem': 'nlp D=192 M=32 N=192, step 2 of the oracle trajectory',
+                'dz_rel_err_inf': float(np.max(np.abs(dzq - stq['dz'])) / np.max(np.abs(stq['dz']))),
+                'same_delta': bool(iq.delta == stq['delta']), 'same_n_factor': bool(iq.n_factor == stq['reg']['n_eig']),
+                'kkt_norms_gpu': list(i2.kkt_norm), 'kkt_norms_oracle': [float(v) for v in stq['kkt_norms']]}
+            e2.close()
+        except Exception as exc:   # the parity field is informative; never let it break the bench line
+            line['parity_check'] = {'error': repr(exc)}
         if world == 1 and not args.no_cpu_baseline:
             os.environ.setdefault('OPENBLAS_NUM_THREADS', str(os.cpu_count()))
             o, sprob, (x, s, lda) = oracle_sample_step()

@@ -84,24 +84,7 @@ class CudaTileOps(object):
                 cptr = base + es * ((k0 + NB) * ld + (k0 + NB))
                 self._lib.check(self.lib.b200ipm_gemm_nt_update(self.ctx.h, cptr, ld, rows, rows, wptr, b, pptr, ld, NB, 1))
         diag[:b * b].view(b, b).copy_(Akk)
-        # inertia: signs of the D blocks, computed on the device (no host synchronisation)
-        pos = neg = zero = 0
-        for t in range(self.nt):
-            _, dblk = self._tile(diag, t)
-            da, db = dblk[2 * NB:3 * NB], dblk[3 * NB:4 * NB]
-            kind = dblk[4 * NB:].view(torch.int32)[:NB]
-            one = (kind == 0)
-            pos = pos + (one & (da > 0)).sum()
-            neg = neg + (one & (da < 0)).sum()
-            zero = zero + (one & (da == 0)).sum()
-            first = (kind == 1)
-            c = torch.roll(da, -1)                       # second diagonal entry of a 2x2 block
-            det = da * c - db * db
-            tr = da + c
-            pos = pos + (first & (det > 0) & (tr > 0)).sum() * 2 + (first & (det < 0)).sum()
-            neg = neg + (first & (det > 0) & (tr < 0)).sum() * 2 + (first & (det < 0)).sum()
-            zero = zero + (first & (det == 0)).sum()
-        diag[-3:] = torch.stack([pos, neg, zero]).to(torch.float64)
+        # (inertia is evaluated once, for all diagonal blocks together, by counts_all)
 
     def panel(self, Bblk, diag):
         """Bblk: rows x b view (row stride ld) -> overwritten with L; returns W = L * D (rows x b, contiguous)."""
@@ -138,8 +121,21 @@ class CudaTileOps(object):
                                                            W.stride(0), L.data_ptr(), L.stride(0), self.b, self.b, grid[0],
                                                            grid[1], coord[0], coord[1], li0, lj0))
 
-    def counts(self, diag):
-        return [int(v) for v in diag[-3:].tolist()]
+    def counts_all(self, diags):
+        """(pos, neg, zero) over all diagonal blocks: signs of the 1x1 / 2x2 blocks of D, one batched evaluation and
+        one synchronisation."""
+        NT = self.tile_doubles
+        tiles = torch.stack([d[self.b * self.b:self.b * self.b + self.nt * NT].view(self.nt, NT) for d in diags])
+        tiles = tiles.reshape(-1, NT)[:, NB * NB:]                      # [ntiles, 288]: dinv_a | dinv_b | d_a | d_b | kind
+        da, db = tiles[:, 2 * NB:3 * NB], tiles[:, 3 * NB:4 * NB]
+        kind = tiles[:, 4 * NB:].contiguous().view(torch.int32)[:, :NB]
+        one, first = (kind == 0), (kind == 1)
+        c = torch.roll(da, -1, dims=1)                                   # second diagonal entry of a 2x2 block
+        det, tr = da * c - db * db, da + c
+        pos = (one & (da > 0)).sum() + (first & (det > 0) & (tr > 0)).sum() * 2 + (first & (det < 0)).sum()
+        neg = (one & (da < 0)).sum() + (first & (det > 0) & (tr < 0)).sum() * 2 + (first & (det < 0)).sum()
+        zero = (one & (da == 0)).sum() + (first & (det == 0)).sum()
+        return [int(v) for v in torch.stack([pos, neg, zero]).tolist()]
 
     def index(self, idx):
         """device index tensor (int64) from a NumPy index array, cached: no per-panel host-to-device copies"""
@@ -232,17 +228,29 @@ class BlockCyclicLDLT(object):
     def factor(self):
         """-> inertia (pos, neg, zero).  Collective: every rank must call it."""
         ops, b, P, Q = self.ops, self.b, self.P, self.Q
+        import os
+        prof = bool(os.environ.get('B200IPM_DIST_PROF')) and self.A0.is_cuda
+        marks = []
+
+        def mark(tag):
+            if prof:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                marks.append((tag, e))
         work = self.A0.clone()
         self.diags, self.panels = [], []
         tot = np.zeros(3, dtype=np.int64)
         for k in range(self.nbk):
             pk, qk = k % P, k % Q
+            mark('start')
             # 1. diagonal block
             diag = ops.empty(ops.diag_size)
             if (self.p, self.q) == (pk, qk):
                 li, lj = self.rows_blk.index(k), self.cols_blk.index(k)
                 ops.factor_diag(work[li * b:(li + 1) * b, lj * b:(lj + 1) * b], diag)
+            mark('diag')
             self._bcast(diag, self._rank_of(pk, qk))
+            mark('bcast_diag')
             self.diags.append(diag)
             nbelow = self.nbk - (k + 1)
             if nbelow == 0:
@@ -255,6 +263,7 @@ class BlockCyclicLDLT(object):
                 li0, lj = self.rows_blk.index(mine[0]), self.cols_blk.index(k)
                 Bv = work[li0 * b:, lj * b:(lj + 1) * b]
                 Wloc = ops.panel(Bv, diag)
+            mark('panel')
             # 3. replicate the panel: owners (psrc, qk) broadcast [L | W] of their row blocks
             Lfull = ops.empty(nbelow * b, b)
             Wfull = ops.empty(nbelow * b, b)
@@ -271,6 +280,7 @@ class BlockCyclicLDLT(object):
                 Lfull.index_copy_(0, pos, buf[0])
                 Wfull.index_copy_(0, pos, buf[1])
             self.panels.append(Lfull)
+            mark('bcast_panel')
             # 4. trailing update of my blocks: A[I, J] -= W[I] L[J]^T for J > k, I >= J -- one launch per rank
             mycols = [J for J in self.cols_blk if J > k]
             if mine and mycols:
@@ -278,9 +288,16 @@ class BlockCyclicLDLT(object):
                 Lmine = Lfull.index_select(0, ops.index(self._idx([J - (k + 1) for J in mycols])))  # L rows of my block cols
                 li0, lj0 = self.rows_blk.index(mine[0]), self.cols_blk.index(mycols[0])
                 ops.update_bc(work[li0 * b:, lj0 * b:], Wmine, Lmine, (P, Q), (self.p, self.q), li0, lj0)
-        for diag in self.diags:      # one synchronisation at the very end
-            tot += np.array(ops.counts(diag))
-        self.inertia = tuple(int(v) for v in tot)
+            mark('update')
+        mark('update')
+        if prof:
+            torch.cuda.synchronize()
+            acc = {}
+            for (t0, e0), (t1, e1) in zip(marks[:-1], marks[1:]):
+                if t1 != 'start':
+                    acc[t1] = acc.get(t1, 0.0) + e0.elapsed_time(e1)
+            print('rank', self.rank, 'phase ms', {k_: round(v, 1) for k_, v in acc.items()}, flush=True)
+        self.inertia = tuple(int(v) for v in ops.counts_all(self.diags))   # one synchronisation at the very end
         self._solver = None
         return self.inertia
 

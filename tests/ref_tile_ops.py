@@ -51,8 +51,12 @@ class RefTileOps(object):
                 if (li0 + bi) * P + p >= (lj0 + bj) * Q + q:
                     Cv[bi * b:(bi + 1) * b, bj * b:(bj + 1) * b] -= full[bi * b:(bi + 1) * b, bj * b:(bj + 1) * b]
 
-    def counts(self, diag):
-        return [int(v) for v in diag[-3:].tolist()]
+    def counts_all(self, diags):
+        tot = [0, 0, 0]
+        for d in diags:
+            for i, v in enumerate(d[-3:].tolist()):
+                tot[i] += int(v)
+        return tot
 
     def index(self, idx):
         return torch.from_numpy(idx)

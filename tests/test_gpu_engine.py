@@ -233,3 +233,28 @@ def test_config5_mu_sweep_full_size_properties():
         assert info.n_neg == prob.neq and info.n_zero == 0, mu
         assert info.resid <= 1e-9 * max(1.0, np.max(np.abs(g))), (mu, info.resid)
     eng.close()
+
+
+def test_config2_full_size_steps_vs_oracle():
+    """BASELINE config 2 at full size (convex QP, D=1024, 256 eq + 1024 box inequalities, K = 3328): the first two
+    Newton steps teacher-forced against the CPU oracle (each oracle step = one eigvalsh(3328) + one LU)."""
+    prob = problems.make_qp()
+    o, tr = oracle_trace(prob, prob.x0, niter=1, miter=2)
+    eng = make_engine(prob)
+    nu_b, de_b = 10.0, 0.0
+    for k, st in enumerate(tr):
+        eng.set_state(st['x'], st['s'], st['lda'], st['mu'], nu_b, de_b)
+        eng.set_mu_host(st['mu_host'])
+        gv, _ = eng.residual()
+        assert relinf(gv, -st['g']) < 1e-12
+        dz, dinfo = eng.direction()
+        assert dinfo.n_factor == st['reg']['n_eig'] and dinfo.delta == st['delta'] and dinfo.n_neg == prob.neq
+        assert relinf(dz, st['dz']) < 1e-8, (k, relinf(dz, st['dz']))
+        eng.set_state(st['x'], st['s'], st['lda'], st['mu'], nu_b, de_b)
+        info = eng.newton_step()
+        assert info.n_backtracks == st['search']['n_backtracks']
+        assert abs(info.alpha_smax - st['alpha_smax']) < 1e-12 and abs(info.alpha_lmax - st['alpha_lmax']) < 1e-12
+        x, s, lda, _, _, _ = eng.get_state()
+        assert relinf(x, st['x_new']) < 1e-8 and relinf(s, st['s_new']) < 1e-8 and relinf(lda, st['lda_new']) < 1e-8
+        nu_b, de_b = st['nu_after'], st['delta']
+    eng.close()
