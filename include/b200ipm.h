@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define B200IPM_VERSION 100
+#define B200IPM_VERSION 101
 
 typedef struct b200ipm_engine* b200ipm_handle;
 typedef struct b200ipm_ldlt*   b200ipm_ldlt_handle;
@@ -39,8 +39,9 @@ typedef struct b200ipm_params {
     int    nrefine;                       /* iterative-refinement sweeps against the UNREDUCED KKT residual */
     int    ls_batch;                      /* speculative line-search trials evaluated per launch */
     int    max_reg_retries;               /* cap on the delta*=10 loop (pyipm.py:1399-1403 has none) */
-    int    reserved;
+    int    flags;                         /* bit 0 (B200IPM_FLAG_NO_SPECULATION): never run reghess attempts concurrently */
 } b200ipm_params;
+#define B200IPM_FLAG_NO_SPECULATION 1
 
 /* Everything one inner iteration (pyipm.py:1714-1754) reports back. */
 typedef struct b200ipm_step_info {
@@ -64,12 +65,18 @@ typedef struct b200ipm_step_info {
     int    n_neg_first, n_zero_first;/* inertia of the FIRST (delta = 0) attempt, i.e. what pyipm.py:1381 tests */
     float  ms_eval, ms_assemble, ms_factor, ms_solve, ms_search, ms_total;   /* CUDA-event phase times */
     float  ms_hess_kernel, ms_condense_kernel;   /* the two SYRK-shaped fp64 contractions, per launch */
+    int    n_spec;                   /* 1 if the delta = 0 and delta = max(delta/2, delta0) attempts of reghess ran
+                                        concurrently on two streams (same decisions, n_factor counts both) */
+    int    spec_used;                /* 1 if the speculative attempt was the accepted factorisation */
 } b200ipm_step_info;
 
 int         b200ipm_version(void);
 const char* b200ipm_last_error(void);
 /* number of kernels this library has launched in this process (bench.py's "gpu_launches") */
 long long   b200ipm_launch_count(void);
+/* sizeof(b200ipm_params) (which = 0) / sizeof(b200ipm_step_info) (which = 1) as compiled: lets a binding verify its
+ * struct mirror before the first call */
+int         b200ipm_struct_size(int which);
 
 /* ---- lifecycle ----------------------------------------------------------------------------------- */
 /* Replaces IPM.__init__/compile() workspace setup (pyipm.py:311-376, 410-467).  `stream` is a cudaStream_t

@@ -23,7 +23,7 @@ class Params(C.Structure):
     _fields_ = [('mu', C.c_double), ('nu', C.c_double), ('rho', C.c_double), ('tau', C.c_double),
                 ('eta', C.c_double), ('beta', C.c_double), ('Xtol', C.c_double), ('Ktol', C.c_double),
                 ('eps', C.c_double), ('reg_coef', C.c_double), ('nrefine', C.c_int), ('ls_batch', C.c_int),
-                ('max_reg_retries', C.c_int), ('reserved', C.c_int)]
+                ('max_reg_retries', C.c_int), ('flags', C.c_int)]
 
 
 class StepInfo(C.Structure):
@@ -37,7 +37,7 @@ class StepInfo(C.Structure):
                 ('n_neg_first', C.c_int), ('n_zero_first', C.c_int),
                 ('ms_eval', C.c_float), ('ms_assemble', C.c_float), ('ms_factor', C.c_float), ('ms_solve', C.c_float),
                 ('ms_search', C.c_float), ('ms_total', C.c_float), ('ms_hess_kernel', C.c_float),
-                ('ms_condense_kernel', C.c_float)]
+                ('ms_condense_kernel', C.c_float), ('n_spec', C.c_int), ('spec_used', C.c_int)]
 
     def asdict(self):
         d = {}
@@ -49,7 +49,7 @@ class StepInfo(C.Structure):
 
 # every symbol include/b200ipm.h declares (tests/test_abi.py checks the library exports exactly these)
 SYMBOLS = [
-    'b200ipm_version', 'b200ipm_last_error', 'b200ipm_launch_count', 'b200ipm_create', 'b200ipm_destroy',
+    'b200ipm_version', 'b200ipm_last_error', 'b200ipm_launch_count', 'b200ipm_struct_size', 'b200ipm_create', 'b200ipm_destroy',
     'b200ipm_set_params', 'b200ipm_sync', 'b200ipm_bind_quad', 'b200ipm_bind_poly', 'b200ipm_set_derivs',
     'b200ipm_set_state', 'b200ipm_get_state', 'b200ipm_set_mu_host', 'b200ipm_state_save', 'b200ipm_state_restore',
     'b200ipm_profile_kernel', 'b200ipm_cost', 'b200ipm_residual',
@@ -82,6 +82,7 @@ def load():
         'b200ipm_version': (i, []),
         'b200ipm_last_error': (C.c_char_p, []),
         'b200ipm_launch_count': (C.c_longlong, []),
+        'b200ipm_struct_size': (i, [i]),
         'b200ipm_create': (i, [i, i, i, C.POINTER(Params), i, vp, C.POINTER(vp)]),
         'b200ipm_destroy': (i, [vp]),
         'b200ipm_set_params': (i, [vp, C.POINTER(Params)]),
@@ -124,6 +125,8 @@ def load():
     for name in SYMBOLS:
         fn = getattr(lib, name)   # AttributeError if the library does not export it
         fn.restype, fn.argtypes = sig[name]
+    if lib.b200ipm_struct_size(0) != C.sizeof(Params) or lib.b200ipm_struct_size(1) != C.sizeof(StepInfo):
+        raise ImportError('libb200ipm.so was built from a different include/b200ipm.h (struct sizes differ): rebuild')
     _lib = lib
     return lib
 
@@ -154,11 +157,11 @@ def torch_stream_handle(device=None):
 
 
 def default_params(mu=0.2, nu=10.0, rho=0.1, tau=0.995, eta=1.0E-4, beta=0.4, Xtol=None, Ktol=1.0E-4, nrefine=2,
-                   ls_batch=32, max_reg_retries=60):
+                   ls_batch=32, max_reg_retries=60, flags=0):
     eps = float(np.finfo(np.float64).eps)
     return Params(mu=mu, nu=nu, rho=rho, tau=tau, eta=eta, beta=beta, Xtol=Xtol if Xtol else eps, Ktol=Ktol, eps=eps,
                   reg_coef=float(np.sqrt(eps)), nrefine=nrefine, ls_batch=ls_batch, max_reg_retries=max_reg_retries,
-                  reserved=0)
+                  flags=flags)
 
 
 class Engine(object):

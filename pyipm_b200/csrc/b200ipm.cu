@@ -47,6 +47,12 @@ struct b200ipm_engine {
     bool strict_retry = false;
     int n_strict = 0;        // number of strict re-factorisations triggered by a poor residual
     LdltWs F;               // condensed KKT factorisation (order Kc)
+    LdltWs Fb;              // speculative second attempt of reghess (lazy), factored concurrently on stB
+    bool Fb_ready = false;
+    cudaStream_t stB = nullptr;
+    cudaEvent_t ev_fork = nullptr;
+    int *h_cntB = nullptr;   // pinned: counts (4 ints) of the speculative attempt
+    double *h_dsB = nullptr; // pinned: dstat (2 doubles) of the speculative attempt
     LdltWs F2;              // pseudo-inverse / second-order-correction systems (lazy)
     bool F2_ready = false;
     int F2_n = 0;
@@ -213,17 +219,44 @@ static int condense(Eng* h) {
     return 0;
 }
 // Kc = [[Hb + delta I, .], [dce', -reg I]]  (lower triangle is what the factorisation reads)
-static int build_kc(Eng* h, double delta, double reg) {
+static int build_kc_into(Eng* h, LdltWs& F, cudaStream_t st, double delta, double reg) {
     const int D = h->D, M = h->M;
-    kc_xx_kernel<<<std::min(cdiv(D * D, 256), 148 * 32), 256, 0, h->st>>>(h->Hb, h->ldW, D, delta, h->F.A, h->F.ld);
+    kc_xx_kernel<<<std::min(cdiv(D * D, 256), 148 * 32), 256, 0, st>>>(h->Hb, h->ldW, D, delta, F.A, F.ld);
     LAUNCHED();
     if (M) {
-        RET(transpose(h->st, h->J, h->ldJ, D, M, h->F.A + (size_t)D * h->F.ld, h->F.ld));
-        kc_ee_kernel<<<cdiv(M * M, 256), 256, 0, h->st>>>(h->F.A, h->F.ld, D, M, reg);
+        RET(transpose(st, h->J, h->ldJ, D, M, F.A + (size_t)D * F.ld, F.ld));
+        kc_ee_kernel<<<cdiv(M * M, 256), 256, 0, st>>>(F.A, F.ld, D, M, reg);
         LAUNCHED();
     }
+    return 0;
+}
+static int build_kc(Eng* h, double delta, double reg) {
+    RET(build_kc_into(h, h->F, h->st, delta, reg));
     h->delta_eff = delta;
     h->reg_cur = reg;
+    return 0;
+}
+// Speculation (reghess, pyipm.py:1373-1406): once a shift was needed, the delta = 0 test almost always fails
+// again and the next candidate max(delta/2, delta0) is known in advance, so both factorisations are started
+// together -- the second one on its own stream and workspace.  A single LDL^T is a serial chain of tile steps that
+// leaves most SMs idle, so the pair costs little more than one.  Decisions are exactly those of the sequential
+// loop: the speculative result is only consumed if the first test fails with reg = 0.
+static int spec_launch(Eng* h, double delta1) {
+    if (!h->Fb_ready) {
+        CU(cudaStreamCreateWithFlags(&h->stB, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+        CU(cudaMallocHost(&h->h_cntB, sizeof(int) * 4));
+        CU(cudaMallocHost(&h->h_dsB, sizeof(double) * 2));
+        RET(ldlt_alloc(h->Fb, h->Kc, h->stB));
+        h->Fb.pivot_u = h->F.pivot_u;
+        h->Fb_ready = true;
+    }
+    CU(cudaEventRecord(h->ev_fork, h->st));          // Hb and J are complete on the main stream
+    CU(cudaStreamWaitEvent(h->stB, h->ev_fork, 0));
+    RET(build_kc_into(h, h->Fb, h->stB, delta1, 0.0));
+    RET(ldlt_factor(h->Fb));
+    CU(cudaMemcpyAsync(h->h_cntB, h->Fb.counts, sizeof(int) * 4, cudaMemcpyDeviceToHost, h->stB));
+    CU(cudaMemcpyAsync(h->h_dsB, h->Fb.dstat, sizeof(double) * 2, cudaMemcpyDeviceToHost, h->stB));
     return 0;
 }
 static int factor_once(Eng* h, double delta, double reg, int* n_neg, int* n_zero, double* rcond) {
@@ -245,6 +278,10 @@ static int factor_regularised(Eng* h, b200ipm_step_info* info) {
     const int M = h->M;
     int n_neg = 0, n_zero = 0, nfac = 0;
     double rcond = 0.0;
+    const double delta1 = (h->delta == 0.0) ? h->p.reg_coef : std::max(h->delta / 2.0, h->p.reg_coef);
+    const bool spec = (h->delta > 0.0) && !(h->p.flags & B200IPM_FLAG_NO_SPECULATION) && !h->strict_retry;
+    bool spec_used = false;
+    if (spec) RET(spec_launch(h, delta1));
     RET(factor_once(h, 0.0, 0.0, &n_neg, &n_zero, &rcond));
     nfac++;
     const double rcond0 = rcond;
@@ -256,9 +293,22 @@ static int factor_regularised(Eng* h, b200ipm_step_info* info) {
             reg = h->p.reg_coef * h->p.eta * pow(h->mu_host, h->p.beta);
             eq_reg = 1;
         }
-        if (h->delta == 0.0) h->delta = h->p.reg_coef;
-        else h->delta = std::max(h->delta / 2.0, h->p.reg_coef);
-        RET(factor_once(h, h->delta, reg, &n_neg, &n_zero, &rcond));
+        h->delta = delta1;
+        if (spec && reg == 0.0) {
+            // adopt the speculative factorisation: it is exactly what factor_once(delta1, 0) would produce
+            CU(cudaStreamSynchronize(h->stB));
+            std::swap(h->F, h->Fb);
+            h->F.st = h->st;
+            h->Fb.st = h->stB;
+            n_neg = h->h_cntB[0];
+            n_zero = h->h_cntB[1];
+            rcond = (n_zero > 0 || !(h->h_dsB[1] > 0.0)) ? 0.0 : h->h_dsB[0] / h->h_dsB[1];
+            h->delta_eff = delta1;
+            h->reg_cur = 0.0;
+            spec_used = true;
+        } else {
+            RET(factor_once(h, h->delta, reg, &n_neg, &n_zero, &rcond));
+        }
         nfac++;
         int guard = 0;
         while (n_neg != M) {
@@ -268,9 +318,10 @@ static int factor_regularised(Eng* h, b200ipm_step_info* info) {
             nfac++;
         }
     }
+    if (spec && !spec_used) CU(cudaStreamSynchronize(h->stB));   // the unused attempt must not outlive this step
     if (info) {
         info->n_neg = n_neg; info->n_zero = n_zero; info->n_factor = nfac; info->rcond = rcond0; info->eq_reg = eq_reg;
-        info->delta = h->delta;
+        info->delta = h->delta; info->n_spec = spec ? 1 : 0; info->spec_used = spec_used ? 1 : 0;
     }
     return 0;
 }
@@ -655,6 +706,9 @@ extern "C" {
 int b200ipm_version(void) { return B200IPM_VERSION; }
 const char* b200ipm_last_error(void) { return g_last_error.c_str(); }
 long long b200ipm_launch_count(void) { return g_launches.load(); }
+int b200ipm_struct_size(int which) {
+    return which == 0 ? (int)sizeof(b200ipm_params) : (which == 1 ? (int)sizeof(b200ipm_step_info) : -1);
+}
 
 int b200ipm_create(int D, int M, int N, const b200ipm_params* p, int device, void* stream, b200ipm_handle* out) {
     if (!out || !p || D <= 0 || M < 0 || N < 0) return fail_msg("b200ipm_create: bad arguments");
@@ -714,6 +768,14 @@ int b200ipm_destroy(b200ipm_handle h) {
     cudaFreeHost(h->h_red);
     ldlt_free(h->F);
     if (h->F2_ready) ldlt_free(h->F2);
+    if (h->Fb_ready) {
+        cudaStreamSynchronize(h->stB);
+        ldlt_free(h->Fb);
+        cudaStreamDestroy(h->stB);
+        cudaEventDestroy(h->ev_fork);
+        cudaFreeHost(h->h_cntB);
+        cudaFreeHost(h->h_dsB);
+    }
     for (int i = 0; i < EV_N; i++) cudaEventDestroy(h->ev[i]);
     if (h->own_stream) cudaStreamDestroy(h->st);
     delete h;

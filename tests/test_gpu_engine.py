@@ -239,7 +239,13 @@ def test_config2_full_size_steps_vs_oracle():
     """BASELINE config 2 at full size (convex QP, D=1024, 256 eq + 1024 box inequalities, K = 3328): the first two
     Newton steps teacher-forced against the CPU oracle (each oracle step = one eigvalsh(3328) + one LU)."""
     prob = problems.make_qp()
-    o, tr = oracle_trace(prob, prob.x0, niter=1, miter=2)
+    # The two-sided box gives EXACTLY dependent constraint gradients (dci = [E, -E]): the reference's own
+    # init_lambda = pinv(J) . df (pyipm.py:729-730, numpy rcond = 1e-15) then keeps singular values of 1.6e-15 and
+    # returns |lda| ~ 1e14, after which reghess multiplies delta by 10 until it overflows.  Both sides therefore
+    # start from the same explicit multipliers through the reference's lda0 argument (pyipm.py:1567-1578).
+    s0 = np.maximum(prob.ci(prob.x0), 1.0E-4)
+    lda0 = np.concatenate([np.zeros(prob.neq), 0.2 / s0])
+    o, tr = oracle_trace(prob, prob.x0, niter=1, miter=2, lda0=lda0)
     eng = make_engine(prob)
     nu_b, de_b = 10.0, 0.0
     for k, st in enumerate(tr):
@@ -258,3 +264,32 @@ def test_config2_full_size_steps_vs_oracle():
         assert relinf(x, st['x_new']) < 1e-8 and relinf(s, st['s_new']) < 1e-8 and relinf(lda, st['lda_new']) < 1e-8
         nu_b, de_b = st['nu_after'], st['delta']
     eng.close()
+
+
+def test_speculative_reghess_matches_sequential():
+    """reghess (pyipm.py:1373-1406) with the delta = 0 and delta/2 attempts factored CONCURRENTLY must take exactly
+    the decisions -- and produce bitwise the direction -- of the sequential loop (flags = NO_SPECULATION)."""
+    prob = problems.make_nlp(D=320, M=48, N=320, seed=5)
+    o, tr = oracle_trace(prob, prob.x0, niter=1, miter=4)
+    eng_s = make_engine(prob)
+    eng_q = make_engine(prob, flags=1)
+    nu_b, de_b = 10.0, 0.0
+    n_spec = 0
+    for k, st in enumerate(tr):
+        out = []
+        for eng in (eng_s, eng_q):
+            eng.set_state(st['x'], st['s'], st['lda'], st['mu'], nu_b, de_b)
+            eng.set_mu_host(st['mu_host'])
+            out.append(eng.direction())
+        (dz_s, i_s), (dz_q, i_q) = out
+        assert i_q.n_spec == 0
+        assert i_s.n_spec == (1 if de_b > 0.0 else 0)
+        n_spec += i_s.n_spec
+        assert (i_s.delta, i_s.n_factor, i_s.n_neg, i_s.n_zero) == (i_q.delta, i_q.n_factor, i_q.n_neg, i_q.n_zero)
+        assert i_s.delta == st['delta'] and i_s.n_factor == st['reg']['n_eig']
+        assert np.array_equal(dz_s, dz_q), (k, relinf(dz_s, dz_q))
+        assert relinf(dz_s, st['dz']) < DZ_RTOL
+        nu_b, de_b = st['nu_after'], st['delta']
+    assert n_spec >= 1      # the nonconvex trajectory does need a shift, so speculation was exercised
+    eng_s.close()
+    eng_q.close()
