@@ -39,9 +39,11 @@ typedef struct b200ipm_params {
     int    nrefine;                       /* iterative-refinement sweeps against the UNREDUCED KKT residual */
     int    ls_batch;                      /* speculative line-search trials evaluated per launch */
     int    max_reg_retries;               /* cap on the delta*=10 loop (pyipm.py:1399-1403 has none) */
-    int    flags;                         /* bit 0 (B200IPM_FLAG_NO_SPECULATION): never run reghess attempts concurrently */
+    int    flags;                         /* B200IPM_FLAG_* bits */
 } b200ipm_params;
 #define B200IPM_FLAG_NO_SPECULATION 1
+#define B200IPM_FLAG_TCGEN05_SYRK   2   /* d2L and condensation contractions on tcgen05 (int8 error-free split) */
+#define B200IPM_FLAG_TCGEN05_WIDE   4   /* with TCGEN05_SYRK: 128x128 tiles / two passes instead of 128x64 / one */
 
 /* Everything one inner iteration (pyipm.py:1714-1754) reports back. */
 typedef struct b200ipm_step_info {
@@ -68,6 +70,9 @@ typedef struct b200ipm_step_info {
     int    n_spec;                   /* 1 if the delta = 0 and delta = max(delta/2, delta0) attempts of reghess ran
                                         concurrently on two streams (same decisions, n_factor counts both) */
     int    spec_used;                /* 1 if the speculative attempt was the accepted factorisation */
+    int    tc_syrk;                  /* 1 if the two contractions of this step ran on tcgen05 (0: fp64 DMMA, also after
+                                        a fallback because of non-finite inputs / unexpected negative weights) */
+    int    reserved;
 } b200ipm_step_info;
 
 int         b200ipm_version(void);
@@ -185,7 +190,8 @@ int b200ipm_gemm_nt_update_bc(b200ipm_ldlt_handle h, double* C_dev, int ldc, int
  * and returns the mean milliseconds per launch plus its algorithmic work (FLOPs or bytes):
  *   which = 0 residual GEMV g_x = df - J*lda (HBM)      1 Lagrangian-Hessian SYRK (fp64 tensor)
  *           2 condensation SYRK dci*S*dci' (fp64 tensor) 3 one LDL^T factorisation of the condensed KKT matrix
- *           4 one forward+backward triangular solve      5 J'*dx GEMV (HBM) */
+ *           4 one forward+backward triangular solve      5 J'*dx GEMV (HBM)
+ *           6 / 7 = 1 / 2 on the tcgen05 int8 path (work is still the fp64-equivalent FLOP count) */
 int b200ipm_profile_kernel(b200ipm_handle h, int which, int reps, float* ms_per_launch, double* work);
 
 /* ---- test hooks: individual kernels against the oracle (tests/test_gpu_kernels.py) ---------------- */
@@ -195,6 +201,14 @@ int b200ipm_test_syrk(int n, const double* Cin, double beta, const double* dadd,
                       int nterms, const double* const* A, const double* const* w, const int* K,
                       const double* alpha, double* C, int force_simple, float* ms);
 int b200ipm_test_gemv(int rows, int cols, const double* A, const double* v, double* y, int transpose);
+/* Same product as b200ipm_test_syrk, computed on the tcgen05 tensor cores by the int8 error-free (Ozaki) path:
+ * signed_mask bit t = alpha_t*w_t may be negative; variant 0 = 128x64 tiles / one pass, 1 = 128x128 tiles / two
+ * passes; lbo, sbo <= 0 keep the default shared-memory descriptor strides; ms[2] = {0, total ms of one call};
+ * *err = device error word (1 non-finite input, 2 negative weight without sign operand, 4 pipeline timeout). */
+int b200ipm_test_syrk_i8(int n, const double* Cin, double beta, const double* dadd, double shift,
+                         int nterms, const double* const* A, const double* const* w, const int* K,
+                         const double* alpha, double* C, unsigned signed_mask, int variant, int lbo, int sbo,
+                         float* ms, int* err);
 
 #ifdef __cplusplus
 }

@@ -37,7 +37,8 @@ class StepInfo(C.Structure):
                 ('n_neg_first', C.c_int), ('n_zero_first', C.c_int),
                 ('ms_eval', C.c_float), ('ms_assemble', C.c_float), ('ms_factor', C.c_float), ('ms_solve', C.c_float),
                 ('ms_search', C.c_float), ('ms_total', C.c_float), ('ms_hess_kernel', C.c_float),
-                ('ms_condense_kernel', C.c_float), ('n_spec', C.c_int), ('spec_used', C.c_int)]
+                ('ms_condense_kernel', C.c_float), ('n_spec', C.c_int), ('spec_used', C.c_int),
+                ('tc_syrk', C.c_int), ('reserved', C.c_int)]
 
     def asdict(self):
         d = {}
@@ -56,7 +57,7 @@ SYMBOLS = [
     'b200ipm_kkt', 'b200ipm_con_jac', 'b200ipm_hess_full', 'b200ipm_d2L', 'b200ipm_merit', 'b200ipm_init_slack',
     'b200ipm_init_lambda', 'b200ipm_update_mu', 'b200ipm_direction', 'b200ipm_step_max', 'b200ipm_newton_step',
     'b200ipm_ldlt_create', 'b200ipm_ldlt_destroy', 'b200ipm_ldlt_factor', 'b200ipm_ldlt_solve',
-    'b200ipm_ldlt_tile_factor', 'b200ipm_ldlt_panel', 'b200ipm_ldlt_import', 'b200ipm_gemm_nt_update', 'b200ipm_gemm_nt_update_bc', 'b200ipm_test_syrk',
+    'b200ipm_ldlt_tile_factor', 'b200ipm_ldlt_panel', 'b200ipm_ldlt_import', 'b200ipm_gemm_nt_update', 'b200ipm_gemm_nt_update_bc', 'b200ipm_test_syrk', 'b200ipm_test_syrk_i8',
     'b200ipm_test_gemv',
 ]
 
@@ -120,6 +121,8 @@ def load():
         'b200ipm_gemm_nt_update_bc': (i, [vp, vp, i, i, i, vp, i, vp, i, i, i, i, i, i, i, i, i]),
         'b200ipm_test_syrk': (i, [i, vp, d, vp, d, i, C.POINTER(vp), C.POINTER(vp), ip, dp, vp, i,
                                   C.POINTER(C.c_float)]),
+        'b200ipm_test_syrk_i8': (i, [i, vp, d, vp, d, i, C.POINTER(vp), C.POINTER(vp), ip, dp, vp, C.c_uint, i, i, i,
+                                     C.POINTER(C.c_float), ip]),
         'b200ipm_test_gemv': (i, [i, i, vp, vp, vp, i]),
     }
     for name in SYMBOLS:
@@ -367,6 +370,25 @@ def test_syrk(n, Cin, beta, dadd, shift, terms, force_simple=False):
     check(lib.b200ipm_test_syrk(int(n), ptr(Cin), float(beta), ptr(dadd), float(shift), nt, Ap, wp, Ks, al, ptr(out),
                                 1 if force_simple else 0, C.byref(ms)))
     return out, ms.value
+
+
+def test_syrk_i8(n, Cin, beta, dadd, shift, terms, signed_mask=0, variant=0, lbo=0, sbo=0):
+    """tcgen05 int8 (Ozaki) version of test_syrk.  Returns (C, ms_total, err_word)."""
+    lib = load()
+    nt = len(terms)
+    As = [f64(t[0]) for t in terms]
+    ws = [f64(t[1]) for t in terms]
+    Ap = (C.c_void_p * max(nt, 1))(*[ptr(a) for a in As])
+    wp = (C.c_void_p * max(nt, 1))(*[ptr(w) if w is not None else None for w in ws])
+    Ks = (C.c_int * max(nt, 1))(*[a.shape[1] for a in As])
+    al = (C.c_double * max(nt, 1))(*[float(t[2]) for t in terms])
+    Cin, dadd = f64(Cin), f64(dadd)
+    out = np.empty((n, n))
+    ms = (C.c_float * 2)()
+    err = C.c_int(0)
+    check(lib.b200ipm_test_syrk_i8(int(n), ptr(Cin), float(beta), ptr(dadd), float(shift), nt, Ap, wp, Ks, al, ptr(out),
+                                   int(signed_mask), int(variant), int(lbo), int(sbo), ms, C.byref(err)))
+    return out, ms[1], err.value
 
 
 def test_gemv(A, v, transpose=False):

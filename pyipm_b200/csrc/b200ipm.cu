@@ -12,6 +12,7 @@
 #include "vec.cuh"
 #include "gemm_nt.cuh"
 #include "ldlt.cuh"
+#include "ozaki_i8.cuh"
 #include "engine_kernels.cuh"
 
 #include <vector>
@@ -47,6 +48,9 @@ struct b200ipm_engine {
     bool strict_retry = false;
     int n_strict = 0;        // number of strict re-factorisations triggered by a poor residual
     LdltWs F;               // condensed KKT factorisation (order Kc)
+    OzWs oz;                // tcgen05 int8 slices (B200IPM_FLAG_TCGEN05_SYRK)
+    bool oz_used = false;   // the current W / Hb came from the tcgen05 path
+    bool oz_off = false;    // this step fell back to DMMA
     LdltWs Fb;              // speculative second attempt of reghess (lazy), factored concurrently on stB
     bool Fb_ready = false;
     cudaStream_t stB = nullptr;
@@ -158,8 +162,13 @@ static int eval_derivs(Eng* h) {
     h->resid_valid = false;
     return 0;
 }
+static bool use_tc(Eng* h) {
+    return (h->p.flags & B200IPM_FLAG_TCGEN05_SYRK) && !h->oz_off && h->D >= 256;
+}
+static void oz_configure(Eng* h) { h->oz.variant = (h->p.flags & B200IPM_FLAG_TCGEN05_WIDE) ? 1 : 0; }
 // W = d2L at the current (x, lda): only needed when a search direction is computed (a3)
 static int eval_hessian(Eng* h) {
+    oz_configure(h);
     RET(eval_derivs(h));
     if (h->hess_valid) return 0;
     const int D = h->D, M = h->M, N = h->N;
@@ -171,7 +180,12 @@ static int eval_hessian(Eng* h) {
         a.shift = 0.0; a.mode = GEMM_UPPER_MIRROR; a.nterms = 0;
         if (M && h->Ut) a.t[a.nterms++] = GemmTerm{h->Ut, h->Ut, h->lam, M, M, M, -1.0};
         if (N && h->Vt) a.t[a.nterms++] = GemmTerm{h->Vt, h->Vt, h->lam + M, N, N, N, 1.0};
-        RET(gemm_nt(h->st, a));
+        if (use_tc(h) && a.nterms) {
+            RET(oz_syrk(h->st, a, h->oz, (M && h->Ut) ? 1u : 0u));   // lda_e has either sign, lda_i >= 0
+            h->oz_used = true;
+        } else {
+            RET(gemm_nt(h->st, a));
+        }
     } else if (h->kind == KIND_POLY) {
         poly_hess_kernel<<<cdiv(D * D, 256), 256, 0, h->st>>>(D, M, N, h->poly, h->x, h->lam, h->W, h->ldW);
         LAUNCHED();
@@ -214,7 +228,12 @@ static int condense(Eng* h) {
     a.shift = 0.0; a.mode = GEMM_UPPER_MIRROR; a.nterms = 0;
     if (N) a.t[a.nterms++] = GemmTerm{h->J + M, h->J + M, h->sigma, h->ldJ, h->ldJ, N, 1.0};
     CU(cudaEventRecord(h->ev[EV_COND0], h->st));
-    RET(gemm_nt(h->st, a));
+    if (use_tc(h) && a.nterms) {
+        RET(oz_syrk(h->st, a, h->oz, 0u));                           // sigma = lda_i / (s + eps) >= 0 in the interior
+        h->oz_used = true;
+    } else {
+        RET(gemm_nt(h->st, a));
+    }
     CU(cudaEventRecord(h->ev[EV_COND1], h->st));
     return 0;
 }
@@ -670,11 +689,32 @@ static int line_search(Eng* h, b200ipm_step_info* info, const double* stats /* h
 // ------------------------------------------------------------------------------------------ direction + step
 static int compute_direction(Eng* h, b200ipm_step_info* info) {
     RET(residual(h));
+    h->oz_off = false;
+    h->oz_used = false;
+    const double delta_in = h->delta;
     RET(eval_hessian(h));
     CU(cudaEventRecord(h->ev[EV_EVAL], h->st));
     RET(condense(h));
     CU(cudaEventRecord(h->ev[EV_ASSEMBLE], h->st));
     RET(factor_regularised(h, info));
+    if (h->oz_used) {
+        // the tcgen05 path reports inputs it cannot represent (non-finite entries, a negative weight where none was
+        // announced, a pipeline timeout) through a device word: redo the step's contractions in fp64 DMMA then
+        int ew = 0;
+        CU(cudaMemcpyAsync(&ew, h->oz.err, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+        CU(cudaStreamSynchronize(h->st));
+        if (ew) {
+            CU(cudaMemsetAsync(h->oz.err, 0, sizeof(int), h->st));
+            h->oz_off = true;
+            h->oz_used = false;
+            h->hess_valid = false;
+            h->delta = delta_in;
+            RET(eval_hessian(h));
+            RET(condense(h));
+            RET(factor_regularised(h, info));
+        }
+    }
+    if (info) info->tc_syrk = h->oz_used ? 1 : 0;
     CU(cudaEventRecord(h->ev[EV_FACTOR], h->st));
     RET(solve_direction(h, info));
     CU(cudaEventRecord(h->ev[EV_SOLVE], h->st));
@@ -767,6 +807,7 @@ int b200ipm_destroy(b200ipm_handle h) {
     cudaFree(h->p_rowptr); cudaFree(h->p_ptr); cudaFree(h->p_fvar); cudaFree(h->p_fpow);
     cudaFreeHost(h->h_red);
     ldlt_free(h->F);
+    oz_free(h->oz);
     if (h->F2_ready) ldlt_free(h->F2);
     if (h->Fb_ready) {
         cudaStreamSynchronize(h->stB);
@@ -939,7 +980,7 @@ int b200ipm_profile_kernel(b200ipm_handle h, int which, int reps, float* ms_per_
     const int D = h->D, M = h->M, N = h->N, C = h->C;
     double wk = 0.0;
     if (which >= 2) RET(condense(h));
-    if (which >= 4) { RET(build_kc(h, h->delta, 0.0)); RET(ldlt_factor(h->F)); }
+    if (which >= 4 && which <= 5) { RET(build_kc(h, h->delta, 0.0)); RET(ldlt_factor(h->F)); }
     CU(cudaStreamSynchronize(h->st));
     CU(cudaEventRecord(h->ev[EV_START], h->st));
     for (int r = 0; r < reps; r++) {
@@ -965,6 +1006,28 @@ int b200ipm_profile_kernel(b200ipm_handle h, int which, int reps, float* ms_per_
                 a.mode = GEMM_UPPER_MIRROR; a.nterms = 0;
                 if (N) a.t[a.nterms++] = GemmTerm{h->J + M, h->J + M, h->sigma, h->ldJ, h->ldJ, N, 1.0};
                 RET(gemm_nt(h->st, a));
+                wk = gemm_nt_flops(a);
+                break;
+            }
+            case 6: {
+                GemmArgs a{};
+                a.C = h->W; a.ldc = h->ldW; a.Cin = h->Q; a.ldcin = D; a.dadd = h->xdiag; a.n = D; a.m = D; a.beta = 1.0;
+                a.mode = GEMM_UPPER_MIRROR; a.nterms = 0;
+                if (h->kind != KIND_QUAD) return fail_msg("profile_kernel(6) needs a bound quad problem");
+                if (M && h->Ut) a.t[a.nterms++] = GemmTerm{h->Ut, h->Ut, h->lam, M, M, M, -1.0};
+                if (N && h->Vt) a.t[a.nterms++] = GemmTerm{h->Vt, h->Vt, h->lam + M, N, N, N, 1.0};
+                oz_configure(h);
+                RET(oz_syrk(h->st, a, h->oz, (M && h->Ut) ? 1u : 0u));
+                wk = gemm_nt_flops(a);
+                break;
+            }
+            case 7: {
+                GemmArgs a{};
+                a.C = h->Hb; a.ldc = h->ldW; a.Cin = h->W; a.ldcin = h->ldW; a.n = D; a.m = D; a.beta = 1.0;
+                a.mode = GEMM_UPPER_MIRROR; a.nterms = 0;
+                if (N) a.t[a.nterms++] = GemmTerm{h->J + M, h->J + M, h->sigma, h->ldJ, h->ldJ, N, 1.0};
+                oz_configure(h);
+                RET(oz_syrk(h->st, a, h->oz, 0u));
                 wk = gemm_nt_flops(a);
                 break;
             }
@@ -1374,6 +1437,63 @@ int b200ipm_test_syrk(int n, const double* Cin, double beta, const double* dadd,
     for (int t = 0; t < 3; t++) { cudaFree(dA[t]); cudaFree(dw[t]); }
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     return 0;
+}
+// Same contract as b200ipm_test_syrk, computed by the tcgen05 int8 Ozaki path (ozaki_i8.cuh).  variant: 0 = 128x64 tiles,
+// one pass; 1 = 128x128 tiles, two passes.  lbo/sbo <= 0 keep the default descriptor strides.  ms[0] = slicing kernel,
+// ms[1] = tensor-core kernel; *err = device error word (1 non-finite, 2 negative weight w/o sign operand, 4 timeout).
+int b200ipm_test_syrk_i8(int n, const double* Cin, double beta, const double* dadd, double shift, int nterms,
+                         const double* const* A, const double* const* w, const int* K, const double* alpha, double* C,
+                         unsigned signed_mask, int variant, int lbo, int sbo, float* ms, int* err) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail_msg("no CUDA device available");
+    if (nterms < 0 || nterms > 3) return fail_msg("test_syrk_i8: 0..3 terms");
+    cudaStream_t st = nullptr;
+    double *dC = nullptr, *dCin = nullptr, *dd = nullptr, *dA[3] = {nullptr, nullptr, nullptr}, *dw[3] = {nullptr, nullptr, nullptr};
+    const int ld = (int)rup(n, 16);
+    RET(dalloc(&dC, (size_t)n * ld));
+    CU(cudaMemset(dC, 0xff, sizeof(double) * (size_t)n * ld));   // NaN pattern: untouched elements are visible
+    GemmArgs a{};
+    a.C = dC; a.ldc = ld; a.n = n; a.m = n; a.beta = beta; a.shift = shift; a.mode = GEMM_UPPER_MIRROR; a.nterms = nterms;
+    if (Cin) {
+        RET(dalloc(&dCin, (size_t)n * ld));
+        CU(cudaMemcpy2D(dCin, sizeof(double) * ld, Cin, sizeof(double) * n, sizeof(double) * n, n, cudaMemcpyHostToDevice));
+        a.Cin = dCin; a.ldcin = ld;
+    }
+    if (dadd) { RET(dalloc(&dd, n)); CU(cudaMemcpy(dd, dadd, sizeof(double) * n, cudaMemcpyHostToDevice)); a.dadd = dd; }
+    for (int t = 0; t < nterms; t++) {
+        const int ldk = (int)rup(K[t], 16);
+        RET(dalloc(&dA[t], (size_t)n * ldk));
+        CU(cudaMemcpy2D(dA[t], sizeof(double) * ldk, A[t], sizeof(double) * K[t], sizeof(double) * K[t], n, cudaMemcpyHostToDevice));
+        if (w && w[t]) { RET(dalloc(&dw[t], K[t])); CU(cudaMemcpy(dw[t], w[t], sizeof(double) * K[t], cudaMemcpyHostToDevice)); }
+        a.t[t] = GemmTerm{dA[t], dA[t], dw[t], ldk, ldk, K[t], alpha[t]};
+    }
+    OzWs ws;
+    ws.variant = variant;
+    if (lbo > 0) ws.lbo = lbo;
+    if (sbo > 0) ws.sbo = sbo;
+    cudaEvent_t e0, e1, e2;
+    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1)); CU(cudaEventCreate(&e2));
+    int rc = oz_syrk(st, a, ws, signed_mask);   // warm-up (allocations, attributes)
+    if (rc == 0 && cudaStreamSynchronize(st) != cudaSuccess) rc = fail_msg("test_syrk_i8: kernel failed");
+    if (rc == 0) {
+        // timed: the two kernels separately
+        CU(cudaEventRecord(e0, st));
+        rc = oz_syrk(st, a, ws, signed_mask);
+        CU(cudaEventRecord(e2, st));
+        CU(cudaEventSynchronize(e2));
+        float t = 0.f;
+        CU(cudaEventElapsedTime(&t, e0, e2));
+        if (ms) { ms[0] = 0.f; ms[1] = t; }
+    }
+    if (rc == 0) {
+        if (err) CU(cudaMemcpy(err, ws.err, sizeof(int), cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy2D(C, sizeof(double) * n, dC, sizeof(double) * ld, sizeof(double) * n, n, cudaMemcpyDeviceToHost));
+    }
+    oz_free(ws);
+    cudaFree(dC); cudaFree(dCin); cudaFree(dd);
+    for (int t = 0; t < 3; t++) { cudaFree(dA[t]); cudaFree(dw[t]); }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+    return rc;
 }
 int b200ipm_test_gemv(int rows, int cols, const double* A, const double* v, double* y, int transpose_) {
     int ndev = 0;

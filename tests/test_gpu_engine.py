@@ -293,3 +293,50 @@ def test_speculative_reghess_matches_sequential():
     assert n_spec >= 1      # the nonconvex trajectory does need a shift, so speculation was exercised
     eng_s.close()
     eng_q.close()
+
+
+@pytest.mark.parametrize('flags', [2, 6])
+def test_tcgen05_syrk_path_teacher_forced(flags):
+    """Engine with the d2L and condensation contractions on tcgen05 (B200IPM_FLAG_TCGEN05_SYRK, 128x64 and 128x128
+    tile variants): same reghess decisions and the same direction as the CPU oracle, to the fp64 tolerance."""
+    prob = problems.make_nlp(D=320, M=48, N=320, seed=5)
+    o, tr = oracle_trace(prob, prob.x0, niter=1, miter=4)
+    eng = make_engine(prob, flags=flags)
+    nu_b, de_b = 10.0, 0.0
+    for k, st in enumerate(tr):
+        eng.set_state(st['x'], st['s'], st['lda'], st['mu'], nu_b, de_b)
+        eng.set_mu_host(st['mu_host'])
+        dz, info = eng.direction()
+        assert info.tc_syrk == 1
+        assert info.delta == st['delta'] and info.n_factor == st['reg']['n_eig'] and info.n_neg == prob.neq
+        assert relinf(dz, st['dz']) < DZ_RTOL, (k, relinf(dz, st['dz']))
+        H = eng.hess_full()
+        Href = o.hess(st['x'], st['s'], st['lda'])
+        assert np.max(np.abs(H - Href)) <= 1e-12 * max(1.0, np.max(np.abs(Href)))
+        eng.set_state(st['x'], st['s'], st['lda'], st['mu'], nu_b, de_b)
+        info = eng.newton_step()
+        assert info.n_backtracks == st['search']['n_backtracks']
+        x, s, lda, _, _, _ = eng.get_state()
+        assert relinf(x, st['x_new']) < 1e-8 and relinf(s, st['s_new']) < 1e-8 and relinf(lda, st['lda_new']) < 1e-8
+        nu_b, de_b = st['nu_after'], st['delta']
+    eng.close()
+
+
+def test_tcgen05_syrk_falls_back_on_negative_multipliers():
+    """A teacher-forced state with negative inequality multipliers (never produced by the IPM itself) cannot be
+    represented by the unsigned operand of the tcgen05 path: the engine must notice and redo the step in fp64 DMMA."""
+    prob = problems.make_nlp(D=320, M=48, N=320, seed=5)
+    rng = np.random.default_rng(0)
+    x = prob.x0.copy()
+    s = np.maximum(prob.ci(x), 1e-2)
+    lda = np.concatenate([rng.standard_normal(prob.neq), rng.standard_normal(prob.nineq)])
+    out = []
+    for flags in (0, 2):
+        eng = make_engine(prob, flags=flags)
+        eng.set_state(x, s, lda, 0.2, 10.0, 0.0)
+        eng.set_mu_host(0.2)
+        out.append(eng.direction())
+        eng.close()
+    (dz0, i0), (dz1, i1) = out
+    assert i1.tc_syrk == 0 and i0.tc_syrk == 0
+    assert np.array_equal(dz0, dz1) and i0.delta == i1.delta and i0.n_factor == i1.n_factor

@@ -134,3 +134,45 @@ def test_ldlt_singular_reports_zero_pivot():
     (pos, neg, zero), rcond = F.factor(K)
     F.close()
     assert zero == 2 and pos == 2 and rcond == 0.0
+
+
+@pytest.mark.parametrize('variant', [0, 1])
+@pytest.mark.parametrize('n,Ks', [(128, [32]), (130, [70, 33]), (300, [70, 203]), (640, [512, 100, 40])])
+def test_syrk_tcgen05_int8_matches_fp64(n, Ks, variant):
+    """The tcgen05 path (error-free int8 split, int32 TMEM accumulators, fp64 recombination) must reproduce the fp64
+    product to fp64 accuracy: signed weights on the first term (lda_e), weights spanning 12 orders of magnitude on
+    the second (Sigma / lda_i), ragged sizes, asymmetric Cin, diagonal add."""
+    rng = np.random.default_rng(n + sum(Ks) + variant)
+    Cin = rng.standard_normal((n, n))
+    dadd = rng.standard_normal(n)
+    terms = []
+    for i, K in enumerate(Ks):
+        if i == 0:
+            w = rng.standard_normal(K)
+        elif i == 1:
+            w = 10.0 ** rng.uniform(-6, 6, K)
+        else:
+            w = None
+        terms.append((rng.standard_normal((n, K)), w, [-1.0, 1.0, 0.5][i]))
+    C, ms, err = _lib.test_syrk_i8(n, Cin, 1.0, dadd, 0.25, terms, signed_mask=1, variant=variant)
+    assert err == 0
+    ref = _syrk_ref(n, Cin, 1.0, dadd, 0.25, terms)
+    # bound relative to the products of the row scales (the fixed-point split is relative to each row's largest entry)
+    rowmax = np.sqrt(sum(((np.abs(A) * np.sqrt(np.abs(al * (1.0 if w is None else w)))).max(axis=1)) ** 2 for A, w, al in terms))
+    scale = np.outer(rowmax, rowmax) * sum(Ks) + np.abs(ref) + 1.0
+    assert np.array_equal(C, C.T), 'output must be bitwise symmetric'
+    assert np.max(np.abs(C - ref) / scale) < 2e-16 * 8
+    # and against the DMMA kernel on the same inputs
+    Cd, _ = _lib.test_syrk(n, Cin, 1.0, dadd, 0.25, terms)
+    assert np.max(np.abs(C - Cd) / scale) < 1e-15 * max(Ks)
+
+
+def test_syrk_tcgen05_reports_unannounced_negative_weight():
+    rng = np.random.default_rng(5)
+    A = rng.standard_normal((128, 64))
+    w = rng.standard_normal(64)
+    _, _, err = _lib.test_syrk_i8(128, None, 0.0, None, 0.0, [(A, w, 1.0)], signed_mask=0)
+    assert err & 2
+    A[3, 5] = np.inf
+    _, _, err = _lib.test_syrk_i8(128, None, 0.0, None, 0.0, [(A, np.abs(w), 1.0)], signed_mask=0)
+    assert err & 1
