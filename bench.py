@@ -38,6 +38,7 @@ PRE_STEPS = 3   # real Newton steps taken from x0 before the teacher-forced stat
 # calls, delta0 * 10^8); starting the sample at 2x this value makes every sampled step do the typical mid-solve
 # work of two inertia tests (delta = 0 rejected, delta/2 accepted) instead of the 10-test discovery.
 DELTA_SAMPLE = 1.4901161193847656
+DEFAULT_FLAGS = 0
 
 
 def measured_peaks():
@@ -246,7 +247,7 @@ def run_b200(args):
     hbm_gbs, bf16_tf, peak_kind = measured_peaks()
     prob = problems.make_nlp(D3, M3, N3)       # same seed on every rank: independent replicas of config 3
     stream = _lib.torch_stream_handle()
-    eng = _lib.Engine(D3, M3, N3, _lib.default_params(), device=local, stream=stream)
+    eng = _lib.Engine(D3, M3, N3, _lib.default_params(flags=args.flags), device=local, stream=stream)
     eng.bind(prob)
     eng.set_state(prob.x0, np.ones(N3), np.zeros(M3 + N3), 0.2, 10.0, 0.0)
     eng.set_mu_host(0.2)
@@ -280,6 +281,21 @@ def run_b200(args):
         best = min(best, e0.elapsed_time(e1))
     fp64_peak_tf = 2 * 4096 ** 3 / best * 1e-9
     del a, b
+    # int8 tensor-core throughput of the vendor library on THIS box (cuBLASLt via torch._int_mm), for the tcgen05 leg
+    int8_peak_tops = None
+    try:
+        ai = torch.randint(-64, 64, (8192, 8192), dtype=torch.int8, device='cuda')
+        bi = torch.randint(-64, 64, (8192, 8192), dtype=torch.int8, device='cuda')
+        torch._int_mm(ai, bi)
+        best = 1e9
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); torch._int_mm(ai, bi); e1.record(); torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        int8_peak_tops = 2 * 8192 ** 3 / best * 1e-9
+        del ai, bi
+    except Exception:
+        pass
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
@@ -337,7 +353,8 @@ def run_b200(args):
         eng.state_restore()
         kern = {}
         for which, name, kind in ((1, 'hess_syrk', 'flop'), (2, 'condense_syrk', 'flop'), (3, 'ldlt_factor', 'flop'),
-                                  (0, 'residual_gemv', 'byte'), (5, 'jt_gemv', 'byte'), (4, 'ldlt_solve', 'byte')):
+                                  (0, 'residual_gemv', 'byte'), (5, 'jt_gemv', 'byte'), (4, 'ldlt_solve', 'byte'),
+                                  (6, 'hess_syrk_tcgen05', 'flop'), (7, 'condense_syrk_tcgen05', 'flop')):
             ms, work = eng.profile_kernel(which, reps=5)
             kern[name] = {'ms': ms, ('tflops' if kind == 'flop' else 'gbs'): work / ms * (1e-9 if kind == 'flop' else 1e-6),
                           'work': work}
@@ -415,6 +432,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--flags', type=int, default=DEFAULT_FLAGS,
+                    help='b200ipm_params.flags: 1 no speculative reghess, 2 tcgen05 int8 SYRKs, (v << 2) tcgen05 tile variant')
     ap.add_argument('--workload', default='c3', choices=['c3', 'c4'])
     ap.add_argument('--c4-n', type=int, default=16384)
     args = ap.parse_args()

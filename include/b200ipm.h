@@ -43,7 +43,7 @@ typedef struct b200ipm_params {
 } b200ipm_params;
 #define B200IPM_FLAG_NO_SPECULATION 1
 #define B200IPM_FLAG_TCGEN05_SYRK   2   /* d2L and condensation contractions on tcgen05 (int8 error-free split) */
-#define B200IPM_FLAG_TCGEN05_WIDE   4   /* with TCGEN05_SYRK: 128x128 tiles / two passes instead of 128x64 / one */
+#define B200IPM_FLAG_TCGEN05_TILE(v) ((v) << 2)   /* with TCGEN05_SYRK: 0 = 128x64 tiles / 1 pass, 1 = 128x128 / 2, 2 = 128x256 / 4 */
 
 /* Everything one inner iteration (pyipm.py:1714-1754) reports back. */
 typedef struct b200ipm_step_info {
@@ -203,7 +203,8 @@ int b200ipm_test_syrk(int n, const double* Cin, double beta, const double* dadd,
 int b200ipm_test_gemv(int rows, int cols, const double* A, const double* v, double* y, int transpose);
 /* Same product as b200ipm_test_syrk, computed on the tcgen05 tensor cores by the int8 error-free (Ozaki) path:
  * signed_mask bit t = alpha_t*w_t may be negative; variant 0 = 128x64 tiles / one pass, 1 = 128x128 tiles / two
- * passes; lbo, sbo <= 0 keep the default shared-memory descriptor strides; ms[2] = {0, total ms of one call};
+ * passes, 2 = 128x256 / four; lbo, sbo <= 0 keep the default shared-memory descriptor strides; ms[2] = {slicing ms,
+ * total ms of one call};
  * *err = device error word (1 non-finite input, 2 negative weight without sign operand, 4 pipeline timeout). */
 int b200ipm_test_syrk_i8(int n, const double* Cin, double beta, const double* dadd, double shift,
                          int nterms, const double* const* A, const double* const* w, const int* K,

@@ -373,7 +373,7 @@ def test_syrk(n, Cin, beta, dadd, shift, terms, force_simple=False):
 
 
 def test_syrk_i8(n, Cin, beta, dadd, shift, terms, signed_mask=0, variant=0, lbo=0, sbo=0):
-    """tcgen05 int8 (Ozaki) version of test_syrk.  Returns (C, ms_total, err_word)."""
+    """tcgen05 int8 (Ozaki) version of test_syrk.  Returns (C, (ms_slicing, ms_total), err_word)."""
     lib = load()
     nt = len(terms)
     As = [f64(t[0]) for t in terms]
@@ -388,7 +388,7 @@ def test_syrk_i8(n, Cin, beta, dadd, shift, terms, signed_mask=0, variant=0, lbo
     err = C.c_int(0)
     check(lib.b200ipm_test_syrk_i8(int(n), ptr(Cin), float(beta), ptr(dadd), float(shift), nt, Ap, wp, Ks, al, ptr(out),
                                    int(signed_mask), int(variant), int(lbo), int(sbo), ms, C.byref(err)))
-    return out, ms[1], err.value
+    return out, (ms[0], ms[1]), err.value
 
 
 def test_gemv(A, v, transpose=False):

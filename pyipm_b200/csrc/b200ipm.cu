@@ -165,7 +165,7 @@ static int eval_derivs(Eng* h) {
 static bool use_tc(Eng* h) {
     return (h->p.flags & B200IPM_FLAG_TCGEN05_SYRK) && !h->oz_off && h->D >= 256;
 }
-static void oz_configure(Eng* h) { h->oz.variant = (h->p.flags & B200IPM_FLAG_TCGEN05_WIDE) ? 1 : 0; }
+static void oz_configure(Eng* h) { h->oz.variant = (h->p.flags >> 2) & 3; if (h->oz.variant == 3) h->oz.variant = 1; }
 // W = d2L at the current (x, lda): only needed when a search direction is computed (a3)
 static int eval_hessian(Eng* h) {
     oz_configure(h);
@@ -1471,6 +1471,7 @@ int b200ipm_test_syrk_i8(int n, const double* Cin, double beta, const double* da
     ws.variant = variant;
     if (lbo > 0) ws.lbo = lbo;
     if (sbo > 0) ws.sbo = sbo;
+    for (int i = 0; i < 3; i++) CU(cudaEventCreate(&ws.ev[i]));
     cudaEvent_t e0, e1, e2;
     CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1)); CU(cudaEventCreate(&e2));
     int rc = oz_syrk(st, a, ws, signed_mask);   // warm-up (allocations, attributes)
@@ -1481,9 +1482,10 @@ int b200ipm_test_syrk_i8(int n, const double* Cin, double beta, const double* da
         rc = oz_syrk(st, a, ws, signed_mask);
         CU(cudaEventRecord(e2, st));
         CU(cudaEventSynchronize(e2));
-        float t = 0.f;
+        float t = 0.f, tsl = 0.f;
         CU(cudaEventElapsedTime(&t, e0, e2));
-        if (ms) { ms[0] = 0.f; ms[1] = t; }
+        if (rc == 0) CU(cudaEventElapsedTime(&tsl, ws.ev[0], ws.ev[1]));
+        if (ms) { ms[0] = tsl; ms[1] = t; }
     }
     if (rc == 0) {
         if (err) CU(cudaMemcpy(err, ws.err, sizeof(int), cudaMemcpyDeviceToHost));

@@ -63,8 +63,13 @@ inline int ldlt_alloc(LdltWs& w, int n, cudaStream_t st) {
     CU(cudaMalloc(&w.A, sizeof(double) * (size_t)npad * w.ld));
     CU(cudaMalloc(&w.Wp, sizeof(double) * npad * 256));
     CU(cudaMalloc(&w.Wp2, sizeof(double) * npad * 256));
-    CU(cudaStreamCreateWithFlags(&w.side, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&w.cap, cudaStreamNonBlocking));
+    // the serial chain (tile -> panel -> in-panel update) is captured on a HIGH-priority stream, the bulk trailing
+    // updates on a LOW-priority one: a chain kernel never queues behind a full wave of long update CTAs (captured
+    // kernel nodes inherit the priority of the stream they were captured on)
+    int prio_lo = 0, prio_hi = 0;
+    CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    CU(cudaStreamCreateWithPriority(&w.side, cudaStreamNonBlocking, prio_lo));
+    CU(cudaStreamCreateWithPriority(&w.cap, cudaStreamNonBlocking, prio_hi));
     for (int i = 0; i < 2; i++) {
         CU(cudaEventCreateWithFlags(&w.ev_panel[i], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&w.ev_upd[i], cudaEventDisableTiming));

@@ -37,22 +37,40 @@ constexpr int OZ_CHUNK = OZ_BM * OZ_KB;      // bytes of one slice of one row bl
 constexpr int OZ_THREADS = 192;
 constexpr unsigned OZ_SMEM_BUDGET = 200 * 1024;
 
-struct OzTerm { const double* A; const double* w; int lda, K, koff; double alpha; };
+struct OzTerm { const double* A; const double* w; int lda, K, koff, sgn; double alpha; };   // koff: multiple of OZ_KB
 struct OzSliceArgs {
     OzTerm t[3];
-    int nterms, n, nkb, write_r;
+    int nterms, n, nkb;
     int8_t* L;
-    int8_t* R;
+    int8_t* R;          // sign-carrying copy, written only for the k-blocks of terms with sgn != 0
+    const double* sw;   // sw[koff + k] = copysign(sqrt|alpha w_k|, alpha w_k)   (oz_weight_kernel)
     int* rexp;
-    int* err;           // err[0] |= 1: non-finite operand, |= 2: negative weight in an unsigned call
+    int* err;           // err[0] |= 1: non-finite operand, |= 2: negative weight in a term announced as non-negative
 };
+
+// sw = signed square roots of the column weights, once per call (instead of once per row in the slicing kernel)
+__global__ void oz_weight_kernel(const OzSliceArgs a, double* sw) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= a.nkb * OZ_KB) return;
+    double v = 0.0;
+    for (int t = 0; t < a.nterms; t++) {
+        const int k = idx - a.t[t].koff;
+        if (k >= 0 && k < a.t[t].K) {
+            const double wk = a.t[t].w ? a.t[t].w[k] * a.t[t].alpha : a.t[t].alpha;
+            v = copysign(sqrt(fabs(wk)), wk);
+            if (wk < 0.0 && !a.t[t].sgn) atomicOr(a.err, 2);
+            if (!(fabs(wk) <= 1.7e308)) atomicOr(a.err, 1);
+        }
+    }
+    sw[idx] = v;
+}
 
 // ------------------------------------------------------------------------------------------- slicing kernel
 // One CTA per 8-row group (one row of core matrices): pass 1 = row maxima -> exponents, pass 2 = digits.
-__device__ __forceinline__ double oz_scaled(const OzTerm& T, int row, int k, bool& neg) {
-    const double wk = T.w ? T.w[k] * T.alpha : T.alpha;
+__device__ __forceinline__ double oz_scaled(const OzTerm& T, const double* __restrict__ sw, int row, int k, bool& neg) {
+    const double wk = sw[T.koff + k];
     neg = wk < 0.0;
-    return T.A[(size_t)row * T.lda + k] * sqrt(fabs(wk));
+    return T.A[(size_t)row * T.lda + k] * fabs(wk);
 }
 __global__ void __launch_bounds__(256) oz_slice_kernel(const OzSliceArgs a) {
     __shared__ int s_exp[8];
@@ -67,7 +85,7 @@ __global__ void __launch_bounds__(256) oz_slice_kernel(const OzSliceArgs a) {
                 const OzTerm T = a.t[t];
                 for (int k = lane; k < T.K; k += 32) {
                     bool ng;
-                    const double v = fabs(oz_scaled(T, row, k, ng));
+                    const double v = fabs(oz_scaled(T, a.sw, row, k, ng));
                     if (!(v <= 1.7e308)) bad = true;      // inf / nan
                     m = fmax(m, v);
                 }
@@ -94,7 +112,7 @@ __global__ void __launch_bounds__(256) oz_slice_kernel(const OzSliceArgs a) {
         const int k0 = cc * 16;
         int t = -1;
         for (int u = 0; u < a.nterms; u++)
-            if (k0 >= a.t[u].koff && k0 < a.t[u].koff + ((a.t[u].K + 15) & ~15)) t = u;
+            if (k0 >= a.t[u].koff && k0 < a.t[u].koff + ((a.t[u].K + OZ_KB - 1) & ~(OZ_KB - 1))) t = u;
         double v[16];
         unsigned negmask = 0;
 #pragma unroll
@@ -106,12 +124,12 @@ __global__ void __launch_bounds__(256) oz_slice_kernel(const OzSliceArgs a) {
             for (int b = 0; b < 16; b++) {
                 if (kl + b < T.K) {
                     bool ng;
-                    v[b] = oz_scaled(T, row, kl + b, ng);
+                    v[b] = oz_scaled(T, a.sw, row, kl + b, ng);
                     if (ng) negmask |= 1u << b;
                 }
             }
         }
-        if (negmask && !a.write_r) atomicOr(a.err, 2);
+        const bool write_r = (t >= 0) && a.t[t].sgn;
         // digits: x = v * 2^(6 - e);  t0 = rint(x); then 7 bits per further slice (all operations exact in fp64)
         double rem[16];
 #pragma unroll
@@ -131,7 +149,7 @@ __global__ void __launch_bounds__(256) oz_slice_kernel(const OzSliceArgs a) {
                 wr[b >> 2] |= ((unsigned)tr & 0xffu) << (8 * (b & 3));
             }
             *reinterpret_cast<uint4*>(a.L + base + (size_t)p * OZ_CHUNK) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
-            if (a.write_r)
+            if (write_r)
                 *reinterpret_cast<uint4*>(a.R + base + (size_t)p * OZ_CHUNK) = make_uint4(wr[0], wr[1], wr[2], wr[3]);
         }
     }
@@ -225,6 +243,8 @@ struct OzGemmArgs {
     double beta, shift;
     uint64_t desc_hi;      // descriptor bits above the start address (LBO, SBO, version, layout)
     uint32_t idesc;
+    int kb_end[3];         // k-blocks [kb_end[t-1], kb_end[t]) belong to term t
+    int sgn[3];            // the B side of a signed term's k-blocks comes from R (sign applied), otherwise from L
 };
 
 // BN = tile width (UMMA N), NPASS passes of DPP = 8 / NPASS diagonals each (DPP * BN = 512 TMEM columns).
@@ -242,7 +262,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzGemmArgs
     __shared__ __align__(8) uint64_t bar_full[STAGES], bar_empty[STAGES], bar_tfull, bar_tempty;
     __shared__ uint32_t s_tmem;
     __shared__ int s_dead;
-    __shared__ int s_cexp[BN];
+    __shared__ double s_cscale[BN];   // 2^(e_j - 6) of the tile's columns
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int2 tile = a.tiles[blockIdx.x];
     const int ti = tile.x, tj = tile.y;
@@ -258,7 +278,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzGemmArgs
         oz_mbar_init(oz_smem_u32(&bar_tempty), 4);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
-    for (int c = tid; c < BN; c += OZ_THREADS) s_cexp[c] = (col0 + c < a.n) ? a.rexp[col0 + c] : 0;
+    for (int c = tid; c < BN; c += OZ_THREADS) s_cscale[c] = scalbn(1.0, ((col0 + c < a.n) ? a.rexp[col0 + c] : 0) - 6);
     if (warp == 0) {
         const uint32_t ncols = 512;
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(oz_smem_u32(&s_tmem)), "r"(ncols)
@@ -287,13 +307,25 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzGemmArgs
                     const uint32_t sa = smem0 + s * STAGE, sb = sa + A_BYTES;
                     const int8_t* srcA = a.L + ((size_t)(ti * a.nkb + kb) * OZ_NS) * OZ_CHUNK;
                     oz_bulk_g2s(sa, srcA, (uint32_t)(nsl * OZ_CHUNK), full);
-                    const int rbB = col0 / OZ_BM, subB = (col0 % OZ_BM) * OZ_KB;   // byte offset of the BN rows in a chunk
-                    const int8_t* srcB = a.R + ((size_t)(rbB * a.nkb + kb) * OZ_NS) * OZ_CHUNK + subB;
-                    if (BN == OZ_BM) {
-                        oz_bulk_g2s(sb, srcB, (uint32_t)(nsl * OZ_CHUNK), full);
+                    const int term = (kb < a.kb_end[0]) ? 0 : ((kb < a.kb_end[1]) ? 1 : 2);
+                    const int8_t* Bsrc = a.sgn[term] ? a.R : a.L;
+                    if (BN <= OZ_BM) {
+                        const int rbB = col0 / OZ_BM, subB = (col0 % OZ_BM) * OZ_KB;   // byte offset of the BN rows in a chunk
+                        const int8_t* srcB = Bsrc + ((size_t)(rbB * a.nkb + kb) * OZ_NS) * OZ_CHUNK + subB;
+                        if (BN == OZ_BM) {
+                            oz_bulk_g2s(sb, srcB, (uint32_t)(nsl * OZ_CHUNK), full);
+                        } else {
+                            for (int q = 0; q < nsl; q++)
+                                oz_bulk_g2s(sb + q * B_SLICE, srcB + (size_t)q * OZ_CHUNK, (uint32_t)B_SLICE, full);
+                        }
                     } else {
+                        // BN = 256: a slice tile is two 128-row chunks from consecutive row blocks (rows beyond n: the
+                        // slicing kernel zero-fills whole row blocks, and nrb is padded so the second block exists)
+                        const int rbB = col0 / OZ_BM;
                         for (int q = 0; q < nsl; q++)
-                            oz_bulk_g2s(sb + q * B_SLICE, srcB + (size_t)q * OZ_CHUNK, (uint32_t)B_SLICE, full);
+                            for (int hh = 0; hh < BN / OZ_BM; hh++)
+                                oz_bulk_g2s(sb + q * B_SLICE + hh * OZ_CHUNK,
+                                            Bsrc + ((size_t)((rbB + hh) * a.nkb + kb) * OZ_NS + q) * OZ_CHUNK, (uint32_t)OZ_CHUNK, full);
                     }
                 }
             }
@@ -329,14 +361,31 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzGemmArgs
             }
         }
     } else {
-        // ===== epilogue: warp (warp & 3) owns TMEM lanes 32*(warp & 3) .. +31 = tile rows
+        // ===== epilogue: warp (warp & 3) owns TMEM lanes 32*(warp & 3) .. +31 = tile rows.  Per 8-column chunk: the
+        // global operands (partial sum of the higher diagonals, Cin) are prefetched one chunk ahead, the DPP int32
+        // accumulators are read with tcgen05.ld, recombined by Horner in fp64 and scaled by exact powers of two.
         const int q4 = warp & 3;
         const int rl = q4 * 32 + lane;
         const int i = row0 + rl;
-        const int ei = (i < a.n) ? a.rexp[i] : 0;
+        const bool rowok = i < a.n;
+        const int ei = rowok ? a.rexp[i] : 0;
+        const double dii = rowok ? (a.shift + (a.dadd ? a.dadd[i] : 0.0)) : 0.0;
         for (int pi = 0; pi < NPASS; pi++) {
             const int d0 = (NPASS - 1 - pi) * DPP;
             const bool last = (pi == NPASS - 1);
+            const bool need_part = (pi > 0), need_cin = last && (a.Cin != nullptr);
+            const double si = scalbn(1.0, ei - 6 - 7 * d0);
+            double pre_p[8], pre_c[8];
+            auto prefetch = [&](int cb) {
+#pragma unroll
+                for (int c = 0; c < 8; c++) {
+                    const int j = col0 + cb * 8 + c;
+                    const bool ok = rowok && j < a.n && i <= j;
+                    pre_p[c] = (ok && need_part) ? a.C[(size_t)i * a.ldc + j] : 0.0;
+                    pre_c[c] = (ok && need_cin) ? a.Cin[(size_t)i * a.ldcin + j] : 0.0;
+                }
+            };
+            prefetch(0);
             oz_mbar_wait(oz_smem_u32(&bar_tfull), (uint32_t)pi & 1u, dead, a.err);
             oz_tc_fence_after();
             for (int cb = 0; cb < BN / 8; cb++) {
@@ -344,8 +393,12 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzGemmArgs
 #pragma unroll
                 for (int dd = 0; dd < DPP; dd++)
                     oz_tmem_ld8(tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(dd * BN + cb * 8), acc[dd]);
+                double cur_p[8], cur_c[8];
+#pragma unroll
+                for (int c = 0; c < 8; c++) { cur_p[c] = pre_p[c]; cur_c[c] = pre_c[c]; }
+                if (cb + 1 < BN / 8) prefetch(cb + 1);
                 oz_tmem_wait_ld();
-                if (i < a.n) {
+                if (rowok) {
 #pragma unroll
                     for (int c = 0; c < 8; c++) {
                         const int j = col0 + cb * 8 + c;
@@ -353,12 +406,11 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzGemmArgs
                         double h = (double)acc[DPP - 1][c];
 #pragma unroll
                         for (int dd = DPP - 2; dd >= 0; dd--) h = fma(h, 0.0078125, (double)acc[dd][c]);
-                        double v = scalbn(h, ei + s_cexp[cb * 8 + c] - 12 - 7 * d0);
+                        double v = (h * si) * s_cscale[cb * 8 + c] + cur_p[c];
                         double* cp = a.C + (size_t)i * a.ldc + j;
-                        if (pi > 0) v += *cp;                     // partial sum of the higher diagonals
                         if (last) {
-                            if (a.Cin) v += a.beta * a.Cin[(size_t)i * a.ldcin + j];
-                            if (i == j) v += a.shift + (a.dadd ? a.dadd[i] : 0.0);
+                            v = fma(a.beta, cur_c[c], v);
+                            if (i == j) v += dii;
                             *cp = v;
                             if (i != j) a.C[(size_t)j * a.ldc + i] = v;
                         } else {
@@ -389,18 +441,24 @@ struct OzWs {
     size_t cap = 0;           // bytes of each of L / R
     int* rexp = nullptr;
     int rexp_cap = 0;
+    double* sw = nullptr;     // signed square roots of the column weights
+    int sw_cap = 0;
     int* err = nullptr;       // device flag word
     int2* tiles = nullptr;
     int tiles_n = 0, tiles_bn = 0, ntiles = 0;
-    // descriptor knobs (overridable by the test hook while the encoding is being pinned down on hardware)
+    // descriptor strides of the pre-tiled K-major / no-swizzle image: 128 B between the two 16-byte K chunks of an MMA
+    // (leading-dimension byte offset), 256 B between 8-row groups (stride byte offset) -- pinned on hardware by
+    // tools/oz_probe.py (the swapped assignment gives garbage)
     int lbo = 128, sbo = 256;
-    int variant = 0;          // 0: BN = 64, one pass;  1: BN = 128, two passes
-    float ms_slice = 0.f, ms_gemm = 0.f;
+    int variant = 1;          // 0: 128x64 tiles, 1 pass;  1: 128x128 tiles, 2 passes;  2: 128x256 tiles, 4 passes
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};   // optional: [0] start, [1] after slicing, [2] end
 };
 inline void oz_free(OzWs& w) {
-    cudaFree(w.L); cudaFree(w.R); cudaFree(w.rexp); cudaFree(w.err); cudaFree(w.tiles);
+    cudaFree(w.L); cudaFree(w.R); cudaFree(w.rexp); cudaFree(w.err); cudaFree(w.tiles); cudaFree(w.sw);
+    for (int i = 0; i < 3; i++) if (w.ev[i]) cudaEventDestroy(w.ev[i]);
     w = OzWs();
 }
+inline int oz_variant_bn(int variant) { return variant == 0 ? 64 : (variant == 2 ? 256 : 128); }
 inline uint64_t oz_desc_hi(int lbo, int sbo) {
     return ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);
 }
@@ -425,39 +483,51 @@ inline int oz_launch(cudaStream_t st, const OzGemmArgs& g, int ntiles) {
 }
 
 // C = beta Cin + diag + sum_t alpha_t A_t diag(w_t) A_t'   (GEMM_UPPER_MIRROR semantics of gemm_nt).
-// `may_be_negative`: bit t set if alpha_t * w_t can be negative (a second, sign-carrying operand is then written).
+// `may_be_negative`: bit t set if alpha_t * w_t can be negative (those k-blocks get a second, sign-carrying operand).
 inline int oz_syrk(cudaStream_t st, const GemmArgs& a, OzWs& w, unsigned may_be_negative) {
     if (a.mode != GEMM_UPPER_MIRROR || a.n != a.m) return fail_msg("oz_syrk: symmetric (upper-mirror) products only");
     if (a.C == a.Cin && w.variant != 0) return fail_msg("oz_syrk: in-place accumulation needs the one-pass variant");
+    if (a.nterms < 1 || a.nterms > 3) return fail_msg("oz_syrk: 1..3 terms");
     OzSliceArgs s{};
+    OzGemmArgs g{};
     int koff = 0;
+    bool anysigned = false;
+    for (int t = 0; t < 3; t++) { g.kb_end[t] = 1 << 30; g.sgn[t] = 0; }
     for (int t = 0; t < a.nterms; t++) {
         if (a.t[t].A != a.t[t].B || a.t[t].lda != a.t[t].ldb) return fail_msg("oz_syrk: terms must be A diag(w) A'");
-        s.t[t] = OzTerm{a.t[t].A, a.t[t].w, a.t[t].lda, a.t[t].K, koff, a.t[t].alpha};
-        koff += (int)rup((size_t)a.t[t].K, 16);
+        const int sg = (may_be_negative >> t) & 1u;
+        s.t[t] = OzTerm{a.t[t].A, a.t[t].w, a.t[t].lda, a.t[t].K, koff, sg, a.t[t].alpha};
+        koff += (int)rup((size_t)a.t[t].K, OZ_KB);
+        g.kb_end[t] = koff / OZ_KB;
+        g.sgn[t] = sg;
+        anysigned = anysigned || sg;
     }
     if (koff > (1 << 17)) return fail_msg("oz_syrk: contraction too long for exact int32 accumulation");
-    const int nkb = cdiv(std::max(koff, 1), OZ_KB);
-    const int nrb = cdiv(a.n, OZ_BM);
+    const int nkb = std::max(koff, OZ_KB) / OZ_KB;
+    const int bn = oz_variant_bn(w.variant);
+    const int nrb = (int)rup((size_t)cdiv(a.n, OZ_BM), (size_t)std::max(1, bn / OZ_BM));   // whole tiles of row blocks
     const size_t need = (size_t)nrb * nkb * OZ_NS * OZ_CHUNK;
-    const bool signedr = may_be_negative != 0;
     if (need > w.cap) {
         cudaFree(w.L); cudaFree(w.R);
         w.L = w.R = nullptr;
         CU(cudaMalloc(&w.L, need));
         w.cap = need;
     }
-    if (signedr && !w.R) CU(cudaMalloc(&w.R, w.cap));
-    if (a.n > w.rexp_cap) {
+    if (anysigned && !w.R) CU(cudaMalloc(&w.R, w.cap));
+    if (nrb * OZ_BM > w.rexp_cap) {
         cudaFree(w.rexp);
         CU(cudaMalloc(&w.rexp, sizeof(int) * nrb * OZ_BM));
         w.rexp_cap = nrb * OZ_BM;
+    }
+    if (nkb * OZ_KB > w.sw_cap) {
+        cudaFree(w.sw);
+        CU(cudaMalloc(&w.sw, sizeof(double) * nkb * OZ_KB));
+        w.sw_cap = nkb * OZ_KB;
     }
     if (!w.err) {
         CU(cudaMalloc(&w.err, sizeof(int)));
         CU(cudaMemsetAsync(w.err, 0, sizeof(int), st));
     }
-    const int bn = (w.variant == 1) ? 128 : 64;
     if (w.tiles_n != a.n || w.tiles_bn != bn) {
         std::vector<int2> tl;
         for (int tj = 0; tj * bn < a.n; tj++)
@@ -468,25 +538,31 @@ inline int oz_syrk(cudaStream_t st, const GemmArgs& a, OzWs& w, unsigned may_be_
         CU(cudaStreamSynchronize(st));
         w.tiles_n = a.n; w.tiles_bn = bn; w.ntiles = (int)tl.size();
     }
-    s.nterms = a.nterms; s.n = a.n; s.nkb = nkb; s.write_r = signedr ? 1 : 0;
-    s.L = w.L; s.R = signedr ? w.R : w.L; s.rexp = w.rexp; s.err = w.err;
+    s.nterms = a.nterms; s.n = a.n; s.nkb = nkb;
+    s.L = w.L; s.R = w.R; s.sw = w.sw; s.rexp = w.rexp; s.err = w.err;
+    if (w.ev[0]) CU(cudaEventRecord(w.ev[0], st));
+    oz_weight_kernel<<<cdiv(nkb * OZ_KB, 256), 256, 0, st>>>(s, w.sw);
+    LAUNCHED();
     oz_slice_kernel<<<nrb * (OZ_BM / 8), 256, 0, st>>>(s);
     LAUNCHED();
-    OzGemmArgs g{};
-    g.L = w.L; g.R = s.R; g.rexp = w.rexp; g.tiles = w.tiles; g.err = w.err;
+    if (w.ev[1]) CU(cudaEventRecord(w.ev[1], st));
+    g.L = w.L; g.R = w.R; g.rexp = w.rexp; g.tiles = w.tiles; g.err = w.err;
     g.C = a.C; g.Cin = a.Cin; g.dadd = a.dadd; g.ldc = a.ldc; g.ldcin = a.ldcin; g.n = a.n; g.nkb = nkb;
     g.beta = a.beta; g.shift = a.shift;
     g.desc_hi = oz_desc_hi(w.lbo, w.sbo);
     g.idesc = oz_idesc(bn);
-    if (w.variant == 1) return oz_launch<128, 2>(st, g, w.ntiles);
-    return oz_launch<64, 1>(st, g, w.ntiles);
+    int rc;
+    if (w.variant == 0) rc = oz_launch<64, 1>(st, g, w.ntiles);
+    else if (w.variant == 2) rc = oz_launch<256, 4>(st, g, w.ntiles);
+    else rc = oz_launch<128, 2>(st, g, w.ntiles);
+    if (rc == 0 && w.ev[2]) CU(cudaEventRecord(w.ev[2], st));
+    return rc;
 }
 
-// what one launch is credited with: int8 multiply-adds actually issued (36 slice pairs)
+// int8 multiply-add operations one call issues on the tensor cores (36 slice pairs over the computed tiles)
 inline double oz_syrk_int8_ops(const GemmArgs& a, int bn) {
     double ksum = 0;
-    for (int t = 0; t < a.nterms; t++) ksum += (double)rup((size_t)a.t[t].K, 16);
-    ksum = (double)cdiv((int)ksum, OZ_KB) * OZ_KB;
+    for (int t = 0; t < a.nterms; t++) ksum += (double)rup((size_t)a.t[t].K, OZ_KB);
     double tiles = 0;
     for (int tj = 0; tj * bn < a.n; tj++)
         for (int ti = 0; ti * OZ_BM < a.n && ti * OZ_BM <= tj * bn + bn - 1; ti++) tiles += 1;

@@ -136,7 +136,7 @@ def test_ldlt_singular_reports_zero_pivot():
     assert zero == 2 and pos == 2 and rcond == 0.0
 
 
-@pytest.mark.parametrize('variant', [0, 1])
+@pytest.mark.parametrize('variant', [0, 1, 2])
 @pytest.mark.parametrize('n,Ks', [(128, [32]), (130, [70, 33]), (300, [70, 203]), (640, [512, 100, 40])])
 def test_syrk_tcgen05_int8_matches_fp64(n, Ks, variant):
     """The tcgen05 path (error-free int8 split, int32 TMEM accumulators, fp64 recombination) must reproduce the fp64

@@ -1,8 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
-L=gpurun_out/oz_probe2.log
+L=gpurun_out/oz_probe3.log
 : > $L
-for cfg in "mid 0" "mid 1" "big 0" "big 1"; do
+for cfg in "mid 2" "big 0" "big 1" "big 2"; do
   timeout 120 python tools/oz_probe.py $cfg >> $L 2>&1 || echo "FAILED($?): $cfg" >> $L
 done
 cat $L
