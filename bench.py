@@ -38,7 +38,7 @@ PRE_STEPS = 3   # real Newton steps taken from x0 before the teacher-forced stat
 # calls, delta0 * 10^8); starting the sample at 2x this value makes every sampled step do the typical mid-solve
 # work of two inertia tests (delta = 0 rejected, delta/2 accepted) instead of the 10-test discovery.
 DELTA_SAMPLE = 1.4901161193847656
-DEFAULT_FLAGS = 0
+DEFAULT_FLAGS = 6     # tcgen05 int8 contractions (128x128 tiles) + speculative / abandoning reghess; 0 = fp64 DMMA contractions
 
 
 def measured_peaks():

@@ -42,6 +42,7 @@ typedef struct b200ipm_params {
     int    flags;                         /* B200IPM_FLAG_* bits */
 } b200ipm_params;
 #define B200IPM_FLAG_NO_SPECULATION 1
+#define B200IPM_FLAG_NO_ABANDON     16  /* always complete a failed inertia test (n_neg_first is then the full count) */
 #define B200IPM_FLAG_TCGEN05_SYRK   2   /* d2L and condensation contractions on tcgen05 (int8 error-free split) */
 #define B200IPM_FLAG_TCGEN05_TILE(v) ((v) << 2)   /* with TCGEN05_SYRK: 0 = 128x64 tiles / 1 pass, 1 = 128x128 / 2, 2 = 128x256 / 4 */
 
@@ -72,7 +73,8 @@ typedef struct b200ipm_step_info {
     int    spec_used;                /* 1 if the speculative attempt was the accepted factorisation */
     int    tc_syrk;                  /* 1 if the two contractions of this step ran on tcgen05 (0: fp64 DMMA, also after
                                         a fallback because of non-finite inputs / unexpected negative weights) */
-    int    reserved;
+    int    abandoned_first;          /* 1 if the delta = 0 inertia test was abandoned on the device as soon as it had
+                                        more than M negative pivots (n_neg_first is then a partial count) */
 } b200ipm_step_info;
 
 int         b200ipm_version(void);

@@ -38,7 +38,7 @@ class StepInfo(C.Structure):
                 ('ms_eval', C.c_float), ('ms_assemble', C.c_float), ('ms_factor', C.c_float), ('ms_solve', C.c_float),
                 ('ms_search', C.c_float), ('ms_total', C.c_float), ('ms_hess_kernel', C.c_float),
                 ('ms_condense_kernel', C.c_float), ('n_spec', C.c_int), ('spec_used', C.c_int),
-                ('tc_syrk', C.c_int), ('reserved', C.c_int)]
+                ('tc_syrk', C.c_int), ('abandoned_first', C.c_int)]
 
     def asdict(self):
         d = {}
@@ -47,6 +47,11 @@ class StepInfo(C.Structure):
             d[name] = list(v) if name == 'kkt_norm' else v
         return d
 
+
+# b200ipm_params.flags used when the caller does not choose: the two dense contractions on tcgen05 (error-free int8
+# split, 128x128 tiles), speculative + abandoning reghess.  0 = fp64 DMMA contractions.
+FLAG_NO_SPECULATION, FLAG_TCGEN05_SYRK, FLAG_NO_ABANDON = 1, 2, 16
+DEFAULT_FLAGS = FLAG_TCGEN05_SYRK | (1 << 2)
 
 # every symbol include/b200ipm.h declares (tests/test_abi.py checks the library exports exactly these)
 SYMBOLS = [
@@ -160,11 +165,11 @@ def torch_stream_handle(device=None):
 
 
 def default_params(mu=0.2, nu=10.0, rho=0.1, tau=0.995, eta=1.0E-4, beta=0.4, Xtol=None, Ktol=1.0E-4, nrefine=2,
-                   ls_batch=32, max_reg_retries=60, flags=0):
+                   ls_batch=32, max_reg_retries=60, flags=None):
     eps = float(np.finfo(np.float64).eps)
     return Params(mu=mu, nu=nu, rho=rho, tau=tau, eta=eta, beta=beta, Xtol=Xtol if Xtol else eps, Ktol=Ktol, eps=eps,
                   reg_coef=float(np.sqrt(eps)), nrefine=nrefine, ls_batch=ls_batch, max_reg_retries=max_reg_retries,
-                  flags=flags)
+                  flags=DEFAULT_FLAGS if flags is None else int(flags))
 
 
 class Engine(object):

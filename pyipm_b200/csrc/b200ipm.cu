@@ -260,11 +260,11 @@ static int build_kc(Eng* h, double delta, double reg) {
 // together -- the second one on its own stream and workspace.  A single LDL^T is a serial chain of tile steps that
 // leaves most SMs idle, so the pair costs little more than one.  Decisions are exactly those of the sequential
 // loop: the speculative result is only consumed if the first test fails with reg = 0.
-static int spec_launch(Eng* h, double delta1) {
+static int spec_launch(Eng* h, double delta1, int neg_limit) {
     if (!h->Fb_ready) {
         CU(cudaStreamCreateWithFlags(&h->stB, cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
-        CU(cudaMallocHost(&h->h_cntB, sizeof(int) * 4));
+        CU(cudaMallocHost(&h->h_cntB, sizeof(int) * 8));
         CU(cudaMallocHost(&h->h_dsB, sizeof(double) * 2));
         RET(ldlt_alloc(h->Fb, h->Kc, h->stB));
         h->Fb.pivot_u = h->F.pivot_u;
@@ -272,40 +272,54 @@ static int spec_launch(Eng* h, double delta1) {
     }
     CU(cudaEventRecord(h->ev_fork, h->st));          // Hb and J are complete on the main stream
     CU(cudaStreamWaitEvent(h->stB, h->ev_fork, 0));
+    RET(ldlt_set_neg_limit(h->Fb, neg_limit));
     RET(build_kc_into(h, h->Fb, h->stB, delta1, 0.0));
     RET(ldlt_factor(h->Fb));
-    CU(cudaMemcpyAsync(h->h_cntB, h->Fb.counts, sizeof(int) * 4, cudaMemcpyDeviceToHost, h->stB));
+    CU(cudaMemcpyAsync(h->h_cntB, h->Fb.counts, sizeof(int) * 8, cudaMemcpyDeviceToHost, h->stB));
     CU(cudaMemcpyAsync(h->h_dsB, h->Fb.dstat, sizeof(double) * 2, cudaMemcpyDeviceToHost, h->stB));
     return 0;
 }
-static int factor_once(Eng* h, double delta, double reg, int* n_neg, int* n_zero, double* rcond) {
+// One inertia test = one factorisation.  `neg_limit`: the test can only pass with exactly M negative pivots, so a
+// factorisation that has already produced more is abandoned on the device (ldlt.cuh control block) -- *abandoned then
+// reports it, and n_neg / rcond describe the part that was factored.
+static int factor_once(Eng* h, double delta, double reg, int neg_limit, int* n_neg, int* n_zero, double* rcond,
+                       int* abandoned) {
+    RET(ldlt_set_neg_limit(h->F, neg_limit));
     RET(build_kc(h, delta, reg));
     RET(ldlt_factor(h->F));
-    int cnt[4];
+    int cnt[8];
     double ds[2];
-    CU(cudaMemcpyAsync(cnt, h->F.counts, sizeof(int) * 4, cudaMemcpyDeviceToHost, h->st));
+    CU(cudaMemcpyAsync(cnt, h->F.counts, sizeof(int) * 8, cudaMemcpyDeviceToHost, h->st));
     CU(cudaMemcpyAsync(ds, h->F.dstat, sizeof(double) * 2, cudaMemcpyDeviceToHost, h->st));
     CU(cudaStreamSynchronize(h->st));
     *n_neg = cnt[0];
     *n_zero = cnt[1];
     *rcond = (cnt[1] > 0 || !(ds[1] > 0.0)) ? 0.0 : ds[0] / ds[1];
+    if (abandoned) *abandoned = cnt[4];
     return 0;
 }
 // reghess (pyipm.py:1373-1406) on the condensed matrix: full-K inertia (D+N, M+N, 0)  <=>  condensed has
 // exactly M negative pivots (Haynsworth).
-static int factor_regularised(Eng* h, b200ipm_step_info* info) {
+// Abandoning a failed test early hides the pivots that were never computed, and with them the rcond <= eps test of
+// pyipm.py:1381 that decides the eq-block regularisation.  The usual case (rcond far above eps) is unaffected; if any
+// LATER, completed attempt of the same step does look singular the whole sequence is redone without abandoning, so
+// the decisions are always those of the reference's loop.
+static int factor_regularised(Eng* h, b200ipm_step_info* info, bool allow_abandon = true) {
     const int M = h->M;
-    int n_neg = 0, n_zero = 0, nfac = 0;
+    const int limit = (allow_abandon && !(h->p.flags & B200IPM_FLAG_NO_ABANDON)) ? M : 0x7fffffff;
+    const double delta_in = h->delta;
+    int n_neg = 0, n_zero = 0, nfac = 0, ab_first = 0, ab = 0;
     double rcond = 0.0;
     const double delta1 = (h->delta == 0.0) ? h->p.reg_coef : std::max(h->delta / 2.0, h->p.reg_coef);
     const bool spec = (h->delta > 0.0) && !(h->p.flags & B200IPM_FLAG_NO_SPECULATION) && !h->strict_retry;
     bool spec_used = false;
-    if (spec) RET(spec_launch(h, delta1));
-    RET(factor_once(h, 0.0, 0.0, &n_neg, &n_zero, &rcond));
+    if (spec) RET(spec_launch(h, delta1, limit));
+    RET(factor_once(h, 0.0, 0.0, limit, &n_neg, &n_zero, &rcond, &ab_first));
     nfac++;
     const double rcond0 = rcond;
     if (info) { info->n_neg_first = n_neg; info->n_zero_first = n_zero; }
     int eq_reg = 0;
+    bool redo = false;
     if (rcond <= h->p.eps || n_neg != M) {
         double reg = 0.0;
         if (rcond <= h->p.eps && M) {
@@ -321,26 +335,37 @@ static int factor_regularised(Eng* h, b200ipm_step_info* info) {
             h->Fb.st = h->stB;
             n_neg = h->h_cntB[0];
             n_zero = h->h_cntB[1];
+            ab = h->h_cntB[4];
             rcond = (n_zero > 0 || !(h->h_dsB[1] > 0.0)) ? 0.0 : h->h_dsB[0] / h->h_dsB[1];
             h->delta_eff = delta1;
             h->reg_cur = 0.0;
             spec_used = true;
         } else {
-            RET(factor_once(h, h->delta, reg, &n_neg, &n_zero, &rcond));
+            RET(factor_once(h, h->delta, reg, limit, &n_neg, &n_zero, &rcond, &ab));
         }
         nfac++;
+        if (ab_first && !ab && rcond <= h->p.eps) redo = true;
         int guard = 0;
-        while (n_neg != M) {
-            if (++guard > h->p.max_reg_retries) return fail_msg("reghess: inertia correction did not converge");
+        while (n_neg != M && !redo) {
+            if (++guard > h->p.max_reg_retries) {
+                if (ab_first) { redo = true; break; }
+                return fail_msg("reghess: inertia correction did not converge");
+            }
             h->delta *= 10.0;
-            RET(factor_once(h, h->delta, reg, &n_neg, &n_zero, &rcond));
+            RET(factor_once(h, h->delta, reg, limit, &n_neg, &n_zero, &rcond, &ab));
             nfac++;
+            if (ab_first && !ab && rcond <= h->p.eps) redo = true;
         }
     }
     if (spec && !spec_used) CU(cudaStreamSynchronize(h->stB));   // the unused attempt must not outlive this step
+    if (redo) {
+        h->delta = delta_in;
+        return factor_regularised(h, info, false);
+    }
     if (info) {
         info->n_neg = n_neg; info->n_zero = n_zero; info->n_factor = nfac; info->rcond = rcond0; info->eq_reg = eq_reg;
         info->delta = h->delta; info->n_spec = spec ? 1 : 0; info->spec_used = spec_used ? 1 : 0;
+        info->abandoned_first = ab_first;
     }
     return 0;
 }
@@ -1349,7 +1374,7 @@ int b200ipm_ldlt_panel(b200ipm_ldlt_handle h, double* panel_dev, int ld, int row
     CU(cudaSetDevice(h->device));
     const int* kind = reinterpret_cast<const int*>(dblk_dev + 4 * NB);
     ldlt_panel_kernel<<<cdiv(rows, NB), 128, PANEL_SMEM, h->st>>>(panel_dev, ld, rows, linv_dev, dblk_dev, dblk_dev + NB,
-                                                                   kind, w_dev, ldw);
+                                                                   kind, w_dev, ldw, nullptr);
     LAUNCHED();
     return 0;
 }

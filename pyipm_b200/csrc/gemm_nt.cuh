@@ -45,6 +45,7 @@ struct GemmArgs {
     // (bc_p, bc_q), local block offsets bc_li0 / bc_lj0 of C's origin): a tile is computed iff its global block row >=
     // its global block column (tiles never straddle blocks: bc_b is a multiple of the tile size).
     int bc_b, bc_P, bc_Q, bc_p, bc_q, bc_li0, bc_lj0;
+    const int* ctrl;      // optional LDL^T control block: ctrl[4] != 0 => the factorisation was abandoned, do nothing
 };
 
 constexpr int G_BM = 128, G_BN = 128, G_BK = 32, G_LDS = 36, G_STAGES = 3;
@@ -105,6 +106,12 @@ constexpr int G_MT = G_BM / (8 * G_NWM), G_NT = G_BN / (8 * G_NWN);
 __global__ void __launch_bounds__(G_THREADS, 1) gemm_nt_dmma_kernel(const GemmArgs a) {
     extern __shared__ __align__(16) double g_smem[];
     const int ti = blockIdx.y, tj = blockIdx.x;
+    if (a.ctrl) {   // one read per CTA: the flag can be raised while this kernel runs (look-ahead streams)
+        __shared__ int s_abort;
+        if (threadIdx.x == 0) s_abort = *reinterpret_cast<const volatile int*>(a.ctrl + 4);
+        __syncthreads();
+        if (s_abort) return;
+    }
     if (a.mode == GEMM_UPPER_MIRROR && ti > tj) return;
     if (a.mode == GEMM_LOWER_ONLY && ti < tj) return;
     if (a.mode == GEMM_BC_LOWER) {
@@ -319,8 +326,15 @@ __device__ __forceinline__ void s_load_tile(double* sdst, const double* __restri
 
 __global__ void __launch_bounds__(128, 2) gemm_nt_sub64_kernel(double* __restrict__ C, int ldc, int rows, int cols,
                                                                const double* __restrict__ A, int lda,
-                                                               const double* __restrict__ B, int ldb, int K) {
+                                                               const double* __restrict__ B, int ldb, int K,
+                                                               const int* __restrict__ ctrl) {
     extern __shared__ __align__(16) double s_smem[];
+    if (ctrl) {
+        __shared__ int s_abort;
+        if (threadIdx.x == 0) s_abort = *reinterpret_cast<const volatile int*>(ctrl + 4);
+        __syncthreads();
+        if (s_abort) return;
+    }
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, tg = lane & 3;
     const int row0 = blockIdx.y * S_BM, col0 = blockIdx.x * S_BN;
@@ -398,18 +412,19 @@ __global__ void __launch_bounds__(128, 2) gemm_nt_sub64_kernel(double* __restric
 
 // C (rows x cols, in place) -= A (rows x K) * B (cols x K)^T
 inline int gemm_nt_sub(cudaStream_t st, double* C, int ldc, int rows, int cols, const double* A, int lda, const double* B,
-                       int ldb, int K) {
+                       int ldb, int K, const int* ctrl = nullptr) {
     if (rows <= 0 || cols <= 0) return 0;
     const bool ok = !(lda & 1) && !(ldb & 1) && !(reinterpret_cast<uintptr_t>(A) & 15) && !(reinterpret_cast<uintptr_t>(B) & 15);
     if (ok && rows >= 48) {
         dim3 grid(cdiv(cols, S_BN), cdiv(rows, S_BM));
-        gemm_nt_sub64_kernel<<<grid, 128, S_SMEM, st>>>(C, ldc, rows, cols, A, lda, B, ldb, K);
+        gemm_nt_sub64_kernel<<<grid, 128, S_SMEM, st>>>(C, ldc, rows, cols, A, lda, B, ldb, K, ctrl);
         LAUNCHED();
         return 0;
     }
     GemmArgs u{};
     u.C = C; u.ldc = ldc; u.Cin = C; u.ldcin = ldc; u.n = rows; u.m = cols; u.beta = 1.0; u.mode = GEMM_FULL; u.nterms = 1;
     u.t[0] = GemmTerm{A, B, nullptr, lda, ldb, K, -1.0};
+    u.ctrl = ctrl;
     return gemm_nt(st, u);
 }
 

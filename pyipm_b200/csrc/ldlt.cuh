@@ -35,7 +35,7 @@ struct LdltWs {
     double* LinvP = nullptr;   // nblk x NB x NB
     double* dinfo = nullptr;   // 4 x n: [dinv_a | dinv_b | d_a | d_b]
     int* kind = nullptr;       // n: 0 = 1x1, 1 = first of 2x2, 2 = second of 2x2
-    int* counts = nullptr;     // [neg, zero, pos]
+    int* counts = nullptr;     // [neg, zero, pos, -, abandoned flag, negative-pivot limit, -, -]  (control block)
     double* dstat = nullptr;   // [min |eig(D)|, max |eig(D)|]
     unsigned* flags = nullptr; // 2 x nblk epoch flags (forward, backward)
     unsigned* ticket = nullptr;
@@ -50,6 +50,7 @@ struct LdltWs {
     double graph_u = -1.0;         // pivot_u the captured graph was built with
     int graph_nodes = 0;
     int graph_state = 0;           // 0 = not tried, 1 = usable, -1 = capture failed: direct launches
+    int neg_limit = 0x7fffffff; // value last written to counts[5]
     double pivot_u = 0.01;     // threshold of the fast (unpivoted) tile attempt: accept step j iff |d_j| >= u * max_i |T[i][j]|
 };
 
@@ -77,7 +78,11 @@ inline int ldlt_alloc(LdltWs& w, int n, cudaStream_t st) {
     CU(cudaMalloc(&w.LinvP, sizeof(double) * (size_t)w.nblk * NB * NB));
     CU(cudaMalloc(&w.dinfo, sizeof(double) * 4 * npad));
     CU(cudaMalloc(&w.kind, sizeof(int) * npad));
-    CU(cudaMalloc(&w.counts, sizeof(int) * 4));
+    CU(cudaMalloc(&w.counts, sizeof(int) * 8));
+    {
+        const int init[8] = {0, 0, 0, 0, 0, 0x7fffffff, 0, 0};
+        CU(cudaMemcpy(w.counts, init, sizeof(init), cudaMemcpyHostToDevice));
+    }
     CU(cudaMalloc(&w.dstat, sizeof(double) * 2));
     CU(cudaMalloc(&w.flags, sizeof(unsigned) * 2 * w.nblk));
     CU(cudaMalloc(&w.ticket, sizeof(unsigned) * 2));
@@ -255,6 +260,12 @@ __global__ void __launch_bounds__(TILE_THREADS) ldlt_tile_kernel(double* __restr
     __shared__ int s_kp2, s_kstep2;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double BK_ALPHA = 0.6403882032022076;
+    // an inertia test that has already failed (more negative pivots than the limit in counts[5]) abandons the rest
+    // of the factorisation: every remaining kernel of the captured graph returns at once
+    if (tid == 0) s_kp2 = counts[4];
+    __syncthreads();
+    if (s_kp2) return;
+    __syncthreads();
 #ifdef TILE_PROF
     long long tp0 = clock64(), tp1 = 0, tp2 = 0, tp3 = 0;
     int nslow = 0;
@@ -628,7 +639,9 @@ __global__ void __launch_bounds__(TILE_THREADS) ldlt_tile_kernel(double* __restr
         mn = warp_min(mn);
         mx = warp_max(mx);
         if (lane == 0) {
-            counts[0] += neg; counts[1] += zero; counts[2] += pos;
+            const int negs = counts[0] + neg;
+            counts[0] = negs; counts[1] += zero; counts[2] += pos;
+            if (negs > counts[5]) counts[4] = 1;
             dstat[0] = fmin(dstat[0], mn); dstat[1] = fmax(dstat[1], mx);
         }
     }
@@ -649,8 +662,15 @@ __global__ void __launch_bounds__(128) ldlt_panel_kernel(double* __restrict__ B,
                                                          const double* __restrict__ LinvP,
                                                          const double* __restrict__ dinv_a,
                                                          const double* __restrict__ dinv_b, const int* __restrict__ kind,
-                                                         double* __restrict__ Wout, int ldw) {
+                                                         double* __restrict__ Wout, int ldw,
+                                                         const int* __restrict__ ctrl) {
     extern __shared__ __align__(16) double psm[];
+    if (ctrl) {
+        __shared__ int s_abort;
+        if (threadIdx.x == 0) s_abort = *reinterpret_cast<const volatile int*>(ctrl + 4);
+        __syncthreads();
+        if (s_abort) return;
+    }
     double* As = psm;
     double* Bs = psm + NB * P_LDS;
     __shared__ double sia[NB], sib[NB];
@@ -715,10 +735,21 @@ __global__ void __launch_bounds__(128) ldlt_panel_kernel(double* __restrict__ B,
 }
 
 __global__ void ldlt_reset_kernel(int* counts, double* dstat, unsigned* ticket) {
-    counts[0] = counts[1] = counts[2] = counts[3] = 0;
+    counts[0] = counts[1] = counts[2] = counts[3] = counts[4] = 0;
     dstat[0] = INFINITY;
     dstat[1] = 0.0;
     ticket[0] = ticket[1] = 0;
+}
+
+// negative-pivot limit of the NEXT factorisation(s) of this workspace (0x7fffffff = never abandon); a plain stream-ordered
+// store outside the captured graph
+__global__ void ldlt_limit_kernel(int* counts, int limit) { counts[5] = limit; }
+inline int ldlt_set_neg_limit(LdltWs& w, int limit) {
+    if (w.neg_limit == limit) return 0;
+    ldlt_limit_kernel<<<1, 1, 0, w.st>>>(w.counts, limit);
+    LAUNCHED();
+    w.neg_limit = limit;
+    return 0;
 }
 
 inline int ldlt_init_attrs() {
@@ -760,10 +791,10 @@ inline int ldlt_factor_launch(LdltWs& w, cudaStream_t st) {
             if (rows <= 0) break;
             double* B = w.A + (size_t)k1 * ld + k0;                      // rows below the tile
             double* Wt = Wb + (size_t)k1 * NBO + (k0 - c0);             // W = L * D for this tile step
-            ldlt_panel_kernel<<<cdiv(rows, NB), 128, PANEL_SMEM, st>>>(B, ld, rows, Lk, ia + k0, ib + k0, w.kind + k0, Wt, NBO);
+            ldlt_panel_kernel<<<cdiv(rows, NB), 128, PANEL_SMEM, st>>>(B, ld, rows, Lk, ia + k0, ib + k0, w.kind + k0, Wt, NBO, w.counts);
             LAUNCHED();
             const int mcols = c1 - k1;                                   // remaining columns of this outer panel
-            if (mcols > 0) RET(gemm_nt_sub(st, w.A + (size_t)k1 * ld + k1, ld, rows, mcols, Wt, NBO, B, ld, NB));
+            if (mcols > 0) RET(gemm_nt_sub(st, w.A + (size_t)k1 * ld + k1, ld, rows, mcols, Wt, NBO, B, ld, NB, w.counts));
         }
         const int rows2 = n - c1;
         if (rows2 <= 0) break;
@@ -775,7 +806,7 @@ inline int ldlt_factor_launch(LdltWs& w, cudaStream_t st) {
         // PREVIOUS panel read-modify-wrote the same columns, so it has to be complete first (this wait also protects
         // the W buffer panel p+1 is about to overwrite: it was read by that same side-stream update).
         if (p >= 1 && side_used) CU(cudaStreamWaitEvent(st, w.ev_upd[(p - 1) & 1], 0));
-        RET(gemm_nt_sub(st, w.A + (size_t)c1 * ld + c1, ld, rows2, na, Wpan, NBO, Lpan, ld, kw));
+        RET(gemm_nt_sub(st, w.A + (size_t)c1 * ld + c1, ld, rows2, na, Wpan, NBO, Lpan, ld, kw, w.counts));
         // (b) everything to the right of the next panel, side stream (lower tiles only), overlapped with panel p+1
         const int rows3 = rows2 - na;
         if (rows3 > 0) {
@@ -783,7 +814,7 @@ inline int ldlt_factor_launch(LdltWs& w, cudaStream_t st) {
             CU(cudaStreamWaitEvent(sd, w.ev_panel[p & 1], 0));
             GemmArgs u{};
             u.C = w.A + (size_t)(c1 + na) * ld + (c1 + na); u.ldc = ld; u.Cin = u.C; u.ldcin = ld; u.n = rows3; u.m = rows3;
-            u.beta = 1.0; u.mode = GEMM_LOWER_ONLY; u.nterms = 1;
+            u.beta = 1.0; u.mode = GEMM_LOWER_ONLY; u.nterms = 1; u.ctrl = w.counts;
             u.t[0] = GemmTerm{Wpan + (size_t)na * NBO, Lpan + (size_t)na * ld, nullptr, NBO, ld, kw, -1.0};
             RET(gemm_nt(sd, u));
             CU(cudaEventRecord(w.ev_upd[p & 1], sd));

@@ -271,7 +271,7 @@ def test_speculative_reghess_matches_sequential():
     the decisions -- and produce bitwise the direction -- of the sequential loop (flags = NO_SPECULATION)."""
     prob = problems.make_nlp(D=320, M=48, N=320, seed=5)
     o, tr = oracle_trace(prob, prob.x0, niter=1, miter=4)
-    eng_s = make_engine(prob)
+    eng_s = make_engine(prob, flags=0)
     eng_q = make_engine(prob, flags=1)
     nu_b, de_b = 10.0, 0.0
     n_spec = 0
@@ -339,3 +339,32 @@ def test_tcgen05_syrk_falls_back_on_negative_multipliers():
     (dz0, i0), (dz1, i1) = out
     assert i1.tc_syrk == 0 and i0.tc_syrk == 0
     assert np.array_equal(dz0, dz1) and i0.delta == i1.delta and i0.n_factor == i1.n_factor
+
+
+def test_abandoned_inertia_tests_do_not_change_decisions():
+    """A failed inertia test is abandoned on the device as soon as it has more than M negative pivots.  Decisions,
+    delta, the number of tests and the direction must be bitwise those of the engine that completes every test
+    (B200IPM_FLAG_NO_ABANDON = 16), with and without speculation."""
+    prob = problems.make_nlp(D=320, M=16, N=320, seed=9)
+    o, tr = oracle_trace(prob, prob.x0, niter=1, miter=3)
+    engs = [make_engine(prob, flags=f) for f in (0, 16, 1, 17)]
+    nu_b, de_b = 10.0, 0.0
+    n_ab = 0
+    for k, st in enumerate(tr):
+        out = []
+        for eng in engs:
+            eng.set_state(st['x'], st['s'], st['lda'], st['mu'], nu_b, de_b)
+            eng.set_mu_host(st['mu_host'])
+            out.append(eng.direction())
+        dz0, i0 = out[0]
+        n_ab += i0.abandoned_first
+        assert out[1][1].abandoned_first == 0 and out[3][1].abandoned_first == 0
+        for dz, i in out[1:]:
+            assert (i.delta, i.n_factor, i.n_neg, i.n_zero, i.eq_reg) == (i0.delta, i0.n_factor, i0.n_neg, i0.n_zero, i0.eq_reg)
+            assert np.array_equal(dz, dz0)
+        assert i0.delta == st['delta'] and i0.n_factor == st['reg']['n_eig']
+        assert relinf(dz0, st['dz']) < DZ_RTOL
+        nu_b, de_b = st['nu_after'], st['delta']
+    assert n_ab >= 1
+    for eng in engs:
+        eng.close()
