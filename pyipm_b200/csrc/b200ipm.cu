@@ -55,7 +55,9 @@ struct b200ipm_engine {
     bool Fb_ready = false;
     cudaStream_t stB = nullptr;
     cudaEvent_t ev_fork = nullptr;
-    int *h_cntB = nullptr;   // pinned: counts (4 ints) of the speculative attempt
+    bool pendingA = false;   // the background delta = 0 test has not been collected yet
+    double pend_delta_in = 0, pend_rcondB = 0;
+    int *h_cntB = nullptr;   // pinned: control block (8 ints) of the background attempt
     double *h_dsB = nullptr; // pinned: dstat (2 doubles) of the speculative attempt
     LdltWs F2;              // pseudo-inverse / second-order-correction systems (lazy)
     bool F2_ready = false;
@@ -255,25 +257,28 @@ static int build_kc(Eng* h, double delta, double reg) {
     h->reg_cur = reg;
     return 0;
 }
-// Speculation (reghess, pyipm.py:1373-1406): once a shift was needed, the delta = 0 test almost always fails
-// again and the next candidate max(delta/2, delta0) is known in advance, so both factorisations are started
-// together -- the second one on its own stream and workspace.  A single LDL^T is a serial chain of tile steps that
-// leaves most SMs idle, so the pair costs little more than one.  Decisions are exactly those of the sequential
-// loop: the speculative result is only consumed if the first test fails with reg = 0.
-static int spec_launch(Eng* h, double delta1, int neg_limit) {
+// Speculation (reghess, pyipm.py:1373-1406): once a shift was needed, the delta = 0 test almost always fails again
+// and the next candidate max(delta/2, delta0) is known in advance.  The delta = 0 test ("A") is therefore started in
+// the BACKGROUND -- own workspace, low-priority streams -- while the candidate ("B") is factored in the foreground
+// and the solve proceeds with it; A's verdict is collected afterwards (resolve_pending).  In the rare cases where A
+// passes, or asks for the eq-block regularisation (rcond <= eps), the step is redone with the sequential loop, so
+// the decisions are always exactly the reference's.
+static int spec_launch_background(Eng* h, int neg_limit) {
     if (!h->Fb_ready) {
-        CU(cudaStreamCreateWithFlags(&h->stB, cudaStreamNonBlocking));
+        int prio_lo = 0, prio_hi = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        CU(cudaStreamCreateWithPriority(&h->stB, cudaStreamNonBlocking, prio_lo));
         CU(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
         CU(cudaMallocHost(&h->h_cntB, sizeof(int) * 8));
         CU(cudaMallocHost(&h->h_dsB, sizeof(double) * 2));
-        RET(ldlt_alloc(h->Fb, h->Kc, h->stB));
+        RET(ldlt_alloc(h->Fb, h->Kc, h->stB, /*background=*/true));
         h->Fb.pivot_u = h->F.pivot_u;
         h->Fb_ready = true;
     }
     CU(cudaEventRecord(h->ev_fork, h->st));          // Hb and J are complete on the main stream
     CU(cudaStreamWaitEvent(h->stB, h->ev_fork, 0));
     RET(ldlt_set_neg_limit(h->Fb, neg_limit));
-    RET(build_kc_into(h, h->Fb, h->stB, delta1, 0.0));
+    RET(build_kc_into(h, h->Fb, h->stB, 0.0, 0.0));
     RET(ldlt_factor(h->Fb));
     CU(cudaMemcpyAsync(h->h_cntB, h->Fb.counts, sizeof(int) * 8, cudaMemcpyDeviceToHost, h->stB));
     CU(cudaMemcpyAsync(h->h_dsB, h->Fb.dstat, sizeof(double) * 2, cudaMemcpyDeviceToHost, h->stB));
@@ -298,52 +303,82 @@ static int factor_once(Eng* h, double delta, double reg, int neg_limit, int* n_n
     if (abandoned) *abandoned = cnt[4];
     return 0;
 }
+// verdict of the background delta = 0 test (call after stB has been synchronised)
+static void background_verdict(Eng* h, int* n_neg, int* n_zero, double* rcond, int* abandoned) {
+    *n_neg = h->h_cntB[0];
+    *n_zero = h->h_cntB[1];
+    *abandoned = h->h_cntB[4];
+    *rcond = (*n_zero > 0 || !(h->h_dsB[1] > 0.0)) ? 0.0 : h->h_dsB[0] / h->h_dsB[1];
+}
 // reghess (pyipm.py:1373-1406) on the condensed matrix: full-K inertia (D+N, M+N, 0)  <=>  condensed has
 // exactly M negative pivots (Haynsworth).
 // Abandoning a failed test early hides the pivots that were never computed, and with them the rcond <= eps test of
 // pyipm.py:1381 that decides the eq-block regularisation.  The usual case (rcond far above eps) is unaffected; if any
 // LATER, completed attempt of the same step does look singular the whole sequence is redone without abandoning, so
 // the decisions are always those of the reference's loop.
-static int factor_regularised(Eng* h, b200ipm_step_info* info, bool allow_abandon = true) {
+static int factor_regularised(Eng* h, b200ipm_step_info* info, bool allow_abandon = true, bool allow_spec = true) {
     const int M = h->M;
     const int limit = (allow_abandon && !(h->p.flags & B200IPM_FLAG_NO_ABANDON)) ? M : 0x7fffffff;
     const double delta_in = h->delta;
     int n_neg = 0, n_zero = 0, nfac = 0, ab_first = 0, ab = 0;
-    double rcond = 0.0;
+    double rcond = 0.0, rcond0 = 0.0;
     const double delta1 = (h->delta == 0.0) ? h->p.reg_coef : std::max(h->delta / 2.0, h->p.reg_coef);
-    const bool spec = (h->delta > 0.0) && !(h->p.flags & B200IPM_FLAG_NO_SPECULATION) && !h->strict_retry;
-    bool spec_used = false;
-    if (spec) RET(spec_launch(h, delta1, limit));
-    RET(factor_once(h, 0.0, 0.0, limit, &n_neg, &n_zero, &rcond, &ab_first));
-    nfac++;
-    const double rcond0 = rcond;
-    if (info) { info->n_neg_first = n_neg; info->n_zero_first = n_zero; }
+    const bool spec = allow_spec && (h->delta > 0.0) && !(h->p.flags & B200IPM_FLAG_NO_SPECULATION) && !h->strict_retry;
     int eq_reg = 0;
-    bool redo = false;
-    if (rcond <= h->p.eps || n_neg != M) {
-        double reg = 0.0;
-        if (rcond <= h->p.eps && M) {
+    bool redo = false, first_failed = false;
+    double reg = 0.0;
+    h->pendingA = false;
+    if (spec) {
+        RET(spec_launch_background(h, limit));                                   // A: delta = 0, background
+        RET(factor_once(h, delta1, 0.0, limit, &n_neg, &n_zero, &rcond, &ab));  // B: the expected candidate
+        nfac = 2;
+        if (n_neg == M) {
+            // proceed with B; A's verdict is collected by resolve_pending() after the solve
+            h->delta = delta1;
+            h->pendingA = true;
+            h->pend_delta_in = delta_in;
+            h->pend_rcondB = rcond;
+            if (info) {
+                info->n_neg = n_neg; info->n_zero = n_zero; info->n_factor = nfac; info->eq_reg = 0; info->delta = h->delta;
+                info->n_spec = 1; info->spec_used = 1;
+            }
+            return 0;
+        }
+        // B failed too: A's verdict is needed now to continue the reference's sequence
+        int nA = 0, zA = 0;
+        CU(cudaStreamSynchronize(h->stB));
+        background_verdict(h, &nA, &zA, &rcond0, &ab_first);
+        if (info) { info->n_neg_first = nA; info->n_zero_first = zA; }
+        if (!(rcond0 <= h->p.eps || nA != M)) {
+            // the unshifted matrix passes although the shifted one did not (only possible through rounding or a
+            // rank-deficient Jacobian): take the plain sequential loop from the incoming delta
+            h->delta = delta_in;
+            return factor_regularised(h, info, allow_abandon, false);
+        }
+        first_failed = true;
+        if (rcond0 <= h->p.eps && M) {
             reg = h->p.reg_coef * h->p.eta * pow(h->mu_host, h->p.beta);
             eq_reg = 1;
         }
         h->delta = delta1;
-        if (spec && reg == 0.0) {
-            // adopt the speculative factorisation: it is exactly what factor_once(delta1, 0) would produce
-            CU(cudaStreamSynchronize(h->stB));
-            std::swap(h->F, h->Fb);
-            h->F.st = h->st;
-            h->Fb.st = h->stB;
-            n_neg = h->h_cntB[0];
-            n_zero = h->h_cntB[1];
-            ab = h->h_cntB[4];
-            rcond = (n_zero > 0 || !(h->h_dsB[1] > 0.0)) ? 0.0 : h->h_dsB[0] / h->h_dsB[1];
-            h->delta_eff = delta1;
-            h->reg_cur = 0.0;
-            spec_used = true;
-        } else {
+        if (reg != 0.0) RET(factor_once(h, h->delta, reg, limit, &n_neg, &n_zero, &rcond, &ab));   // B had assumed reg = 0
+    } else {
+        RET(factor_once(h, 0.0, 0.0, limit, &n_neg, &n_zero, &rcond, &ab_first));
+        nfac = 1;
+        rcond0 = rcond;
+        if (info) { info->n_neg_first = n_neg; info->n_zero_first = n_zero; }
+        if (rcond <= h->p.eps || n_neg != M) {
+            first_failed = true;
+            if (rcond <= h->p.eps && M) {
+                reg = h->p.reg_coef * h->p.eta * pow(h->mu_host, h->p.beta);
+                eq_reg = 1;
+            }
+            h->delta = delta1;
             RET(factor_once(h, h->delta, reg, limit, &n_neg, &n_zero, &rcond, &ab));
+            nfac++;
         }
-        nfac++;
+    }
+    if (first_failed) {
         if (ab_first && !ab && rcond <= h->p.eps) redo = true;
         int guard = 0;
         while (n_neg != M && !redo) {
@@ -357,16 +392,35 @@ static int factor_regularised(Eng* h, b200ipm_step_info* info, bool allow_abando
             if (ab_first && !ab && rcond <= h->p.eps) redo = true;
         }
     }
-    if (spec && !spec_used) CU(cudaStreamSynchronize(h->stB));   // the unused attempt must not outlive this step
     if (redo) {
         h->delta = delta_in;
-        return factor_regularised(h, info, false);
+        return factor_regularised(h, info, false, false);
     }
     if (info) {
         info->n_neg = n_neg; info->n_zero = n_zero; info->n_factor = nfac; info->rcond = rcond0; info->eq_reg = eq_reg;
-        info->delta = h->delta; info->n_spec = spec ? 1 : 0; info->spec_used = spec_used ? 1 : 0;
+        info->delta = h->delta; info->n_spec = spec ? 1 : 0; info->spec_used = 0;
         info->abandoned_first = ab_first;
     }
+    return 0;
+}
+// Collect the verdict of the background delta = 0 test.  *redo = true: the tentative choice of B was not what the
+// reference's loop would have done (A passes, A asks for the eq-block regularisation, or A was abandoned while B
+// looks singular) -- the caller restarts the step's factorisation sequentially from the incoming delta.
+static int resolve_pending(Eng* h, b200ipm_step_info* info, bool* redo) {
+    *redo = false;
+    if (!h->pendingA) return 0;
+    h->pendingA = false;
+    CU(cudaStreamSynchronize(h->stB));
+    int nA = 0, zA = 0, abA = 0;
+    double rcA = 0.0;
+    background_verdict(h, &nA, &zA, &rcA, &abA);
+    if (info) { info->n_neg_first = nA; info->n_zero_first = zA; info->rcond = rcA; info->abandoned_first = abA; }
+    const bool a_fails = (rcA <= h->p.eps || nA != h->M);
+    const bool a_eqreg = (rcA <= h->p.eps && h->M);
+    const bool hidden_singular = abA && (h->pend_rcondB <= h->p.eps);
+    if (a_fails && !a_eqreg && !hidden_singular) return 0;
+    h->delta = h->pend_delta_in;
+    *redo = true;
     return 0;
 }
 
@@ -742,6 +796,14 @@ static int compute_direction(Eng* h, b200ipm_step_info* info) {
     if (info) info->tc_syrk = h->oz_used ? 1 : 0;
     CU(cudaEventRecord(h->ev[EV_FACTOR], h->st));
     RET(solve_direction(h, info));
+    {
+        bool redo = false;
+        RET(resolve_pending(h, info, &redo));
+        if (redo) {
+            RET(factor_regularised(h, info, /*allow_abandon=*/false, /*allow_spec=*/false));   // every pivot of every test is seen
+            RET(solve_direction(h, info));
+        }
+    }
     CU(cudaEventRecord(h->ev[EV_SOLVE], h->st));
     return 0;
 }

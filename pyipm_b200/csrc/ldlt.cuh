@@ -18,6 +18,7 @@
 // Solves are ONE launch per direction: CTA i owns block-row i, spins on per-block epoch flags published by the
 // CTAs of earlier block rows (tickets guarantee forward progress), and applies LinvP_i as a 64 x 64 GEMV.
 #pragma once
+#include <algorithm>
 #include "common.cuh"
 #include "gemm_nt.cuh"
 #include "vec.cuh"
@@ -54,7 +55,7 @@ struct LdltWs {
     double pivot_u = 0.01;     // threshold of the fast (unpivoted) tile attempt: accept step j iff |d_j| >= u * max_i |T[i][j]|
 };
 
-inline int ldlt_alloc(LdltWs& w, int n, cudaStream_t st) {
+inline int ldlt_alloc(LdltWs& w, int n, cudaStream_t st, bool background = false) {
     w.n = n;
     w.ld = (int)rup(n, 16);
     w.nblk = cdiv(n, NB);
@@ -69,8 +70,13 @@ inline int ldlt_alloc(LdltWs& w, int n, cudaStream_t st) {
     // kernel nodes inherit the priority of the stream they were captured on)
     int prio_lo = 0, prio_hi = 0;
     CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-    CU(cudaStreamCreateWithPriority(&w.side, cudaStreamNonBlocking, prio_lo));
-    CU(cudaStreamCreateWithPriority(&w.cap, cudaStreamNonBlocking, prio_hi));
+    // (numerically smaller = more urgent).  A BACKGROUND workspace (the speculative delta = 0 inertia test whose
+    // verdict is only needed later) sits entirely below a foreground one.
+    const int span = prio_lo - prio_hi;
+    const int p_chain = background ? prio_hi + std::min(span, 2) : prio_hi;
+    const int p_side = background ? prio_lo : prio_hi + std::min(span, 1);
+    CU(cudaStreamCreateWithPriority(&w.side, cudaStreamNonBlocking, p_side));
+    CU(cudaStreamCreateWithPriority(&w.cap, cudaStreamNonBlocking, p_chain));
     for (int i = 0; i < 2; i++) {
         CU(cudaEventCreateWithFlags(&w.ev_panel[i], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&w.ev_upd[i], cudaEventDisableTiming));

@@ -368,3 +368,30 @@ def test_abandoned_inertia_tests_do_not_change_decisions():
     assert n_ab >= 1
     for eng in engs:
         eng.close()
+
+
+def test_background_inertia_test_that_passes_is_honoured():
+    """Speculative reghess assumes the delta = 0 test fails and proceeds with delta/2.  On a CONVEX problem entered with
+    a left-over delta > 0 the delta = 0 test passes (pyipm.py:1381): the engine must notice when it collects the
+    background verdict and return what the reference's loop returns -- one test, delta unchanged, no shift applied."""
+    prob = problems.make_qp(D=320, M=64, nbox=100, seed=2)
+    s0 = np.maximum(prob.ci(prob.x0), 1.0E-4)
+    lda0 = np.concatenate([np.zeros(prob.neq), 0.2 / s0])
+    o = OracleIPM(x0=prob.x0.copy(), verbosity=-1, **prob.callables())
+    o.nvar = prob.nvar
+    o.compile()
+    o.mu_host, o.mu_dev, o.nu_host, o.nu_dev, o.delta, o.signal = 0.2, np.float64(0.2), 10.0, np.float64(10.0), np.float64(1.0), 0
+    tr = []
+    o.trace = tr
+    with np.errstate(all='ignore'):
+        o.newton_step(prob.x0.copy(), s0.copy(), lda0.copy())
+    st = tr[0]
+    assert st['reg']['n_eig'] == 1 and st['delta'] == 1.0
+    for flags in (0, 6):
+        eng = make_engine(prob, flags=flags)
+        eng.set_state(prob.x0, s0, lda0, 0.2, 10.0, 1.0)
+        eng.set_mu_host(0.2)
+        dz, info = eng.direction()
+        assert info.n_factor == 1 and info.delta == 1.0 and info.n_neg == prob.neq
+        assert relinf(dz, st['dz']) < DZ_RTOL
+        eng.close()
