@@ -46,6 +46,9 @@ struct GemmArgs {
     // its global block column (tiles never straddle blocks: bc_b is a multiple of the tile size).
     int bc_b, bc_P, bc_Q, bc_p, bc_q, bc_li0, bc_lj0;
     const int* ctrl;      // optional LDL^T control block: ctrl[4] != 0 => the factorisation was abandoned, do nothing
+    int max_ctas;         // > 0 (GEMM_LOWER_ONLY, square): persistent launch with at most this many CTAs, so that the
+                          // rest of the SMs stay free for the latency-critical kernels of a concurrent stream
+    int persistent_tiles; // set by gemm_nt()
 };
 
 constexpr int G_BM = 128, G_BN = 128, G_BK = 32, G_LDS = 36, G_STAGES = 3;
@@ -103,15 +106,7 @@ __device__ __forceinline__ void g_load_w(double* sdst, const double* __restrict_
 // 2 x 4 (256 threads, 64 x 32 warp tiles) 26.0 TF/s, 4 x 4 (512 threads, 32 x 32 warp tiles) 24.3 TF/s.
 constexpr int G_NWM = 2, G_NWN = 4, G_THREADS = 32 * G_NWM * G_NWN;
 constexpr int G_MT = G_BM / (8 * G_NWM), G_NT = G_BN / (8 * G_NWN);
-__global__ void __launch_bounds__(G_THREADS, 1) gemm_nt_dmma_kernel(const GemmArgs a) {
-    extern __shared__ __align__(16) double g_smem[];
-    const int ti = blockIdx.y, tj = blockIdx.x;
-    if (a.ctrl) {   // one read per CTA: the flag can be raised while this kernel runs (look-ahead streams)
-        __shared__ int s_abort;
-        if (threadIdx.x == 0) s_abort = *reinterpret_cast<const volatile int*>(a.ctrl + 4);
-        __syncthreads();
-        if (s_abort) return;
-    }
+__device__ __forceinline__ void gemm_nt_tile(const GemmArgs& a, const int ti, const int tj, double* g_smem) {
     if (a.mode == GEMM_UPPER_MIRROR && ti > tj) return;
     if (a.mode == GEMM_LOWER_ONLY && ti < tj) return;
     if (a.mode == GEMM_BC_LOWER) {
@@ -245,6 +240,28 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_nt_dmma_kernel(const GemmAr
     }
 }
 
+__global__ void __launch_bounds__(G_THREADS, 1) gemm_nt_dmma_kernel(const GemmArgs a) {
+    extern __shared__ __align__(16) double g_smem[];
+    if (a.ctrl) {   // one read per CTA: the flag can be raised while this kernel runs (look-ahead streams)
+        __shared__ int s_abort;
+        if (threadIdx.x == 0) s_abort = *reinterpret_cast<const volatile int*>(a.ctrl + 4);
+        __syncthreads();
+        if (s_abort) return;
+    }
+    if (a.persistent_tiles > 0) {
+        // lower-triangular tile t -> (r, c) with c <= r, row by row
+        for (int t = blockIdx.x; t < a.persistent_tiles; t += gridDim.x) {
+            int r = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+            while ((r + 1) * (r + 2) / 2 <= t) r++;
+            while (r * (r + 1) / 2 > t) r--;
+            gemm_nt_tile(a, r, t - r * (r + 1) / 2, g_smem);
+            __syncthreads();
+        }
+    } else {
+        gemm_nt_tile(a, blockIdx.y, blockIdx.x, g_smem);
+    }
+}
+
 // scalar reference kernel: any size / alignment (tiny problems, odd leading dimensions, test cross-check)
 __global__ void gemm_nt_simple_kernel(const GemmArgs a) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -288,7 +305,16 @@ inline int gemm_nt(cudaStream_t st, const GemmArgs& a, bool force_simple = false
     const bool big = (a.n >= 48 && a.m >= 48);
     if (!force_simple && big && gemm_nt_can_dmma(a)) {
         dim3 grid(cdiv(a.m, G_BN), cdiv(a.n, G_BM));
-        gemm_nt_dmma_kernel<<<grid, G_THREADS, G_SMEM, st>>>(a);
+        GemmArgs b = a;
+        b.persistent_tiles = 0;
+        if (a.max_ctas > 0 && a.mode == GEMM_LOWER_ONLY && a.n == a.m) {
+            const int nt = (int)grid.y * ((int)grid.y + 1) / 2;
+            if (nt > a.max_ctas) {
+                b.persistent_tiles = nt;
+                grid = dim3(a.max_ctas, 1);
+            }
+        }
+        gemm_nt_dmma_kernel<<<grid, G_THREADS, G_SMEM, st>>>(b);
         LAUNCHED();
     } else {
         dim3 blk(32, 8), grid(cdiv(a.m, 32), cdiv(a.n, 8));

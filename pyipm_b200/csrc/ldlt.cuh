@@ -52,6 +52,7 @@ struct LdltWs {
     int graph_nodes = 0;
     int graph_state = 0;           // 0 = not tried, 1 = usable, -1 = capture failed: direct launches
     int neg_limit = 0x7fffffff; // value last written to counts[5]
+    int side_ctas = 0;         // > 0: the bulk trailing updates run as persistent kernels of at most this many CTAs
     double pivot_u = 0.01;     // threshold of the fast (unpivoted) tile attempt: accept step j iff |d_j| >= u * max_i |T[i][j]|
 };
 
@@ -75,6 +76,11 @@ inline int ldlt_alloc(LdltWs& w, int n, cudaStream_t st, bool background = false
     const int span = prio_lo - prio_hi;
     const int p_chain = background ? prio_hi + std::min(span, 2) : prio_hi;
     const int p_side = background ? prio_lo : prio_hi + std::min(span, 1);
+    {
+        // SMs left to the serial chain while a bulk update runs (B200IPM_SIDE_FG / B200IPM_SIDE_BG override, 0 = all)
+        const char* e = getenv(background ? "B200IPM_SIDE_BG" : "B200IPM_SIDE_FG");
+        w.side_ctas = e ? atoi(e) : (background ? 48 : 96);   // measured at config 3 (tools/sweep_side.py)
+    }
     CU(cudaStreamCreateWithPriority(&w.side, cudaStreamNonBlocking, p_side));
     CU(cudaStreamCreateWithPriority(&w.cap, cudaStreamNonBlocking, p_chain));
     for (int i = 0; i < 2; i++) {
@@ -820,7 +826,7 @@ inline int ldlt_factor_launch(LdltWs& w, cudaStream_t st) {
             CU(cudaStreamWaitEvent(sd, w.ev_panel[p & 1], 0));
             GemmArgs u{};
             u.C = w.A + (size_t)(c1 + na) * ld + (c1 + na); u.ldc = ld; u.Cin = u.C; u.ldcin = ld; u.n = rows3; u.m = rows3;
-            u.beta = 1.0; u.mode = GEMM_LOWER_ONLY; u.nterms = 1; u.ctrl = w.counts;
+            u.beta = 1.0; u.mode = GEMM_LOWER_ONLY; u.nterms = 1; u.ctrl = w.counts; u.max_ctas = w.side_ctas;
             u.t[0] = GemmTerm{Wpan + (size_t)na * NBO, Lpan + (size_t)na * ld, nullptr, NBO, ld, kw, -1.0};
             RET(gemm_nt(sd, u));
             CU(cudaEventRecord(w.ev_upd[p & 1], sd));
