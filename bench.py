@@ -333,7 +333,9 @@ def run_b200(args):
         'config': {'workload': WORKLOAD, 'D': D3, 'M': M3, 'N': N3, 'K_full': K3, 'K_condensed': D3 + M3,
                    'parallelism': 'replicas x%d (one independent Newton step per GPU, no collective)' % world,
                    'state': 'teacher-forced from the state after %d real Newton steps from x0' % PRE_STEPS,
-                   'factorisations_per_step': nfac, 'refinement_sweeps': 2,
+                   'factorisations_per_step': nfac, 'refinement_sweeps': 2, 'engine_flags': args.flags,
+                   'contractions': 'tcgen05 int8 error-free split' if args.flags & 2 else 'fp64 DMMA',
+                   'reghess': ('sequential' if args.flags & 1 else 'delta=0 test in the background, candidate in the foreground'),
                    'l2': 'working set (J 151 MB, Vt/Gt/Q 134 MB each, KKT 170 MB) exceeds the 126 MB L2; no flush'},
         'clocks': clocks,
         'e2e': {'value': e2e_value, 'unit': 'steps/s', 'h2d_bytes_per_step': int(8 * (D3 + N3 + M3 + N3)),
@@ -358,20 +360,50 @@ def run_b200(args):
             ms, work = eng.profile_kernel(which, reps=5)
             kern[name] = {'ms': ms, ('tflops' if kind == 'flop' else 'gbs'): work / ms * (1e-9 if kind == 'flop' else 1e-6),
                           'work': work}
-        dom = kern['hess_syrk']
-        line['roofline'] = {
-            'kernel': 'gemm_nt_dmma_kernel (Lagrangian-Hessian SYRK: Ut diag(lda_e) Ut\' + Vt diag(lda_i) Vt\', fp64 DMMA)',
-            'bound': 'tensor', 'achieved': dom['tflops'], 'peak': fp64_peak_tf, 'unit': 'TFLOP/s',
-            'frac': dom['tflops'] / fp64_peak_tf, 'traffic': None,
-            'peak_source': 'cuBLAS DGEMM 4096^3 measured in this run (fp64 tensor pipe; MEASURED_PEAKS.json has no fp64 '
-                           'entry: its bf16 figure %.0f TF/s (%s) is a different pipe -- tcgen05 has no f64 kind)'
-                           % (bf16_tf, peak_kind),
-            'flops_per_launch': dom['work'],
-        }
+        tc_on = bool(args.flags & 2)
+        if tc_on:
+            ms8, ops8 = eng.profile_kernel(8, reps=5)
+            ach = ops8 / ms8 * 1e-9
+            peak = int8_peak_tops if int8_peak_tops else 2.0 * bf16_tf
+            kern['hess_syrk_tcgen05_kernel_only'] = {'ms': ms8, 'int8_tops': ach, 'work': ops8}
+            line['roofline'] = {
+                'kernel': 'oz_syrk_kernel<128,2> (Lagrangian-Hessian contraction Ut diag(lda_e) Ut\' + Vt diag(lda_i) Vt\' as 36 '
+                          'exact int8 slice products on tcgen05.mma.kind::i8, int32 TMEM accumulators, fp64 recombination)',
+                'bound': 'tensor', 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s', 'frac': ach / peak,
+                'traffic': 1.023e9,
+                'traffic_source': 'ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch '
+                                  '(profiles/r1_ncu_oz_syrk.md); operands (302 MB of int8 slices) stream from L2',
+                'peak_source': ('cuBLASLt int8 GEMM 8192^3 (torch._int_mm) measured in this run = %.0f TOP/s; dense int8 is '
+                                '2x the bf16 rate: 2 x MEASURED_PEAKS bf16_tflops = %.0f (%s)'
+                                % (int8_peak_tops or 0.0, 2.0 * bf16_tf, peak_kind)),
+                'ops_per_launch': ops8,
+                'note': 'achieved/peak count int8 multiply-adds issued (the algorithm: 36 slice pairs x upper tiles x K); the '
+                        'fp64-equivalent rate of the whole operation (slicing + tensor kernel) is in roofline_fp64',
+            }
+            full = kern['hess_syrk_tcgen05']
+            line['roofline_fp64'] = {
+                'kernel': 'Lagrangian-Hessian contraction, fp64-equivalent: slicing + tcgen05 kernel vs the fp64 tensor pipe',
+                'achieved': full['tflops'], 'peak': fp64_peak_tf, 'unit': 'TFLOP/s', 'frac': full['tflops'] / fp64_peak_tf,
+                'dmma_kernel_tflops': kern['hess_syrk']['tflops'],
+                'peak_source': 'cuBLAS DGEMM 4096^3 measured in this run (the DMMA pipe; tcgen05 has no f64 kind)',
+                'flops_per_launch': full['work']}
+        else:
+            dom = kern['hess_syrk']
+            line['roofline'] = {
+                'kernel': 'gemm_nt_dmma_kernel (Lagrangian-Hessian SYRK: Ut diag(lda_e) Ut\' + Vt diag(lda_i) Vt\', fp64 DMMA)',
+                'bound': 'tensor', 'achieved': dom['tflops'], 'peak': fp64_peak_tf, 'unit': 'TFLOP/s',
+                'frac': dom['tflops'] / fp64_peak_tf, 'traffic': 6.31e8,
+                'traffic_source': 'ncu --set full (profiles/r1_ncu_syrk_final.md)',
+                'peak_source': 'cuBLAS DGEMM 4096^3 measured in this run (fp64 tensor pipe; MEASURED_PEAKS.json has no fp64 '
+                               'entry: its bf16 figure %.0f TF/s (%s) is a different pipe -- tcgen05 has no f64 kind)'
+                               % (bf16_tf, peak_kind),
+                'flops_per_launch': dom['work'],
+            }
         res = kern['residual_gemv']
         line['roofline_hbm'] = {'kernel': 'gemv_n_kernel (g_x = df - J*lda, fused KKT norm)', 'bound': 'hbm',
                                 'achieved': res['gbs'], 'peak': hbm_gbs, 'unit': 'GB/s', 'frac': res['gbs'] / hbm_gbs,
-                                'traffic': None, 'peak_source': 'MEASURED_PEAKS.json hbm_gbs (%s)' % peak_kind,
+                                'traffic': 1.393e8, 'traffic_source': 'ncu --set full (profiles/r1_ncu_residual_gemv_final.md)',
+                                'peak_source': 'MEASURED_PEAKS.json hbm_gbs (%s)' % peak_kind,
                                 'bytes_per_launch': res['work']}
         line['kernels'] = kern
         # "KKT-residual match vs CPU ref": one teacher-forced Newton step of a small instance of the same NLP

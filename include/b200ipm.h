@@ -193,7 +193,8 @@ int b200ipm_gemm_nt_update_bc(b200ipm_ldlt_handle h, double* C_dev, int ldc, int
  *   which = 0 residual GEMV g_x = df - J*lda (HBM)      1 Lagrangian-Hessian SYRK (fp64 tensor)
  *           2 condensation SYRK dci*S*dci' (fp64 tensor) 3 one LDL^T factorisation of the condensed KKT matrix
  *           4 one forward+backward triangular solve      5 J'*dx GEMV (HBM)
- *           6 / 7 = 1 / 2 on the tcgen05 int8 path (work is still the fp64-equivalent FLOP count) */
+ *           6 / 7 = 1 / 2 on the tcgen05 int8 path (work is still the fp64-equivalent FLOP count)
+ *           8 = the tcgen05 kernel of 6 alone, slices reused (work = int8 operations issued) */
 int b200ipm_profile_kernel(b200ipm_handle h, int which, int reps, float* ms_per_launch, double* work);
 
 /* ---- test hooks: individual kernels against the oracle (tests/test_gpu_kernels.py) ---------------- */

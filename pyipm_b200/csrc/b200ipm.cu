@@ -1108,6 +1108,25 @@ int b200ipm_profile_kernel(b200ipm_handle h, int which, int reps, float* ms_per_
                 wk = gemm_nt_flops(a);
                 break;
             }
+            case 8: {   // the tcgen05 kernel of case 6 alone (slices kept from the first repetition); work = int8 operations
+                GemmArgs a{};
+                a.C = h->W; a.ldc = h->ldW; a.Cin = h->Q; a.ldcin = D; a.dadd = h->xdiag; a.n = D; a.m = D; a.beta = 1.0;
+                a.mode = GEMM_UPPER_MIRROR; a.nterms = 0;
+                if (h->kind != KIND_QUAD) return fail_msg("profile_kernel(8) needs a bound quad problem");
+                if (M && h->Ut) a.t[a.nterms++] = GemmTerm{h->Ut, h->Ut, h->lam, M, M, M, -1.0};
+                if (N && h->Vt) a.t[a.nterms++] = GemmTerm{h->Vt, h->Vt, h->lam + M, N, N, N, 1.0};
+                oz_configure(h);
+                if (r == 0) {
+                    RET(oz_syrk(h->st, a, h->oz, (M && h->Ut) ? 1u : 0u));
+                    CU(cudaEventRecord(h->ev[EV_START], h->st));   // restart the clock after the slicing pass
+                }
+                h->oz.reuse_slices = true;
+                const int rc8 = oz_syrk(h->st, a, h->oz, (M && h->Ut) ? 1u : 0u);
+                h->oz.reuse_slices = false;
+                RET(rc8);
+                wk = oz_syrk_int8_ops(a, oz_variant_bn(h->oz.variant));
+                break;
+            }
             case 7: {
                 GemmArgs a{};
                 a.C = h->Hb; a.ldc = h->ldW; a.Cin = h->W; a.ldcin = h->ldW; a.n = D; a.m = D; a.beta = 1.0;

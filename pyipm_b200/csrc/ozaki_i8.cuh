@@ -199,6 +199,17 @@ __device__ __forceinline__ void oz_bulk_g2s(uint32_t dst, const void* src, uint3
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
+__device__ __forceinline__ bool oz_elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred P;\n"
+        "elect.sync _|P, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, P;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void oz_tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void oz_tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void oz_tc_commit(uint32_t bar) {
@@ -331,34 +342,43 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzGemmArgs
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer: one thread
-        if (lane == 0) {
-            int it = 0;
-            for (int pi = 0; pi < NPASS; pi++) {
-                const int d0 = (NPASS - 1 - pi) * DPP;
-                if (pi > 0) {
-                    oz_mbar_wait(oz_smem_u32(&bar_tempty), (uint32_t)(pi - 1) & 1u, dead, a.err);
-                    oz_tc_fence_after();
-                }
-                for (int kb = 0; kb < a.nkb; kb++, it++) {
-                    const int s = it % STAGES;
-                    const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-                    oz_mbar_wait(oz_smem_u32(&bar_full[s]), ph, dead, a.err);
-                    oz_tc_fence_after();
-                    const uint32_t sa = smem0 + s * STAGE, sb = sa + A_BYTES;
+        // ===== MMA issuer.  The WHOLE warp runs the loop with warp-uniform values (descriptors stay in uniform
+        // registers); only the tcgen05 instructions themselves are issued by one elected lane.  With a single-lane
+        // branch around the loop the compiler has to re-uniformise every descriptor (ELECT / R2UR loops, ~30
+        // instructions per MMA) and the issue rate, not the tensor pipe, bounds the kernel.
+        int it = 0;
 #pragma unroll
-                    for (int dd = 0; dd < DPP; dd++) {
-                        const int d = d0 + dd;
-                        for (int p = 0; p <= d; p++) {
-                            const int q = d - p;
-                            oz_mma_i8(tmem + (uint32_t)(dd * BN), oz_desc(sa + p * OZ_CHUNK, a.desc_hi),
-                                      oz_desc(sb + q * B_SLICE, a.desc_hi), a.idesc, (kb > 0 || p > 0) ? 1u : 0u);
+        for (int pi = 0; pi < NPASS; pi++) {
+            constexpr int DPPc = DPP;
+            const int d0 = (NPASS - 1 - pi) * DPPc;
+            if (pi > 0) {
+                oz_mbar_wait(oz_smem_u32(&bar_tempty), (uint32_t)(pi - 1) & 1u, dead, a.err);
+                oz_tc_fence_after();
+            }
+            for (int kb = 0; kb < a.nkb; kb++, it++) {
+                const int s = it % STAGES;
+                const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+                oz_mbar_wait(oz_smem_u32(&bar_full[s]), ph, dead, a.err);
+                oz_tc_fence_after();
+                const uint32_t sa = smem0 + s * STAGE, sb = sa + A_BYTES;
+                const uint64_t da0 = oz_desc(sa, a.desc_hi), db0 = oz_desc(sb, a.desc_hi);
+                const uint32_t acc_first = (kb > 0) ? 1u : 0u;
+                if (oz_elect_one()) {
+#pragma unroll
+                    for (int dd = 0; dd < DPPc; dd++) {
+#pragma unroll
+                        for (int p = 0; p <= d0 + dd; p++) {
+                            const int q = d0 + dd - p;
+                            oz_mma_i8(tmem + (uint32_t)(dd * BN), da0 + (uint64_t)(p * (OZ_CHUNK >> 4)),
+                                      db0 + (uint64_t)(q * (B_SLICE >> 4)), a.idesc, (p > 0) ? 1u : acc_first);
                         }
                     }
                     oz_tc_commit(oz_smem_u32(&bar_empty[s]));      // frees the stage when these MMAs have read it
                 }
-                oz_tc_commit(oz_smem_u32(&bar_tfull));             // accumulators of this pass are complete
+                __syncwarp();
             }
+            if (oz_elect_one()) oz_tc_commit(oz_smem_u32(&bar_tfull));   // accumulators of this pass are complete
+            __syncwarp();
         }
     } else {
         // ===== epilogue: warp (warp & 3) owns TMEM lanes 32*(warp & 3) .. +31 = tile rows.  Per 8-column chunk: the
@@ -452,6 +472,7 @@ struct OzWs {
     int lbo = 128, sbo = 256;
     int variant = 1;          // 0: 128x64 tiles, 1 pass;  1: 128x128 tiles, 2 passes;  2: 128x256 tiles, 4 passes
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};   // optional: [0] start, [1] after slicing, [2] end
+    bool reuse_slices = false; // profiling: skip the slicing kernels (the slices of the previous identical call are kept)
 };
 inline void oz_free(OzWs& w) {
     cudaFree(w.L); cudaFree(w.R); cudaFree(w.rexp); cudaFree(w.err); cudaFree(w.tiles); cudaFree(w.sw);
@@ -541,10 +562,12 @@ inline int oz_syrk(cudaStream_t st, const GemmArgs& a, OzWs& w, unsigned may_be_
     s.nterms = a.nterms; s.n = a.n; s.nkb = nkb;
     s.L = w.L; s.R = w.R; s.sw = w.sw; s.rexp = w.rexp; s.err = w.err;
     if (w.ev[0]) CU(cudaEventRecord(w.ev[0], st));
-    oz_weight_kernel<<<cdiv(nkb * OZ_KB, 256), 256, 0, st>>>(s, w.sw);
-    LAUNCHED();
-    oz_slice_kernel<<<nrb * (OZ_BM / 8), 256, 0, st>>>(s);
-    LAUNCHED();
+    if (!w.reuse_slices) {
+        oz_weight_kernel<<<cdiv(nkb * OZ_KB, 256), 256, 0, st>>>(s, w.sw);
+        LAUNCHED();
+        oz_slice_kernel<<<nrb * (OZ_BM / 8), 256, 0, st>>>(s);
+        LAUNCHED();
+    }
     if (w.ev[1]) CU(cudaEventRecord(w.ev[1], st));
     g.L = w.L; g.R = w.R; g.rexp = w.rexp; g.tiles = w.tiles; g.err = w.err;
     g.C = a.C; g.Cin = a.Cin; g.dadd = a.dadd; g.ldc = a.ldc; g.ldcin = a.ldcin; g.n = a.n; g.nkb = nkb;
