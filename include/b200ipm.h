@@ -42,6 +42,8 @@ typedef struct b200ipm_params {
     int    flags;                         /* B200IPM_FLAG_* bits */
 } b200ipm_params;
 #define B200IPM_FLAG_NO_SPECULATION 1
+#define B200IPM_FLAG_DELAY_BG       32  /* start the background inertia test only when the foreground factorisation is past
+                                           its first third (measured: no net gain at config 3, off by default) */
 #define B200IPM_FLAG_NO_ABANDON     16  /* always complete a failed inertia test (n_neg_first is then the full count) */
 #define B200IPM_FLAG_TCGEN05_SYRK   2   /* d2L and condensation contractions on tcgen05 (int8 error-free split) */
 #define B200IPM_FLAG_TCGEN05_TILE(v) ((v) << 2)   /* with TCGEN05_SYRK: 0 = 128x64 tiles / 1 pass, 1 = 128x128 / 2, 2 = 128x256 / 4 */
@@ -204,6 +206,11 @@ int b200ipm_test_syrk(int n, const double* Cin, double beta, const double* dadd,
                       int nterms, const double* const* A, const double* const* w, const int* K,
                       const double* alpha, double* C, int force_simple, float* ms);
 int b200ipm_test_gemv(int rows, int cols, const double* A, const double* v, double* y, int transpose);
+/* Device-side timeline of the factorisation kernels (profiling aid): after trace_start, selected CTAs of the LDL^T
+ * kernels stamp %globaltimer (ns) at entry/exit; trace_dump copies up to `max` records (kernel id 1 tile, 2 panel,
+ * 3 mini, 4 in-panel update, 5 DMMA trailing update; CTA index; t0; t1) to the host and switches the trace off. */
+int b200ipm_trace_start(void);
+int b200ipm_trace_dump(int* id, int* blk, unsigned long long* t0, unsigned long long* t1, int max, int* n);
 /* Same product as b200ipm_test_syrk, computed on the tcgen05 tensor cores by the int8 error-free (Ozaki) path:
  * signed_mask bit t = alpha_t*w_t may be negative; variant 0 = 128x64 tiles / one pass, 1 = 128x128 tiles / two
  * passes, 2 = 128x256 / four; lbo, sbo <= 0 keep the default shared-memory descriptor strides; ms[2] = {slicing ms,

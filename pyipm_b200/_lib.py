@@ -62,7 +62,7 @@ SYMBOLS = [
     'b200ipm_kkt', 'b200ipm_con_jac', 'b200ipm_hess_full', 'b200ipm_d2L', 'b200ipm_merit', 'b200ipm_init_slack',
     'b200ipm_init_lambda', 'b200ipm_update_mu', 'b200ipm_direction', 'b200ipm_step_max', 'b200ipm_newton_step',
     'b200ipm_ldlt_create', 'b200ipm_ldlt_destroy', 'b200ipm_ldlt_factor', 'b200ipm_ldlt_solve',
-    'b200ipm_ldlt_tile_factor', 'b200ipm_ldlt_panel', 'b200ipm_ldlt_import', 'b200ipm_gemm_nt_update', 'b200ipm_gemm_nt_update_bc', 'b200ipm_test_syrk', 'b200ipm_test_syrk_i8',
+    'b200ipm_ldlt_tile_factor', 'b200ipm_ldlt_panel', 'b200ipm_ldlt_import', 'b200ipm_gemm_nt_update', 'b200ipm_gemm_nt_update_bc', 'b200ipm_test_syrk', 'b200ipm_test_syrk_i8', 'b200ipm_trace_start', 'b200ipm_trace_dump',
     'b200ipm_test_gemv',
 ]
 
@@ -129,6 +129,8 @@ def load():
         'b200ipm_test_syrk_i8': (i, [i, vp, d, vp, d, i, C.POINTER(vp), C.POINTER(vp), ip, dp, vp, C.c_uint, i, i, i,
                                      C.POINTER(C.c_float), ip]),
         'b200ipm_test_gemv': (i, [i, i, vp, vp, vp, i]),
+        'b200ipm_trace_start': (i, []),
+        'b200ipm_trace_dump': (i, [vp, vp, vp, vp, i, ip]),
     }
     for name in SYMBOLS:
         fn = getattr(lib, name)   # AttributeError if the library does not export it
@@ -394,6 +396,22 @@ def test_syrk_i8(n, Cin, beta, dadd, shift, terms, signed_mask=0, variant=0, lbo
     check(lib.b200ipm_test_syrk_i8(int(n), ptr(Cin), float(beta), ptr(dadd), float(shift), nt, Ap, wp, Ks, al, ptr(out),
                                    int(signed_mask), int(variant), int(lbo), int(sbo), ms, C.byref(err)))
     return out, (ms[0], ms[1]), err.value
+
+
+def trace_start():
+    check(load().b200ipm_trace_start())
+
+
+def trace_dump(maxrec=65536):
+    """-> structured array (id, blk, t0, t1) of the device-side timeline records since trace_start()"""
+    ids = np.zeros(maxrec, dtype=np.int32)
+    blk = np.zeros(maxrec, dtype=np.int32)
+    t0 = np.zeros(maxrec, dtype=np.uint64)
+    t1 = np.zeros(maxrec, dtype=np.uint64)
+    n = C.c_int(0)
+    check(load().b200ipm_trace_dump(ptr(ids), ptr(blk), ptr(t0), ptr(t1), int(maxrec), C.byref(n)))
+    k = n.value
+    return ids[:k], blk[:k], t0[:k].astype(np.int64), t1[:k].astype(np.int64)
 
 
 def test_gemv(A, v, transpose=False):

@@ -47,6 +47,34 @@ inline int fail_msg(const char* msg) {
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline size_t rup(size_t a, size_t b) { return (a + b - 1) / b * b; }
 
+// ------------------------------------------------------------------------------------ device-side timeline trace
+// Profiling aid (b200ipm_trace_start / b200ipm_trace_dump): when enabled, selected CTAs of the factorisation kernels
+// stamp %globaltimer at entry and exit.  Disabled (null pointer) it costs one global load per kernel.
+struct TraceRec { int id, blk; unsigned long long t0, t1; };
+constexpr int TRACE_CAP = 1 << 16;
+__device__ TraceRec* g_trace = nullptr;
+__device__ int g_trace_n = 0;
+__device__ __forceinline__ unsigned long long trace_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ int trace_begin(int id) {
+    TraceRec* t = g_trace;
+    if (!t) return -1;
+    const int i = atomicAdd(&g_trace_n, 1);
+    if (i >= TRACE_CAP) return -1;
+    t[i].id = id;
+    t[i].blk = (int)(blockIdx.x + blockIdx.y * gridDim.x);
+    t[i].t0 = trace_now();
+    t[i].t1 = 0;
+    return i;
+}
+__device__ __forceinline__ void trace_end(int i) {
+    if (i >= 0) g_trace[i].t1 = trace_now();
+}
+enum { TR_TILE = 1, TR_PANEL = 2, TR_MINI = 3, TR_SUB64 = 4, TR_DMMA = 5 };
+
 // ------------------------------------------------------------------------------------ device reductions
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

@@ -248,6 +248,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_nt_dmma_kernel(const GemmAr
         __syncthreads();
         if (s_abort) return;
     }
+    const int trc = (threadIdx.x == 0 && ((blockIdx.x == 0 && blockIdx.y == 0) || (blockIdx.x == gridDim.x - 1 && blockIdx.y == gridDim.y - 1)))
+                        ? trace_begin(TR_DMMA) : -1;
     if (a.persistent_tiles > 0) {
         // lower-triangular tile t -> (r, c) with c <= r, row by row
         for (int t = blockIdx.x; t < a.persistent_tiles; t += gridDim.x) {
@@ -260,6 +262,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_nt_dmma_kernel(const GemmAr
     } else {
         gemm_nt_tile(a, blockIdx.y, blockIdx.x, g_smem);
     }
+    trace_end(trc);
 }
 
 // scalar reference kernel: any size / alignment (tiny problems, odd leading dimensions, test cross-check)
@@ -291,6 +294,9 @@ __global__ void gemm_nt_simple_kernel(const GemmArgs a) {
     if (a.mode == GEMM_UPPER_MIRROR && i != j) a.C[(size_t)j * a.ldc + i] = v;
 }
 
+inline bool gemm_nt_sub_uses_tiles(int rows, const double* A, int lda, const double* B, int ldb) {
+    return !(lda & 1) && !(ldb & 1) && !(reinterpret_cast<uintptr_t>(A) & 15) && !(reinterpret_cast<uintptr_t>(B) & 15) && rows >= 48;
+}
 inline bool gemm_nt_can_dmma(const GemmArgs& a) {
     for (int t = 0; t < a.nterms; t++) {
         const GemmTerm& T = a.t[t];
@@ -353,8 +359,11 @@ __device__ __forceinline__ void s_load_tile(double* sdst, const double* __restri
 __global__ void __launch_bounds__(128, 2) gemm_nt_sub64_kernel(double* __restrict__ C, int ldc, int rows, int cols,
                                                                const double* __restrict__ A, int lda,
                                                                const double* __restrict__ B, int ldb, int K,
-                                                               const int* __restrict__ ctrl) {
+                                                               const int* __restrict__ ctrl, int skip00) {
     extern __shared__ __align__(16) double s_smem[];
+    if (skip00 && blockIdx.x == 0 && blockIdx.y == 0) return;   // that tile was already updated on the chain stream
+    const int trc = (threadIdx.x == 0 && ((blockIdx.x == 1 && blockIdx.y == 0) || (blockIdx.x == gridDim.x - 1 && blockIdx.y == gridDim.y - 1)))
+                        ? trace_begin(TR_SUB64) : -1;
     if (ctrl) {
         __shared__ int s_abort;
         if (threadIdx.x == 0) s_abort = *reinterpret_cast<const volatile int*>(ctrl + 4);
@@ -434,19 +443,21 @@ __global__ void __launch_bounds__(128, 2) gemm_nt_sub64_kernel(double* __restric
                 }
         }
     }
+    trace_end(trc);
 }
 
 // C (rows x cols, in place) -= A (rows x K) * B (cols x K)^T
 inline int gemm_nt_sub(cudaStream_t st, double* C, int ldc, int rows, int cols, const double* A, int lda, const double* B,
-                       int ldb, int K, const int* ctrl = nullptr) {
+                       int ldb, int K, const int* ctrl = nullptr, int skip00 = 0) {
     if (rows <= 0 || cols <= 0) return 0;
     const bool ok = !(lda & 1) && !(ldb & 1) && !(reinterpret_cast<uintptr_t>(A) & 15) && !(reinterpret_cast<uintptr_t>(B) & 15);
     if (ok && rows >= 48) {
         dim3 grid(cdiv(cols, S_BN), cdiv(rows, S_BM));
-        gemm_nt_sub64_kernel<<<grid, 128, S_SMEM, st>>>(C, ldc, rows, cols, A, lda, B, ldb, K, ctrl);
+        gemm_nt_sub64_kernel<<<grid, 128, S_SMEM, st>>>(C, ldc, rows, cols, A, lda, B, ldb, K, ctrl, skip00);
         LAUNCHED();
         return 0;
     }
+    if (skip00) return fail_msg("gemm_nt_sub: skip00 needs the 64 x 64 tile kernel");
     GemmArgs u{};
     u.C = C; u.ldc = ldc; u.Cin = C; u.ldcin = ldc; u.n = rows; u.m = cols; u.beta = 1.0; u.mode = GEMM_FULL; u.nterms = 1;
     u.t[0] = GemmTerm{A, B, nullptr, lda, ldb, K, -1.0};

@@ -43,12 +43,20 @@ struct LdltWs {
     double *yv = nullptr, *zv = nullptr, *xv = nullptr;
     unsigned epoch = 0;
     cudaStream_t st = nullptr;
-    double* Wp2 = nullptr;     // second outer-panel scratch (look-ahead double buffering)
+    double* Wp2 = nullptr;     // second / third outer-panel scratch (look-ahead depth 2: triple buffering)
+    double* Wp3 = nullptr;
+    cudaEvent_t ev_urg[2] = {nullptr, nullptr};
     cudaStream_t side = nullptr;   // trailing updates beyond the next panel run here, overlapped with the next panel
     cudaEvent_t ev_panel[2] = {nullptr, nullptr}, ev_upd[2] = {nullptr, nullptr};
+    cudaStream_t upd = nullptr;    // in-panel updates off the chain (everything of a tile step but the next diagonal tile)
+    cudaEvent_t ev_tile = nullptr, ev_mini = nullptr, ev_urest = nullptr;
+    int* sig = nullptr;            // device word set to 1 when tile step sig_tile starts (baked into the graph)
+    int sig_tile = -1;
+    int use_mini = 1;              // B200IPM_LDLT_MINI=0 restores the tile -> panel -> update chain
     cudaStream_t cap = nullptr;    // internal capture-origin stream (the caller's stream may be the legacy default one)
     cudaGraphExec_t gexec = nullptr;
     double graph_u = -1.0;         // pivot_u the captured graph was built with
+    int graph_sig_tile = -1;       // sig_tile the captured graph was built with
     int graph_nodes = 0;
     int graph_state = 0;           // 0 = not tried, 1 = usable, -1 = capture failed: direct launches
     int neg_limit = 0x7fffffff; // value last written to counts[5]
@@ -66,6 +74,7 @@ inline int ldlt_alloc(LdltWs& w, int n, cudaStream_t st, bool background = false
     CU(cudaMalloc(&w.A, sizeof(double) * (size_t)npad * w.ld));
     CU(cudaMalloc(&w.Wp, sizeof(double) * npad * 256));
     CU(cudaMalloc(&w.Wp2, sizeof(double) * npad * 256));
+    CU(cudaMalloc(&w.Wp3, sizeof(double) * npad * 256));
     // the serial chain (tile -> panel -> in-panel update) is captured on a HIGH-priority stream, the bulk trailing
     // updates on a LOW-priority one: a chain kernel never queues behind a full wave of long update CTAs (captured
     // kernel nodes inherit the priority of the stream they were captured on)
@@ -83,9 +92,15 @@ inline int ldlt_alloc(LdltWs& w, int n, cudaStream_t st, bool background = false
     }
     CU(cudaStreamCreateWithPriority(&w.side, cudaStreamNonBlocking, p_side));
     CU(cudaStreamCreateWithPriority(&w.cap, cudaStreamNonBlocking, p_chain));
+    CU(cudaStreamCreateWithPriority(&w.upd, cudaStreamNonBlocking, p_chain));
+    CU(cudaEventCreateWithFlags(&w.ev_tile, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&w.ev_mini, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&w.ev_urest, cudaEventDisableTiming));
+    { const char* e = getenv("B200IPM_LDLT_MINI"); if (e) w.use_mini = atoi(e); }
     for (int i = 0; i < 2; i++) {
         CU(cudaEventCreateWithFlags(&w.ev_panel[i], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&w.ev_upd[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&w.ev_urg[i], cudaEventDisableTiming));
     }
     CU(cudaMalloc(&w.LinvP, sizeof(double) * (size_t)w.nblk * NB * NB));
     CU(cudaMalloc(&w.dinfo, sizeof(double) * 4 * npad));
@@ -106,9 +121,14 @@ inline int ldlt_alloc(LdltWs& w, int n, cudaStream_t st, bool background = false
     return 0;
 }
 inline void ldlt_free(LdltWs& w) {
-    cudaFree(w.A); cudaFree(w.Wp); cudaFree(w.Wp2);
+    cudaFree(w.A); cudaFree(w.Wp); cudaFree(w.Wp2); cudaFree(w.Wp3);
+    for (int i = 0; i < 2; i++) if (w.ev_urg[i]) cudaEventDestroy(w.ev_urg[i]);
     if (w.gexec) cudaGraphExecDestroy(w.gexec);
     if (w.side) cudaStreamDestroy(w.side);
+    if (w.upd) cudaStreamDestroy(w.upd);
+    if (w.ev_tile) cudaEventDestroy(w.ev_tile);
+    if (w.ev_mini) cudaEventDestroy(w.ev_mini);
+    if (w.ev_urest) cudaEventDestroy(w.ev_urest);
     if (w.cap) cudaStreamDestroy(w.cap);
     for (int i = 0; i < 2; i++) { if (w.ev_panel[i]) cudaEventDestroy(w.ev_panel[i]); if (w.ev_upd[i]) cudaEventDestroy(w.ev_upd[i]); }
     cudaFree(w.LinvP); cudaFree(w.dinfo); cudaFree(w.kind); cudaFree(w.counts);
@@ -261,8 +281,10 @@ __global__ void __launch_bounds__(TILE_THREADS) ldlt_tile_kernel(double* __restr
                                                                  double* __restrict__ dinv_b, double* __restrict__ d_a,
                                                                  double* __restrict__ d_b, int* __restrict__ kind,
                                                                  int* __restrict__ perm_out, int* __restrict__ counts,
-                                                                 double* __restrict__ dstat, const double pivot_u) {
+                                                                 double* __restrict__ dstat, const double pivot_u,
+                                                                 int* __restrict__ sig) {
     extern __shared__ __align__(16) double tsm[];
+    if (sig != nullptr && threadIdx.x == 0) atomicExch(sig, 1);   // "this far" marker for a delayed background factorisation
     double* Tf = tsm;                 // T[i][m] = Tf[i * NBP + m]   (authoritative only inside slow steps / at the ends)
     double* Xf = tsm + NB * NBP;      // X[i][m] = Xf[i * NBP + m]
     __shared__ double sda[NB], sdb[NB];
@@ -278,6 +300,7 @@ __global__ void __launch_bounds__(TILE_THREADS) ldlt_tile_kernel(double* __restr
     __syncthreads();
     if (s_kp2) return;
     __syncthreads();
+    const int trc = (tid == 0) ? trace_begin(TR_TILE) : -1;
 #ifdef TILE_PROF
     long long tp0 = clock64(), tp1 = 0, tp2 = 0, tp3 = 0;
     int nslow = 0;
@@ -657,6 +680,8 @@ __global__ void __launch_bounds__(TILE_THREADS) ldlt_tile_kernel(double* __restr
             dstat[0] = fmin(dstat[0], mn); dstat[1] = fmax(dstat[1], mx);
         }
     }
+    __syncthreads();
+    trace_end(trc);
 #ifdef TILE_PROF
     __syncthreads();
     tp3 = clock64();
@@ -690,6 +715,7 @@ __global__ void __launch_bounds__(128) ldlt_panel_kernel(double* __restrict__ B,
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, tg = lane & 3;
     const int r0 = blockIdx.x * NB;
+    const int trc = (tid == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) ? trace_begin(TR_PANEL) : -1;
     if (tid < NB) { sia[tid] = dinv_a[tid]; sib[tid] = dinv_b[tid]; skd[tid] = kind[tid]; }
 #pragma unroll
     for (int i = 0; i < 16; i++) {
@@ -744,6 +770,108 @@ __global__ void __launch_bounds__(128) ldlt_panel_kernel(double* __restrict__ B,
             B[(size_t)gr * ld + col] = wv * ia + As[r * P_LDS + nbr] * ibn;
         }
     }
+    trace_end(trc);
+}
+
+// Chain shortcut ("mini" step).  One CTA: the panel computation of ldlt_panel_kernel for the 64 rows right below tile k
+// (W = B LinvP', L = W D^-1, stored exactly as the panel kernel stores them), followed by the update of the NEXT
+// diagonal tile  T -= W L'.  Tile k+1 can then be factored while the rest of panel step k (all other rows, all other
+// tiles of the in-panel update) runs on the update stream: the serial chain per tile step is tile + mini instead of
+// tile + panel + update.
+__global__ void __launch_bounds__(128) ldlt_mini_kernel(double* __restrict__ B, int ld, int rows,
+                                                        const double* __restrict__ LinvP,
+                                                        const double* __restrict__ dinv_a,
+                                                        const double* __restrict__ dinv_b, const int* __restrict__ kind,
+                                                        double* __restrict__ Wout, int ldw, double* __restrict__ T,
+                                                        const int* __restrict__ ctrl) {
+    extern __shared__ __align__(16) double psm[];
+    __shared__ int s_abort;
+    if (threadIdx.x == 0) s_abort = *reinterpret_cast<const volatile int*>(ctrl + 4);
+    __syncthreads();
+    if (s_abort) return;
+    double* As = psm;
+    double* Bs = psm + NB * P_LDS;
+    __shared__ double sia[NB], sib[NB];
+    __shared__ int skd[NB];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, tg = lane & 3;
+    const int nn = min(NB, rows);
+    const int trc = (tid == 0) ? trace_begin(TR_MINI) : -1;
+    if (tid < NB) { sia[tid] = dinv_a[tid]; sib[tid] = dinv_b[tid]; skd[tid] = kind[tid]; }
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const int c = tid + 128 * i;
+        const int row = c >> 5, kc = (c & 31) * 2;
+        const bool ok = row < nn;
+        cp_async16(As + row * P_LDS + kc, ok ? B + (size_t)row * ld + kc : B, ok ? 16 : 0);
+        cp_async16(Bs + row * P_LDS + kc, LinvP + row * NB + kc, 16);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    double acc[2][8][2];
+    const double* as = As + (warp * 16 + g) * P_LDS + tg;
+    const double* bs = Bs + g * P_LDS + tg;
+    auto product = [&]() {
+#pragma unroll
+        for (int a = 0; a < 2; a++)
+#pragma unroll
+            for (int b = 0; b < 8; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
+#pragma unroll
+        for (int kk = 0; kk < 16; kk++) {
+            double af[2], bf[8];
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++) af[mt] = as[mt * 8 * P_LDS + kk * 4];
+#pragma unroll
+            for (int nt = 0; nt < 8; nt++) bf[nt] = bs[nt * 8 * P_LDS + kk * 4];
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                for (int nt = 0; nt < 8; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
+        }
+    };
+    product();                       // W = B * LinvP'
+    __syncthreads();                 // everybody is done reading As / Bs
+#pragma unroll
+    for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+        for (int nt = 0; nt < 8; nt++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) As[(warp * 16 + mt * 8 + g) * P_LDS + nt * 8 + tg * 2 + e] = acc[mt][nt][e];
+    __syncthreads();
+    {
+        const int col = tid & 63;
+        const int k = skd[col];
+        const double ia = sia[col];
+        const double ibn = (k == 1) ? sib[col] : ((k == 2) ? sib[col - 1] : 0.0);
+        const int nbr = (k == 1) ? col + 1 : ((k == 2) ? col - 1 : col);
+#pragma unroll 4
+        for (int i = 0; i < 32; i++) {
+            const int r = (tid >> 6) + 2 * i;
+            const double wv = As[r * P_LDS + col];
+            const double lv = wv * ia + As[r * P_LDS + nbr] * ibn;
+            Bs[r * P_LDS + col] = lv;                 // rows >= nn are exact zeros (zero-filled loads)
+            if (r < nn) {
+                Wout[(size_t)r * ldw + col] = wv;
+                B[(size_t)r * ld + col] = lv;
+            }
+        }
+    }
+    __syncthreads();
+    product();                       // W * L'
+#pragma unroll
+    for (int mt = 0; mt < 2; mt++) {
+        const int i = warp * 16 + mt * 8 + g;
+#pragma unroll
+        for (int nt = 0; nt < 8; nt++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const int j = nt * 8 + tg * 2 + e;
+                if (i < nn && j < nn) T[(size_t)i * ld + j] -= acc[mt][nt][e];
+            }
+    }
+    __syncthreads();
+    trace_end(trc);
 }
 
 __global__ void ldlt_reset_kernel(int* counts, double* dstat, unsigned* ticket) {
@@ -764,9 +892,20 @@ inline int ldlt_set_neg_limit(LdltWs& w, int limit) {
     return 0;
 }
 
+// Bounded device-side wait for the marker above (background factorisation: start only when the foreground one is past
+// its update-heavy first third).  Gives up after ~20 ms so that a missing marker can never hang the stream.
+__global__ void ldlt_wait_sig_kernel(int* sig) {
+    const unsigned long long t0 = trace_now();
+    while (atomicCAS(sig, 1, 0) != 1) {
+        __nanosleep(500);
+        if (trace_now() - t0 > 20000000ull) break;
+    }
+}
+
 inline int ldlt_init_attrs() {
     CU(cudaFuncSetAttribute(ldlt_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM));
     CU(cudaFuncSetAttribute(ldlt_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM));
+    CU(cudaFuncSetAttribute(ldlt_mini_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM));
     CU(cudaFuncSetAttribute(gemm_nt_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM));
     CU(cudaFuncSetAttribute(gemm_nt_sub64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S_SMEM));
     return 0;
@@ -788,25 +927,51 @@ inline int ldlt_factor_launch(LdltWs& w, cudaStream_t st) {
     ldlt_reset_kernel<<<1, 1, 0, st>>>(w.counts, w.dstat, w.ticket);
     LAUNCHED();
     int p = 0;
-    bool side_used = false;
+    bool side_used = false, upd_pending = false;
     for (int c0 = 0; c0 < n; c0 += NBO, p++) {
         const int c1 = min(c0 + NBO, n);
-        double* Wb = (p & 1) ? w.Wp2 : w.Wp;
+        double* Wb = (p % 3 == 0) ? w.Wp : ((p % 3 == 1) ? w.Wp2 : w.Wp3);
         for (int k0 = c0; k0 < c1; k0 += NB) {
             const int k = k0 / NB, nb = min(NB, n - k0), k1 = k0 + nb;
             double* Akk = w.A + (size_t)k0 * ld + k0;
             double* Lk = w.LinvP + (size_t)k * NB * NB;
             ldlt_tile_kernel<<<1, TILE_THREADS, TILE_SMEM, st>>>(Akk, ld, nb, Lk, ia + k0, ib + k0, da + k0, db + k0, w.kind + k0,
-                                                        nullptr, w.counts, w.dstat, w.pivot_u);
+                                                        nullptr, w.counts, w.dstat, w.pivot_u,
+                                                        (k == w.sig_tile) ? w.sig : nullptr);
             LAUNCHED();
             const int rows = n - k1;
             if (rows <= 0) break;
             double* B = w.A + (size_t)k1 * ld + k0;                      // rows below the tile
             double* Wt = Wb + (size_t)k1 * NBO + (k0 - c0);             // W = L * D for this tile step
-            ldlt_panel_kernel<<<cdiv(rows, NB), 128, PANEL_SMEM, st>>>(B, ld, rows, Lk, ia + k0, ib + k0, w.kind + k0, Wt, NBO, w.counts);
-            LAUNCHED();
             const int mcols = c1 - k1;                                   // remaining columns of this outer panel
-            if (mcols > 0) RET(gemm_nt_sub(st, w.A + (size_t)k1 * ld + k1, ld, rows, mcols, Wt, NBO, B, ld, NB, w.counts));
+            double* C11 = w.A + (size_t)k1 * ld + k1;
+            const bool mini = w.use_mini && mcols > 0 && rows >= 2 * NB && gemm_nt_sub_uses_tiles(rows, Wt, NBO, B, ld);
+            if (upd_pending) {   // the chain consumes what the update stream produced for the previous tile step
+                CU(cudaStreamWaitEvent(st, w.ev_urest, 0));
+                upd_pending = false;
+            }
+            if (!mini) {
+                ldlt_panel_kernel<<<cdiv(rows, NB), 128, PANEL_SMEM, st>>>(B, ld, rows, Lk, ia + k0, ib + k0, w.kind + k0, Wt, NBO, w.counts);
+                LAUNCHED();
+                if (mcols > 0) RET(gemm_nt_sub(st, C11, ld, rows, mcols, Wt, NBO, B, ld, NB, w.counts));
+            } else {
+                CU(cudaEventRecord(w.ev_tile, st));
+                ldlt_mini_kernel<<<1, 128, PANEL_SMEM, st>>>(B, ld, rows, Lk, ia + k0, ib + k0, w.kind + k0, Wt, NBO, C11, w.counts);
+                LAUNCHED();
+                CU(cudaEventRecord(w.ev_mini, st));
+                CU(cudaStreamWaitEvent(w.upd, w.ev_tile, 0));
+                ldlt_panel_kernel<<<cdiv(rows - NB, NB), 128, PANEL_SMEM, w.upd>>>(B + (size_t)NB * ld, ld, rows - NB, Lk, ia + k0, ib + k0,
+                                                                                   w.kind + k0, Wt + (size_t)NB * NBO, NBO, w.counts);
+                LAUNCHED();
+                CU(cudaStreamWaitEvent(w.upd, w.ev_mini, 0));
+                RET(gemm_nt_sub(w.upd, C11, ld, rows, mcols, Wt, NBO, B, ld, NB, w.counts, /*skip00=*/1));
+                CU(cudaEventRecord(w.ev_urest, w.upd));
+                upd_pending = true;
+            }
+        }
+        if (upd_pending) {
+            CU(cudaStreamWaitEvent(st, w.ev_urest, 0));
+            upd_pending = false;
         }
         const int rows2 = n - c1;
         if (rows2 <= 0) break;
@@ -814,21 +979,31 @@ inline int ldlt_factor_launch(LdltWs& w, cudaStream_t st) {
         const double* Wpan = Wb + (size_t)c1 * NBO;                      // W rows c1..n of this outer panel
         const double* Lpan = w.A + (size_t)c1 * ld + c0;                 // L rows c1..n
         const int na = min(NBO, rows2);                                  // width of the next outer panel
-        // (a) next panel's columns, main stream: A[c1:, c1:c1+na] -= W L[c1:c1+na]^T.  The side-stream update of the
-        // PREVIOUS panel read-modify-wrote the same columns, so it has to be complete first (this wait also protects
-        // the W buffer panel p+1 is about to overwrite: it was read by that same side-stream update).
-        if (p >= 1 && side_used) CU(cudaStreamWaitEvent(st, w.ev_upd[(p - 1) & 1], 0));
+        // (a) next panel's columns, chain stream: A[c1:, c1:c1+na] -= W L[c1:c1+na]^T.  The same columns were
+        // read-modify-written by the URGENT part of the previous panel's side update, which must be complete.
+        if (p >= 1 && side_used) CU(cudaStreamWaitEvent(st, w.ev_urg[(p - 1) & 1], 0));
         RET(gemm_nt_sub(st, w.A + (size_t)c1 * ld + c1, ld, rows2, na, Wpan, NBO, Lpan, ld, kw, w.counts));
-        // (b) everything to the right of the next panel, side stream (lower tiles only), overlapped with panel p+1
+        // (b) everything to the right of the next panel, side stream, in two pieces: first the columns of the panel
+        // AFTER the next one (urgent: the chain needs them one panel later), then the rest (lower tiles only).  The rest
+        // has two panel periods to finish before anything waits for it (look-ahead depth 2; W is triple buffered).
         const int rows3 = rows2 - na;
         if (rows3 > 0) {
             CU(cudaEventRecord(w.ev_panel[p & 1], st));
             CU(cudaStreamWaitEvent(sd, w.ev_panel[p & 1], 0));
-            GemmArgs u{};
-            u.C = w.A + (size_t)(c1 + na) * ld + (c1 + na); u.ldc = ld; u.Cin = u.C; u.ldcin = ld; u.n = rows3; u.m = rows3;
-            u.beta = 1.0; u.mode = GEMM_LOWER_ONLY; u.nterms = 1; u.ctrl = w.counts; u.max_ctas = w.side_ctas;
-            u.t[0] = GemmTerm{Wpan + (size_t)na * NBO, Lpan + (size_t)na * ld, nullptr, NBO, ld, kw, -1.0};
-            RET(gemm_nt(sd, u));
+            const int na2 = min(NBO, rows3);
+            const int o2 = c1 + na;
+            RET(gemm_nt_sub(sd, w.A + (size_t)o2 * ld + o2, ld, rows3, na2, Wpan + (size_t)na * NBO, NBO, Lpan + (size_t)na * ld, ld, kw,
+                            w.counts));
+            CU(cudaEventRecord(w.ev_urg[p & 1], sd));
+            const int rows4 = rows3 - na2;
+            if (rows4 > 0) {
+                const int o3 = o2 + na2;
+                GemmArgs u{};
+                u.C = w.A + (size_t)o3 * ld + o3; u.ldc = ld; u.Cin = u.C; u.ldcin = ld; u.n = rows4; u.m = rows4;
+                u.beta = 1.0; u.mode = GEMM_LOWER_ONLY; u.nterms = 1; u.ctrl = w.counts; u.max_ctas = w.side_ctas;
+                u.t[0] = GemmTerm{Wpan + (size_t)(na + na2) * NBO, Lpan + (size_t)(na + na2) * ld, nullptr, NBO, ld, kw, -1.0};
+                RET(gemm_nt(sd, u));
+            }
             CU(cudaEventRecord(w.ev_upd[p & 1], sd));
             side_used = true;
         }
@@ -840,7 +1015,7 @@ inline int ldlt_factor_launch(LdltWs& w, cudaStream_t st) {
 // (both streams; fork/join through the events) and replayed: the matrix lives in the same buffers every time, so
 // only the launch overhead changes.  Falls back to direct launches if capture is not possible.
 inline int ldlt_factor(LdltWs& w) {
-    if (w.graph_state == 1 && w.graph_u != w.pivot_u) {   // parameters baked into the graph changed: rebuild
+    if (w.graph_state == 1 && (w.graph_u != w.pivot_u || w.graph_sig_tile != w.sig_tile)) {   // baked parameters changed: rebuild
         cudaGraphExecDestroy(w.gexec);
         w.gexec = nullptr;
         w.graph_state = 0;
@@ -857,6 +1032,7 @@ inline int ldlt_factor(LdltWs& w) {
                 cudaGraphInstantiate(&w.gexec, graph, 0) == cudaSuccess) {
                 w.graph_state = 1;
                 w.graph_u = w.pivot_u;
+                w.graph_sig_tile = w.sig_tile;
                 size_t nn = 0;
                 cudaGraphGetNodes(graph, nullptr, &nn);
                 w.graph_nodes = (int)nn;

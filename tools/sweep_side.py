@@ -6,7 +6,7 @@ from pyipm_b200 import _lib, problems
 
 prob = problems.make_nlp()
 flags = int(sys.argv[1]) if len(sys.argv) > 1 else 6
-for fg, bg in [(0, 0), (128, 64), (112, 48), (112, 32), (96, 48), (96, 32), (128, 32), (0, 48), (112, 0), (80, 40)]:
+for fg, bg in [(96, 48), (0, 0), (128, 64), (128, 96), (112, 112), (0, 96), (96, 96), (64, 64)]:
     os.environ['B200IPM_SIDE_FG'] = str(fg)
     os.environ['B200IPM_SIDE_BG'] = str(bg)
     eng = _lib.Engine(prob.nvar, prob.neq, prob.nineq, _lib.default_params(flags=flags))
