@@ -1059,6 +1059,25 @@ __device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
 }
 
+// Block results are published by VALUE: yv / xv are pre-filled with a NaN sentinel and a consumer polls the entries it
+// needs until they differ from it -- no flag, no fence, one L2 round trip less per step of the serial chain.
+constexpr unsigned long long SOLVE_SENTINEL = 0x7FF8B200DEADBEEFull;
+__device__ __forceinline__ double ld_poll_f64(const double* p) {
+    const long long t0 = clock64();
+    unsigned long long b;
+    do {
+        asm volatile("ld.volatile.global.u64 %0, [%1];\n" : "=l"(b) : "l"(p) : "memory");
+    } while (b == SOLVE_SENTINEL && clock64() - t0 < 200000000LL);   // bounded: never hang the device
+    return __longlong_as_double((long long)b);
+}
+__global__ void ldlt_fill_sentinel_kernel(double* a, double* b, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        a[i] = __longlong_as_double((long long)SOLVE_SENTINEL);
+        b[i] = __longlong_as_double((long long)SOLVE_SENTINEL);
+    }
+}
+
 // forward:  y_i = LinvP_i * (b_i - sum_{j<i} L_ij y_j),  z_i = D_i^-1 y_i
 __global__ void __launch_bounds__(256) ldlt_fwd_kernel(const double* __restrict__ A, int ld, int n, int nblk,
                                                        const double* __restrict__ LinvP, const double* __restrict__ dinv_a,
@@ -1066,7 +1085,7 @@ __global__ void __launch_bounds__(256) ldlt_fwd_kernel(const double* __restrict_
                                                        const double* __restrict__ b, double* yv, double* __restrict__ zv,
                                                        unsigned* flags, unsigned epoch, unsigned* ticket) {
     __shared__ double Ls[NB][NB];   // LinvP_i
-    __shared__ double accv[NB], ys[NB];
+    __shared__ double accv[NB], ys[NB], ybuf[2][NB];
     __shared__ int s_i;
     const int tid = threadIdx.x;
     if (tid == 0) s_i = (int)atomicAdd(ticket, 1u);
@@ -1095,13 +1114,11 @@ __global__ void __launch_bounds__(256) ldlt_fwd_kernel(const double* __restrict_
 #pragma unroll
             for (int c = 0; c < 16; c++) lv[c] = 0.0;
         }
-        if (tid == 0) {
-            while (ld_acquire_u32(flags + j) != epoch) __nanosleep(32);
-        }
+        double* yb = ybuf[j & 1];
+        if (tid < NB) yb[tid] = ld_poll_f64(yv + (size_t)j * NB + tid);
         __syncthreads();
-        const double* yj = yv + (size_t)j * NB + q * 16;
 #pragma unroll
-        for (int c = 0; c < 16; c++) part += lv[c] * __ldcg(yj + c);
+        for (int c = 0; c < 16; c++) part += lv[c] * yb[q * 16 + c];
     }
     part += __shfl_xor_sync(0xffffffffu, part, 1);
     part += __shfl_xor_sync(0xffffffffu, part, 2);
@@ -1114,7 +1131,7 @@ __global__ void __launch_bounds__(256) ldlt_fwd_kernel(const double* __restrict_
     yp += __shfl_xor_sync(0xffffffffu, yp, 2);
     if (q == 0) {
         ys[r] = yp;
-        if (rowok) yv[r0 + r] = yp;
+        yv[r0 + r] = rowok ? yp : 0.0;     // publication (padded rows too: consumers poll whole blocks)
     }
     __syncthreads();
     if (q == 0 && rowok) {
@@ -1125,9 +1142,6 @@ __global__ void __launch_bounds__(256) ldlt_fwd_kernel(const double* __restrict_
         else if (k == 2) z += dinv_b[gidx - 1] * ys[r - 1];
         zv[gidx] = z;
     }
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) st_release_u32(flags + i, epoch);
 }
 
 // backward:  x_i = LinvP_i^T * (z_i - sum_{j>i} L_ji^T x_j)
@@ -1168,11 +1182,7 @@ __global__ void __launch_bounds__(256) ldlt_bwd_kernel(const double* __restrict_
 #pragma unroll
             for (int c = 0; c < 16; c++) lv[c] = 0.0;
         }
-        if (tid == 0) {
-            while (ld_acquire_u32(flags + j) != epoch) __nanosleep(32);
-        }
-        __syncthreads();
-        const double xr = rowok ? __ldcg(xv + gr) : 0.0;
+        const double xr = ld_poll_f64(xv + gr);      // published by the CTA of block row j (zeros in padded rows)
 #pragma unroll
         for (int c = 0; c < 16; c++) pacc[c] += lv[c] * xr;
     }
@@ -1188,11 +1198,8 @@ __global__ void __launch_bounds__(256) ldlt_bwd_kernel(const double* __restrict_
     if (tid < NB) {
         double s = 0.0;
         for (int rr = 0; rr < NB; rr++) s += Ls[rr][tid] * tv[rr];
-        if (c0 + tid < n) xv[c0 + tid] = s;
+        xv[c0 + tid] = (c0 + tid < n) ? s : 0.0;     // publication
     }
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) st_release_u32(flags + i, epoch);
 }
 
 inline int ldlt_init_solve_attrs() {
@@ -1207,6 +1214,8 @@ inline int ldlt_solve(LdltWs& w, const double* b, double* x) {
     double *ia = w.dinfo, *ib = w.dinfo + npad;
     w.epoch++;
     CU(cudaMemsetAsync(w.ticket, 0, sizeof(unsigned) * 2, st));
+    ldlt_fill_sentinel_kernel<<<cdiv((int)npad, 256), 256, 0, st>>>(w.yv, w.xv, (int)npad);
+    LAUNCHED();
     ldlt_fwd_kernel<<<w.nblk, 256, 0, st>>>(w.A, w.ld, w.n, w.nblk, w.LinvP, ia, ib, w.kind, b, w.yv, w.zv, w.flags,
                                             w.epoch, w.ticket);
     LAUNCHED();

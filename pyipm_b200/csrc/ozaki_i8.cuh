@@ -37,7 +37,7 @@ constexpr int OZ_CHUNK = OZ_BM * OZ_KB;      // bytes of one slice of one row bl
 constexpr int OZ_THREADS = 192;
 constexpr unsigned OZ_SMEM_BUDGET = 200 * 1024;
 
-struct OzTerm { const double* A; const double* w; int lda, K, koff, sgn; double alpha; };   // koff: multiple of OZ_KB
+struct OzTerm { const double* A; const double* w; int lda, K, koff, sgn, vec; double alpha; };   // koff: multiple of OZ_KB; vec: 16-byte loads ok
 struct OzSliceArgs {
     OzTerm t[3];
     int nterms, n, nkb;
@@ -65,50 +65,49 @@ __global__ void oz_weight_kernel(const OzSliceArgs a, double* sw) {
     sw[idx] = v;
 }
 
-// ------------------------------------------------------------------------------------------- slicing kernel
-// One CTA per 8-row group (one row of core matrices): pass 1 = row maxima -> exponents, pass 2 = digits.
+// ------------------------------------------------------------------------------------------- slicing kernels
 __device__ __forceinline__ double oz_scaled(const OzTerm& T, const double* __restrict__ sw, int row, int k, bool& neg) {
     const double wk = sw[T.koff + k];
     neg = wk < 0.0;
     return T.A[(size_t)row * T.lda + k] * fabs(wk);
 }
-__global__ void __launch_bounds__(256) oz_slice_kernel(const OzSliceArgs a) {
-    __shared__ int s_exp[8];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int row0 = blockIdx.x * 8;
-    {   // pass 1: warp w scans row row0 + w
-        const int row = row0 + warp;
-        double m = 0.0;
-        bool bad = false;
-        if (row < a.n) {
-            for (int t = 0; t < a.nterms; t++) {
-                const OzTerm T = a.t[t];
-                for (int k = lane; k < T.K; k += 32) {
-                    bool ng;
-                    const double v = fabs(oz_scaled(T, a.sw, row, k, ng));
-                    if (!(v <= 1.7e308)) bad = true;      // inf / nan
-                    m = fmax(m, v);
-                }
-            }
-        }
-        m = warp_max(m);
-        bad = __any_sync(0xffffffffu, bad);
-        if (lane == 0) {
-            int e = 0;
-            if (m > 0.0 && !bad) e = ilogb(m) + 1;        // |L| * 2^-e < 1
-            s_exp[warp] = e;
-            if (row < a.n) a.rexp[row] = e;
-            if (bad) atomicOr(a.err, 1);
+// pass 1: one warp per row -> exponent e_i with |L[i, :]| * 2^-e_i < 1
+__global__ void __launch_bounds__(128) oz_rowmax_kernel(const OzSliceArgs a) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int row = blockIdx.x * 4 + warp;
+    if (row >= a.n) return;
+    double m = 0.0;
+    bool bad = false;
+    for (int t = 0; t < a.nterms; t++) {
+        const OzTerm T = a.t[t];
+        const double* __restrict__ ar = T.A + (size_t)row * T.lda;
+        const double* __restrict__ sw = a.sw + T.koff;
+        for (int k = lane; k < T.K; k += 32) {
+            const double v = fabs(ar[k] * sw[k]);
+            if (!(v <= 1.7e308)) bad = true;      // inf / nan
+            m = fmax(m, v);
         }
     }
-    __syncthreads();
-    // pass 2: thread = (row r of the group, 16-element k-chunk); 8 consecutive threads write one 128-byte core matrix
+    m = warp_max(m);
+    bad = __any_sync(0xffffffffu, bad);
+    if (lane == 0) {
+        a.rexp[row] = (m > 0.0 && !bad) ? ilogb(m) + 1 : 0;
+        if (bad) atomicOr(a.err, 1);
+    }
+}
+// pass 2: CTA = (8-row group, k-range); thread = (row r of the group, 16-element k-chunk); 8 consecutive threads write
+// one 128-byte core matrix per slice
+__global__ void __launch_bounds__(256) oz_slice_kernel(const OzSliceArgs a) {
+    const int tid = threadIdx.x;
+    const int row0 = blockIdx.x * 8;
     const int r = tid & 7;
     const int row = row0 + r;
-    const int e = s_exp[r];
+    const int e = (row < a.n) ? a.rexp[row] : 0;
     const int rb = row0 / OZ_BM, g = (row0 % OZ_BM) / 8;
     const int nchunks = a.nkb * 2;
-    for (int cc = tid >> 3; cc < nchunks; cc += 32) {
+    const int per = (nchunks + gridDim.y - 1) / gridDim.y;
+    const int c_lo = blockIdx.y * per, c_hi = min(nchunks, c_lo + per);
+    for (int cc = c_lo + (tid >> 3); cc < c_hi; cc += 32) {
         const int k0 = cc * 16;
         int t = -1;
         for (int u = 0; u < a.nterms; u++)
@@ -120,12 +119,26 @@ __global__ void __launch_bounds__(256) oz_slice_kernel(const OzSliceArgs a) {
         if (t >= 0 && row < a.n) {
             const OzTerm T = a.t[t];
             const int kl = k0 - T.koff;
+            const double* __restrict__ ar = T.A + (size_t)row * T.lda + kl;
+            const double* __restrict__ sw = a.sw + k0;
+            if (T.vec && kl + 16 <= T.K) {
 #pragma unroll
-            for (int b = 0; b < 16; b++) {
-                if (kl + b < T.K) {
-                    bool ng;
-                    v[b] = oz_scaled(T, a.sw, row, kl + b, ng);
-                    if (ng) negmask |= 1u << b;
+                for (int b = 0; b < 16; b += 2) {
+                    const double2 x = *reinterpret_cast<const double2*>(ar + b);
+                    const double2 w = *reinterpret_cast<const double2*>(sw + b);
+                    v[b] = x.x * fabs(w.x);
+                    v[b + 1] = x.y * fabs(w.y);
+                    if (w.x < 0.0) negmask |= 1u << b;
+                    if (w.y < 0.0) negmask |= 2u << b;
+                }
+            } else {
+#pragma unroll
+                for (int b = 0; b < 16; b++) {
+                    if (kl + b < T.K) {
+                        const double w = sw[b];
+                        v[b] = ar[b] * fabs(w);
+                        if (w < 0.0) negmask |= 1u << b;
+                    }
                 }
             }
         }
@@ -517,7 +530,8 @@ inline int oz_syrk(cudaStream_t st, const GemmArgs& a, OzWs& w, unsigned may_be_
     for (int t = 0; t < a.nterms; t++) {
         if (a.t[t].A != a.t[t].B || a.t[t].lda != a.t[t].ldb) return fail_msg("oz_syrk: terms must be A diag(w) A'");
         const int sg = (may_be_negative >> t) & 1u;
-        s.t[t] = OzTerm{a.t[t].A, a.t[t].w, a.t[t].lda, a.t[t].K, koff, sg, a.t[t].alpha};
+        const int vec = (!(a.t[t].lda & 1) && !(reinterpret_cast<uintptr_t>(a.t[t].A) & 15)) ? 1 : 0;
+        s.t[t] = OzTerm{a.t[t].A, a.t[t].w, a.t[t].lda, a.t[t].K, koff, sg, vec, a.t[t].alpha};
         koff += (int)rup((size_t)a.t[t].K, OZ_KB);
         g.kb_end[t] = koff / OZ_KB;
         g.sgn[t] = sg;
@@ -565,7 +579,9 @@ inline int oz_syrk(cudaStream_t st, const GemmArgs& a, OzWs& w, unsigned may_be_
     if (!w.reuse_slices) {
         oz_weight_kernel<<<cdiv(nkb * OZ_KB, 256), 256, 0, st>>>(s, w.sw);
         LAUNCHED();
-        oz_slice_kernel<<<nrb * (OZ_BM / 8), 256, 0, st>>>(s);
+        oz_rowmax_kernel<<<cdiv(a.n, 4), 128, 0, st>>>(s);
+        LAUNCHED();
+        oz_slice_kernel<<<dim3(nrb * (OZ_BM / 8), std::max(1, std::min(8, nkb / 16))), 256, 0, st>>>(s);
         LAUNCHED();
     }
     if (w.ev[1]) CU(cudaEventRecord(w.ev[1], st));
