@@ -8,7 +8,10 @@ KEYS = ['gpu__time_duration.sum', 'launch__grid_size', 'launch__block_size', 'la
         'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'sm__warps_active.avg.pct_of_peak_sustained_active',
         'lts__t_sector_hit_rate.pct', 'smsp__inst_executed.sum', 'sm__inst_executed.avg.per_cycle_active',
         'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'dram__bytes_read.sum.per_second',
-        'smsp__average_warp_latency_per_inst_issued.ratio']
+        'smsp__average_warp_latency_per_inst_issued.ratio', 'gpc__cycles_elapsed.avg.per_second',
+        'l1tex__m_xbar2l1tex_read_bytes_mem_global_op_tma_ld.sum', 'l1tex__m_xbar2l1tex_read_bytes_mem_global_op_tma_ld.sum.per_second',
+        'l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed', 'sm__inst_executed_pipe_uniform.sum',
+        'launch__shared_mem_per_block_dynamic', 'launch__occupancy_limit_shared_mem']
 
 
 def main(rep, title):
