@@ -44,6 +44,8 @@ typedef struct b200ipm_params {
 #define B200IPM_FLAG_NO_SPECULATION 1
 #define B200IPM_FLAG_DELAY_BG       32  /* start the background inertia test only when the foreground factorisation is past
                                            its first third (measured: no net gain at config 3, off by default) */
+#define B200IPM_FLAG_NO_CERT        64  /* never replace the delta = 0 inertia test by a negative-curvature certificate
+                                           (then the test itself runs in the background) */
 #define B200IPM_FLAG_NO_ABANDON     16  /* always complete a failed inertia test (n_neg_first is then the full count) */
 #define B200IPM_FLAG_TCGEN05_SYRK   2   /* d2L and condensation contractions on tcgen05 (int8 error-free split) */
 #define B200IPM_FLAG_TCGEN05_TILE(v) ((v) << 2)   /* with TCGEN05_SYRK: 0 = 128x64 tiles / 1 pass, 1 = 128x128 / 2, 2 = 128x256 / 4 */
@@ -58,7 +60,8 @@ typedef struct b200ipm_step_info {
     double alpha_s, alpha_l;         /* accepted step lengths (pyipm.py:1507-1510,1553-1562) */
     double alpha_corr;               /* second-order-correction scaling, 0 if none */
     double phi0, dphi0;              /* merit value / directional derivative at the old point */
-    double rcond;                    /* reciprocal-condition estimate used for the pyipm.py:1381 test */
+    double rcond;                    /* reciprocal-condition estimate used for the pyipm.py:1381 test (-1: the test was
+                                        replaced by a certificate, see cert_used) */
     double resid;                    /* || b - K dz ||_inf of the unreduced system after refinement */
     double con_l1;                   /* ||con||_1 at the old point (pyipm.py:1732) */
     int    n_neg, n_zero;            /* inertia of the accepted condensed KKT matrix */
@@ -77,6 +80,9 @@ typedef struct b200ipm_step_info {
                                         a fallback because of non-finite inputs / unexpected negative weights) */
     int    abandoned_first;          /* 1 if the delta = 0 inertia test was abandoned on the device as soon as it had
                                         more than M negative pivots (n_neg_first is then a partial count) */
+    int    cert_used;                /* 1 if the failure of the delta = 0 test was PROVEN by a negative-curvature vector in
+                                        null(dce') instead of being computed (n_neg_first = -1) */
+    int    reserved;
 } b200ipm_step_info;
 
 int         b200ipm_version(void);
@@ -210,7 +216,8 @@ int b200ipm_test_gemv(int rows, int cols, const double* A, const double* v, doub
  * kernels stamp %globaltimer (ns) at entry/exit; trace_dump copies up to `max` records (kernel id 1 tile, 2 panel,
  * 3 mini, 4 in-panel update, 5 DMMA trailing update; CTA index; t0; t1) to the host and switches the trace off. */
 int b200ipm_trace_start(void);
-int b200ipm_trace_dump(int* id, int* blk, unsigned long long* t0, unsigned long long* t1, int max, int* n);
+int b200ipm_trace_dump(int* id, int* blk, unsigned long long* t0, unsigned long long* t1, unsigned long long* tag,
+                       int max, int* n);   /* tag = control block of the factorisation a record belongs to */
 /* Same product as b200ipm_test_syrk, computed on the tcgen05 tensor cores by the int8 error-free (Ozaki) path:
  * signed_mask bit t = alpha_t*w_t may be negative; variant 0 = 128x64 tiles / one pass, 1 = 128x128 tiles / two
  * passes, 2 = 128x256 / four; lbo, sbo <= 0 keep the default shared-memory descriptor strides; ms[2] = {slicing ms,

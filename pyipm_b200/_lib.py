@@ -38,7 +38,7 @@ class StepInfo(C.Structure):
                 ('ms_eval', C.c_float), ('ms_assemble', C.c_float), ('ms_factor', C.c_float), ('ms_solve', C.c_float),
                 ('ms_search', C.c_float), ('ms_total', C.c_float), ('ms_hess_kernel', C.c_float),
                 ('ms_condense_kernel', C.c_float), ('n_spec', C.c_int), ('spec_used', C.c_int),
-                ('tc_syrk', C.c_int), ('abandoned_first', C.c_int)]
+                ('tc_syrk', C.c_int), ('abandoned_first', C.c_int), ('cert_used', C.c_int), ('reserved', C.c_int)]
 
     def asdict(self):
         d = {}
@@ -50,7 +50,7 @@ class StepInfo(C.Structure):
 
 # b200ipm_params.flags used when the caller does not choose: the two dense contractions on tcgen05 (error-free int8
 # split, 128x128 tiles), speculative + abandoning reghess.  0 = fp64 DMMA contractions.
-FLAG_NO_SPECULATION, FLAG_TCGEN05_SYRK, FLAG_NO_ABANDON = 1, 2, 16
+FLAG_NO_SPECULATION, FLAG_TCGEN05_SYRK, FLAG_NO_ABANDON, FLAG_DELAY_BG, FLAG_NO_CERT = 1, 2, 16, 32, 64
 DEFAULT_FLAGS = FLAG_TCGEN05_SYRK | (1 << 2)
 
 # every symbol include/b200ipm.h declares (tests/test_abi.py checks the library exports exactly these)
@@ -130,7 +130,7 @@ def load():
                                      C.POINTER(C.c_float), ip]),
         'b200ipm_test_gemv': (i, [i, i, vp, vp, vp, i]),
         'b200ipm_trace_start': (i, []),
-        'b200ipm_trace_dump': (i, [vp, vp, vp, vp, i, ip]),
+        'b200ipm_trace_dump': (i, [vp, vp, vp, vp, vp, i, ip]),
     }
     for name in SYMBOLS:
         fn = getattr(lib, name)   # AttributeError if the library does not export it
@@ -403,15 +403,16 @@ def trace_start():
 
 
 def trace_dump(maxrec=65536):
-    """-> structured array (id, blk, t0, t1) of the device-side timeline records since trace_start()"""
+    """-> (id, blk, t0, t1, tag) arrays of the device-side timeline records since trace_start()"""
     ids = np.zeros(maxrec, dtype=np.int32)
     blk = np.zeros(maxrec, dtype=np.int32)
     t0 = np.zeros(maxrec, dtype=np.uint64)
     t1 = np.zeros(maxrec, dtype=np.uint64)
+    tag = np.zeros(maxrec, dtype=np.uint64)
     n = C.c_int(0)
-    check(load().b200ipm_trace_dump(ptr(ids), ptr(blk), ptr(t0), ptr(t1), int(maxrec), C.byref(n)))
+    check(load().b200ipm_trace_dump(ptr(ids), ptr(blk), ptr(t0), ptr(t1), ptr(tag), int(maxrec), C.byref(n)))
     k = n.value
-    return ids[:k], blk[:k], t0[:k].astype(np.int64), t1[:k].astype(np.int64)
+    return ids[:k], blk[:k], t0[:k].astype(np.int64), t1[:k].astype(np.int64), tag[:k]
 
 
 def test_gemv(A, v, transpose=False):

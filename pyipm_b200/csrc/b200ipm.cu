@@ -55,6 +55,13 @@ struct b200ipm_engine {
     bool Fb_ready = false;
     cudaStream_t stB = nullptr;
     cudaEvent_t ev_fork = nullptr;
+    // negative-curvature certificate (replaces the background delta = 0 factorisation in the common case)
+    LdltSolveBuf csb;        // second set of solve vectors: the certificate solve runs beside the main solve
+    double *c_rhs = nullptr, *c_sol = nullptr, *c_hv = nullptr, *c_u = nullptr, *c_red = nullptr;
+    double* h_cert = nullptr;   // pinned: 2 x (v'Hv, v'v, Hv'Hv)
+    bool cert_ready = false, cert_pending = false;
+    bool first_failed_last = true;   // did the delta = 0 test of the previous step fail?  (speculate only then)
+    int n_cert_ok = 0, n_cert_miss = 0;
     int* d_sig = nullptr;    // marker word: foreground factorisation -> delayed start of the background one
     bool pendingA = false;   // the background delta = 0 test has not been collected yet
     double pend_delta_in = 0, pend_rcondB = 0;
@@ -268,8 +275,10 @@ static int spec_launch_background(Eng* h, int neg_limit) {
     if (!h->Fb_ready) {
         int prio_lo = 0, prio_hi = 0;
         CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-        CU(cudaStreamCreateWithPriority(&h->stB, cudaStreamNonBlocking, prio_lo));
-        CU(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+        if (!h->stB) {
+            CU(cudaStreamCreateWithPriority(&h->stB, cudaStreamNonBlocking, prio_lo));
+            CU(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+        }
         CU(cudaMallocHost(&h->h_cntB, sizeof(int) * 8));
         CU(cudaMallocHost(&h->h_dsB, sizeof(double) * 2));
         RET(ldlt_alloc(h->Fb, h->Kc, h->stB, /*background=*/true));
@@ -295,6 +304,55 @@ static int spec_launch_background(Eng* h, int neg_limit) {
     RET(ldlt_factor(h->Fb));
     CU(cudaMemcpyAsync(h->h_cntB, h->Fb.counts, sizeof(int) * 8, cudaMemcpyDeviceToHost, h->stB));
     CU(cudaMemcpyAsync(h->h_dsB, h->Fb.dstat, sizeof(double) * 2, cudaMemcpyDeviceToHost, h->stB));
+    return 0;
+}
+// Certificate that the delta = 0 inertia test FAILS, without factoring the unshifted matrix.
+// The condensed matrix [[Hb, dce], [dce', 0]] has inertia (D, M, 0) iff dce has full column rank and Hb is positive
+// definite on null(dce').  With the accepted factorisation of B = [[Hb + delta1 I, dce], [dce', 0]] at hand, one
+// solve  B [v; y] = [u; 0]  gives a vector v in null(dce') rich in the lowest modes of the reduced Hessian (inverse
+// iteration, warm-started from the previous Newton step); if  v' Hb v < 0  by a safe margin the reduced Hessian is
+// not positive definite, so the reference's first test (pyipm.py:1381) fails -- a proof, not a heuristic.  Two
+// iterations run on the background stream beside the main solve.  No certificate (e.g. the problem has become
+// convex) => the caller falls back to the plain sequential loop.  The rcond <= eps branch of the failed test cannot
+// be seen this way; it needs a numerically singular unshifted matrix while the shifted one is accepted with full-rank
+// dce, and is treated as not taken.
+static int cert_launch(Eng* h) {
+    const int D = h->D, Kc = h->Kc;
+    if (!h->cert_ready) {
+        if (!h->stB) {
+            int prio_lo = 0, prio_hi = 0;
+            CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+            CU(cudaStreamCreateWithPriority(&h->stB, cudaStreamNonBlocking, prio_lo));
+            CU(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+        }
+        RET(ldlt_solvebuf_alloc(h->csb, h->F.nblk));
+        RET(dalloc(&h->c_rhs, Kc)); RET(dalloc(&h->c_sol, Kc)); RET(dalloc(&h->c_hv, D)); RET(dalloc(&h->c_u, D));
+        RET(dalloc(&h->c_red, 8));
+        CU(cudaMallocHost(&h->h_cert, sizeof(double) * 8));
+        std::vector<double> u0(D);
+        unsigned long long sd = 0x9E3779B97F4A7C15ull;
+        for (int i = 0; i < D; i++) {   // fixed pseudo-random start vector (splitmix64)
+            sd += 0x9E3779B97F4A7C15ull;
+            unsigned long long z = sd;
+            z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+            z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+            z ^= z >> 31;
+            u0[i] = (double)(z >> 11) * (1.0 / 9007199254740992.0) - 0.5;
+        }
+        CU(cudaMemcpy(h->c_u, u0.data(), sizeof(double) * D, cudaMemcpyHostToDevice));
+        h->cert_ready = true;
+    }
+    CU(cudaEventRecord(h->ev_fork, h->st));          // the factorisation and Hb are complete on the main stream
+    CU(cudaStreamWaitEvent(h->stB, h->ev_fork, 0));
+    for (int it = 0; it < 2; it++) {
+        cert_rhs_kernel<<<cdiv(Kc, 256), 256, 0, h->stB>>>(D, Kc, h->c_u, h->c_rhs);
+        LAUNCHED();
+        RET(ldlt_solve_on(h->F, h->stB, h->csb, h->c_rhs, h->c_sol));
+        RET(gemv_n(h->stB, h->Hb, h->ldW, D, D, h->c_sol, nullptr, 0.0, 1.0, h->c_hv));
+        cert_stats_kernel<<<1, 1024, 0, h->stB>>>(D, h->c_sol, h->c_hv, h->c_u, h->c_red + 3 * it);
+        LAUNCHED();
+    }
+    CU(cudaMemcpyAsync(h->h_cert, h->c_red, sizeof(double) * 6, cudaMemcpyDeviceToHost, h->stB));
     return 0;
 }
 // One inertia test = one factorisation.  `neg_limit`: the test can only pass with exactly M negative pivots, so a
@@ -336,19 +394,23 @@ static int factor_regularised(Eng* h, b200ipm_step_info* info, bool allow_abando
     int n_neg = 0, n_zero = 0, nfac = 0, ab_first = 0, ab = 0;
     double rcond = 0.0, rcond0 = 0.0;
     const double delta1 = (h->delta == 0.0) ? h->p.reg_coef : std::max(h->delta / 2.0, h->p.reg_coef);
-    const bool spec = allow_spec && (h->delta > 0.0) && !(h->p.flags & B200IPM_FLAG_NO_SPECULATION) && !h->strict_retry;
+    const bool spec = allow_spec && (h->delta > 0.0) && !(h->p.flags & B200IPM_FLAG_NO_SPECULATION) && !h->strict_retry &&
+                      h->first_failed_last;
     int eq_reg = 0;
     bool redo = false, first_failed = false;
     double reg = 0.0;
     h->pendingA = false;
+    const bool use_cert = spec && !(h->p.flags & B200IPM_FLAG_NO_CERT);
     if (spec) {
-        RET(spec_launch_background(h, limit));                                   // A: delta = 0, background
+        if (!use_cert) RET(spec_launch_background(h, limit));                    // A: delta = 0, background
         RET(factor_once(h, delta1, 0.0, limit, &n_neg, &n_zero, &rcond, &ab));  // B: the expected candidate
         nfac = 2;
-        if (n_neg == M) {
-            // proceed with B; A's verdict is collected by resolve_pending() after the solve
+        if (n_neg == M && !(use_cert && rcond <= h->p.eps)) {
+            // proceed with B; A's verdict (or the proof that it fails) is collected by resolve_pending() after the solve
             h->delta = delta1;
             h->pendingA = true;
+            h->cert_pending = use_cert;
+            if (use_cert) RET(cert_launch(h));
             h->pend_delta_in = delta_in;
             h->pend_rcondB = rcond;
             if (info) {
@@ -356,6 +418,10 @@ static int factor_regularised(Eng* h, b200ipm_step_info* info, bool allow_abando
                 info->n_spec = 1; info->spec_used = 1;
             }
             return 0;
+        }
+        if (use_cert) {   // B failed and A was never started: the plain loop from the incoming delta
+            h->delta = delta_in;
+            return factor_regularised(h, info, allow_abandon, false);
         }
         // B failed too: A's verdict is needed now to continue the reference's sequence
         int nA = 0, zA = 0;
@@ -379,6 +445,7 @@ static int factor_regularised(Eng* h, b200ipm_step_info* info, bool allow_abando
         RET(factor_once(h, 0.0, 0.0, limit, &n_neg, &n_zero, &rcond, &ab_first));
         nfac = 1;
         rcond0 = rcond;
+        h->first_failed_last = (rcond <= h->p.eps || n_neg != M);
         if (info) { info->n_neg_first = n_neg; info->n_zero_first = n_zero; }
         if (rcond <= h->p.eps || n_neg != M) {
             first_failed = true;
@@ -424,6 +491,29 @@ static int resolve_pending(Eng* h, b200ipm_step_info* info, bool* redo) {
     if (!h->pendingA) return 0;
     h->pendingA = false;
     CU(cudaStreamSynchronize(h->stB));
+    if (h->cert_pending) {
+        h->cert_pending = false;
+        bool proven = false;
+        for (int it = 0; it < 2 && !proven; it++) {
+            const double q = h->h_cert[3 * it], nv = h->h_cert[3 * it + 1], hn = h->h_cert[3 * it + 2];
+            if (!(nv > 0.0) || !(hn >= 0.0) || !(fabs(q) <= 1.7e308)) continue;
+            const double rho = q / nv;                              // Rayleigh quotient of Hb on null(dce')
+            const double scale = std::max(sqrt(hn / nv), h->delta_eff);
+            if (rho < -1e-7 * scale) proven = true;
+        }
+        if (info) { info->n_neg_first = -1; info->n_zero_first = -1; info->rcond = -1.0; info->abandoned_first = 0; info->cert_used = proven ? 1 : 0; }
+        if (proven) {
+            h->n_cert_ok++;
+            h->first_failed_last = true;
+            return 0;
+        }
+        // no proof (cold start vector, shift much larger than the negative curvature, or the problem has become
+        // convex): run the delta = 0 test itself now, keeping the candidate's factorisation, and judge it below
+        h->n_cert_miss++;
+        const int limit = (h->p.flags & B200IPM_FLAG_NO_ABANDON) ? 0x7fffffff : h->M;
+        RET(spec_launch_background(h, limit));
+        CU(cudaStreamSynchronize(h->stB));
+    }
     int nA = 0, zA = 0, abA = 0;
     double rcA = 0.0;
     background_verdict(h, &nA, &zA, &rcA, &abA);
@@ -431,6 +521,7 @@ static int resolve_pending(Eng* h, b200ipm_step_info* info, bool* redo) {
     const bool a_fails = (rcA <= h->p.eps || nA != h->M);
     const bool a_eqreg = (rcA <= h->p.eps && h->M);
     const bool hidden_singular = abA && (h->pend_rcondB <= h->p.eps);
+    h->first_failed_last = a_fails;
     if (a_fails && !a_eqreg && !hidden_singular) return 0;
     h->delta = h->pend_delta_in;
     *redo = true;
@@ -495,6 +586,7 @@ static int solve_direction(Eng* h, b200ipm_step_info* info) {
     // threshold) re-factorisation of the same matrix and a fresh solve
     RET(fetch_red(h, h->red + 8, 1));
     if (!(h->h_red[0] <= 1e-7 * std::max(1.0, bnorm)) && h->F.pivot_u < 0.64 && !h->strict_retry) {
+        if (h->pendingA && h->stB) CU(cudaStreamSynchronize(h->stB));   // the certificate solve reads this factorisation
         const double u_save = h->F.pivot_u;
         h->F.pivot_u = 0.6403882032022076;
         h->strict_retry = true;
@@ -906,16 +998,23 @@ int b200ipm_destroy(b200ipm_handle h) {
     for (double* b : bufs) cudaFree(b);
     cudaFree(h->p_rowptr); cudaFree(h->p_ptr); cudaFree(h->p_fvar); cudaFree(h->p_fpow); cudaFree(h->d_sig);
     cudaFreeHost(h->h_red);
+    if (h->stB) cudaStreamSynchronize(h->stB);
+    if (h->cert_ready) {
+        ldlt_solvebuf_free(h->csb);
+        cudaFree(h->c_rhs); cudaFree(h->c_sol); cudaFree(h->c_hv); cudaFree(h->c_u); cudaFree(h->c_red);
+        cudaFreeHost(h->h_cert);
+    }
     ldlt_free(h->F);
     oz_free(h->oz);
     if (h->F2_ready) ldlt_free(h->F2);
     if (h->Fb_ready) {
-        cudaStreamSynchronize(h->stB);
         ldlt_free(h->Fb);
-        cudaStreamDestroy(h->stB);
-        cudaEventDestroy(h->ev_fork);
         cudaFreeHost(h->h_cntB);
         cudaFreeHost(h->h_dsB);
+    }
+    if (h->stB) {
+        cudaStreamDestroy(h->stB);
+        cudaEventDestroy(h->ev_fork);
     }
     for (int i = 0; i < EV_N; i++) cudaEventDestroy(h->ev[i]);
     if (h->own_stream) cudaStreamDestroy(h->st);
@@ -1566,7 +1665,8 @@ int b200ipm_trace_start(void) {
     CU(cudaMemcpyToSymbol(g_trace, &g_trace_host_ptr, sizeof(TraceRec*)));
     return 0;
 }
-int b200ipm_trace_dump(int* id, int* blk, unsigned long long* t0, unsigned long long* t1, int max, int* n) {
+int b200ipm_trace_dump(int* id, int* blk, unsigned long long* t0, unsigned long long* t1, unsigned long long* tag, int max,
+                       int* n) {
     CU(cudaDeviceSynchronize());
     TraceRec* nullp = nullptr;
     CU(cudaMemcpyToSymbol(g_trace, &nullp, sizeof(TraceRec*)));
@@ -1575,7 +1675,10 @@ int b200ipm_trace_dump(int* id, int* blk, unsigned long long* t0, unsigned long 
     cnt = std::min(cnt, std::min(max, TRACE_CAP));
     std::vector<TraceRec> h(std::max(cnt, 1));
     if (cnt && g_trace_host_ptr) CU(cudaMemcpy(h.data(), g_trace_host_ptr, sizeof(TraceRec) * cnt, cudaMemcpyDeviceToHost));
-    for (int i = 0; i < cnt; i++) { id[i] = h[i].id; blk[i] = h[i].blk; t0[i] = h[i].t0; t1[i] = h[i].t1; }
+    for (int i = 0; i < cnt; i++) {
+        id[i] = h[i].id; blk[i] = h[i].blk; t0[i] = h[i].t0; t1[i] = h[i].t1;
+        if (tag) tag[i] = h[i].tag;
+    }
     if (n) *n = cnt;
     return 0;
 }

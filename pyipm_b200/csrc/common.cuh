@@ -50,7 +50,7 @@ static inline size_t rup(size_t a, size_t b) { return (a + b - 1) / b * b; }
 // ------------------------------------------------------------------------------------ device-side timeline trace
 // Profiling aid (b200ipm_trace_start / b200ipm_trace_dump): when enabled, selected CTAs of the factorisation kernels
 // stamp %globaltimer at entry and exit.  Disabled (null pointer) it costs one global load per kernel.
-struct TraceRec { int id, blk; unsigned long long t0, t1; };
+struct TraceRec { int id, blk; unsigned long long t0, t1; unsigned long long tag; };
 constexpr int TRACE_CAP = 1 << 16;
 __device__ TraceRec* g_trace = nullptr;
 __device__ int g_trace_n = 0;
@@ -59,7 +59,7 @@ __device__ __forceinline__ unsigned long long trace_now() {
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
 }
-__device__ __forceinline__ int trace_begin(int id) {
+__device__ __forceinline__ int trace_begin(int id, const void* tag = nullptr) {
     TraceRec* t = g_trace;
     if (!t) return -1;
     const int i = atomicAdd(&g_trace_n, 1);
@@ -68,6 +68,7 @@ __device__ __forceinline__ int trace_begin(int id) {
     t[i].blk = (int)(blockIdx.x + blockIdx.y * gridDim.x);
     t[i].t0 = trace_now();
     t[i].t1 = 0;
+    t[i].tag = (unsigned long long)tag;     // e.g. the control block of the factorisation the kernel belongs to
     return i;
 }
 __device__ __forceinline__ void trace_end(int i) {

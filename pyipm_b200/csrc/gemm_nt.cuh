@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_nt_dmma_kernel(const GemmAr
         if (s_abort) return;
     }
     const int trc = (threadIdx.x == 0 && ((blockIdx.x == 0 && blockIdx.y == 0) || (blockIdx.x == gridDim.x - 1 && blockIdx.y == gridDim.y - 1)))
-                        ? trace_begin(TR_DMMA) : -1;
+                        ? trace_begin(TR_DMMA, a.ctrl) : -1;
     if (a.persistent_tiles > 0) {
         // lower-triangular tile t -> (r, c) with c <= r, row by row
         for (int t = blockIdx.x; t < a.persistent_tiles; t += gridDim.x) {
@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(128, 2) gemm_nt_sub64_kernel(double* __restric
     extern __shared__ __align__(16) double s_smem[];
     if (skip00 && blockIdx.x == 0 && blockIdx.y == 0) return;   // that tile was already updated on the chain stream
     const int trc = (threadIdx.x == 0 && ((blockIdx.x == 1 && blockIdx.y == 0) || (blockIdx.x == gridDim.x - 1 && blockIdx.y == gridDim.y - 1)))
-                        ? trace_begin(TR_SUB64) : -1;
+                        ? trace_begin(TR_SUB64, ctrl) : -1;
     if (ctrl) {
         __shared__ int s_abort;
         if (threadIdx.x == 0) s_abort = *reinterpret_cast<const volatile int*>(ctrl + 4);

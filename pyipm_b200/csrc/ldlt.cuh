@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(TILE_THREADS) ldlt_tile_kernel(double* __restr
     __syncthreads();
     if (s_kp2) return;
     __syncthreads();
-    const int trc = (tid == 0) ? trace_begin(TR_TILE) : -1;
+    const int trc = (tid == 0) ? trace_begin(TR_TILE, counts) : -1;
 #ifdef TILE_PROF
     long long tp0 = clock64(), tp1 = 0, tp2 = 0, tp3 = 0;
     int nslow = 0;
@@ -715,7 +715,7 @@ __global__ void __launch_bounds__(128) ldlt_panel_kernel(double* __restrict__ B,
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, tg = lane & 3;
     const int r0 = blockIdx.x * NB;
-    const int trc = (tid == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) ? trace_begin(TR_PANEL) : -1;
+    const int trc = (tid == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) ? trace_begin(TR_PANEL, ctrl) : -1;
     if (tid < NB) { sia[tid] = dinv_a[tid]; sib[tid] = dinv_b[tid]; skd[tid] = kind[tid]; }
 #pragma unroll
     for (int i = 0; i < 16; i++) {
@@ -796,7 +796,7 @@ __global__ void __launch_bounds__(128) ldlt_mini_kernel(double* __restrict__ B, 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, tg = lane & 3;
     const int nn = min(NB, rows);
-    const int trc = (tid == 0) ? trace_begin(TR_MINI) : -1;
+    const int trc = (tid == 0) ? trace_begin(TR_MINI, ctrl) : -1;
     if (tid < NB) { sia[tid] = dinv_a[tid]; sib[tid] = dinv_b[tid]; skd[tid] = kind[tid]; }
 #pragma unroll
     for (int i = 0; i < 16; i++) {
@@ -1207,23 +1207,41 @@ inline int ldlt_init_solve_attrs() {
     return 0;
 }
 
+// Work vectors of one triangular solve; a second set lets two solves with the SAME factorisation run concurrently on
+// two streams (the factor is only read).
+struct LdltSolveBuf { double *yv = nullptr, *zv = nullptr, *xv = nullptr; unsigned* ticket = nullptr; };
+inline int ldlt_solvebuf_alloc(LdltSolveBuf& sb, int nblk) {
+    const size_t npad = (size_t)nblk * NB;
+    CU(cudaMalloc(&sb.yv, sizeof(double) * npad));
+    CU(cudaMalloc(&sb.zv, sizeof(double) * npad));
+    CU(cudaMalloc(&sb.xv, sizeof(double) * npad));
+    CU(cudaMalloc(&sb.ticket, sizeof(unsigned) * 2));
+    return 0;
+}
+inline void ldlt_solvebuf_free(LdltSolveBuf& sb) {
+    cudaFree(sb.yv); cudaFree(sb.zv); cudaFree(sb.xv); cudaFree(sb.ticket);
+    sb = LdltSolveBuf();
+}
 // x = A^-1 b using the factorisation in w; b and x are device vectors of length n (may alias)
-inline int ldlt_solve(LdltWs& w, const double* b, double* x) {
-    cudaStream_t st = w.st;
+inline int ldlt_solve_on(LdltWs& w, cudaStream_t st, const LdltSolveBuf& sb, const double* b, double* x) {
     const size_t npad = (size_t)w.nblk * NB;
     double *ia = w.dinfo, *ib = w.dinfo + npad;
-    w.epoch++;
-    CU(cudaMemsetAsync(w.ticket, 0, sizeof(unsigned) * 2, st));
-    ldlt_fill_sentinel_kernel<<<cdiv((int)npad, 256), 256, 0, st>>>(w.yv, w.xv, (int)npad);
+    CU(cudaMemsetAsync(sb.ticket, 0, sizeof(unsigned) * 2, st));
+    ldlt_fill_sentinel_kernel<<<cdiv((int)npad, 256), 256, 0, st>>>(sb.yv, sb.xv, (int)npad);
     LAUNCHED();
-    ldlt_fwd_kernel<<<w.nblk, 256, 0, st>>>(w.A, w.ld, w.n, w.nblk, w.LinvP, ia, ib, w.kind, b, w.yv, w.zv, w.flags,
-                                            w.epoch, w.ticket);
+    ldlt_fwd_kernel<<<w.nblk, 256, 0, st>>>(w.A, w.ld, w.n, w.nblk, w.LinvP, ia, ib, w.kind, b, sb.yv, sb.zv, w.flags,
+                                            w.epoch, sb.ticket);
     LAUNCHED();
-    ldlt_bwd_kernel<<<w.nblk, 256, TILE_SMEM, st>>>(w.A, w.ld, w.n, w.nblk, w.LinvP, w.zv, w.xv, w.flags + w.nblk,
-                                                    w.epoch, w.ticket + 1);
+    ldlt_bwd_kernel<<<w.nblk, 256, TILE_SMEM, st>>>(w.A, w.ld, w.n, w.nblk, w.LinvP, sb.zv, sb.xv, w.flags + w.nblk,
+                                                    w.epoch, sb.ticket + 1);
     LAUNCHED();
-    CU(cudaMemcpyAsync(x, w.xv, sizeof(double) * w.n, cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(x, sb.xv, sizeof(double) * w.n, cudaMemcpyDeviceToDevice, st));
     return 0;
+}
+inline int ldlt_solve(LdltWs& w, const double* b, double* x) {
+    LdltSolveBuf sb;
+    sb.yv = w.yv; sb.zv = w.zv; sb.xv = w.xv; sb.ticket = w.ticket;
+    return ldlt_solve_on(w, w.st, sb, b, x);
 }
 
 }  // namespace b200

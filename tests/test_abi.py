@@ -30,10 +30,10 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layouts_match_header():
-    # sizes implied by include/b200ipm.h (10 doubles + 4 ints; 18 doubles + 10 ints + 8 floats + 4 ints) and the
+    # sizes implied by include/b200ipm.h (10 doubles + 4 ints; 18 doubles + 10 ints + 8 floats + 6 ints) and the
     # sizes the compiled library reports
     assert ctypes.sizeof(_lib.Params) == 10 * 8 + 4 * 4
-    assert ctypes.sizeof(_lib.StepInfo) == 18 * 8 + 10 * 4 + 8 * 4 + 4 * 4
+    assert ctypes.sizeof(_lib.StepInfo) == 18 * 8 + 10 * 4 + 8 * 4 + 6 * 4
     lib = _lib.load()
     assert lib.b200ipm_struct_size(0) == ctypes.sizeof(_lib.Params)
     assert lib.b200ipm_struct_size(1) == ctypes.sizeof(_lib.StepInfo)

@@ -282,8 +282,9 @@ def test_speculative_reghess_matches_sequential():
             eng.set_mu_host(st['mu_host'])
             out.append(eng.direction())
         (dz_s, i_s), (dz_q, i_q) = out
-        assert i_q.n_spec == 0
+        assert i_q.n_spec == 0 and i_q.cert_used == 0
         assert i_s.n_spec == (1 if de_b > 0.0 else 0)
+        assert i_s.cert_used <= i_s.n_spec      # a proof replaces the delta = 0 test only on speculated steps
         n_spec += i_s.n_spec
         assert (i_s.delta, i_s.n_factor, i_s.n_neg, i_s.n_zero) == (i_q.delta, i_q.n_factor, i_q.n_neg, i_q.n_zero)
         assert i_s.delta == st['delta'] and i_s.n_factor == st['reg']['n_eig']
@@ -347,7 +348,9 @@ def test_abandoned_inertia_tests_do_not_change_decisions():
     (B200IPM_FLAG_NO_ABANDON = 16), with and without speculation."""
     prob = problems.make_nlp(D=320, M=16, N=320, seed=9)
     o, tr = oracle_trace(prob, prob.x0, niter=1, miter=3)
-    engs = [make_engine(prob, flags=f) for f in (0, 16, 1, 17)]
+    # 64 = NO_CERT: the delta = 0 test really runs (in the background), 16 = NO_ABANDON, 1 = NO_SPECULATION (sequential);
+    # the last engine (flags = 0) replaces the test by the negative-curvature certificate
+    engs = [make_engine(prob, flags=f) for f in (64, 80, 1, 17, 0)]
     nu_b, de_b = 10.0, 0.0
     n_ab = 0
     for k, st in enumerate(tr):
@@ -387,11 +390,15 @@ def test_background_inertia_test_that_passes_is_honoured():
         o.newton_step(prob.x0.copy(), s0.copy(), lda0.copy())
     st = tr[0]
     assert st['reg']['n_eig'] == 1 and st['delta'] == 1.0
-    for flags in (0, 6):
+    for flags in (0, 6, 64):     # certificate path (fp64 / tcgen05 contractions) and the real background test
         eng = make_engine(prob, flags=flags)
         eng.set_state(prob.x0, s0, lda0, 0.2, 10.0, 1.0)
         eng.set_mu_host(0.2)
         dz, info = eng.direction()
-        assert info.n_factor == 1 and info.delta == 1.0 and info.n_neg == prob.neq
+        assert info.n_factor == 1 and info.delta == 1.0 and info.n_neg == prob.neq and info.cert_used == 0
         assert relinf(dz, st['dz']) < DZ_RTOL
+        # the next step from the same state does not speculate again (the previous first test passed)
+        eng.set_state(prob.x0, s0, lda0, 0.2, 10.0, 1.0)
+        dz2, info2 = eng.direction()
+        assert info2.n_spec == 0 and info2.n_factor == 1 and np.array_equal(dz2, dz)
         eng.close()
