@@ -58,7 +58,7 @@ struct b200ipm_engine {
     // negative-curvature certificate (replaces the background delta = 0 factorisation in the common case)
     LdltSolveBuf csb;        // second set of solve vectors: the certificate solve runs beside the main solve
     double *c_rhs = nullptr, *c_sol = nullptr, *c_hv = nullptr, *c_u = nullptr, *c_red = nullptr;
-    double* h_cert = nullptr;   // pinned: 2 x (v'Hv, v'v, Hv'Hv)
+    double* h_cert = nullptr;   // pinned: 2 x (v'Hv, v'v, Hv'Hv, v'u)
     bool cert_ready = false, cert_pending = false;
     bool first_failed_last = true;   // did the delta = 0 test of the previous step fail?  (speculate only then)
     int n_cert_ok = 0, n_cert_miss = 0;
@@ -328,6 +328,7 @@ static int cert_launch(Eng* h) {
         RET(ldlt_solvebuf_alloc(h->csb, h->F.nblk));
         RET(dalloc(&h->c_rhs, Kc)); RET(dalloc(&h->c_sol, Kc)); RET(dalloc(&h->c_hv, D)); RET(dalloc(&h->c_u, D));
         RET(dalloc(&h->c_red, 8));
+        CU(cudaMemset(h->c_red, 0, sizeof(double) * 8));
         CU(cudaMallocHost(&h->h_cert, sizeof(double) * 8));
         std::vector<double> u0(D);
         unsigned long long sd = 0x9E3779B97F4A7C15ull;
@@ -349,10 +350,10 @@ static int cert_launch(Eng* h) {
         LAUNCHED();
         RET(ldlt_solve_on(h->F, h->stB, h->csb, h->c_rhs, h->c_sol));
         RET(gemv_n(h->stB, h->Hb, h->ldW, D, D, h->c_sol, nullptr, 0.0, 1.0, h->c_hv));
-        cert_stats_kernel<<<1, 1024, 0, h->stB>>>(D, h->c_sol, h->c_hv, h->c_u, h->c_red + 3 * it);
+        cert_stats_kernel<<<1, 1024, 0, h->stB>>>(D, h->c_sol, h->c_hv, h->c_u, h->c_red + 4 * it);
         LAUNCHED();
     }
-    CU(cudaMemcpyAsync(h->h_cert, h->c_red, sizeof(double) * 6, cudaMemcpyDeviceToHost, h->stB));
+    CU(cudaMemcpyAsync(h->h_cert, h->c_red, sizeof(double) * 8, cudaMemcpyDeviceToHost, h->stB));
     return 0;
 }
 // One inertia test = one factorisation.  `neg_limit`: the test can only pass with exactly M negative pivots, so a
@@ -495,11 +496,15 @@ static int resolve_pending(Eng* h, b200ipm_step_info* info, bool* redo) {
         h->cert_pending = false;
         bool proven = false;
         for (int it = 0; it < 2 && !proven; it++) {
-            const double q = h->h_cert[3 * it], nv = h->h_cert[3 * it + 1], hn = h->h_cert[3 * it + 2];
-            if (!(nv > 0.0) || !(hn >= 0.0) || !(fabs(q) <= 1.7e308)) continue;
-            const double rho = q / nv;                              // Rayleigh quotient of Hb on null(dce')
+            const double q = h->h_cert[4 * it], nv = h->h_cert[4 * it + 1], hn = h->h_cert[4 * it + 2], vu = h->h_cert[4 * it + 3];
+            if (!(nv > 0.0) || !(hn >= 0.0) || !(fabs(q) <= 1.7e308) || !(fabs(vu) <= 1.7e308)) continue;
+            const double rho = q / nv;                              // Rayleigh quotient of Hb on null(dce'), explicit
+            // the same quantity from the solve itself: (Hb + delta1 I) v + dce y = u and dce' v = 0  =>  v'(Hb + delta1 I) v = v'u.
+            // The two agree only if the solve was accurate AND v is (numerically) in null(dce'): a consistency check of
+            // exactly the assumptions the proof rests on.
+            const double rho2 = vu / nv - h->delta_eff;
             const double scale = std::max(sqrt(hn / nv), h->delta_eff);
-            if (rho < -1e-7 * scale) proven = true;
+            if (rho < -1e-7 * scale && rho2 < -1e-7 * scale && fabs(rho - rho2) <= 0.05 * fabs(rho)) proven = true;
         }
         if (info) { info->n_neg_first = -1; info->n_zero_first = -1; info->rcond = -1.0; info->abandoned_first = 0; info->cert_used = proven ? 1 : 0; }
         if (proven) {

@@ -604,21 +604,22 @@ __global__ void cert_rhs_kernel(int D, int Kc, const double* __restrict__ u, dou
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < Kc) rhs[i] = (i < D) ? u[i] : 0.0;
 }
-// red[0..2] = (v' Hv, v' v, Hv' Hv);  u_next = v / ||v||   (one CTA, deterministic tree)
+// red[0..3] = (v' Hv, v' v, Hv' Hv, v' u);  then u <- v / ||v||   (one CTA, deterministic tree)
 __global__ void __launch_bounds__(1024) cert_stats_kernel(int D, const double* __restrict__ v, const double* __restrict__ hv,
-                                                          double* __restrict__ u_next, double* __restrict__ red) {
+                                                          double* __restrict__ u, double* __restrict__ red) {
     __shared__ double sh[33];
-    double q = 0.0, nv = 0.0, hn = 0.0;
+    double q = 0.0, nv = 0.0, hn = 0.0, vu = 0.0;
     for (int i = threadIdx.x; i < D; i += blockDim.x) {
         const double a = v[i], b = hv[i];
-        q += a * b; nv += a * a; hn += b * b;
+        q += a * b; nv += a * a; hn += b * b; vu += a * u[i];
     }
     q = block_sum(q, sh);
     nv = block_sum(nv, sh);
     hn = block_sum(hn, sh);
+    vu = block_sum(vu, sh);
     const double sc = (nv > 0.0 && nv < 1.7e308) ? rsqrt(nv) : 0.0;
-    for (int i = threadIdx.x; i < D; i += blockDim.x) u_next[i] = v[i] * sc;
-    if (threadIdx.x == 0) { red[0] = q; red[1] = nv; red[2] = hn; }
+    for (int i = threadIdx.x; i < D; i += blockDim.x) u[i] = v[i] * sc;
+    if (threadIdx.x == 0) { red[0] = q; red[1] = nv; red[2] = hn; red[3] = vu; }
 }
 
 }  // namespace b200
