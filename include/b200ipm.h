@@ -44,6 +44,7 @@ typedef struct b200ipm_params {
 #define B200IPM_FLAG_NO_SPECULATION 1
 #define B200IPM_FLAG_DELAY_BG       32  /* start the background inertia test only when the foreground factorisation is past
                                            its first third (measured: no net gain at config 3, off by default) */
+#define B200IPM_FLAG_TCGEN05_FULLCOND 128 /* condensation product with all 34 slice pairs instead of 21 (it is only factored) */
 #define B200IPM_FLAG_NO_CERT        64  /* never replace the delta = 0 inertia test by a negative-curvature certificate
                                            (then the test itself runs in the background) */
 #define B200IPM_FLAG_NO_ABANDON     16  /* always complete a failed inertia test (n_neg_first is then the full count) */
@@ -219,8 +220,8 @@ int b200ipm_trace_start(void);
 int b200ipm_trace_dump(int* id, int* blk, unsigned long long* t0, unsigned long long* t1, unsigned long long* tag,
                        int max, int* n);   /* tag = control block of the factorisation a record belongs to */
 /* Same product as b200ipm_test_syrk, computed on the tcgen05 tensor cores by the int8 error-free (Ozaki) path:
- * signed_mask bit t = alpha_t*w_t may be negative; variant 0 = 128x64 tiles / one pass, 1 = 128x128 tiles / two
- * passes, 2 = 128x256 / four; lbo, sbo <= 0 keep the default shared-memory descriptor strides; ms[2] = {slicing ms,
+ * signed_mask bit t = alpha_t*w_t may be negative; variant & 15: 0 = 128x64 tiles / one pass, 1 = 128x128 tiles / two
+ * passes, 2 = 128x256 / four; variant >> 4 (128x128 tiles only): slice-pair diagonals kept, 6 / 7 / 8 (default 8); lbo, sbo <= 0 keep the default shared-memory descriptor strides; ms[2] = {slicing ms,
  * total ms of one call};
  * *err = device error word (1 non-finite input, 2 negative weight without sign operand, 4 pipeline timeout). */
 int b200ipm_test_syrk_i8(int n, const double* Cin, double beta, const double* dadd, double shift,

@@ -173,7 +173,8 @@ static int eval_derivs(Eng* h) {
     return 0;
 }
 static bool use_tc(Eng* h) {
-    return (h->p.flags & B200IPM_FLAG_TCGEN05_SYRK) && !h->oz_off && h->D >= 256;
+    return (h->p.flags & B200IPM_FLAG_TCGEN05_SYRK) && !h->oz_off && h->D >= 256 &&
+           (int)(rup((size_t)h->M, OZ_KB) + rup((size_t)h->N, OZ_KB)) <= OZ_KMAX;   // exact int32 accumulation
 }
 static void oz_configure(Eng* h) { h->oz.variant = (h->p.flags >> 2) & 3; if (h->oz.variant == 3) h->oz.variant = 1; }
 // W = d2L at the current (x, lda): only needed when a search direction is computed (a3)
@@ -191,6 +192,7 @@ static int eval_hessian(Eng* h) {
         if (M && h->Ut) a.t[a.nterms++] = GemmTerm{h->Ut, h->Ut, h->lam, M, M, M, -1.0};
         if (N && h->Vt) a.t[a.nterms++] = GemmTerm{h->Vt, h->Vt, h->lam + M, N, N, N, 1.0};
         if (use_tc(h) && a.nterms) {
+            h->oz.ndiag = 8;                                         // d2L enters the refinement residual: full accuracy
             RET(oz_syrk(h->st, a, h->oz, (M && h->Ut) ? 1u : 0u));   // lda_e has either sign, lda_i >= 0
             h->oz_used = true;
         } else {
@@ -239,6 +241,9 @@ static int condense(Eng* h) {
     if (N) a.t[a.nterms++] = GemmTerm{h->J + M, h->J + M, h->sigma, h->ldJ, h->ldJ, N, 1.0};
     CU(cudaEventRecord(h->ev[EV_COND0], h->st));
     if (use_tc(h) && a.nterms) {
+        // Hb is only factored (inertia + preconditioner of the refinement against the unreduced system, which uses W, J
+        // and Sigma themselves): B200IPM_FLAG_TCGEN05_FULLCOND keeps all 34 slice pairs, the default keeps 21 (~1e-12)
+        h->oz.ndiag = (h->p.flags & B200IPM_FLAG_TCGEN05_FULLCOND) ? 8 : 6;
         RET(oz_syrk(h->st, a, h->oz, 0u));                           // sigma = lda_i / (s + eps) >= 0 in the interior
         h->oz_used = true;
     } else {
@@ -1221,6 +1226,7 @@ int b200ipm_profile_kernel(b200ipm_handle h, int which, int reps, float* ms_per_
                 if (M && h->Ut) a.t[a.nterms++] = GemmTerm{h->Ut, h->Ut, h->lam, M, M, M, -1.0};
                 if (N && h->Vt) a.t[a.nterms++] = GemmTerm{h->Vt, h->Vt, h->lam + M, N, N, N, 1.0};
                 oz_configure(h);
+                h->oz.ndiag = 8;
                 RET(oz_syrk(h->st, a, h->oz, (M && h->Ut) ? 1u : 0u));
                 wk = gemm_nt_flops(a);
                 break;
@@ -1233,6 +1239,7 @@ int b200ipm_profile_kernel(b200ipm_handle h, int which, int reps, float* ms_per_
                 if (M && h->Ut) a.t[a.nterms++] = GemmTerm{h->Ut, h->Ut, h->lam, M, M, M, -1.0};
                 if (N && h->Vt) a.t[a.nterms++] = GemmTerm{h->Vt, h->Vt, h->lam + M, N, N, N, 1.0};
                 oz_configure(h);
+                h->oz.ndiag = 8;
                 if (r == 0) {
                     RET(oz_syrk(h->st, a, h->oz, (M && h->Ut) ? 1u : 0u));
                     CU(cudaEventRecord(h->ev[EV_START], h->st));   // restart the clock after the slicing pass
@@ -1241,7 +1248,7 @@ int b200ipm_profile_kernel(b200ipm_handle h, int which, int reps, float* ms_per_
                 const int rc8 = oz_syrk(h->st, a, h->oz, (M && h->Ut) ? 1u : 0u);
                 h->oz.reuse_slices = false;
                 RET(rc8);
-                wk = oz_syrk_int8_ops(a, oz_variant_bn(h->oz.variant));
+                wk = oz_syrk_int8_ops(a, oz_variant_bn(h->oz.variant), h->oz.variant == 1 ? h->oz.ndiag : 7);
                 break;
             }
             case 7: {
@@ -1250,6 +1257,7 @@ int b200ipm_profile_kernel(b200ipm_handle h, int which, int reps, float* ms_per_
                 a.mode = GEMM_UPPER_MIRROR; a.nterms = 0;
                 if (N) a.t[a.nterms++] = GemmTerm{h->J + M, h->J + M, h->sigma, h->ldJ, h->ldJ, N, 1.0};
                 oz_configure(h);
+                h->oz.ndiag = (h->p.flags & B200IPM_FLAG_TCGEN05_FULLCOND) ? 8 : 6;
                 RET(oz_syrk(h->st, a, h->oz, 0u));
                 wk = gemm_nt_flops(a);
                 break;
@@ -1717,7 +1725,8 @@ int b200ipm_test_syrk_i8(int n, const double* Cin, double beta, const double* da
         a.t[t] = GemmTerm{dA[t], dA[t], dw[t], ldk, ldk, K[t], alpha[t]};
     }
     OzWs ws;
-    ws.variant = variant;
+    ws.variant = variant & 15;
+    if (variant >> 4) ws.ndiag = variant >> 4;     // 128x128 tiles: slice-pair diagonals kept (6, 7, 8)
     if (lbo > 0) ws.lbo = lbo;
     if (sbo > 0) ws.sbo = sbo;
     for (int i = 0; i < 3; i++) CU(cudaEventCreate(&ws.ev[i]));

@@ -5,13 +5,15 @@
 // (pyipm.py:498, 824-844 eliminated) -- are computed by an error-free transformation
 // (Ozaki scheme): every row of the scaled operand  L[i, k] = A[i, k] * sqrt|alpha w_k|  is written as
 //
-//     L[i, k] = 2^e_i * sum_{p = 0..7}  t_p[i, k] * 2^(-6 - 7 p),      t_p in [-64, 64]  (int8, signed digits)
+//     L[i, k] = 2^e_i * sum_{p = 0..6}  t_p[i, k] * 2^(-7 - 8 p),      t_p in [-128, 127]  (int8)
 //
-// (6 + 7*7 = 55 bits below the row's largest entry), the slice products  sum_k t_p[i, k] u_q[j, k]  are EXACT in
-// the int32 accumulators of tcgen05.mma.kind::i8 (|t u| <= 4096, K <= 2^17), all pairs with p + q = d share one
-// TMEM accumulator, and the eight diagonals d = 0..7 (36 slice pairs) are recombined in fp64:
+// with BALANCED base-256 digits (|L| 2^-e_i < 1/2, so t_0 in [-64, 65]; 6 + 6*8 = 54 bits + rounding = 55 bits below
+// the row's largest entry; balanced digits are zero-mean, so the truncated slice pairs carry no systematic bias).
+// The slice products  sum_k t_p[i, k] u_q[j, k]  are EXACT in the int32 accumulators of tcgen05.mma.kind::i8
+// (|t u| <= 2^14, 7 pairs per accumulator, K <= 18432), all pairs with p + q = d share one TMEM accumulator, and the
+// seven diagonals d = 0..6 (28 slice pairs) are recombined in fp64:
 //
-//     C[i, j] = beta Cin[i, j] + [i == j] (dadd_i + shift) + 2^(e_i + e_j - 12) * sum_d acc_d[i, j] * 2^(-7 d).
+//     C[i, j] = beta Cin[i, j] + [i == j] (dadd_i + shift) + 2^(e_i + e_j - 14) * sum_d acc_d[i, j] * 2^(-8 d).
 //
 // Negative weights (lda_e) are carried by a second operand R = L with the sign of alpha*w_k applied per column.
 //
@@ -30,7 +32,9 @@
 
 namespace b200 {
 
-constexpr int OZ_NS = 8;                     // slices per operand
+constexpr int OZ_NS = 7;                     // slices per operand (balanced base-256 digits)
+constexpr int OZ_NPAIRS = OZ_NS * (OZ_NS + 1) / 2;   // slice pairs with p + q <= OZ_NS - 1
+constexpr int OZ_KMAX = 18432;               // OZ_NS * K * 2^14 < 2^31
 constexpr int OZ_KB = 32;                    // int8 elements (bytes) of K per pipeline stage = one MMA K step
 constexpr int OZ_BM = 128;                   // rows per block (UMMA M)
 constexpr int OZ_CHUNK = OZ_BM * OZ_KB;      // bytes of one slice of one row block for one k-block
@@ -91,7 +95,7 @@ __global__ void __launch_bounds__(128) oz_rowmax_kernel(const OzSliceArgs a) {
     m = warp_max(m);
     bad = __any_sync(0xffffffffu, bad);
     if (lane == 0) {
-        a.rexp[row] = (m > 0.0 && !bad) ? ilogb(m) + 1 : 0;
+        a.rexp[row] = (m > 0.0 && !bad) ? ilogb(m) + 2 : 0;     // |L| * 2^-e < 1/2
         if (bad) atomicOr(a.err, 1);
     }
 }
@@ -143,27 +147,45 @@ __global__ void __launch_bounds__(256) oz_slice_kernel(const OzSliceArgs a) {
             }
         }
         const bool write_r = (t >= 0) && a.t[t].sgn;
-        // digits: x = v * 2^(6 - e);  t0 = rint(x); then 7 bits per further slice (all operations exact in fp64)
-        double rem[16];
-#pragma unroll
-        for (int b = 0; b < 16; b++) rem[b] = scalbn(v[b], 6 - e);
+        // digits: y0 = v * 2^(7 - e) in (-64, 64): t0 = rint(y0); then 8 bits per further slice, t = rint(256 r) in
+        // [-128, 128] (every operation exact in fp64); a digit +128 becomes -128 with a carry into the digit above.
+        // The sign-carrying copy R needs the digits of -v (negating a digit -128 would overflow).
         const size_t base = ((size_t)(rb * a.nkb + (cc >> 1)) * OZ_NS) * OZ_CHUNK + g * 256 + (cc & 1) * 128 + r * 16;
+        unsigned wl[OZ_NS][4], wr[OZ_NS][4];
+#pragma unroll
+        for (int p = 0; p < OZ_NS; p++)
+#pragma unroll
+            for (int q = 0; q < 4; q++) wl[p][q] = wr[p][q] = 0u;
+#pragma unroll
+        for (int b = 0; b < 16; b++) {
+#pragma unroll
+            for (int side = 0; side < 2; side++) {
+                if (side == 1 && !write_r) continue;
+                const bool flip = (side == 1) && ((negmask >> b) & 1u);
+                double rem = scalbn(flip ? -v[b] : v[b], 7 - e);
+                int dg[OZ_NS];
+#pragma unroll
+                for (int p = 0; p < OZ_NS; p++) {
+                    const double x = (p == 0) ? rem : rem * 256.0;
+                    const double tq = rint(x);
+                    rem = x - tq;
+                    dg[p] = (int)tq;
+                }
+#pragma unroll
+                for (int p = OZ_NS - 1; p >= 1; p--)
+                    if (dg[p] == 128) { dg[p] = -128; dg[p - 1] += 1; }
+#pragma unroll
+                for (int p = 0; p < OZ_NS; p++) {
+                    const unsigned byte = ((unsigned)dg[p] & 0xffu) << (8 * (b & 3));
+                    if (side == 0) wl[p][b >> 2] |= byte; else wr[p][b >> 2] |= byte;
+                }
+            }
+        }
 #pragma unroll
         for (int p = 0; p < OZ_NS; p++) {
-            unsigned wl[4] = {0, 0, 0, 0}, wr[4] = {0, 0, 0, 0};
-#pragma unroll
-            for (int b = 0; b < 16; b++) {
-                const double x = (p == 0) ? rem[b] : rem[b] * 128.0;
-                const double tq = rint(x);
-                rem[b] = x - tq;
-                const int ti = (int)tq;
-                wl[b >> 2] |= ((unsigned)ti & 0xffu) << (8 * (b & 3));
-                const int tr = ((negmask >> b) & 1u) ? -ti : ti;
-                wr[b >> 2] |= ((unsigned)tr & 0xffu) << (8 * (b & 3));
-            }
-            *reinterpret_cast<uint4*>(a.L + base + (size_t)p * OZ_CHUNK) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+            *reinterpret_cast<uint4*>(a.L + base + (size_t)p * OZ_CHUNK) = make_uint4(wl[p][0], wl[p][1], wl[p][2], wl[p][3]);
             if (write_r)
-                *reinterpret_cast<uint4*>(a.R + base + (size_t)p * OZ_CHUNK) = make_uint4(wr[0], wr[1], wr[2], wr[3]);
+                *reinterpret_cast<uint4*>(a.R + base + (size_t)p * OZ_CHUNK) = make_uint4(wr[p][0], wr[p][1], wr[p][2], wr[p][3]);
         }
     }
 }
@@ -271,22 +293,36 @@ struct OzGemmArgs {
     int sgn[3];            // the B side of a signed term's k-blocks comes from R (sign applied), otherwise from L
 };
 
-// BN = tile width (UMMA N), NPASS passes of DPP = 8 / NPASS diagonals each (DPP * BN = 512 TMEM columns).
-template <int BN, int NPASS>
+// BN = tile width (UMMA N), ND = number of slice-pair diagonals kept (p + q < ND, p, q < OZ_NS):
+//   ND = 8: 34 pairs, error ~ fp64 rounding of the product;  ND = 7: 28 pairs, ~1e-15 relative to the row scales;
+//   ND = 6: 21 pairs, ~1e-12 (enough for a matrix that is only factored and refined against).
+// At most MAXD = 512 / BN diagonals fit in the 512 TMEM columns, so they are done in NPASS passes from the top: pass pi
+// covers diagonals [d_lo, d_hi), d_hi = ND - pi * MAXD, and needs the slices 0 .. min(d_hi, OZ_NS) - 1 of both operands.
+template <int BN, int ND>
+struct OzShape {
+    static constexpr int MAXD = 512 / BN;
+    static constexpr int NPASS = (ND + MAXD - 1) / MAXD;
+    static constexpr int A_BYTES = OZ_NS * OZ_CHUNK;           // all slices of the A side for one k-block
+    static constexpr int B_SLICE = BN * OZ_KB;
+    static constexpr int B_BYTES = OZ_NS * B_SLICE;
+    static constexpr int STAGE = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (int)(OZ_SMEM_BUDGET / STAGE) > 4 ? 4 : (int)(OZ_SMEM_BUDGET / STAGE);
+    static constexpr int SMEM = STAGES * STAGE + 1024;
+    __host__ __device__ static constexpr int d_hi(int pi) { return ND - pi * MAXD; }
+    __host__ __device__ static constexpr int d_lo(int pi) { return d_hi(pi) - MAXD > 0 ? d_hi(pi) - MAXD : 0; }
+};
+
+template <int BN, int ND>
 __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzGemmArgs a) {
-    constexpr int DPP = OZ_NS / NPASS;
-    constexpr int A_BYTES = OZ_NS * OZ_CHUNK;           // all slices of the A side for one k-block
-    constexpr int B_SLICE = BN * OZ_KB;
-    constexpr int B_BYTES = OZ_NS * B_SLICE;
-    constexpr int STAGE = A_BYTES + B_BYTES;
-    constexpr int STAGES = (int)(OZ_SMEM_BUDGET / STAGE);
-    static_assert(DPP * BN == 512, "the pass must fill the 512 TMEM columns");
+    using S = OzShape<BN, ND>;
+    constexpr int MAXD = S::MAXD, NPASS = S::NPASS, A_BYTES = S::A_BYTES, B_SLICE = S::B_SLICE, STAGE = S::STAGE,
+                  STAGES = S::STAGES;
     static_assert(STAGES >= 2, "pipeline needs two stages");
     extern __shared__ __align__(1024) uint8_t oz_smem[];
     __shared__ __align__(8) uint64_t bar_full[STAGES], bar_empty[STAGES], bar_tfull, bar_tempty;
     __shared__ uint32_t s_tmem;
     __shared__ int s_dead;
-    __shared__ double s_cscale[BN];   // 2^(e_j - 6) of the tile's columns
+    __shared__ double s_cscale[BN];   // 2^(e_j - 7) of the tile's columns
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int2 tile = a.tiles[blockIdx.x];
     const int ti = tile.x, tj = tile.y;
@@ -302,7 +338,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzGemmArgs
         oz_mbar_init(oz_smem_u32(&bar_tempty), 4);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
-    for (int c = tid; c < BN; c += OZ_THREADS) s_cscale[c] = scalbn(1.0, ((col0 + c < a.n) ? a.rexp[col0 + c] : 0) - 6);
+    for (int c = tid; c < BN; c += OZ_THREADS) s_cscale[c] = scalbn(1.0, ((col0 + c < a.n) ? a.rexp[col0 + c] : 0) - 7);
     if (warp == 0) {
         const uint32_t ncols = 512;
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(oz_smem_u32(&s_tmem)), "r"(ncols)
@@ -321,7 +357,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzGemmArgs
         if (lane == 0) {
             int it = 0;
             for (int pi = 0; pi < NPASS; pi++) {
-                const int nsl = (NPASS - pi) * DPP;      // slices 0 .. nsl-1 are needed for diagonals < nsl
+                const int nsl = S::d_hi(pi) < OZ_NS ? S::d_hi(pi) : OZ_NS;   // slices 0 .. nsl-1 are needed for diagonals < d_hi
                 for (int kb = 0; kb < a.nkb; kb++, it++) {
                     const int s = it % STAGES;
                     const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
@@ -362,8 +398,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzGemmArgs
         int it = 0;
 #pragma unroll
         for (int pi = 0; pi < NPASS; pi++) {
-            constexpr int DPPc = DPP;
-            const int d0 = (NPASS - 1 - pi) * DPPc;
+            const int d_lo = S::d_lo(pi), d_hi = S::d_hi(pi);
             if (pi > 0) {
                 oz_mbar_wait(oz_smem_u32(&bar_tempty), (uint32_t)(pi - 1) & 1u, dead, a.err);
                 oz_tc_fence_after();
@@ -378,12 +413,13 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzGemmArgs
                 const uint32_t acc_first = (kb > 0) ? 1u : 0u;
                 if (oz_elect_one()) {
 #pragma unroll
-                    for (int dd = 0; dd < DPPc; dd++) {
+                    for (int d = d_lo; d < d_hi; d++) {
+                        const int p0 = (d - (OZ_NS - 1) > 0) ? d - (OZ_NS - 1) : 0;      // p, q <= OZ_NS - 1
 #pragma unroll
-                        for (int p = 0; p <= d0 + dd; p++) {
-                            const int q = d0 + dd - p;
-                            oz_mma_i8(tmem + (uint32_t)(dd * BN), da0 + (uint64_t)(p * (OZ_CHUNK >> 4)),
-                                      db0 + (uint64_t)(q * (B_SLICE >> 4)), a.idesc, (p > 0) ? 1u : acc_first);
+                        for (int p = p0; p <= d && p < OZ_NS; p++) {
+                            const int q = d - p;
+                            oz_mma_i8(tmem + (uint32_t)((d - d_lo) * BN), da0 + (uint64_t)(p * (OZ_CHUNK >> 4)),
+                                      db0 + (uint64_t)(q * (B_SLICE >> 4)), a.idesc, (p > p0) ? 1u : acc_first);
                         }
                     }
                     oz_tc_commit(oz_smem_u32(&bar_empty[s]));      // frees the stage when these MMAs have read it
@@ -395,19 +431,21 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzGemmArgs
         }
     } else {
         // ===== epilogue: warp (warp & 3) owns TMEM lanes 32*(warp & 3) .. +31 = tile rows.  Per 8-column chunk: the
-        // global operands (partial sum of the higher diagonals, Cin) are prefetched one chunk ahead, the DPP int32
-        // accumulators are read with tcgen05.ld, recombined by Horner in fp64 and scaled by exact powers of two.
+        // global operands (partial sum of the higher diagonals, Cin) are prefetched one chunk ahead, the int32
+        // accumulators of the pass are read with tcgen05.ld, recombined by Horner in fp64 and scaled by exact powers of 2.
         const int q4 = warp & 3;
         const int rl = q4 * 32 + lane;
         const int i = row0 + rl;
         const bool rowok = i < a.n;
         const int ei = rowok ? a.rexp[i] : 0;
         const double dii = rowok ? (a.shift + (a.dadd ? a.dadd[i] : 0.0)) : 0.0;
+#pragma unroll
         for (int pi = 0; pi < NPASS; pi++) {
-            const int d0 = (NPASS - 1 - pi) * DPP;
+            const int d_lo = S::d_lo(pi), d_hi = S::d_hi(pi);
+            const int dn = d_hi - d_lo;
             const bool last = (pi == NPASS - 1);
             const bool need_part = (pi > 0), need_cin = last && (a.Cin != nullptr);
-            const double si = scalbn(1.0, ei - 6 - 7 * d0);
+            const double si = scalbn(1.0, ei - 7 - 8 * d_lo);
             double pre_p[8], pre_c[8];
             auto prefetch = [&](int cb) {
 #pragma unroll
@@ -422,10 +460,10 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzGemmArgs
             oz_mbar_wait(oz_smem_u32(&bar_tfull), (uint32_t)pi & 1u, dead, a.err);
             oz_tc_fence_after();
             for (int cb = 0; cb < BN / 8; cb++) {
-                int acc[DPP][8];
+                int acc[MAXD][8];
 #pragma unroll
-                for (int dd = 0; dd < DPP; dd++)
-                    oz_tmem_ld8(tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(dd * BN + cb * 8), acc[dd]);
+                for (int dd = 0; dd < MAXD; dd++)
+                    if (dd < dn) oz_tmem_ld8(tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(dd * BN + cb * 8), acc[dd]);
                 double cur_p[8], cur_c[8];
 #pragma unroll
                 for (int c = 0; c < 8; c++) { cur_p[c] = pre_p[c]; cur_c[c] = pre_c[c]; }
@@ -436,9 +474,10 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzGemmArgs
                     for (int c = 0; c < 8; c++) {
                         const int j = col0 + cb * 8 + c;
                         if (j >= a.n || i > j) continue;          // only the upper triangle is authoritative
-                        double h = (double)acc[DPP - 1][c];
+                        double h = 0.0;
 #pragma unroll
-                        for (int dd = DPP - 2; dd >= 0; dd--) h = fma(h, 0.0078125, (double)acc[dd][c]);
+                        for (int dd = MAXD - 1; dd >= 0; dd--)
+                            if (dd < dn) h = fma(h, 0.00390625, (double)acc[dd][c]);
                         double v = (h * si) * s_cscale[cb * 8 + c] + cur_p[c];
                         double* cp = a.C + (size_t)i * a.ldc + j;
                         if (last) {
@@ -483,7 +522,8 @@ struct OzWs {
     // (leading-dimension byte offset), 256 B between 8-row groups (stride byte offset) -- pinned on hardware by
     // tools/oz_probe.py (the swapped assignment gives garbage)
     int lbo = 128, sbo = 256;
-    int variant = 1;          // 0: 128x64 tiles, 1 pass;  1: 128x128 tiles, 2 passes;  2: 128x256 tiles, 4 passes
+    int variant = 1;          // 0: 128x64 tiles, 1 pass (7 diagonals);  1: 128x128 tiles, 2 passes;  2: 128x256, 4 passes
+    int ndiag = 8;            // 128x128 tiles: slice-pair diagonals kept (8: 34 pairs, 7: 28, 6: 21), see oz_syrk_kernel
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};   // optional: [0] start, [1] after slicing, [2] end
     bool reuse_slices = false; // profiling: skip the slicing kernels (the slices of the previous identical call are kept)
 };
@@ -501,17 +541,15 @@ inline uint32_t oz_idesc(int bn) {
     // a/b major = K (0), n_dim [17,23) = N >> 3, m_dim [24,29) = M >> 4
     return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(OZ_BM >> 4) << 24);
 }
-template <int BN, int NPASS>
+template <int BN, int ND>
 inline int oz_launch(cudaStream_t st, const OzGemmArgs& g, int ntiles) {
-    constexpr int STAGE = OZ_NS * OZ_CHUNK + OZ_NS * BN * OZ_KB;
-    constexpr int STAGES = (int)(OZ_SMEM_BUDGET / STAGE);
-    constexpr int SMEM = STAGES * STAGE + 1024;
+    constexpr int SMEM = OzShape<BN, ND>::SMEM;
     static bool attr_done = false;
     if (!attr_done) {
-        CU(cudaFuncSetAttribute(oz_syrk_kernel<BN, NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        CU(cudaFuncSetAttribute(oz_syrk_kernel<BN, ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
         attr_done = true;
     }
-    oz_syrk_kernel<BN, NPASS><<<ntiles, OZ_THREADS, SMEM, st>>>(g);
+    oz_syrk_kernel<BN, ND><<<ntiles, OZ_THREADS, SMEM, st>>>(g);
     LAUNCHED();
     return 0;
 }
@@ -537,7 +575,7 @@ inline int oz_syrk(cudaStream_t st, const GemmArgs& a, OzWs& w, unsigned may_be_
         g.sgn[t] = sg;
         anysigned = anysigned || sg;
     }
-    if (koff > (1 << 17)) return fail_msg("oz_syrk: contraction too long for exact int32 accumulation");
+    if (koff > OZ_KMAX) return fail_msg("oz_syrk: contraction too long for exact int32 accumulation");
     const int nkb = std::max(koff, OZ_KB) / OZ_KB;
     const int bn = oz_variant_bn(w.variant);
     const int nrb = (int)rup((size_t)cdiv(a.n, OZ_BM), (size_t)std::max(1, bn / OZ_BM));   // whole tiles of row blocks
@@ -591,21 +629,29 @@ inline int oz_syrk(cudaStream_t st, const GemmArgs& a, OzWs& w, unsigned may_be_
     g.desc_hi = oz_desc_hi(w.lbo, w.sbo);
     g.idesc = oz_idesc(bn);
     int rc;
-    if (w.variant == 0) rc = oz_launch<64, 1>(st, g, w.ntiles);
-    else if (w.variant == 2) rc = oz_launch<256, 4>(st, g, w.ntiles);
-    else rc = oz_launch<128, 2>(st, g, w.ntiles);
+    if (w.variant == 0) rc = oz_launch<64, 7>(st, g, w.ntiles);             // test variants: 7 diagonals
+    else if (w.variant == 2) rc = oz_launch<256, 7>(st, g, w.ntiles);
+    else if (w.ndiag <= 6) rc = oz_launch<128, 6>(st, g, w.ntiles);
+    else if (w.ndiag == 7) rc = oz_launch<128, 7>(st, g, w.ntiles);
+    else rc = oz_launch<128, 8>(st, g, w.ntiles);
     if (rc == 0 && w.ev[2]) CU(cudaEventRecord(w.ev[2], st));
     return rc;
 }
 
-// int8 multiply-add operations one call issues on the tensor cores (36 slice pairs over the computed tiles)
-inline double oz_syrk_int8_ops(const GemmArgs& a, int bn) {
+// int8 multiply-add operations one call issues on the tensor cores (slice pairs x computed tiles x K)
+inline int oz_npairs(int nd) {
+    int np = 0;
+    for (int d = 0; d < nd; d++)
+        for (int p = 0; p <= d; p++) np += (p < OZ_NS && d - p < OZ_NS) ? 1 : 0;
+    return np;
+}
+inline double oz_syrk_int8_ops(const GemmArgs& a, int bn, int nd) {
     double ksum = 0;
     for (int t = 0; t < a.nterms; t++) ksum += (double)rup((size_t)a.t[t].K, OZ_KB);
     double tiles = 0;
     for (int tj = 0; tj * bn < a.n; tj++)
         for (int ti = 0; ti * OZ_BM < a.n && ti * OZ_BM <= tj * bn + bn - 1; ti++) tiles += 1;
-    return 2.0 * tiles * OZ_BM * bn * ksum * 36.0;
+    return 2.0 * tiles * OZ_BM * bn * ksum * (double)oz_npairs(nd);
 }
 
 }  // namespace b200

@@ -296,9 +296,10 @@ def test_speculative_reghess_matches_sequential():
     eng_q.close()
 
 
-@pytest.mark.parametrize('flags', [2, 6, 10])
+@pytest.mark.parametrize('flags', [2, 6, 10, 6 | 128])
 def test_tcgen05_syrk_path_teacher_forced(flags):
-    """Engine with the d2L and condensation contractions on tcgen05 (B200IPM_FLAG_TCGEN05_SYRK, all three tile variants): same reghess decisions and the same direction as the CPU oracle, to the fp64 tolerance."""
+    """Engine with the d2L and condensation contractions on tcgen05 (B200IPM_FLAG_TCGEN05_SYRK, all three tile variants,
+    and the condensation with all 34 slice pairs instead of 21): same reghess decisions and the same direction as the CPU oracle, to the fp64 tolerance."""
     prob = problems.make_nlp(D=320, M=48, N=320, seed=5)
     o, tr = oracle_trace(prob, prob.x0, niter=1, miter=4)
     eng = make_engine(prob, flags=flags)

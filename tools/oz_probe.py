@@ -75,8 +75,8 @@ def main():
     diff = np.where(bad, np.inf, np.abs(C - ref))
     relerr = float(np.max(diff) / scale)
     sym = bool(np.array_equal(C, C.T))
-    print('case=%s variant=%d lbo=%d sbo=%d  err_word=%d  max|C-ref|/max|ref|=%.3e  nonfinite=%d  symmetric=%s  ms(slice,total)=%.3f,%.3f  wall=%.1fs'
-          % (case, variant, lbo, sbo, err, relerr, int(bad.sum()), sym, ms[0], ms[1], wall), flush=True)
+    print('case=%s variant=%d (tile %d, ndiag %d) lbo=%d sbo=%d  err_word=%d  max|C-ref|/max|ref|=%.3e  nonfinite=%d  symmetric=%s  ms(slice,total)=%.3f,%.3f  wall=%.1fs'
+          % (case, variant, variant & 15, variant >> 4, lbo, sbo, err, relerr, int(bad.sum()), sym, ms[0], ms[1], wall), flush=True)
     if case in ('tiny', 'small') and relerr > 1e-12:
         out = os.path.join('gpurun_out', 'oz_%s_v%d_%d_%d.npz' % (case, variant, lbo, sbo))
         np.savez_compressed(out, A=terms[0][0], C=C, ref=ref)
