@@ -147,9 +147,8 @@ __global__ void __launch_bounds__(256) oz_slice_kernel(const OzSliceArgs a) {
             }
         }
         const bool write_r = (t >= 0) && a.t[t].sgn;
-        // digits: y0 = v * 2^(7 - e) in (-64, 64): t0 = rint(y0); then 8 bits per further slice, t = rint(256 r) in
-        // [-128, 128] (every operation exact in fp64); a digit +128 becomes -128 with a carry into the digit above.
-        // The sign-carrying copy R needs the digits of -v (negating a digit -128 would overflow).
+        // digits of L (and, for signed terms, of the column-sign-flipped copy R: negating a digit -128 would overflow,
+        // so R gets the digits of -v)
         const size_t base = ((size_t)(rb * a.nkb + (cc >> 1)) * OZ_NS) * OZ_CHUNK + g * 256 + (cc & 1) * 128 + r * 16;
         unsigned wl[OZ_NS][4], wr[OZ_NS][4];
 #pragma unroll
@@ -158,26 +157,20 @@ __global__ void __launch_bounds__(256) oz_slice_kernel(const OzSliceArgs a) {
             for (int q = 0; q < 4; q++) wl[p][q] = wr[p][q] = 0u;
 #pragma unroll
         for (int b = 0; b < 16; b++) {
+            // fixed point: X = rint(v * 2^(55 - e)), |X| < 2^54; balanced base-256 digits from the bottom by integer
+            // arithmetic: t = sign-extended low byte, X = (X - t) >> 8; the last quotient is t0 in [-64, 64].  The byte
+            // stored is X & 255 itself (two's complement of t).
+            const long long X0 = __double2ll_rn(scalbn(v[b], 55 - e));
 #pragma unroll
             for (int side = 0; side < 2; side++) {
                 if (side == 1 && !write_r) continue;
-                const bool flip = (side == 1) && ((negmask >> b) & 1u);
-                double rem = scalbn(flip ? -v[b] : v[b], 7 - e);
-                int dg[OZ_NS];
+                long long X = (side == 1 && ((negmask >> b) & 1u)) ? -X0 : X0;
 #pragma unroll
-                for (int p = 0; p < OZ_NS; p++) {
-                    const double x = (p == 0) ? rem : rem * 256.0;
-                    const double tq = rint(x);
-                    rem = x - tq;
-                    dg[p] = (int)tq;
-                }
-#pragma unroll
-                for (int p = OZ_NS - 1; p >= 1; p--)
-                    if (dg[p] == 128) { dg[p] = -128; dg[p - 1] += 1; }
-#pragma unroll
-                for (int p = 0; p < OZ_NS; p++) {
-                    const unsigned byte = ((unsigned)dg[p] & 0xffu) << (8 * (b & 3));
-                    if (side == 0) wl[p][b >> 2] |= byte; else wr[p][b >> 2] |= byte;
+                for (int p = OZ_NS - 1; p >= 0; p--) {
+                    const unsigned byte = (unsigned)X & 0xffu;
+                    const unsigned word = byte << (8 * (b & 3));
+                    if (side == 0) wl[p][b >> 2] |= word; else wr[p][b >> 2] |= word;
+                    X = (X - (long long)(signed char)byte) >> 8;
                 }
             }
         }
