@@ -14,6 +14,6 @@ print("roofline", {k: d["roofline"][k] for k in ("achieved","peak","frac")}, "hb
 print("clocks", d["clocks"], "launches", d["gpu_launches"])
 r=json.load(open("gpurun_out/${TAG}_bench_ref.json")); print("ref arm", r["value"], r["cpu_baseline"]["sample"][:120])
 PY
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${TAG}_launches.csv python tools/prof_step.py > gpurun_out/${TAG}_prof_step.log 2>&1
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:oz_syrk -c 1 -f -o gpurun_out/${TAG}_prof_oz python tools/prof_step.py > /dev/null 2>&1
+timeout 300 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${TAG}_launches.csv python tools/prof_step.py > gpurun_out/${TAG}_prof_step.log 2>&1
+timeout 300 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:oz_syrk -c 1 -f -o gpurun_out/${TAG}_prof_oz python tools/prof_step.py > /dev/null 2>&1
 ls -la gpurun_out | tail -8

@@ -12,5 +12,21 @@ s = np.maximum(prob.ci(prob.x0), 1e-4)
 lda = np.concatenate([0.1 * rng.standard_normal(M), 0.2 / s])
 eng.set_state(prob.x0, s, lda, 0.2, 10.0, 2 * 1.4901161193847656)   # delta already active: 2 factorisations
 eng.set_mu_host(0.2)
+eng.state_save()
+# warm-up steps from the same state (graph capture, certificate vector), then ONE profiled step: run under
+#   ncu --profile-from-start off ...   so that only the steady-state step is captured
+for _ in range(2):
+    eng.newton_step()
+    eng.state_restore()
+import ctypes
+try:
+    rt = ctypes.CDLL('libcudart.so')
+except OSError:
+    rt = None
+if rt is not None:
+    rt.cudaProfilerStart()
 info = eng.newton_step()
+if rt is not None:
+    rt.cudaDeviceSynchronize()
+    rt.cudaProfilerStop()
 print(info.asdict())
