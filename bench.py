@@ -367,8 +367,8 @@ def run_b200(args):
             peak = 2.0 * bf16_tf     # dense int8 runs at twice the bf16 rate on this part; bf16_tf is the MEASURED burst figure
             kern['hess_syrk_tcgen05_kernel_only'] = {'ms': ms8, 'int8_tops': ach, 'work': ops8}
             line['roofline'] = {
-                'kernel': 'oz_syrk_kernel<128,2> (Lagrangian-Hessian contraction Ut diag(lda_e) Ut\' + Vt diag(lda_i) Vt\' as 36 '
-                          'exact int8 slice products on tcgen05.mma.kind::i8, int32 TMEM accumulators, fp64 recombination)',
+                'kernel': 'oz_syrk_kernel<128,7> (Lagrangian-Hessian contraction Ut diag(lda_e) Ut\' + Vt diag(lda_i) Vt\' as 28 '
+                          'exact int8 slice-pair products on tcgen05.mma.kind::i8, int32 TMEM accumulators, fp64 recombination)',
                 'bound': 'tensor', 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s', 'frac': ach / peak,
                 'traffic': 0.999e9,
                 'traffic_source': 'ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch '
@@ -378,7 +378,7 @@ def run_b200(args):
                                 % (peak_kind, 2.0 * bf16_tf, int8_peak_tops or 0.0)),
                 'frac_of_cublaslt_int8': (ach / int8_peak_tops) if int8_peak_tops else None,
                 'ops_per_launch': ops8,
-                'note': 'achieved/peak count int8 multiply-adds issued (the algorithm: 36 slice pairs x upper tiles x K); the '
+                'note': 'achieved/peak count int8 multiply-adds issued (the algorithm: 28 slice pairs x upper tiles x K); the '
                         'fp64-equivalent rate of the whole operation (slicing + tensor kernel) is in roofline_fp64',
             }
             full = kern['hess_syrk_tcgen05']

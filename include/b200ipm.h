@@ -44,7 +44,8 @@ typedef struct b200ipm_params {
 #define B200IPM_FLAG_NO_SPECULATION 1
 #define B200IPM_FLAG_DELAY_BG       32  /* start the background inertia test only when the foreground factorisation is past
                                            its first third (measured: no net gain at config 3, off by default) */
-#define B200IPM_FLAG_TCGEN05_FULLCOND 128 /* condensation product with all 34 slice pairs instead of 21 (it is only factored) */
+#define B200IPM_FLAG_TCGEN05_FULLCOND 128 /* keep all 34 slice pairs in both tcgen05 products (default: 28 for d2L = 1.4e-15,
+                                            21 for the condensation, which is only factored) */
 #define B200IPM_FLAG_NO_CERT        64  /* never replace the delta = 0 inertia test by a negative-curvature certificate
                                            (then the test itself runs in the background) */
 #define B200IPM_FLAG_NO_ABANDON     16  /* always complete a failed inertia test (n_neg_first is then the full count) */

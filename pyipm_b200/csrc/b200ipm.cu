@@ -192,7 +192,8 @@ static int eval_hessian(Eng* h) {
         if (M && h->Ut) a.t[a.nterms++] = GemmTerm{h->Ut, h->Ut, h->lam, M, M, M, -1.0};
         if (N && h->Vt) a.t[a.nterms++] = GemmTerm{h->Vt, h->Vt, h->lam + M, N, N, N, 1.0};
         if (use_tc(h) && a.nterms) {
-            h->oz.ndiag = 8;                                         // d2L enters the refinement residual: full accuracy
+            // d2L enters the refinement residual: 28 pairs = 1.4e-15 max|C| (the DMMA kernel: 6.2e-15); FULLCOND: all 34
+            h->oz.ndiag = (h->p.flags & B200IPM_FLAG_TCGEN05_FULLCOND) ? 8 : 7;
             RET(oz_syrk(h->st, a, h->oz, (M && h->Ut) ? 1u : 0u));   // lda_e has either sign, lda_i >= 0
             h->oz_used = true;
         } else {
@@ -1226,7 +1227,7 @@ int b200ipm_profile_kernel(b200ipm_handle h, int which, int reps, float* ms_per_
                 if (M && h->Ut) a.t[a.nterms++] = GemmTerm{h->Ut, h->Ut, h->lam, M, M, M, -1.0};
                 if (N && h->Vt) a.t[a.nterms++] = GemmTerm{h->Vt, h->Vt, h->lam + M, N, N, N, 1.0};
                 oz_configure(h);
-                h->oz.ndiag = 8;
+                h->oz.ndiag = (h->p.flags & B200IPM_FLAG_TCGEN05_FULLCOND) ? 8 : 7;
                 RET(oz_syrk(h->st, a, h->oz, (M && h->Ut) ? 1u : 0u));
                 wk = gemm_nt_flops(a);
                 break;
@@ -1239,7 +1240,7 @@ int b200ipm_profile_kernel(b200ipm_handle h, int which, int reps, float* ms_per_
                 if (M && h->Ut) a.t[a.nterms++] = GemmTerm{h->Ut, h->Ut, h->lam, M, M, M, -1.0};
                 if (N && h->Vt) a.t[a.nterms++] = GemmTerm{h->Vt, h->Vt, h->lam + M, N, N, N, 1.0};
                 oz_configure(h);
-                h->oz.ndiag = 8;
+                h->oz.ndiag = (h->p.flags & B200IPM_FLAG_TCGEN05_FULLCOND) ? 8 : 7;
                 if (r == 0) {
                     RET(oz_syrk(h->st, a, h->oz, (M && h->Ut) ? 1u : 0u));
                     CU(cudaEventRecord(h->ev[EV_START], h->st));   // restart the clock after the slicing pass
