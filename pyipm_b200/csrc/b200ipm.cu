@@ -49,6 +49,7 @@ struct b200ipm_engine {
     int n_strict = 0;        // number of strict re-factorisations triggered by a poor residual
     LdltWs F;               // condensed KKT factorisation (order Kc)
     OzWs oz;                // tcgen05 int8 slices (B200IPM_FLAG_TCGEN05_SYRK)
+    OzWs oz_soc;            // same for the (M+N)-order normal equations of the second-order correction (lazy)
     bool oz_used = false;   // the current W / Hb came from the tcgen05 path
     bool oz_off = false;    // this step fell back to DMMA
     LdltWs Fb;              // speculative second attempt of reghess (lazy), factored concurrently on stB
@@ -700,7 +701,14 @@ static int soc_direction(Eng* h, const double* cnew /* device, M+N */, double* p
         LAUNCHED();
     }
     a.dadd = h->uvec;
-    RET(gemm_nt(h->st, a));
+    if (use_tc(h) && C >= 256 && (int)rup((size_t)D, OZ_KB) <= OZ_KMAX) {
+        h->oz_soc.variant = 1;
+        h->oz_soc.ndiag = 7;
+        if (!h->oz_soc.err) h->oz_soc.err = h->oz.err;   // one error word for the engine (owned by h->oz)
+        RET(oz_syrk(h->st, a, h->oz_soc, 0u));   // the normal-equations product on tcgen05 as well (weights are all 1)
+    } else {
+        RET(gemm_nt(h->st, a));
+    }
     RET(ldlt_factor(h->F2));
     // iterated Tikhonov: z_{k+1} = z_k + A'(G)^-1 (c - A z_k);   A z = [J' z_x]_e, [J' z_x]_i - z_s
     CU(cudaMemsetAsync(pz, 0, sizeof(double) * (D + N), h->st));
@@ -1016,6 +1024,8 @@ int b200ipm_destroy(b200ipm_handle h) {
         cudaFreeHost(h->h_cert);
     }
     ldlt_free(h->F);
+    if (h->oz_soc.err == h->oz.err) h->oz_soc.err = nullptr;
+    oz_free(h->oz_soc);
     oz_free(h->oz);
     if (h->F2_ready) ldlt_free(h->F2);
     if (h->Fb_ready) {

@@ -27,7 +27,7 @@ class IPM(object):
     def __init__(self, x0=None, x_dev=None, f=None, df=None, d2f=None, ce=None, dce=None, d2ce=None, ci=None, dci=None,
                  d2ci=None, lda0=None, lambda_dev=None, s0=None, mu=0.2, nu=10.0, rho=0.1, tau=0.995, eta=1.0E-4,
                  beta=0.4, miter=20, niter=10, Xtol=None, Ktol=1.0E-4, Ftol=None, lbfgs=False, lbfgs_zeta=None,
-                 float_dtype=np.float64, verbosity=1, device=0, stream=None, nrefine=2):
+                 float_dtype=np.float64, verbosity=1, device=0, stream=None, nrefine=2, engine_flags=None):
         # pyipm.py:316-376
         self.x0 = x0
         self.x_dev = x_dev            # ignored (no symbolic graph)
@@ -54,6 +54,7 @@ class IPM(object):
         self.delta0 = self.reg_coef
         self.compiled = False
         self.device, self.stream, self.nrefine = device, stream, nrefine
+        self.engine_flags = engine_flags      # b200ipm_params.flags (None: _lib.DEFAULT_FLAGS; 0: fp64 DMMA contractions)
         self.engine = None
         self.delta = 0.0
         self.mu_host = mu
@@ -103,7 +104,7 @@ class IPM(object):
                     'callable mode needs %s (no symbolic autodiff; pass a PolyProblem/QuadProblem to have ' \
                     'derivatives generated on the device)' % name
         params = _lib.default_params(mu=self.mu, nu=self.nu, rho=self.rho, tau=self.tau, eta=self.eta, beta=self.beta,
-                                     Xtol=self.Xtol, Ktol=self.Ktol, nrefine=self.nrefine)
+                                     Xtol=self.Xtol, Ktol=self.Ktol, nrefine=self.nrefine, flags=self.engine_flags)
         if self.engine is not None:
             self.engine.close()
         self.engine = _lib.Engine(self.nvar, self.neq, self.nineq, params, device=self.device, stream=self.stream)

@@ -9,4 +9,4 @@ eng.init_slack(); eng.init_lambda()
 for i in range(int(sys.argv[2]) if len(sys.argv) > 2 else 6):
     info = eng.newton_step()
     print(i, 'n_factor', info.n_factor, 'first attempt neg/zero', info.n_neg_first, info.n_zero_first, 'abandoned', info.abandoned_first, 'cert', info.cert_used, 'spec', info.n_spec, info.spec_used, 'tc', info.tc_syrk, 'final neg', info.n_neg, 'delta %.3e' % info.delta,
-          'ms factor %.2f solve %.2f total %.2f' % (info.ms_factor, info.ms_solve, info.ms_total), 'kkt', ['%.2e' % v for v in info.kkt_norm], 'bt', info.n_backtracks, 'alpha %.3f' % info.alpha_s)
+          'ms factor %.2f solve %.2f total %.2f' % (info.ms_factor, info.ms_solve, info.ms_total), 'kkt', ['%.2e' % v for v in info.kkt_norm], 'bt', info.n_backtracks, 'soc', info.soc_tried, info.soc_accepted, 'search ms %.2f' % info.ms_search, 'alpha %.3f' % info.alpha_s)
