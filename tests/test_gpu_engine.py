@@ -403,3 +403,26 @@ def test_background_inertia_test_that_passes_is_honoured():
         dz2, info2 = eng.direction()
         assert info2.n_spec == 0 and info2.n_factor == 1 and np.array_equal(dz2, dz)
         eng.close()
+
+
+@pytest.mark.parametrize('D,M,N', [(96, 0, 96), (96, 16, 0), (320, 48, 320)])
+def test_reghess_certificate_path_all_constraint_structures(D, M, N):
+    """Default engine (speculative reghess with the negative-curvature certificate) on nonconvex problems without
+    equality constraints (the condensed matrix is Hb alone), without inequalities (no condensation) and with both:
+    decisions and directions of the CPU oracle at every step, whether the failure of the delta = 0 test was proven
+    (cert_used) or computed."""
+    prob = problems.make_nlp(D=D, M=M, N=N, seed=11)
+    o, tr = oracle_trace(prob, prob.x0, niter=1, miter=5)
+    eng = make_engine(prob)
+    nu_b, de_b = 10.0, 0.0
+    n_cert = 0
+    for k, st in enumerate(tr):
+        eng.set_state(st['x'], st['s'], st['lda'], st['mu'], nu_b, de_b)
+        eng.set_mu_host(st['mu_host'])
+        dz, info = eng.direction()
+        n_cert += info.cert_used
+        assert info.delta == st['delta'] and info.n_factor == st['reg']['n_eig'] and info.n_neg == prob.neq, (k, info.asdict())
+        assert relinf(dz, st['dz']) < DZ_RTOL, (k, relinf(dz, st['dz']))
+        nu_b, de_b = st['nu_after'], st['delta']
+    eng.close()
+    assert n_cert >= 1     # the certificate did replace at least one delta = 0 factorisation on each trajectory
