@@ -773,17 +773,20 @@ __global__ void __launch_bounds__(128) ldlt_panel_kernel(double* __restrict__ B,
     trace_end(trc);
 }
 
-// Chain shortcut ("mini" step).  One CTA: the panel computation of ldlt_panel_kernel for the 64 rows right below tile k
-// (W = B LinvP', L = W D^-1, stored exactly as the panel kernel stores them), followed by the update of the NEXT
-// diagonal tile  T -= W L'.  Tile k+1 can then be factored while the rest of panel step k (all other rows, all other
-// tiles of the in-panel update) runs on the update stream: the serial chain per tile step is tile + mini instead of
-// tile + panel + update.
-__global__ void __launch_bounds__(128) ldlt_mini_kernel(double* __restrict__ B, int ld, int rows,
-                                                        const double* __restrict__ LinvP,
-                                                        const double* __restrict__ dinv_a,
-                                                        const double* __restrict__ dinv_b, const int* __restrict__ kind,
-                                                        double* __restrict__ Wout, int ldw, double* __restrict__ T,
-                                                        const int* __restrict__ ctrl) {
+// Chain shortcut ("mini" step).  One CTA, 8 warps: the panel computation of ldlt_panel_kernel for the 64 rows right
+// below tile k (W = B LinvP', L = W D^-1, stored exactly as the panel kernel stores them), followed by the update of the
+// NEXT diagonal tile  T -= W L'.  Tile k+1 can then be factored while the rest of panel step k (all other rows, all
+// other tiles of the in-panel update) runs on the update stream: the serial chain per tile step is tile + mini instead
+// of tile + panel + update.  Latency-oriented: B, LinvP and T are fetched together with cp.async at entry, every warp
+// owns one 8-row fragment strip (half the DMMA chain of a 4-warp layout).
+constexpr int MINI_THREADS = 256;
+constexpr int MINI_SMEM = 3 * NB * P_LDS * 8;
+__global__ void __launch_bounds__(MINI_THREADS) ldlt_mini_kernel(double* __restrict__ B, int ld, int rows,
+                                                                 const double* __restrict__ LinvP,
+                                                                 const double* __restrict__ dinv_a,
+                                                                 const double* __restrict__ dinv_b, const int* __restrict__ kind,
+                                                                 double* __restrict__ Wout, int ldw, double* __restrict__ T,
+                                                                 const int* __restrict__ ctrl) {
     extern __shared__ __align__(16) double psm[];
     __shared__ int s_abort;
     if (threadIdx.x == 0) s_abort = *reinterpret_cast<const volatile int*>(ctrl + 4);
@@ -791,6 +794,7 @@ __global__ void __launch_bounds__(128) ldlt_mini_kernel(double* __restrict__ B, 
     if (s_abort) return;
     double* As = psm;
     double* Bs = psm + NB * P_LDS;
+    double* Ts = psm + 2 * NB * P_LDS;
     __shared__ double sia[NB], sib[NB];
     __shared__ int skd[NB];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -799,45 +803,40 @@ __global__ void __launch_bounds__(128) ldlt_mini_kernel(double* __restrict__ B, 
     const int trc = (tid == 0) ? trace_begin(TR_MINI, ctrl) : -1;
     if (tid < NB) { sia[tid] = dinv_a[tid]; sib[tid] = dinv_b[tid]; skd[tid] = kind[tid]; }
 #pragma unroll
-    for (int i = 0; i < 16; i++) {
-        const int c = tid + 128 * i;
+    for (int i = 0; i < 8; i++) {
+        const int c = tid + MINI_THREADS * i;
         const int row = c >> 5, kc = (c & 31) * 2;
         const bool ok = row < nn;
         cp_async16(As + row * P_LDS + kc, ok ? B + (size_t)row * ld + kc : B, ok ? 16 : 0);
         cp_async16(Bs + row * P_LDS + kc, LinvP + row * NB + kc, 16);
+        const bool okt = ok && (kc < nn);                              // nn is even unless the matrix order is odd
+        cp_async16(Ts + row * P_LDS + kc, okt ? T + (size_t)row * ld + kc : T, okt ? min(16, (nn - kc) * 8) : 0);
     }
     cp_async_commit();
     cp_async_wait<0>();
     __syncthreads();
-    double acc[2][8][2];
-    const double* as = As + (warp * 16 + g) * P_LDS + tg;
+    double acc[8][2];
+    const double* as = As + (warp * 8 + g) * P_LDS + tg;
     const double* bs = Bs + g * P_LDS + tg;
     auto product = [&]() {
 #pragma unroll
-        for (int a = 0; a < 2; a++)
-#pragma unroll
-            for (int b = 0; b < 8; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
+        for (int b = 0; b < 8; b++) acc[b][0] = acc[b][1] = 0.0;
 #pragma unroll
         for (int kk = 0; kk < 16; kk++) {
-            double af[2], bf[8];
-#pragma unroll
-            for (int mt = 0; mt < 2; mt++) af[mt] = as[mt * 8 * P_LDS + kk * 4];
+            double bf[8];
+            const double af = as[kk * 4];
 #pragma unroll
             for (int nt = 0; nt < 8; nt++) bf[nt] = bs[nt * 8 * P_LDS + kk * 4];
 #pragma unroll
-            for (int mt = 0; mt < 2; mt++)
-#pragma unroll
-                for (int nt = 0; nt < 8; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
+            for (int nt = 0; nt < 8; nt++) dmma884(acc[nt][0], acc[nt][1], af, bf[nt]);
         }
     };
     product();                       // W = B * LinvP'
     __syncthreads();                 // everybody is done reading As / Bs
 #pragma unroll
-    for (int mt = 0; mt < 2; mt++)
+    for (int nt = 0; nt < 8; nt++)
 #pragma unroll
-        for (int nt = 0; nt < 8; nt++)
-#pragma unroll
-            for (int e = 0; e < 2; e++) As[(warp * 16 + mt * 8 + g) * P_LDS + nt * 8 + tg * 2 + e] = acc[mt][nt][e];
+        for (int e = 0; e < 2; e++) As[(warp * 8 + g) * P_LDS + nt * 8 + tg * 2 + e] = acc[nt][e];
     __syncthreads();
     {
         const int col = tid & 63;
@@ -846,8 +845,8 @@ __global__ void __launch_bounds__(128) ldlt_mini_kernel(double* __restrict__ B, 
         const double ibn = (k == 1) ? sib[col] : ((k == 2) ? sib[col - 1] : 0.0);
         const int nbr = (k == 1) ? col + 1 : ((k == 2) ? col - 1 : col);
 #pragma unroll 4
-        for (int i = 0; i < 32; i++) {
-            const int r = (tid >> 6) + 2 * i;
+        for (int i = 0; i < 16; i++) {
+            const int r = (tid >> 6) + 4 * i;
             const double wv = As[r * P_LDS + col];
             const double lv = wv * ia + As[r * P_LDS + nbr] * ibn;
             Bs[r * P_LDS + col] = lv;                 // rows >= nn are exact zeros (zero-filled loads)
@@ -859,15 +858,14 @@ __global__ void __launch_bounds__(128) ldlt_mini_kernel(double* __restrict__ B, 
     }
     __syncthreads();
     product();                       // W * L'
-#pragma unroll
-    for (int mt = 0; mt < 2; mt++) {
-        const int i = warp * 16 + mt * 8 + g;
+    {
+        const int i = warp * 8 + g;
 #pragma unroll
         for (int nt = 0; nt < 8; nt++)
 #pragma unroll
             for (int e = 0; e < 2; e++) {
                 const int j = nt * 8 + tg * 2 + e;
-                if (i < nn && j < nn) T[(size_t)i * ld + j] -= acc[mt][nt][e];
+                if (i < nn && j < nn) T[(size_t)i * ld + j] = Ts[i * P_LDS + j] - acc[nt][e];
             }
     }
     __syncthreads();
@@ -905,7 +903,7 @@ __global__ void ldlt_wait_sig_kernel(int* sig) {
 inline int ldlt_init_attrs() {
     CU(cudaFuncSetAttribute(ldlt_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM));
     CU(cudaFuncSetAttribute(ldlt_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM));
-    CU(cudaFuncSetAttribute(ldlt_mini_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM));
+    CU(cudaFuncSetAttribute(ldlt_mini_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MINI_SMEM));
     CU(cudaFuncSetAttribute(gemm_nt_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM));
     CU(cudaFuncSetAttribute(gemm_nt_sub64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S_SMEM));
     return 0;
@@ -956,7 +954,7 @@ inline int ldlt_factor_launch(LdltWs& w, cudaStream_t st) {
                 if (mcols > 0) RET(gemm_nt_sub(st, C11, ld, rows, mcols, Wt, NBO, B, ld, NB, w.counts));
             } else {
                 CU(cudaEventRecord(w.ev_tile, st));
-                ldlt_mini_kernel<<<1, 128, PANEL_SMEM, st>>>(B, ld, rows, Lk, ia + k0, ib + k0, w.kind + k0, Wt, NBO, C11, w.counts);
+                ldlt_mini_kernel<<<1, MINI_THREADS, MINI_SMEM, st>>>(B, ld, rows, Lk, ia + k0, ib + k0, w.kind + k0, Wt, NBO, C11, w.counts);
                 LAUNCHED();
                 CU(cudaEventRecord(w.ev_mini, st));
                 CU(cudaStreamWaitEvent(w.upd, w.ev_tile, 0));
