@@ -45,6 +45,8 @@ struct LdltWs {
     cudaStream_t st = nullptr;
     double* Wp2 = nullptr;     // second / third outer-panel scratch (look-ahead depth 2: triple buffering)
     double* Wp3 = nullptr;
+    double* Wp4 = nullptr;
+    cudaStream_t urg = nullptr;    // urgent pieces of the trailing update (block columns of the next two panels)
     cudaEvent_t ev_urg[2] = {nullptr, nullptr};
     cudaStream_t side = nullptr;   // trailing updates beyond the next panel run here, overlapped with the next panel
     cudaEvent_t ev_panel[2] = {nullptr, nullptr}, ev_upd[2] = {nullptr, nullptr};
@@ -75,6 +77,7 @@ inline int ldlt_alloc(LdltWs& w, int n, cudaStream_t st, bool background = false
     CU(cudaMalloc(&w.Wp, sizeof(double) * npad * 256));
     CU(cudaMalloc(&w.Wp2, sizeof(double) * npad * 256));
     CU(cudaMalloc(&w.Wp3, sizeof(double) * npad * 256));
+    CU(cudaMalloc(&w.Wp4, sizeof(double) * npad * 256));
     // the serial chain (tile -> panel -> in-panel update) is captured on a HIGH-priority stream, the bulk trailing
     // updates on a LOW-priority one: a chain kernel never queues behind a full wave of long update CTAs (captured
     // kernel nodes inherit the priority of the stream they were captured on)
@@ -93,6 +96,7 @@ inline int ldlt_alloc(LdltWs& w, int n, cudaStream_t st, bool background = false
     CU(cudaStreamCreateWithPriority(&w.side, cudaStreamNonBlocking, p_side));
     CU(cudaStreamCreateWithPriority(&w.cap, cudaStreamNonBlocking, p_chain));
     CU(cudaStreamCreateWithPriority(&w.upd, cudaStreamNonBlocking, p_chain));
+    CU(cudaStreamCreateWithPriority(&w.urg, cudaStreamNonBlocking, std::min(p_chain + 1, p_side)));
     CU(cudaEventCreateWithFlags(&w.ev_tile, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&w.ev_mini, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&w.ev_urest, cudaEventDisableTiming));
@@ -121,7 +125,8 @@ inline int ldlt_alloc(LdltWs& w, int n, cudaStream_t st, bool background = false
     return 0;
 }
 inline void ldlt_free(LdltWs& w) {
-    cudaFree(w.A); cudaFree(w.Wp); cudaFree(w.Wp2); cudaFree(w.Wp3);
+    cudaFree(w.A); cudaFree(w.Wp); cudaFree(w.Wp2); cudaFree(w.Wp3); cudaFree(w.Wp4);
+    if (w.urg) cudaStreamDestroy(w.urg);
     for (int i = 0; i < 2; i++) if (w.ev_urg[i]) cudaEventDestroy(w.ev_urg[i]);
     if (w.gexec) cudaGraphExecDestroy(w.gexec);
     if (w.side) cudaStreamDestroy(w.side);
@@ -925,10 +930,10 @@ inline int ldlt_factor_launch(LdltWs& w, cudaStream_t st) {
     ldlt_reset_kernel<<<1, 1, 0, st>>>(w.counts, w.dstat, w.ticket);
     LAUNCHED();
     int p = 0;
-    bool side_used = false, upd_pending = false;
+    bool side_used = false, upd_pending = false, u1_used = false, urg_used = false, r_prev = false;
     for (int c0 = 0; c0 < n; c0 += NBO, p++) {
         const int c1 = min(c0 + NBO, n);
-        double* Wb = (p % 3 == 0) ? w.Wp : ((p % 3 == 1) ? w.Wp2 : w.Wp3);
+        double* Wb = (p % 4 == 0) ? w.Wp : ((p % 4 == 1) ? w.Wp2 : ((p % 4 == 2) ? w.Wp3 : w.Wp4));
         for (int k0 = c0; k0 < c1; k0 += NB) {
             const int k = k0 / NB, nb = min(NB, n - k0), k1 = k0 + nb;
             double* Akk = w.A + (size_t)k0 * ld + k0;
@@ -977,36 +982,64 @@ inline int ldlt_factor_launch(LdltWs& w, cudaStream_t st) {
         const double* Wpan = Wb + (size_t)c1 * NBO;                      // W rows c1..n of this outer panel
         const double* Lpan = w.A + (size_t)c1 * ld + c0;                 // L rows c1..n
         const int na = min(NBO, rows2);                                  // width of the next outer panel
+        CU(cudaEventRecord(w.ev_panel[p & 1], st));                      // W / L of panel p are complete
         // (a) next panel's columns, chain stream: A[c1:, c1:c1+na] -= W L[c1:c1+na]^T.  The same columns were
-        // read-modify-written by the URGENT part of the previous panel's side update, which must be complete.
-        if (p >= 1 && side_used) CU(cudaStreamWaitEvent(st, w.ev_urg[(p - 1) & 1], 0));
+        // read-modify-written by U1 of the previous panel, which must be complete.
+        if (p >= 1 && u1_used) CU(cudaStreamWaitEvent(st, w.ev_urg[(p - 1) & 1], 0));
         RET(gemm_nt_sub(st, w.A + (size_t)c1 * ld + c1, ld, rows2, na, Wpan, NBO, Lpan, ld, kw, w.counts));
-        // (b) everything to the right of the next panel, side stream, in two pieces: first the columns of the panel
-        // AFTER the next one (urgent: the chain needs them one panel later), then the rest (lower tiles only).  The rest
-        // has two panel periods to finish before anything waits for it (look-ahead depth 2; W is triple buffered).
+        // (b) everything to the right of the next panel, in three pieces on two more streams (look-ahead depth 3, W in
+        // four buffers): U1 = the block column of panel p+2 and U2 = that of panel p+3 on the URGENT stream, R = the
+        // rest (lower tiles only, persistent SM-budgeted kernel) on the bulk stream.  Per block column q the updates are
+        // ordered  R_(q-4) -> U2_(q-3) -> U1_(q-2) -> (a)_(q-1): the urgent stream is in order, U2 waits for the
+        // previous panel's R, (a) waits for U1.  An R therefore has two panel periods before anything waits for it,
+        // and the short urgent pieces never queue behind it.
+        u1_used = false;
         const int rows3 = rows2 - na;
         if (rows3 > 0) {
-            CU(cudaEventRecord(w.ev_panel[p & 1], st));
-            CU(cudaStreamWaitEvent(sd, w.ev_panel[p & 1], 0));
+            CU(cudaStreamWaitEvent(w.urg, w.ev_panel[p & 1], 0));
             const int na2 = min(NBO, rows3);
             const int o2 = c1 + na;
-            RET(gemm_nt_sub(sd, w.A + (size_t)o2 * ld + o2, ld, rows3, na2, Wpan + (size_t)na * NBO, NBO, Lpan + (size_t)na * ld, ld, kw,
-                            w.counts));
-            CU(cudaEventRecord(w.ev_urg[p & 1], sd));
+            RET(gemm_nt_sub(w.urg, w.A + (size_t)o2 * ld + o2, ld, rows3, na2, Wpan + (size_t)na * NBO, NBO, Lpan + (size_t)na * ld, ld,
+                            kw, w.counts));
+            CU(cudaEventRecord(w.ev_urg[p & 1], w.urg));
+            u1_used = true;
+            urg_used = true;
             const int rows4 = rows3 - na2;
+            bool r_now = false;
             if (rows4 > 0) {
+                const int na3 = min(NBO, rows4);
                 const int o3 = o2 + na2;
-                GemmArgs u{};
-                u.C = w.A + (size_t)o3 * ld + o3; u.ldc = ld; u.Cin = u.C; u.ldcin = ld; u.n = rows4; u.m = rows4;
-                u.beta = 1.0; u.mode = GEMM_LOWER_ONLY; u.nterms = 1; u.ctrl = w.counts; u.max_ctas = w.side_ctas;
-                u.t[0] = GemmTerm{Wpan + (size_t)(na + na2) * NBO, Lpan + (size_t)(na + na2) * ld, nullptr, NBO, ld, kw, -1.0};
-                RET(gemm_nt(sd, u));
+                if (r_prev) CU(cudaStreamWaitEvent(w.urg, w.ev_upd[(p - 1) & 1], 0));
+                RET(gemm_nt_sub(w.urg, w.A + (size_t)o3 * ld + o3, ld, rows4, na3, Wpan + (size_t)(na + na2) * NBO, NBO,
+                                Lpan + (size_t)(na + na2) * ld, ld, kw, w.counts));
+                const int rows5 = rows4 - na3;
+                if (rows5 > 0) {
+                    const int o4 = o3 + na3;
+                    CU(cudaStreamWaitEvent(sd, w.ev_panel[p & 1], 0));
+                    GemmArgs u{};
+                    u.C = w.A + (size_t)o4 * ld + o4; u.ldc = ld; u.Cin = u.C; u.ldcin = ld; u.n = rows5; u.m = rows5;
+                    u.beta = 1.0; u.mode = GEMM_LOWER_ONLY; u.nterms = 1; u.ctrl = w.counts; u.max_ctas = w.side_ctas;
+                    u.t[0] = GemmTerm{Wpan + (size_t)(na + na2 + na3) * NBO, Lpan + (size_t)(na + na2 + na3) * ld, nullptr, NBO, ld, kw, -1.0};
+                    RET(gemm_nt(sd, u));
+                    CU(cudaEventRecord(w.ev_upd[p & 1], sd));
+                    r_now = true;
+                    side_used = true;
+                }
             }
-            CU(cudaEventRecord(w.ev_upd[p & 1], sd));
-            side_used = true;
+            r_prev = r_now;
+        } else {
+            r_prev = false;
         }
     }
-    if (side_used) CU(cudaStreamWaitEvent(st, w.ev_upd[(p - 1) & 1], 0));   // join (no-op if already waited)
+    // join the forked streams
+    if (urg_used) {
+        CU(cudaEventRecord(w.ev_urg[0], w.urg));
+        CU(cudaStreamWaitEvent(st, w.ev_urg[0], 0));
+    }
+    if (side_used) {
+        CU(cudaEventRecord(w.ev_upd[0], sd));
+        CU(cudaStreamWaitEvent(st, w.ev_upd[0], 0));
+    }
     return 0;
 }
 // The ~230 short, mutually dependent launches of one factorisation are captured ONCE per workspace into a CUDA graph
