@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define B200IPM_VERSION 101
+#define B200IPM_VERSION 102
 
 typedef struct b200ipm_engine* b200ipm_handle;
 typedef struct b200ipm_ldlt*   b200ipm_ldlt_handle;

@@ -2,6 +2,7 @@
 # end-of-session evidence run: full GPU test suite, bench (both arms), ncu launch list + full capture of the top kernel
 mkdir -p gpurun_out
 TAG=${1:-s2}
+timeout 120 python __graft_entry__.py smoke 2>&1 | tail -2
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -6 > gpurun_out/${TAG}_tests.log
 tail -3 gpurun_out/${TAG}_tests.log
 timeout 300 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err

@@ -6,7 +6,7 @@ from pyipm_b200 import _lib, problems
 
 prob = problems.make_nlp()
 flags = int(sys.argv[1]) if len(sys.argv) > 1 else 6
-for fg, bg in [(96, 48), (0, 0), (128, 64), (128, 96), (112, 112), (0, 96), (96, 96), (64, 64)]:
+for fg, bg in [(96, 48), (0, 48), (132, 48), (120, 48), (108, 48), (84, 48), (72, 48)]:
     os.environ['B200IPM_SIDE_FG'] = str(fg)
     os.environ['B200IPM_SIDE_BG'] = str(bg)
     eng = _lib.Engine(prob.nvar, prob.neq, prob.nineq, _lib.default_params(flags=flags))
