@@ -1046,7 +1046,10 @@ inline int ldlt_factor_launch(LdltWs& w, cudaStream_t st) {
 // (both streams; fork/join through the events) and replayed: the matrix lives in the same buffers every time, so
 // only the launch overhead changes.  Falls back to direct launches if capture is not possible.
 inline int ldlt_factor(LdltWs& w) {
-    if (w.graph_state == 1 && (w.graph_u != w.pivot_u || w.graph_sig_tile != w.sig_tile)) {   // baked parameters changed: rebuild
+    // A different pivot threshold (the rare strict re-factorisation) is launched directly and leaves the cached graph
+    // alone: re-capturing twice (there and back) costs ~20 ms, 230 direct launches less than 1 ms.
+    if (w.graph_state == 1 && w.graph_u != w.pivot_u) return ldlt_factor_launch(w, w.st);
+    if (w.graph_state == 1 && w.graph_sig_tile != w.sig_tile) {   // baked parameter changed: rebuild
         cudaGraphExecDestroy(w.gexec);
         w.gexec = nullptr;
         w.graph_state = 0;
