@@ -724,6 +724,12 @@ static int soc_direction(Eng* h, const double* cnew /* device, M+N */, double* p
                 axpby_kernel<<<cdiv(N, 256), 256, 0, h->st>>>(N, 1.0, h->ycor + M, 1.0, pz + D, h->ycor + M);
                 LAUNCHED();
             }
+            // a consistent system (full-rank Jacobian) converges in one or two sweeps: stop when the residual is at
+            // rounding level; an inconsistent / rank-deficient one never gets there and takes all six (the pinv limit)
+            absmax2_kernel<<<1, 1024, 0, h->st>>>(C, h->ycor, cnew, h->red + 12);
+            LAUNCHED();
+            RET(fetch_red(h, h->red + 12, 2));
+            if (h->h_red[0] <= 1e-13 * h->h_red[1]) break;
         }
         RET(ldlt_solve(h->F2, h->ycor, h->rho));                                            // u = G^-1 r
         // z_x += J u ; z_s += -u_i

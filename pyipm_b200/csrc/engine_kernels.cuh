@@ -598,6 +598,28 @@ __global__ void __launch_bounds__(256) row_sqnorm_max_kernel(const double* __res
     if (threadIdx.x == 0) part[blockIdx.x] = m;
 }
 
+// out[0] = max |a|, out[1] = max |b|   (one CTA; NaNs propagate as +inf so that callers never stop early on them)
+__global__ void __launch_bounds__(1024) absmax2_kernel(int n, const double* __restrict__ a, const double* __restrict__ b,
+                                                       double* __restrict__ out) {
+    double ma = 0.0, mb = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double x = fabs(a[i]), y = fabs(b[i]);
+        ma = (x <= 1.7e308) ? fmax(ma, x) : INFINITY;
+        mb = (y <= 1.7e308) ? fmax(mb, y) : INFINITY;
+    }
+    __shared__ double sh[2][32];
+    ma = warp_max(ma);
+    mb = warp_max(mb);
+    if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = ma; sh[1][threadIdx.x >> 5] = mb; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double ta = 0.0, tb = 0.0;
+        for (int k = 0; k < (int)(blockDim.x >> 5); k++) { ta = fmax(ta, sh[0][k]); tb = fmax(tb, sh[1][k]); }
+        out[0] = ta;
+        out[1] = tb;
+    }
+}
+
 // ------------------------------------------------------------------------------------------- curvature certificate
 // rhs = [u; 0]  (length Kc = D + M)
 __global__ void cert_rhs_kernel(int D, int Kc, const double* __restrict__ u, double* __restrict__ rhs) {
