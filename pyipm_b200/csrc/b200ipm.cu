@@ -494,8 +494,9 @@ static int factor_regularised(Eng* h, b200ipm_step_info* info, bool allow_abando
 // Collect the verdict of the background delta = 0 test.  *redo = true: the tentative choice of B was not what the
 // reference's loop would have done (A passes, A asks for the eq-block regularisation, or A was abandoned while B
 // looks singular) -- the caller restarts the step's factorisation sequentially from the incoming delta.
-static int resolve_pending(Eng* h, b200ipm_step_info* info, bool* redo) {
+static int resolve_pending(Eng* h, b200ipm_step_info* info, bool* redo, bool* resolve_only) {
     *redo = false;
+    *resolve_only = false;
     if (!h->pendingA) return 0;
     h->pendingA = false;
     CU(cudaStreamSynchronize(h->stB));
@@ -536,6 +537,20 @@ static int resolve_pending(Eng* h, b200ipm_step_info* info, bool* redo) {
     h->first_failed_last = a_fails;
     if (a_fails && !a_eqreg && !hidden_singular) return 0;
     h->delta = h->pend_delta_in;
+    if (!a_fails && !abA) {
+        // the unshifted matrix passes (pyipm.py:1381): its factorisation already exists in the background workspace --
+        // adopt it (device-to-device copy of the factor data, ~0.1 ms) and only redo the solve
+        RET(ldlt_copy_factor(h->F, h->Fb, h->st));
+        h->delta_eff = 0.0;
+        h->reg_cur = 0.0;
+        if (info) {
+            info->n_neg = nA; info->n_zero = zA; info->n_factor = 1; info->eq_reg = 0; info->delta = h->delta;
+            info->n_spec = 1; info->spec_used = 0;
+        }
+        *redo = true;
+        *resolve_only = true;
+        return 0;
+    }
     *redo = true;
     return 0;
 }
@@ -927,10 +942,11 @@ static int compute_direction(Eng* h, b200ipm_step_info* info) {
     CU(cudaEventRecord(h->ev[EV_FACTOR], h->st));
     RET(solve_direction(h, info));
     {
-        bool redo = false;
-        RET(resolve_pending(h, info, &redo));
+        bool redo = false, resolve_only = false;
+        RET(resolve_pending(h, info, &redo, &resolve_only));
         if (redo) {
-            RET(factor_regularised(h, info, /*allow_abandon=*/false, /*allow_spec=*/false));   // every pivot of every test is seen
+            if (!resolve_only)
+                RET(factor_regularised(h, info, /*allow_abandon=*/false, /*allow_spec=*/false));   // every pivot of every test is seen
             RET(solve_direction(h, info));
         }
     }

@@ -1241,6 +1241,20 @@ inline int ldlt_init_solve_attrs() {
     return 0;
 }
 
+// dst <- the factorisation held by src (same order): factor, per-tile inverses, D blocks, kinds, inertia counters.
+// Lets the engine adopt a factorisation computed in another workspace without touching streams or captured graphs.
+inline int ldlt_copy_factor(LdltWs& dst, const LdltWs& src, cudaStream_t st) {
+    if (dst.n != src.n || dst.ld != src.ld) return fail_msg("ldlt_copy_factor: workspaces differ");
+    const size_t npad = (size_t)src.nblk * NB;
+    CU(cudaMemcpyAsync(dst.A, src.A, sizeof(double) * npad * src.ld, cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(dst.LinvP, src.LinvP, sizeof(double) * (size_t)src.nblk * NB * NB, cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(dst.dinfo, src.dinfo, sizeof(double) * 4 * npad, cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(dst.kind, src.kind, sizeof(int) * npad, cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(dst.counts, src.counts, sizeof(int) * 4, cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(dst.dstat, src.dstat, sizeof(double) * 2, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
 // Work vectors of one triangular solve; a second set lets two solves with the SAME factorisation run concurrently on
 // two streams (the factor is only read).
 struct LdltSolveBuf { double *yv = nullptr, *zv = nullptr, *xv = nullptr; unsigned* ticket = nullptr; };
