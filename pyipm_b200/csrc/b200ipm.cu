@@ -1594,7 +1594,7 @@ int b200ipm_ldlt_tile_factor(b200ipm_ldlt_handle h, double* tile_dev, int ld, in
         h->tile_counts_live = true;
     }
     ldlt_tile_kernel<<<1, TILE_THREADS, TILE_SMEM, h->st>>>(tile_dev, ld, nb, linv_dev, dblk_dev, dblk_dev + NB, dblk_dev + 2 * NB,
-                                                   dblk_dev + 3 * NB, kind, perm_dev, h->F.counts, h->F.dstat, h->F.pivot_u, nullptr);
+                                                   dblk_dev + 3 * NB, kind, perm_dev, h->F.counts, h->F.dstat, h->F.pivot_u, nullptr, h->F.tile_blocked);
     LAUNCHED();
     if (counts) {
         int cnt[4];

@@ -54,6 +54,7 @@ struct LdltWs {
     cudaEvent_t ev_tile = nullptr, ev_mini = nullptr, ev_urest = nullptr;
     int* sig = nullptr;            // device word set to 1 when tile step sig_tile starts (baked into the graph)
     int sig_tile = -1;
+    int tile_blocked = 0;          // B200IPM_TILE_BLOCKED=1: blocked fast attempt inside the tile kernel
     int use_mini = 1;              // B200IPM_LDLT_MINI=0 restores the tile -> panel -> update chain
     cudaStream_t cap = nullptr;    // internal capture-origin stream (the caller's stream may be the legacy default one)
     cudaGraphExec_t gexec = nullptr;
@@ -101,6 +102,7 @@ inline int ldlt_alloc(LdltWs& w, int n, cudaStream_t st, bool background = false
     CU(cudaEventCreateWithFlags(&w.ev_mini, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&w.ev_urest, cudaEventDisableTiming));
     { const char* e = getenv("B200IPM_LDLT_MINI"); if (e) w.use_mini = atoi(e); }
+    { const char* e = getenv("B200IPM_TILE_BLOCKED"); if (e) w.tile_blocked = atoi(e); }
     for (int i = 0; i < 2; i++) {
         CU(cudaEventCreateWithFlags(&w.ev_panel[i], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&w.ev_upd[i], cudaEventDisableTiming));
@@ -281,13 +283,154 @@ __device__ __forceinline__ void tile_fast_block(double (&b)[TILE_RPW][2], int nb
     }
 }
 
+// Blocked variant of the fast attempt (same acceptance rule, same outputs: L^-1 in Xf, pivots in sda).
+// The 64 x 64 tile is eliminated in eight 8-column blocks:
+//   (1) panel: ONE warp holds the 64 x 8 column panel in registers (rows lane, lane + 32) and runs the eight pivot steps
+//       with shuffles only -- no CTA barrier inside a block; every lane applies the sticky threshold test
+//       |d_j| >= u |T[i][j]| to the entries it owns;
+//   (2) the trailing part of the tile gets its rank-8 update  T -= (L D) L'  from all eight warps by DMMA
+//       (lower 8 x 8 sub-tiles only: the elimination never reads the upper triangle);
+//   (3) after the last block  X = L^-1  is built by block forward substitution, one block column per warp:
+//       X_jj = inv(L_jj),  X_ij = -X_ii * sum_{k=j}^{i-1} L_ik X_kj.
+// Two CTA barriers per block instead of one per pivot step.
+__device__ __forceinline__ void tile_fast_blocked(double* __restrict__ Tf, double* __restrict__ Xf, double* __restrict__ sda,
+                                                  double* __restrict__ xscr, int nb, int lane, int warp, double pivot_u,
+                                                  int& viol, bool& allpos, bool& allneg) {
+    const int g = lane >> 2, tg = lane & 3;
+#ifdef TILE_PROF
+    long long cy_panel = 0, cy_upd = 0, cy_x = 0, cy_t = clock64();
+#endif
+#pragma unroll 1
+    for (int kb = 0; kb < NB / 8; kb++) {
+        const int c0 = 8 * kb;
+        if (warp == 0) {
+            double p0[8], p1[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                p0[j] = Tf[lane * NBP + c0 + j];
+                p1[j] = Tf[(lane + 32) * NBP + c0 + j];
+            }
+            const bool hi = (kb >= 4);                 // the block's own rows live in the upper half of the lanes' rows
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int piv = c0 + j;
+                const double d = __shfl_sync(0xffffffffu, hi ? p1[j] : p0[j], piv & 31);
+                const double dinv = (d != 0.0) ? fast_rcp(d) : 0.0;
+                const bool act0 = lane > piv, act1 = (lane + 32) > piv;
+                const double thr = fabs(d);
+                viol |= ((act0 && pivot_u * fabs(p0[j]) > thr) || (act1 && pivot_u * fabs(p1[j]) > thr)) ? 1 : 0;
+                if (piv < nb) {
+                    allpos = allpos && (d > 0.0);
+                    allneg = allneg && (d < 0.0);
+                }
+                const double l0 = act0 ? p0[j] * dinv : 0.0;
+                const double l1 = act1 ? p1[j] * dinv : 0.0;
+#pragma unroll
+                for (int jj = j + 1; jj < 8; jj++) {
+                    // T[piv][c0 + jj] = T[c0 + jj][piv] (symmetry): column j of the panel, row c0 + jj
+                    const double prj = __shfl_sync(0xffffffffu, hi ? p1[j] : p0[j], (c0 + jj) & 31);
+                    p0[jj] = fma(-l0, prj, p0[jj]);
+                    p1[jj] = fma(-l1, prj, p1[jj]);
+                }
+                if (act0) p0[j] = l0;
+                if (act1) p1[j] = l1;
+                if (lane == 0) sda[piv] = d;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                if (lane >= c0 + j) Tf[lane * NBP + c0 + j] = p0[j];
+                if (lane + 32 >= c0 + j) Tf[(lane + 32) * NBP + c0 + j] = p1[j];
+            }
+        }
+        __syncthreads();
+#ifdef TILE_PROF
+        { const long long t = clock64(); cy_panel += t - cy_t; cy_t = t; }
+#endif
+        if (kb < NB / 8 - 1) {
+            const int nbt = NB / 8 - 1 - kb;
+            const int ntiles = nbt * (nbt + 1) / 2;
+            for (int t = warp; t < ntiles; t += TILE_THREADS / 32) {
+                int bi = 0, rem = t;
+                while (rem > bi) { rem -= bi + 1; bi++; }
+                const int BI = kb + 1 + bi, BM = kb + 1 + rem;
+                double* cp = Tf + (8 * BI + g) * NBP + 8 * BM + 2 * tg;
+                double acc0 = cp[0], acc1 = cp[1];
+#pragma unroll
+                for (int kk = 0; kk < 8; kk += 4) {
+                    const int col = c0 + kk + tg;
+                    const double av = -Tf[(8 * BI + g) * NBP + col] * sda[col];
+                    const double bv = Tf[(8 * BM + g) * NBP + col];
+                    dmma884(acc0, acc1, av, bv);
+                }
+                cp[0] = acc0;
+                cp[1] = acc1;
+            }
+        }
+        __syncthreads();
+#ifdef TILE_PROF
+        { const long long t = clock64(); cy_upd += t - cy_t; cy_t = t; }
+#endif
+    }
+    // ---- X = L^-1.  Diagonal blocks first (warp b, lanes 0..7: one column each, forward substitution)
+    if (lane < 8) {
+        const int b0 = 8 * warp, c = lane;
+        double x[8];
+#pragma unroll
+        for (int r = 0; r < 8; r++) x[r] = (r == c) ? 1.0 : 0.0;
+#pragma unroll
+        for (int r = 1; r < 8; r++) {
+            double sacc = 0.0;
+#pragma unroll
+            for (int k = 0; k < r; k++) sacc = fma(Tf[(b0 + r) * NBP + b0 + k], x[k], sacc);   // x[k] = 0 for k < c
+            if (r > c) x[r] = -sacc;
+        }
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+            if (r >= c) Xf[(b0 + r) * NBP + b0 + c] = x[r];
+    }
+    __syncthreads();
+    {
+        const int j = warp;                            // block column
+        double* scr = xscr + warp * 64;
+        for (int i = j + 1; i < NB / 8; i++) {
+            double s0 = 0.0, s1 = 0.0;
+            for (int k = j; k < i; k++) {
+#pragma unroll
+                for (int kk = 0; kk < 8; kk += 4) {
+                    const double av = Tf[(8 * i + g) * NBP + 8 * k + kk + tg];           // L_ik[g][kk + tg]
+                    const double bv = Xf[(8 * k + kk + tg) * NBP + 8 * j + g];           // X_kj[kk + tg][g]
+                    dmma884(s0, s1, av, bv);
+                }
+            }
+            scr[g * 8 + 2 * tg] = s0;
+            scr[g * 8 + 2 * tg + 1] = s1;
+            __syncwarp();
+            double x0 = 0.0, x1 = 0.0;
+#pragma unroll
+            for (int kk = 0; kk < 8; kk += 4) {
+                const double av = -Xf[(8 * i + g) * NBP + 8 * i + kk + tg];               // -X_ii[g][kk + tg]
+                const double bv = scr[(kk + tg) * 8 + g];                                 // S[kk + tg][g]
+                dmma884(x0, x1, av, bv);
+            }
+            Xf[(8 * i + g) * NBP + 8 * j + 2 * tg] = x0;
+            Xf[(8 * i + g) * NBP + 8 * j + 2 * tg + 1] = x1;
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+#ifdef TILE_PROF
+    cy_x = clock64() - cy_t;
+    if (warp == 0 && lane == 0) printf("TILE_PROF blocked: panel=%lld update=%lld xinv=%lld cycles\n", cy_panel, cy_upd, cy_x);
+#endif
+}
+
 __global__ void __launch_bounds__(TILE_THREADS) ldlt_tile_kernel(double* __restrict__ A, int ld, int nb,
                                                                  double* __restrict__ LinvP, double* __restrict__ dinv_a,
                                                                  double* __restrict__ dinv_b, double* __restrict__ d_a,
                                                                  double* __restrict__ d_b, int* __restrict__ kind,
                                                                  int* __restrict__ perm_out, int* __restrict__ counts,
                                                                  double* __restrict__ dstat, const double pivot_u,
-                                                                 int* __restrict__ sig) {
+                                                                 int* __restrict__ sig, const int blocked) {
     extern __shared__ __align__(16) double tsm[];
     if (sig != nullptr && threadIdx.x == 0) atomicExch(sig, 1);   // "this far" marker for a delayed background factorisation
     double* Tf = tsm;                 // T[i][m] = Tf[i * NBP + m]   (authoritative only inside slow steps / at the ends)
@@ -365,7 +508,23 @@ __global__ void __launch_bounds__(TILE_THREADS) ldlt_tile_kernel(double* __restr
     // Per step the serial chain is: barrier -> LDS pivot row -> rcp -> 2 FMA on the next pivot row -> STS.
     // =====================================================================================================
     int fast_ok = 0;
-    {
+    if (blocked) {
+        __shared__ double xscr[(TILE_THREADS / 32) * 64];
+        __shared__ int s_sign[2];
+        int viol = 0;
+        bool allpos = true, allneg = true;
+        tile_fast_blocked(Tf, Xf, sda, xscr, nb, lane, warp, pivot_u, viol, allpos, allneg);
+        if (tid == 0) { s_sign[0] = allpos ? 1 : 0; s_sign[1] = allneg ? 1 : 0; }   // tracked by warp 0 (lane-uniform)
+        const int anyviol = __syncthreads_or(viol);
+        const bool ap = s_sign[0] != 0, an = s_sign[1] != 0;
+        fast_ok = ((!anyviol) || ap || an) ? 1 : 0;
+        if (!(ap || an)) {
+            bool haszero = false;
+            for (int p2 = 0; p2 < nb; p2++) haszero = haszero || (sda[p2] == 0.0);
+            if (haszero) fast_ok = 0;
+        }
+        if (fast_ok && tid < NB) { sdb[tid] = 0.0; skind[tid] = 0; }
+    } else {
         double b[TILE_RPW][2];     // transposed ownership: rows lane / lane+32, columns warp + 8k
 #pragma unroll
         for (int k = 0; k < TILE_RPW; k++) {
@@ -940,7 +1099,7 @@ inline int ldlt_factor_launch(LdltWs& w, cudaStream_t st) {
             double* Lk = w.LinvP + (size_t)k * NB * NB;
             ldlt_tile_kernel<<<1, TILE_THREADS, TILE_SMEM, st>>>(Akk, ld, nb, Lk, ia + k0, ib + k0, da + k0, db + k0, w.kind + k0,
                                                         nullptr, w.counts, w.dstat, w.pivot_u,
-                                                        (k == w.sig_tile) ? w.sig : nullptr);
+                                                        (k == w.sig_tile) ? w.sig : nullptr, w.tile_blocked);
             LAUNCHED();
             const int rows = n - k1;
             if (rows <= 0) break;
