@@ -54,7 +54,7 @@ struct LdltWs {
     cudaEvent_t ev_tile = nullptr, ev_mini = nullptr, ev_urest = nullptr;
     int* sig = nullptr;            // device word set to 1 when tile step sig_tile starts (baked into the graph)
     int sig_tile = -1;
-    int tile_blocked = 0;          // B200IPM_TILE_BLOCKED=1: blocked fast attempt inside the tile kernel
+    int tile_blocked = 1;          // blocked fast attempt inside the tile kernel (B200IPM_TILE_BLOCKED=0: per-pivot barrier version)
     int use_mini = 1;              // B200IPM_LDLT_MINI=0 restores the tile -> panel -> update chain
     cudaStream_t cap = nullptr;    // internal capture-origin stream (the caller's stream may be the legacy default one)
     cudaGraphExec_t gexec = nullptr;
@@ -285,17 +285,19 @@ __device__ __forceinline__ void tile_fast_block(double (&b)[TILE_RPW][2], int nb
 
 // Blocked variant of the fast attempt (same acceptance rule, same outputs: L^-1 in Xf, pivots in sda).
 // The 64 x 64 tile is eliminated in eight 8-column blocks:
-//   (1) panel: ONE warp holds the 64 x 8 column panel in registers (rows lane, lane + 32) and runs the eight pivot steps
-//       with shuffles only -- no CTA barrier inside a block; every lane applies the sticky threshold test
-//       |d_j| >= u |T[i][j]| to the entries it owns;
+//   (1) the 8 x 8 diagonal block is factored by ONE thread entirely in registers (the serial chain of a pivot step is
+//       rcp -> mul -> fma, no shuffle and no barrier); the rows below it then follow independently, one thread per row,
+//       by forward substitution against U = D L8'.  The threshold test |d_j| >= u |T[i][j]| is applied in the
+//       equivalent form |l_ij| <= 1/u.  (A first version ran the whole 64 x 8 panel on one warp with shuffles: 483
+//       cycles per pivot, no faster than the per-pivot barrier kernel.)
 //   (2) the trailing part of the tile gets its rank-8 update  T -= (L D) L'  from all eight warps by DMMA
 //       (lower 8 x 8 sub-tiles only: the elimination never reads the upper triangle);
 //   (3) after the last block  X = L^-1  is built by block forward substitution, one block column per warp:
 //       X_jj = inv(L_jj),  X_ij = -X_ii * sum_{k=j}^{i-1} L_ik X_kj.
 // Two CTA barriers per block instead of one per pivot step.
 __device__ __forceinline__ void tile_fast_blocked(double* __restrict__ Tf, double* __restrict__ Xf, double* __restrict__ sda,
-                                                  double* __restrict__ xscr, int nb, int lane, int warp, double pivot_u,
-                                                  int& viol, bool& allpos, bool& allneg) {
+                                                  double* __restrict__ xscr, double* __restrict__ pinv, int nb, int lane, int warp,
+                                                  double pivot_u, int& viol, bool& allpos, bool& allneg) {
     const int g = lane >> 2, tg = lane & 3;
 #ifdef TILE_PROF
     long long cy_panel = 0, cy_upd = 0, cy_x = 0, cy_t = clock64();
@@ -303,43 +305,64 @@ __device__ __forceinline__ void tile_fast_blocked(double* __restrict__ Tf, doubl
 #pragma unroll 1
     for (int kb = 0; kb < NB / 8; kb++) {
         const int c0 = 8 * kb;
-        if (warp == 0) {
-            double p0[8], p1[8];
+        // (1a) the 8 x 8 diagonal block, by ONE thread entirely in registers: no shuffle, no barrier on the serial chain
+        if (warp == 0 && lane == 0) {
+            double a[8][8];
+#pragma unroll
+            for (int r = 0; r < 8; r++)
+#pragma unroll
+                for (int c = 0; c <= r; c++) a[r][c] = Tf[(c0 + r) * NBP + c0 + c];
+            const double lim = 1.0 / pivot_u;
 #pragma unroll
             for (int j = 0; j < 8; j++) {
-                p0[j] = Tf[lane * NBP + c0 + j];
-                p1[j] = Tf[(lane + 32) * NBP + c0 + j];
-            }
-            const bool hi = (kb >= 4);                 // the block's own rows live in the upper half of the lanes' rows
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const int piv = c0 + j;
-                const double d = __shfl_sync(0xffffffffu, hi ? p1[j] : p0[j], piv & 31);
+                const double d = a[j][j];
                 const double dinv = (d != 0.0) ? fast_rcp(d) : 0.0;
-                const bool act0 = lane > piv, act1 = (lane + 32) > piv;
-                const double thr = fabs(d);
-                viol |= ((act0 && pivot_u * fabs(p0[j]) > thr) || (act1 && pivot_u * fabs(p1[j]) > thr)) ? 1 : 0;
-                if (piv < nb) {
+                if (c0 + j < nb) {
                     allpos = allpos && (d > 0.0);
                     allneg = allneg && (d < 0.0);
                 }
-                const double l0 = act0 ? p0[j] * dinv : 0.0;
-                const double l1 = act1 ? p1[j] * dinv : 0.0;
+                double l[8];
 #pragma unroll
-                for (int jj = j + 1; jj < 8; jj++) {
-                    // T[piv][c0 + jj] = T[c0 + jj][piv] (symmetry): column j of the panel, row c0 + jj
-                    const double prj = __shfl_sync(0xffffffffu, hi ? p1[j] : p0[j], (c0 + jj) & 31);
-                    p0[jj] = fma(-l0, prj, p0[jj]);
-                    p1[jj] = fma(-l1, prj, p1[jj]);
+                for (int r = j + 1; r < 8; r++) {
+                    l[r] = a[r][j] * dinv;
+                    viol |= (fabs(l[r]) > lim) ? 1 : 0;          // |d_j| >= u |T[r][j]|  <=>  |l_rj| <= 1/u
                 }
-                if (act0) p0[j] = l0;
-                if (act1) p1[j] = l1;
-                if (lane == 0) sda[piv] = d;
+#pragma unroll
+                for (int r = j + 1; r < 8; r++)
+#pragma unroll
+                    for (int c = j + 1; c <= r; c++) a[r][c] = fma(-l[r], a[c][j], a[r][c]);
+#pragma unroll
+                for (int r = j + 1; r < 8; r++) a[r][j] = l[r];
+                sda[c0 + j] = d;
+                pinv[j] = dinv;
             }
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                if (lane >= c0 + j) Tf[lane * NBP + c0 + j] = p0[j];
-                if (lane + 32 >= c0 + j) Tf[(lane + 32) * NBP + c0 + j] = p1[j];
+            for (int r = 1; r < 8; r++)
+#pragma unroll
+                for (int c = 0; c < r; c++) Tf[(c0 + r) * NBP + c0 + c] = a[r][c];
+        }
+        __syncthreads();
+        // (1b) the rows below the block, one thread per row:  l_i U = t_i  with  U = D L8' (forward substitution along the
+        // eight columns; rows are independent)
+        {
+            const int row = c0 + 8 + (int)threadIdx.x;
+            if (row < NB) {
+                double t[8], l[8];
+#pragma unroll
+                for (int c = 0; c < 8; c++) t[c] = Tf[row * NBP + c0 + c];
+                const double lim = 1.0 / pivot_u;
+                int v = 0;
+#pragma unroll
+                for (int c = 0; c < 8; c++) {
+                    double acc = t[c];
+#pragma unroll
+                    for (int j = 0; j < c; j++) acc = fma(-l[j] * sda[c0 + j], Tf[(c0 + c) * NBP + c0 + j], acc);   // U[j][c] = d_j l_cj
+                    l[c] = acc * pinv[c];
+                    v |= (fabs(l[c]) > lim) ? 1 : 0;
+                }
+                viol |= v;
+#pragma unroll
+                for (int c = 0; c < 8; c++) Tf[row * NBP + c0 + c] = l[c];
             }
         }
         __syncthreads();
@@ -511,9 +534,10 @@ __global__ void __launch_bounds__(TILE_THREADS) ldlt_tile_kernel(double* __restr
     if (blocked) {
         __shared__ double xscr[(TILE_THREADS / 32) * 64];
         __shared__ int s_sign[2];
+        __shared__ double s_pinv[8];
         int viol = 0;
         bool allpos = true, allneg = true;
-        tile_fast_blocked(Tf, Xf, sda, xscr, nb, lane, warp, pivot_u, viol, allpos, allneg);
+        tile_fast_blocked(Tf, Xf, sda, xscr, s_pinv, nb, lane, warp, pivot_u, viol, allpos, allneg);
         if (tid == 0) { s_sign[0] = allpos ? 1 : 0; s_sign[1] = allneg ? 1 : 0; }   // tracked by warp 0 (lane-uniform)
         const int anyviol = __syncthreads_or(viol);
         const bool ap = s_sign[0] != 0, an = s_sign[1] != 0;
