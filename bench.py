@@ -61,7 +61,7 @@ class ClockSampler(object):
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE,
+                                          '--format=csv,noheader,nounits', '-lms', '20'], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, universal_newlines=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -298,12 +298,18 @@ def run_b200(args):
         pass
 
     def timed(fn, steps, warmup):
+        # nvidia-smi needs ~0.1 s before its first sample and K steps last well under that: the sampler starts before the
+        # warm-up, and extra untimed warm-up steps keep the GPU under the same load until samples are flowing, so that
+        # the clock record covers the load of the timed region (which follows immediately)
+        sampler = ClockSampler(local)
+        sampler.start()
         for _ in range(warmup):
+            fn()
+        t_wait = time.time()
+        while len(sampler.rows) < 2 and time.time() - t_wait < 2.0:
             fn()
         barrier()
         n0 = _lib.launch_count()
-        sampler = ClockSampler(local)
-        sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         infos = [fn() for _ in range(steps)]
