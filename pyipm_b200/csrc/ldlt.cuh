@@ -300,48 +300,66 @@ __device__ __forceinline__ void tile_fast_blocked(double* __restrict__ Tf, doubl
                                                   double pivot_u, int& viol, bool& allpos, bool& allneg) {
     const int g = lane >> 2, tg = lane & 3;
 #ifdef TILE_PROF
-    long long cy_panel = 0, cy_upd = 0, cy_x = 0, cy_t = clock64();
+    long long cy_x = 0, cy_t = clock64();
 #endif
+    // (1a) an 8 x 8 diagonal block, by ONE thread entirely in registers: no shuffle, no barrier on the serial chain
+    auto diag_block = [&](const int c0) {
+        double a[8][8];
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+#pragma unroll
+            for (int c = 0; c <= r; c++) a[r][c] = Tf[(c0 + r) * NBP + c0 + c];
+        const double lim = 1.0 / pivot_u;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const double d = a[j][j];
+            const double dinv = (d != 0.0) ? fast_rcp(d) : 0.0;
+            if (c0 + j < nb) {
+                allpos = allpos && (d > 0.0);
+                allneg = allneg && (d < 0.0);
+            }
+            double l[8];
+#pragma unroll
+            for (int r = j + 1; r < 8; r++) {
+                l[r] = a[r][j] * dinv;
+                viol |= (fabs(l[r]) > lim) ? 1 : 0;          // |d_j| >= u |T[r][j]|  <=>  |l_rj| <= 1/u
+            }
+#pragma unroll
+            for (int r = j + 1; r < 8; r++)
+#pragma unroll
+                for (int c = j + 1; c <= r; c++) a[r][c] = fma(-l[r], a[c][j], a[r][c]);
+#pragma unroll
+            for (int r = j + 1; r < 8; r++) a[r][j] = l[r];
+            sda[c0 + j] = d;
+            pinv[j] = dinv;
+        }
+#pragma unroll
+        for (int r = 1; r < 8; r++)
+#pragma unroll
+            for (int c = 0; c < r; c++) Tf[(c0 + r) * NBP + c0 + c] = a[r][c];
+    };
+    auto update_tile = [&](const int kb, const int t) {      // t-th lower 8 x 8 tile of the part behind block kb
+        const int c0 = 8 * kb;
+        int bi = 0, rem = t;
+        while (rem > bi) { rem -= bi + 1; bi++; }
+        const int BI = kb + 1 + bi, BM = kb + 1 + rem;
+        double* cp = Tf + (8 * BI + g) * NBP + 8 * BM + 2 * tg;
+        double acc0 = cp[0], acc1 = cp[1];
+#pragma unroll
+        for (int kk = 0; kk < 8; kk += 4) {
+            const int col = c0 + kk + tg;
+            const double av = -Tf[(8 * BI + g) * NBP + col] * sda[col];
+            const double bv = Tf[(8 * BM + g) * NBP + col];
+            dmma884(acc0, acc1, av, bv);
+        }
+        cp[0] = acc0;
+        cp[1] = acc1;
+    };
+    if (warp == 0 && lane == 0) diag_block(0);
 #pragma unroll 1
     for (int kb = 0; kb < NB / 8; kb++) {
         const int c0 = 8 * kb;
-        // (1a) the 8 x 8 diagonal block, by ONE thread entirely in registers: no shuffle, no barrier on the serial chain
-        if (warp == 0 && lane == 0) {
-            double a[8][8];
-#pragma unroll
-            for (int r = 0; r < 8; r++)
-#pragma unroll
-                for (int c = 0; c <= r; c++) a[r][c] = Tf[(c0 + r) * NBP + c0 + c];
-            const double lim = 1.0 / pivot_u;
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const double d = a[j][j];
-                const double dinv = (d != 0.0) ? fast_rcp(d) : 0.0;
-                if (c0 + j < nb) {
-                    allpos = allpos && (d > 0.0);
-                    allneg = allneg && (d < 0.0);
-                }
-                double l[8];
-#pragma unroll
-                for (int r = j + 1; r < 8; r++) {
-                    l[r] = a[r][j] * dinv;
-                    viol |= (fabs(l[r]) > lim) ? 1 : 0;          // |d_j| >= u |T[r][j]|  <=>  |l_rj| <= 1/u
-                }
-#pragma unroll
-                for (int r = j + 1; r < 8; r++)
-#pragma unroll
-                    for (int c = j + 1; c <= r; c++) a[r][c] = fma(-l[r], a[c][j], a[r][c]);
-#pragma unroll
-                for (int r = j + 1; r < 8; r++) a[r][j] = l[r];
-                sda[c0 + j] = d;
-                pinv[j] = dinv;
-            }
-#pragma unroll
-            for (int r = 1; r < 8; r++)
-#pragma unroll
-                for (int c = 0; c < r; c++) Tf[(c0 + r) * NBP + c0 + c] = a[r][c];
-        }
-        __syncthreads();
+        __syncthreads();                   // diagonal block kb is factored; the update behind block kb-1 is complete
         // (1b) the rows below the block, one thread per row:  l_i U = t_i  with  U = D L8' (forward substitution along the
         // eight columns; rows are independent)
         {
@@ -366,34 +384,22 @@ __device__ __forceinline__ void tile_fast_blocked(double* __restrict__ Tf, doubl
             }
         }
         __syncthreads();
-#ifdef TILE_PROF
-        { const long long t = clock64(); cy_panel += t - cy_t; cy_t = t; }
-#endif
+        // (2) rank-8 update of the lower tiles behind the block.  Warp 0 takes the next diagonal tile first and thread 0
+        // goes straight on to factor it (pinv and the next sda entries are free again: (1b) is over), overlapped with
+        // the other seven warps updating the remaining tiles.
         if (kb < NB / 8 - 1) {
             const int nbt = NB / 8 - 1 - kb;
             const int ntiles = nbt * (nbt + 1) / 2;
-            for (int t = warp; t < ntiles; t += TILE_THREADS / 32) {
-                int bi = 0, rem = t;
-                while (rem > bi) { rem -= bi + 1; bi++; }
-                const int BI = kb + 1 + bi, BM = kb + 1 + rem;
-                double* cp = Tf + (8 * BI + g) * NBP + 8 * BM + 2 * tg;
-                double acc0 = cp[0], acc1 = cp[1];
-#pragma unroll
-                for (int kk = 0; kk < 8; kk += 4) {
-                    const int col = c0 + kk + tg;
-                    const double av = -Tf[(8 * BI + g) * NBP + col] * sda[col];
-                    const double bv = Tf[(8 * BM + g) * NBP + col];
-                    dmma884(acc0, acc1, av, bv);
-                }
-                cp[0] = acc0;
-                cp[1] = acc1;
+            if (warp == 0) {
+                update_tile(kb, 0);
+                __syncwarp();
+                if (lane == 0) diag_block(c0 + 8);
+            } else {
+                for (int t = warp; t < ntiles; t += TILE_THREADS / 32 - 1) update_tile(kb, t);
             }
         }
-        __syncthreads();
-#ifdef TILE_PROF
-        { const long long t = clock64(); cy_upd += t - cy_t; cy_t = t; }
-#endif
     }
+    __syncthreads();
     // ---- X = L^-1.  Diagonal blocks first (warp b, lanes 0..7: one column each, forward substitution)
     if (lane < 8) {
         const int b0 = 8 * warp, c = lane;
@@ -443,7 +449,7 @@ __device__ __forceinline__ void tile_fast_blocked(double* __restrict__ Tf, doubl
     __syncthreads();
 #ifdef TILE_PROF
     cy_x = clock64() - cy_t;
-    if (warp == 0 && lane == 0) printf("TILE_PROF blocked: panel=%lld update=%lld xinv=%lld cycles\n", cy_panel, cy_upd, cy_x);
+    if (warp == 0 && lane == 0) printf("TILE_PROF blocked: total=%lld cycles\n", cy_x);
 #endif
 }
 
