@@ -34,6 +34,21 @@ class IPM(object):
         self.lda0 = lda0
         self.lambda_dev = lambda_dev  # ignored
         self.s0 = s0
+        from . import symbolic as _symbolic
+        if _symbolic.is_symbolic(f):
+            # the reference's expression input mode (pyipm.py:83-146): SymPy expressions of the symbols in x_dev instead
+            # of Aesara expressions of x_dev; polynomials are lowered to the device, anything else is differentiated
+            # symbolically into callables
+            assert x_dev is not None, 'symbolic f/ce/ci need x_dev = the sequence of SymPy symbols they are written in'
+            assert all(d is None for d in (df, d2f, dce, d2ce, dci, d2ci)), \
+                'with symbolic f/ce/ci the derivatives are generated; do not pass df/d2f/dce/d2ce/dci/d2ci'
+            lowered = _symbolic.lower(x_dev, f, ce, ci)
+            if isinstance(lowered, dict):
+                f, df, d2f = lowered['f'], lowered['df'], lowered['d2f']
+                ce, dce, d2ce = lowered.get('ce'), lowered.get('dce'), lowered.get('d2ce')
+                ci, dci, d2ci = lowered.get('ci'), lowered.get('dci'), lowered.get('d2ci')
+            else:
+                f, ce, ci = lowered, None, None
         self.problem = f if isinstance(f, (_problems.PolyProblem, _problems.QuadProblem)) else None
         self.f, self.df, self.d2f = f, df, d2f
         self.ce, self.dce, self.d2ce = ce, dce, d2ce
