@@ -1464,6 +1464,7 @@ int b200ipm_direction(b200ipm_handle h, double* dz, b200ipm_step_info* info) {
     CU(cudaSetDevice(h->device));
     b200ipm_step_info tmp{};
     if (!info) info = &tmp;
+    memset(info, 0, sizeof(*info));
     CU(cudaEventRecord(h->ev[EV_START], h->st));
     RET(compute_direction(h, info));
     RET(fetch_red(h, h->red + 8, 1));
