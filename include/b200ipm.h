@@ -84,7 +84,8 @@ typedef struct b200ipm_step_info {
                                         more than M negative pivots (n_neg_first is then a partial count) */
     int    cert_used;                /* 1 if the failure of the delta = 0 test was PROVEN by a negative-curvature vector in
                                         null(dce') instead of being computed (n_neg_first = -1) */
-    int    reserved;
+    int    n_factor_phys;            /* factorisations PHYSICALLY executed this step (n_factor counts the reference's
+                                        eigvalsh-equivalents: a proven delta = 0 failure is counted there but costs none here) */
 } b200ipm_step_info;
 
 int         b200ipm_version(void);

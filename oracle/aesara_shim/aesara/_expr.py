@@ -10,7 +10,7 @@ class Expr(object):
         self.args = args
 
     def eval(self, env):
-        vals = [a.eval(env) if isinstance(a, Expr) else a for a in self.args]
+        vals = [_ev(a, env) for a in self.args]
         return self.fn(*vals)
 
     # arithmetic
@@ -26,7 +26,11 @@ class Expr(object):
     def __neg__(self): return Expr(lambda a: -a, (self,))
 
     def __getitem__(self, idx):
-        return Expr(lambda a: a[idx], (self,))
+        return Sub(self, idx)
+
+    @property
+    def size(self):
+        return Expr(lambda a: np.asarray(a).size, (self,))
 
     @property
     def shape(self):
@@ -37,10 +41,44 @@ class Expr(object):
         return Expr(lambda a: a.T, (self,))
 
     def reshape(self, shp):
-        return Expr(lambda a: a.reshape(shp), (self,))
+        return Expr(lambda a, sh: np.asarray(a).reshape(sh), (self, shp))
 
     def ravel(self):
         return Expr(lambda a: a.ravel(), (self,))
+
+
+def _ev(a, env):
+    """Evaluate a leaf / node; tuples, lists and slices may contain symbolic entries (shapes such as
+    (nineq, 2 * m_lbfgs), slices such as [:m_lbfgs] -- the L-BFGS graph, pyipm.py:1007-1182)."""
+    if isinstance(a, Expr):
+        return a.eval(env)
+    if isinstance(a, tuple):
+        return tuple(_ev(x, env) for x in a)
+    if isinstance(a, list):
+        return [_ev(x, env) for x in a]
+    if isinstance(a, slice):
+        return slice(_ev(a.start, env), _ev(a.stop, env), _ev(a.step, env))
+    return a
+
+
+class Sub(Expr):
+    """a[idx]; remembers base and index so that inc_subtensor / set_subtensor can rebuild the full array."""
+
+    def __init__(self, base, idx):
+        self.base = base
+        self.idx = idx
+        Expr.__init__(self, lambda a, i: a[i], (base, idx))
+
+
+class Lazy(Expr):
+    """ifelse(cond, a, b): only the selected branch is evaluated (aesara.ifelse is lazy; the branch not taken may be
+    ill-defined, e.g. a solve with a 0 x 0 matrix while no L-BFGS pair is stored)."""
+
+    def __init__(self, cond, a, b):
+        self.cond, self.a, self.b = cond, a, b
+
+    def eval(self, env):
+        return _ev(self.a, env) if bool(_ev(self.cond, env)) else _ev(self.b, env)
 
 
 class _Shape(object):

@@ -1,8 +1,9 @@
 import numpy as np
-from .._expr import Expr, Var
+from .._expr import Expr, Var, Sub
 from . import nlinalg, slinalg, basic  # noqa: F401
 
 
+def scalar(name=None): return Var(name, 0)
 def vector(name=None): return Var(name, 1)
 def matrix(name=None): return Var(name, 2)
 def _w(fn): return lambda *a: Expr(fn, a)
@@ -21,32 +22,32 @@ diagonal = _w(np.diagonal)
 
 
 def max(a, axis=None): return Expr(lambda v: np.max(v, axis=axis), (a,))
+def min(a, axis=None): return Expr(lambda v: np.min(v, axis=axis), (a,))
+
+
+le = _w(lambda a, b: a <= b)
+gt = _w(lambda a, b: a > b)
 
 
 def concatenate(lst, axis=0):
     return Expr(lambda *v: np.concatenate(v, axis=axis), tuple(lst))
 
 
-def _set(a, idx, v, inc):
-    def fn(arr, val):
+def _upd(sub, val, inc):
+    assert isinstance(sub, Sub), 'inc_subtensor / set_subtensor need an indexed expression'
+
+    def fn(arr, idx, v):
         out = np.array(arr, copy=True)
         if inc:
-            out[idx] += val
+            out[idx] += v
         else:
-            out[idx] = val
+            out[idx] = v
         return out
-    return fn
+    return Expr(fn, (sub.base, sub.idx, val))
 
 
-class _Sub(Expr):
-    pass
-
-
-def set_subtensor(sub, val):
-    raise NotImplementedError('symbolic-expression input mode is not supported by the stand-in')
-
-
-inc_subtensor = set_subtensor
+def set_subtensor(sub, val): return _upd(sub, val, False)
+def inc_subtensor(sub, val): return _upd(sub, val, True)
 
 
 def grad(*a, **k):

@@ -35,11 +35,11 @@ import scipy.linalg
 
 
 class OracleIPM(object):
-    """Restatement of `class IPM` (pyipm.py:23-1863), exact-Hessian branch only (lbfgs=False)."""
+    """Restatement of `class IPM` (pyipm.py:23-1863): exact-Hessian branch and the L-BFGS branch (lbfgs=m)."""
 
     def __init__(self, x0=None, f=None, df=None, d2f=None, ce=None, dce=None, d2ce=None, ci=None, dci=None,
                  d2ci=None, lda0=None, s0=None, mu=0.2, nu=10.0, rho=0.1, tau=0.995, eta=1.0E-4,
-                 beta=0.4, miter=20, niter=10, Xtol=None, Ktol=1.0E-4, Ftol=None,
+                 beta=0.4, miter=20, niter=10, Xtol=None, Ktol=1.0E-4, Ftol=None, lbfgs=False, lbfgs_zeta=None,
                  float_dtype=np.float64, verbosity=-1, trace=None):
         # pyipm.py:311-376
         self.x0 = x0
@@ -73,6 +73,13 @@ class OracleIPM(object):
         self.Ktol = Ktol
         self.Ftol = Ftol
         self.reg_coef = float_dtype(np.sqrt(self.eps))
+        # pyipm.py:355-360
+        self.lbfgs = lbfgs
+        if self.lbfgs and lbfgs_zeta is None:
+            self.lbfgs_zeta = float_dtype(1.0)
+        else:
+            self.lbfgs_zeta = lbfgs_zeta
+        self.lbfgs_fail_max = lbfgs
         self.float_dtype = float_dtype
         # the two Aesara shared scalars (pyipm.py:363-364); kept separate from mu_host/nu_host on purpose
         # (quirk xi: mu_dev is not reset by a second solve() when nineq>0, pyipm.py:1603 vs 1607)
@@ -103,6 +110,10 @@ class OracleIPM(object):
         assert self.Xtol >= self.eps
         assert self.Ktol >= self.eps
         assert self.Ftol is None or self.Ftol >= 0.0
+        assert self.lbfgs >= 0 or self.lbfgs == False  # noqa: E712  (pyipm.py:405-408)
+        if self.lbfgs:
+            assert isinstance(self.lbfgs, int)
+        assert self.lbfgs_zeta is None or self.lbfgs_zeta > 0.0
 
     def compile(self, nvar=None, neq=None, nineq=None):
         """Size discovery pyipm.py:414-467, then the NumPy lambdas of the precompile path."""
@@ -272,7 +283,8 @@ class OracleIPM(object):
                 return df_func(x)
         self.barrier_cost_grad = barrier_cost_grad
 
-        # Lagrangian Hessian and full KKT matrix, pyipm.py:768-814 (only triu(d2L) is used: quirk ii)
+        # Lagrangian Hessian and full KKT matrix, pyipm.py:768-814 (only triu(d2L) is used: quirk ii); in L-BFGS mode
+        # (pyipm.py:767) these slots exist but are never called (d2f/d2ce/d2ci may be None)
         if neq and nineq:
             def d2L(x, lda):
                 return d2f_func(x) - d2ce_func(x, lda) - d2ci_func(x, lda)
@@ -343,6 +355,136 @@ class OracleIPM(object):
             kkt3 = self.float_dtype(0.0)
             kkt4 = self.float_dtype(0.0)
         return kkt1, kkt2, kkt3, kkt4
+
+
+    # ------------------------------------------------------------------ L-BFGS (pyipm.py:993-1371)
+    def lbfgs_init(self):
+        """pyipm.py:993-1005."""
+        zeta = self.float_dtype(self.lbfgs_zeta)
+        S = np.array([], dtype=self.float_dtype).reshape((self.nvar, 0))
+        Y = np.array([], dtype=self.float_dtype).reshape((self.nvar, 0))
+        SS = np.array([], dtype=self.float_dtype).reshape((0, 0))
+        L = np.array([], dtype=self.float_dtype).reshape((0, 0))
+        D = np.array([], dtype=self.float_dtype).reshape((0, 0))
+        return zeta, S, Y, SS, L, D, 0
+
+    def lbfgs_dir(self, x, s, lda, g, zeta, S, Y, SS, L, D):
+        """pyipm.py:1184-1246 with the graph of lbfgs_builder (pyipm.py:1007-1182) evaluated eagerly in NumPy/SciPy:
+        compact representation + Woodbury for constrained problems (general, non-reduced variant pyipm.py:1099-1148),
+        two-loop-free compact inverse for unconstrained ones (pyipm.py:1149-1175).  The square-Jacobian reduced variant
+        (pyipm.py:1061-1097) cannot be compiled by the reference itself (duplicate `s_dev` in the inputs of
+        `lbfgs_dir_func_sqr`, pyipm.py:877-878) and is not restated; `solve` here is scipy.linalg.solve(assume_a='gen')
+        as in sym_solve (pyipm.py:18-20), `eigh` is numpy.linalg.eigh (aesara nlinalg.eigh)."""
+        nvar, neq, nineq, eps = self.nvar, self.neq, self.nineq, self.eps
+        solve = lambda A, b: scipy.linalg.solve(A, b, assume_a='gen')  # noqa: E731
+        m = S.shape[1]
+        if neq or nineq:
+            B = self.jaco(x)
+            Adiag = zeta * np.ones((nvar, 1))
+            if nineq:
+                Sigma = (lda[neq:] / (s + eps)).reshape((nineq, 1))
+                Adiag = np.concatenate([Adiag, Sigma], axis=0)
+            BT_invA = np.dot(B.T, np.diag(1.0 / Adiag.reshape((Adiag.size,))))
+            BT_invA_B = np.dot(BT_invA, B)
+            self.last_lbfgs = {'eq_reg': False, 'm': m}
+            if neq:
+                w = np.linalg.eigh(BT_invA_B[:neq, :neq])[0]
+                rcond = np.min(np.abs(w)) / np.max(np.abs(w))
+                self.last_lbfgs['rcond'] = float(rcond)
+                if rcond <= eps:
+                    BT_invA_B = np.array(BT_invA_B, copy=True)
+                    BT_invA_B[:neq, :neq] += self.reg_coef * self.eta * (self.mu_dev ** self.beta) * np.eye(neq)
+                    self.last_lbfgs['eq_reg'] = True
+            gp = g[:nvar + nineq].reshape((nvar + nineq, 1))
+            gd = g[nvar + nineq:].reshape((neq + nineq, 1))
+            v00 = np.dot(BT_invA, gp)
+            v01 = solve(BT_invA_B, v00)
+            v02 = gp / Adiag - np.dot(BT_invA.T, v01)
+            v03 = -solve(BT_invA_B, gd)
+            v04 = -np.dot(BT_invA.T, v03)
+            Zg = np.concatenate([v02 + v04, v01 + v03], axis=0)
+            if m > 0:
+                W = np.concatenate([zeta * S, Y], axis=1)
+                if nineq:
+                    W = np.concatenate([W, np.zeros((nineq, 2 * m))], axis=0)
+                BT_gmaW = np.dot(B.T, W) / zeta
+                X00 = -solve(BT_invA_B, BT_gmaW)
+                X01 = W / zeta + np.dot(BT_invA.T, X00)
+                X02 = np.dot(W.T, X01)
+                M0 = np.concatenate([zeta * SS, L], axis=1)
+                M1 = np.concatenate([L.T, -D], axis=1)
+                Minv = np.concatenate([M0, M1], axis=0)
+                v10 = np.dot(W.T, Zg[:nvar + nineq])
+                v11 = solve(X02 - Minv, v10)
+                X10 = np.concatenate([X01, -X00], axis=0)
+                dz = Zg - np.dot(X10, v11)
+            else:
+                dz = Zg
+        else:
+            Hg = zeta * g.reshape((nvar, 1))
+            if m > 0:
+                W = np.concatenate([S, zeta * Y], axis=1)
+                WT_g = np.dot(W.T, g)
+                Bv = -solve(L, WT_g[:m].reshape((m, 1)))
+                Av = (-solve(L.T, np.dot(D + zeta * SS, Bv)) - solve(L.T, WT_g[m:].reshape((m, 1))))
+                dz = Hg + np.dot(W, np.concatenate([Av, Bv], axis=0))
+            else:
+                dz = Hg
+        return dz.reshape((dz.size,))
+
+    def lbfgs_update(self, x_old, x_new, g_old, g_new, zeta, S, Y, SS, L, D, lbfgs_fail):
+        """pyipm.py:1282-1371 (the curvature perturbation is commented out in the reference)."""
+        nvar = self.nvar
+        dx = x_new - x_old
+        dg = g_old[:nvar] - g_new[:nvar]
+        if self.neq or self.nineq:
+            zeta_new = np.dot(dg, dx) / (np.dot(dx, dx) + self.eps)
+        else:
+            zeta_new = np.dot(dg, dx) / (np.dot(dg, dg) + self.eps)
+        if np.dot(dx, dg) > np.sqrt(self.eps) and zeta_new > np.sqrt(self.eps):
+            zeta = zeta_new
+            if S.shape[1] > self.lbfgs:
+                S[:, :-1] = S[:, 1:]
+                Y[:, :-1] = Y[:, 1:]
+                SS[:-1, :-1] = SS[1:, 1:]
+                L[:-1, :-1] = L[1:, 1:]
+                D[:-1, :-1] = D[1:, 1:]
+            else:
+                lsize = S.shape[1] + 1
+                S = np.concatenate([S, np.zeros((nvar, 1), dtype=self.float_dtype)], axis=1)
+                Y = np.concatenate([Y, np.zeros((nvar, 1), dtype=self.float_dtype)], axis=1)
+                SS = np.concatenate([SS, np.zeros((1, lsize - 1), dtype=self.float_dtype)], axis=0)
+                SS = np.concatenate([SS, np.zeros((lsize, 1), dtype=self.float_dtype)], axis=1)
+                L = np.concatenate([L, np.zeros((1, lsize - 1), dtype=self.float_dtype)], axis=0)
+                L = np.concatenate([L, np.zeros((lsize, 1), dtype=self.float_dtype)], axis=1)
+                D = np.concatenate([D, np.zeros((1, lsize - 1), dtype=self.float_dtype)], axis=0)
+                D = np.concatenate([D, np.zeros((lsize, 1), dtype=self.float_dtype)], axis=1)
+            S[:, -1] = dx
+            Y[:, -1] = dg
+            if self.neq or self.nineq:
+                SS_update = np.dot(S.T, dx.reshape((nvar, 1)))
+            else:
+                SS_update = np.dot(Y.T, dg.reshape((nvar, 1)))      # this is YY for unconstrained problems
+            SS[:, -1] = SS_update.reshape((SS_update.size,))
+            SS[-1, :] = SS_update.reshape((SS_update.size,))
+            lsize = SS.shape[1]
+            SS = SS.reshape((lsize, lsize))
+            if self.neq or self.nineq:
+                L_update = np.dot(dx.reshape((1, nvar)), Y)
+                L[-1, :] = L_update
+                L[-1, -1] = self.float_dtype(0.0)
+            else:
+                L_update = np.dot(S.T, dg.reshape((nvar, 1))).reshape((S.shape[1],))   # this is R
+                L[:, -1] = L_update
+            L = L.reshape((lsize, lsize))
+            D[-1, -1] = np.dot(dx, dg)
+            D = D.reshape((lsize, lsize))
+            lbfgs_fail = 0
+        else:
+            lbfgs_fail += 1
+        if lbfgs_fail > self.lbfgs_fail_max and S.shape[1] > 0:
+            zeta, S, Y, SS, L, D, lbfgs_fail = self.lbfgs_init()
+        return zeta, S, Y, SS, L, D, lbfgs_fail
 
     # ------------------------------------------------------------------ reghess
     def reghess(self, Hc):
@@ -513,14 +655,31 @@ class OracleIPM(object):
         nvar, neq, nineq = self.nvar, self.neq, self.nineq
         tm = self.timers
         t0 = time.perf_counter()
-        g = -self.grad(x, s, lda)
-        t1 = time.perf_counter()
-        H = self.hess(x, s, lda)
-        t2 = time.perf_counter()
-        Hc = self.reghess(H)
-        t3 = time.perf_counter()
-        dz = self.sym_solve_cmp(Hc, g.reshape((g.size, 1))).reshape((g.size,))
-        t4 = time.perf_counter()
+        if self.lbfgs:
+            # pyipm.py:1702-1713
+            lb = self._lb
+            if lb['not_first']:
+                g_old = -self.grad(lb['x_old'], s, lda)
+                g_new = -self.grad(x, s, lda)
+                (lb['zeta'], lb['S'], lb['Y'], lb['SS'], lb['L'], lb['D'], lb['fail']) = self.lbfgs_update(
+                    lb['x_old'], x, g_old, g_new, lb['zeta'], lb['S'], lb['Y'], lb['SS'], lb['L'], lb['D'], lb['fail'])
+                lb['x_old'] = np.copy(x)
+                lb['g'] = np.copy(g_new)
+            g = lb['g']
+            t1 = t2 = t3 = time.perf_counter()
+            dz = self.lbfgs_dir(x, s, lda, g, lb['zeta'], lb['S'], lb['Y'], lb['SS'], lb['L'], lb['D'])
+            self.last_reg = {'n_eig': 0, 'delta': float(self.delta), 'lbfgs_m': int(lb['S'].shape[1]),
+                             'lbfgs_fail': int(lb['fail']), 'zeta': float(lb['zeta'])}
+            t4 = time.perf_counter()
+        else:
+            g = -self.grad(x, s, lda)
+            t1 = time.perf_counter()
+            H = self.hess(x, s, lda)
+            t2 = time.perf_counter()
+            Hc = self.reghess(H)
+            t3 = time.perf_counter()
+            dz = self.sym_solve_cmp(Hc, g.reshape((g.size, 1))).reshape((g.size,))
+            t4 = time.perf_counter()
         if neq or nineq:
             dz[nvar + nineq:] = -dz[nvar + nineq:]
         if neq or nineq:
@@ -563,7 +722,7 @@ class OracleIPM(object):
 
     # ------------------------------------------------------------------ solve
     def solve(self, x0=None, s0=None, lda0=None, force_recompile=False):
-        """pyipm.py:1567-1863 (prints reduced to the final summary; L-BFGS branch omitted)."""
+        """pyipm.py:1567-1863 (prints reduced to the final summary)."""
         if x0 is not None:
             self.x0 = x0
         if s0 is not None:
@@ -610,6 +769,11 @@ class OracleIPM(object):
         self.delta = self.float_dtype(0.0)
         kkt = self.KKT(x, s, lda)
         self.init_state = (np.copy(x), np.copy(s), np.copy(lda))
+        if self.lbfgs:
+            # pyipm.py:1633-1637
+            zeta, S, Y, SS, L, D, lbfgs_fail = self.lbfgs_init()
+            self._lb = {'zeta': zeta, 'S': S, 'Y': Y, 'SS': SS, 'L': L, 'D': D, 'fail': lbfgs_fail,
+                        'x_old': np.copy(x), 'g': -self.grad(x, s, lda), 'not_first': False}
 
         iter_count = 0
         if self.Ftol is not None:
@@ -636,6 +800,8 @@ class OracleIPM(object):
                         Ktol_converged = True
                     break
 
+                if self.lbfgs:
+                    self._lb['not_first'] = (inner > 0 or outer > 0)     # pyipm.py:1705
                 x, s, lda, kkt = self.newton_step(x, s, lda)
                 iter_count += 1
 

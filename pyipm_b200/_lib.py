@@ -38,7 +38,7 @@ class StepInfo(C.Structure):
                 ('ms_eval', C.c_float), ('ms_assemble', C.c_float), ('ms_factor', C.c_float), ('ms_solve', C.c_float),
                 ('ms_search', C.c_float), ('ms_total', C.c_float), ('ms_hess_kernel', C.c_float),
                 ('ms_condense_kernel', C.c_float), ('n_spec', C.c_int), ('spec_used', C.c_int),
-                ('tc_syrk', C.c_int), ('abandoned_first', C.c_int), ('cert_used', C.c_int), ('reserved', C.c_int)]
+                ('tc_syrk', C.c_int), ('abandoned_first', C.c_int), ('cert_used', C.c_int), ('n_factor_phys', C.c_int)]
 
     def asdict(self):
         d = {}

@@ -47,6 +47,7 @@ struct b200ipm_engine {
     double reg_cur = 0, delta_eff = 0;
     bool strict_retry = false;
     int n_strict = 0;        // number of strict re-factorisations triggered by a poor residual
+    int n_phys = 0;          // factorisations physically executed in the current step (info->n_factor_phys)
     LdltWs F;               // condensed KKT factorisation (order Kc)
     OzWs oz;                // tcgen05 int8 slices (B200IPM_FLAG_TCGEN05_SYRK)
     OzWs oz_soc;            // same for the (M+N)-order normal equations of the second-order correction (lazy)
@@ -304,6 +305,7 @@ static int spec_launch_background(Eng* h, int neg_limit) {
     CU(cudaStreamWaitEvent(h->stB, h->ev_fork, 0));
     RET(ldlt_set_neg_limit(h->Fb, neg_limit));
     RET(build_kc_into(h, h->Fb, h->stB, 0.0, 0.0));
+    h->n_phys++;
     if (delay) {
         ldlt_wait_sig_kernel<<<1, 1, 0, h->stB>>>(h->d_sig);
         LAUNCHED();
@@ -371,6 +373,7 @@ static int factor_once(Eng* h, double delta, double reg, int neg_limit, int* n_n
     RET(ldlt_set_neg_limit(h->F, neg_limit));
     RET(build_kc(h, delta, reg));
     RET(ldlt_factor(h->F));
+    h->n_phys++;
     int cnt[8];
     double ds[2];
     CU(cudaMemcpyAsync(cnt, h->F.counts, sizeof(int) * 8, cudaMemcpyDeviceToHost, h->st));
@@ -619,6 +622,7 @@ static int solve_direction(Eng* h, b200ipm_step_info* info) {
         h->strict_retry = true;
         RET(build_kc(h, h->delta_eff, h->reg_cur));
         RET(ldlt_factor(h->F));
+        h->n_phys++;
         int r = solve_direction(h, info);
         h->strict_retry = false;
         h->F.pivot_u = u_save;
@@ -912,6 +916,7 @@ static int line_search(Eng* h, b200ipm_step_info* info, const double* stats /* h
 
 // ------------------------------------------------------------------------------------------ direction + step
 static int compute_direction(Eng* h, b200ipm_step_info* info) {
+    h->n_phys = 0;
     RET(residual(h));
     h->oz_off = false;
     h->oz_used = false;
@@ -951,6 +956,7 @@ static int compute_direction(Eng* h, b200ipm_step_info* info) {
         }
     }
     CU(cudaEventRecord(h->ev[EV_SOLVE], h->st));
+    if (info) info->n_factor_phys = h->n_phys;
     return 0;
 }
 static int dir_stats(Eng* h, double* stats) {

@@ -401,6 +401,9 @@ class IPM(object):
         D, M, N = self.nvar, self.neq, self.nineq
         x, s, lda, _, _, _ = eng.get_state()
         dz, info = eng.direction()
+        # the shift reghess settled on persists across steps (pyipm.py:1390-1395): every later set_state of this step
+        # must carry it, or the next factorisation would restart from the pre-step value
+        self.delta = info.delta
         _, nrm0 = eng.residual(want_g=False)
         con_l1 = 0.0
         if M:

@@ -379,6 +379,17 @@ def make_nlp(D=4096, M=512, N=4096, seed=None):
     return QuadProblem(Q, c, 1.0, A=A, U=U, b=b, G=G, V=V, r=r, x0=x0, name='nlp_D%d_M%d_N%d' % (D, M, N))
 
 
+def make_rankdef_nlp(D=24, M=6, N=16, seed=41):
+    """make_nlp with the LAST equality constraint an exact copy of the first: dce has two identical columns, the KKT
+    matrix is exactly singular for every delta, so the reference's `rcond <= eps` branch (pyipm.py:1381-1389: eq-block
+    regularisation -sqrt(eps)*eta*mu^beta*I) fires at every step."""
+    p = make_nlp(D=D, M=M, N=N, seed=seed)
+    A_, U_, b_ = p.At.T.copy(), p.Ut.T.copy(), p.b.copy()
+    A_[M - 1], U_[M - 1], b_[M - 1] = A_[0], U_[0], b_[0]
+    return QuadProblem(p.Q, p.c, p.q4, A=A_, U=U_, b=b_, G=p.Gt.T, V=p.Vt.T, r=p.r, x0=p.x0,
+                       name='nlp_rankdef_D%d_M%d_N%d' % (D, M, N))
+
+
 def mu_sweep_state(prob, mu, seed=5):
     """BASELINE.json config 5 -- ill-conditioned barrier state for a teacher-forced Newton step
     (SURVEY.md section 8d 'C5'): s_i*lda_i = mu, 25% 'active' rows with s_i = mu^0.9, rest U(0.1, 1)."""

@@ -111,6 +111,68 @@ def run_reference(prob, x0, n_solves=1, **kw):
     return p, steps, results
 
 
+def run_reference_lbfgs(prob, x0, lbfgs=4, **kw):
+    """The reference's L-BFGS mode (pyipm.py:993-1371, hooks 1702-1713), lbfgs=4 as in unit_tests.py:49; second
+    derivatives are not passed (the mode never uses them)."""
+    cal = {k: F(v) for k, v in prob.callables().items() if not k.startswith('d2')}
+    p = ref.IPM(x0=np.array(x0, dtype=np.float64), x_dev=T.vector('x_dev'), lambda_dev=T.vector('lda_dev'),
+                verbosity=-1, lbfgs=lbfgs, **cal, **kw)
+    p.compile(nvar=prob.nvar)
+    steps = []
+    cur = {}
+    o_dir, o_upd, o_search = p.lbfgs_dir, p.lbfgs_update, p.search
+
+    def w_upd(x_old, x_new, g_old, g_new, zeta, S, Y, SS, L, D, fail):
+        out = o_upd(x_old, x_new, g_old, g_new, zeta, S, Y, SS, L, D, fail)
+        cur['upd'] = True
+        return out
+
+    def w_dir(x, s, lda, g, zeta, S, Y, SS, L, D):
+        upd = cur.get('upd', False)
+        cur.clear()
+        cur.update(x=np.copy(x), s=np.copy(s), lda=np.copy(lda), g=np.copy(g), zeta=float(zeta), m=int(S.shape[1]),
+                   mu=float(p.mu_dev.get_value()), mu_host=float(p.mu_host), nu_before=float(p.nu_dev.get_value()),
+                   updated=bool(upd))
+        dz = o_dir(x, s, lda, g, zeta, S, Y, SS, L, D)
+        cur['dz_raw'] = np.copy(dz)
+        return dz
+
+    def w_search(x0_, s0_, lda0_, dz, a_s, a_l):
+        cur['dz'] = np.copy(dz)
+        cur['nu'] = float(p.nu_dev.get_value())
+        cur['alpha_smax'], cur['alpha_lmax'] = float(a_s), float(a_l)
+        x, s, lda = o_search(x0_, s0_, lda0_, dz, a_s, a_l)
+        cur['x_new'], cur['s_new'], cur['lda_new'] = np.copy(x), np.copy(s), np.copy(lda)
+        cur['signal'] = int(p.signal)
+        steps.append(dict(cur))
+        return x, s, lda
+
+    p.lbfgs_dir, p.lbfgs_update, p.search = w_dir, w_upd, w_search
+    x, s, lda, fval, kkt = p.solve()
+    res = dict(x=np.copy(x), s=np.copy(s), lda=np.copy(lda), fval=float(fval),
+               kkt=[np.atleast_1d(np.asarray(k, dtype=np.float64)) for k in kkt], signal=int(p.signal), nsteps=len(steps))
+    return p, steps, res
+
+
+def pack_lbfgs(prob, x0, steps, r, kw):
+    out = {'x0': np.asarray(x0, dtype=np.float64), 'dims': np.array([prob.nvar, prob.neq, prob.nineq])}
+    for k, v in kw.items():
+        out['kw_' + k] = np.float64(v)
+    out['sol0_x'], out['sol0_s'], out['sol0_lda'], out['sol0_fval'] = r['x'], r['s'], r['lda'], np.float64(r['fval'])
+    for j in range(4):
+        out['sol0_kkt%d' % (j + 1)] = r['kkt'][j]
+    out['sol0_signal'], out['sol0_nsteps'] = np.int64(r['signal']), np.int64(r['nsteps'])
+    out['nsteps'] = np.int64(len(steps))
+    if steps:
+        for key in ('x', 's', 'lda', 'g', 'dz_raw', 'dz', 'x_new', 's_new', 'lda_new'):
+            out['st_' + key] = np.stack([st[key] for st in steps])
+        for key in ('mu', 'mu_host', 'nu_before', 'nu', 'alpha_smax', 'alpha_lmax', 'zeta'):
+            out['st_' + key] = np.array([st[key] for st in steps], dtype=np.float64)
+        for key in ('m', 'signal', 'updated'):
+            out['st_' + key] = np.array([st[key] for st in steps], dtype=np.int64)
+    return out
+
+
 def pack(prob, x0, steps, results, kw, keep_H=False):
     out = {'x0': np.asarray(x0, dtype=np.float64), 'dims': np.array([prob.nvar, prob.neq, prob.nineq])}
     for k, v in kw.items():
@@ -143,6 +205,37 @@ def pack(prob, x0, steps, results, kw, keep_H=False):
 def main():
     summary = []
     kw = dict(Ftol=1.0E-8)   # unit_tests.py:50 / pyipm.py:1894
+    only = set(sys.argv[1:])
+    if 'nlp_rankdef' in only or not only:
+        # rank-deficient equality Jacobian: 4 Newton steps of the reference (it does not converge on this problem;
+        # the fixture pins the rcond <= eps branch of reghess, not a solution)
+        prob = problems.make_rankdef_nlp()
+        kw3 = dict(kw, niter=1, miter=4)
+        p, steps, results = run_reference(prob, prob.x0, **kw3)
+        np.savez_compressed(os.path.join(HERE, 'ref_nlp_rankdef.npz'), **pack(prob, prob.x0, steps, results, kw3, True))
+        summary.append(('nlp_rankdef', results[0]['signal'], results[0]['nsteps'], float('nan')))
+        if only == {'nlp_rankdef'}:
+            print(summary)
+            return
+    if 'lbfgs' in only or not only:
+        # L-BFGS mode: the ten examples with lbfgs=4 (unit_tests.py:49) + three synthetic problems
+        cases = [('example%d' % k, problems.example_problem(k)[0], problems.example_x0(k), problems.example_problem(k)[1])
+                 for k in range(1, 11)]
+        for name, prob in (('qp_small', problems.make_qp(D=24, M=6, nbox=8, seed=11)),
+                           ('nlp_small', problems.make_nlp(D=20, M=4, N=16, seed=13)),
+                           ('nlp_eqonly', problems.make_nlp(D=24, M=6, N=0, seed=15))):
+            if prob.nineq == 0:
+                prob.Gt = prob.Vt = prob.r = None
+            cases.append((name, prob, prob.x0, None))
+        for name, prob, x0, gts in cases:
+            p, steps, res = run_reference_lbfgs(prob, x0, lbfgs=4, **kw)
+            err = min(np.linalg.norm(res['x'] - g) for g in gts) if gts else float('nan')
+            np.savez_compressed(os.path.join(HERE, 'ref_lbfgs_%s.npz' % name), **pack_lbfgs(prob, x0, steps, res, kw))
+            summary.append(('lbfgs_' + name, res['signal'], res['nsteps'], err))
+        if only == {'lbfgs'}:
+            for row in summary:
+                print('%-18s signal=%2d steps=%3d  |x-x_gt|=%.3e' % row)
+            return
     for k in range(1, 11):
         prob, gts = problems.example_problem(k)
         x0 = problems.example_x0(k)

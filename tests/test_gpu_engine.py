@@ -426,3 +426,22 @@ def test_reghess_certificate_path_all_constraint_structures(D, M, N):
         nu_b, de_b = st['nu_after'], st['delta']
     eng.close()
     assert n_cert >= 1     # the certificate did replace at least one delta = 0 factorisation on each trajectory
+
+
+def test_callable_mode_nonconvex_delta_trace():
+    """Callable mode on a nonconvex problem: the diagonal shift must be carried from step to step exactly like the
+    reference's self.delta (pyipm.py:1390-1395): per-step delta and number of inertia tests of the oracle trajectory."""
+    prob, x0, _ = get_problem('nlp_mid')
+    o, tr = oracle_trace(prob, x0)
+    p = IPM(x0=np.array(x0), Ftol=1.0E-8, verbosity=-1, **prob.callables())
+    p.solve()
+    assert any(st['delta'] > 0.0 for st in tr)
+    n = 0
+    for st, lg in zip(tr, p.step_log):
+        assert lg['delta'] == st['delta'], (n, lg['delta'], st['delta'])
+        assert lg['n_factor'] == st['reg']['n_eig'], (n, lg['n_factor'], st['reg']['n_eig'])
+        assert lg['n_backtracks'] == st['search']['n_backtracks']
+        n += 1
+        if st['search']['soc_tried']:
+            break      # trajectories may differ once a second-order correction is involved
+    assert n >= 5

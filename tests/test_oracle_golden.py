@@ -87,3 +87,30 @@ def test_oracle_full_kkt_matrix_matches_reference():
             H = o.hess(g['st_x'][k], g['st_s'][k], g['st_lda'][k])
             np.testing.assert_allclose(H, g['st_Hfull'][k], rtol=RTOL, atol=ATOL)
             assert np.array_equal(H, H.T)
+
+
+def test_oracle_rcond_branch_matches_reference():
+    """The `rcond <= eps` branch of reghess (pyipm.py:1381-1389: eq-block regularisation) on the rank-deficient
+    fixture: 4 Newton steps of the unmodified reference (niter=1, miter=4), every one with the eq block regularised."""
+    from pyipm_b200 import problems
+    g = load_golden('nlp_rankdef')
+    prob = problems.make_rankdef_nlp()
+    tr = []
+    o = OracleIPM(x0=prob.x0.copy(), Ftol=1.0E-8, verbosity=-1, niter=1, miter=4, trace=tr, **prob.callables())
+    with np.errstate(all='ignore'):
+        o.solve()
+    assert len(tr) == int(g['nsteps']) == 4
+    for k, st in enumerate(tr):
+        assert st['reg']['eq_reg'] and st['reg']['rcond'] <= o.eps
+        assert g['st_rcond'][k] <= o.eps
+        assert st['delta'] == g['st_delta'][k]
+        assert st['reg']['n_eig'] == int(g['st_n_eig'][k])
+        np.testing.assert_allclose(st['g'], g['st_g'][k], rtol=1e-9, atol=1e-11)
+        # the matrix reghess returns: eq block = -sqrt(eps)*eta*mu^beta, (x,x) block shifted by delta
+        D, M, N = prob.nvar, prob.neq, prob.nineq
+        Hreg = g['st_Hreg'][k]
+        reg = np.sqrt(o.eps) * o.eta * g['st_mu_host'][k] ** o.beta
+        np.testing.assert_allclose(np.diagonal(Hreg)[D + N:D + N + M], -reg, rtol=1e-12)
+        # the system is singular to working precision (condition ~1e13 after the regularisation): the LU solution is
+        # reproducible only to that level
+        np.testing.assert_allclose(st['dz'], g['st_dz'][k], rtol=1e-4, atol=1e-6 * np.max(np.abs(g['st_dz'][k])))
