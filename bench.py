@@ -117,40 +117,80 @@ def oracle_sample_step(D=1024, M=128, N=1024, seed=7):
     return o, prob, (x, s, lda)
 
 
+STATE_FILE = os.path.join(ROOT, 'tests', 'golden', 'c3_state_after3.npz')
+
+
+def load_c3_state():
+    """The teacher-forced config-3 state both arms step from: the iterate after PRE_STEPS real Newton steps from x0
+    (tools/make_c3_state.py, produced once on a B200 and committed: the reference arm has no GPU to produce it with)."""
+    g = np.load(STATE_FILE)
+    return (g['x'], g['s'], g['lda'], float(g['mu']), float(g['nu']), float(g['delta']), float(g['mu_host']))
+
+
+def oracle_c3_step():
+    """ONE real config-3 Newton step of the CPU oracle (pyipm.py:1714-1754 restated) from the committed state: the same
+    problem, the same iterate and the same (mu, nu, delta) as the B200 arm's timed step.  delta > 0 on entry, so reghess
+    does what it does in the middle of the solve: eigvalsh(12800) at delta = 0 (fails), eigvalsh at delta / 2 (passes),
+    then one LU solve of the 12800^2 system."""
+    from oracle.pyipm_numpy import OracleIPM
+    from pyipm_b200 import problems
+    prob = problems.make_nlp(D3, M3, N3)
+    x, s, lda, mu, nu, delta, mu_host = load_c3_state()
+    o = OracleIPM(x0=prob.x0.copy(), verbosity=-1, mu=mu, **prob.callables())
+    o.nvar = D3
+    o.compile()
+    o.mu_host, o.mu_dev, o.nu_host, o.nu_dev, o.signal = mu_host, np.float64(mu), nu, np.float64(nu), 0
+    o.delta = np.float64(delta)
+    o.timers = {}
+    tr = []
+    o.trace = tr
+    t0 = time.perf_counter()
+    with np.errstate(all='ignore'):
+        o.newton_step(x.copy(), s.copy(), lda.copy())
+    dt = time.perf_counter() - t0
+    return o, tr[0], dt
+
+
 def run_reference(args):
+    """The reference's own CPU arithmetic on the SAME configuration: one real config-3 step (about 5-10 minutes on 16
+    cores: two eigvalsh(12800) + one LU).  --steps / --warmup beyond one step are ignored -- the line says steps = 1,
+    warmup = 0 -- because K steps of this size do not fit any bench window; the n = 1024 sample of the same family is kept
+    as a labelled extra (`sample_n1024`)."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return 0
     os.environ.setdefault('OPENBLAS_NUM_THREADS', str(os.cpu_count()))
     cores = os.cpu_count()
-    o, prob, (x, s, lda) = oracle_sample_step()
-    K = prob.nvar + 2 * prob.nineq + prob.neq
-    scale = (float(K3) / K) ** 3
-    times = []
-    with np.errstate(all='ignore'):
-        for it in range(args.warmup + args.steps):
-            o.delta = np.float64(2.0 * DELTA_SAMPLE)
-            o.timers = {}
-            t0 = time.perf_counter()
-            o.newton_step(x.copy(), s.copy(), lda.copy())
-            dt = time.perf_counter() - t0
-            if it >= args.warmup:
-                times.append(dt)
-    t_sample = float(np.mean(times))
-    t_c3 = t_sample * scale
-    value = 1.0 / t_c3
-    sample = ('oracle Newton step (pyipm.py:1714-1754 restated) on the same NLP family at n=1024 (K=%d), mean of %d '
-              'steps = %.2f s, %d eigvalsh + 1 LU per step; scaled to config 3 by (K3/K)^3 = %.0f'
-              % (K, len(times), t_sample, o.last_reg['n_eig'], scale))
+    extra = None
+    if not args.ref_skip_sample:
+        o1, p1, (x1, s1, l1) = oracle_sample_step()
+        o1.delta = np.float64(2.0 * DELTA_SAMPLE)
+        o1.timers = {}
+        t0 = time.perf_counter()
+        with np.errstate(all='ignore'):
+            o1.newton_step(x1.copy(), s1.copy(), l1.copy())
+        t1 = time.perf_counter() - t0
+        K1 = p1.nvar + 2 * p1.nineq + p1.neq
+        extra = {'n': p1.nvar, 'K': K1, 'step_s': t1, 'n_eigvalsh': o1.last_reg['n_eig'],
+                 'cubic_extrapolation_to_config3_s': t1 * (float(K3) / K1) ** 3,
+                 'note': 'same NLP family at n=1024; NOT the headline number, kept to show the cubic law'}
+    o, st, dt = oracle_c3_step()
+    value = 1.0 / dt
+    sample = ('ONE full config-3 oracle Newton step (K=%d) from tests/golden/c3_state_after3.npz: %.1f s, %d eigvalsh(12800) '
+              '+ 1 LU; requested steps=%d warmup=%d ignored beyond one step' % (K3, dt, st['reg']['n_eig'], args.steps, args.warmup))
     line = {
         'impl': 'reference', 'metric': 'newton_steps_per_sec', 'value': value, 'unit': 'steps/s', 'n_gpus': args.gpus,
-        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * t_c3, 'higher_is_better': True,
+        'steps': 1, 'warmup': 0, 'steps_requested': args.steps, 'warmup_requested': args.warmup,
+        'ms_per_step': 1e3 * dt, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': WORKLOAD, 'D': D3, 'M': M3, 'N': N3, 'K_full': K3},
+        'config': {'workload': WORKLOAD, 'D': D3, 'M': M3, 'N': N3, 'K_full': K3,
+                   'state': 'teacher-forced from the state after %d real Newton steps from x0 (committed fixture)' % PRE_STEPS},
         'cpu_baseline': {'value': value, 'unit': 'steps/s', 'cores': cores, 'kind': 'port', 'sample': sample,
-                         'split_s': {k: v for k, v in o.timers.items() if k != 'steps'}},
+                         'same_config': True, 'split_s': {k: v for k, v in o.timers.items() if k != 'steps'}},
         'e2e': {'value': value, 'unit': 'steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-        'ms_per_kkt_solve': 1e3 * scale * (o.timers.get('reghess', 0.0) + o.timers.get('solve', 0.0)),
+        'ms_per_kkt_solve': 1e3 * (o.timers.get('reghess', 0.0) + o.timers.get('solve', 0.0)),
+        'reghess': {'n_eigvalsh': st['reg']['n_eig'], 'delta': st['delta'], 'n_backtracks': st['search']['n_backtracks']},
+        'sample_n1024': extra,
     }
     print(json.dumps(line))
     return 0
@@ -325,12 +365,46 @@ def run_b200(args):
 
     ms_res, infos, launches, clocks = timed(step_resident, args.steps, args.warmup)
     ms_e2e, infos_e, _, _ = timed(step_e2e, args.steps, max(args.warmup, 3))
+    # real-trajectory leg: consecutive TRUE Newton steps from x0 (no state restore: cold certificate vectors, second-order
+    # corrections and delta discovery included), timed per step on the device
+    traj = None
+    if rank == 0 and args.traj_steps > 0:
+        eng.set_state(prob.x0, np.ones(N3), np.zeros(M3 + N3), 0.2, 10.0, 0.0)
+        eng.set_mu_host(0.2)
+        eng.init_slack()
+        eng.init_lambda()
+        eng.sync()
+        tinfo = []
+        t0 = time.perf_counter()
+        for _ in range(args.traj_steps):
+            tinfo.append(eng.newton_step())
+        wall = (time.perf_counter() - t0) * 1e3
+        ms = [float(i.ms_total) for i in tinfo]
+        traj = {'steps': len(tinfo), 'ms_mean': float(np.mean(ms)), 'ms_median': float(np.median(ms)), 'ms_max': float(np.max(ms)),
+                'ms_min': float(np.min(ms)), 'wall_ms_per_step': wall / len(tinfo),
+                'ms_per_step_list': [round(v, 3) for v in ms],
+                'n_soc_tried': int(sum(i.soc_tried for i in tinfo)), 'n_soc_accepted': int(sum(i.soc_accepted for i in tinfo)),
+                'n_cert_used': int(sum(i.cert_used for i in tinfo)), 'n_speculated': int(sum(i.n_spec for i in tinfo)),
+                'factorisations_reference_equivalent': [int(i.n_factor) for i in tinfo],
+                'factorisations_physical': [int(i.n_factor_phys) for i in tinfo],
+                'n_backtracks': [int(i.n_backtracks) for i in tinfo],
+                'kkt_norm_last': [float(v) for v in tinfo[-1].kkt_norm],
+                'note': 'niter=1-style inner iterations from x0 at fixed mu = 0.2 (no barrier update), step 1 discovers delta '
+                        '(10 inertia tests), later steps speculate; ms from CUDA events inside b200ipm_newton_step'}
+    state_check = None
+    if os.path.exists(STATE_FILE):
+        xf, sf, lf, muf, nuf, df_, _ = load_c3_state()
+        state_check = {'fixture': 'tests/golden/c3_state_after3.npz',
+                       'max_rel_diff_x': float(np.max(np.abs(xf - x_h)) / np.max(np.abs(x_h))),
+                       'max_rel_diff_lda': float(np.max(np.abs(lf - l_h)) / np.max(np.abs(l_h))),
+                       'delta_equal': bool(df_ == delta), 'nu_rel_diff': float(abs(nuf - nu) / abs(nu))}
     per_step = ms_res / args.steps
     value = world * args.steps / (ms_res * 1e-3)
     e2e_value = world * args.steps / (ms_e2e * 1e-3)
     last = infos[-1].asdict()
     kkt_ms = float(np.mean([i.ms_factor + i.ms_solve for i in infos]))
     nfac = float(np.mean([i.n_factor for i in infos]))
+    nfac_phys = float(np.mean([i.n_factor_phys for i in infos]))
 
     line = {
         'metric': 'newton_steps_per_sec', 'value': value, 'unit': 'steps/s', 'n_gpus': world, 'steps': args.steps,
@@ -339,7 +413,9 @@ def run_b200(args):
         'config': {'workload': WORKLOAD, 'D': D3, 'M': M3, 'N': N3, 'K_full': K3, 'K_condensed': D3 + M3,
                    'parallelism': 'replicas x%d (one independent Newton step per GPU, no collective)' % world,
                    'state': 'teacher-forced from the state after %d real Newton steps from x0' % PRE_STEPS,
-                   'factorisations_per_step': nfac, 'refinement_sweeps': 2, 'engine_flags': args.flags,
+                   'factorisations_per_step_reference_equivalent': nfac, 'factorisations_per_step_physical': nfac_phys,
+                   'cert_used_per_step': float(np.mean([i.cert_used for i in infos])),
+                   'refinement_sweeps': 2, 'engine_flags': args.flags,
                    'contractions': 'tcgen05 int8 error-free split' if args.flags & 2 else 'fp64 DMMA',
                    'reghess': ('sequential' if args.flags & 1 else 'delta=0 test in the background, candidate in the foreground'),
                    'l2': 'working set (J 151 MB, Vt/Gt/Q 134 MB each, KKT 170 MB) exceeds the 126 MB L2; no flush'},
@@ -354,6 +430,7 @@ def run_b200(args):
         'kkt_residual_inf': last['resid'],
         'phase_ms': {k: float(np.mean([getattr(i, k) for i in infos])) for k in
                      ('ms_eval', 'ms_assemble', 'ms_factor', 'ms_solve', 'ms_search', 'ms_total')},
+        'trajectory': traj, 'state_check': state_check,
     }
     if rank == 0:
         # roofline legs: the dominant kernel (fp64 DMMA contraction) and the HBM-bound residual GEMV, each timed
@@ -366,52 +443,61 @@ def run_b200(args):
             ms, work = eng.profile_kernel(which, reps=5)
             kern[name] = {'ms': ms, ('tflops' if kind == 'flop' else 'gbs'): work / ms * (1e-9 if kind == 'flop' else 1e-6),
                           'work': work}
+        traffic = {}
+        tpath = os.path.join(ROOT, 'profiles', 'r2_traffic.json')
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath))
         tc_on = bool(args.flags & 2)
+        ph = line['phase_ms']
+        # dominant kernel family of the step: the LDL^T factorisation of the condensed KKT matrix (one CUDA graph).
+        # Algorithmic work Kc^3 / 3 over the fp64 DGEMM rate measured in this run.
+        fac = kern['ldlt_factor']
+        line['roofline'] = {
+            'kernel': 'ldlt_factor: tile-pivoted LDL^T of the condensed KKT matrix (order %d), one CUDA graph (tile / mini / '
+                      'panel / DMMA + tcgen05 trailing updates)' % (D3 + M3),
+            'bound': 'tensor', 'achieved': fac['tflops'], 'peak': fp64_peak_tf, 'unit': 'TFLOP/s',
+            'frac': fac['tflops'] / fp64_peak_tf, 'ms': fac['ms'], 'flops_per_launch': fac['work'],
+            'share_of_step': ph['ms_factor'] / ph['ms_total'] if ph['ms_total'] else None,
+            'traffic': traffic.get('ldlt_factor'), 'traffic_source': traffic.get('source'),
+            'peak_source': 'cuBLAS DGEMM 4096^3 measured in this run = %.1f TF/s (fp64 tensor pipe; MEASURED_PEAKS.json has '
+                           'no fp64 entry: its bf16 figure %.0f TF/s (%s) is a different pipe)' % (fp64_peak_tf, bf16_tf, peak_kind)}
         if tc_on:
             ms8, ops8 = eng.profile_kernel(8, reps=5)
             ach = ops8 / ms8 * 1e-9
             peak = 2.0 * bf16_tf     # dense int8 runs at twice the bf16 rate on this part; bf16_tf is the MEASURED burst figure
             kern['hess_syrk_tcgen05_kernel_only'] = {'ms': ms8, 'int8_tops': ach, 'work': ops8}
-            line['roofline'] = {
+            full = kern['hess_syrk_tcgen05']
+            alg = full['work']     # fp64 FLOPs of the product itself (D^2 (M+N))
+            line['roofline_tensor'] = {
                 'kernel': 'oz_syrk_kernel<128,7> (Lagrangian-Hessian contraction Ut diag(lda_e) Ut\' + Vt diag(lda_i) Vt\' as 28 '
                           'exact int8 slice-pair products on tcgen05.mma.kind::i8, int32 TMEM accumulators, fp64 recombination)',
-                'bound': 'tensor', 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s', 'frac': ach / peak,
-                'traffic': 0.999e9,
-                'traffic_source': 'ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch '
-                                  '(profiles/r1_ncu_oz_syrk.md); operands (302 MB of int8 slices) stream from L2',
-                'peak_source': ('2 x MEASURED_PEAKS.json bf16_tflops (%s; dense int8 = twice the bf16 rate) = %.0f TOP/s; for '
-                                'comparison cuBLASLt int8 GEMM 8192^3 (torch._int_mm) measured in this run = %.0f TOP/s'
-                                % (peak_kind, 2.0 * bf16_tf, int8_peak_tops or 0.0)),
+                'bound': 'tensor', 'unit': 'TFLOP/s',
+                'issue_rate_int8_tops': ach, 'issue_rate_peak': peak, 'issue_rate_frac': ach / peak,
                 'frac_of_cublaslt_int8': (ach / int8_peak_tops) if int8_peak_tops else None,
-                'ops_per_launch': ops8,
-                'note': 'achieved/peak count int8 multiply-adds issued (the algorithm: 28 slice pairs x upper tiles x K); the '
-                        'fp64-equivalent rate of the whole operation (slicing + tensor kernel) is in roofline_fp64',
-            }
-            full = kern['hess_syrk_tcgen05']
-            line['roofline_fp64'] = {
-                'kernel': 'Lagrangian-Hessian contraction, fp64-equivalent: slicing + tcgen05 kernel vs the fp64 tensor pipe',
-                'achieved': full['tflops'], 'peak': fp64_peak_tf, 'unit': 'TFLOP/s', 'frac': full['tflops'] / fp64_peak_tf,
+                'algorithmic_fp64_flops_per_launch': alg, 'int8_ops_per_launch': ops8,
+                'algorithmic_tflops_kernel_only': alg / ms8 * 1e-9,
+                'algorithmic_frac_of_int8_pipe': (alg / ms8 * 1e-9) / peak,
+                'fp64_equivalent_tflops_incl_slicing': full['tflops'], 'fp64_dgemm_peak': fp64_peak_tf,
+                'fp64_equivalent_vs_dgemm': full['tflops'] / fp64_peak_tf,
                 'dmma_kernel_tflops': kern['hess_syrk']['tflops'],
-                'peak_source': 'cuBLAS DGEMM 4096^3 measured in this run (the DMMA pipe; tcgen05 has no f64 kind)',
-                'flops_per_launch': full['work']}
-        else:
-            dom = kern['hess_syrk']
-            line['roofline'] = {
-                'kernel': 'gemm_nt_dmma_kernel (Lagrangian-Hessian SYRK: Ut diag(lda_e) Ut\' + Vt diag(lda_i) Vt\', fp64 DMMA)',
-                'bound': 'tensor', 'achieved': dom['tflops'], 'peak': fp64_peak_tf, 'unit': 'TFLOP/s',
-                'frac': dom['tflops'] / fp64_peak_tf, 'traffic': 6.31e8,
-                'traffic_source': 'ncu --set full (profiles/r1_ncu_syrk_final.md)',
-                'peak_source': 'cuBLAS DGEMM 4096^3 measured in this run (fp64 tensor pipe; MEASURED_PEAKS.json has no fp64 '
-                               'entry: its bf16 figure %.0f TF/s (%s) is a different pipe -- tcgen05 has no f64 kind)'
-                               % (bf16_tf, peak_kind),
-                'flops_per_launch': dom['work'],
-            }
+                'share_of_step': float(np.mean([i.ms_hess_kernel for i in infos])) / ph['ms_total'] if ph['ms_total'] else None,
+                'traffic': traffic.get('oz_syrk_kernel'), 'traffic_source': traffic.get('source'),
+                'peak_source': ('2 x MEASURED_PEAKS.json bf16_tflops (%s; dense int8 = twice the bf16 rate) = %.0f TOP/s; cuBLASLt '
+                                'int8 GEMM 8192^3 (torch._int_mm) measured in this run = %.0f TOP/s'
+                                % (peak_kind, 2.0 * bf16_tf, int8_peak_tops or 0.0)),
+                'note': 'issue_rate_* count the int8 multiply-adds the error-free split issues (28 slice pairs); algorithmic_* '
+                        'count the fp64 FLOPs of the product (SURVEY 8d) -- tcgen05 has no f64 kind, so 28 int8 products '
+                        'buy one fp64 product'}
         res = kern['residual_gemv']
+        sol = kern['ldlt_solve']
         line['roofline_hbm'] = {'kernel': 'gemv_n_kernel (g_x = df - J*lda, fused KKT norm)', 'bound': 'hbm',
                                 'achieved': res['gbs'], 'peak': hbm_gbs, 'unit': 'GB/s', 'frac': res['gbs'] / hbm_gbs,
-                                'traffic': 1.393e8, 'traffic_source': 'ncu --set full (profiles/r1_ncu_residual_gemv_final.md)',
+                                'traffic': traffic.get('gemv_n_kernel'), 'traffic_source': traffic.get('source'),
                                 'peak_source': 'MEASURED_PEAKS.json hbm_gbs (%s)' % peak_kind,
-                                'bytes_per_launch': res['work']}
+                                'bytes_per_launch': res['work'],
+                                'triangular_solve': {'kernel': 'ldlt_fwd_kernel + ldlt_bwd_kernel (one right-hand side)',
+                                                     'ms': sol['ms'], 'achieved': sol['gbs'], 'frac': sol['gbs'] / hbm_gbs,
+                                                     'bytes_per_launch': sol['work']}}
         line['kernels'] = kern
         # "KKT-residual match vs CPU ref": one teacher-forced Newton step of a small instance of the same NLP
         # family on this GPU against the CPU oracle (the full parity suite is tests/test_gpu_engine.py)
@@ -471,6 +557,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--ref-skip-sample', action='store_true', help='reference arm: skip the n=1024 extra')
+    ap.add_argument('--traj-steps', type=int, default=12, help='real-trajectory leg: consecutive Newton steps from x0')
     ap.add_argument('--flags', type=int, default=DEFAULT_FLAGS,
                     help='b200ipm_params.flags: 1 no speculative reghess, 2 tcgen05 int8 SYRKs, (v << 2) tcgen05 tile variant')
     ap.add_argument('--workload', default='c3', choices=['c3', 'c4'])
@@ -479,7 +567,7 @@ def main():
     if args.workload == 'c4':
         return run_c4(args)
     if args.impl == 'reference':
-        return run_reference(args)    # each step is a ~3-6 s bounded CPU sample (see oracle_sample_step)
+        return run_reference(args)    # ONE real config-3 step (minutes); see run_reference
     args.warmup = max(args.warmup, 3)
     return run_b200(args)
 

@@ -164,6 +164,20 @@ int b200ipm_step_max(b200ipm_handle h, double* alpha_smax, double* alpha_lmax);
  * search (+ second-order correction), state update, KKT at the new point. */
 int b200ipm_newton_step(b200ipm_handle h, b200ipm_step_info* info);
 
+/* ---- L-BFGS mode (pyipm.py:993-1371): compact representation + Woodbury on the device ---------- */
+/* lbfgs_init (pyipm.py:993-1005, 1633-1637): m = IPM's `lbfgs` (up to m + 1 pairs are kept, pyipm.py:1300), zeta =
+ * `lbfgs_zeta`; empties the storage and snapshots the current x as x_old. */
+int b200ipm_lbfgs_init(b200ipm_handle h, int m, double zeta);
+/* lbfgs_update (pyipm.py:1282-1371) with dx = x - x_old, dg = dL/dx(x) - dL/dx(x_old) at the CURRENT (s, lda)
+ * (pyipm.py:1706-1707).  gradx_old (D doubles, host) = dL/dx at x_old; NULL: evaluated here (lowered problems). */
+int b200ipm_lbfgs_update(b200ipm_handle h, const double* gradx_old);
+/* lbfgs_dir (pyipm.py:1184-1246, graph 1007-1182) + sign flip (1723-1725): dz (K, may be NULL). */
+int b200ipm_lbfgs_direction(b200ipm_handle h, double* dz, b200ipm_step_info* info);
+/* One inner iteration in L-BFGS mode (pyipm.py:1702-1713, 1723-1754): [update] + direction + nu rule + step rules +
+ * line search + KKT at the new point.  do_update = (inner > 0 or outer > 0), pyipm.py:1705. */
+int b200ipm_lbfgs_step(b200ipm_handle h, int do_update, b200ipm_step_info* info);
+int b200ipm_lbfgs_state(b200ipm_handle h, int* m, double* zeta, int* fail);
+
 /* ---- generic dense symmetric-indefinite factor/solve (sym_solve_cmp slot, pyipm.py:911-914; config 4) -- */
 /* A is n x n (leading dimension lda) symmetric, lower triangle referenced; factored in a private copy. */
 int b200ipm_ldlt_create(int n, int device, void* stream, b200ipm_ldlt_handle* out);

@@ -63,7 +63,8 @@ SYMBOLS = [
     'b200ipm_init_lambda', 'b200ipm_update_mu', 'b200ipm_direction', 'b200ipm_step_max', 'b200ipm_newton_step',
     'b200ipm_ldlt_create', 'b200ipm_ldlt_destroy', 'b200ipm_ldlt_factor', 'b200ipm_ldlt_solve',
     'b200ipm_ldlt_tile_factor', 'b200ipm_ldlt_panel', 'b200ipm_ldlt_import', 'b200ipm_gemm_nt_update', 'b200ipm_gemm_nt_update_bc', 'b200ipm_test_syrk', 'b200ipm_test_syrk_i8', 'b200ipm_trace_start', 'b200ipm_trace_dump',
-    'b200ipm_test_gemv',
+    'b200ipm_test_gemv', 'b200ipm_lbfgs_init', 'b200ipm_lbfgs_update', 'b200ipm_lbfgs_direction', 'b200ipm_lbfgs_step',
+    'b200ipm_lbfgs_state',
 ]
 
 _lib = None
@@ -129,6 +130,11 @@ def load():
         'b200ipm_test_syrk_i8': (i, [i, vp, d, vp, d, i, C.POINTER(vp), C.POINTER(vp), ip, dp, vp, C.c_uint, i, i, i,
                                      C.POINTER(C.c_float), ip]),
         'b200ipm_test_gemv': (i, [i, i, vp, vp, vp, i]),
+        'b200ipm_lbfgs_init': (i, [vp, i, d]),
+        'b200ipm_lbfgs_update': (i, [vp, vp]),
+        'b200ipm_lbfgs_direction': (i, [vp, vp, C.POINTER(StepInfo)]),
+        'b200ipm_lbfgs_step': (i, [vp, i, C.POINTER(StepInfo)]),
+        'b200ipm_lbfgs_state': (i, [vp, ip, dp, ip]),
         'b200ipm_trace_start': (i, []),
         'b200ipm_trace_dump': (i, [vp, vp, vp, vp, vp, i, ip]),
     }
@@ -302,6 +308,30 @@ class Engine(object):
         info = StepInfo()
         check(self.lib.b200ipm_newton_step(self.h, C.byref(info)))
         return info
+
+    # ---- L-BFGS mode (pyipm.py:993-1371)
+    def lbfgs_init(self, m, zeta=1.0):
+        check(self.lib.b200ipm_lbfgs_init(self.h, int(m), float(zeta)))
+
+    def lbfgs_update(self, gradx_old=None):
+        gradx_old = f64(gradx_old)
+        check(self.lib.b200ipm_lbfgs_update(self.h, ptr(gradx_old)))
+
+    def lbfgs_direction(self, want_dz=True):
+        dz = np.empty(self.K) if want_dz else None
+        info = StepInfo()
+        check(self.lib.b200ipm_lbfgs_direction(self.h, ptr(dz), C.byref(info)))
+        return dz, info
+
+    def lbfgs_step(self, do_update):
+        info = StepInfo()
+        check(self.lib.b200ipm_lbfgs_step(self.h, 1 if do_update else 0, C.byref(info)))
+        return info
+
+    def lbfgs_state(self):
+        m, fail, zeta = C.c_int(), C.c_int(), C.c_double()
+        check(self.lib.b200ipm_lbfgs_state(self.h, C.byref(m), C.byref(zeta), C.byref(fail)))
+        return m.value, zeta.value, fail.value
 
     def sync(self):
         check(self.lib.b200ipm_sync(self.h))

@@ -90,6 +90,14 @@ struct b200ipm_engine {
     PolyData poly{};
     cudaEvent_t ev[EV_N];
     double last_red[8];     // host copy of the residual reductions at the current state
+    // L-BFGS mode (pyipm.py:993-1371): storage S, Y on the device (row k = pair k, oldest first), the small m x m arrays
+    // SS, L, D of the compact representation on the host
+    int lb_max = 0, lb_m = 0, lb_fail = 0, lb_eq_reg = 0;
+    double lb_zeta = 1.0, lb_zeta0 = 1.0, lb_rcond = 0.0;
+    double *lb_S = nullptr, *lb_Y = nullptr, *lb_W = nullptr, *lb_xold = nullptr, *lb_gold = nullptr, *lb_dx = nullptr,
+           *lb_dg = nullptr, *lb_X00 = nullptr, *lb_X01 = nullptr, *lb_zg = nullptr, *lb_t = nullptr, *lb_q = nullptr,
+           *lb_dots = nullptr, *lb_coef = nullptr;
+    std::vector<double> lb_SS, lb_L, lb_D;
     // device-resident snapshot
     double *sv_x = nullptr, *sv_s = nullptr, *sv_lam = nullptr;
     double sv_mu = 0, sv_nu = 0, sv_delta = 0, sv_mu_host = 0;
@@ -979,6 +987,296 @@ static void fill_times(Eng* h, b200ipm_step_info* info) {
     info->ms_condense_kernel = el(EV_COND0, EV_COND1);
 }
 
+
+// ------------------------------------------------------------------------------------------ L-BFGS mode
+// pyipm.py:993-1371 behind the same boundary.  The O(D m), O(D (M+N)) and O((M+N)^3) work (storage products, J / J'
+// images, the Schur complement B' A^-1 B and its factorisation) runs on the device; the 2m x 2m systems of the compact
+// representation are solved on the host (general LU with partial pivoting, as sym_solve does, pyipm.py:18-20).
+static int lu_solve_host(int n, std::vector<double>& A, std::vector<double>& b) {
+    for (int k = 0; k < n; k++) {
+        int piv = k;
+        double best = fabs(A[(size_t)k * n + k]);
+        for (int i = k + 1; i < n; i++) {
+            const double v = fabs(A[(size_t)i * n + k]);
+            if (v > best) { best = v; piv = i; }
+        }
+        if (best == 0.0) return fail_msg("L-BFGS: singular compact-representation system");
+        if (piv != k) {
+            for (int j = 0; j < n; j++) std::swap(A[(size_t)k * n + j], A[(size_t)piv * n + j]);
+            std::swap(b[k], b[piv]);
+        }
+        const double d = A[(size_t)k * n + k];
+        for (int i = k + 1; i < n; i++) {
+            const double l = A[(size_t)i * n + k] / d;
+            if (l == 0.0) continue;
+            for (int j = k + 1; j < n; j++) A[(size_t)i * n + j] -= l * A[(size_t)k * n + j];
+            b[i] -= l * b[k];
+        }
+    }
+    for (int i = n - 1; i >= 0; i--) {
+        double acc = b[i];
+        for (int j = i + 1; j < n; j++) acc -= A[(size_t)i * n + j] * b[j];
+        b[i] = acc / A[(size_t)i * n + i];
+    }
+    return 0;
+}
+static void lb_reset(Eng* h) {   // lbfgs_init, pyipm.py:993-1005
+    h->lb_zeta = h->lb_zeta0;
+    h->lb_m = 0;
+    h->lb_fail = 0;
+    std::fill(h->lb_SS.begin(), h->lb_SS.end(), 0.0);
+    std::fill(h->lb_L.begin(), h->lb_L.end(), 0.0);
+    std::fill(h->lb_D.begin(), h->lb_D.end(), 0.0);
+}
+static int lb_alloc(Eng* h, int m) {
+    if (h->lb_S && h->lb_max == m) return 0;
+    double* old[] = {h->lb_S, h->lb_Y, h->lb_W, h->lb_xold, h->lb_gold, h->lb_dx, h->lb_dg, h->lb_X00, h->lb_X01, h->lb_zg,
+                     h->lb_t, h->lb_q, h->lb_dots, h->lb_coef};
+    for (double* b : old) cudaFree(b);
+    const size_t cap = (size_t)m + 1, D = h->D, C = std::max(h->C, 1), P = h->D + h->N;
+    RET(dalloc(&h->lb_S, cap * D)); RET(dalloc(&h->lb_Y, cap * D)); RET(dalloc(&h->lb_W, 2 * cap * D));
+    RET(dalloc(&h->lb_xold, D)); RET(dalloc(&h->lb_gold, D)); RET(dalloc(&h->lb_dx, D)); RET(dalloc(&h->lb_dg, D));
+    RET(dalloc(&h->lb_X00, 2 * cap * C)); RET(dalloc(&h->lb_X01, 2 * cap * P)); RET(dalloc(&h->lb_zg, (size_t)h->K));
+    RET(dalloc(&h->lb_t, C)); RET(dalloc(&h->lb_q, C)); RET(dalloc(&h->lb_dots, 4 * cap + 8)); RET(dalloc(&h->lb_coef, 2 * cap));
+    h->lb_max = m;
+    h->lb_SS.assign(cap * cap, 0.0);
+    h->lb_L.assign(cap * cap, 0.0);
+    h->lb_D.assign(cap * cap, 0.0);
+    return 0;
+}
+// lbfgs_update, pyipm.py:1282-1371.  gradx_old: dL/dx at (x_old; current s, lda) on the host, or NULL for a lowered problem
+// (then it is evaluated here; the reference recomputes it the same way, pyipm.py:1706).
+static int lb_update(Eng* h, const double* gradx_old) {
+    const int D = h->D, C = h->C, cap = h->lb_max + 1;
+    const double eps = h->p.eps, rt = sqrt(eps);
+    if (gradx_old) {
+        RET(up(h, h->lb_gold, gradx_old, D, 0));
+    } else {
+        if (h->kind != KIND_QUAD && h->kind != KIND_POLY) return fail_msg("lbfgs_update: gradx_old is required in callable mode");
+        CU(cudaMemcpyAsync(h->xt, h->x, sizeof(double) * D, cudaMemcpyDeviceToDevice, h->st));
+        CU(cudaMemcpyAsync(h->x, h->lb_xold, sizeof(double) * D, cudaMemcpyDeviceToDevice, h->st));
+        h->eval_valid = false;
+        RET(eval_derivs(h));
+        if (C) RET(gemv_n(h->st, h->J, h->ldJ, D, C, h->lam, h->df, 1.0, -1.0, h->lb_gold));
+        else CU(cudaMemcpyAsync(h->lb_gold, h->df, sizeof(double) * D, cudaMemcpyDeviceToDevice, h->st));
+        CU(cudaMemcpyAsync(h->x, h->xt, sizeof(double) * D, cudaMemcpyDeviceToDevice, h->st));
+        h->eval_valid = false;
+    }
+    RET(residual(h));     // g at the current point (also the g of the direction, pyipm.py:1711)
+    axpby_kernel<<<cdiv(D, 256), 256, 0, h->st>>>(D, 1.0, h->g, -1.0, h->lb_gold, h->lb_dg);       // dg = g_old - g_new (g = -grad)
+    LAUNCHED();
+    axpby_kernel<<<cdiv(D, 256), 256, 0, h->st>>>(D, 1.0, h->x, -1.0, h->lb_xold, h->lb_dx);
+    LAUNCHED();
+    dots_kernel<<<1, 256, 0, h->st>>>(D, h->lb_dg, h->lb_dx, D, h->lb_dots);
+    LAUNCHED();
+    dots_kernel<<<1, 256, 0, h->st>>>(D, h->lb_dx, h->lb_dx, D, h->lb_dots + 1);
+    LAUNCHED();
+    dots_kernel<<<1, 256, 0, h->st>>>(D, h->lb_dg, h->lb_dg, D, h->lb_dots + 2);
+    LAUNCHED();
+    RET(fetch_red(h, h->lb_dots, 3));
+    const double dgdx = h->h_red[0], dxdx = h->h_red[1], dgdg = h->h_red[2];
+    const double zeta_new = C ? dgdx / (dxdx + eps) : dgdx / (dgdg + eps);
+    if (dgdx > rt && zeta_new > rt) {
+        h->lb_zeta = zeta_new;
+        int m = h->lb_m;
+        if (m > h->lb_max) {
+            for (int k = 1; k < m; k++) {
+                CU(cudaMemcpyAsync(h->lb_S + (size_t)(k - 1) * D, h->lb_S + (size_t)k * D, sizeof(double) * D, cudaMemcpyDeviceToDevice, h->st));
+                CU(cudaMemcpyAsync(h->lb_Y + (size_t)(k - 1) * D, h->lb_Y + (size_t)k * D, sizeof(double) * D, cudaMemcpyDeviceToDevice, h->st));
+            }
+            for (int i = 0; i + 1 < m; i++)
+                for (int j = 0; j + 1 < m; j++) {
+                    h->lb_SS[(size_t)i * cap + j] = h->lb_SS[(size_t)(i + 1) * cap + j + 1];
+                    h->lb_L[(size_t)i * cap + j] = h->lb_L[(size_t)(i + 1) * cap + j + 1];
+                    h->lb_D[(size_t)i * cap + j] = h->lb_D[(size_t)(i + 1) * cap + j + 1];
+                }
+        } else {
+            m += 1;
+            for (int i = 0; i < m; i++) {
+                h->lb_SS[(size_t)i * cap + m - 1] = h->lb_SS[(size_t)(m - 1) * cap + i] = 0.0;
+                h->lb_L[(size_t)i * cap + m - 1] = h->lb_L[(size_t)(m - 1) * cap + i] = 0.0;
+                h->lb_D[(size_t)i * cap + m - 1] = h->lb_D[(size_t)(m - 1) * cap + i] = 0.0;
+            }
+            h->lb_m = m;
+        }
+        CU(cudaMemcpyAsync(h->lb_S + (size_t)(m - 1) * D, h->lb_dx, sizeof(double) * D, cudaMemcpyDeviceToDevice, h->st));
+        CU(cudaMemcpyAsync(h->lb_Y + (size_t)(m - 1) * D, h->lb_dg, sizeof(double) * D, cudaMemcpyDeviceToDevice, h->st));
+        // constrained: SS_update = S' dx, L_update = dx' Y;  unconstrained: "SS" = Y' dg (YY), "L" = S' dg (R)
+        dots_kernel<<<m, 256, 0, h->st>>>(D, C ? h->lb_dx : h->lb_dg, C ? h->lb_S : h->lb_Y, D, h->lb_dots);
+        LAUNCHED();
+        dots_kernel<<<m, 256, 0, h->st>>>(D, C ? h->lb_dx : h->lb_dg, C ? h->lb_Y : h->lb_S, D, h->lb_dots + cap);
+        LAUNCHED();
+        RET(fetch_red(h, h->lb_dots, 2 * cap));
+        for (int i = 0; i < m; i++) {
+            h->lb_SS[(size_t)i * cap + m - 1] = h->h_red[i];
+            h->lb_SS[(size_t)(m - 1) * cap + i] = h->h_red[i];
+        }
+        if (C) {
+            for (int j = 0; j < m; j++) h->lb_L[(size_t)(m - 1) * cap + j] = h->h_red[cap + j];
+            h->lb_L[(size_t)(m - 1) * cap + m - 1] = 0.0;
+        } else {
+            for (int i = 0; i < m; i++) h->lb_L[(size_t)i * cap + m - 1] = h->h_red[cap + i];
+        }
+        h->lb_D[(size_t)(m - 1) * cap + m - 1] = dgdx;
+        h->lb_fail = 0;
+    } else {
+        h->lb_fail++;
+    }
+    if (h->lb_fail > h->lb_max && h->lb_m > 0) lb_reset(h);
+    CU(cudaMemcpyAsync(h->lb_xold, h->x, sizeof(double) * D, cudaMemcpyDeviceToDevice, h->st));
+    return 0;
+}
+// lbfgs_dir, pyipm.py:1184-1246 with the graph of lbfgs_builder (1007-1182); result in h->dz (reference sign convention)
+static int lb_direction(Eng* h, b200ipm_step_info* info) {
+    const int D = h->D, M = h->M, N = h->N, C = h->C, K = h->K, m = h->lb_m, P = D + N;
+    const double zeta = h->lb_zeta;
+    RET(residual(h));
+    axpby_kernel<<<cdiv(K, 256), 256, 0, h->st>>>(K, -1.0, h->g, 0.0, nullptr, h->bvec);   // g of the reference = -grad
+    LAUNCHED();
+    CU(cudaMemsetAsync(h->red + 8, 0, sizeof(double), h->st));
+    h->lb_eq_reg = 0;
+    if (C) {
+        // G = B' A^-1 B = J'J / zeta + diag(0_M, 1/Sigma)      (pyipm.py:1101-1104)
+        const int ldt = (int)rup(D, 16);
+        if (!h->Jt) RET(dalloc(&h->Jt, (size_t)C * ldt));
+        RET(transpose(h->st, h->J, h->ldJ, D, C, h->Jt, ldt));
+        RET(ensure_F2(h, C));
+        lb_gdiag_kernel<<<cdiv(std::max(M, N), 256), 256, 0, h->st>>>(M, N, h->sigma, h->uvec);
+        LAUNCHED();
+        for (int attempt = 0; attempt < 2; attempt++) {
+            GemmArgs a{};
+            a.C = h->F2.A; a.ldc = h->F2.ld; a.Cin = nullptr; a.n = C; a.m = C; a.beta = 0.0; a.shift = 0.0; a.dadd = h->uvec;
+            a.mode = GEMM_UPPER_MIRROR; a.nterms = 1;
+            a.t[0] = GemmTerm{h->Jt, h->Jt, nullptr, ldt, ldt, D, 1.0 / zeta};
+            RET(gemm_nt(h->st, a));
+            if (attempt == 1) {
+                // eq block regularised (pyipm.py:1110-1112): + sqrt(eps) eta mu^beta I on G[:M, :M]
+                fill_kernel<<<cdiv(M, 256), 256, 0, h->st>>>(M, h->p.reg_coef * h->p.eta * pow(h->mu, h->p.beta), h->lb_q);
+                LAUNCHED();
+                kc_diag_add_kernel<<<cdiv(M, 256), 256, 0, h->st>>>(h->F2.A, h->F2.ld, M, h->lb_q);
+                LAUNCHED();
+            }
+            RET(ldlt_factor(h->F2));
+            if (attempt == 1 || !M) break;
+            // rcond of the eq block G[:M, :M] (pyipm.py:1107-1109, eigh there): estimated from the pivots of its LDL^T,
+            // which are the first M pivots of G's (positive definite: no interchanges)
+            std::vector<double> piv((size_t)M);
+            const size_t npad = (size_t)h->F2.nblk * NB;
+            CU(cudaMemcpyAsync(piv.data(), h->F2.dinfo + 2 * npad, sizeof(double) * M, cudaMemcpyDeviceToHost, h->st));
+            CU(cudaStreamSynchronize(h->st));
+            double mn = INFINITY, mx = 0.0;
+            for (int i = 0; i < M; i++) { mn = std::min(mn, fabs(piv[i])); mx = std::max(mx, fabs(piv[i])); }
+            h->lb_rcond = (mx > 0.0) ? mn / mx : 0.0;
+            if (!(h->lb_rcond <= h->p.eps)) break;
+            h->lb_eq_reg = 1;
+        }
+        // t = G^-1 (B' A^-1 g_p - g_d);   Zg = [g_p / Adiag - A^-1 B t ; t]        (pyipm.py:1115-1124, merged by linearity)
+        const double* gp = h->bvec;
+        const double* gd = h->bvec + P;
+        RET(gemv_t(h->st, h->J, h->ldJ, D, C, gp, nullptr, 0.0, 1.0, h->jt, h->scr));
+        lb_btainv_kernel<<<cdiv(C, 256), 256, 0, h->st>>>(M, N, zeta, h->jt, N ? gp + D : nullptr, h->sigma, gd, h->lb_q);
+        LAUNCHED();
+        RET(ldlt_solve(h->F2, h->lb_q, h->lb_t));
+        RET(gemv_n(h->st, h->J, h->ldJ, D, C, h->lb_t, nullptr, 0.0, 1.0, h->wx));
+        lb_ainvb_kernel<<<cdiv(P, 256), 256, 0, h->st>>>(D, M, N, zeta, gp, 1.0, h->wx, h->lb_t, -1.0, h->sigma, h->lb_zg);
+        LAUNCHED();
+        CU(cudaMemcpyAsync(h->lb_zg + P, h->lb_t, sizeof(double) * C, cudaMemcpyDeviceToDevice, h->st));
+        if (m > 0) {
+            const int m2 = 2 * m;
+            dim3 gw(cdiv(D, 256), m2);
+            lb_build_w_kernel<<<gw, 256, 0, h->st>>>(D, m, D, h->lb_S, h->lb_Y, zeta, 1.0, h->lb_W);   // W = [zeta S, Y]
+            LAUNCHED();
+            for (int c = 0; c < m2; c++) {
+                const double* Wc = h->lb_W + (size_t)c * D;
+                double* x00 = h->lb_X00 + (size_t)c * C;
+                double* x01 = h->lb_X01 + (size_t)c * P;
+                // X00_c = -G^-1 (B' W_c / zeta);  X01_c = W_c / zeta + A^-1 B X00_c      (pyipm.py:1134-1136)
+                RET(gemv_t(h->st, h->J, h->ldJ, D, C, Wc, nullptr, 0.0, 1.0, h->jt, h->scr));
+                lb_btainv_kernel<<<cdiv(C, 256), 256, 0, h->st>>>(M, N, zeta, h->jt, nullptr, h->sigma, nullptr, h->lb_q);
+                LAUNCHED();
+                RET(ldlt_solve(h->F2, h->lb_q, x00));
+                axpby_kernel<<<cdiv(C, 256), 256, 0, h->st>>>(C, -1.0, x00, 0.0, nullptr, x00);
+                LAUNCHED();
+                RET(gemv_n(h->st, h->J, h->ldJ, D, C, x00, nullptr, 0.0, 1.0, h->wx));
+                CU(cudaMemsetAsync(x01 + D, 0, sizeof(double) * N, h->st));
+                CU(cudaMemcpyAsync(x01, Wc, sizeof(double) * D, cudaMemcpyDeviceToDevice, h->st));
+                lb_ainvb_kernel<<<cdiv(P, 256), 256, 0, h->st>>>(D, M, N, zeta, x01, 1.0, h->wx, x00, 1.0, h->sigma, x01);
+                LAUNCHED();
+            }
+            // X02 = W' X01 (2m x 2m), v10 = W' Zg_p   ->  host
+            std::vector<double> X02((size_t)m2 * m2), v10((size_t)m2), tmp((size_t)m2);
+            double* dd = h->lb_dots;   // 2*cap + ... entries: reuse per column
+            for (int c = 0; c <= m2; c++) {
+                const double* vec = (c < m2) ? h->lb_X01 + (size_t)c * P : h->lb_zg;
+                dots_kernel<<<m2, 256, 0, h->st>>>(D, vec, h->lb_W, D, dd);
+                LAUNCHED();
+                CU(cudaMemcpyAsync(tmp.data(), dd, sizeof(double) * m2, cudaMemcpyDeviceToHost, h->st));
+                CU(cudaStreamSynchronize(h->st));
+                for (int a2 = 0; a2 < m2; a2++) {
+                    if (c < m2) X02[(size_t)a2 * m2 + c] = tmp[a2];
+                    else v10[a2] = tmp[a2];
+                }
+            }
+            // (X02 - Minv) v11 = v10,  Minv = [[zeta SS, L], [L', -D]]        (pyipm.py:1138-1144)
+            const int cap = h->lb_max + 1;
+            for (int i = 0; i < m; i++)
+                for (int j = 0; j < m; j++) {
+                    X02[(size_t)i * m2 + j] -= zeta * h->lb_SS[(size_t)i * cap + j];
+                    X02[(size_t)i * m2 + m + j] -= h->lb_L[(size_t)i * cap + j];
+                    X02[(size_t)(m + i) * m2 + j] -= h->lb_L[(size_t)j * cap + i];
+                    X02[(size_t)(m + i) * m2 + m + j] += h->lb_D[(size_t)i * cap + j];
+                }
+            RET(lu_solve_host(m2, X02, v10));
+            CU(cudaMemcpyAsync(h->lb_coef, v10.data(), sizeof(double) * m2, cudaMemcpyHostToDevice, h->st));
+            // dz = Zg - [X01; -X00] v11
+            lb_combine_kernel<<<cdiv(P, 256), 256, 0, h->st>>>(P, m2, P, h->lb_X01, h->lb_coef, -1.0, h->lb_zg);
+            LAUNCHED();
+            lb_combine_kernel<<<cdiv(C, 256), 256, 0, h->st>>>(C, m2, C, h->lb_X00, h->lb_coef, 1.0, h->lb_zg + P);
+            LAUNCHED();
+            CU(cudaStreamSynchronize(h->st));    // v10 lives on this stack frame
+        }
+    } else {
+        // unconstrained: dz = zeta g + W [A; B],  W = [S, zeta Y]   (pyipm.py:1149-1175; R = L, Y'Y = SS)
+        axpby_kernel<<<cdiv(D, 256), 256, 0, h->st>>>(D, zeta, h->bvec, 0.0, nullptr, h->lb_zg);
+        LAUNCHED();
+        if (m > 0) {
+            const int m2 = 2 * m, cap = h->lb_max + 1;
+            dim3 gw(cdiv(D, 256), m2);
+            lb_build_w_kernel<<<gw, 256, 0, h->st>>>(D, m, D, h->lb_S, h->lb_Y, 1.0, zeta, h->lb_W);
+            LAUNCHED();
+            dots_kernel<<<m2, 256, 0, h->st>>>(D, h->bvec, h->lb_W, D, h->lb_dots);
+            LAUNCHED();
+            std::vector<double> wtg((size_t)m2);
+            CU(cudaMemcpyAsync(wtg.data(), h->lb_dots, sizeof(double) * m2, cudaMemcpyDeviceToHost, h->st));
+            CU(cudaStreamSynchronize(h->st));
+            std::vector<double> Lm((size_t)m * m), Lt((size_t)m * m), bv(wtg.begin(), wtg.begin() + m), rhs((size_t)m), t2(wtg.begin() + m, wtg.end());
+            for (int i = 0; i < m; i++)
+                for (int j = 0; j < m; j++) { Lm[(size_t)i * m + j] = h->lb_L[(size_t)i * cap + j]; Lt[(size_t)j * m + i] = h->lb_L[(size_t)i * cap + j]; }
+            std::vector<double> A1 = Lm;
+            RET(lu_solve_host(m, A1, bv));                       // B = -L^-1 WT_g[:m]
+            for (int i = 0; i < m; i++) bv[i] = -bv[i];
+            for (int i = 0; i < m; i++) {
+                double acc = 0.0;
+                for (int j = 0; j < m; j++) acc += (h->lb_D[(size_t)i * cap + j] + zeta * h->lb_SS[(size_t)i * cap + j]) * bv[j];
+                rhs[i] = acc;
+            }
+            std::vector<double> A2 = Lt, A3 = Lt;
+            RET(lu_solve_host(m, A2, rhs));                      // L^-T (D + zeta SS) B
+            RET(lu_solve_host(m, A3, t2));                       // L^-T WT_g[m:]
+            std::vector<double> coef((size_t)m2);
+            for (int i = 0; i < m; i++) { coef[i] = -rhs[i] - t2[i]; coef[m + i] = bv[i]; }
+            CU(cudaMemcpyAsync(h->lb_coef, coef.data(), sizeof(double) * m2, cudaMemcpyHostToDevice, h->st));
+            lb_combine_kernel<<<cdiv(D, 256), 256, 0, h->st>>>(D, m2, D, h->lb_W, h->lb_coef, 1.0, h->lb_zg);
+            LAUNCHED();
+            CU(cudaStreamSynchronize(h->st));
+        }
+    }
+    flip_kernel<<<cdiv(K, 256), 256, 0, h->st>>>(D, N, K, h->lb_zg, h->dz);     // pyipm.py:1723-1725
+    LAUNCHED();
+    if (info) { info->eq_reg = h->lb_eq_reg; info->rcond = h->lb_rcond; info->n_factor = 0; info->delta = h->delta; }
+    return 0;
+}
+
 // =========================================================================================== C ABI
 extern "C" {
 
@@ -1043,6 +1341,8 @@ int b200ipm_destroy(b200ipm_handle h) {
                       h->ud, h->gd, h->vd, h->Q, h->qc, h->At, h->Ut, h->qb, h->Gt, h->Vt, h->qr, h->Jt, h->p_coeff, h->sv_x,
                       h->sv_s, h->sv_lam};
     for (double* b : bufs) cudaFree(b);
+    for (double* b : {h->lb_S, h->lb_Y, h->lb_W, h->lb_xold, h->lb_gold, h->lb_dx, h->lb_dg, h->lb_X00, h->lb_X01, h->lb_zg, h->lb_t,
+                      h->lb_q, h->lb_dots, h->lb_coef}) cudaFree(b);
     cudaFree(h->p_rowptr); cudaFree(h->p_ptr); cudaFree(h->p_fvar); cudaFree(h->p_fpow); cudaFree(h->d_sig);
     cudaFreeHost(h->h_red);
     if (h->stB) cudaStreamSynchronize(h->stB);
@@ -1145,7 +1445,7 @@ int b200ipm_bind_poly(b200ipm_handle h, int nterms, const int* term_row, const d
 
 int b200ipm_set_derivs(b200ipm_handle h, double fval, const double* df, const double* ce, const double* ci, const double* J,
                        const double* d2L, int on_device) {
-    if (!h || !df || !d2L) return fail_msg("set_derivs: df and d2L are required");
+    if (!h || !df) return fail_msg("set_derivs: df is required");   // d2L may be NULL in L-BFGS mode (never used there)
     CU(cudaSetDevice(h->device));
     const int D = h->D, M = h->M, N = h->N, C = h->C;
     if (C && !J) return fail_msg("set_derivs: J is required when there are constraints");
@@ -1155,14 +1455,16 @@ int b200ipm_set_derivs(b200ipm_handle h, double fval, const double* df, const do
     if (M) RET(up(h, h->ce, ce, M, on_device));
     if (N) RET(up(h, h->ci, ci, N, on_device));
     if (C) CU(cudaMemcpy2DAsync(h->J, sizeof(double) * h->ldJ, J, sizeof(double) * C, sizeof(double) * C, D, kd, h->st));
-    CU(cudaMemcpy2DAsync(h->W, sizeof(double) * h->ldW, d2L, sizeof(double) * D, sizeof(double) * D, D, kd, h->st));
-    dim3 blk(32, 8), grid(cdiv(D, 32), cdiv(D, 8));
-    sym_from_upper_kernel<<<grid, blk, 0, h->st>>>(h->W, h->ldW, D);
-    LAUNCHED();
+    if (d2L) {
+        CU(cudaMemcpy2DAsync(h->W, sizeof(double) * h->ldW, d2L, sizeof(double) * D, sizeof(double) * D, D, kd, h->st));
+        dim3 blk(32, 8), grid(cdiv(D, 32), cdiv(D, 8));
+        sym_from_upper_kernel<<<grid, blk, 0, h->st>>>(h->W, h->ldW, D);
+        LAUNCHED();
+    }
     CU(cudaStreamSynchronize(h->st));   // fval lives on the caller's stack
     if (h->kind == KIND_NONE) h->kind = KIND_CALLABLE;
     h->eval_valid = true;
-    h->hess_valid = true;
+    h->hess_valid = (d2L != nullptr);
     h->resid_valid = false;
     return 0;
 }
@@ -1488,15 +1790,12 @@ int b200ipm_step_max(b200ipm_handle h, double* alpha_smax, double* alpha_lmax) {
     return 0;
 }
 
-int b200ipm_newton_step(b200ipm_handle h, b200ipm_step_info* info) {
-    if (!h || !info) return fail_msg("null argument");
-    CU(cudaSetDevice(h->device));
-    memset(info, 0, sizeof(*info));
-    CU(cudaEventRecord(h->ev[EV_START], h->st));
-    RET(compute_direction(h, info));
+// nu rule (pyipm.py:1727-1735), step rules + line search (1737-1749), KKT at the new point (1754): everything of an inner
+// iteration after the search direction h->dz is known
+static int finish_step(Eng* h, b200ipm_step_info* info) {
     double stats[9];
     RET(dir_stats(h, stats));
-    info->resid = h->h_red[8];
+    info->resid = h->h_red[8];       // ||b - K dz||_inf of the last refinement sweep (red[8], fetched with the stats)
     info->con_l1 = h->last_red[4];
     if (h->C) {
         // merit parameter update (pyipm.py:1727-1735); IEEE semantics for ||con||_1 == 0 are the reference's
@@ -1514,6 +1813,65 @@ int b200ipm_newton_step(b200ipm_handle h, b200ipm_step_info* info) {
     info->mu = h->mu; info->nu = h->nu; info->delta = h->delta;
     CU(cudaStreamSynchronize(h->st));
     fill_times(h, info);
+    return 0;
+}
+
+int b200ipm_newton_step(b200ipm_handle h, b200ipm_step_info* info) {
+    if (!h || !info) return fail_msg("null argument");
+    CU(cudaSetDevice(h->device));
+    memset(info, 0, sizeof(*info));
+    CU(cudaEventRecord(h->ev[EV_START], h->st));
+    RET(compute_direction(h, info));
+    return finish_step(h, info);
+}
+
+// ------------------------------------------------------------------------------------------ L-BFGS ABI
+int b200ipm_lbfgs_init(b200ipm_handle h, int m, double zeta) {
+    if (!h || m <= 0 || !(zeta > 0.0)) return fail_msg("lbfgs_init: bad arguments");
+    CU(cudaSetDevice(h->device));
+    RET(lb_alloc(h, m));
+    h->lb_zeta0 = zeta;
+    lb_reset(h);
+    CU(cudaMemcpyAsync(h->lb_xold, h->x, sizeof(double) * h->D, cudaMemcpyDeviceToDevice, h->st));
+    return 0;
+}
+int b200ipm_lbfgs_update(b200ipm_handle h, const double* gradx_old) {
+    if (!h || !h->lb_S) return fail_msg("lbfgs_update: call b200ipm_lbfgs_init first");
+    CU(cudaSetDevice(h->device));
+    return lb_update(h, gradx_old);
+}
+int b200ipm_lbfgs_direction(b200ipm_handle h, double* dz, b200ipm_step_info* info) {
+    if (!h || !h->lb_S) return fail_msg("lbfgs_direction: call b200ipm_lbfgs_init first");
+    CU(cudaSetDevice(h->device));
+    b200ipm_step_info tmp{};
+    if (!info) info = &tmp;
+    memset(info, 0, sizeof(*info));
+    CU(cudaEventRecord(h->ev[EV_START], h->st));
+    RET(lb_direction(h, info));
+    if (dz) { RET(down(h, dz, h->dz, h->K)); }
+    CU(cudaStreamSynchronize(h->st));
+    info->mu = h->mu; info->nu = h->nu;
+    return 0;
+}
+int b200ipm_lbfgs_step(b200ipm_handle h, int do_update, b200ipm_step_info* info) {
+    if (!h || !info) return fail_msg("null argument");
+    if (!h->lb_S) return fail_msg("lbfgs_step: call b200ipm_lbfgs_init first");
+    if (h->kind != KIND_QUAD && h->kind != KIND_POLY) return fail_msg("lbfgs_step needs a lowered problem (callable mode: update + direction)");
+    CU(cudaSetDevice(h->device));
+    memset(info, 0, sizeof(*info));
+    CU(cudaEventRecord(h->ev[EV_START], h->st));
+    if (do_update) RET(lb_update(h, nullptr));       // pyipm.py:1705-1710
+    for (int e : {EV_EVAL, EV_ASSEMBLE, EV_HESS0, EV_HESS1, EV_COND0, EV_COND1}) CU(cudaEventRecord(h->ev[e], h->st));
+    RET(lb_direction(h, info));                      // pyipm.py:1711-1713
+    CU(cudaEventRecord(h->ev[EV_FACTOR], h->st));
+    CU(cudaEventRecord(h->ev[EV_SOLVE], h->st));
+    return finish_step(h, info);
+}
+int b200ipm_lbfgs_state(b200ipm_handle h, int* m, double* zeta, int* fail) {
+    if (!h) return fail_msg("null handle");
+    if (m) *m = h->lb_m;
+    if (zeta) *zeta = h->lb_zeta;
+    if (fail) *fail = h->lb_fail;
     return 0;
 }
 

@@ -644,4 +644,64 @@ __global__ void __launch_bounds__(1024) cert_stats_kernel(int D, const double* _
     if (threadIdx.x == 0) { red[0] = q; red[1] = nv; red[2] = hn; red[3] = vu; }
 }
 
+// ------------------------------------------------------------------------------------------- L-BFGS (pyipm.py:993-1371)
+// out[j] = a . B[j, :]   for j < k   (B row-major k x n, leading dimension ldb; one CTA per row, deterministic tree)
+__global__ void __launch_bounds__(256) dots_kernel(int n, const double* __restrict__ a, const double* __restrict__ B, int ldb,
+                                                   double* __restrict__ out) {
+    __shared__ double sh[33];
+    const double* b = B + (size_t)blockIdx.x * ldb;
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) acc += a[i] * b[i];
+    acc = block_sum(acc, sh);
+    if (threadIdx.x == 0) out[blockIdx.x] = acc;
+}
+// W (2m x D): rows 0..m-1 = cs * S_k, rows m..2m-1 = cy * Y_k   (constrained: cs = zeta, cy = 1; unconstrained: 1, zeta)
+__global__ void lb_build_w_kernel(int D, int m, int ld, const double* __restrict__ S, const double* __restrict__ Y, double cs,
+                                  double cy, double* __restrict__ W) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (i < D) W[(size_t)r * ld + i] = (r < m) ? cs * S[(size_t)r * ld + i] : cy * Y[(size_t)(r - m) * ld + i];
+}
+// u (C) <- [0_M ; 1 / sigma]   (the slack part of B' A^-1 B, pyipm.py:1099-1104)
+__global__ void lb_gdiag_kernel(int M, int N, const double* __restrict__ sigma, double* __restrict__ u) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < M) u[i] = 0.0;
+    if (i < N) u[M + i] = 1.0 / sigma[i];
+}
+// q (C) <- jt / zeta + [0 ; -v_s / sigma] - sub      (B' A^-1 v for v = [v_x; v_s], jt = J' v_x; sub optional)
+__global__ void lb_btainv_kernel(int M, int N, double zeta, const double* __restrict__ jt, const double* __restrict__ vs,
+                                 const double* __restrict__ sigma, const double* __restrict__ sub, double* __restrict__ q) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < M + N) {
+        double v = jt[i] / zeta;
+        if (i >= M && vs) v -= vs[i - M] / sigma[i - M];
+        if (sub) v -= sub[i];
+        q[i] = v;
+    }
+}
+// out (D+N) <- a_scale * base / Adiag + sgn * A^-1 B u :  x rows: (a_scale * base_x + sgn * ju) / zeta,
+// s rows: (a_scale * base_s - sgn * u_i) / sigma         (ju = J u; base optional)
+__global__ void lb_ainvb_kernel(int D, int M, int N, double zeta, const double* __restrict__ base, double a_scale,
+                                const double* __restrict__ ju, const double* __restrict__ u, double sgn,
+                                const double* __restrict__ sigma, double* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < D) out[i] = ((base ? a_scale * base[i] : 0.0) + sgn * ju[i]) / zeta;
+    else if (i < D + N) out[i] = ((base ? a_scale * base[i] : 0.0) - sgn * u[M + i - D]) / sigma[i - D];
+}
+// A[i, i] += d[i]  for i < n
+__global__ void kc_diag_add_kernel(double* __restrict__ A, int ld, int n, const double* __restrict__ d) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) A[(size_t)i * ld + i] += d[i];
+}
+// y <- y - sum_c coef[c] * X[c, :]    (X row-major ncol x n)
+__global__ void lb_combine_kernel(int n, int ncol, int ldx, const double* __restrict__ X, const double* __restrict__ coef,
+                                  double sgn, double* __restrict__ y) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        double acc = 0.0;
+        for (int c = 0; c < ncol; c++) acc += coef[c] * X[(size_t)c * ldx + i];
+        y[i] += sgn * acc;
+    }
+}
+
 }  // namespace b200

@@ -9,7 +9,8 @@ same ``KKT()``, ``validate()``, ``compile()``, the same progress messages and ``
   autodiff, pyipm.py:473-509) or a set of plain Python callables ``f, df, d2f, ce, dce, d2ce, ci, dci, d2ci``
   with the reference's "precompiled function" conventions (pyipm.py:216-231).  ``x_dev`` / ``lambda_dev`` are
   accepted and ignored.
-* ``lbfgs`` must be False (the L-BFGS branch is outside the hot path this package replaces).
+* ``lbfgs=m`` selects the reference's L-BFGS mode (pyipm.py:993-1371): compact representation + Woodbury on the device
+  (``b200ipm_lbfgs_*``); second derivatives are then not needed.
 * The callable slots of the reference (``cost, grad, hess, con, jaco, phi, dphi, init_lambda, init_slack``)
   exist with the same signatures and run on the device for lowered problems.
 
@@ -60,7 +61,10 @@ class IPM(object):
         self.Xtol = Xtol if Xtol else self.eps
         self.Ktol, self.Ftol = Ktol, Ftol
         self.reg_coef = float_dtype(np.sqrt(self.eps))
-        self.lbfgs, self.lbfgs_zeta = lbfgs, lbfgs_zeta
+        # pyipm.py:355-360
+        self.lbfgs = lbfgs
+        self.lbfgs_zeta = float_dtype(1.0) if (lbfgs and lbfgs_zeta is None) else lbfgs_zeta
+        self.lbfgs_fail_max = lbfgs
         self.float_dtype = float_dtype
         # the reference's two shared scalars (pyipm.py:363-364)
         self.nu_dev = float(nu)
@@ -94,7 +98,10 @@ class IPM(object):
         assert self.Xtol >= self.eps
         assert self.Ktol >= self.eps
         assert self.Ftol is None or self.Ftol >= 0.0
-        assert not self.lbfgs, 'pyipm_b200 implements the exact-Hessian path only (lbfgs=False)'
+        assert self.lbfgs >= 0 or self.lbfgs == False  # noqa: E712  (pyipm.py:405-408)
+        if self.lbfgs:
+            assert isinstance(self.lbfgs, int)
+        assert self.lbfgs_zeta is None or self.lbfgs_zeta > 0.0
         assert self.float_dtype == np.float64, 'pyipm_b200 computes in float64'
 
     def compile(self, nvar=None, neq=None, nineq=None):
@@ -114,7 +121,10 @@ class IPM(object):
                 self.nineq = np.asarray(self.ci(self.x0)).size
             elif nineq is None:
                 self.nineq = 0
-            for name in ('df', 'd2f') + (('dce', 'd2ce') if self.neq else ()) + (('dci', 'd2ci') if self.nineq else ()):
+            need = ('df',) + (('dce',) if self.neq else ()) + (('dci',) if self.nineq else ())
+            if not self.lbfgs:     # second derivatives are only used by the exact-Hessian mode (pyipm.py:478-509)
+                need += ('d2f',) + (('d2ce',) if self.neq else ()) + (('d2ci',) if self.nineq else ())
+            for name in need:
                 assert getattr(self, name) is not None, \
                     'callable mode needs %s (no symbolic autodiff; pass a PolyProblem/QuadProblem to have ' \
                     'derivatives generated on the device)' % name
@@ -139,17 +149,19 @@ class IPM(object):
         D, M, N = self.nvar, self.neq, self.nineq
         fval = float(self.f(x))
         df = np.asarray(self.df(x), dtype=np.float64).reshape(D)
-        W = np.array(self.d2f(x), dtype=np.float64).reshape(D, D)
+        W = None if self.lbfgs else np.array(self.d2f(x), dtype=np.float64).reshape(D, D)
         ce = ci = None
         blocks = []
         if M:
             ce = np.asarray(self.ce(x), dtype=np.float64).reshape(M)
             blocks.append(np.asarray(self.dce(x), dtype=np.float64).reshape(D, M))
-            W = W - np.asarray(self.d2ce(x, lda), dtype=np.float64).reshape(D, D)
+            if W is not None:
+                W = W - np.asarray(self.d2ce(x, lda), dtype=np.float64).reshape(D, D)
         if N:
             ci = np.asarray(self.ci(x), dtype=np.float64).reshape(N)
             blocks.append(np.asarray(self.dci(x), dtype=np.float64).reshape(D, N))
-            W = W - np.asarray(self.d2ci(x, lda), dtype=np.float64).reshape(D, D)
+            if W is not None:
+                W = W - np.asarray(self.d2ci(x, lda), dtype=np.float64).reshape(D, D)
         J = np.concatenate(blocks, axis=1) if blocks else None
         self.engine.set_derivs(fval, df, ce, ci, J, W)
 
@@ -250,8 +262,15 @@ class IPM(object):
         Ktol_converged = False
         Ftol_converged = False
         self.signal = 0
+        if self.lbfgs:
+            # pyipm.py:1633-1637
+            eng.lbfgs_init(self.lbfgs, float(self.lbfgs_zeta))
+            self._x_old = np.array(x)
         if self.verbosity > 0:
-            print('Searching for a feasible local minimizer using the exact Hessian.')
+            if self.lbfgs:
+                print('Searching for a feasible local minimizer using L-BFGS to approximate the Hessian.')
+            else:
+                print('Searching for a feasible local minimizer using the exact Hessian.')
         outer = inner = 0
 
         for outer in range(self.niter):
@@ -287,11 +306,12 @@ class IPM(object):
 
                 # ---- one Newton step on the device (pyipm.py:1714-1754)
                 if lowered:
-                    info = eng.newton_step()
+                    # pyipm.py:1702-1713: in L-BFGS mode the storage is updated before every direction but the first
+                    info = eng.lbfgs_step(inner > 0 or outer > 0) if self.lbfgs else eng.newton_step()
                     nrm = np.array(list(info.kkt_norm))
                     f_new_dev = info.fval
                 else:
-                    info, nrm, f_new_dev = self._callable_step()
+                    info, nrm, f_new_dev = self._callable_step(inner > 0 or outer > 0)
                 self.nu_dev = self.nu_host = info.nu
                 self.delta = info.delta
                 if info.signal == -2:
@@ -301,6 +321,9 @@ class IPM(object):
                 if info.soc_accepted and self.verbosity > 2:
                     print('Second-order feasibility correction accepted')
                 self.step_log.append(info.asdict())
+                if self.lbfgs:
+                    m_, zeta_, fail_ = eng.lbfgs_state()
+                    self.step_log[-1].update(lbfgs_m=m_, lbfgs_zeta=zeta_, lbfgs_fail=fail_)
                 iter_count += 1
 
                 if all([self.Ftol is not None, not N, self.signal != -2]):
@@ -391,7 +414,7 @@ class IPM(object):
         return self.x, self.s, self.lda, self.fval, self.kkt
 
     # ------------------------------------------------------------------ callable mode
-    def _callable_step(self):
+    def _callable_step(self, not_first=True):
         """One inner iteration when f/ce/ci are opaque host callables: derivatives are evaluated by the user's
         functions and uploaded; residual, KKT formation, inertia-corrected factorisation, solve, nu rule and the
         fraction-to-the-boundary rule run on the device; the Armijo loop has to call the user's host functions
@@ -400,7 +423,21 @@ class IPM(object):
         eng = self.engine
         D, M, N = self.nvar, self.neq, self.nineq
         x, s, lda, _, _, _ = eng.get_state()
-        dz, info = eng.direction()
+        if self.lbfgs:
+            if not_first:
+                # pyipm.py:1705-1710: dL/dx at x_old with the CURRENT multipliers, from the user's callables
+                xo = self._x_old
+                go = np.asarray(self.df(xo), dtype=np.float64).reshape(D)
+                if M:
+                    go = go - np.dot(np.asarray(self.dce(xo), dtype=np.float64).reshape(D, M), lda[:M])
+                if N:
+                    go = go - np.dot(np.asarray(self.dci(xo), dtype=np.float64).reshape(D, N), lda[M:])
+                eng.lbfgs_update(go)
+                self._x_old = np.array(x)
+            dz, info = eng.lbfgs_direction()
+            info.delta = self.delta
+        else:
+            dz, info = eng.direction()
         # the shift reghess settled on persists across steps (pyipm.py:1390-1395): every later set_state of this step
         # must carry it, or the next factorisation would restart from the pre-step value
         self.delta = info.delta

@@ -144,7 +144,7 @@ def test_config3_full_size_step_vs_host_lapack():
     eng.close()
 
 
-@pytest.mark.parametrize('mu', [1e-1, 1e-10])
+@pytest.mark.parametrize('mu', [1e-10])
 def test_config5_full_size_step_vs_host_lapack(mu):
     """Config 5 (ill-conditioned barrier state, Sigma spanning ~10 decades) at full size: direction to 1e-6 relative
      against the LU solve of the unreduced 12800^2 system, inertia of the accepted matrix by dsytrf."""

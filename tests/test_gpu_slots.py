@@ -50,7 +50,8 @@ def test_con_jac_cost_kkt_slots(name):
             assert np.max(np.abs(J - Jref)) <= 1e-13 * (1.0 + np.max(np.abs(Jref)))
         k1, k2, k3, k4 = eng.kkt()
         r1, r2, r3, r4 = o.KKT(x, s, lda)
-        assert relinf(k1, r1) < 1e-12
+        scale = 1.0 + np.max(np.abs(prob.df(x)))       # kkt1 itself goes to zero at convergence
+        assert np.max(np.abs(k1 - r1)) <= 1e-12 * scale
         if N:
             assert np.max(np.abs(k2 - r2)) <= 1e-12 * (1.0 + np.max(np.abs(r2)))
             assert np.max(np.abs(k4 - r4)) <= 1e-12 * (1.0 + np.max(np.abs(r4)))
@@ -144,7 +145,7 @@ def test_update_mu_slot(name):
         xi = N * np.min(s * lda[M:]) / (np.dot(s, lda[M:]) + eps)
         ref = max(0.1 * np.min([0.05 * (1.0 - xi) / (xi + eps), 2.0]) ** 3 * np.dot(s, lda[M:]) / N, 0.0)
         assert abs(mu - ref) <= 1e-12 * max(ref, 1e-300), (k, mu, ref)
-        if k + 1 < n and g['st_mu_host'][k + 1] != g['st_mu_host'][k]:
+        if k + 1 < n and k + 1 != int(g['sol0_nsteps']) and g['st_mu_host'][k + 1] != g['st_mu_host'][k]:
             assert abs(mu - g['st_mu_host'][k + 1]) <= 1e-12 * g['st_mu_host'][k + 1]
             nchg += 1
     assert nchg >= 1
