@@ -540,8 +540,11 @@ def run_b200(args):
                 t_sample = float(np.median(ts))
             line['cpu_baseline'] = {
                 'value': 1.0 / (t_sample * scale), 'unit': 'steps/s', 'cores': os.cpu_count(), 'kind': 'port',
-                'sample': 'oracle Newton step on the same NLP family at n=1024 (K=%d): median of 3 = %.2f s (%d eigvalsh + '
-                          '1 LU each), scaled to config 3 by (K3/K)^3 = %.0f' % (K, t_sample, o.last_reg['n_eig'], scale),
+                'same_config': False, 'scaled_from_n': sprob.nvar, 'scale_factor': scale,
+                'sample': 'BOUNDED SAMPLE, extrapolated: oracle Newton step on the same NLP family at n=1024 (K=%d): median of 3 '
+                          '= %.2f s (%d eigvalsh + 1 LU each), scaled to config 3 by (K3/K)^3 = %.0f.  The same-configuration '
+                          'measurement is `bench.py --impl reference` (one real config-3 step, ~2 min on 16 cores; '
+                          'profiles/r2_bench_reference.json)' % (K, t_sample, o.last_reg['n_eig'], scale),
                 'split_s': {k: v for k, v in o.timers.items() if k != 'steps'}}
         print(json.dumps(line))
     if world > 1:
