@@ -388,6 +388,9 @@ def run_b200(args):
                 'factorisations_reference_equivalent': [int(i.n_factor) for i in tinfo],
                 'factorisations_physical': [int(i.n_factor_phys) for i in tinfo],
                 'n_backtracks': [int(i.n_backtracks) for i in tinfo],
+                'soc_tried': [int(i.soc_tried) for i in tinfo], 'cert_used': [int(i.cert_used) for i in tinfo],
+                'phase_ms': {k: [round(float(getattr(i, k)), 3) for i in tinfo] for k in
+                             ('ms_eval', 'ms_assemble', 'ms_factor', 'ms_solve', 'ms_search')},
                 'kkt_norm_last': [float(v) for v in tinfo[-1].kkt_norm],
                 'note': 'niter=1-style inner iterations from x0 at fixed mu = 0.2 (no barrier update), step 1 discovers delta '
                         '(10 inertia tests), later steps speculate; ms from CUDA events inside b200ipm_newton_step'}

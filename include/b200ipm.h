@@ -49,6 +49,8 @@ typedef struct b200ipm_params {
 #define B200IPM_FLAG_NO_CERT        64  /* never replace the delta = 0 inertia test by a negative-curvature certificate
                                            (then the test itself runs in the background) */
 #define B200IPM_FLAG_NO_ABANDON     16  /* always complete a failed inertia test (n_neg_first is then the full count) */
+#define B200IPM_FLAG_SLOW_STEP      256 /* b200ipm_newton_step never takes the one-sync path (every decision read back when it
+                                           is taken, as b200ipm_direction does): A/B knob, identical results */
 #define B200IPM_FLAG_TCGEN05_SYRK   2   /* d2L and condensation contractions on tcgen05 (int8 error-free split) */
 #define B200IPM_FLAG_TCGEN05_TILE(v) ((v) << 2)   /* with TCGEN05_SYRK: 0 = 128x64 tiles / 1 pass, 1 = 128x128 / 2, 2 = 128x256 / 4 */
 
@@ -177,6 +179,19 @@ int b200ipm_lbfgs_direction(b200ipm_handle h, double* dz, b200ipm_step_info* inf
  * line search + KKT at the new point.  do_update = (inner > 0 or outer > 0), pyipm.py:1705. */
 int b200ipm_lbfgs_step(b200ipm_handle h, int do_update, b200ipm_step_info* info);
 int b200ipm_lbfgs_state(b200ipm_handle h, int* m, double* zeta, int* fail);
+
+/* ---- batched multi-start solves of SMALL problems (the reference's examples, pyipm.py:1920-2131) -----
+ * The whole IPM.solve() loop (pyipm.py:1567-1863, exact-Hessian mode) for `batch` starting points of ONE polynomial
+ * problem (same descriptor as b200ipm_bind_poly), one warp per instance, one launch for the whole batch; K = D + 2N + M
+ * <= 32.  At this size the reference is followed literally: full K x K KKT matrix, reghess on its eigenvalues (cyclic
+ * Jacobi), LU with partial pivoting.  x0 is batch x D (host); outputs (host, any of s/lda/fval/kkt_norm/signal/iters/ms may
+ * be NULL): x batch x D, s batch x N, lda batch x (M+N), fval batch, kkt_norm batch x 4, signal batch (pyipm.py:1656
+ * codes: 1 Ktol, 2 Ftol, -1 max iterations, -2 bad direction), iters batch (total Newton steps), ms = kernel time. */
+int b200ipm_batch_solve_poly(int D, int M, int N, int nterms, const int* term_row, const double* term_coeff,
+                             const int* term_ptr, const int* fac_var, const int* fac_pow, double xlogx_coeff,
+                             double xlogx_shift, const b200ipm_params* p, int niter, int miter, int use_ftol, double Ftol,
+                             int batch, const double* x0, int device, double* x, double* s, double* lda, double* fval,
+                             double* kkt_norm, int* signal, int* iters, float* ms);
 
 /* ---- generic dense symmetric-indefinite factor/solve (sym_solve_cmp slot, pyipm.py:911-914; config 4) -- */
 /* A is n x n (leading dimension lda) symmetric, lower triangle referenced; factored in a private copy. */

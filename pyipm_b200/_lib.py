@@ -64,7 +64,7 @@ SYMBOLS = [
     'b200ipm_ldlt_create', 'b200ipm_ldlt_destroy', 'b200ipm_ldlt_factor', 'b200ipm_ldlt_solve',
     'b200ipm_ldlt_tile_factor', 'b200ipm_ldlt_panel', 'b200ipm_ldlt_import', 'b200ipm_gemm_nt_update', 'b200ipm_gemm_nt_update_bc', 'b200ipm_test_syrk', 'b200ipm_test_syrk_i8', 'b200ipm_trace_start', 'b200ipm_trace_dump',
     'b200ipm_test_gemv', 'b200ipm_lbfgs_init', 'b200ipm_lbfgs_update', 'b200ipm_lbfgs_direction', 'b200ipm_lbfgs_step',
-    'b200ipm_lbfgs_state',
+    'b200ipm_lbfgs_state', 'b200ipm_batch_solve_poly',
 ]
 
 _lib = None
@@ -135,6 +135,8 @@ def load():
         'b200ipm_lbfgs_direction': (i, [vp, vp, C.POINTER(StepInfo)]),
         'b200ipm_lbfgs_step': (i, [vp, i, C.POINTER(StepInfo)]),
         'b200ipm_lbfgs_state': (i, [vp, ip, dp, ip]),
+        'b200ipm_batch_solve_poly': (i, [i, i, i, i, ip, dp, ip, ip, ip, d, d, C.POINTER(Params), i, i, i, d, i, vp, i, vp, vp, vp,
+                                     vp, vp, vp, vp, C.POINTER(C.c_float)]),
         'b200ipm_trace_start': (i, []),
         'b200ipm_trace_dump': (i, [vp, vp, vp, vp, vp, i, ip]),
     }

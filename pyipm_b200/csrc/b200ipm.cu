@@ -14,6 +14,7 @@
 #include "ldlt.cuh"
 #include "ozaki_i8.cuh"
 #include "engine_kernels.cuh"
+#include "batch.cuh"
 
 #include <vector>
 #include <algorithm>
@@ -47,6 +48,8 @@ struct b200ipm_engine {
     double reg_cur = 0, delta_eff = 0;
     bool strict_retry = false;
     int n_strict = 0;        // number of strict re-factorisations triggered by a poor residual
+    int n_fast_ok = 0, n_fast_miss = 0;   // one-sync steps taken / abandoned for the sequential path
+    int* h_fi = nullptr;     // pinned: control block + error word of the one-sync step
     int n_phys = 0;          // factorisations physically executed in the current step (info->n_factor_phys)
     LdltWs F;               // condensed KKT factorisation (order Kc)
     OzWs oz;                // tcgen05 int8 slices (B200IPM_FLAG_TCGEN05_SYRK)
@@ -622,7 +625,12 @@ static int solve_direction(Eng* h, b200ipm_step_info* info) {
     }
     // safety net for the relaxed pivot threshold: a poor refined residual triggers ONE strict (Bunch-Kaufman
     // threshold) re-factorisation of the same matrix and a fresh solve
+    CU(cudaMemcpyAsync(h->h_fi + 9, h->F.serr, sizeof(int), cudaMemcpyDeviceToHost, h->st));
     RET(fetch_red(h, h->red + 8, 1));
+    if (h->h_fi[9]) {
+        CU(cudaMemsetAsync(h->F.serr, 0, sizeof(int), h->st));
+        return fail_msg("triangular solve: a block result never arrived (device poll timed out); the direction is not usable");
+    }
     if (!(h->h_red[0] <= 1e-7 * std::max(1.0, bnorm)) && h->F.pivot_u < 0.64 && !h->strict_retry) {
         if (h->pendingA && h->stB) CU(cudaStreamSynchronize(h->stB));   // the certificate solve reads this factorisation
         const double u_save = h->F.pivot_u;
@@ -662,21 +670,25 @@ static int merit_pieces_at(Eng* h, const double* xt, const double* st) {
     return 0;
 }
 // trials alpha0 * tau^(k0 + k), k = 0..nb-1 along the current dz -> h->trial (3 per trial), copied to host
-static int merit_trials(Eng* h, double alpha0, int k0, int nb, std::vector<double>& out) {
+static int merit_trials_launch(Eng* h, double alpha0, int k0, int nb, const double* alpha_dev) {
     const int D = h->D, M = h->M, N = h->N;
     if (h->kind == KIND_POLY) {
         if (sizeof(double) * (D + N) > 40 * 1024) return fail_msg("polynomial lowering supports D + N <= 5120");
         poly_trial_kernel<<<nb, 256, sizeof(double) * (D + N), h->st>>>(D, M, N, h->poly, h->x, h->s, h->dz, h->dz + D,
-                                                                         alpha0, h->p.tau, k0, h->trial);
+                                                                         alpha0, h->p.tau, k0, h->trial, alpha_dev);
         LAUNCHED();
     } else if (h->kind == KIND_QUAD) {
         QuadImages im{h->qx, h->ax, h->ux, h->gx, h->vx, h->qd, h->ad, h->ud, h->gd, h->vd};
         quad_trial_kernel<<<nb, 256, 0, h->st>>>(D, M, N, quad_data(h), im, h->x, h->s, h->dz, h->dz + D, alpha0, h->p.tau,
-                                                 k0, h->trial);
+                                                 k0, h->trial, alpha_dev);
         LAUNCHED();
     } else {
         return fail_msg("line search needs a lowered problem (quad / poly)");
     }
+    return 0;
+}
+static int merit_trials(Eng* h, double alpha0, int k0, int nb, std::vector<double>& out) {
+    RET(merit_trials_launch(h, alpha0, k0, nb, nullptr));
     out.resize((size_t)3 * nb);
     CU(cudaMemcpyAsync(out.data(), h->trial, sizeof(double) * 3 * nb, cudaMemcpyDeviceToHost, h->st));
     CU(cudaStreamSynchronize(h->st));
@@ -774,7 +786,8 @@ static int soc_direction(Eng* h, const double* cnew /* device, M+N */, double* p
 
 // ------------------------------------------------------------------------------------------ line search
 // search() (pyipm.py:1438-1565).  Scalars and branch decisions on the host, every vector operation on the device.
-static int line_search(Eng* h, b200ipm_step_info* info, const double* stats /* host dir stats */) {
+static int line_search(Eng* h, b200ipm_step_info* info, const double* stats /* host dir stats */,
+                       const double* first_trial = nullptr /* host: the trial at alpha_smax, already evaluated */) {
     const int D = h->D, M = h->M, N = h->N;
     const double eta = h->p.eta, tau = h->p.tau, eps = h->p.eps;
     const bool con = (M + N) > 0;
@@ -798,7 +811,7 @@ static int line_search(Eng* h, b200ipm_step_info* info, const double* stats /* h
     info->alpha_corr = 0.0;
     info->signal = 0;
 
-    if (h->kind == KIND_QUAD) RET(quad_images(h, h->dz, h->qd, h->ad, h->ud, h->gd, h->vd));
+    if (h->kind == KIND_QUAD && !first_trial) RET(quad_images(h, h->dz, h->qd, h->ad, h->ud, h->gd, h->vd));
     auto phi_of = [&](const double* t) {
         double v = t[0];
         if (con) v += h->nu * t[1];
@@ -806,7 +819,8 @@ static int line_search(Eng* h, b200ipm_step_info* info, const double* stats /* h
         return v;
     };
     std::vector<double> tr;
-    RET(merit_trials(h, a_s, 0, 1, tr));
+    if (first_trial) tr.assign(first_trial, first_trial + 3);
+    else RET(merit_trials(h, a_s, 0, 1, tr));
     bool correction = false;
     double alpha_corr = 0.0;
     if (phi_of(tr.data()) > phi0 + a_s * eta * dphi0) {
@@ -1325,6 +1339,8 @@ int b200ipm_create(int D, int M, int N, const b200ipm_params* p, int device, voi
     RET(dalloc(&h->qx, D)); RET(dalloc(&h->ax, M)); RET(dalloc(&h->ux, M)); RET(dalloc(&h->gx, N)); RET(dalloc(&h->vx, N));
     RET(dalloc(&h->qd, D)); RET(dalloc(&h->ad, M)); RET(dalloc(&h->ud, M)); RET(dalloc(&h->gd, N)); RET(dalloc(&h->vd, N));
     CU(cudaMallocHost(&h->h_red, sizeof(double) * 64));
+    CU(cudaMallocHost(&h->h_fi, sizeof(int) * 16));
+    memset(h->h_fi, 0, sizeof(int) * 16);
     RET(ldlt_alloc(h->F, h->Kc, h->st));
     CU(cudaStreamSynchronize(h->st));
     *out = h;
@@ -1345,6 +1361,7 @@ int b200ipm_destroy(b200ipm_handle h) {
                       h->lb_q, h->lb_dots, h->lb_coef}) cudaFree(b);
     cudaFree(h->p_rowptr); cudaFree(h->p_ptr); cudaFree(h->p_fvar); cudaFree(h->p_fpow); cudaFree(h->d_sig);
     cudaFreeHost(h->h_red);
+    if (h->h_fi) cudaFreeHost(h->h_fi);
     if (h->stB) cudaStreamSynchronize(h->stB);
     if (h->cert_ready) {
         ldlt_solvebuf_free(h->csb);
@@ -1790,19 +1807,153 @@ int b200ipm_step_max(b200ipm_handle h, double* alpha_smax, double* alpha_lmax) {
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------ one-sync step
+// The common step of a nonconvex solve (delta > 0 on entry, the previous delta = 0 test failed, certificate enabled) takes
+// the same decisions every time: the candidate delta / 2 passes, one refinement sweep brings the unreduced residual to
+// rounding level, the failure of the delta = 0 test is proven.  fast_step() therefore ISSUES that whole sequence --
+// factorisation, certificate solves, solve, one refinement sweep, direction statistics, the merit trial at the step
+// limit -- without waiting for any of its own decisions, reads every scalar back ONCE, and only then checks them.  Any
+// check that fails (wrong inertia, singular candidate, poor residual, no proof, tcgen05 error word) falls back to the
+// sequential code path from the untouched state: the decisions are those of compute_direction() in every case.
+// returns 1 = done (info filled, stats / trial valid), 0 = not applicable or a check failed (caller runs the slow path)
+static int fast_step(Eng* h, b200ipm_step_info* info, double* stats, double* trial, int* done) {
+    *done = 0;
+    const int M = h->M, K = h->K;
+    const bool lowered = (h->kind == KIND_QUAD || h->kind == KIND_POLY);
+    const bool spec = (h->delta > 0.0) && !(h->p.flags & (B200IPM_FLAG_NO_SPECULATION | B200IPM_FLAG_NO_CERT | B200IPM_FLAG_SLOW_STEP)) &&
+                      !h->strict_retry && h->first_failed_last && lowered && h->p.nrefine >= 1;
+    if (!spec) return 0;
+    h->n_phys = 0;
+    RET(residual(h));
+    h->oz_off = false;
+    h->oz_used = false;
+    const double delta_in = h->delta;
+    RET(eval_hessian(h));
+    CU(cudaEventRecord(h->ev[EV_EVAL], h->st));
+    RET(condense(h));
+    CU(cudaEventRecord(h->ev[EV_ASSEMBLE], h->st));
+    const int limit = (h->p.flags & B200IPM_FLAG_NO_ABANDON) ? 0x7fffffff : M;
+    const double delta1 = std::max(h->delta / 2.0, h->p.reg_coef);
+    RET(ldlt_set_neg_limit(h->F, limit));
+    RET(build_kc(h, delta1, 0.0));
+    RET(ldlt_factor(h->F));
+    h->n_phys++;
+    CU(cudaMemcpyAsync(h->h_fi, h->F.counts, sizeof(int) * 8, cudaMemcpyDeviceToHost, h->st));
+    CU(cudaMemcpyAsync(h->h_red + 32, h->F.dstat, sizeof(double) * 2, cudaMemcpyDeviceToHost, h->st));
+    h->h_fi[8] = 0;
+    if (h->oz_used) CU(cudaMemcpyAsync(h->h_fi + 8, h->oz.err, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    h->delta = delta1;
+    h->pendingA = true;
+    h->cert_pending = true;
+    h->pend_delta_in = delta_in;
+    RET(cert_launch(h));
+    CU(cudaEventRecord(h->ev[EV_FACTOR], h->st));
+    // solve + exactly one refinement sweep against the unreduced system
+    axpby_kernel<<<cdiv(K, 256), 256, 0, h->st>>>(K, -1.0, h->g, 0.0, nullptr, h->bvec);
+    LAUNCHED();
+    RET(condensed_solve(h, h->bvec, h->ycur));
+    RET(kkt_residual_vec(h, h->bvec, h->ycur, h->rho));
+    CU(cudaMemcpyAsync(h->red + 16, h->red + 8, sizeof(double), cudaMemcpyDeviceToDevice, h->st));
+    RET(condensed_solve(h, h->rho, h->ycor));
+    axpby_kernel<<<cdiv(K, 256), 256, 0, h->st>>>(K, 1.0, h->ycur, 1.0, h->ycor, h->ycur);
+    LAUNCHED();
+    RET(kkt_residual_vec(h, h->bvec, h->ycur, h->rho));
+    flip_kernel<<<cdiv(K, 256), 256, 0, h->st>>>(h->D, h->N, K, h->ycur, h->dz);
+    LAUNCHED();
+    CU(cudaEventRecord(h->ev[EV_SOLVE], h->st));
+    dir_stats_kernel<<<1, 1024, 0, h->st>>>(h->D, h->M, h->N, h->df, h->s, h->lam, h->dz, h->mu, h->p.eps, h->p.tau, h->red);
+    LAUNCHED();
+    if (h->kind == KIND_QUAD) RET(quad_images(h, h->dz, h->qd, h->ad, h->ud, h->gd, h->vd));
+    RET(merit_trials_launch(h, 1.0, 0, 1, h->N ? h->red + 6 : nullptr));
+    CU(cudaMemcpyAsync(h->h_red, h->red, sizeof(double) * 17, cudaMemcpyDeviceToHost, h->st));
+    CU(cudaMemcpyAsync(h->h_red + 20, h->trial, sizeof(double) * 3, cudaMemcpyDeviceToHost, h->st));
+    CU(cudaMemcpyAsync(h->h_fi + 9, h->F.serr, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    CU(cudaStreamSynchronize(h->st));                                            // <-- the one read-back
+    if (h->h_fi[9]) {
+        CU(cudaMemsetAsync(h->F.serr, 0, sizeof(int), h->st));
+        return fail_msg("triangular solve: a block result never arrived (device poll timed out); the direction is not usable");
+    }
+    // ---- checks, in the order the sequential path would have met them
+    auto bail = [&]() -> int {
+        if (h->stB) CU(cudaStreamSynchronize(h->stB));
+        h->pendingA = false;
+        h->cert_pending = false;
+        h->delta = delta_in;
+        h->n_fast_miss++;
+        return 0;
+    };
+    const int n_neg = h->h_fi[0], n_zero = h->h_fi[1];
+    const double dmin = h->h_red[32], dmax = h->h_red[33];
+    const double rcond = (n_zero > 0 || !(dmax > 0.0)) ? 0.0 : dmin / dmax;
+    if (h->h_fi[8]) {   // tcgen05 error word: the slow path redoes the contractions in fp64 DMMA
+        CU(cudaMemsetAsync(h->oz.err, 0, sizeof(int), h->st));
+        h->oz_off = true;
+        h->oz_used = false;
+        h->hess_valid = false;
+        RET(bail());
+        RET(eval_hessian(h));
+        return 0;
+    }
+    if (!(n_neg == M && !(rcond <= h->p.eps))) return bail();
+    double bnorm = 0.0;
+    for (int i = 0; i < 4; i++) bnorm = std::max(bnorm, h->last_red[i]);
+    const double tol = 1e-14 * std::max(1.0, bnorm);
+    double res = h->h_red[8];
+    bool extra = false;
+    for (int it = 1; !(res <= tol) && it < h->p.nrefine; it++) {      // rare: further sweeps, each read back
+        RET(condensed_solve(h, h->rho, h->ycor));
+        axpby_kernel<<<cdiv(K, 256), 256, 0, h->st>>>(K, 1.0, h->ycur, 1.0, h->ycor, h->ycur);
+        LAUNCHED();
+        RET(kkt_residual_vec(h, h->bvec, h->ycur, h->rho));
+        RET(fetch_red(h, h->red + 8, 1));
+        res = h->h_red[0];
+        extra = true;
+    }
+    if (!(res <= 1e-7 * std::max(1.0, bnorm))) return bail();         // the strict re-factorisation is the slow path's job
+    if (extra) {
+        flip_kernel<<<cdiv(K, 256), 256, 0, h->st>>>(h->D, h->N, K, h->ycur, h->dz);
+        LAUNCHED();
+        dir_stats_kernel<<<1, 1024, 0, h->st>>>(h->D, h->M, h->N, h->df, h->s, h->lam, h->dz, h->mu, h->p.eps, h->p.tau, h->red);
+        LAUNCHED();
+        if (h->kind == KIND_QUAD) RET(quad_images(h, h->dz, h->qd, h->ad, h->ud, h->gd, h->vd));
+        RET(merit_trials_launch(h, 1.0, 0, 1, h->N ? h->red + 6 : nullptr));
+        CU(cudaMemcpyAsync(h->h_red, h->red, sizeof(double) * 9, cudaMemcpyDeviceToHost, h->st));
+        CU(cudaMemcpyAsync(h->h_red + 20, h->trial, sizeof(double) * 3, cudaMemcpyDeviceToHost, h->st));
+        CU(cudaStreamSynchronize(h->st));
+    }
+    h->pend_rcondB = rcond;
+    info->n_neg = n_neg; info->n_zero = n_zero; info->n_factor = 2; info->eq_reg = 0; info->delta = h->delta;
+    info->n_spec = 1; info->spec_used = 1;
+    info->tc_syrk = h->oz_used ? 1 : 0;
+    bool redo = false, resolve_only = false;
+    RET(resolve_pending(h, info, &redo, &resolve_only));
+    if (redo || !info->cert_used) {
+        // no proof: resolve_pending has already run the delta = 0 test itself; if it confirmed the tentative choice nothing
+        // has to be redone, otherwise the sequential path decides
+        if (redo) { h->delta = delta_in; h->n_fast_miss++; return 0; }
+    }
+    info->n_factor_phys = h->n_phys;
+    for (int i = 0; i < 9; i++) stats[i] = h->h_red[i];
+    for (int i = 0; i < 3; i++) trial[i] = h->h_red[20 + i];
+    *done = 1;
+    h->n_fast_ok++;
+    return 0;
+}
+
 // nu rule (pyipm.py:1727-1735), step rules + line search (1737-1749), KKT at the new point (1754): everything of an inner
 // iteration after the search direction h->dz is known
-static int finish_step(Eng* h, b200ipm_step_info* info) {
+static int finish_step(Eng* h, b200ipm_step_info* info, const double* stats_in = nullptr, const double* first_trial = nullptr) {
     double stats[9];
-    RET(dir_stats(h, stats));
-    info->resid = h->h_red[8];       // ||b - K dz||_inf of the last refinement sweep (red[8], fetched with the stats)
+    if (stats_in) { for (int i = 0; i < 9; i++) stats[i] = stats_in[i]; }
+    else RET(dir_stats(h, stats));
+    info->resid = stats_in ? stats_in[8] : h->h_red[8];   // ||b - K dz||_inf of the last refinement sweep (red[8])
     info->con_l1 = h->last_red[4];
     if (h->C) {
         // merit parameter update (pyipm.py:1727-1735); IEEE semantics for ||con||_1 == 0 are the reference's
         const double nu_thres = stats[0] / (1.0 - h->p.rho) / h->last_red[4];
         if (h->nu < nu_thres) h->nu = nu_thres;
     }
-    RET(line_search(h, info, stats));
+    RET(line_search(h, info, stats, first_trial));
     CU(cudaEventRecord(h->ev[EV_SEARCH], h->st));
     // KKT conditions at the new point (pyipm.py:1754); doubles as the residual of the next step
     if (h->kind != KIND_CALLABLE) {
@@ -1821,6 +1972,12 @@ int b200ipm_newton_step(b200ipm_handle h, b200ipm_step_info* info) {
     CU(cudaSetDevice(h->device));
     memset(info, 0, sizeof(*info));
     CU(cudaEventRecord(h->ev[EV_START], h->st));
+    {
+        double stats[9], trial[3];
+        int done = 0;
+        RET(fast_step(h, info, stats, trial, &done));
+        if (done) return finish_step(h, info, stats, trial);
+    }
     RET(compute_direction(h, info));
     return finish_step(h, info);
 }
@@ -1872,6 +2029,69 @@ int b200ipm_lbfgs_state(b200ipm_handle h, int* m, double* zeta, int* fail) {
     if (m) *m = h->lb_m;
     if (zeta) *zeta = h->lb_zeta;
     if (fail) *fail = h->lb_fail;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ batched multi-start
+int b200ipm_batch_solve_poly(int D, int M, int N, int nterms, const int* term_row, const double* term_coeff,
+                             const int* term_ptr, const int* fac_var, const int* fac_pow, double xlogx_coeff,
+                             double xlogx_shift, const b200ipm_params* p, int niter, int miter, int use_ftol, double Ftol,
+                             int batch, const double* x0, int device, double* x, double* s, double* lda, double* fval,
+                             double* kkt_norm, int* signal, int* iters, float* ms) {
+    if (!p || !x0 || !x || batch <= 0 || D <= 0 || M < 0 || N < 0) return fail_msg("batch_solve_poly: bad arguments");
+    const int K = D + 2 * N + M, C = M + N;
+    if (K > BK_MAX) return fail_msg("batch_solve_poly: K = D + 2N + M must be <= 32 (one warp per instance)");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail_msg("b200ipm_batch_solve_poly: no CUDA device available (this library has no CPU fallback)");
+    CU(cudaSetDevice(device));
+    const int R = 1 + M + N;
+    std::vector<int> rowptr(R + 1, 0);
+    for (int t = 0; t < nterms; t++) {
+        if (term_row[t] < 0 || term_row[t] >= R) return fail_msg("batch_solve_poly: term_row out of range");
+        if (t > 0 && term_row[t] < term_row[t - 1]) return fail_msg("batch_solve_poly: terms must be sorted by row");
+        rowptr[term_row[t] + 1]++;
+    }
+    for (int r = 0; r < R; r++) rowptr[r + 1] += rowptr[r];
+    const int nfac = nterms ? term_ptr[nterms] : 0;
+    int *d_rowptr = nullptr, *d_ptr = nullptr, *d_fvar = nullptr, *d_fpow = nullptr, *d_sig = nullptr, *d_it = nullptr;
+    double *d_coeff = nullptr, *d_x0 = nullptr, *d_x = nullptr, *d_s = nullptr, *d_l = nullptr, *d_f = nullptr, *d_k = nullptr;
+    RET(dalloc(&d_rowptr, R + 1)); RET(dalloc(&d_ptr, nterms + 1)); RET(dalloc(&d_fvar, nfac)); RET(dalloc(&d_fpow, nfac));
+    RET(dalloc(&d_coeff, nterms));
+    RET(dalloc(&d_x0, (size_t)batch * D)); RET(dalloc(&d_x, (size_t)batch * D)); RET(dalloc(&d_s, (size_t)batch * N));
+    RET(dalloc(&d_l, (size_t)batch * C)); RET(dalloc(&d_f, batch)); RET(dalloc(&d_k, (size_t)batch * 4));
+    RET(dalloc(&d_sig, batch)); RET(dalloc(&d_it, batch));
+    std::vector<int> tp(nterms + 1, 0);
+    for (int t = 0; t <= nterms; t++) tp[t] = nterms ? term_ptr[t] : 0;
+    CU(cudaMemcpy(d_rowptr, rowptr.data(), sizeof(int) * (R + 1), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d_ptr, tp.data(), sizeof(int) * (nterms + 1), cudaMemcpyHostToDevice));
+    if (nfac) {
+        CU(cudaMemcpy(d_fvar, fac_var, sizeof(int) * nfac, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(d_fpow, fac_pow, sizeof(int) * nfac, cudaMemcpyHostToDevice));
+    }
+    if (nterms) CU(cudaMemcpy(d_coeff, term_coeff, sizeof(double) * nterms, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d_x0, x0, sizeof(double) * (size_t)batch * D, cudaMemcpyHostToDevice));
+    PolyData P{nterms, R, d_rowptr, d_coeff, d_ptr, d_fvar, d_fpow, xlogx_coeff, xlogx_shift};
+    BatchParams bp{p->mu, p->nu, p->rho, p->tau, p->eta, p->beta, p->Ktol, Ftol, p->eps, p->reg_coef, niter, miter, use_ftol};
+    CU(cudaFuncSetAttribute(batch_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BatchWs)));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    CU(cudaEventRecord(e0, nullptr));
+    batch_solve_kernel<<<batch, 32, sizeof(BatchWs), nullptr>>>(D, M, N, P, bp, batch, d_x0, d_x, d_s, d_l, d_f, d_k, d_sig, d_it);
+    LAUNCHED();
+    CU(cudaEventRecord(e1, nullptr));
+    CU(cudaEventSynchronize(e1));
+    if (ms) CU(cudaEventElapsedTime(ms, e0, e1));
+    CU(cudaMemcpy(x, d_x, sizeof(double) * (size_t)batch * D, cudaMemcpyDeviceToHost));
+    if (s && N) CU(cudaMemcpy(s, d_s, sizeof(double) * (size_t)batch * N, cudaMemcpyDeviceToHost));
+    if (lda && C) CU(cudaMemcpy(lda, d_l, sizeof(double) * (size_t)batch * C, cudaMemcpyDeviceToHost));
+    if (fval) CU(cudaMemcpy(fval, d_f, sizeof(double) * batch, cudaMemcpyDeviceToHost));
+    if (kkt_norm) CU(cudaMemcpy(kkt_norm, d_k, sizeof(double) * (size_t)batch * 4, cudaMemcpyDeviceToHost));
+    if (signal) CU(cudaMemcpy(signal, d_sig, sizeof(int) * batch, cudaMemcpyDeviceToHost));
+    if (iters) CU(cudaMemcpy(iters, d_it, sizeof(int) * batch, cudaMemcpyDeviceToHost));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d_rowptr); cudaFree(d_ptr); cudaFree(d_fvar); cudaFree(d_fpow); cudaFree(d_coeff); cudaFree(d_x0); cudaFree(d_x);
+    cudaFree(d_s); cudaFree(d_l); cudaFree(d_f); cudaFree(d_k); cudaFree(d_sig); cudaFree(d_it);
     return 0;
 }
 

@@ -73,9 +73,10 @@ struct QuadImages {
 __global__ void __launch_bounds__(256) quad_trial_kernel(int D, int M, int N, QuadData q, QuadImages im,
                                                          const double* __restrict__ x, const double* __restrict__ s,
                                                          const double* __restrict__ dx, const double* __restrict__ ds,
-                                                         double alpha0, double tau, int k0, double* __restrict__ out) {
+                                                         double alpha0, double tau, int k0, double* __restrict__ out,
+                                                         const double* __restrict__ alpha_dev = nullptr) {
     __shared__ double sh[33];
-    double alpha = alpha0;
+    double alpha = alpha_dev ? *alpha_dev : alpha0;      // alpha_dev: the step limit a kernel of the same stream just wrote
     for (int k = 0; k < k0 + (int)blockIdx.x; k++) alpha *= tau;
     double fa = 0.0, c1 = 0.0, ls = 0.0;
     for (int i = threadIdx.x; i < D; i += blockDim.x) {
@@ -251,12 +252,12 @@ __global__ void __launch_bounds__(256) poly_point_merit_kernel(int D, int M, int
 __global__ void __launch_bounds__(256) poly_trial_kernel(int D, int M, int N, PolyData P, const double* __restrict__ x,
                                                          const double* __restrict__ s, const double* __restrict__ dx,
                                                          const double* __restrict__ ds, double alpha0, double tau, int k0,
-                                                         double* __restrict__ out) {
+                                                         double* __restrict__ out, const double* __restrict__ alpha_dev = nullptr) {
     extern __shared__ double psm[];
     __shared__ double sh[33];
     double* xt = psm;
     double* st = psm + D;
-    double alpha = alpha0;
+    double alpha = alpha_dev ? *alpha_dev : alpha0;
     for (int k = 0; k < k0 + (int)blockIdx.x; k++) alpha *= tau;
     for (int i = threadIdx.x; i < D; i += blockDim.x) xt[i] = x[i] + alpha * dx[i];
     for (int j = threadIdx.x; j < N; j += blockDim.x) st[j] = s[j] + alpha * ds[j];

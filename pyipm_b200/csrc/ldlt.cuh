@@ -64,6 +64,7 @@ struct LdltWs {
     int graph_state = 0;           // 0 = not tried, 1 = usable, -1 = capture failed: direct launches
     int neg_limit = 0x7fffffff; // value last written to counts[5]
     int side_ctas = 0;         // > 0: the bulk trailing updates run as persistent kernels of at most this many CTAs
+    int* serr = nullptr;       // device error word of the solve kernels (bit 8: a poll timed out)
     double pivot_u = 0.01;     // threshold of the fast (unpivoted) tile attempt: accept step j iff |d_j| >= u * max_i |T[i][j]|
 };
 
@@ -117,6 +118,8 @@ inline int ldlt_alloc(LdltWs& w, int n, cudaStream_t st, bool background = false
         CU(cudaMemcpy(w.counts, init, sizeof(init), cudaMemcpyHostToDevice));
     }
     CU(cudaMalloc(&w.dstat, sizeof(double) * 2));
+    CU(cudaMalloc(&w.serr, sizeof(int)));
+    CU(cudaMemset(w.serr, 0, sizeof(int)));
     CU(cudaMalloc(&w.flags, sizeof(unsigned) * 2 * w.nblk));
     CU(cudaMalloc(&w.ticket, sizeof(unsigned) * 2));
     CU(cudaMalloc(&w.yv, sizeof(double) * npad));
@@ -139,7 +142,7 @@ inline void ldlt_free(LdltWs& w) {
     if (w.cap) cudaStreamDestroy(w.cap);
     for (int i = 0; i < 2; i++) { if (w.ev_panel[i]) cudaEventDestroy(w.ev_panel[i]); if (w.ev_upd[i]) cudaEventDestroy(w.ev_upd[i]); }
     cudaFree(w.LinvP); cudaFree(w.dinfo); cudaFree(w.kind); cudaFree(w.counts);
-    cudaFree(w.dstat); cudaFree(w.flags); cudaFree(w.ticket); cudaFree(w.yv); cudaFree(w.zv); cudaFree(w.xv);
+    cudaFree(w.dstat); cudaFree(w.serr); cudaFree(w.flags); cudaFree(w.ticket); cudaFree(w.yv); cudaFree(w.zv); cudaFree(w.xv);
     w = LdltWs();
 }
 
@@ -1285,14 +1288,6 @@ __device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
 // Block results are published by VALUE: yv / xv are pre-filled with a NaN sentinel and a consumer polls the entries it
 // needs until they differ from it -- no flag, no fence, one L2 round trip less per step of the serial chain.
 constexpr unsigned long long SOLVE_SENTINEL = 0x7FF8B200DEADBEEFull;
-__device__ __forceinline__ double ld_poll_f64(const double* p) {
-    const long long t0 = clock64();
-    unsigned long long b;
-    do {
-        asm volatile("ld.volatile.global.u64 %0, [%1];\n" : "=l"(b) : "l"(p) : "memory");
-    } while (b == SOLVE_SENTINEL && clock64() - t0 < 200000000LL);   // bounded: never hang the device
-    return __longlong_as_double((long long)b);
-}
 __global__ void ldlt_fill_sentinel_kernel(double* a, double* b, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
@@ -1301,13 +1296,29 @@ __global__ void ldlt_fill_sentinel_kernel(double* a, double* b, int n) {
     }
 }
 
+// A poll that times out raises bit 8 of *err (the caller must then discard the solve) instead of silently passing the
+// sentinel on as data; publication / polling use relaxed gpu-scope accesses (morally strong: no tearing, no caching in L1).
+__device__ __forceinline__ double ld_poll_f64_err(const double* p, int* err) {
+    const long long t0 = clock64();
+    unsigned long long b;
+    do {
+        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];\n" : "=l"(b) : "l"(p) : "memory");
+        if (b != SOLVE_SENTINEL) return __longlong_as_double((long long)b);
+    } while (clock64() - t0 < 400000000LL);
+    if (err) atomicOr(err, 8);
+    return 0.0;
+}
+__device__ __forceinline__ void st_publish_f64(double* p, double v) {
+    asm volatile("st.relaxed.gpu.global.f64 [%0], %1;\n" ::"l"(p), "d"(v) : "memory");
+}
+
 // forward:  y_i = LinvP_i * (b_i - sum_{j<i} L_ij y_j),  z_i = D_i^-1 y_i
 __global__ void __launch_bounds__(256) ldlt_fwd_kernel(const double* __restrict__ A, int ld, int n, int nblk,
                                                        const double* __restrict__ LinvP, const double* __restrict__ dinv_a,
                                                        const double* __restrict__ dinv_b, const int* __restrict__ kind,
                                                        const double* __restrict__ b, double* yv, double* __restrict__ zv,
-                                                       unsigned* flags, unsigned epoch, unsigned* ticket) {
-    __shared__ double Ls[NB][NB];   // LinvP_i
+                                                       int* err, unsigned* ticket) {
+    __shared__ double Ls[NB][NB + 4];   // LinvP_i; row stride 68 + interleaved columns: conflict-free 64-bit reads
     __shared__ double accv[NB], ys[NB], ybuf[2][NB];
     __shared__ int s_i;
     const int tid = threadIdx.x;
@@ -1338,7 +1349,7 @@ __global__ void __launch_bounds__(256) ldlt_fwd_kernel(const double* __restrict_
             for (int c = 0; c < 16; c++) lv[c] = 0.0;
         }
         double* yb = ybuf[j & 1];
-        if (tid < NB) yb[tid] = ld_poll_f64(yv + (size_t)j * NB + tid);
+        if (tid < NB) yb[tid] = ld_poll_f64_err(yv + (size_t)j * NB + tid, err);
         __syncthreads();
 #pragma unroll
         for (int c = 0; c < 16; c++) part += lv[c] * yb[q * 16 + c];
@@ -1349,12 +1360,12 @@ __global__ void __launch_bounds__(256) ldlt_fwd_kernel(const double* __restrict_
     __syncthreads();
     double yp = 0.0;
 #pragma unroll
-    for (int c = 0; c < 16; c++) yp += Ls[r][q * 16 + c] * accv[q * 16 + c];
+    for (int c = 0; c < 16; c++) yp += Ls[r][4 * c + q] * accv[4 * c + q];
     yp += __shfl_xor_sync(0xffffffffu, yp, 1);
     yp += __shfl_xor_sync(0xffffffffu, yp, 2);
     if (q == 0) {
         ys[r] = yp;
-        yv[r0 + r] = rowok ? yp : 0.0;     // publication (padded rows too: consumers poll whole blocks)
+        st_publish_f64(yv + r0 + r, rowok ? yp : 0.0);     // publication (padded rows too: consumers poll whole blocks)
     }
     __syncthreads();
     if (q == 0 && rowok) {
@@ -1370,7 +1381,7 @@ __global__ void __launch_bounds__(256) ldlt_fwd_kernel(const double* __restrict_
 // backward:  x_i = LinvP_i^T * (z_i - sum_{j>i} L_ji^T x_j)
 __global__ void __launch_bounds__(256) ldlt_bwd_kernel(const double* __restrict__ A, int ld, int n, int nblk,
                                                        const double* __restrict__ LinvP, const double* __restrict__ zv,
-                                                       double* xv, unsigned* flags, unsigned epoch, unsigned* ticket) {
+                                                       double* xv, int* err, unsigned* ticket) {
     extern __shared__ __align__(16) double bsm[];
     double(*P)[NBP] = reinterpret_cast<double(*)[NBP]>(bsm);          // partial sums [row r][col c]
     double(*Ls)[NBP] = reinterpret_cast<double(*)[NBP]>(bsm + NB * NBP);
@@ -1405,25 +1416,31 @@ __global__ void __launch_bounds__(256) ldlt_bwd_kernel(const double* __restrict_
 #pragma unroll
             for (int c = 0; c < 16; c++) lv[c] = 0.0;
         }
-        const double xr = ld_poll_f64(xv + gr);      // published by the CTA of block row j (zeros in padded rows)
+        const double xr = ld_poll_f64_err(xv + gr, err);   // published by the CTA of block row j (zeros in padded rows)
 #pragma unroll
         for (int c = 0; c < 16; c++) pacc[c] += lv[c] * xr;
     }
 #pragma unroll
     for (int c = 0; c < 16; c++) P[r][q * 16 + c] = pacc[c];
     __syncthreads();
-    if (tid < NB) {
+    {   // column sums and x = LinvP^T tv with all 256 threads: column cc, four interleaved row chunks, shuffle-reduced
+        const int cc = tid >> 2, qq = tid & 3;
         double s = 0.0;
-        for (int rr = 0; rr < NB; rr++) s += P[rr][tid];
-        tv[tid] = ((c0 + tid) < n ? zv[c0 + tid] : 0.0) - s;
-    }
-    __syncthreads();
-    if (tid < NB) {
-        double s = 0.0;
-        for (int rr = 0; rr < NB; rr++) s += Ls[rr][tid] * tv[rr];
-        xv[c0 + tid] = (c0 + tid < n) ? s : 0.0;     // publication
+#pragma unroll
+        for (int k = 0; k < 16; k++) s += P[4 * k + qq][cc];
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        if (qq == 0) tv[cc] = ((c0 + cc) < n ? zv[c0 + cc] : 0.0) - s;
+        __syncthreads();
+        double xx = 0.0;
+#pragma unroll
+        for (int k = 0; k < 16; k++) xx = fma(Ls[4 * k + qq][cc], tv[4 * k + qq], xx);
+        xx += __shfl_xor_sync(0xffffffffu, xx, 1);
+        xx += __shfl_xor_sync(0xffffffffu, xx, 2);
+        if (qq == 0) st_publish_f64(xv + c0 + cc, (c0 + cc < n) ? xx : 0.0);     // publication
     }
 }
+
 
 inline int ldlt_init_solve_attrs() {
     CU(cudaFuncSetAttribute(ldlt_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM));
@@ -1466,11 +1483,9 @@ inline int ldlt_solve_on(LdltWs& w, cudaStream_t st, const LdltSolveBuf& sb, con
     CU(cudaMemsetAsync(sb.ticket, 0, sizeof(unsigned) * 2, st));
     ldlt_fill_sentinel_kernel<<<cdiv((int)npad, 256), 256, 0, st>>>(sb.yv, sb.xv, (int)npad);
     LAUNCHED();
-    ldlt_fwd_kernel<<<w.nblk, 256, 0, st>>>(w.A, w.ld, w.n, w.nblk, w.LinvP, ia, ib, w.kind, b, sb.yv, sb.zv, w.flags,
-                                            w.epoch, sb.ticket);
+    ldlt_fwd_kernel<<<w.nblk, 256, 0, st>>>(w.A, w.ld, w.n, w.nblk, w.LinvP, ia, ib, w.kind, b, sb.yv, sb.zv, w.serr, sb.ticket);
     LAUNCHED();
-    ldlt_bwd_kernel<<<w.nblk, 256, TILE_SMEM, st>>>(w.A, w.ld, w.n, w.nblk, w.LinvP, sb.zv, sb.xv, w.flags + w.nblk,
-                                                    w.epoch, sb.ticket + 1);
+    ldlt_bwd_kernel<<<w.nblk, 256, TILE_SMEM, st>>>(w.A, w.ld, w.n, w.nblk, w.LinvP, sb.zv, sb.xv, w.serr, sb.ticket + 1);
     LAUNCHED();
     CU(cudaMemcpyAsync(x, sb.xv, sizeof(double) * w.n, cudaMemcpyDeviceToDevice, st));
     return 0;
