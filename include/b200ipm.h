@@ -157,6 +157,11 @@ int b200ipm_init_lambda(b200ipm_handle h);
 /* barrier update, pyipm.py:1804-1814: returns the new mu (caller stores it via set_state/set_mu_host). */
 int b200ipm_update_mu(b200ipm_handle h, double* mu_new);
 
+/* Second-order feasibility correction, pyipm.py:1464-1489 / 1516-1536: dz_p = -lstsq(jaco(x)', c_new) at the current state
+ * (minimum-norm least squares on the device).  cnew: M+N doubles (host), pz: D+N doubles (host).  The lowered-problem
+ * line search calls the same routine internally; this entry point serves callable mode, where c_new comes from the
+ * user's functions. */
+int b200ipm_soc_direction(b200ipm_handle h, const double* cnew, double* pz);
 /* reghess + sym_solve_cmp, pyipm.py:1373-1406,1718-1725: condensed KKT formation, inertia-corrected LDL^T,
  * solve + refinement, multiplier sign flip.  dz (K, may be NULL) is in the reference ordering. */
 int b200ipm_direction(b200ipm_handle h, double* dz, b200ipm_step_info* info);

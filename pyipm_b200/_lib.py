@@ -64,7 +64,7 @@ SYMBOLS = [
     'b200ipm_ldlt_create', 'b200ipm_ldlt_destroy', 'b200ipm_ldlt_factor', 'b200ipm_ldlt_solve',
     'b200ipm_ldlt_tile_factor', 'b200ipm_ldlt_panel', 'b200ipm_ldlt_import', 'b200ipm_gemm_nt_update', 'b200ipm_gemm_nt_update_bc', 'b200ipm_test_syrk', 'b200ipm_test_syrk_i8', 'b200ipm_trace_start', 'b200ipm_trace_dump',
     'b200ipm_test_gemv', 'b200ipm_lbfgs_init', 'b200ipm_lbfgs_update', 'b200ipm_lbfgs_direction', 'b200ipm_lbfgs_step',
-    'b200ipm_lbfgs_state', 'b200ipm_batch_solve_poly',
+    'b200ipm_lbfgs_state', 'b200ipm_batch_solve_poly', 'b200ipm_soc_direction',
 ]
 
 _lib = None
@@ -137,6 +137,7 @@ def load():
         'b200ipm_lbfgs_state': (i, [vp, ip, dp, ip]),
         'b200ipm_batch_solve_poly': (i, [i, i, i, i, ip, dp, ip, ip, ip, d, d, C.POINTER(Params), i, i, i, d, i, vp, i, vp, vp, vp,
                                      vp, vp, vp, vp, C.POINTER(C.c_float)]),
+        'b200ipm_soc_direction': (i, [vp, vp, vp]),
         'b200ipm_trace_start': (i, []),
         'b200ipm_trace_dump': (i, [vp, vp, vp, vp, vp, i, ip]),
     }
@@ -228,6 +229,19 @@ class Engine(object):
     def set_derivs(self, fval, df, ce, ci, J, d2L):
         df, ce, ci, J, d2L = f64(df), f64(ce), f64(ci), f64(J), f64(d2L)
         check(self.lib.b200ipm_set_derivs(self.h, float(fval), ptr(df), ptr(ce), ptr(ci), ptr(J), ptr(d2L), 0))
+
+    def set_derivs_device(self, fval, df, ce, ci, J, d2L):
+        """Same, from torch CUDA tensors (float64, contiguous) on the engine's device: device-to-device copies, nothing
+        crosses PCIe (b200ipm_set_derivs with on_device = 1)."""
+        def dp(t):
+            return None if t is None else C.c_void_p(t.data_ptr())
+        check(self.lib.b200ipm_set_derivs(self.h, float(fval), dp(df), dp(ce), dp(ci), dp(J), dp(d2L), 1))
+
+    def soc_direction(self, cnew):
+        cnew = f64(cnew)
+        pz = np.empty(self.D + self.N)
+        check(self.lib.b200ipm_soc_direction(self.h, ptr(cnew), ptr(pz)))
+        return pz
 
     # ---- state
     def set_state(self, x=None, s=None, lda=None, mu=0.2, nu=10.0, delta=0.0):

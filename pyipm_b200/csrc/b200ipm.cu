@@ -11,8 +11,8 @@
 #include "common.cuh"
 #include "vec.cuh"
 #include "gemm_nt.cuh"
-#include "ldlt.cuh"
 #include "ozaki_i8.cuh"
+#include "ldlt.cuh"
 #include "engine_kernels.cuh"
 #include "batch.cuh"
 
@@ -382,14 +382,20 @@ static int cert_launch(Eng* h) {
 static int factor_once(Eng* h, double delta, double reg, int neg_limit, int* n_neg, int* n_zero, double* rcond,
                        int* abandoned) {
     RET(ldlt_set_neg_limit(h->F, neg_limit));
-    RET(build_kc(h, delta, reg));
-    RET(ldlt_factor(h->F));
-    h->n_phys++;
     int cnt[8];
     double ds[2];
-    CU(cudaMemcpyAsync(cnt, h->F.counts, sizeof(int) * 8, cudaMemcpyDeviceToHost, h->st));
-    CU(cudaMemcpyAsync(ds, h->F.dstat, sizeof(double) * 2, cudaMemcpyDeviceToHost, h->st));
-    CU(cudaStreamSynchronize(h->st));
+    for (int attempt = 0; attempt < 2; attempt++) {
+        RET(build_kc(h, delta, reg));
+        RET(ldlt_factor(h->F));
+        h->n_phys++;
+        CU(cudaMemcpyAsync(cnt, h->F.counts, sizeof(int) * 8, cudaMemcpyDeviceToHost, h->st));
+        CU(cudaMemcpyAsync(ds, h->F.dstat, sizeof(double) * 2, cudaMemcpyDeviceToHost, h->st));
+        CU(cudaStreamSynchronize(h->st));
+        if (!cnt[6] || !h->F.tc_update) break;
+        // the tcgen05 trailing updates met an operand they cannot represent (non-finite entry) or a pipeline timeout:
+        // this workspace goes back to the fp64 DMMA updates for good and the factorisation is redone
+        ldlt_disable_tc(h->F);
+    }
     *n_neg = cnt[0];
     *n_zero = cnt[1];
     *rcond = (cnt[1] > 0 || !(ds[1] > 0.0)) ? 0.0 : ds[0] / ds[1];
@@ -1980,6 +1986,20 @@ int b200ipm_newton_step(b200ipm_handle h, b200ipm_step_info* info) {
     }
     RET(compute_direction(h, info));
     return finish_step(h, info);
+}
+
+// second-order correction direction (pyipm.py:1468-1477, 1520-1529) at the CURRENT state: dz_p = -lstsq(jaco(x)', c_new).
+// Exposed for callable mode, where the host evaluates c_new = con(x0 + a dx, s0 + a ds) with the user's functions.
+int b200ipm_soc_direction(b200ipm_handle h, const double* cnew, double* pz) {
+    if (!h || !cnew || !pz) return fail_msg("null argument");
+    if (!h->C) return fail_msg("soc_direction: the problem has no constraints");
+    CU(cudaSetDevice(h->device));
+    RET(eval_derivs(h));
+    RET(up(h, h->cnew, cnew, h->C, 0));
+    RET(soc_direction(h, h->cnew, h->pvec));
+    RET(down(h, pz, h->pvec, h->D + h->N));
+    CU(cudaStreamSynchronize(h->st));
+    return 0;
 }
 
 // ------------------------------------------------------------------------------------------ L-BFGS ABI

@@ -21,6 +21,7 @@
 #include <algorithm>
 #include "common.cuh"
 #include "gemm_nt.cuh"
+#include "ozaki_i8.cuh"
 #include "vec.cuh"
 
 namespace b200 {
@@ -65,6 +66,9 @@ struct LdltWs {
     int neg_limit = 0x7fffffff; // value last written to counts[5]
     int side_ctas = 0;         // > 0: the bulk trailing updates run as persistent kernels of at most this many CTAs
     int* serr = nullptr;       // device error word of the solve kernels (bit 8: a poll timed out)
+    int tc_update = 0;         // bulk trailing updates on tcgen05 (error-free int8 split), B200IPM_LDLT_TC=0 restores DMMA
+    int tc_ctas = 96;          // CTAs per wave of the tcgen05 update (B200IPM_LDLT_TC_CTAS)
+    OzUpdWs tcu;
     double pivot_u = 0.01;     // threshold of the fast (unpivoted) tile attempt: accept step j iff |d_j| >= u * max_i |T[i][j]|
 };
 
@@ -120,6 +124,20 @@ inline int ldlt_alloc(LdltWs& w, int n, cudaStream_t st, bool background = false
     CU(cudaMalloc(&w.dstat, sizeof(double) * 2));
     CU(cudaMalloc(&w.serr, sizeof(int)));
     CU(cudaMemset(w.serr, 0, sizeof(int)));
+    {
+        // tcgen05 trailing updates pay off once the bulk piece (everything beyond the next three outer panels) exists
+        const char* e = getenv("B200IPM_LDLT_TC");
+        w.tc_update = (e ? atoi(e) : 1) && n >= 2048;
+        const char* c = getenv("B200IPM_LDLT_TC_CTAS");
+        if (c) w.tc_ctas = atoi(c);
+        if (w.tc_update) {
+            RET(oz_upd_alloc(w.tcu, n, 256));
+            for (int c0 = 0; c0 < n; c0 += 256) {
+                const int rows5 = n - std::min(c0 + 256, n) - 3 * 256;
+                if (rows5 >= 256) RET(oz_upd_tiles(w.tcu, rows5));
+            }
+        }
+    }
     CU(cudaMalloc(&w.flags, sizeof(unsigned) * 2 * w.nblk));
     CU(cudaMalloc(&w.ticket, sizeof(unsigned) * 2));
     CU(cudaMalloc(&w.yv, sizeof(double) * npad));
@@ -131,6 +149,7 @@ inline int ldlt_alloc(LdltWs& w, int n, cudaStream_t st, bool background = false
 }
 inline void ldlt_free(LdltWs& w) {
     cudaFree(w.A); cudaFree(w.Wp); cudaFree(w.Wp2); cudaFree(w.Wp3); cudaFree(w.Wp4);
+    oz_upd_free(w.tcu);
     if (w.urg) cudaStreamDestroy(w.urg);
     for (int i = 0; i < 2; i++) if (w.ev_urg[i]) cudaEventDestroy(w.ev_urg[i]);
     if (w.gexec) cudaGraphExecDestroy(w.gexec);
@@ -1071,6 +1090,7 @@ __global__ void __launch_bounds__(MINI_THREADS) ldlt_mini_kernel(double* __restr
 
 __global__ void ldlt_reset_kernel(int* counts, double* dstat, unsigned* ticket) {
     counts[0] = counts[1] = counts[2] = counts[3] = counts[4] = 0;
+    counts[6] = 0;      // error word of the tcgen05 trailing updates (1: non-finite operand, 4: pipeline timeout)
     dstat[0] = INFINITY;
     dstat[1] = 0.0;
     ticket[0] = ticket[1] = 0;
@@ -1103,6 +1123,7 @@ inline int ldlt_init_attrs() {
     CU(cudaFuncSetAttribute(ldlt_mini_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MINI_SMEM));
     CU(cudaFuncSetAttribute(gemm_nt_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM));
     CU(cudaFuncSetAttribute(gemm_nt_sub64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S_SMEM));
+    CU(cudaFuncSetAttribute(oz_syrk_kernel<64, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, OzShape<64, 6>::SMEM));
     return 0;
 }
 
@@ -1208,11 +1229,17 @@ inline int ldlt_factor_launch(LdltWs& w, cudaStream_t st) {
                 if (rows5 > 0) {
                     const int o4 = o3 + na3;
                     CU(cudaStreamWaitEvent(sd, w.ev_panel[p & 1], 0));
-                    GemmArgs u{};
-                    u.C = w.A + (size_t)o4 * ld + o4; u.ldc = ld; u.Cin = u.C; u.ldcin = ld; u.n = rows5; u.m = rows5;
-                    u.beta = 1.0; u.mode = GEMM_LOWER_ONLY; u.nterms = 1; u.ctrl = w.counts; u.max_ctas = w.side_ctas;
-                    u.t[0] = GemmTerm{Wpan + (size_t)(na + na2 + na3) * NBO, Lpan + (size_t)(na + na2 + na3) * ld, nullptr, NBO, ld, kw, -1.0};
-                    RET(gemm_nt(sd, u));
+                    if (w.tc_update && rows5 >= 256 && kw == NBO && na == NBO && na2 == NBO && na3 == NBO) {
+                        // the panel-update contraction on tcgen05 (int8 error-free split, 21 slice pairs, in place)
+                        RET(oz_update_lower(sd, w.A + (size_t)o4 * ld + o4, ld, rows5, Wpan + (size_t)(na + na2 + na3) * NBO, NBO,
+                                            Lpan + (size_t)(na + na2 + na3) * ld, ld, kw, w.tcu, w.counts + 6, w.counts, w.tc_ctas));
+                    } else {
+                        GemmArgs u{};
+                        u.C = w.A + (size_t)o4 * ld + o4; u.ldc = ld; u.Cin = u.C; u.ldcin = ld; u.n = rows5; u.m = rows5;
+                        u.beta = 1.0; u.mode = GEMM_LOWER_ONLY; u.nterms = 1; u.ctrl = w.counts; u.max_ctas = w.side_ctas;
+                        u.t[0] = GemmTerm{Wpan + (size_t)(na + na2 + na3) * NBO, Lpan + (size_t)(na + na2 + na3) * ld, nullptr, NBO, ld, kw, -1.0};
+                        RET(gemm_nt(sd, u));
+                    }
                     CU(cudaEventRecord(w.ev_upd[p & 1], sd));
                     r_now = true;
                     side_used = true;
@@ -1233,6 +1260,12 @@ inline int ldlt_factor_launch(LdltWs& w, cudaStream_t st) {
         CU(cudaStreamWaitEvent(st, w.ev_upd[0], 0));
     }
     return 0;
+}
+// back to fp64 DMMA trailing updates (the captured graph contains the tcgen05 launches: drop it)
+inline void ldlt_disable_tc(LdltWs& w) {
+    w.tc_update = 0;
+    if (w.gexec) { cudaGraphExecDestroy(w.gexec); w.gexec = nullptr; }
+    w.graph_state = 0;
 }
 // The ~230 short, mutually dependent launches of one factorisation are captured ONCE per workspace into a CUDA graph
 // (both streams; fork/join through the events) and replayed: the matrix lives in the same buffers every time, so

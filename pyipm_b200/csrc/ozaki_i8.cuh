@@ -50,10 +50,12 @@ struct OzSliceArgs {
     const double* sw;   // sw[koff + k] = copysign(sqrt|alpha w_k|, alpha w_k)   (oz_weight_kernel)
     int* rexp;
     int* err;           // err[0] |= 1: non-finite operand, |= 2: negative weight in a term announced as non-negative
+    const int* ctrl;    // optional LDL^T control block: ctrl[4] != 0 => the factorisation was abandoned, do nothing
 };
 
 // sw = signed square roots of the column weights, once per call (instead of once per row in the slicing kernel)
 __global__ void oz_weight_kernel(const OzSliceArgs a, double* sw) {
+    if (a.ctrl && a.ctrl[4]) return;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= a.nkb * OZ_KB) return;
     double v = 0.0;
@@ -77,6 +79,7 @@ __device__ __forceinline__ double oz_scaled(const OzTerm& T, const double* __res
 }
 // pass 1: one warp per row -> exponent e_i with |L[i, :]| * 2^-e_i < 1
 __global__ void __launch_bounds__(128) oz_rowmax_kernel(const OzSliceArgs a) {
+    if (a.ctrl && a.ctrl[4]) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int row = blockIdx.x * 4 + warp;
     if (row >= a.n) return;
@@ -102,6 +105,7 @@ __global__ void __launch_bounds__(128) oz_rowmax_kernel(const OzSliceArgs a) {
 // pass 2: CTA = (8-row group, k-range); thread = (row r of the group, 16-element k-chunk); 8 consecutive threads write
 // one 128-byte core matrix per slice
 __global__ void __launch_bounds__(256) oz_slice_kernel(const OzSliceArgs a) {
+    if (a.ctrl && a.ctrl[4]) return;
     const int tid = threadIdx.x;
     const int row0 = blockIdx.x * 8;
     const int r = tid & 7;
@@ -284,6 +288,12 @@ struct OzGemmArgs {
     uint32_t idesc;
     int kb_end[3];         // k-blocks [kb_end[t-1], kb_end[t]) belong to term t
     int sgn[3];            // the B side of a signed term's k-blocks comes from R (sign applied), otherwise from L
+    // general product C (+)= A B' with DISTINCT operands (LDL^T trailing update C -= W L'): the A side streams from L
+    // (slices of W, row exponents rexp), the B side from R (slices of -Lpanel, row exponents rexp_col); `lower`: only
+    // elements i >= j are authoritative, read from / written to the lower triangle in place, no mirror
+    const int* rexp_col;   // null: same as rexp
+    int lower;
+    const int* ctrl;       // optional LDL^T control block (ctrl[4] != 0: abandoned, return at once)
 };
 
 // BN = tile width (UMMA N), ND = number of slice-pair diagonals kept (p + q < ND, p, q < OZ_NS):
@@ -317,9 +327,11 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzGemmArgs
     __shared__ int s_dead;
     __shared__ double s_cscale[BN];   // 2^(e_j - 7) of the tile's columns
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (a.ctrl && *reinterpret_cast<const volatile int*>(a.ctrl + 4)) return;      // before any barrier / TMEM allocation
     const int2 tile = a.tiles[blockIdx.x];
     const int ti = tile.x, tj = tile.y;
     const int row0 = ti * OZ_BM, col0 = tj * BN;
+    const int* __restrict__ rexp_c = a.rexp_col ? a.rexp_col : a.rexp;
 
     if (tid == 0) {
         s_dead = 0;
@@ -331,7 +343,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzGemmArgs
         oz_mbar_init(oz_smem_u32(&bar_tempty), 4);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
-    for (int c = tid; c < BN; c += OZ_THREADS) s_cscale[c] = scalbn(1.0, ((col0 + c < a.n) ? a.rexp[col0 + c] : 0) - 7);
+    for (int c = tid; c < BN; c += OZ_THREADS) s_cscale[c] = scalbn(1.0, ((col0 + c < a.n) ? rexp_c[col0 + c] : 0) - 7);
     if (warp == 0) {
         const uint32_t ncols = 512;
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(oz_smem_u32(&s_tmem)), "r"(ncols)
@@ -444,7 +456,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzGemmArgs
 #pragma unroll
                 for (int c = 0; c < 8; c++) {
                     const int j = col0 + cb * 8 + c;
-                    const bool ok = rowok && j < a.n && i <= j;
+                    const bool ok = rowok && j < a.n && (a.lower ? i >= j : i <= j);
                     pre_p[c] = (ok && need_part) ? a.C[(size_t)i * a.ldc + j] : 0.0;
                     pre_c[c] = (ok && need_cin) ? a.Cin[(size_t)i * a.ldcin + j] : 0.0;
                 }
@@ -466,7 +478,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzGemmArgs
 #pragma unroll
                     for (int c = 0; c < 8; c++) {
                         const int j = col0 + cb * 8 + c;
-                        if (j >= a.n || i > j) continue;          // only the upper triangle is authoritative
+                        if (j >= a.n || (a.lower ? i < j : i > j)) continue;   // only one triangle is authoritative
                         double h = 0.0;
 #pragma unroll
                         for (int dd = MAXD - 1; dd >= 0; dd--)
@@ -477,7 +489,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzGemmArgs
                             v = fma(a.beta, cur_c[c], v);
                             if (i == j) v += dii;
                             *cp = v;
-                            if (i != j) a.C[(size_t)j * a.ldc + i] = v;
+                            if (i != j && !a.lower) a.C[(size_t)j * a.ldc + i] = v;
                         } else {
                             *cp = v;
                         }
@@ -629,6 +641,92 @@ inline int oz_syrk(cudaStream_t st, const GemmArgs& a, OzWs& w, unsigned may_be_
     else rc = oz_launch<128, 8>(st, g, w.ntiles);
     if (rc == 0 && w.ev[2]) CU(cudaEventRecord(w.ev[2], st));
     return rc;
+}
+
+
+// ------------------------------------------------------------------------------------------- LDL^T trailing update
+// C (n x n, lower triangle, in place) -= W * Lp'   with W, Lp n x K row-major (K <= 256): the panel-update contraction
+// inside the factorisation on tcgen05 (BASELINE north_star), through the same error-free int8 split -- W's rows and
+// Lp's rows are sliced separately (own row exponents), the B side streams the digits of -Lp, so 2x2 pivots (W != Lp D
+// column-wise) need no special case.  128 x 64 tiles, six slice-pair diagonals (21 pairs, ~4e-12 of the row-scale
+// products: the factor is a preconditioner + inertia test, every solve is refined against the unreduced system) in ONE
+// pass, which is what allows the in-place accumulation.  Everything is preallocated (oz_upd_alloc) so that the calls can
+// be captured into the factorisation's CUDA graph.
+struct OzUpdWs {
+    int nmax = 0, kmax = 0;
+    int8_t *LA = nullptr, *LB = nullptr, *RB = nullptr;   // digits of W, of Lp (unused by the kernel), of -Lp
+    int *rexpA = nullptr, *rexpB = nullptr;
+    double* sw = nullptr;
+    std::vector<int2*> tiles;      // per trailing order (index = n / OZ_BM)
+    std::vector<int> ntiles;
+};
+inline void oz_upd_free(OzUpdWs& w) {
+    cudaFree(w.LA); cudaFree(w.LB); cudaFree(w.RB); cudaFree(w.rexpA); cudaFree(w.rexpB); cudaFree(w.sw);
+    for (int2* t : w.tiles) cudaFree(t);
+    w = OzUpdWs();
+}
+inline int oz_upd_alloc(OzUpdWs& w, int nmax, int kmax) {
+    w.nmax = nmax; w.kmax = kmax;
+    const int nrb = cdiv(nmax, OZ_BM), nkb = cdiv(kmax, OZ_KB);
+    const size_t bytes = (size_t)nrb * nkb * OZ_NS * OZ_CHUNK;
+    CU(cudaMalloc(&w.LA, bytes)); CU(cudaMalloc(&w.LB, bytes)); CU(cudaMalloc(&w.RB, bytes));
+    CU(cudaMalloc(&w.rexpA, sizeof(int) * nrb * OZ_BM)); CU(cudaMalloc(&w.rexpB, sizeof(int) * nrb * OZ_BM));
+    CU(cudaMalloc(&w.sw, sizeof(double) * nkb * OZ_KB));
+    w.tiles.assign(nrb + 1, nullptr);
+    w.ntiles.assign(nrb + 1, 0);
+    return 0;
+}
+// tile list of a trailing matrix of order n (cached per n / 128; must be called OUTSIDE stream capture the first time)
+inline int oz_upd_tiles(OzUpdWs& w, int n) {
+    const int key = cdiv(n, OZ_BM);
+    if (key >= (int)w.tiles.size()) return fail_msg("oz_upd_tiles: order exceeds the workspace");
+    if (w.tiles[key]) return 0;
+    std::vector<int2> tl;
+    for (int ti = 0; ti * OZ_BM < n; ti++)
+        for (int tj = 0; tj * 64 < n && tj * 64 <= ti * OZ_BM + OZ_BM - 1; tj++) tl.push_back(make_int2(ti, tj));
+    CU(cudaMalloc(&w.tiles[key], sizeof(int2) * tl.size()));
+    CU(cudaMemcpy(w.tiles[key], tl.data(), sizeof(int2) * tl.size(), cudaMemcpyHostToDevice));
+    w.ntiles[key] = (int)tl.size();
+    return 0;
+}
+inline int oz_update_lower(cudaStream_t st, double* C, int ldc, int n, const double* W, int ldw, const double* Lp, int ldl,
+                           int K, OzUpdWs& w, int* err, const int* ctrl, int max_ctas) {
+    if (n > w.nmax || K > w.kmax) return fail_msg("oz_update_lower: workspace too small");
+    const int key = cdiv(n, OZ_BM);
+    if (!w.tiles[key]) return fail_msg("oz_update_lower: tile list not prepared (oz_upd_tiles)");
+    const int nkb = cdiv(K, OZ_KB), nrb = cdiv(n, OZ_BM);
+    for (int side = 0; side < 2; side++) {
+        OzSliceArgs s{};
+        const double* A = side ? Lp : W;
+        const int lda = side ? ldl : ldw;
+        const int vec = (!(lda & 1) && !(reinterpret_cast<uintptr_t>(A) & 15)) ? 1 : 0;
+        s.t[0] = OzTerm{A, nullptr, lda, K, 0, side, vec, side ? -1.0 : 1.0};
+        s.nterms = 1; s.n = n; s.nkb = nkb;
+        s.L = side ? w.LB : w.LA; s.R = side ? w.RB : nullptr; s.sw = w.sw; s.rexp = side ? w.rexpB : w.rexpA;
+        s.err = err; s.ctrl = ctrl;
+        oz_weight_kernel<<<cdiv(nkb * OZ_KB, 256), 256, 0, st>>>(s, w.sw);
+        LAUNCHED();
+        oz_rowmax_kernel<<<cdiv(n, 4), 128, 0, st>>>(s);
+        LAUNCHED();
+        oz_slice_kernel<<<dim3(nrb * (OZ_BM / 8), 1), 256, 0, st>>>(s);
+        LAUNCHED();
+    }
+    OzGemmArgs g{};
+    g.L = w.LA; g.R = w.RB; g.rexp = w.rexpA; g.rexp_col = w.rexpB; g.tiles = w.tiles[key]; g.err = err;
+    g.C = C; g.Cin = C; g.dadd = nullptr; g.ldc = ldc; g.ldcin = ldc; g.n = n; g.nkb = nkb;
+    g.beta = 1.0; g.shift = 0.0; g.lower = 1; g.ctrl = ctrl;
+    g.desc_hi = oz_desc_hi(128, 256);
+    g.idesc = oz_idesc(64);
+    for (int t = 0; t < 3; t++) { g.kb_end[t] = 1 << 30; g.sgn[t] = 0; }
+    g.kb_end[0] = nkb; g.sgn[0] = 1;
+    // one CTA = one tile, ~200 KB of shared memory: a full-width launch would occupy every SM and the latency-critical
+    // chain kernels of the factorisation would wait for a slot, so the tile list goes out in waves of at most max_ctas
+    const int wave = max_ctas > 0 ? max_ctas : w.ntiles[key];
+    for (int off = 0; off < w.ntiles[key]; off += wave) {
+        g.tiles = w.tiles[key] + off;
+        RET((oz_launch<64, 6>(st, g, std::min(wave, w.ntiles[key] - off))));
+    }
+    return 0;
 }
 
 // int8 multiply-add operations one call issues on the tensor cores (slice pairs x computed tiles x K)

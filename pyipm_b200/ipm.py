@@ -28,7 +28,8 @@ class IPM(object):
     def __init__(self, x0=None, x_dev=None, f=None, df=None, d2f=None, ce=None, dce=None, d2ce=None, ci=None, dci=None,
                  d2ci=None, lda0=None, lambda_dev=None, s0=None, mu=0.2, nu=10.0, rho=0.1, tau=0.995, eta=1.0E-4,
                  beta=0.4, miter=20, niter=10, Xtol=None, Ktol=1.0E-4, Ftol=None, lbfgs=False, lbfgs_zeta=None,
-                 float_dtype=np.float64, verbosity=1, device=0, stream=None, nrefine=2, engine_flags=None):
+                 float_dtype=np.float64, verbosity=1, device=0, stream=None, nrefine=2, engine_flags=None,
+                 device_callables=False):
         # pyipm.py:316-376
         self.x0 = x0
         self.x_dev = x_dev            # ignored (no symbolic graph)
@@ -73,6 +74,9 @@ class IPM(object):
         self.delta0 = self.reg_coef
         self.compiled = False
         self.device, self.stream, self.nrefine = device, stream, nrefine
+        # device_callables: f/df/d2f/ce/... take and return torch CUDA float64 tensors on `device` (the reference's
+        # 'precompiled function' input mode, pyipm.py:216-231, without leaving the GPU: b200ipm_set_derivs(on_device = 1))
+        self.device_callables = bool(device_callables)
         self.engine_flags = engine_flags      # b200ipm_params.flags (None: _lib.DEFAULT_FLAGS; 0: fp64 DMMA contractions)
         self.engine = None
         self.delta = 0.0
@@ -114,11 +118,11 @@ class IPM(object):
             self.neq = neq
             self.nineq = nineq
             if self.ce is not None and self.neq is None:
-                self.neq = np.asarray(self.ce(self.x0)).size
+                self.neq = self._h(self.ce(self._arg(self.x0))).size
             elif neq is None:
                 self.neq = 0
             if self.ci is not None and self.nineq is None:
-                self.nineq = np.asarray(self.ci(self.x0)).size
+                self.nineq = self._h(self.ci(self._arg(self.x0))).size
             elif nineq is None:
                 self.nineq = 0
             need = ('df',) + (('dce',) if self.neq else ()) + (('dci',) if self.nineq else ())
@@ -147,6 +151,8 @@ class IPM(object):
 
     def _upload_derivs(self, x, lda):
         D, M, N = self.nvar, self.neq, self.nineq
+        if self.device_callables:
+            return self._upload_derivs_device(x, lda)
         fval = float(self.f(x))
         df = np.asarray(self.df(x), dtype=np.float64).reshape(D)
         W = None if self.lbfgs else np.array(self.d2f(x), dtype=np.float64).reshape(D, D)
@@ -164,6 +170,43 @@ class IPM(object):
                 W = W - np.asarray(self.d2ci(x, lda), dtype=np.float64).reshape(D, D)
         J = np.concatenate(blocks, axis=1) if blocks else None
         self.engine.set_derivs(fval, df, ce, ci, J, W)
+
+    # ---- torch-CUDA callables: nothing but scalars crosses PCIe
+    def _dev(self, a):
+        import torch
+        return torch.as_tensor(np.asarray(a, dtype=np.float64), device=torch.device('cuda', self.device))
+
+    def _upload_derivs_device(self, x, lda):
+        import torch
+        D, M, N = self.nvar, self.neq, self.nineq
+        xt, lt = self._dev(x), self._dev(lda)
+        fval = float(self.f(xt))
+        df = self.df(xt).reshape(D).contiguous()
+        W = None if self.lbfgs else self.d2f(xt).reshape(D, D)
+        ce = ci = None
+        blocks = []
+        if M:
+            ce = self.ce(xt).reshape(M).contiguous()
+            blocks.append(self.dce(xt).reshape(D, M))
+            if W is not None:
+                W = W - self.d2ce(xt, lt).reshape(D, D)
+        if N:
+            ci = self.ci(xt).reshape(N).contiguous()
+            blocks.append(self.dci(xt).reshape(D, N))
+            if W is not None:
+                W = W - self.d2ci(xt, lt).reshape(D, D)
+        J = torch.cat(blocks, dim=1).contiguous() if blocks else None
+        if W is not None:
+            W = W.contiguous()
+        torch.cuda.current_stream(self.device).synchronize()      # the engine copies on its own stream
+        self.engine.set_derivs_device(fval, df, ce, ci, J, W)
+
+    def _h(self, v):
+        """host NumPy view of a callable's result (torch CUDA tensor in device_callables mode)"""
+        return v.detach().cpu().numpy() if self.device_callables else np.asarray(v)
+
+    def _arg(self, x):
+        return self._dev(x) if self.device_callables else x
 
     # ------------------------------------------------------------------ operator slots (pyipm.py:855-954)
     def _at(self, x, s=None, lda=None):
@@ -247,7 +290,7 @@ class IPM(object):
             if lowered:
                 eng.init_slack()
             else:
-                s = np.maximum(np.asarray(self.ci(x), dtype=np.float64).reshape(N), self.Ktol)
+                s = np.maximum(self._h(self.ci(self._arg(x))).astype(np.float64).reshape(N), self.Ktol)
                 self._push(x, s, lda)
         if (M or N) and self.lda0 is None:
             eng.init_lambda()
@@ -418,8 +461,9 @@ class IPM(object):
         """One inner iteration when f/ce/ci are opaque host callables: derivatives are evaluated by the user's
         functions and uploaded; residual, KKT formation, inertia-corrected factorisation, solve, nu rule and the
         fraction-to-the-boundary rule run on the device; the Armijo loop has to call the user's host functions
-        for every trial point, so its scalar bookkeeping (pyipm.py:1457-1505) stays on the host.  The
-        second-order correction is not attempted in this mode."""
+        for every trial point, so its scalar bookkeeping (pyipm.py:1457-1505) stays on the host; the second-order
+        correction's least squares (pyipm.py:1468-1477, 1520-1529) is b200ipm_soc_direction on the device.  With
+        device_callables=True the user's functions take / return torch CUDA tensors and only scalars reach the host."""
         eng = self.engine
         D, M, N = self.nvar, self.neq, self.nineq
         x, s, lda, _, _, _ = eng.get_state()
@@ -427,11 +471,12 @@ class IPM(object):
             if not_first:
                 # pyipm.py:1705-1710: dL/dx at x_old with the CURRENT multipliers, from the user's callables
                 xo = self._x_old
-                go = np.asarray(self.df(xo), dtype=np.float64).reshape(D)
+                xa = self._arg(xo)
+                go = self._h(self.df(xa)).astype(np.float64).reshape(D)
                 if M:
-                    go = go - np.dot(np.asarray(self.dce(xo), dtype=np.float64).reshape(D, M), lda[:M])
+                    go = go - np.dot(self._h(self.dce(xa)).reshape(D, M), lda[:M])
                 if N:
-                    go = go - np.dot(np.asarray(self.dci(xo), dtype=np.float64).reshape(D, N), lda[M:])
+                    go = go - np.dot(self._h(self.dci(xa)).reshape(D, N), lda[M:])
                 eng.lbfgs_update(go)
                 self._x_old = np.array(x)
             dz, info = eng.lbfgs_direction()
@@ -442,12 +487,19 @@ class IPM(object):
         # must carry it, or the next factorisation would restart from the pre-step value
         self.delta = info.delta
         _, nrm0 = eng.residual(want_g=False)
-        con_l1 = 0.0
-        if M:
-            con_l1 += np.sum(np.abs(np.asarray(self.ce(x)).reshape(M)))
-        if N:
-            con_l1 += np.sum(np.abs(np.asarray(self.ci(x)).reshape(N) - s))
-        df = np.asarray(self.df(x), dtype=np.float64).reshape(D)
+
+        def con_vec(xx, ss):
+            """con(x, s) = [ce ; ci - s] (pyipm.py:564-579) through the user's functions"""
+            parts = []
+            xa = self._arg(xx)
+            if M:
+                parts.append(self._h(self.ce(xa)).reshape(M))
+            if N:
+                parts.append(self._h(self.ci(xa)).reshape(N) - ss)
+            return np.concatenate(parts) if parts else np.zeros(0)
+
+        con_l1 = float(np.sum(np.abs(con_vec(x, s))))
+        df = self._h(self.df(self._arg(x))).astype(np.float64).reshape(D)
         if M or N:
             bcg = np.concatenate([df, -self.mu_dev / (s + self.eps)]) if N else df
             nu_thres = np.dot(bcg, dz[:D + N]) / (1 - self.rho) / con_l1
@@ -460,17 +512,21 @@ class IPM(object):
         dx, ds, dl = dz[:D], dz[D:D + N], dz[D + N:]
 
         def phi(xx, ss):
-            v = float(self.f(xx))
-            c1 = 0.0
-            if M:
-                c1 += np.sum(np.abs(np.asarray(self.ce(xx)).reshape(M)))
-            if N:
-                c1 += np.sum(np.abs(np.asarray(self.ci(xx)).reshape(N) - ss))
+            v = float(self.f(self._arg(xx)))
             if M or N:
-                v += self.nu_dev * c1
+                v += self.nu_dev * np.sum(np.abs(con_vec(xx, ss)))
             if N:
                 v -= self.mu_dev * np.sum(np.log(ss))
             return v
+
+        def step_host(v, dv):
+            """closed form of step() (pyipm.py:1408-1436), as the device kernels compute it"""
+            thr = (1.0 - self.tau) * v
+            bad = ~(v + dv >= thr)
+            if not bad.any():
+                return 1.0
+            a = np.where(dv < 0.0, (v - thr) / np.where(dv < 0.0, -dv, 1.0), 0.0)
+            return float(min(np.min(a[bad]), 1.0))
 
         phi0 = phi(x, s)
         dphi0 = np.dot(df, dx)
@@ -479,27 +535,54 @@ class IPM(object):
         if N:
             dphi0 -= np.dot(self.mu_dev / (s + self.eps), ds)
         info.alpha_smax, info.alpha_lmax = a_s, a_l
+        info.phi0, info.dphi0 = phi0, dphi0
         nb = 0
+        correction = False
+        alpha_corr = 0.0
+        dz_p = None
         with np.errstate(all='ignore'):
             if phi(x + a_s * dx, s + a_s * ds) > phi0 + a_s * self.eta * dphi0:
-                a_s *= self.tau
-                a_l *= self.tau
-                nb = 1
-                while phi(x + a_s * dx, s + a_s * ds) > phi0 + a_s * self.eta * dphi0:
-                    nrm_step = (np.sqrt(np.linalg.norm(a_s * dx) ** 2 + np.linalg.norm(a_l * ds) ** 2) if N
-                                else np.linalg.norm(a_s * dx))
-                    if nrm_step < self.eps:
-                        info.signal = -2
-                        break
+                if M or N:
+                    # second-order correction (pyipm.py:1464-1489 / 1516-1536): least squares on the device
+                    c_new = con_vec(x + a_s * dx, s + a_s * ds)
+                    if np.sum(np.abs(c_new)) > con_l1:
+                        info.soc_tried = 1
+                        dz_p = eng.soc_direction(c_new)
+                        px, ps = dz_p[:D], dz_p[D:]
+                        if phi(x + a_s * dx + px, s + a_s * ds + ps) <= phi0 + a_s * self.eta * dphi0:
+                            if N:
+                                alpha_corr = step_host(s, a_s * ds + ps)
+                                if (phi(x + alpha_corr * (a_s * dx + px), s + alpha_corr * (a_s * ds + ps)) <=
+                                        phi0 + a_s * self.eta * dphi0):
+                                    correction = True
+                            else:
+                                alpha_corr = 1.0
+                                correction = True
+                if not correction:
                     a_s *= self.tau
                     a_l *= self.tau
-                    nb += 1
+                    nb = 1
+                    while phi(x + a_s * dx, s + a_s * ds) > phi0 + a_s * self.eta * dphi0:
+                        nrm_step = (np.sqrt(np.linalg.norm(a_s * dx) ** 2 + np.linalg.norm(a_l * ds) ** 2) if N
+                                    else np.linalg.norm(a_s * dx))
+                        if nrm_step < self.eps:
+                            info.signal = -2
+                            break
+                        a_s *= self.tau
+                        a_l *= self.tau
+                        nb += 1
         info.n_backtracks = nb
+        info.soc_accepted = 1 if correction else 0
+        info.alpha_corr = alpha_corr
         if info.signal != -2:
-            x = x + a_s * dx
-            s = s + a_s * ds
+            if correction:
+                x = x + alpha_corr * (a_s * dx + dz_p[:D])
+                s = s + alpha_corr * (a_s * ds + dz_p[D:])
+            else:
+                x = x + a_s * dx
+                s = s + a_s * ds
             lda = lda + a_l * dl if (M or N) else lda
         info.alpha_s, info.alpha_l, info.nu = a_s, a_l, self.nu_dev
         self._push(x, s, lda)
         _, nrm = eng.residual(want_g=False)
-        return info, nrm, float(self.f(x))
+        return info, nrm, float(self.f(self._arg(x)))

@@ -445,3 +445,49 @@ def test_callable_mode_nonconvex_delta_trace():
         if st['search']['soc_tried']:
             break      # trajectories may differ once a second-order correction is involved
     assert n >= 3
+
+
+def test_callable_mode_second_order_correction_matches_oracle():
+    """Callable mode now attempts the second-order correction (pyipm.py:1464-1489) like the reference: on problems whose
+    oracle trajectory tries / accepts it, signal, iteration count and the final iterate agree."""
+    n_tried = 0
+    for name in ('nlp_small', 'nlp_mid', 'example8', 'example10'):
+        prob, x0, _ = get_problem(name)
+        g = load_golden(name)
+        o, tr = oracle_trace(prob, x0)
+        n_tried += sum(int(st['search']['soc_tried']) for st in tr)
+        p = IPM(x0=np.array(x0), Ftol=1.0E-8, verbosity=-1, **prob.callables())
+        x, s, lda, fval, kkt = p.solve()
+        assert p.signal == int(g['sol0_signal']), name
+        assert p.iter_count == int(g['sol0_nsteps']), (name, p.iter_count, int(g['sol0_nsteps']))
+        assert sum(lg['soc_tried'] for lg in p.step_log) == sum(int(st['search']['soc_tried']) for st in tr)
+        assert np.linalg.norm(x - g['sol0_x']) <= 1e-6 * (1 + np.linalg.norm(g['sol0_x'])), name
+    assert n_tried >= 1
+
+
+def test_device_callables_mode():
+    """torch-CUDA callables: derivatives stay on the device (b200ipm_set_derivs with on_device = 1); same
+    solution as the lowered problem."""
+    import torch
+    prob = problems.make_nlp(D=96, M=12, N=64, seed=61)
+    dev = torch.device('cuda', 0)
+    T = lambda a: torch.as_tensor(a, device=dev, dtype=torch.float64)
+    Q, c, At, Ut, b, Gt, Vt, r = (T(a) for a in (prob.Q, prob.c, prob.At, prob.Ut, prob.b, prob.Gt, prob.Vt, prob.r))
+    M = prob.neq
+    kw = dict(
+        f=lambda x: 0.5 * x @ (Q @ x) + c @ x + 0.25 * prob.q4 * (x ** 4).sum(),
+        df=lambda x: Q @ x + c + prob.q4 * x ** 3,
+        d2f=lambda x: Q + torch.diag(3.0 * prob.q4 * x ** 2),
+        ce=lambda x: x @ At - b + 0.5 * (x @ Ut) ** 2,
+        dce=lambda x: At + Ut * (x @ Ut)[None, :],
+        d2ce=lambda x, lda: (Ut * lda[:M][None, :]) @ Ut.T,
+        ci=lambda x: x @ Gt + r - 0.5 * (x @ Vt) ** 2,
+        dci=lambda x: Gt - Vt * (x @ Vt)[None, :],
+        d2ci=lambda x, lda: -(Vt * lda[M:][None, :]) @ Vt.T)
+    pd = IPM(x0=prob.x0.copy(), Ftol=1.0E-8, verbosity=-1, device_callables=True, **kw)
+    xd, sd, ld, fd, kd = pd.solve()
+    pl = IPM(x0=prob.x0.copy(), f=prob, Ftol=1.0E-8, verbosity=-1)
+    xl, sl, ll, fl, kl = pl.solve()
+    assert pd.signal == pl.signal and pd.iter_count == pl.iter_count
+    assert np.linalg.norm(xd - xl) <= 1e-6 * (1 + np.linalg.norm(xl))
+    assert np.linalg.norm(ld - ll) <= 1e-5 * (1 + np.linalg.norm(ll))

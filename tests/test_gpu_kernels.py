@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import scipy.linalg
 
-from pyipm_b200 import _lib
+from pyipm_b200 import _lib, problems
 
 pytestmark = pytest.mark.gpu
 
@@ -181,3 +181,22 @@ def test_syrk_tcgen05_reports_unannounced_negative_weight():
     A[3, 5] = np.inf
     _, _, err = _lib.test_syrk_i8(128, None, 0.0, None, 0.0, [(A, np.abs(w), 1.0)], signed_mask=0)
     assert err & 1
+
+
+@pytest.mark.parametrize('tc', ['1', '0'])
+def test_ldlt_tcgen05_trailing_updates(tc, monkeypatch):
+    """The bulk trailing updates of the factorisation on tcgen05 (int8 error-free split, 21 slice pairs, B200IPM_LDLT_TC=1,
+    default for n >= 2048) against the fp64 DMMA updates (=0): same inertia of a quasi-definite KKT matrix with diagonal
+    entries spanning 8 decades, solution to 1e-9 after refinement either way."""
+    monkeypatch.setenv('B200IPM_LDLT_TC', tc)
+    n, m = 2560, 320
+    K, rhs = problems.make_dense_kkt(n, m, seed=77)
+    F = _lib.DenseLDLT(n)
+    (pos, neg, zero), _ = F.factor(K)
+    assert (pos, neg, zero) == (n - m, m, 0)
+    X = F.solve(rhs[:, :2], nrefine=2)
+    F.close()
+    Xref = np.linalg.solve(K, rhs[:, :2])
+    assert np.max(np.abs(X - Xref)) / np.max(np.abs(Xref)) < 1e-9
+    res = np.max(np.abs(K @ X - rhs[:, :2])) / (np.max(np.abs(K)) * np.max(np.abs(X)))
+    assert res < 1e-14, res
