@@ -174,7 +174,20 @@ def run_reference(args):
         extra = {'n': p1.nvar, 'K': K1, 'step_s': t1, 'n_eigvalsh': o1.last_reg['n_eig'],
                  'cubic_extrapolation_to_config3_s': t1 * (float(K3) / K1) ** 3,
                  'note': 'same NLP family at n=1024; NOT the headline number, kept to show the cubic law'}
-    o, st, dt = oracle_c3_step()
+    if args.ref_test_size:
+        # contract test only (tests/test_bench_contract_cpu.py): the same code path on a toy instance of the family
+        o, p1, (x1, s1, l1) = oracle_sample_step(D=args.ref_test_size, M=args.ref_test_size // 8, N=args.ref_test_size)
+        o.delta = np.float64(2.0 * DELTA_SAMPLE)
+        o.timers = {}
+        tr = []
+        o.trace = tr
+        t0 = time.perf_counter()
+        with np.errstate(all='ignore'):
+            o.newton_step(x1.copy(), s1.copy(), l1.copy())
+        dt = time.perf_counter() - t0
+        st = tr[0]
+    else:
+        o, st, dt = oracle_c3_step()
     value = 1.0 / dt
     sample = ('ONE full config-3 oracle Newton step (K=%d) from tests/golden/c3_state_after3.npz: %.1f s, %d eigvalsh(12800) '
               '+ 1 LU; requested steps=%d warmup=%d ignored beyond one step' % (K3, dt, st['reg']['n_eig'], args.steps, args.warmup))
@@ -183,7 +196,8 @@ def run_reference(args):
         'steps': 1, 'warmup': 0, 'steps_requested': args.steps, 'warmup_requested': args.warmup,
         'ms_per_step': 1e3 * dt, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': WORKLOAD, 'D': D3, 'M': M3, 'N': N3, 'K_full': K3,
+        'config': {'workload': WORKLOAD + (' -- CONTRACT TEST AT REDUCED SIZE D=%d, not a measurement' % args.ref_test_size
+                                           if args.ref_test_size else ''), 'D': D3, 'M': M3, 'N': N3, 'K_full': K3,
                    'state': 'teacher-forced from the state after %d real Newton steps from x0 (committed fixture)' % PRE_STEPS},
         'cpu_baseline': {'value': value, 'unit': 'steps/s', 'cores': cores, 'kind': 'port', 'sample': sample,
                          'same_config': True, 'split_s': {k: v for k, v in o.timers.items() if k != 'steps'}},
@@ -197,19 +211,14 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------- config 4 (multi-GPU LDL^T)
-def run_c4(args):
-    """BASELINE config 4: dense symmetric quasi-definite KKT of order 16384, 2-D block-cyclic LDL^T over the GPUs of
-    one node (pyipm_b200/dist_ldlt.py), 8 right-hand sides.  Prints its own JSON line (not the headline metric)."""
+def measure_c4(world, rank, local, n, steps, warmup, fp64_peak_tf=None):
+    """BASELINE config 4: dense symmetric quasi-definite KKT of order n (default 16384), 2-D block-cyclic LDL^T over the GPUs
+    of one node (pyipm_b200/dist_ldlt.py: look-ahead pipeline, NCCL panel broadcasts), 8 right-hand sides.  STRONG scaling:
+    the matrix is the same for every world size.  Needs an initialised process group when world > 1."""
     import torch
     import torch.distributed as dist
     from pyipm_b200.dist_ldlt import BlockCyclicLDLT, CudaTileOps, choose_grid
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    rank = int(os.environ.get('RANK', '0'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
-    n, m = args.c4_n, args.c4_n // 8
+    m = n // 8
     nh = n - m
     g = torch.Generator(device='cuda')
     g.manual_seed(16384)
@@ -226,9 +235,9 @@ def run_c4(args):
     grid = choose_grid(world)
     F = BlockCyclicLDLT(n, grid, CudaTileOps(local), block=256)
     F.load_device(K)
-    xref_res = None
     times_f, times_s = [], []
-    for it in range(args.warmup + args.steps):
+    inertia = None
+    for it in range(warmup + steps):
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -244,20 +253,43 @@ def run_c4(args):
             t = torch.tensor([tf, ts], device='cuda', dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             tf, ts = float(t[0]), float(t[1])
-        if it >= args.warmup:
+        if it >= warmup:
             times_f.append(tf)
             times_s.append(ts)
     R = rhs - F.matvec(X)
     resid = float(R.abs().max() / (K.abs().max() * X.abs().max()))
+    tf, ts = float(np.mean(times_f)), float(np.mean(times_s))
+    tfl = n ** 3 / 3.0 / tf * 1e-9
+    rec = {'workload': 'config4: dense symmetric quasi-definite KKT order %d (%d + %d), 8 RHS, 2-D block-cyclic LDL^T, grid '
+                       '%dx%d, block 256, look-ahead 1' % (n, nh, m, grid[0], grid[1]),
+           'n_gpus': world, 'scaling': 'strong', 'factor_ms': tf, 'solve_ms_8rhs_1refine': ts,
+           'factor_tflops_aggregate': tfl, 'inertia': list(inertia), 'inertia_expected': [nh, m, 0],
+           'scaled_residual_inf': resid, 'steps': steps, 'warmup': warmup}
+    if fp64_peak_tf:
+        rec['fp64_peak_tf_per_gpu'] = fp64_peak_tf
+        rec['frac_of_aggregate_fp64_peak'] = tfl / (world * fp64_peak_tf)
+    del F, K
+    torch.cuda.empty_cache()
+    return rec
+
+
+def run_c4(args):
+    """`--workload c4`: config 4 alone (its own JSON line; not the headline metric)."""
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    rec = measure_c4(world, rank, local, args.c4_n, args.steps, args.warmup)
     if rank == 0:
-        tf, ts = float(np.mean(times_f)), float(np.mean(times_s))
-        print(json.dumps({
-            'metric': 'kkt_factor_solve_ms', 'value': tf + ts, 'unit': 'ms', 'n_gpus': world, 'higher_is_better': False,
-            'steps': args.steps, 'warmup': args.warmup, 'scaling': 'strong', 'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': 'config4: dense symmetric quasi-definite KKT order %d (%d + %d), 8 RHS, 2-D block-cyclic '
-                                   'LDL^T, grid %dx%d, block 256' % (n, nh, m, grid[0], grid[1])},
-            'factor_ms': tf, 'solve_ms_8rhs_1refine': ts, 'factor_tflops': n ** 3 / 3.0 / tf * 1e-9,
-            'inertia': list(inertia), 'inertia_expected': [nh, m, 0], 'scaled_residual_inf': resid}))
+        line = {'metric': 'kkt_factor_solve_ms', 'value': rec['factor_ms'] + rec['solve_ms_8rhs_1refine'], 'unit': 'ms',
+                'n_gpus': world, 'higher_is_better': False, 'steps': args.steps, 'warmup': args.warmup, 'scaling': 'strong',
+                'dtype': 'f64', 'data': 'synthetic', 'config': {'workload': rec['workload']}}
+        line.update(rec)
+        print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -435,6 +467,15 @@ def run_b200(args):
                      ('ms_eval', 'ms_assemble', 'ms_factor', 'ms_solve', 'ms_search', 'ms_total')},
         'trajectory': traj, 'state_check': state_check,
     }
+    # config 4 (the path that DOES shard): every rank takes part; the record rides on the same JSON line so that the driver's
+    # 1/2/4/8-GPU runs capture its strong scaling
+    c4 = None
+    if args.c4_n > 0:
+        try:
+            c4 = measure_c4(world, rank, local, args.c4_n, 3, 1, fp64_peak_tf)
+        except Exception as exc:
+            c4 = {'error': repr(exc)}
+    line['c4'] = c4
     if rank == 0:
         # roofline legs: the dominant kernel (fp64 DMMA contraction) and the HBM-bound residual GEMV, each timed
         # alone with CUDA events on the launching stream
@@ -564,11 +605,12 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--ref-skip-sample', action='store_true', help='reference arm: skip the n=1024 extra')
+    ap.add_argument('--ref-test-size', type=int, default=0, help=argparse.SUPPRESS)   # contract test: toy instance
     ap.add_argument('--traj-steps', type=int, default=12, help='real-trajectory leg: consecutive Newton steps from x0')
     ap.add_argument('--flags', type=int, default=DEFAULT_FLAGS,
                     help='b200ipm_params.flags: 1 no speculative reghess, 2 tcgen05 int8 SYRKs, (v << 2) tcgen05 tile variant')
     ap.add_argument('--workload', default='c3', choices=['c3', 'c4'])
-    ap.add_argument('--c4-n', type=int, default=16384)
+    ap.add_argument('--c4-n', type=int, default=16384, help='order of the config-4 matrix (0: skip the c4 sub-record)')
     args = ap.parse_args()
     if args.workload == 'c4':
         return run_c4(args)

@@ -225,6 +225,17 @@ int b200ipm_ldlt_import(b200ipm_ldlt_handle h, const double* A_dev, int lda, con
                         const double* dinfo_dev, const int* kind_dev);
 int b200ipm_gemm_nt_update(b200ipm_ldlt_handle h, double* C_dev, int ldc, int rows, int cols,
                            const double* A_dev, int lda, const double* B_dev, int ldb, int k, int lower_only);
+/* Composite calls of the block-cyclic driver (one call per block column): factor the b x b diagonal block at A_dev in
+ * place (b a multiple of 64; tile steps + in-block panel / update) and pack its factor data into diag_dev -- [b*b copy of
+ * the factored block | per 64-tile: LinvP 64*64, dinv_a, dinv_b, d_a, d_b (64 each), kind (64 ints)]; wdiag_dev is b*b
+ * doubles of scratch.  block_panel: B_dev (rows x b, leading dimension ld) <- L, W_dev (rows x b contiguous) <- W = L D. */
+int b200ipm_ldlt_block_factor(b200ipm_ldlt_handle h, double* A_dev, int ld, int b, double* diag_dev, double* wdiag_dev);
+int b200ipm_ldlt_block_panel(b200ipm_ldlt_handle h, double* B_dev, int ld, int rows, int b, const double* diag_dev,
+                             double* W_dev);
+/* y (rows) = A (rows x cols, row-major, leading dimension lda) * v: the residual's HBM-bound GEMV kernel on device pointers
+ * (distributed refinement mat-vec of the block-cyclic driver); asynchronous on the handle's stream. */
+int b200ipm_ldlt_gemv(b200ipm_ldlt_handle h, const double* A_dev, int lda, int rows, int cols, const double* v_dev,
+                      double* y_dev);
 /* Trailing update of a rank's local piece of a 2-D block-cyclic matrix in ONE launch: C (rows x cols, local
  * storage, origin at local block (li0, lj0)) -= A B^T on every 128 x 128 tile whose global block row
  * (li*P + p) >= its global block column (lj*Q + q); block must be a multiple of 128. */

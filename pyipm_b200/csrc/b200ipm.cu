@@ -2251,6 +2251,74 @@ int b200ipm_gemm_nt_update(b200ipm_ldlt_handle h, double* C_dev, int ldc, int ro
     return 0;
 }
 
+// Composite calls of the block-cyclic driver: one C call per block column instead of a dozen (the host-side launch
+// sequencing of a column was the critical path of the multi-GPU factorisation).  diag_dev layout (CudaTileOps): [b*b copy
+// of the factored block | per 64-tile: LinvP (64*64) | dinv_a | dinv_b | d_a | d_b (64 each) | kind (64 ints = 32 doubles)].
+int b200ipm_ldlt_block_factor(b200ipm_ldlt_handle h, double* A_dev, int ld, int b, double* diag_dev, double* wdiag_dev) {
+    if (!h || !A_dev || !diag_dev || !wdiag_dev || b <= 0 || (b % NB) != 0) return fail_msg("block_factor: bad arguments");
+    CU(cudaSetDevice(h->device));
+    const int nt = b / NB, tile_doubles = NB * NB + 4 * NB + NB / 2;
+    if (!h->tile_counts_live) {
+        ldlt_reset_kernel<<<1, 1, 0, h->st>>>(h->F.counts, h->F.dstat, h->F.ticket);
+        LAUNCHED();
+        h->tile_counts_live = true;
+    }
+    for (int t = 0; t < nt; t++) {
+        const int k0 = t * NB;
+        double* linv = diag_dev + (size_t)b * b + (size_t)t * tile_doubles;
+        double* dblk = linv + NB * NB;
+        int* kind = reinterpret_cast<int*>(dblk + 4 * NB);
+        ldlt_tile_kernel<<<1, TILE_THREADS, TILE_SMEM, h->st>>>(A_dev + (size_t)k0 * ld + k0, ld, NB, linv, dblk, dblk + NB, dblk + 2 * NB,
+                                                       dblk + 3 * NB, kind, nullptr, h->F.counts, h->F.dstat, h->F.pivot_u, nullptr,
+                                                       h->F.tile_blocked);
+        LAUNCHED();
+        const int rows = b - k0 - NB;
+        if (rows > 0) {
+            double* pp = A_dev + (size_t)(k0 + NB) * ld + k0;
+            double* wp = wdiag_dev + (size_t)(k0 + NB) * b + k0;
+            ldlt_panel_kernel<<<cdiv(rows, NB), 128, PANEL_SMEM, h->st>>>(pp, ld, rows, linv, dblk, dblk + NB, kind, wp, b, nullptr);
+            LAUNCHED();
+            GemmArgs u{};
+            u.C = A_dev + (size_t)(k0 + NB) * ld + (k0 + NB); u.ldc = ld; u.Cin = u.C; u.ldcin = ld; u.n = rows; u.m = rows; u.beta = 1.0;
+            u.mode = GEMM_LOWER_ONLY; u.nterms = 1;
+            u.t[0] = GemmTerm{wp, pp, nullptr, b, ld, NB, -1.0};
+            RET(gemm_nt(h->st, u));
+        }
+    }
+    CU(cudaMemcpy2DAsync(diag_dev, sizeof(double) * b, A_dev, sizeof(double) * ld, sizeof(double) * b, b, cudaMemcpyDeviceToDevice, h->st));
+    return 0;
+}
+// B_dev (rows x b, leading dimension ld) <- L of the panel, W_dev (rows x b, contiguous) <- W = L D, given the factor
+// data of the diagonal block
+int b200ipm_ldlt_block_panel(b200ipm_ldlt_handle h, double* B_dev, int ld, int rows, int b, const double* diag_dev, double* W_dev) {
+    if (!h || !B_dev || !diag_dev || !W_dev || b <= 0 || (b % NB) != 0) return fail_msg("block_panel: bad arguments");
+    if (rows <= 0) return 0;
+    CU(cudaSetDevice(h->device));
+    const int nt = b / NB, tile_doubles = NB * NB + 4 * NB + NB / 2;
+    for (int t = 0; t < nt; t++) {
+        const int k0 = t * NB;
+        const double* linv = diag_dev + (size_t)b * b + (size_t)t * tile_doubles;
+        const double* dblk = linv + NB * NB;
+        const int* kind = reinterpret_cast<const int*>(dblk + 4 * NB);
+        ldlt_panel_kernel<<<cdiv(rows, NB), 128, PANEL_SMEM, h->st>>>(B_dev + k0, ld, rows, linv, dblk, dblk + NB, kind, W_dev + k0, b, nullptr);
+        LAUNCHED();
+        const int cols = b - k0 - NB;
+        if (cols > 0)   // remaining columns of this block column: B[:, k0+64:] -= W_t * L_kk[k0+64:, k0:k0+64]^T
+            RET(gemm_nt_sub(h->st, B_dev + k0 + NB, ld, rows, cols, W_dev + k0, b, diag_dev + (size_t)(k0 + NB) * b + k0, b, NB));
+    }
+    return 0;
+}
+
+// y (rows) = A (rows x cols, row-major, leading dimension lda) * v (cols): the HBM-bound GEMV kernel of the residual,
+// for the distributed refinement mat-vec of the block-cyclic driver (device pointers, asynchronous on the handle's stream)
+int b200ipm_ldlt_gemv(b200ipm_ldlt_handle h, const double* A_dev, int lda, int rows, int cols, const double* v_dev,
+                      double* y_dev) {
+    if (!h || !A_dev || !v_dev || !y_dev) return fail_msg("ldlt_gemv: bad arguments");
+    if (rows <= 0 || cols <= 0) return 0;
+    CU(cudaSetDevice(h->device));
+    return gemv_n(h->st, A_dev, lda, rows, cols, v_dev, nullptr, 0.0, 1.0, y_dev);
+}
+
 int b200ipm_gemm_nt_update_bc(b200ipm_ldlt_handle h, double* C_dev, int ldc, int rows, int cols, const double* A_dev,
                               int lda, const double* B_dev, int ldb, int k, int block, int P, int Q, int p, int q, int li0,
                               int lj0) {

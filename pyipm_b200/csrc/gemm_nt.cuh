@@ -19,6 +19,8 @@
 // pipeline (16-byte LDGSTS, zero-filled edges), smem row stride 20 doubles => every fragment LDS.64 is the
 // minimum two wavefronts.  Algorithmic FLOPs per launch: 2 * (#computed tile elements) * sum_t K_t.
 #pragma once
+#include <cuda.h>
+#include <cstdint>
 #include "common.cuh"
 
 namespace b200 {
@@ -446,13 +448,215 @@ __global__ void __launch_bounds__(128, 2) gemm_nt_sub64_kernel(double* __restric
     trace_end(trc);
 }
 
+
+// ------------------------------------------------------------------------------------------- TMA-staged 64 x 64 update
+// Same contract as gemm_nt_sub64_kernel (C -= A B', 64 x 64 tiles, 128 threads, fp64 DMMA), but the operand tiles are
+// staged by the TENSOR MEMORY ACCELERATOR: one elected thread issues cp.async.bulk.tensor.2d (SASS: UTMALDG) against two
+// cuTensorMap descriptors that describe the WHOLE operand matrices (the L panels inside the KKT matrix, the W = L D
+// scratch panels), boxes of 64 rows x 16 doubles (128 bytes) with the 128-byte swizzle, completion on per-stage
+// mbarriers.  The swizzle (16-byte chunk index XOR row mod 8) makes the DMMA fragment reads -- 8 rows x 4 consecutive
+// doubles per quarter-warp -- hit every bank exactly twice, the minimum for 64-bit accesses, without padding the rows.
+// No per-thread address arithmetic or LDGSTS issue for the loads: the four warps only compute.
+constexpr int T_STAGES = 3;
+constexpr int T_BOX_BYTES = 64 * 128;                     // one box: 64 rows x 16 doubles
+constexpr int T_STAGE_BYTES = 4 * T_BOX_BYTES;            // A: two k-halves, B: two k-halves (K step = 32)
+constexpr int T_SMEM = T_STAGES * T_STAGE_BYTES + 1024;   // + alignment slack (boxes must be 1024-byte aligned)
+
+struct TmaMat {              // host-side handle of one operand matrix
+    CUtensorMap map;         // 2-D tensor [rows][ld] of doubles, box 64 x 16, SWIZZLE_128B
+    const double* base = nullptr;
+    int ld = 0;
+    bool ok = false;
+};
+
+__device__ __forceinline__ uint32_t t_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void t_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void t_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool t_mbar_try(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void t_tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(dst),
+        "l"(map), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+// element (row, k) of a swizzled 64 x 16 box
+__device__ __forceinline__ double t_box_ld(const unsigned char* box, int row, int k) {
+    return *reinterpret_cast<const double*>(box + row * 128 + ((((k >> 1) ^ (row & 7)) << 4) | ((k & 1) << 3)));
+}
+
+__global__ void __launch_bounds__(128, 2) gemm_nt_sub64_tma_kernel(double* __restrict__ C, int ldc, int rows, int cols,
+                                                                   const __grid_constant__ CUtensorMap mapA, int a_row0,
+                                                                   int a_col0, const __grid_constant__ CUtensorMap mapB,
+                                                                   int b_row0, int b_col0, int K,
+                                                                   const int* __restrict__ ctrl, int skip00) {
+    extern __shared__ __align__(1024) unsigned char t_smem_raw[];
+    __shared__ __align__(8) uint64_t bar_full[T_STAGES];
+    if (skip00 && blockIdx.x == 0 && blockIdx.y == 0) return;   // that tile was already updated on the chain stream
+    if (ctrl) {
+        __shared__ int s_abort;
+        if (threadIdx.x == 0) s_abort = *reinterpret_cast<const volatile int*>(ctrl + 4);
+        __syncthreads();
+        if (s_abort) return;
+    }
+    const int trc = (threadIdx.x == 0 && ((blockIdx.x == 1 && blockIdx.y == 0) || (blockIdx.x == gridDim.x - 1 && blockIdx.y == gridDim.y - 1)))
+                        ? trace_begin(TR_SUB64, ctrl) : -1;
+    unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(t_smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, tg = lane & 3;
+    const int row0 = blockIdx.y * S_BM, col0 = blockIdx.x * S_BN;
+    const int nk = K / 32;
+    if (tid == 0) {
+        for (int s = 0; s < T_STAGES; s++) t_mbar_init(t_smem_u32(&bar_full[s]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int kt) {
+        const int s = kt % T_STAGES;
+        const uint32_t bar = t_smem_u32(&bar_full[s]);
+        const uint32_t dst = t_smem_u32(sm + s * T_STAGE_BYTES);
+        t_mbar_expect_tx(bar, T_STAGE_BYTES);
+        const int k0 = kt * 32;
+        t_tma_load_2d(dst, &mapA, a_col0 + k0, a_row0 + row0, bar);
+        t_tma_load_2d(dst + T_BOX_BYTES, &mapA, a_col0 + k0 + 16, a_row0 + row0, bar);
+        t_tma_load_2d(dst + 2 * T_BOX_BYTES, &mapB, b_col0 + k0, b_row0 + col0, bar);
+        t_tma_load_2d(dst + 3 * T_BOX_BYTES, &mapB, b_col0 + k0 + 16, b_row0 + col0, bar);
+    };
+    if (tid == 0)
+        for (int s = 0; s < T_STAGES - 1 && s < nk; s++) issue(s);
+    double acc[2][8][2];
+#pragma unroll
+    for (int a = 0; a < 2; a++)
+#pragma unroll
+        for (int b = 0; b < 8; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
+    for (int kt = 0; kt < nk; kt++) {
+        const int s = kt % T_STAGES;
+        const uint32_t bar = t_smem_u32(&bar_full[s]);
+        const uint32_t ph = (uint32_t)(kt / T_STAGES) & 1u;
+        {
+            const long long t0 = clock64();
+            while (!t_mbar_try(bar, ph)) {
+                if (clock64() - t0 > 4000000000LL) break;        // bounded: never hang the device
+            }
+        }
+        __syncthreads();         // everybody is past stage (kt - 1): its buffer may be refilled
+        if (tid == 0 && kt + T_STAGES - 1 < nk) issue(kt + T_STAGES - 1);
+        const unsigned char* st = sm + s * T_STAGE_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < 8; kk++) {
+            const unsigned char* ab = st + (kk >> 2) * T_BOX_BYTES;
+            const unsigned char* bb = st + (2 + (kk >> 2)) * T_BOX_BYTES;
+            const int k = (kk & 3) * 4 + tg;
+            double af[2], bf[8];
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++) af[mt] = t_box_ld(ab, warp * 16 + mt * 8 + g, k);
+#pragma unroll
+            for (int nt = 0; nt < 8; nt++) bf[nt] = t_box_ld(bb, nt * 8 + g, k);
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                for (int nt = 0; nt < 8; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
+        }
+    }
+    const bool interior = (row0 + S_BM <= rows) && (col0 + S_BN <= cols) && ((ldc & 1) == 0) &&
+                          ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+#pragma unroll
+    for (int mt = 0; mt < 2; mt++) {
+        const int i = row0 + warp * 16 + mt * 8 + g;
+        if (interior) {
+            double2 cin[8];
+#pragma unroll
+            for (int nt = 0; nt < 8; nt++) cin[nt] = *reinterpret_cast<const double2*>(C + (size_t)i * ldc + col0 + nt * 8 + tg * 2);
+#pragma unroll
+            for (int nt = 0; nt < 8; nt++) {
+                cin[nt].x -= acc[mt][nt][0];
+                cin[nt].y -= acc[mt][nt][1];
+                *reinterpret_cast<double2*>(C + (size_t)i * ldc + col0 + nt * 8 + tg * 2) = cin[nt];
+            }
+        } else if (i < rows) {
+#pragma unroll
+            for (int nt = 0; nt < 8; nt++)
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const int j = col0 + nt * 8 + tg * 2 + e;
+                    if (j < cols) C[(size_t)i * ldc + j] -= acc[mt][nt][e];
+                }
+        }
+    }
+    trace_end(trc);
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda at link time)
+typedef CUresult (*t_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline t_encode_fn tma_encode_fn() {
+    static t_encode_fn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<t_encode_fn>(p);
+        cudaGetLastError();
+    }
+    return fn;
+}
+// describe a row-major matrix of doubles (rows x ld) for 64 x 16 boxes with the 128-byte swizzle
+inline int tma_describe(TmaMat& m, const double* base, int rows, int ld) {
+    m.ok = false;
+    m.base = base;
+    m.ld = ld;
+    t_encode_fn fn = tma_encode_fn();
+    if (!fn || (reinterpret_cast<uintptr_t>(base) & 15) || (ld & 1)) return 0;      // silently: the cp.async kernel is used
+    const cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * 8};
+    const cuuint32_t box[2] = {16, 64};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(&m.map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    m.ok = (r == CUDA_SUCCESS);
+    return 0;
+}
+
 // C (rows x cols, in place) -= A (rows x K) * B (cols x K)^T
 inline int gemm_nt_sub(cudaStream_t st, double* C, int ldc, int rows, int cols, const double* A, int lda, const double* B,
-                       int ldb, int K, const int* ctrl = nullptr, int skip00 = 0) {
+                       int ldb, int K, const int* ctrl = nullptr, int skip00 = 0, const TmaMat* ta = nullptr,
+                       const TmaMat* tb = nullptr) {
     if (rows <= 0 || cols <= 0) return 0;
     const bool ok = !(lda & 1) && !(ldb & 1) && !(reinterpret_cast<uintptr_t>(A) & 15) && !(reinterpret_cast<uintptr_t>(B) & 15);
     if (ok && rows >= 48) {
         dim3 grid(cdiv(cols, S_BN), cdiv(rows, S_BM));
+        if (ta && tb && ta->ok && tb->ok && (K % 32) == 0 && ta->ld == lda && tb->ld == ldb) {
+            // operands through the tensor memory accelerator: coordinates of the tile origin inside the described matrices
+            const size_t offa = (size_t)(A - ta->base), offb = (size_t)(B - tb->base);
+            const int a_row0 = (int)(offa / (size_t)lda), a_col0 = (int)(offa % (size_t)lda);
+            const int b_row0 = (int)(offb / (size_t)ldb), b_col0 = (int)(offb % (size_t)ldb);
+            if ((a_col0 & 1) == 0 && (b_col0 & 1) == 0) {
+                gemm_nt_sub64_tma_kernel<<<grid, 128, T_SMEM, st>>>(C, ldc, rows, cols, ta->map, a_row0, a_col0, tb->map, b_row0,
+                                                                    b_col0, K, ctrl, skip00);
+                LAUNCHED();
+                return 0;
+            }
+        }
         gemm_nt_sub64_kernel<<<grid, 128, S_SMEM, st>>>(C, ldc, rows, cols, A, lda, B, ldb, K, ctrl, skip00);
         LAUNCHED();
         return 0;

@@ -52,7 +52,8 @@ struct LdltWs {
     cudaStream_t side = nullptr;   // trailing updates beyond the next panel run here, overlapped with the next panel
     cudaEvent_t ev_panel[2] = {nullptr, nullptr}, ev_upd[2] = {nullptr, nullptr};
     cudaStream_t upd = nullptr;    // in-panel updates off the chain (everything of a tile step but the next diagonal tile)
-    cudaEvent_t ev_tile = nullptr, ev_mini = nullptr, ev_urest = nullptr;
+    cudaEvent_t ev_tile = nullptr, ev_mini = nullptr, ev_urest = nullptr, ev_a2 = nullptr;
+    int split_a = 1;               // B200IPM_LDLT_SPLITA=0: the whole boundary update on the chain stream
     int* sig = nullptr;            // device word set to 1 when tile step sig_tile starts (baked into the graph)
     int sig_tile = -1;
     int tile_blocked = 1;          // blocked fast attempt inside the tile kernel (B200IPM_TILE_BLOCKED=0: per-pivot barrier version)
@@ -69,6 +70,8 @@ struct LdltWs {
     int tc_update = 0;         // bulk trailing updates on tcgen05 (error-free int8 split), B200IPM_LDLT_TC=0 restores DMMA
     int tc_ctas = 96;          // CTAs per wave of the tcgen05 update (B200IPM_LDLT_TC_CTAS)
     OzUpdWs tcu;
+    TmaMat tmA, tmW[4];        // tensor maps of the KKT matrix and the four W scratch panels (TMA-staged updates)
+    int use_tma = 1;           // B200IPM_LDLT_TMA=0: cp.async staging (gemm_nt_sub64_kernel)
     double pivot_u = 0.01;     // threshold of the fast (unpivoted) tile attempt: accept step j iff |d_j| >= u * max_i |T[i][j]|
 };
 
@@ -106,6 +109,8 @@ inline int ldlt_alloc(LdltWs& w, int n, cudaStream_t st, bool background = false
     CU(cudaEventCreateWithFlags(&w.ev_tile, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&w.ev_mini, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&w.ev_urest, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&w.ev_a2, cudaEventDisableTiming));
+    { const char* e = getenv("B200IPM_LDLT_SPLITA"); if (e) w.split_a = atoi(e); }
     { const char* e = getenv("B200IPM_LDLT_MINI"); if (e) w.use_mini = atoi(e); }
     { const char* e = getenv("B200IPM_TILE_BLOCKED"); if (e) w.tile_blocked = atoi(e); }
     for (int i = 0; i < 2; i++) {
@@ -124,6 +129,15 @@ inline int ldlt_alloc(LdltWs& w, int n, cudaStream_t st, bool background = false
     CU(cudaMalloc(&w.dstat, sizeof(double) * 2));
     CU(cudaMalloc(&w.serr, sizeof(int)));
     CU(cudaMemset(w.serr, 0, sizeof(int)));
+    {
+        const char* e = getenv("B200IPM_LDLT_TMA");
+        if (e) w.use_tma = atoi(e);
+        if (w.use_tma) {
+            RET(tma_describe(w.tmA, w.A, (int)npad, w.ld));
+            double* wb[4] = {w.Wp, w.Wp2, w.Wp3, w.Wp4};
+            for (int i = 0; i < 4; i++) RET(tma_describe(w.tmW[i], wb[i], (int)npad, 256));
+        }
+    }
     {
         // tcgen05 trailing updates pay off once the bulk piece (everything beyond the next three outer panels) exists
         const char* e = getenv("B200IPM_LDLT_TC");
@@ -158,6 +172,7 @@ inline void ldlt_free(LdltWs& w) {
     if (w.ev_tile) cudaEventDestroy(w.ev_tile);
     if (w.ev_mini) cudaEventDestroy(w.ev_mini);
     if (w.ev_urest) cudaEventDestroy(w.ev_urest);
+    if (w.ev_a2) cudaEventDestroy(w.ev_a2);
     if (w.cap) cudaStreamDestroy(w.cap);
     for (int i = 0; i < 2; i++) { if (w.ev_panel[i]) cudaEventDestroy(w.ev_panel[i]); if (w.ev_upd[i]) cudaEventDestroy(w.ev_upd[i]); }
     cudaFree(w.LinvP); cudaFree(w.dinfo); cudaFree(w.kind); cudaFree(w.counts);
@@ -377,11 +392,63 @@ __device__ __forceinline__ void tile_fast_blocked(double* __restrict__ Tf, doubl
         cp[0] = acc0;
         cp[1] = acc1;
     };
+    // X = L^-1 one block ROW at a time, by warp 7, concurrently with the elimination of the following block columns
+    // (row block i of L is final once diagonal block i is factored, i.e. at the barrier that opens iteration i):
+    //   X_ii = inv(L_ii),   X_ij = -X_ii * sum_{k=j}^{i-1} L_ik X_kj   (j < i; the X_kj are earlier block rows)
+    auto inverse_block_row = [&](const int i) {
+        double* scr = xscr + warp * 64;
+        if (lane < 8) {
+            const int b0 = 8 * i, c = lane;
+            double x[8];
+#pragma unroll
+            for (int r = 0; r < 8; r++) x[r] = (r == c) ? 1.0 : 0.0;
+#pragma unroll
+            for (int r = 1; r < 8; r++) {
+                double sacc = 0.0;
+#pragma unroll
+                for (int k = 0; k < r; k++) sacc = fma(Tf[(b0 + r) * NBP + b0 + k], x[k], sacc);   // x[k] = 0 for k < c
+                if (r > c) x[r] = -sacc;
+            }
+#pragma unroll
+            for (int r = 0; r < 8; r++)
+                if (r >= c) Xf[(b0 + r) * NBP + b0 + c] = x[r];
+        }
+        __syncwarp();
+        for (int j = 0; j < i; j++) {
+            double s0 = 0.0, s1 = 0.0;
+            for (int k = j; k < i; k++) {
+#pragma unroll
+                for (int kk = 0; kk < 8; kk += 4) {
+                    const double av = Tf[(8 * i + g) * NBP + 8 * k + kk + tg];           // L_ik[g][kk + tg]
+                    const double bv = Xf[(8 * k + kk + tg) * NBP + 8 * j + g];           // X_kj[kk + tg][g]
+                    dmma884(s0, s1, av, bv);
+                }
+            }
+            scr[g * 8 + 2 * tg] = s0;
+            scr[g * 8 + 2 * tg + 1] = s1;
+            __syncwarp();
+            double x0 = 0.0, x1 = 0.0;
+#pragma unroll
+            for (int kk = 0; kk < 8; kk += 4) {
+                const double av = -Xf[(8 * i + g) * NBP + 8 * i + kk + tg];               // -X_ii[g][kk + tg]
+                const double bv = scr[(kk + tg) * 8 + g];                                 // S[kk + tg][g]
+                dmma884(x0, x1, av, bv);
+            }
+            Xf[(8 * i + g) * NBP + 8 * j + 2 * tg] = x0;
+            Xf[(8 * i + g) * NBP + 8 * j + 2 * tg + 1] = x1;
+            __syncwarp();
+        }
+    };
+    constexpr int NUPD = TILE_THREADS / 32 - 1;        // warps 0 .. 6 eliminate, warp 7 inverts
     if (warp == 0 && lane == 0) diag_block(0);
 #pragma unroll 1
     for (int kb = 0; kb < NB / 8; kb++) {
         const int c0 = 8 * kb;
         __syncthreads();                   // diagonal block kb is factored; the update behind block kb-1 is complete
+        if (warp == NUPD) {
+            inverse_block_row(kb);         // reads only FINAL entries of T (columns < c0 + 8 of rows c0 .. c0 + 7) and writes X
+            continue;                      // next: the barrier that opens iteration kb + 1
+        }
         // (1b) the rows below the block, one thread per row:  l_i U = t_i  with  U = D L8' (forward substitution along the
         // eight columns; rows are independent)
         {
@@ -405,10 +472,10 @@ __device__ __forceinline__ void tile_fast_blocked(double* __restrict__ Tf, doubl
                 for (int c = 0; c < 8; c++) Tf[row * NBP + c0 + c] = l[c];
             }
         }
-        __syncthreads();
+        asm volatile("bar.sync 1, %0;\n" ::"n"(NUPD * 32) : "memory");      // the eliminating warps only
         // (2) rank-8 update of the lower tiles behind the block.  Warp 0 takes the next diagonal tile first and thread 0
         // goes straight on to factor it (pinv and the next sda entries are free again: (1b) is over), overlapped with
-        // the other seven warps updating the remaining tiles.
+        // the other six warps updating the remaining tiles.
         if (kb < NB / 8 - 1) {
             const int nbt = NB / 8 - 1 - kb;
             const int ntiles = nbt * (nbt + 1) / 2;
@@ -417,55 +484,8 @@ __device__ __forceinline__ void tile_fast_blocked(double* __restrict__ Tf, doubl
                 __syncwarp();
                 if (lane == 0) diag_block(c0 + 8);
             } else {
-                for (int t = warp; t < ntiles; t += TILE_THREADS / 32 - 1) update_tile(kb, t);
+                for (int t = warp; t < ntiles; t += NUPD - 1) update_tile(kb, t);
             }
-        }
-    }
-    __syncthreads();
-    // ---- X = L^-1.  Diagonal blocks first (warp b, lanes 0..7: one column each, forward substitution)
-    if (lane < 8) {
-        const int b0 = 8 * warp, c = lane;
-        double x[8];
-#pragma unroll
-        for (int r = 0; r < 8; r++) x[r] = (r == c) ? 1.0 : 0.0;
-#pragma unroll
-        for (int r = 1; r < 8; r++) {
-            double sacc = 0.0;
-#pragma unroll
-            for (int k = 0; k < r; k++) sacc = fma(Tf[(b0 + r) * NBP + b0 + k], x[k], sacc);   // x[k] = 0 for k < c
-            if (r > c) x[r] = -sacc;
-        }
-#pragma unroll
-        for (int r = 0; r < 8; r++)
-            if (r >= c) Xf[(b0 + r) * NBP + b0 + c] = x[r];
-    }
-    __syncthreads();
-    {
-        const int j = warp;                            // block column
-        double* scr = xscr + warp * 64;
-        for (int i = j + 1; i < NB / 8; i++) {
-            double s0 = 0.0, s1 = 0.0;
-            for (int k = j; k < i; k++) {
-#pragma unroll
-                for (int kk = 0; kk < 8; kk += 4) {
-                    const double av = Tf[(8 * i + g) * NBP + 8 * k + kk + tg];           // L_ik[g][kk + tg]
-                    const double bv = Xf[(8 * k + kk + tg) * NBP + 8 * j + g];           // X_kj[kk + tg][g]
-                    dmma884(s0, s1, av, bv);
-                }
-            }
-            scr[g * 8 + 2 * tg] = s0;
-            scr[g * 8 + 2 * tg + 1] = s1;
-            __syncwarp();
-            double x0 = 0.0, x1 = 0.0;
-#pragma unroll
-            for (int kk = 0; kk < 8; kk += 4) {
-                const double av = -Xf[(8 * i + g) * NBP + 8 * i + kk + tg];               // -X_ii[g][kk + tg]
-                const double bv = scr[(kk + tg) * 8 + g];                                 // S[kk + tg][g]
-                dmma884(x0, x1, av, bv);
-            }
-            Xf[(8 * i + g) * NBP + 8 * j + 2 * tg] = x0;
-            Xf[(8 * i + g) * NBP + 8 * j + 2 * tg + 1] = x1;
-            __syncwarp();
         }
     }
     __syncthreads();
@@ -1123,6 +1143,7 @@ inline int ldlt_init_attrs() {
     CU(cudaFuncSetAttribute(ldlt_mini_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MINI_SMEM));
     CU(cudaFuncSetAttribute(gemm_nt_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM));
     CU(cudaFuncSetAttribute(gemm_nt_sub64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S_SMEM));
+    CU(cudaFuncSetAttribute(gemm_nt_sub64_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM));
     CU(cudaFuncSetAttribute(oz_syrk_kernel<64, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, OzShape<64, 6>::SMEM));
     return 0;
 }
@@ -1143,10 +1164,12 @@ inline int ldlt_factor_launch(LdltWs& w, cudaStream_t st) {
     ldlt_reset_kernel<<<1, 1, 0, st>>>(w.counts, w.dstat, w.ticket);
     LAUNCHED();
     int p = 0;
-    bool side_used = false, upd_pending = false, u1_used = false, urg_used = false, r_prev = false;
+    bool side_used = false, upd_pending = false, u1_used = false, urg_used = false, r_prev = false, a2_pending = false;
     for (int c0 = 0; c0 < n; c0 += NBO, p++) {
         const int c1 = min(c0 + NBO, n);
         double* Wb = (p % 4 == 0) ? w.Wp : ((p % 4 == 1) ? w.Wp2 : ((p % 4 == 2) ? w.Wp3 : w.Wp4));
+        const TmaMat* tW = w.use_tma ? &w.tmW[p % 4] : nullptr;
+        const TmaMat* tA = w.use_tma ? &w.tmA : nullptr;
         for (int k0 = c0; k0 < c1; k0 += NB) {
             const int k = k0 / NB, nb = min(NB, n - k0), k1 = k0 + nb;
             double* Akk = w.A + (size_t)k0 * ld + k0;
@@ -1167,9 +1190,13 @@ inline int ldlt_factor_launch(LdltWs& w, cudaStream_t st) {
                 upd_pending = false;
             }
             if (!mini) {
+                if (a2_pending) {    // the whole block column is read here: the deferred part of the boundary update must be in
+                    CU(cudaStreamWaitEvent(st, w.ev_a2, 0));
+                    a2_pending = false;
+                }
                 ldlt_panel_kernel<<<cdiv(rows, NB), 128, PANEL_SMEM, st>>>(B, ld, rows, Lk, ia + k0, ib + k0, w.kind + k0, Wt, NBO, w.counts);
                 LAUNCHED();
-                if (mcols > 0) RET(gemm_nt_sub(st, C11, ld, rows, mcols, Wt, NBO, B, ld, NB, w.counts));
+                if (mcols > 0) RET(gemm_nt_sub(st, C11, ld, rows, mcols, Wt, NBO, B, ld, NB, w.counts, 0, tW, tA));
             } else {
                 CU(cudaEventRecord(w.ev_tile, st));
                 ldlt_mini_kernel<<<1, MINI_THREADS, MINI_SMEM, st>>>(B, ld, rows, Lk, ia + k0, ib + k0, w.kind + k0, Wt, NBO, C11, w.counts);
@@ -1180,9 +1207,10 @@ inline int ldlt_factor_launch(LdltWs& w, cudaStream_t st) {
                                                                                    w.kind + k0, Wt + (size_t)NB * NBO, NBO, w.counts);
                 LAUNCHED();
                 CU(cudaStreamWaitEvent(w.upd, w.ev_mini, 0));
-                RET(gemm_nt_sub(w.upd, C11, ld, rows, mcols, Wt, NBO, B, ld, NB, w.counts, /*skip00=*/1));
+                RET(gemm_nt_sub(w.upd, C11, ld, rows, mcols, Wt, NBO, B, ld, NB, w.counts, /*skip00=*/1, tW, tA));
                 CU(cudaEventRecord(w.ev_urest, w.upd));
                 upd_pending = true;
+                a2_pending = false;      // ev_urest is recorded after (a2) on the same stream: waiting for it covers (a2)
             }
         }
         if (upd_pending) {
@@ -1199,7 +1227,22 @@ inline int ldlt_factor_launch(LdltWs& w, cudaStream_t st) {
         // (a) next panel's columns, chain stream: A[c1:, c1:c1+na] -= W L[c1:c1+na]^T.  The same columns were
         // read-modify-written by U1 of the previous panel, which must be complete.
         if (p >= 1 && u1_used) CU(cudaStreamWaitEvent(st, w.ev_urg[(p - 1) & 1], 0));
-        RET(gemm_nt_sub(st, w.A + (size_t)c1 * ld + c1, ld, rows2, na, Wpan, NBO, Lpan, ld, kw, w.counts));
+        const int ncrit = 2 * NB;
+        if (w.split_a && rows2 > ncrit && na > NB) {
+            // (a1) chain stream: only the 128 x 128 corner -- the next diagonal tile, the 64 rows below it and the diagonal
+            // tile after that, i.e. everything the next tile + mini step read.  (a2) the rest of the block column goes to the
+            // update stream, ahead of the next panel's own panel / in-panel kernels (stream order), so a panel boundary costs
+            // the chain one 4-CTA launch instead of a 250-CTA one that queues behind the bulk update.
+            RET(gemm_nt_sub(st, w.A + (size_t)c1 * ld + c1, ld, ncrit, ncrit, Wpan, NBO, Lpan, ld, kw, w.counts, 0, tW, tA));
+            CU(cudaStreamWaitEvent(w.upd, w.ev_panel[p & 1], 0));
+            if (p >= 1 && u1_used) CU(cudaStreamWaitEvent(w.upd, w.ev_urg[(p - 1) & 1], 0));
+            RET(gemm_nt_sub(w.upd, w.A + (size_t)(c1 + ncrit) * ld + c1, ld, rows2 - ncrit, na, Wpan + (size_t)ncrit * NBO, NBO, Lpan, ld,
+                            kw, w.counts, 0, tW, tA));
+            CU(cudaEventRecord(w.ev_a2, w.upd));
+            a2_pending = true;
+        } else {
+            RET(gemm_nt_sub(st, w.A + (size_t)c1 * ld + c1, ld, rows2, na, Wpan, NBO, Lpan, ld, kw, w.counts, 0, tW, tA));
+        }
         // (b) everything to the right of the next panel, in three pieces on two more streams (look-ahead depth 3, W in
         // four buffers): U1 = the block column of panel p+2 and U2 = that of panel p+3 on the URGENT stream, R = the
         // rest (lower tiles only, persistent SM-budgeted kernel) on the bulk stream.  Per block column q the updates are
@@ -1213,7 +1256,7 @@ inline int ldlt_factor_launch(LdltWs& w, cudaStream_t st) {
             const int na2 = min(NBO, rows3);
             const int o2 = c1 + na;
             RET(gemm_nt_sub(w.urg, w.A + (size_t)o2 * ld + o2, ld, rows3, na2, Wpan + (size_t)na * NBO, NBO, Lpan + (size_t)na * ld, ld,
-                            kw, w.counts));
+                            kw, w.counts, 0, tW, tA));
             CU(cudaEventRecord(w.ev_urg[p & 1], w.urg));
             u1_used = true;
             urg_used = true;
@@ -1224,7 +1267,7 @@ inline int ldlt_factor_launch(LdltWs& w, cudaStream_t st) {
                 const int o3 = o2 + na2;
                 if (r_prev) CU(cudaStreamWaitEvent(w.urg, w.ev_upd[(p - 1) & 1], 0));
                 RET(gemm_nt_sub(w.urg, w.A + (size_t)o3 * ld + o3, ld, rows4, na3, Wpan + (size_t)(na + na2) * NBO, NBO,
-                                Lpan + (size_t)(na + na2) * ld, ld, kw, w.counts));
+                                Lpan + (size_t)(na + na2) * ld, ld, kw, w.counts, 0, tW, tA));
                 const int rows5 = rows4 - na3;
                 if (rows5 > 0) {
                     const int o4 = o3 + na3;
@@ -1251,6 +1294,7 @@ inline int ldlt_factor_launch(LdltWs& w, cudaStream_t st) {
         }
     }
     // join the forked streams
+    if (a2_pending) CU(cudaStreamWaitEvent(st, w.ev_a2, 0));
     if (urg_used) {
         CU(cudaEventRecord(w.ev_urg[0], w.urg));
         CU(cudaStreamWaitEvent(st, w.ev_urg[0], 0));

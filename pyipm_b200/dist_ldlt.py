@@ -49,10 +49,15 @@ class CudaTileOps(object):
         self.device = torch.device('cuda', device)
         stream = _lib.torch_stream_handle(self.device)
         self.ctx = _lib.DenseLDLT(NB, device=device, stream=stream)     # carries device + stream for the tile calls
+        # the serial chain (diagonal factor, panel, broadcasts) runs on its own high-priority stream so that it overlaps
+        # with the trailing update of the previous block column (look-ahead 1)
+        self.s_chain = torch.cuda.Stream(device=self.device, priority=-1)
+        self.ctx_chain = _lib.DenseLDLT(NB, device=device, stream=self.s_chain.cuda_stream)
         self.tile_doubles = NB * NB + 4 * NB + NB // 2                   # LinvP + [dinv_a|dinv_b|d_a|d_b] + kind (ints)
         self.diag_size = self.b * self.b + self.nt * self.tile_doubles + 3
         self.perm = torch.empty(NB, dtype=torch.int32, device=self.device)
         self.wdiag = torch.empty((self.b, self.b), dtype=torch.float64, device=self.device)
+        self.wdiag_chain = torch.empty((self.b, self.b), dtype=torch.float64, device=self.device)
         self._idx_cache = {}
 
     def empty(self, *shape):
@@ -65,42 +70,36 @@ class CudaTileOps(object):
         off = self.b * self.b + t * self.tile_doubles
         return diag[off:off + NB * NB], diag[off + NB * NB:off + self.tile_doubles]
 
-    def factor_diag(self, Akk, diag):
-        """Akk: b x b view (row stride ld) of the working matrix; factored in place; fills `diag`."""
-        b, ld = self.b, Akk.stride(0)
-        es = 8
-        base = Akk.data_ptr()
-        for t in range(self.nt):
-            k0 = t * NB
-            linv, dblk = self._tile(diag, t)
-            self._lib.check(self.lib.b200ipm_ldlt_tile_factor(self.ctx.h, base + es * (k0 * ld + k0), ld, NB, linv.data_ptr(),
-                                                              dblk.data_ptr(), self.perm.data_ptr(), None))
-            rows = b - k0 - NB
-            if rows > 0:
-                pptr = base + es * ((k0 + NB) * ld + k0)
-                wptr = self.wdiag.data_ptr() + es * ((k0 + NB) * b + k0)
-                self._lib.check(self.lib.b200ipm_ldlt_panel(self.ctx.h, pptr, ld, rows, linv.data_ptr(), dblk.data_ptr(),
-                                                            None, wptr, b))
-                cptr = base + es * ((k0 + NB) * ld + (k0 + NB))
-                self._lib.check(self.lib.b200ipm_gemm_nt_update(self.ctx.h, cptr, ld, rows, rows, wptr, b, pptr, ld, NB, 1))
-        diag[:b * b].view(b, b).copy_(Akk)
+    # ---- stream plumbing of the look-ahead pipeline
+    def chain(self):
+        return torch.cuda.stream(self.s_chain)
+
+    def record(self):
+        e = torch.cuda.Event()
+        e.record(torch.cuda.current_stream(self.device))
+        return e
+
+    def wait(self, ev):
+        if ev is not None:
+            torch.cuda.current_stream(self.device).wait_event(ev)
+
+    def sync(self):
+        torch.cuda.synchronize(self.device)
+
+    def factor_diag(self, Akk, diag, chain=False):
+        """Akk: b x b view (row stride ld) of the working matrix; factored in place; fills `diag` (one C call)."""
+        ctx = self.ctx_chain if chain else self.ctx
+        wd = self.wdiag_chain if chain else self.wdiag
+        self._lib.check(self.lib.b200ipm_ldlt_block_factor(ctx.h, Akk.data_ptr(), Akk.stride(0), self.b, diag.data_ptr(),
+                                                           wd.data_ptr()))
         # (inertia is evaluated once, for all diagonal blocks together, by counts_all)
 
-    def panel(self, Bblk, diag):
+    def panel(self, Bblk, diag, chain=False):
         """Bblk: rows x b view (row stride ld) -> overwritten with L; returns W = L * D (rows x b, contiguous)."""
-        b, ld, rows = self.b, Bblk.stride(0), Bblk.shape[0]
-        es = 8
-        W = self.empty(rows, b)
-        base, wbase, lkk = Bblk.data_ptr(), W.data_ptr(), diag.data_ptr()
-        for t in range(self.nt):
-            k0 = t * NB
-            linv, dblk = self._tile(diag, t)
-            self._lib.check(self.lib.b200ipm_ldlt_panel(self.ctx.h, base + es * k0, ld, rows, linv.data_ptr(), dblk.data_ptr(),
-                                                        None, wbase + es * k0, b))
-            cols = b - k0 - NB
-            if cols > 0:   # remaining columns of this block column: B[:, k0+64:] -= W_t * L_kk[k0+64:, k0:k0+64]^T
-                self._lib.check(self.lib.b200ipm_gemm_nt_update(self.ctx.h, base + es * (k0 + NB), ld, rows, cols,
-                                                                wbase + es * k0, b, lkk + es * ((k0 + NB) * b + k0), b, NB, 0))
+        ctx = self.ctx_chain if chain else self.ctx
+        W = self.empty(Bblk.shape[0], self.b)
+        self._lib.check(self.lib.b200ipm_ldlt_block_panel(ctx.h, Bblk.data_ptr(), Bblk.stride(0), Bblk.shape[0], self.b,
+                                                          diag.data_ptr(), W.data_ptr()))
         return W
 
     def update(self, Cv, W, L):
@@ -121,6 +120,15 @@ class CudaTileOps(object):
                                                            W.stride(0), L.data_ptr(), L.stride(0), self.b, self.b, grid[0],
                                                            grid[1], coord[0], coord[1], li0, lj0))
 
+    def matvec_local(self, A0, Xc):
+        """Xc (nrhs x cols, contiguous) -> nrhs x rows:  row r = A0 * Xc[r]  with the repo's GEMV kernel"""
+        rows, cols = A0.shape
+        out = self.empty(Xc.shape[0], rows)
+        for r in range(Xc.shape[0]):
+            self._lib.check(self.lib.b200ipm_ldlt_gemv(self.ctx.h, A0.data_ptr(), A0.stride(0), rows, cols,
+                                                       Xc[r].data_ptr(), out[r].data_ptr()))
+        return out
+
     def counts_all(self, diags):
         """(pos, neg, zero) over all diagonal blocks: signs of the 1x1 / 2x2 blocks of D, one batched evaluation and
         one synchronisation."""
@@ -139,7 +147,7 @@ class CudaTileOps(object):
 
     def index(self, idx):
         """device index tensor (int64) from a NumPy index array, cached: no per-panel host-to-device copies"""
-        key = (idx.size, int(idx[0]) if idx.size else -1, int(idx[-1]) if idx.size else -1)
+        key = idx.tobytes()
         t = self._idx_cache.get(key)
         if t is None:
             t = torch.from_numpy(idx).to(self.device)
@@ -226,84 +234,102 @@ class BlockCyclicLDLT(object):
         self.ri, self.ci = ri, ci
 
     def factor(self):
-        """-> inertia (pos, neg, zero).  Collective: every rank must call it."""
-        ops, b, P, Q = self.ops, self.b, self.P, self.Q
-        import os
-        prof = bool(os.environ.get('B200IPM_DIST_PROF')) and self.A0.is_cuda
-        marks = []
+        """-> inertia (pos, neg, zero).  Collective: every rank must call it.
 
-        def mark(tag):
-            if prof:
-                e = torch.cuda.Event(enable_timing=True)
-                e.record()
-                marks.append((tag, e))
+        Pipeline with look-ahead 1 on two streams.  CHAIN stream (high priority), per block column k: wait until column k
+        carries every update through step k - 1; the owner of (k, k) factors the diagonal block and broadcasts its factor
+        data; process column k mod Q computes its rows of the panel; the panel is broadcast from its P owners straight
+        into per-owner slices of one buffer (no reshuffling copies).  UPDATE stream: as soon as panel k has arrived, the
+        blocks of block column k + 1 are updated FIRST (that is all the chain's next step waits for), then everything to
+        the right of it -- overlapped with the chain work and the broadcasts of step k + 1."""
+        ops, b, P, Q = self.ops, self.b, self.P, self.Q
         work = self.A0.clone()
-        self.diags, self.panels = [], []
-        tot = np.zeros(3, dtype=np.int64)
+        self.diags, self.panels, self._pgrp = [], [], []
+        if getattr(self, '_Wbuf', None) is None:
+            self._Wbuf = [ops.empty(max(self.nbk - 1, 1) * b, b) for _ in range(2)]
+        ev_look = None                 # block column k is up to date (recorded on the update stream)
+        ev_wfree = [None, None]        # the W buffer of parity k % 2 is no longer read by an update
+        ev_start = ops.record()        # `work` is a fresh clone made on the update stream
         for k in range(self.nbk):
             pk, qk = k % P, k % Q
-            mark('start')
-            # 1. diagonal block
-            diag = ops.empty(ops.diag_size)
-            if (self.p, self.q) == (pk, qk):
-                li, lj = self.rows_blk.index(k), self.cols_blk.index(k)
-                ops.factor_diag(work[li * b:(li + 1) * b, lj * b:(lj + 1) * b], diag)
-            mark('diag')
-            self._bcast(diag, self._rank_of(pk, qk))
-            mark('bcast_diag')
-            self.diags.append(diag)
             nbelow = self.nbk - (k + 1)
-            if nbelow == 0:
-                self.panels.append(None)
-                break
-            # 2. my part of the panel (process column qk only)
-            mine = [I for I in self.rows_blk if I > k]
-            Wloc = None
-            if self.q == qk and mine:
-                li0, lj = self.rows_blk.index(mine[0]), self.cols_blk.index(k)
-                Bv = work[li0 * b:, lj * b:(lj + 1) * b]
-                Wloc = ops.panel(Bv, diag)
-            mark('panel')
-            # 3. replicate the panel: owners (psrc, qk) broadcast [L | W] of their row blocks
-            Lfull = ops.empty(nbelow * b, b)
-            Wfull = ops.empty(nbelow * b, b)
-            for psrc in range(P):
-                blks = [I for I in range(k + 1, self.nbk) if I % P == psrc]
-                if not blks:
-                    continue
-                buf = ops.empty(2, len(blks) * b, b)
-                if self.p == psrc and self.q == qk:
-                    buf[0].copy_(Bv)
-                    buf[1].copy_(Wloc)
-                self._bcast(buf, self._rank_of(psrc, qk))
-                pos = ops.index(self._idx([I - (k + 1) for I in blks]))
-                Lfull.index_copy_(0, pos, buf[0])
-                Wfull.index_copy_(0, pos, buf[1])
-            self.panels.append(Lfull)
-            mark('bcast_panel')
-            # 4. trailing update of my blocks: A[I, J] -= W[I] L[J]^T for J > k, I >= J -- one launch per rank
+            groups = [[I for I in range(k + 1, self.nbk) if I % P == ps] for ps in range(P)]
+            offs = np.concatenate([[0], np.cumsum([len(gp) * b for gp in groups])]).astype(np.int64)
+            mine = groups[self.p]
+            with ops.chain():
+                ops.wait(ev_start if k == 0 else ev_look)
+                # 1. diagonal block
+                diag = ops.empty(ops.diag_size)
+                if (self.p, self.q) == (pk, qk):
+                    li, lj = self.rows_blk.index(k), self.cols_blk.index(k)
+                    ops.factor_diag(work[li * b:(li + 1) * b, lj * b:(lj + 1) * b], diag, chain=True)
+                self._bcast(diag, self._rank_of(pk, qk))
+                self.diags.append(diag)
+                if nbelow == 0:
+                    self._pgrp.append(None)
+                    break
+                # 2. my rows of the panel (process column qk only), 3. replicate it: owner (ps, qk) -> slice ps
+                Lall = ops.empty(nbelow * b, b)
+                ops.wait(ev_wfree[k % 2])
+                Wall = self._Wbuf[k % 2][:nbelow * b]
+                if self.q == qk and mine:
+                    li0, lj = self.rows_blk.index(mine[0]), self.cols_blk.index(k)
+                    Bv = work[li0 * b:, lj * b:(lj + 1) * b]
+                    Wloc = ops.panel(Bv, diag, chain=True)
+                    Lall[offs[self.p]:offs[self.p + 1]].copy_(Bv)
+                    Wall[offs[self.p]:offs[self.p + 1]].copy_(Wloc)
+                for ps in range(P):
+                    if groups[ps]:
+                        self._bcast(Lall[offs[ps]:offs[ps + 1]], self._rank_of(ps, qk))
+                        self._bcast(Wall[offs[ps]:offs[ps + 1]], self._rank_of(ps, qk))
+                self._pgrp.append((Lall, groups))
+                ev_panel = ops.record()
+            # 4. trailing update of my blocks: A[I, J] -= W[I] L[J]^T for J > k, I >= J; block column k + 1 first
+            ops.wait(ev_panel)
+            ev_look = None
             mycols = [J for J in self.cols_blk if J > k]
             if mine and mycols:
-                Wmine = Wfull.index_select(0, ops.index(self._idx([I - (k + 1) for I in mine])))   # my block rows, local order
-                Lmine = Lfull.index_select(0, ops.index(self._idx([J - (k + 1) for J in mycols])))  # L rows of my block cols
+                Wmine = Wall[offs[self.p]:offs[self.p + 1]]                      # my block rows, local order: contiguous
+                pos = np.concatenate([np.arange(b) + offs[J % P] + groups[J % P].index(J) * b for J in mycols])
+                Lmine = Lall.index_select(0, ops.index(pos))                       # L rows of my block columns
                 li0, lj0 = self.rows_blk.index(mine[0]), self.cols_blk.index(mycols[0])
-                ops.update_bc(work[li0 * b:, lj0 * b:], Wmine, Lmine, (P, Q), (self.p, self.q), li0, lj0)
-            mark('update')
-        mark('update')
-        if prof:
-            torch.cuda.synchronize()
-            acc = {}
-            for (t0, e0), (t1, e1) in zip(marks[:-1], marks[1:]):
-                if t1 != 'start':
-                    acc[t1] = acc.get(t1, 0.0) + e0.elapsed_time(e1)
-            print('rank', self.rank, 'phase ms', {k_: round(v, 1) for k_, v in acc.items()}, flush=True)
+                if mycols[0] == k + 1:
+                    ops.update_bc(work[li0 * b:, lj0 * b:(lj0 + 1) * b], Wmine, Lmine[:b], (P, Q), (self.p, self.q), li0, lj0)
+                    ev_look = ops.record()
+                    if len(mycols) > 1:
+                        ops.update_bc(work[li0 * b:, (lj0 + 1) * b:], Wmine, Lmine[b:], (P, Q), (self.p, self.q), li0, lj0 + 1)
+                else:
+                    ops.update_bc(work[li0 * b:, lj0 * b:], Wmine, Lmine, (P, Q), (self.p, self.q), li0, lj0)
+            if ev_look is None:
+                ev_look = ops.record()
+            ev_wfree[k % 2] = ops.record()
+        ops.sync()
         self.inertia = tuple(int(v) for v in ops.counts_all(self.diags))   # one synchronisation at the very end
         self._solver = None
         return self.inertia
 
+    def _global_panels(self):
+        """L panels in global row order (what the replicated solver imports), from the per-owner layout of factor()"""
+        out = []
+        b = self.b
+        for k, pg in enumerate(self._pgrp):
+            if pg is None:
+                out.append(None)
+                continue
+            Lall, groups = pg
+            order = [I for gp in groups for I in gp]                 # grouped position -> global block
+            inv = np.argsort(np.asarray(order))
+            pos = np.concatenate([np.arange(b) + int(i) * b for i in inv])
+            out.append(Lall.index_select(0, self.ops.index(pos)))
+        return out
+
     def matvec(self, Xt):
         """Y = A X for nrhs x n device tensors (distributed original matrix: local product + all-reduce)."""
-        part = torch.matmul(Xt[:, self.ci], self.A0.t())               # nrhs x (my rows)
+        Xc = Xt.index_select(1, self.ci).contiguous()
+        if hasattr(self.ops, 'matvec_local'):
+            part = self.ops.matvec_local(self.A0, Xc)                  # nrhs x (my rows), this repo's GEMV kernel
+        else:
+            part = torch.matmul(Xc, self.A0.t())                       # CPU reference backend (tests)
         Y = torch.zeros_like(Xt)
         Y[:, self.ri] = part
         if self.world > 1:
@@ -313,6 +339,7 @@ class BlockCyclicLDLT(object):
     def solve_device(self, Bt, nrefine=1):
         """Bt: nrhs x n device tensor -> X (nrhs x n device tensor)."""
         if self._solver is None:
+            self.panels = self._global_panels()
             self._solver = self.ops.make_solver(self.n, self.diags, self.panels)
         X = self._solver(Bt.clone())
         for _ in range(nrefine):

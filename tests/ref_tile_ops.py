@@ -18,7 +18,21 @@ class RefTileOps(object):
     def zeros(self, *shape):
         return torch.zeros(shape, dtype=torch.float64)
 
-    def factor_diag(self, Akk, diag):
+    # the look-ahead pipeline's stream plumbing degenerates to plain sequential execution on CPU
+    def chain(self):
+        import contextlib
+        return contextlib.nullcontext()
+
+    def record(self):
+        return None
+
+    def wait(self, ev):
+        pass
+
+    def sync(self):
+        pass
+
+    def factor_diag(self, Akk, diag, chain=False):
         b = self.b
         T = np.tril(Akk.numpy())
         T = T + np.tril(T, -1).T
@@ -32,7 +46,7 @@ class RefTileOps(object):
         b = self.b
         return diag[:b * b].view(b, b).numpy(), diag[b * b:2 * b * b].view(b, b).numpy()
 
-    def panel(self, Bblk, diag):
+    def panel(self, Bblk, diag, chain=False):
         lu, d = self._unpack(diag)
         B = Bblk.numpy()
         W = np.linalg.solve(lu, B.T).T

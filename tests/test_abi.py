@@ -56,3 +56,19 @@ def test_product_does_not_import_the_oracle():
             if fn.endswith(('.py', '.cu', '.cuh', '.h')):
                 src = open(os.path.join(dirpath, fn)).read()
                 assert not re.search(r'^\s*(from|import)\s+oracle', src, flags=re.M), fn
+
+
+def test_integration_md_stub_matches_the_header():
+    """The ctypes stub printed in INTEGRATION.md must stay in step with include/b200ipm.h: its struct mirrors are executed
+    here and their sizes compared with the library's."""
+    import ctypes as C
+    import re
+    text = open(os.path.join(ROOT, 'INTEGRATION.md')).read()
+    m = re.search(r"class _Params\(C\.Structure\):.*?(?=\nassert _b200)", text, re.S)
+    assert m, 'stub not found'
+    import numpy as np
+    ns = {'C': C, 'np': np}
+    exec(m.group(0), ns)
+    lib = _lib.load()
+    assert lib.b200ipm_struct_size(0) == C.sizeof(ns['_Params'])
+    assert lib.b200ipm_struct_size(1) == C.sizeof(ns['_StepInfo'])

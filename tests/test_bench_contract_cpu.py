@@ -11,15 +11,16 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_reference_arm_prints_one_contract_line():
-    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '0'],
-                         capture_output=True, text=True, timeout=900, cwd=ROOT)
+    # --ref-test-size: the same code path on a toy instance (the real arm runs ONE full config-3 step: minutes of CPU)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '10', '--warmup', '3',
+                          '--ref-test-size', '128', '--ref-skip-sample'], capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.strip().startswith('{')]
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d['impl'] == 'reference' and d['metric'] == 'newton_steps_per_sec' and d['unit'] == 'steps/s'
     assert d['higher_is_better'] is True and d['vs_baseline'] is None and d['dtype'] == 'f64' and d['data'] == 'synthetic'
-    assert d['value'] > 0 and d['steps'] == 1 and d['warmup'] == 0
+    assert d['value'] > 0 and d['steps'] == 1 and d['warmup'] == 0 and d['steps_requested'] == 10      # one real step, said so
     assert 'workload' in d['config'] and 'config3' in d['config']['workload']
     cb = d['cpu_baseline']
     assert cb['kind'] == 'port' and cb['cores'] >= 1 and cb['value'] == d['value'] and 'sample' in cb
