@@ -52,7 +52,7 @@ struct LdltWs {
     cudaStream_t side = nullptr;   // trailing updates beyond the next panel run here, overlapped with the next panel
     cudaEvent_t ev_panel[2] = {nullptr, nullptr}, ev_upd[2] = {nullptr, nullptr};
     cudaStream_t upd = nullptr;    // in-panel updates off the chain (everything of a tile step but the next diagonal tile)
-    cudaEvent_t ev_tile = nullptr, ev_mini = nullptr, ev_urest = nullptr, ev_a2 = nullptr;
+    cudaEvent_t ev_tile = nullptr, ev_mini = nullptr, ev_urest = nullptr, ev_a2 = nullptr, ev_corner = nullptr;
     int split_a = 1;               // B200IPM_LDLT_SPLITA=0: the whole boundary update on the chain stream
     int* sig = nullptr;            // device word set to 1 when tile step sig_tile starts (baked into the graph)
     int sig_tile = -1;
@@ -110,6 +110,7 @@ inline int ldlt_alloc(LdltWs& w, int n, cudaStream_t st, bool background = false
     CU(cudaEventCreateWithFlags(&w.ev_mini, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&w.ev_urest, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&w.ev_a2, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&w.ev_corner, cudaEventDisableTiming));
     { const char* e = getenv("B200IPM_LDLT_SPLITA"); if (e) w.split_a = atoi(e); }
     { const char* e = getenv("B200IPM_LDLT_MINI"); if (e) w.use_mini = atoi(e); }
     { const char* e = getenv("B200IPM_TILE_BLOCKED"); if (e) w.tile_blocked = atoi(e); }
@@ -173,6 +174,7 @@ inline void ldlt_free(LdltWs& w) {
     if (w.ev_mini) cudaEventDestroy(w.ev_mini);
     if (w.ev_urest) cudaEventDestroy(w.ev_urest);
     if (w.ev_a2) cudaEventDestroy(w.ev_a2);
+    if (w.ev_corner) cudaEventDestroy(w.ev_corner);
     if (w.cap) cudaStreamDestroy(w.cap);
     for (int i = 0; i < 2; i++) { if (w.ev_panel[i]) cudaEventDestroy(w.ev_panel[i]); if (w.ev_upd[i]) cudaEventDestroy(w.ev_upd[i]); }
     cudaFree(w.LinvP); cudaFree(w.dinfo); cudaFree(w.kind); cudaFree(w.counts);
@@ -340,6 +342,8 @@ __device__ __forceinline__ void tile_fast_blocked(double* __restrict__ Tf, doubl
     long long cy_x = 0, cy_t = clock64();
 #endif
     // (1a) an 8 x 8 diagonal block, by ONE thread entirely in registers: no shuffle, no barrier on the serial chain
+    // (~2200 cycles per block, TILE_PROF; a warp-cooperative version -- 36 elements over the lanes, three shuffle rounds per
+    // pivot -- was measured at 31 us per tile against 19: shuffle latency on the dependent chain costs more than it saves)
     auto diag_block = [&](const int c0) {
         double a[8][8];
 #pragma unroll
@@ -392,7 +396,7 @@ __device__ __forceinline__ void tile_fast_blocked(double* __restrict__ Tf, doubl
         cp[0] = acc0;
         cp[1] = acc1;
     };
-    // X = L^-1 one block ROW at a time, by warp 7, concurrently with the elimination of the following block columns
+    // X = L^-1 one block ROW at a time, by warps 6 and 7 (block columns of even / odd index), concurrently with the elimination of the following block columns
     // (row block i of L is final once diagonal block i is factored, i.e. at the barrier that opens iteration i):
     //   X_ii = inv(L_ii),   X_ij = -X_ii * sum_{k=j}^{i-1} L_ik X_kj   (j < i; the X_kj are earlier block rows)
     auto inverse_block_row = [&](const int i) {
@@ -414,7 +418,7 @@ __device__ __forceinline__ void tile_fast_blocked(double* __restrict__ Tf, doubl
                 if (r >= c) Xf[(b0 + r) * NBP + b0 + c] = x[r];
         }
         __syncwarp();
-        for (int j = 0; j < i; j++) {
+        for (int j = (warp & 1); j < i; j += 2) {      // both inverting warps hold X_ii (identical values); they split the block columns
             double s0 = 0.0, s1 = 0.0;
             for (int k = j; k < i; k++) {
 #pragma unroll
@@ -439,13 +443,19 @@ __device__ __forceinline__ void tile_fast_blocked(double* __restrict__ Tf, doubl
             __syncwarp();
         }
     };
-    constexpr int NUPD = TILE_THREADS / 32 - 1;        // warps 0 .. 6 eliminate, warp 7 inverts
+    constexpr int NUPD = TILE_THREADS / 32 - 2;        // warps 0 .. 5 eliminate, warps 6 and 7 invert
     if (warp == 0 && lane == 0) diag_block(0);
 #pragma unroll 1
     for (int kb = 0; kb < NB / 8; kb++) {
         const int c0 = 8 * kb;
+#ifdef TILE_PROF
+        const long long pp0 = clock64();
+#endif
         __syncthreads();                   // diagonal block kb is factored; the update behind block kb-1 is complete
-        if (warp == NUPD) {
+#ifdef TILE_PROF
+        const long long pp1 = clock64();
+#endif
+        if (warp >= NUPD) {
             inverse_block_row(kb);         // reads only FINAL entries of T (columns < c0 + 8 of rows c0 .. c0 + 7) and writes X
             continue;                      // next: the barrier that opens iteration kb + 1
         }
@@ -473,6 +483,9 @@ __device__ __forceinline__ void tile_fast_blocked(double* __restrict__ Tf, doubl
             }
         }
         asm volatile("bar.sync 1, %0;\n" ::"n"(NUPD * 32) : "memory");      // the eliminating warps only
+#ifdef TILE_PROF
+        const long long pp2 = clock64();
+#endif
         // (2) rank-8 update of the lower tiles behind the block.  Warp 0 takes the next diagonal tile first and thread 0
         // goes straight on to factor it (pinv and the next sda entries are free again: (1b) is over), overlapped with
         // the other six warps updating the remaining tiles.
@@ -482,9 +495,18 @@ __device__ __forceinline__ void tile_fast_blocked(double* __restrict__ Tf, doubl
             if (warp == 0) {
                 update_tile(kb, 0);
                 __syncwarp();
+#ifdef TILE_PROF
+                const long long pp3 = clock64();
+#endif
                 if (lane == 0) diag_block(c0 + 8);
+#ifdef TILE_PROF
+                if (lane == 0) printf("TILE_PROF kb=%d wait_top=%lld rows_below=%lld upd0=%lld diag=%lld\n", kb, pp1 - pp0, pp2 - pp1, pp3 - pp2, clock64() - pp3);
+#endif
             } else {
                 for (int t = warp; t < ntiles; t += NUPD - 1) update_tile(kb, t);
+#ifdef TILE_PROF
+                if (warp == 1 && lane == 0) printf("TILE_PROF kb=%d warp1 upd=%lld (tiles %d)\n", kb, clock64() - pp2, ntiles);
+#endif
             }
         }
     }
@@ -1009,13 +1031,15 @@ __global__ void __launch_bounds__(128) ldlt_panel_kernel(double* __restrict__ B,
     trace_end(trc);
 }
 
-// Chain shortcut ("mini" step).  One CTA, 8 warps: the panel computation of ldlt_panel_kernel for the 64 rows right
+// Chain shortcut ("mini" step).  MINI_CTAS CTAs of 8 warps (one SM's DMMA pipe needs 2.1 us per 64^3 product: the second
+// product, T -= W L', is split by rows over the CTAs; each computes W = B LinvP' itself because it needs all of L): the panel computation of ldlt_panel_kernel for the 64 rows right
 // below tile k (W = B LinvP', L = W D^-1, stored exactly as the panel kernel stores them), followed by the update of the
 // NEXT diagonal tile  T -= W L'.  Tile k+1 can then be factored while the rest of panel step k (all other rows, all
 // other tiles of the in-panel update) runs on the update stream: the serial chain per tile step is tile + mini instead
 // of tile + panel + update.  Latency-oriented: B, LinvP and T are fetched together with cp.async at entry, every warp
 // owns one 8-row fragment strip (half the DMMA chain of a 4-warp layout).
 constexpr int MINI_THREADS = 256;
+constexpr int MINI_CTAS = 4;      // the update of the next diagonal tile is split over four CTAs (the first product is redundant)
 constexpr int MINI_SMEM = 3 * NB * P_LDS * 8;
 __global__ void __launch_bounds__(MINI_THREADS) ldlt_mini_kernel(double* __restrict__ B, int ld, int rows,
                                                                  const double* __restrict__ LinvP,
@@ -1036,7 +1060,7 @@ __global__ void __launch_bounds__(MINI_THREADS) ldlt_mini_kernel(double* __restr
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, tg = lane & 3;
     const int nn = min(NB, rows);
-    const int trc = (tid == 0) ? trace_begin(TR_MINI, ctrl) : -1;
+    const int trc = (tid == 0 && blockIdx.x == 0) ? trace_begin(TR_MINI, ctrl) : -1;
     if (tid < NB) { sia[tid] = dinv_a[tid]; sib[tid] = dinv_b[tid]; skd[tid] = kind[tid]; }
 #pragma unroll
     for (int i = 0; i < 8; i++) {
@@ -1067,13 +1091,14 @@ __global__ void __launch_bounds__(MINI_THREADS) ldlt_mini_kernel(double* __restr
             for (int nt = 0; nt < 8; nt++) dmma884(acc[nt][0], acc[nt][1], af, bf[nt]);
         }
     };
-    product();                       // W = B * LinvP'
+    product();                       // W = B * LinvP'   (every CTA: the second product needs all of L)
     __syncthreads();                 // everybody is done reading As / Bs
 #pragma unroll
     for (int nt = 0; nt < 8; nt++)
 #pragma unroll
         for (int e = 0; e < 2; e++) As[(warp * 8 + g) * P_LDS + nt * 8 + tg * 2 + e] = acc[nt][e];
     __syncthreads();
+    const int q = blockIdx.x;        // this CTA's quarter: rows 16 q .. 16 q + 15 of W / L / T
     {
         const int col = tid & 63;
         const int k = skd[col];
@@ -1086,22 +1111,33 @@ __global__ void __launch_bounds__(MINI_THREADS) ldlt_mini_kernel(double* __restr
             const double wv = As[r * P_LDS + col];
             const double lv = wv * ia + As[r * P_LDS + nbr] * ibn;
             Bs[r * P_LDS + col] = lv;                 // rows >= nn are exact zeros (zero-filled loads)
-            if (r < nn) {
+            if (r < nn && (r >> 4) == q) {
                 Wout[(size_t)r * ldw + col] = wv;
                 B[(size_t)r * ld + col] = lv;
             }
         }
     }
     __syncthreads();
-    product();                       // W * L'
+    // T[16 q .. 16 q + 15, :] -= W L' : warp w -> 8-row fragment (w & 1), column blocks 2 (w >> 1), 2 (w >> 1) + 1
     {
-        const int i = warp * 8 + g;
+        double a2[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+        const int rr = 16 * q + 8 * (warp & 1) + g;
+        const int cb = 2 * (warp >> 1);
+        const double* as2 = As + rr * P_LDS + tg;
+        const double* bs2 = Bs + (cb * 8 + g) * P_LDS + tg;
 #pragma unroll
-        for (int nt = 0; nt < 8; nt++)
+        for (int kk = 0; kk < 16; kk++) {
+            const double af = as2[kk * 4];
+            const double b0 = bs2[kk * 4], b1 = bs2[8 * P_LDS + kk * 4];
+            dmma884(a2[0][0], a2[0][1], af, b0);
+            dmma884(a2[1][0], a2[1][1], af, b1);
+        }
+#pragma unroll
+        for (int nt = 0; nt < 2; nt++)
 #pragma unroll
             for (int e = 0; e < 2; e++) {
-                const int j = nt * 8 + tg * 2 + e;
-                if (i < nn && j < nn) T[(size_t)i * ld + j] = Ts[i * P_LDS + j] - acc[nt][e];
+                const int j = (cb + nt) * 8 + tg * 2 + e;
+                if (rr < nn && j < nn) T[(size_t)rr * ld + j] = Ts[rr * P_LDS + j] - a2[nt][e];
             }
     }
     __syncthreads();
@@ -1170,6 +1206,7 @@ inline int ldlt_factor_launch(LdltWs& w, cudaStream_t st) {
         double* Wb = (p % 4 == 0) ? w.Wp : ((p % 4 == 1) ? w.Wp2 : ((p % 4 == 2) ? w.Wp3 : w.Wp4));
         const TmaMat* tW = w.use_tma ? &w.tmW[p % 4] : nullptr;
         const TmaMat* tA = w.use_tma ? &w.tmA : nullptr;
+        bool corner_pre = false;
         for (int k0 = c0; k0 < c1; k0 += NB) {
             const int k = k0 / NB, nb = min(NB, n - k0), k1 = k0 + nb;
             double* Akk = w.A + (size_t)k0 * ld + k0;
@@ -1199,7 +1236,7 @@ inline int ldlt_factor_launch(LdltWs& w, cudaStream_t st) {
                 if (mcols > 0) RET(gemm_nt_sub(st, C11, ld, rows, mcols, Wt, NBO, B, ld, NB, w.counts, 0, tW, tA));
             } else {
                 CU(cudaEventRecord(w.ev_tile, st));
-                ldlt_mini_kernel<<<1, MINI_THREADS, MINI_SMEM, st>>>(B, ld, rows, Lk, ia + k0, ib + k0, w.kind + k0, Wt, NBO, C11, w.counts);
+                ldlt_mini_kernel<<<MINI_CTAS, MINI_THREADS, MINI_SMEM, st>>>(B, ld, rows, Lk, ia + k0, ib + k0, w.kind + k0, Wt, NBO, C11, w.counts);
                 LAUNCHED();
                 CU(cudaEventRecord(w.ev_mini, st));
                 CU(cudaStreamWaitEvent(w.upd, w.ev_tile, 0));
@@ -1211,6 +1248,17 @@ inline int ldlt_factor_launch(LdltWs& w, cudaStream_t st) {
                 CU(cudaEventRecord(w.ev_urest, w.upd));
                 upd_pending = true;
                 a2_pending = false;      // ev_urest is recorded after (a2) on the same stream: waiting for it covers (a2)
+                if (w.split_a && k1 == c1 - NB && c1 - c0 == NBO && n - c1 > 2 * NB) {
+                    // the NEXT tile is the last of this outer panel.  The 128 x 128 corner of the next panel -- all the chain
+                    // reads after the boundary -- already gets the contributions of the first three tile steps here, on the
+                    // update stream, while the last tile is being factored; the boundary itself then only adds the last
+                    // step's rank-64 term (4 CTAs, K = 64 instead of K = 256).
+                    if (p >= 1 && u1_used) CU(cudaStreamWaitEvent(w.upd, w.ev_urg[(p - 1) & 1], 0));
+                    RET(gemm_nt_sub(w.upd, w.A + (size_t)c1 * ld + c1, ld, 2 * NB, 2 * NB, Wb + (size_t)c1 * NBO, NBO,
+                                    w.A + (size_t)c1 * ld + c0, ld, 3 * NB, w.counts, 0, tW, tA));
+                    CU(cudaEventRecord(w.ev_corner, w.upd));
+                    corner_pre = true;
+                }
             }
         }
         if (upd_pending) {
@@ -1233,7 +1281,12 @@ inline int ldlt_factor_launch(LdltWs& w, cudaStream_t st) {
             // tile after that, i.e. everything the next tile + mini step read.  (a2) the rest of the block column goes to the
             // update stream, ahead of the next panel's own panel / in-panel kernels (stream order), so a panel boundary costs
             // the chain one 4-CTA launch instead of a 250-CTA one that queues behind the bulk update.
-            RET(gemm_nt_sub(st, w.A + (size_t)c1 * ld + c1, ld, ncrit, ncrit, Wpan, NBO, Lpan, ld, kw, w.counts, 0, tW, tA));
+            if (corner_pre) {
+                CU(cudaStreamWaitEvent(st, w.ev_corner, 0));
+                RET(gemm_nt_sub(st, w.A + (size_t)c1 * ld + c1, ld, ncrit, ncrit, Wpan + 3 * NB, NBO, Lpan + 3 * NB, ld, NB, w.counts, 0, tW, tA));
+            } else {
+                RET(gemm_nt_sub(st, w.A + (size_t)c1 * ld + c1, ld, ncrit, ncrit, Wpan, NBO, Lpan, ld, kw, w.counts, 0, tW, tA));
+            }
             CU(cudaStreamWaitEvent(w.upd, w.ev_panel[p & 1], 0));
             if (p >= 1 && u1_used) CU(cudaStreamWaitEvent(w.upd, w.ev_urg[(p - 1) & 1], 0));
             RET(gemm_nt_sub(w.upd, w.A + (size_t)(c1 + ncrit) * ld + c1, ld, rows2 - ncrit, na, Wpan + (size_t)ncrit * NBO, NBO, Lpan, ld,

@@ -491,3 +491,53 @@ def test_device_callables_mode():
     assert pd.signal == pl.signal and pd.iter_count == pl.iter_count
     assert np.linalg.norm(xd - xl) <= 1e-6 * (1 + np.linalg.norm(xl))
     assert np.linalg.norm(ld - ll) <= 1e-5 * (1 + np.linalg.norm(ll))
+
+
+def test_adversarial_singular_leading_tiles_at_size():
+    """Pivoting is confined to 64 x 64 diagonal tiles.  Adversarial case for that design: a LINEAR objective with equality
+    constraints only (example 8's structure at D = 1024, M = 256): d2L = -sum lda_e U'U has rank <= M, so with lda = 0 the
+    leading D x D block of the KKT matrix is EXACTLY zero -- all 16 leading tiles singular.  The reference sees rcond <= eps
+    (eq-block regularisation) and shifts; the engine must take the same decisions and produce the same direction."""
+    rng = np.random.default_rng(8)
+    D, M = 1024, 256
+    A = rng.standard_normal((M, D)) / np.sqrt(D)
+    U = rng.standard_normal((M, D)) / np.sqrt(D)
+    xs = 0.5 * rng.standard_normal(D)
+    ux = U @ xs
+    b = A @ xs + 0.5 * ux * ux
+    prob = problems.QuadProblem(np.zeros((D, D)), rng.standard_normal(D), 0.0, A=A, U=U, b=b, x0=xs + 0.05 * rng.standard_normal(D))
+    tr = []
+    o = OracleIPM(x0=prob.x0.copy(), verbosity=-1, niter=1, miter=2, trace=tr, lda0=np.zeros(M), **prob.callables())
+    with np.errstate(all='ignore'):
+        o.solve()
+    assert tr[0]['reg']['eq_reg'] and tr[0]['reg']['rcond'] <= o.eps
+    for flags in (6, 1):
+        eng = make_engine(prob, flags=flags)
+        nu_b, de_b = 10.0, 0.0
+        for k, st in enumerate(tr):
+            eng.set_state(st['x'], None, st['lda'], st['mu'], nu_b, de_b)
+            eng.set_mu_host(st['mu_host'])
+            dz, info = eng.direction()
+            assert info.delta == st['delta'] and info.n_factor == st['reg']['n_eig'], (flags, k, info.asdict(), st['reg'])
+            assert info.eq_reg == int(st['reg']['eq_reg'])
+            assert info.n_neg == M and info.n_zero == 0
+            assert relinf(dz, st['dz']) < 1e-7, (flags, k, relinf(dz, st['dz']))
+            nu_b, de_b = st['nu_after'], st['delta']
+        eng.close()
+
+
+def test_config2_own_init_lambda_with_dependent_box_constraints():
+    """Config 2's two-sided box gives EXACTLY dependent inequality gradients (dci = [E, -E]).  The reference's own
+    pinv-based init_lambda blows up on it, so the parity test passes lda0 explicitly; here the engine
+    starts from ITS OWN init_lambda (regularised least squares on the device): finite multipliers, and the convex QP
+    converges to the same minimiser as the run started from the explicit multipliers."""
+    prob = problems.make_qp(D=256, M=64, nbox=128, seed=3)
+    p1 = IPM(x0=prob.x0.copy(), f=prob, Ftol=1.0E-10, Ktol=1.0E-6, verbosity=-1, niter=20)
+    x1, s1, l1, f1, k1 = p1.solve()
+    s0 = np.maximum(prob.ci(prob.x0), 1.0E-4)
+    lda0 = np.concatenate([np.zeros(prob.neq), 0.2 / s0])
+    p2 = IPM(x0=prob.x0.copy(), f=prob, lda0=lda0, Ftol=1.0E-10, Ktol=1.0E-6, verbosity=-1, niter=20)
+    x2, s2, l2, f2, k2 = p2.solve()
+    assert np.all(np.isfinite(l1)) and p1.signal in (1, 2) and p2.signal in (1, 2)
+    assert np.linalg.norm(x1 - x2) <= 1e-4 * (1.0 + np.linalg.norm(x2))
+    assert abs(f1 - f2) <= 1e-6 * (1.0 + abs(f2))
