@@ -48,7 +48,7 @@ struct LdltWs {
     double* Wp3 = nullptr;
     double* Wp4 = nullptr;
     cudaStream_t urg = nullptr;    // urgent pieces of the trailing update (block columns of the next two panels)
-    cudaEvent_t ev_urg[2] = {nullptr, nullptr};
+    cudaEvent_t ev_urg[2] = {nullptr, nullptr}, ev_slice[2] = {nullptr, nullptr};
     cudaStream_t side = nullptr;   // trailing updates beyond the next panel run here, overlapped with the next panel
     cudaEvent_t ev_panel[2] = {nullptr, nullptr}, ev_upd[2] = {nullptr, nullptr};
     cudaStream_t upd = nullptr;    // in-panel updates off the chain (everything of a tile step but the next diagonal tile)
@@ -118,6 +118,7 @@ inline int ldlt_alloc(LdltWs& w, int n, cudaStream_t st, bool background = false
         CU(cudaEventCreateWithFlags(&w.ev_panel[i], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&w.ev_upd[i], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&w.ev_urg[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&w.ev_slice[i], cudaEventDisableTiming));
     }
     CU(cudaMalloc(&w.LinvP, sizeof(double) * (size_t)w.nblk * NB * NB));
     CU(cudaMalloc(&w.dinfo, sizeof(double) * 4 * npad));
@@ -147,9 +148,17 @@ inline int ldlt_alloc(LdltWs& w, int n, cudaStream_t st, bool background = false
         if (c) w.tc_ctas = atoi(c);
         if (w.tc_update) {
             RET(oz_upd_alloc(w.tcu, n, 256));
+            // tile lists of every piece the factorisation will launch (they must exist before the graph is captured)
             for (int c0 = 0; c0 < n; c0 += 256) {
-                const int rows5 = n - std::min(c0 + 256, n) - 3 * 256;
-                if (rows5 >= 256) RET(oz_upd_tiles(w.tcu, rows5));
+                const int c1 = std::min(c0 + 256, n), rows2 = n - c1;
+                const int na = std::min(256, rows2), rows3 = rows2 - na;
+                if (rows3 <= 0) continue;
+                const int na2 = std::min(256, rows3), rows4 = rows3 - na2;
+                RET(oz_upd_tiles(w.tcu, rows3, na2));
+                if (rows4 <= 0) continue;
+                const int na3 = std::min(256, rows4), rows5 = rows4 - na3;
+                RET(oz_upd_tiles(w.tcu, rows4, na3));
+                if (rows5 > 0) RET(oz_upd_tiles(w.tcu, rows5, rows5));
             }
         }
     }
@@ -166,7 +175,7 @@ inline void ldlt_free(LdltWs& w) {
     cudaFree(w.A); cudaFree(w.Wp); cudaFree(w.Wp2); cudaFree(w.Wp3); cudaFree(w.Wp4);
     oz_upd_free(w.tcu);
     if (w.urg) cudaStreamDestroy(w.urg);
-    for (int i = 0; i < 2; i++) if (w.ev_urg[i]) cudaEventDestroy(w.ev_urg[i]);
+    for (int i = 0; i < 2; i++) { if (w.ev_urg[i]) cudaEventDestroy(w.ev_urg[i]); if (w.ev_slice[i]) cudaEventDestroy(w.ev_slice[i]); }
     if (w.gexec) cudaGraphExecDestroy(w.gexec);
     if (w.side) cudaStreamDestroy(w.side);
     if (w.upd) cudaStreamDestroy(w.upd);
@@ -1308,8 +1317,19 @@ inline int ldlt_factor_launch(LdltWs& w, cudaStream_t st) {
             CU(cudaStreamWaitEvent(w.urg, w.ev_panel[p & 1], 0));
             const int na2 = min(NBO, rows3);
             const int o2 = c1 + na;
-            RET(gemm_nt_sub(w.urg, w.A + (size_t)o2 * ld + o2, ld, rows3, na2, Wpan + (size_t)na * NBO, NBO, Lpan + (size_t)na * ld, ld,
-                            kw, w.counts, 0, tW, tA));
+            // tcgen05 path: the digits of W / -L rows o2 .. n of this panel are produced ONCE (urgent stream) and shared by the
+            // three pieces U1, U2 and R, which address them through 128-row block offsets
+            const bool tc = w.tc_update && kw == NBO && na == NBO && (rows3 % OZ_BM) == 0 && rows3 >= 2 * NBO;
+            if (tc) {
+                RET(oz_panel_slice(w.urg, rows3, Wpan + (size_t)na * NBO, NBO, Lpan + (size_t)na * ld, ld, kw, w.tcu, p % OZ_UPD_NBUF,
+                                   w.counts + 6, w.counts));
+                CU(cudaEventRecord(w.ev_slice[p & 1], w.urg));
+                RET(oz_panel_update(w.urg, w.A + (size_t)o2 * ld + o2, ld, rows3, na2, 0, kw, w.tcu, p % OZ_UPD_NBUF, w.counts + 6,
+                                    w.counts, 0));
+            } else {
+                RET(gemm_nt_sub(w.urg, w.A + (size_t)o2 * ld + o2, ld, rows3, na2, Wpan + (size_t)na * NBO, NBO, Lpan + (size_t)na * ld, ld,
+                                kw, w.counts, 0, tW, tA));
+            }
             CU(cudaEventRecord(w.ev_urg[p & 1], w.urg));
             u1_used = true;
             urg_used = true;
@@ -1319,16 +1339,22 @@ inline int ldlt_factor_launch(LdltWs& w, cudaStream_t st) {
                 const int na3 = min(NBO, rows4);
                 const int o3 = o2 + na2;
                 if (r_prev) CU(cudaStreamWaitEvent(w.urg, w.ev_upd[(p - 1) & 1], 0));
-                RET(gemm_nt_sub(w.urg, w.A + (size_t)o3 * ld + o3, ld, rows4, na3, Wpan + (size_t)(na + na2) * NBO, NBO,
-                                Lpan + (size_t)(na + na2) * ld, ld, kw, w.counts, 0, tW, tA));
+                if (tc && na2 == NBO) {
+                    RET(oz_panel_update(w.urg, w.A + (size_t)o3 * ld + o3, ld, rows4, na3, na2 / OZ_BM, kw, w.tcu, p % OZ_UPD_NBUF,
+                                        w.counts + 6, w.counts, 0));
+                } else {
+                    RET(gemm_nt_sub(w.urg, w.A + (size_t)o3 * ld + o3, ld, rows4, na3, Wpan + (size_t)(na + na2) * NBO, NBO,
+                                    Lpan + (size_t)(na + na2) * ld, ld, kw, w.counts, 0, tW, tA));
+                }
                 const int rows5 = rows4 - na3;
                 if (rows5 > 0) {
                     const int o4 = o3 + na3;
                     CU(cudaStreamWaitEvent(sd, w.ev_panel[p & 1], 0));
-                    if (w.tc_update && rows5 >= 256 && kw == NBO && na == NBO && na2 == NBO && na3 == NBO) {
-                        // the panel-update contraction on tcgen05 (int8 error-free split, 21 slice pairs, in place)
-                        RET(oz_update_lower(sd, w.A + (size_t)o4 * ld + o4, ld, rows5, Wpan + (size_t)(na + na2 + na3) * NBO, NBO,
-                                            Lpan + (size_t)(na + na2 + na3) * ld, ld, kw, w.tcu, w.counts + 6, w.counts, w.tc_ctas));
+                    if (tc && na2 == NBO && na3 == NBO) {
+                        // the bulk of the panel-update contraction on tcgen05 (int8 error-free split, 21 slice pairs, in place)
+                        CU(cudaStreamWaitEvent(sd, w.ev_slice[p & 1], 0));
+                        RET(oz_panel_update(sd, w.A + (size_t)o4 * ld + o4, ld, rows5, rows5, (na2 + na3) / OZ_BM, kw, w.tcu,
+                                            p % OZ_UPD_NBUF, w.counts + 6, w.counts, w.tc_ctas));
                     } else {
                         GemmArgs u{};
                         u.C = w.A + (size_t)o4 * ld + o4; u.ldc = ld; u.Cin = u.C; u.ldcin = ld; u.n = rows5; u.m = rows5;

@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(256) oz_slice_kernel(const OzSliceArgs a) {
         }
 #pragma unroll
         for (int p = 0; p < OZ_NS; p++) {
-            *reinterpret_cast<uint4*>(a.L + base + (size_t)p * OZ_CHUNK) = make_uint4(wl[p][0], wl[p][1], wl[p][2], wl[p][3]);
+            if (a.L) *reinterpret_cast<uint4*>(a.L + base + (size_t)p * OZ_CHUNK) = make_uint4(wl[p][0], wl[p][1], wl[p][2], wl[p][3]);
             if (write_r)
                 *reinterpret_cast<uint4*>(a.R + base + (size_t)p * OZ_CHUNK) = make_uint4(wr[p][0], wr[p][1], wr[p][2], wr[p][3]);
         }
@@ -292,7 +292,8 @@ struct OzGemmArgs {
     // (slices of W, row exponents rexp), the B side from R (slices of -Lpanel, row exponents rexp_col); `lower`: only
     // elements i >= j are authoritative, read from / written to the lower triangle in place, no mirror
     const int* rexp_col;   // null: same as rexp
-    int lower;
+    int lower;             // 0: upper triangle authoritative + mirror (SYRK); 1: lower triangle only, in place
+    int ncols;             // > 0: only columns j < ncols exist (block-column update); 0: square (n)
     const int* ctrl;       // optional LDL^T control block (ctrl[4] != 0: abandoned, return at once)
 };
 
@@ -332,6 +333,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzGemmArgs
     const int ti = tile.x, tj = tile.y;
     const int row0 = ti * OZ_BM, col0 = tj * BN;
     const int* __restrict__ rexp_c = a.rexp_col ? a.rexp_col : a.rexp;
+    const int ncol = a.ncols > 0 ? a.ncols : a.n;
 
     if (tid == 0) {
         s_dead = 0;
@@ -343,7 +345,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzGemmArgs
         oz_mbar_init(oz_smem_u32(&bar_tempty), 4);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
-    for (int c = tid; c < BN; c += OZ_THREADS) s_cscale[c] = scalbn(1.0, ((col0 + c < a.n) ? rexp_c[col0 + c] : 0) - 7);
+    for (int c = tid; c < BN; c += OZ_THREADS) s_cscale[c] = scalbn(1.0, ((col0 + c < ncol) ? rexp_c[col0 + c] : 0) - 7);
     if (warp == 0) {
         const uint32_t ncols = 512;
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(oz_smem_u32(&s_tmem)), "r"(ncols)
@@ -456,7 +458,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzGemmArgs
 #pragma unroll
                 for (int c = 0; c < 8; c++) {
                     const int j = col0 + cb * 8 + c;
-                    const bool ok = rowok && j < a.n && (a.lower ? i >= j : i <= j);
+                    const bool ok = rowok && j < ncol && (a.lower ? i >= j : i <= j);
                     pre_p[c] = (ok && need_part) ? a.C[(size_t)i * a.ldc + j] : 0.0;
                     pre_c[c] = (ok && need_cin) ? a.Cin[(size_t)i * a.ldcin + j] : 0.0;
                 }
@@ -478,7 +480,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzGemmArgs
 #pragma unroll
                     for (int c = 0; c < 8; c++) {
                         const int j = col0 + cb * 8 + c;
-                        if (j >= a.n || (a.lower ? i < j : i > j)) continue;   // only one triangle is authoritative
+                        if (j >= ncol || (a.lower ? i < j : i > j)) continue;   // only one triangle is authoritative
                         double h = 0.0;
 #pragma unroll
                         for (int dd = MAXD - 1; dd >= 0; dd--)
@@ -652,68 +654,93 @@ inline int oz_syrk(cudaStream_t st, const GemmArgs& a, OzWs& w, unsigned may_be_
 // products: the factor is a preconditioner + inertia test, every solve is refined against the unreduced system) in ONE
 // pass, which is what allows the in-place accumulation.  Everything is preallocated (oz_upd_alloc) so that the calls can
 // be captured into the factorisation's CUDA graph.
+constexpr int OZ_UPD_NBUF = 4;     // panels in flight (same rotation as the W scratch panels of the factorisation)
 struct OzUpdWs {
     int nmax = 0, kmax = 0;
-    int8_t *LA = nullptr, *LB = nullptr, *RB = nullptr;   // digits of W, of Lp (unused by the kernel), of -Lp
-    int *rexpA = nullptr, *rexpB = nullptr;
-    double* sw = nullptr;
-    std::vector<int2*> tiles;      // per trailing order (index = n / OZ_BM)
+    size_t stride = 0;                                     // bytes of the digits of one 128-row block (all k-blocks, all slices)
+    int8_t *LA[OZ_UPD_NBUF] = {}, *RB[OZ_UPD_NBUF] = {};   // digits of the W rows / of the -L rows of a panel
+    int *rexpA[OZ_UPD_NBUF] = {}, *rexpB[OZ_UPD_NBUF] = {};
+    double* sw = nullptr;                                  // +1 / -1 column weights (two halves)
+    std::vector<int2*> tiles;      // per (trailing order / 128, columns / 64)
     std::vector<int> ntiles;
+    int ncolmax = 0;
 };
 inline void oz_upd_free(OzUpdWs& w) {
-    cudaFree(w.LA); cudaFree(w.LB); cudaFree(w.RB); cudaFree(w.rexpA); cudaFree(w.rexpB); cudaFree(w.sw);
+    for (int i = 0; i < OZ_UPD_NBUF; i++) { cudaFree(w.LA[i]); cudaFree(w.RB[i]); cudaFree(w.rexpA[i]); cudaFree(w.rexpB[i]); }
+    cudaFree(w.sw);
     for (int2* t : w.tiles) cudaFree(t);
     w = OzUpdWs();
 }
 inline int oz_upd_alloc(OzUpdWs& w, int nmax, int kmax) {
     w.nmax = nmax; w.kmax = kmax;
     const int nrb = cdiv(nmax, OZ_BM), nkb = cdiv(kmax, OZ_KB);
-    const size_t bytes = (size_t)nrb * nkb * OZ_NS * OZ_CHUNK;
-    CU(cudaMalloc(&w.LA, bytes)); CU(cudaMalloc(&w.LB, bytes)); CU(cudaMalloc(&w.RB, bytes));
-    CU(cudaMalloc(&w.rexpA, sizeof(int) * nrb * OZ_BM)); CU(cudaMalloc(&w.rexpB, sizeof(int) * nrb * OZ_BM));
-    CU(cudaMalloc(&w.sw, sizeof(double) * nkb * OZ_KB));
-    w.tiles.assign(nrb + 1, nullptr);
-    w.ntiles.assign(nrb + 1, 0);
+    w.stride = (size_t)nkb * OZ_NS * OZ_CHUNK;
+    for (int i = 0; i < OZ_UPD_NBUF; i++) {
+        CU(cudaMalloc(&w.LA[i], (size_t)nrb * w.stride)); CU(cudaMalloc(&w.RB[i], (size_t)nrb * w.stride));
+        CU(cudaMalloc(&w.rexpA[i], sizeof(int) * nrb * OZ_BM)); CU(cudaMalloc(&w.rexpB[i], sizeof(int) * nrb * OZ_BM));
+    }
+    CU(cudaMalloc(&w.sw, sizeof(double) * 2 * nkb * OZ_KB));
+    {   // the column weights never change: +1 for the W side, -1 for the L side (C -= W L')
+        std::vector<double> h((size_t)2 * nkb * OZ_KB);
+        for (int i = 0; i < nkb * OZ_KB; i++) { h[i] = 1.0; h[(size_t)nkb * OZ_KB + i] = -1.0; }
+        CU(cudaMemcpy(w.sw, h.data(), sizeof(double) * h.size(), cudaMemcpyHostToDevice));
+    }
+    w.ncolmax = nrb * 2 + 1;
+    w.tiles.assign((size_t)(nrb + 1) * w.ncolmax, nullptr);
+    w.ntiles.assign((size_t)(nrb + 1) * w.ncolmax, 0);
     return 0;
 }
-// tile list of a trailing matrix of order n (cached per n / 128; must be called OUTSIDE stream capture the first time)
-inline int oz_upd_tiles(OzUpdWs& w, int n) {
-    const int key = cdiv(n, OZ_BM);
-    if (key >= (int)w.tiles.size()) return fail_msg("oz_upd_tiles: order exceeds the workspace");
+// tile list of a lower-trapezoidal piece: rows 0 .. n-1, columns 0 .. ncols-1 (ncols <= n), origin on the diagonal
+// (cached; must be called OUTSIDE stream capture the first time)
+inline int oz_upd_tiles(OzUpdWs& w, int n, int ncols) {
+    const int kr = cdiv(n, OZ_BM), kc = cdiv(ncols, 64);
+    if (kr >= (int)(w.tiles.size() / w.ncolmax) || kc >= w.ncolmax) return fail_msg("oz_upd_tiles: order exceeds the workspace");
+    const size_t key = (size_t)kr * w.ncolmax + kc;
     if (w.tiles[key]) return 0;
     std::vector<int2> tl;
     for (int ti = 0; ti * OZ_BM < n; ti++)
-        for (int tj = 0; tj * 64 < n && tj * 64 <= ti * OZ_BM + OZ_BM - 1; tj++) tl.push_back(make_int2(ti, tj));
+        for (int tj = 0; tj * 64 < ncols && tj * 64 <= ti * OZ_BM + OZ_BM - 1; tj++) tl.push_back(make_int2(ti, tj));
     CU(cudaMalloc(&w.tiles[key], sizeof(int2) * tl.size()));
     CU(cudaMemcpy(w.tiles[key], tl.data(), sizeof(int2) * tl.size(), cudaMemcpyHostToDevice));
     w.ntiles[key] = (int)tl.size();
     return 0;
 }
-inline int oz_update_lower(cudaStream_t st, double* C, int ldc, int n, const double* W, int ldw, const double* Lp, int ldl,
-                           int K, OzUpdWs& w, int* err, const int* ctrl, int max_ctas) {
-    if (n > w.nmax || K > w.kmax) return fail_msg("oz_update_lower: workspace too small");
-    const int key = cdiv(n, OZ_BM);
-    if (!w.tiles[key]) return fail_msg("oz_update_lower: tile list not prepared (oz_upd_tiles)");
-    const int nkb = cdiv(K, OZ_KB), nrb = cdiv(n, OZ_BM);
+// digits of the rows of one outer panel: W (rows x K, leading dimension ldw) and -Lp (rows x K, ldl) -> buffer set `buf`
+inline int oz_panel_slice(cudaStream_t st, int rows, const double* W, int ldw, const double* Lp, int ldl, int K, OzUpdWs& w,
+                          int buf, int* err, const int* ctrl) {
+    if (rows > w.nmax || K > w.kmax) return fail_msg("oz_panel_slice: workspace too small");
+    const int nkb = cdiv(K, OZ_KB), nrb = cdiv(rows, OZ_BM);
     for (int side = 0; side < 2; side++) {
         OzSliceArgs s{};
         const double* A = side ? Lp : W;
         const int lda = side ? ldl : ldw;
         const int vec = (!(lda & 1) && !(reinterpret_cast<uintptr_t>(A) & 15)) ? 1 : 0;
         s.t[0] = OzTerm{A, nullptr, lda, K, 0, side, vec, side ? -1.0 : 1.0};
-        s.nterms = 1; s.n = n; s.nkb = nkb;
-        s.L = side ? w.LB : w.LA; s.R = side ? w.RB : nullptr; s.sw = w.sw; s.rexp = side ? w.rexpB : w.rexpA;
+        s.nterms = 1; s.n = rows; s.nkb = nkb;
+        s.L = side ? nullptr : w.LA[buf]; s.R = side ? w.RB[buf] : nullptr;
+        s.sw = w.sw + (size_t)side * (w.kmax / OZ_KB) * OZ_KB; s.rexp = side ? w.rexpB[buf] : w.rexpA[buf];
         s.err = err; s.ctrl = ctrl;
-        oz_weight_kernel<<<cdiv(nkb * OZ_KB, 256), 256, 0, st>>>(s, w.sw);
-        LAUNCHED();
-        oz_rowmax_kernel<<<cdiv(n, 4), 128, 0, st>>>(s);
+        oz_rowmax_kernel<<<cdiv(rows, 4), 128, 0, st>>>(s);
         LAUNCHED();
         oz_slice_kernel<<<dim3(nrb * (OZ_BM / 8), 1), 256, 0, st>>>(s);
         LAUNCHED();
     }
+    return 0;
+}
+// C (lower trapezoid n x ncols, origin on the diagonal, in place) -= W L'  from the digits in buffer set `buf`; the piece
+// starts rb_off 128-row blocks below the first sliced row of the panel.  128 x 64 tiles, six slice-pair diagonals in ONE
+// pass (21 pairs, ~4e-12 of the row-scale products) -- the single pass is what allows the in-place accumulation.
+inline int oz_panel_update(cudaStream_t st, double* C, int ldc, int n, int ncols, int rb_off, int K, OzUpdWs& w, int buf,
+                           int* err, const int* ctrl, int max_ctas) {
+    const int kr = cdiv(n, OZ_BM), kc = cdiv(ncols, 64);
+    const size_t key = (size_t)kr * w.ncolmax + kc;
+    if (key >= w.tiles.size() || !w.tiles[key]) return fail_msg("oz_panel_update: tile list not prepared (oz_upd_tiles)");
+    const int nkb = cdiv(K, OZ_KB);
     OzGemmArgs g{};
-    g.L = w.LA; g.R = w.RB; g.rexp = w.rexpA; g.rexp_col = w.rexpB; g.tiles = w.tiles[key]; g.err = err;
-    g.C = C; g.Cin = C; g.dadd = nullptr; g.ldc = ldc; g.ldcin = ldc; g.n = n; g.nkb = nkb;
+    g.L = w.LA[buf] + (size_t)rb_off * w.stride; g.R = w.RB[buf] + (size_t)rb_off * w.stride;
+    g.rexp = w.rexpA[buf] + rb_off * OZ_BM; g.rexp_col = w.rexpB[buf] + rb_off * OZ_BM;
+    g.err = err;
+    g.C = C; g.Cin = C; g.dadd = nullptr; g.ldc = ldc; g.ldcin = ldc; g.n = n; g.ncols = ncols; g.nkb = nkb;
     g.beta = 1.0; g.shift = 0.0; g.lower = 1; g.ctrl = ctrl;
     g.desc_hi = oz_desc_hi(128, 256);
     g.idesc = oz_idesc(64);
