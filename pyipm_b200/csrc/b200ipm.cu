@@ -2233,6 +2233,7 @@ int b200ipm_ldlt_import(b200ipm_ldlt_handle h, const double* A_dev, int lda, con
     CU(cudaMemcpyAsync(h->F.LinvP, linvp_dev, sizeof(double) * (size_t)h->F.nblk * NB * NB, cudaMemcpyDeviceToDevice, h->st));
     CU(cudaMemcpyAsync(h->F.dinfo, dinfo_dev, sizeof(double) * 4 * npad, cudaMemcpyDeviceToDevice, h->st));
     CU(cudaMemcpyAsync(h->F.kind, kind_dev, sizeof(int) * npad, cudaMemcpyDeviceToDevice, h->st));
+    if (h->F.solve256) RET(ldlt_blockinv_launch(h->F, h->st, 0, h->F.nb256));    // inverses of the 256-row diagonal blocks
     CU(cudaStreamSynchronize(h->st));
     h->factored = true;
     return 0;

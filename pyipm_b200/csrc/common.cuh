@@ -74,7 +74,7 @@ __device__ __forceinline__ int trace_begin(int id, const void* tag = nullptr) {
 __device__ __forceinline__ void trace_end(int i) {
     if (i >= 0) g_trace[i].t1 = trace_now();
 }
-enum { TR_TILE = 1, TR_PANEL = 2, TR_MINI = 3, TR_SUB64 = 4, TR_DMMA = 5 };
+enum { TR_TILE = 1, TR_PANEL = 2, TR_MINI = 3, TR_SUB64 = 4, TR_DMMA = 5, TR_OZ = 6, TR_SLICE = 7, TR_BINV = 8 };
 
 // ------------------------------------------------------------------------------------ device reductions
 __device__ __forceinline__ double warp_sum(double v) {

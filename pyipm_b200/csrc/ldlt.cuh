@@ -19,12 +19,14 @@
 // CTAs of earlier block rows (tickets guarantee forward progress), and applies LinvP_i as a 64 x 64 GEMV.
 #pragma once
 #include <algorithm>
+#include <cooperative_groups.h>
 #include "common.cuh"
 #include "gemm_nt.cuh"
 #include "ozaki_i8.cuh"
 #include "vec.cuh"
 
 namespace b200 {
+namespace cg = cooperative_groups;
 
 constexpr int NB = 64;
 constexpr int NBP = NB + 1;   // padded smem row
@@ -72,6 +74,10 @@ struct LdltWs {
     OzUpdWs tcu;
     TmaMat tmA, tmW[4];        // tensor maps of the KKT matrix and the four W scratch panels (TMA-staged updates)
     int use_tma = 1;           // B200IPM_LDLT_TMA=0: cp.async staging (gemm_nt_sub64_kernel)
+    double *Xinv = nullptr, *XinvT = nullptr;   // explicit inverses of the 256-row diagonal blocks (block-256 solves) + transposes
+    int nb256 = 0;
+    int solve256 = 1;          // B200IPM_SOLVE256=0: the 64-row chain (ldlt_fwd_kernel / ldlt_bwd_kernel)
+    int binv_mode = 1;         // where the block inverses are built: 1 one launch at the end (default), 0 per outer panel on the bulk stream
     double pivot_u = 0.01;     // threshold of the fast (unpivoted) tile attempt: accept step j iff |d_j| >= u * max_i |T[i][j]|
 };
 
@@ -164,9 +170,17 @@ inline int ldlt_alloc(LdltWs& w, int n, cudaStream_t st, bool background = false
     }
     CU(cudaMalloc(&w.flags, sizeof(unsigned) * 2 * w.nblk));
     CU(cudaMalloc(&w.ticket, sizeof(unsigned) * 2));
-    CU(cudaMalloc(&w.yv, sizeof(double) * npad));
-    CU(cudaMalloc(&w.zv, sizeof(double) * npad));
-    CU(cudaMalloc(&w.xv, sizeof(double) * npad));
+    w.nb256 = cdiv(w.nblk, 4);
+    { const char* e = getenv("B200IPM_SOLVE256"); if (e) w.solve256 = atoi(e); }
+    { const char* e = getenv("B200IPM_BINV_MODE"); if (e) w.binv_mode = atoi(e); }
+    const size_t npad256 = (size_t)w.nb256 * 256;
+    CU(cudaMalloc(&w.yv, sizeof(double) * npad256));
+    CU(cudaMalloc(&w.zv, sizeof(double) * npad256));
+    CU(cudaMalloc(&w.xv, sizeof(double) * npad256));
+    CU(cudaMalloc(&w.Xinv, sizeof(double) * npad256 * 256));
+    CU(cudaMalloc(&w.XinvT, sizeof(double) * npad256 * 256));
+    CU(cudaMemsetAsync(w.Xinv, 0, sizeof(double) * npad256 * 256, st));
+    CU(cudaMemsetAsync(w.XinvT, 0, sizeof(double) * npad256 * 256, st));
     CU(cudaMemsetAsync(w.flags, 0, sizeof(unsigned) * 2 * w.nblk, st));
     CU(cudaMemsetAsync(w.A, 0, sizeof(double) * (size_t)npad * w.ld, st));
     return 0;
@@ -188,6 +202,7 @@ inline void ldlt_free(LdltWs& w) {
     for (int i = 0; i < 2; i++) { if (w.ev_panel[i]) cudaEventDestroy(w.ev_panel[i]); if (w.ev_upd[i]) cudaEventDestroy(w.ev_upd[i]); }
     cudaFree(w.LinvP); cudaFree(w.dinfo); cudaFree(w.kind); cudaFree(w.counts);
     cudaFree(w.dstat); cudaFree(w.serr); cudaFree(w.flags); cudaFree(w.ticket); cudaFree(w.yv); cudaFree(w.zv); cudaFree(w.xv);
+    cudaFree(w.Xinv); cudaFree(w.XinvT);
     w = LdltWs();
 }
 
@@ -1201,6 +1216,8 @@ inline int ldlt_init_attrs() {
 // side stream, overlapped with the next panel's tile steps (W is double buffered).  Results stay on the device
 // (counts/dstat) until the caller needs the inertia decision.
 constexpr int NBO = 256;
+struct LdltWs;
+inline int ldlt_blockinv_launch(LdltWs& w, cudaStream_t st, int blk0, int nblocks);   // defined with the solve kernels
 inline int ldlt_factor_launch(LdltWs& w, cudaStream_t st) {
     cudaStream_t sd = w.side;
     const int n = w.n, ld = w.ld;
@@ -1371,7 +1388,15 @@ inline int ldlt_factor_launch(LdltWs& w, cudaStream_t st) {
         } else {
             r_prev = false;
         }
+        if (w.solve256 && w.binv_mode == 0) {
+            // explicit inverse of this panel's 256 x 256 diagonal block (block-256 solves): off the chain, behind the bulk
+            // update of the same panel -- nothing waits for it before the end of the factorisation
+            CU(cudaStreamWaitEvent(sd, w.ev_panel[p & 1], 0));
+            RET(ldlt_blockinv_launch(w, sd, p, 1));
+            side_used = true;
+        }
     }
+    if (w.solve256 && w.binv_mode == 0) RET(ldlt_blockinv_launch(w, st, p, 1));     // the last panel: on the chain stream itself
     // join the forked streams
     if (a2_pending) CU(cudaStreamWaitEvent(st, w.ev_a2, 0));
     if (urg_used) {
@@ -1382,6 +1407,7 @@ inline int ldlt_factor_launch(LdltWs& w, cudaStream_t st) {
         CU(cudaEventRecord(w.ev_upd[0], sd));
         CU(cudaStreamWaitEvent(st, w.ev_upd[0], 0));
     }
+    if (w.solve256 && w.binv_mode == 1) RET(ldlt_blockinv_launch(w, st, 0, w.nb256));
     return 0;
 }
 // back to fp64 DMMA trailing updates (the captured graph contains the tcgen05 launches: drop it)
@@ -1598,8 +1624,282 @@ __global__ void __launch_bounds__(256) ldlt_bwd_kernel(const double* __restrict_
 }
 
 
+// ------------------------------------------------------------------------------------------- block-256 solves
+// The 64-row chain above costs one L2 round trip per tile (72 links of ~2.5 us at config 3 = 0.07 of the HBM roofline).
+// Here a link of the chain is a 256-row block I: the factorisation also emits the explicit inverse  X_I = T_I^-1  of the
+// block lower-triangular matrix  T_I = [Lt_ij], Lt_ii = (LinvP_i)^-1, Lt_ij = the stored L tile (i > j)  of the four
+// tiles of the block (ldlt_blockinv_kernel: X_ii = LinvP_i, X_ij = -LinvP_i sum_{j<=k<i} Lt_ik X_kj), and a solve is
+//   forward   y_I = X_I   (b_I - sum_{J<I} L_IJ y_J),   z = D^-1 y
+//   backward  x_I = X_I^T (z_I - sum_{J>I} L_JI^T x_J)
+// run by one thread-block CLUSTER of eight CTAs per link: CTA c owns 32 rows / columns of the block, polls the 256
+// published values of every earlier link once, and the eight CTAs exchange their 32 partial results through distributed
+// shared memory (one cluster barrier) before each applies its rows of X_I from registers.  A link costs one L2 round
+// trip + one cluster barrier instead of four L2 round trips.
+constexpr int SB = 256;
+constexpr int SBT = SB / NB;
+static_assert(SBT == 4, "the solve clusters are written for four tiles per link");
+constexpr int BINV_SLAB = 8;           // columns of X_I per CTA of the inverse builder
+constexpr int BINV_NSL = NB / BINV_SLAB;   // slabs per block column
+constexpr int BINV_LDA = NB + 2;       // row stride of the staged left operand: 16-byte aligned rows, conflict-free reads
+constexpr int BINV_SMEM = (2 * NB * BINV_LDA + 3 * NB * BINV_SLAB + NB * BINV_SLAB) * 8;
+
+// grid (4 * BINV_NSL, blocks): blockIdx.x = BINV_NSL * j + slab -> 8 columns of block column j of X_I, I = blk0 +
+// blockIdx.y.  Columns of a triangular inverse are independent, so no CTA waits for another.  The left operands of the
+// successive 64 x 64 x 8 products (Lt_ik for k = j .. i-1, then LinvP_i, for i = j+1 ..) are all INPUTS, so they are
+// streamed through a two-deep cp.async ring one product ahead.  X (row-major 256 x 256 per block) and XT (its
+// transpose) are zero-initialised once; entries of padded rows / columns (index >= n) are never set.
+__global__ void __launch_bounds__(256) ldlt_blockinv_kernel(const double* __restrict__ A, int ld, int n, int nblk,
+                                                            const double* __restrict__ LinvP, double* __restrict__ X,
+                                                            double* __restrict__ XT, int blk0, const int* __restrict__ ctrl) {
+    extern __shared__ __align__(16) double bsm[];
+    __shared__ int s_abort;
+    if (threadIdx.x == 0) s_abort = ctrl ? *reinterpret_cast<const volatile int*>(ctrl + 4) : 0;
+    __syncthreads();
+    if (s_abort) return;
+    double* As = bsm;                               // [2][64][66]  left operand ring
+    double* Xs = As + 2 * NB * BINV_LDA;            // [3][64][8]   X_kj slabs, k = j .. j + 2
+    double* Ss = Xs + 3 * NB * BINV_SLAB;           // [64][8]      S = sum_k Lt_ik X_kj
+    const int tid = threadIdx.x;
+    const int I = blk0 + blockIdx.y, j = blockIdx.x / BINV_NSL, c0 = (blockIdx.x % BINV_NSL) * BINV_SLAB;
+    const int t0 = I * SBT, ntl = min(SBT, nblk - t0);
+    if (j >= ntl) return;
+    double* Xo = X + (size_t)I * SB * SB;
+    double* XTo = XT + (size_t)I * SB * SB;
+    const int r = tid >> 2, cq = (tid & 3) * 2;          // this thread's outputs: row r, slab columns cq, cq + 1
+    const int gcol0 = (t0 + j) * NB + c0;                // global index of slab column 0
+    // the sequence of left operands: for i = j+1 .. ntl-1: Lt_ij, ..., Lt_i,i-1, LinvP_i
+    const int nrounds = (ntl - 1 - j) * (ntl - j) / 2 + (ntl - 1 - j);
+    auto round_ik = [&](int rd, int& i, int& k) {        // k == i: the LinvP_i round
+        i = j + 1;
+        while (rd >= i - j + 1) { rd -= i - j + 1; i++; }
+        k = j + rd;
+    };
+    auto prefetch = [&](int rd) {
+        if (rd < nrounds) {
+            int i, k;
+            round_ik(rd, i, k);
+            const double* src = (k == i) ? LinvP + (size_t)(t0 + i) * NB * NB : A + (size_t)(t0 + i) * NB * ld + (size_t)(t0 + k) * NB;
+            const int lds = (k == i) ? NB : ld;
+            double* dst = As + (rd & 1) * NB * BINV_LDA;
+#pragma unroll
+            for (int it = 0; it < NB * NB / 2 / 256; it++) {
+                const int idx = tid + 256 * it;
+                const int row = idx >> 5, kc = (idx & 31) * 2;
+                const bool ok = (t0 + i) * NB + row < n;   // rows of L beyond the matrix: zeros (so are padded rows of S)
+                cp_async16(dst + row * BINV_LDA + kc, ok ? src + (size_t)row * lds + kc : src, ok ? 16 : 0);
+            }
+        }
+        cp_async_commit();
+    };
+    auto product = [&](const double* Al, const double* Bs, double (&acc)[2]) {      // acc += Al[r][:] * Bs[:][cq, cq + 1]
+        double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+#pragma unroll 8
+        for (int k = 0; k < NB; k += 2) {
+            const double2 a = *reinterpret_cast<const double2*>(Al + r * BINV_LDA + k);
+            const double2 x0 = *reinterpret_cast<const double2*>(Bs + k * BINV_SLAB + cq);
+            const double2 x1 = *reinterpret_cast<const double2*>(Bs + (k + 1) * BINV_SLAB + cq);
+            a0 = fma(a.x, x0.x, a0); a1 = fma(a.x, x0.y, a1);
+            b0 = fma(a.y, x1.x, b0); b1 = fma(a.y, x1.y, b1);
+        }
+        acc[0] += a0 + b0;
+        acc[1] += a1 + b1;
+    };
+    auto emit = [&](int i, const double (&v)[2], double* slab) {   // tile (i, j) of X, this thread's two entries
+        const int gi = (t0 + i) * NB + r;
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            const double x = (gi < n && gcol0 + cq + e < n) ? v[e] : 0.0;
+            if (slab) slab[r * BINV_SLAB + cq + e] = x;
+            Xo[(size_t)(i * NB + r) * SB + j * NB + c0 + cq + e] = x;
+            XTo[(size_t)(j * NB + c0 + cq + e) * SB + i * NB + r] = x;
+        }
+    };
+    prefetch(0);
+    prefetch(1);
+    {   // X_jj = LinvP_j
+        const double* Lj = LinvP + (size_t)(t0 + j) * NB * NB;
+        double v[2];
+#pragma unroll
+        for (int e = 0; e < 2; e++) v[e] = Lj[r * NB + c0 + cq + e];
+        emit(j, v, Xs);
+    }
+    int rd = 0;
+    for (int i = j + 1; i < ntl; i++) {
+        double sacc[2] = {0.0, 0.0};
+        for (int k = j; k <= i; k++, rd++) {
+            cp_async_wait<1>();                  // round rd has landed (one younger group may still be in flight)
+            if (k == i) {
+#pragma unroll
+                for (int e = 0; e < 2; e++) Ss[r * BINV_SLAB + cq + e] = sacc[e];
+            }
+            __syncthreads();                     // ring slot rd & 1, the X slabs and (k == i) S are visible
+            const double* Al = As + (rd & 1) * NB * BINV_LDA;
+            if (k < i) {
+                product(Al, Xs + (k - j) * NB * BINV_SLAB, sacc);
+            } else {
+                double x[2] = {0.0, 0.0};
+                product(Al, Ss, x);
+                x[0] = -x[0]; x[1] = -x[1];
+                emit(i, x, (i - j < 3) ? Xs + (i - j) * NB * BINV_SLAB : nullptr);
+            }
+            __syncthreads();                     // everybody is done with ring slot rd & 1
+            prefetch(rd + 2);
+        }
+    }
+    cp_async_wait<0>();
+}
+
+// forward link: one cluster of SBC = 8 CTAs, CTA c = rows 32 c .. 32 c + 31 of block I (ticket order = scheduling order);
+// 8 lanes per row, so a thread keeps 32 entries of its row of X_I and 32 entries of the current L block in registers
+constexpr int SBC = 8;             // CTAs per cluster
+constexpr int SBR = SB / SBC;      // rows (forward) / columns (backward) per CTA
+__global__ void __cluster_dims__(SBC, 1, 1) __launch_bounds__(256)
+ldlt_fwd256_kernel(const double* __restrict__ A, int ld, int n, int nblk, const double* __restrict__ X,
+                   const double* __restrict__ b, double* yv, int* err, unsigned* ticket) {
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ __align__(16) double accv[SB];        // b_I - sum: the 32 values of CTA c' arrive from that CTA
+    __shared__ __align__(16) double ybuf[2][SB];
+    __shared__ int s_I;
+    const int tid = threadIdx.x;
+    const int cr = (int)cluster.block_rank();
+    if (cr == 0 && tid == 0) s_I = (int)atomicAdd(ticket, 1u);
+    cluster.sync();
+    const int I = *cluster.map_shared_rank(&s_I, 0);
+    const int r0 = I * SB + cr * SBR;
+    const int r = tid >> 3, q = tid & 7;
+    const bool rowok = (r0 + r) < n;
+    const int ncol = NB * (cr / 2 + 1);              // X_I is block lower triangular in 64 x 64 tiles
+    double xr[32];
+    {
+        const double* xrow = X + ((size_t)I * SB + cr * SBR + r) * SB;
+#pragma unroll
+        for (int c = 0; c < 32; c++) xr[c] = (8 * c < ncol) ? __ldg(xrow + 8 * c + q) : 0.0;
+    }
+    const double bval = rowok ? b[r0 + r] : 0.0;
+    double part[4] = {0.0, 0.0, 0.0, 0.0};
+    // lane q of a row reads the 16-byte pieces 8 c' + q of the 256 columns: the eight lanes cover 128 contiguous bytes
+    const double2* arow = reinterpret_cast<const double2*>(A + (size_t)(rowok ? r0 + r : 0) * ld) + q;
+    for (int J = 0; J < I; J++) {
+        double2 lv[16];
+#pragma unroll
+        for (int c = 0; c < 16; c++) lv[c] = rowok ? __ldg(arow + (size_t)J * (SB / 2) + 8 * c) : make_double2(0.0, 0.0);
+        double* yb = ybuf[J & 1];
+        yb[tid] = ld_poll_f64_err(yv + (size_t)J * SB + tid, err);
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < 16; c++) {
+            const double2 yy = *reinterpret_cast<const double2*>(yb + 16 * c + 2 * q);
+            part[c & 3] = fma(lv[c].x, yy.x, part[c & 3]);
+            part[c & 3] = fma(lv[c].y, yy.y, part[c & 3]);
+        }
+    }
+    double p = (part[0] + part[1]) + (part[2] + part[3]);
+    p += __shfl_xor_sync(0xffffffffu, p, 1);
+    p += __shfl_xor_sync(0xffffffffu, p, 2);
+    p += __shfl_xor_sync(0xffffffffu, p, 4);
+    const double acc = rowok ? (bval - p) : 0.0;
+    if (q >= (cr & ~1)) cluster.map_shared_rank(accv, q)[cr * SBR + r] = acc;     // lane q delivers the row's value to CTA q
+    cluster.sync();
+    double yp[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int c = 0; c < 32; c++)
+        if (8 * c < ncol) yp[c & 3] = fma(xr[c], accv[8 * c + q], yp[c & 3]);
+    double y = (yp[0] + yp[1]) + (yp[2] + yp[3]);
+    y += __shfl_xor_sync(0xffffffffu, y, 1);
+    y += __shfl_xor_sync(0xffffffffu, y, 2);
+    y += __shfl_xor_sync(0xffffffffu, y, 4);
+    if (q == 0) st_publish_f64(yv + r0 + r, rowok ? y : 0.0);     // publication (padded rows too)
+}
+
+// backward link: CTA c owns columns 32 c .. 32 c + 31 of block I; z = D^-1 y is formed here from the finished y
+__global__ void __cluster_dims__(SBC, 1, 1) __launch_bounds__(256)
+ldlt_bwd256_kernel(const double* __restrict__ A, int ld, int n, int nblk, int nb256, const double* __restrict__ XT,
+                   const double* __restrict__ dinv_a, const double* __restrict__ dinv_b, const int* __restrict__ kind,
+                   const double* __restrict__ yv, double* xv, int* err, unsigned* ticket) {
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ double P[SBR][SBR + 1];               // partial sums [row r][column]
+    __shared__ __align__(16) double tvv[SB];         // z_I - sum: the 32 values of CTA c' arrive from that CTA
+    __shared__ __align__(16) double xbuf[2][SB];
+    __shared__ int s_I;
+    const int tid = threadIdx.x;
+    const int cr = (int)cluster.block_rank();
+    if (cr == 0 && tid == 0) s_I = nb256 - 1 - (int)atomicAdd(ticket, 1u);
+    cluster.sync();
+    const int I = *cluster.map_shared_rank(&s_I, 0);
+    const int c0 = I * SB + cr * SBR;
+    const int r = tid >> 3, q = tid & 7;
+    const int kmin = NB * (cr / 2);                  // X_I^T is block UPPER triangular: row 32 cr + cc needs tv[kmin ..]
+    double xt[32];
+    {
+        const double* xrow = XT + ((size_t)I * SB + cr * SBR + r) * SB;
+#pragma unroll
+        for (int c = 0; c < 32; c++) xt[c] = (8 * c >= kmin) ? __ldg(xrow + 8 * c + q) : 0.0;
+    }
+    double zval = 0.0;                               // z of column c0 + r (r doubles as the column index cc below)
+    if (c0 + r < n) {
+        const int g = c0 + r;
+        const int k = kind[g];
+        zval = dinv_a[g] * yv[g];
+        if (k == 1) zval += dinv_b[g] * yv[g + 1];
+        else if (k == 2) zval += dinv_b[g - 1] * yv[g - 1];
+    }
+    double pacc[4] = {0.0, 0.0, 0.0, 0.0};
+    const bool colsok = c0 < n;
+    for (int J = nb256 - 1; J > I; J--) {
+        double2 lv[16];                              // rows J*256 + 32 u + r (u = 0..7), columns c0 + 4 q .. + 3
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int gr = J * SB + u * SBR + r;
+            const bool ok = colsok && gr < n;
+            const double2* p2 = reinterpret_cast<const double2*>(A + (size_t)(ok ? gr : 0) * ld + c0 + 4 * q);
+            lv[2 * u] = ok ? __ldg(p2) : make_double2(0.0, 0.0);
+            lv[2 * u + 1] = ok ? __ldg(p2 + 1) : make_double2(0.0, 0.0);
+        }
+        double* xb = xbuf[J & 1];
+        xb[tid] = ld_poll_f64_err(xv + (size_t)J * SB + tid, err);     // zeros in padded rows
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const double xr = xb[u * SBR + r];
+            pacc[0] = fma(lv[2 * u].x, xr, pacc[0]);
+            pacc[1] = fma(lv[2 * u].y, xr, pacc[1]);
+            pacc[2] = fma(lv[2 * u + 1].x, xr, pacc[2]);
+            pacc[3] = fma(lv[2 * u + 1].y, xr, pacc[3]);
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; e++) P[r][4 * q + e] = pacc[e];
+    __syncthreads();
+    const int cc = r, qq = q;
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) s += P[8 * k + qq][cc];
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    const bool colok = (c0 + cc) < n;
+    const double tv = colok ? (zval - s) : 0.0;
+    if (qq <= (cr | 1)) cluster.map_shared_rank(tvv, qq)[cr * SBR + cc] = tv;     // lane qq delivers to CTA qq
+    cluster.sync();
+    double xp[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int c = 0; c < 32; c++)
+        if (8 * c >= kmin) xp[c & 3] = fma(xt[c], tvv[8 * c + qq], xp[c & 3]);
+    double xx = (xp[0] + xp[1]) + (xp[2] + xp[3]);
+    xx += __shfl_xor_sync(0xffffffffu, xx, 1);
+    xx += __shfl_xor_sync(0xffffffffu, xx, 2);
+    xx += __shfl_xor_sync(0xffffffffu, xx, 4);
+    if (qq == 0) st_publish_f64(xv + c0 + cc, colok ? xx : 0.0);     // publication
+}
+
 inline int ldlt_init_solve_attrs() {
     CU(cudaFuncSetAttribute(ldlt_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM));
+    CU(cudaFuncSetAttribute(ldlt_blockinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BINV_SMEM));
+    return 0;
+}
+inline int ldlt_blockinv_launch(LdltWs& w, cudaStream_t st, int blk0, int nblocks) {
+    ldlt_blockinv_kernel<<<dim3(4 * BINV_NSL, nblocks), 256, BINV_SMEM, st>>>(w.A, w.ld, w.n, w.nblk, w.LinvP, w.Xinv, w.XinvT, blk0, w.counts);
+    LAUNCHED();
     return 0;
 }
 
@@ -1610,6 +1910,8 @@ inline int ldlt_copy_factor(LdltWs& dst, const LdltWs& src, cudaStream_t st) {
     const size_t npad = (size_t)src.nblk * NB;
     CU(cudaMemcpyAsync(dst.A, src.A, sizeof(double) * npad * src.ld, cudaMemcpyDeviceToDevice, st));
     CU(cudaMemcpyAsync(dst.LinvP, src.LinvP, sizeof(double) * (size_t)src.nblk * NB * NB, cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(dst.Xinv, src.Xinv, sizeof(double) * (size_t)src.nb256 * SB * SB, cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(dst.XinvT, src.XinvT, sizeof(double) * (size_t)src.nb256 * SB * SB, cudaMemcpyDeviceToDevice, st));
     CU(cudaMemcpyAsync(dst.dinfo, src.dinfo, sizeof(double) * 4 * npad, cudaMemcpyDeviceToDevice, st));
     CU(cudaMemcpyAsync(dst.kind, src.kind, sizeof(int) * npad, cudaMemcpyDeviceToDevice, st));
     CU(cudaMemcpyAsync(dst.counts, src.counts, sizeof(int) * 4, cudaMemcpyDeviceToDevice, st));
@@ -1621,7 +1923,7 @@ inline int ldlt_copy_factor(LdltWs& dst, const LdltWs& src, cudaStream_t st) {
 // two streams (the factor is only read).
 struct LdltSolveBuf { double *yv = nullptr, *zv = nullptr, *xv = nullptr; unsigned* ticket = nullptr; };
 inline int ldlt_solvebuf_alloc(LdltSolveBuf& sb, int nblk) {
-    const size_t npad = (size_t)nblk * NB;
+    const size_t npad = (size_t)cdiv(nblk, 4) * 256;
     CU(cudaMalloc(&sb.yv, sizeof(double) * npad));
     CU(cudaMalloc(&sb.zv, sizeof(double) * npad));
     CU(cudaMalloc(&sb.xv, sizeof(double) * npad));
@@ -1637,6 +1939,18 @@ inline int ldlt_solve_on(LdltWs& w, cudaStream_t st, const LdltSolveBuf& sb, con
     const size_t npad = (size_t)w.nblk * NB;
     double *ia = w.dinfo, *ib = w.dinfo + npad;
     CU(cudaMemsetAsync(sb.ticket, 0, sizeof(unsigned) * 2, st));
+    if (w.solve256) {
+        const int np256 = w.nb256 * SB;
+        ldlt_fill_sentinel_kernel<<<cdiv(np256, 256), 256, 0, st>>>(sb.yv, sb.xv, np256);
+        LAUNCHED();
+        ldlt_fwd256_kernel<<<w.nb256 * SBC, 256, 0, st>>>(w.A, w.ld, w.n, w.nblk, w.Xinv, b, sb.yv, w.serr, sb.ticket);
+        LAUNCHED();
+        ldlt_bwd256_kernel<<<w.nb256 * SBC, 256, 0, st>>>(w.A, w.ld, w.n, w.nblk, w.nb256, w.XinvT, ia, ib, w.kind, sb.yv, sb.xv,
+                                                          w.serr, sb.ticket + 1);
+        LAUNCHED();
+        CU(cudaMemcpyAsync(x, sb.xv, sizeof(double) * w.n, cudaMemcpyDeviceToDevice, st));
+        return 0;
+    }
     ldlt_fill_sentinel_kernel<<<cdiv((int)npad, 256), 256, 0, st>>>(sb.yv, sb.xv, (int)npad);
     LAUNCHED();
     ldlt_fwd_kernel<<<w.nblk, 256, 0, st>>>(w.A, w.ld, w.n, w.nblk, w.LinvP, ia, ib, w.kind, b, sb.yv, sb.zv, w.serr, sb.ticket);

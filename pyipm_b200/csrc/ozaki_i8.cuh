@@ -329,6 +329,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzGemmArgs
     __shared__ double s_cscale[BN];   // 2^(e_j - 7) of the tile's columns
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (a.ctrl && *reinterpret_cast<const volatile int*>(a.ctrl + 4)) return;      // before any barrier / TMEM allocation
+    const int trc = (a.ctrl && tid == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) ? trace_begin(TR_OZ, a.ctrl) : -1;
     const int2 tile = a.tiles[blockIdx.x];
     const int ti = tile.x, tj = tile.y;
     const int row0 = ti * OZ_BM, col0 = tj * BN;
@@ -511,6 +512,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzGemmArgs
         const uint32_t ncols = 512;
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(ncols) : "memory");
     }
+    trace_end(trc);
 }
 
 // ------------------------------------------------------------------------------------------- host side

@@ -200,3 +200,25 @@ def test_ldlt_tcgen05_trailing_updates(tc, monkeypatch):
     assert np.max(np.abs(X - Xref)) / np.max(np.abs(Xref)) < 1e-9
     res = np.max(np.abs(K @ X - rhs[:, :2])) / (np.max(np.abs(K)) * np.max(np.abs(X)))
     assert res < 1e-14, res
+
+
+@pytest.mark.parametrize('n,m', [(100, 20), (257, 31), (1000, 124), (2560, 320), (4608, 512)])
+def test_ldlt_block256_solve_matches_tile_chain(n, m, monkeypatch):
+    """The block-256 cluster solves (explicit inverses of the 256-row diagonal blocks, one DSMEM exchange per link;
+    default) against the 64-row chain (B200IPM_SOLVE256=0): same factorisation, UNREFINED solutions of a quasi-definite
+    KKT matrix agree to the conditioning-level error of either, both reach 1e-9 of LAPACK after refinement."""
+    K, rhs = problems.make_dense_kkt(n, m, seed=n)
+    Xref = np.linalg.solve(K, rhs[:, :2])
+    raw = {}
+    for flag in ('1', '0'):
+        monkeypatch.setenv('B200IPM_SOLVE256', flag)
+        F = _lib.DenseLDLT(n)
+        (pos, neg, zero), _ = F.factor(K)
+        assert (pos, neg, zero) == (n - m, m, 0)
+        raw[flag] = F.solve(rhs[:, :2], nrefine=0)
+        X = F.solve(rhs[:, :2], nrefine=2)
+        F.close()
+        assert np.max(np.abs(X - Xref)) / np.max(np.abs(Xref)) < 1e-9
+    sc = np.max(np.abs(Xref))
+    e1, e0 = np.max(np.abs(raw['1'] - Xref)) / sc, np.max(np.abs(raw['0'] - Xref)) / sc
+    assert e1 < max(100.0 * e0, 1e-10), (e1, e0)

@@ -25,7 +25,7 @@ else:
     _lib.trace_start()
     info = eng.newton_step(); ms = info.ms_factor
 ids, blk, t0, t1, tag = _lib.trace_dump()
-names = {1: 'tile', 2: 'panel', 3: 'mini', 4: 'upd64', 5: 'dmma'}
+names = {1: 'tile', 2: 'panel', 3: 'mini', 4: 'upd64', 5: 'dmma', 6: 'oz'}
 base = t0.min()
 print('factor ms %.3f, %d records, span %.3f ms' % (ms, len(ids), (t1.max() - base) / 1e6))
 for tg in np.unique(tag[ids == 1]):
@@ -49,3 +49,10 @@ if len(sys.argv) > 2:
     o = np.argsort(t0)
     for i in o[:int(sys.argv[2])]:
         print('%8.1f %8.1f  %-6s blk %d tag %x' % ((t0[i] - base) / 1e3, (t1[i] - base) / 1e3, names.get(int(ids[i]), '?'), blk[i], int(tag[i]) & 0xfffff))
+if len(sys.argv) > 4:
+    lo, hi = float(sys.argv[3]), float(sys.argv[4])
+    o = np.argsort(t0)
+    for i in o:
+        a, b = (t0[i] - base) / 1e3, (t1[i] - base) / 1e3
+        if a >= lo and a <= hi:
+            print('%8.1f %8.1f  %-6s blk %d' % (a, b, names.get(int(ids[i]), '?'), blk[i]))
