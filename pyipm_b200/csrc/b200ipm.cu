@@ -2310,6 +2310,46 @@ int b200ipm_ldlt_block_panel(b200ipm_ldlt_handle h, double* B_dev, int ld, int r
     return 0;
 }
 
+// One block column of the block-column-cyclic driver in ONE call: A_dev = top-left corner of the (rows_total x b) block
+// column (b = 256), factored with the single-GPU factorisation's own panel schedule (tile -> 4-CTA mini step on the chain,
+// panel rows + in-panel updates on the workspace's update stream), L in place, W = L D to Wb_dev (rows_total x b), factor
+// data of the diagonal block packed into diag_dev (layout of block_factor).  The handle must have order >= b.
+__global__ void diag_pack_kernel(const double* __restrict__ A, int ld, int b, const double* __restrict__ LinvP,
+                                 const double* __restrict__ dinfo, int npad, const int* __restrict__ kind, double* __restrict__ diag) {
+    const int t = blockIdx.x, tid = threadIdx.x;
+    const int tile_doubles = NB * NB + 4 * NB + NB / 2;
+    double* linv = diag + (size_t)b * b + (size_t)t * tile_doubles;
+    double* dblk = linv + NB * NB;
+    int* kd = reinterpret_cast<int*>(dblk + 4 * NB);
+    for (int i = tid; i < NB * NB; i += blockDim.x) linv[i] = LinvP[(size_t)t * NB * NB + i];
+    for (int i = tid; i < 4 * NB; i += blockDim.x) dblk[i] = dinfo[(size_t)(i / NB) * npad + t * NB + (i % NB)];
+    for (int i = tid; i < NB; i += blockDim.x) kd[i] = kind[t * NB + i];
+    for (int i = tid; i < NB * b; i += blockDim.x) {       // rows t*64 .. t*64+63 of the factored diagonal block
+        const int r = t * NB + i / b, c = i % b;
+        diag[(size_t)r * b + c] = A[(size_t)r * ld + c];
+    }
+}
+int b200ipm_ldlt_colblock_factor(b200ipm_ldlt_handle h, double* A_dev, int ld, int rows_total, int b, double* diag_dev,
+                                 double* Wb_dev) {
+    if (!h || !A_dev || !diag_dev || !Wb_dev || b != NBO || rows_total < b || (rows_total % NB) != 0)
+        return fail_msg("colblock_factor: bad arguments");
+    if (h->F.n < b) return fail_msg("colblock_factor: the handle's order must be at least the block size");
+    if ((ld & 1) || (reinterpret_cast<uintptr_t>(A_dev) & 15) || (reinterpret_cast<uintptr_t>(Wb_dev) & 15))
+        return fail_msg("colblock_factor: operands must be 16-byte aligned");
+    CU(cudaSetDevice(h->device));
+    LdltWs& F = h->F;
+    double* A_save = F.A;
+    const int ld_save = F.ld, n_save = F.n;
+    F.A = A_dev; F.ld = ld; F.n = rows_total;
+    const int rc = ldlt_factor_launch(F, h->st, Wb_dev);
+    F.A = A_save; F.ld = ld_save; F.n = n_save;
+    RET(rc);
+    const int npad = F.nblk * NB;
+    diag_pack_kernel<<<b / NB, 256, 0, h->st>>>(A_dev, ld, b, F.LinvP, F.dinfo, npad, F.kind, diag_dev);
+    LAUNCHED();
+    return 0;
+}
+
 // y (rows) = A (rows x cols, row-major, leading dimension lda) * v (cols): the HBM-bound GEMV kernel of the residual,
 // for the distributed refinement mat-vec of the block-cyclic driver (device pointers, asynchronous on the handle's stream)
 int b200ipm_ldlt_gemv(b200ipm_ldlt_handle h, const double* A_dev, int lda, int rows, int cols, const double* v_dev,

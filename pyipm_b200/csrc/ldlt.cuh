@@ -1065,7 +1065,11 @@ __global__ void __launch_bounds__(128) ldlt_panel_kernel(double* __restrict__ B,
 constexpr int MINI_THREADS = 256;
 constexpr int MINI_CTAS = 4;      // the update of the next diagonal tile is split over four CTAs (the first product is redundant)
 constexpr int MINI_SMEM = 3 * NB * P_LDS * 8;
-__global__ void __launch_bounds__(MINI_THREADS) ldlt_mini_kernel(double* __restrict__ B, int ld, int rows,
+// The four CTAs read ALL 64 rows of B at entry and each later overwrites its own 16 rows with L in place: a CTA that starts
+// late (no free SM while the trailing updates saturate the GPU) would read rows its siblings have already overwritten.
+// The CTAs therefore form one thread-block cluster (co-scheduled) and pass a cluster barrier between the loads and the
+// first store; the barrier's arrive / wait are split around the first product, which hides its latency.
+__global__ void __cluster_dims__(MINI_CTAS, 1, 1) __launch_bounds__(MINI_THREADS) ldlt_mini_kernel(double* __restrict__ B, int ld, int rows,
                                                                  const double* __restrict__ LinvP,
                                                                  const double* __restrict__ dinv_a,
                                                                  const double* __restrict__ dinv_b, const int* __restrict__ kind,
@@ -1099,6 +1103,7 @@ __global__ void __launch_bounds__(MINI_THREADS) ldlt_mini_kernel(double* __restr
     cp_async_commit();
     cp_async_wait<0>();
     __syncthreads();
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");     // this CTA holds its copy of B
     double acc[8][2];
     const double* as = As + (warp * 8 + g) * P_LDS + tg;
     const double* bs = Bs + g * P_LDS + tg;
@@ -1116,6 +1121,7 @@ __global__ void __launch_bounds__(MINI_THREADS) ldlt_mini_kernel(double* __restr
         }
     };
     product();                       // W = B * LinvP'   (every CTA: the second product needs all of L)
+    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");       // every sibling holds its copy of B
     __syncthreads();                 // everybody is done reading As / Bs
 #pragma unroll
     for (int nt = 0; nt < 8; nt++)
@@ -1218,7 +1224,11 @@ inline int ldlt_init_attrs() {
 constexpr int NBO = 256;
 struct LdltWs;
 inline int ldlt_blockinv_launch(LdltWs& w, cudaStream_t st, int blk0, int nblocks);   // defined with the solve kernels
-inline int ldlt_factor_launch(LdltWs& w, cudaStream_t st) {
+// Wb0 != nullptr: COLUMN-BLOCK mode (block-column-cyclic multi-GPU driver): w.A is the top-left corner of an n x 256 block
+// column (leading dimension w.ld); only the first outer panel is processed -- the four tile steps with their mini / panel /
+// in-panel kernels, L in place, W = L D to Wb0 (n x 256, row index = row of the block column) -- and nothing is updated
+// to the right of it.
+inline int ldlt_factor_launch(LdltWs& w, cudaStream_t st, double* Wb0 = nullptr) {
     cudaStream_t sd = w.side;
     const int n = w.n, ld = w.ld;
     const size_t npad = (size_t)w.nblk * NB;
@@ -1229,9 +1239,9 @@ inline int ldlt_factor_launch(LdltWs& w, cudaStream_t st) {
     bool side_used = false, upd_pending = false, u1_used = false, urg_used = false, r_prev = false, a2_pending = false;
     for (int c0 = 0; c0 < n; c0 += NBO, p++) {
         const int c1 = min(c0 + NBO, n);
-        double* Wb = (p % 4 == 0) ? w.Wp : ((p % 4 == 1) ? w.Wp2 : ((p % 4 == 2) ? w.Wp3 : w.Wp4));
-        const TmaMat* tW = w.use_tma ? &w.tmW[p % 4] : nullptr;
-        const TmaMat* tA = w.use_tma ? &w.tmA : nullptr;
+        double* Wb = Wb0 ? Wb0 : ((p % 4 == 0) ? w.Wp : ((p % 4 == 1) ? w.Wp2 : ((p % 4 == 2) ? w.Wp3 : w.Wp4)));
+        const TmaMat* tW = (w.use_tma && !Wb0) ? &w.tmW[p % 4] : nullptr;
+        const TmaMat* tA = (w.use_tma && !Wb0) ? &w.tmA : nullptr;
         bool corner_pre = false;
         for (int k0 = c0; k0 < c1; k0 += NB) {
             const int k = k0 / NB, nb = min(NB, n - k0), k1 = k0 + nb;
@@ -1274,7 +1284,7 @@ inline int ldlt_factor_launch(LdltWs& w, cudaStream_t st) {
                 CU(cudaEventRecord(w.ev_urest, w.upd));
                 upd_pending = true;
                 a2_pending = false;      // ev_urest is recorded after (a2) on the same stream: waiting for it covers (a2)
-                if (w.split_a && k1 == c1 - NB && c1 - c0 == NBO && n - c1 > 2 * NB) {
+                if (w.split_a && !Wb0 && k1 == c1 - NB && c1 - c0 == NBO && n - c1 > 2 * NB) {
                     // the NEXT tile is the last of this outer panel.  The 128 x 128 corner of the next panel -- all the chain
                     // reads after the boundary -- already gets the contributions of the first three tile steps here, on the
                     // update stream, while the last tile is being factored; the boundary itself then only adds the last
@@ -1291,6 +1301,7 @@ inline int ldlt_factor_launch(LdltWs& w, cudaStream_t st) {
             CU(cudaStreamWaitEvent(st, w.ev_urest, 0));
             upd_pending = false;
         }
+        if (Wb0) return 0;
         const int rows2 = n - c1;
         if (rows2 <= 0) break;
         const int kw = c1 - c0;

@@ -48,11 +48,11 @@ class CudaTileOps(object):
         self.nt = block // NB
         self.device = torch.device('cuda', device)
         stream = _lib.torch_stream_handle(self.device)
-        self.ctx = _lib.DenseLDLT(NB, device=device, stream=stream)     # carries device + stream for the tile calls
+        self.ctx = _lib.DenseLDLT(block, device=device, stream=stream)  # carries device + stream for the tile calls
         # the serial chain (diagonal factor, panel, broadcasts) runs on its own high-priority stream so that it overlaps
         # with the trailing update of the previous block column (look-ahead 1)
         self.s_chain = torch.cuda.Stream(device=self.device, priority=-1)
-        self.ctx_chain = _lib.DenseLDLT(NB, device=device, stream=self.s_chain.cuda_stream)
+        self.ctx_chain = _lib.DenseLDLT(block, device=device, stream=self.s_chain.cuda_stream)
         self.tile_doubles = NB * NB + 4 * NB + NB // 2                   # LinvP + [dinv_a|dinv_b|d_a|d_b] + kind (ints)
         self.diag_size = self.b * self.b + self.nt * self.tile_doubles + 3
         self.perm = torch.empty(NB, dtype=torch.int32, device=self.device)
@@ -83,6 +83,11 @@ class CudaTileOps(object):
         if ev is not None:
             torch.cuda.current_stream(self.device).wait_event(ev)
 
+    def record_timed(self):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record(torch.cuda.current_stream(self.device))
+        return e
+
     def sync(self):
         torch.cuda.synchronize(self.device)
 
@@ -94,13 +99,21 @@ class CudaTileOps(object):
                                                            wd.data_ptr()))
         # (inertia is evaluated once, for all diagonal blocks together, by counts_all)
 
-    def panel(self, Bblk, diag, chain=False):
-        """Bblk: rows x b view (row stride ld) -> overwritten with L; returns W = L * D (rows x b, contiguous)."""
+    def panel(self, Bblk, diag, chain=False, out=None):
+        """Bblk: rows x b view (row stride ld) -> overwritten with L; returns W = L * D (rows x b, contiguous; written
+        into `out` when given)."""
         ctx = self.ctx_chain if chain else self.ctx
-        W = self.empty(Bblk.shape[0], self.b)
+        W = self.empty(Bblk.shape[0], self.b) if out is None else out
         self._lib.check(self.lib.b200ipm_ldlt_block_panel(ctx.h, Bblk.data_ptr(), Bblk.stride(0), Bblk.shape[0], self.b,
                                                           diag.data_ptr(), W.data_ptr()))
         return W
+
+    def colblock(self, Acol, diag, Wb, chain=True):
+        """Acol: (rows_total x b) view of a whole block column from its diagonal block down (row stride ld): factored in
+        place with the single-GPU panel schedule (one C call); Wb (rows_total x b, contiguous) <- W = L D; fills `diag`."""
+        ctx = self.ctx_chain if chain else self.ctx
+        self._lib.check(self.lib.b200ipm_ldlt_colblock_factor(ctx.h, Acol.data_ptr(), Acol.stride(0), Acol.shape[0], self.b,
+                                                              diag.data_ptr(), Wb.data_ptr()))
 
     def update(self, Cv, W, L):
         """Cv (rows x cols view, row stride ldc) -= W (rows x b) @ L (cols x b)^T"""
@@ -156,27 +169,31 @@ class CudaTileOps(object):
 
     # ---- replicated solve on the gathered factor
     def make_solver(self, n, diags, panels):
+        """Replicated solver on the gathered factor.  The native handle and the staging buffers are created ONCE per order
+        and re-used by later factorisations (creating / destroying a 10 GB workspace costs tens of milliseconds of
+        synchronous cudaMalloc / cudaFree)."""
         b, nt = self.b, self.nt
         nblk = n // NB
-        A = self.zeros(n, n)
-        linvp = self.empty(nblk, NB, NB)
-        dinfo = self.zeros(4, n)
-        kind = torch.zeros(n, dtype=torch.int32, device=self.device)
+        cache = getattr(self, '_solver_cache', None)
+        if cache is None or cache[0] != n:
+            stream = self._lib.torch_stream_handle(self.device)
+            cache = (n, self.zeros(n, n), self.empty(nblk, NB, NB), self.zeros(4, n),
+                     torch.zeros(n, dtype=torch.int32, device=self.device),
+                     self._lib.DenseLDLT(n, device=self.device.index, stream=stream))
+            self._solver_cache = cache
+        _, A, linvp, dinfo, kind, F = cache
         for k, diag in enumerate(diags):
             r0 = k * b
             A[r0:r0 + b, r0:r0 + b] = diag[:b * b].view(b, b)
             if panels[k] is not None:
                 A[r0 + b:, r0:r0 + b] = panels[k]
-            for t in range(nt):
-                linv, dblk = self._tile(diag, t)
-                g0 = r0 + t * NB
-                linvp[g0 // NB] = linv.view(NB, NB)
-                dinfo[:, g0:g0 + NB] = dblk[:4 * NB].view(4, NB)
-                kind[g0:g0 + NB] = dblk[4 * NB:].view(torch.int32)[:NB]
-        stream = self._lib.torch_stream_handle(self.device)
-        F = self._lib.DenseLDLT(n, device=self.device.index, stream=stream)
+        # per-tile factor data of all diagonal blocks in three batched copies
+        NT = self.tile_doubles
+        tiles = torch.stack([d[b * b:b * b + nt * NT].view(nt, NT) for d in diags]).reshape(nblk, NT)
+        linvp.copy_(tiles[:, :NB * NB].reshape(nblk, NB, NB))
+        dinfo.copy_(tiles[:, NB * NB:NB * NB + 4 * NB].reshape(nblk, 4, NB).permute(1, 0, 2).reshape(4, n))
+        kind.copy_(tiles[:, NB * NB + 4 * NB:].contiguous().view(torch.int32)[:, :NB].reshape(n))
         self._lib.check(self.lib.b200ipm_ldlt_import(F.h, A.data_ptr(), n, linvp.data_ptr(), dinfo.data_ptr(), kind.data_ptr()))
-        del A
         lib, chk = self.lib, self._lib.check
 
         def solve(Bt):   # Bt: nrhs x n contiguous device tensor, solved in place
@@ -234,7 +251,104 @@ class BlockCyclicLDLT(object):
         self.ri, self.ci = ri, ci
 
     def factor(self):
-        """-> inertia (pos, neg, zero).  Collective: every rank must call it.
+        """-> inertia (pos, neg, zero).  Collective: every rank must call it.  1 x Q grids take the block-column-cyclic
+        pipeline (`_factor_cols`), P > 1 the general 2-D one below."""
+        if self.P == 1:
+            return self._factor_cols()
+        return self._factor_2d()
+
+    def _factor_cols(self):
+        """1 x Q grid = 1-D block-column-cyclic: block column k lives whole on rank k mod Q, so the serial part of a step --
+        diagonal block (4 tile steps) and the panel below it -- never leaves one GPU, and a step has exactly ONE collective:
+        the broadcast of the contiguous record [factor data of the diagonal block | L | W = L D] from the owner (NVSwitch:
+        every peer at full bandwidth).  Look-ahead 1 on two streams: the UPDATE stream of the owner of column k + 1 updates
+        that block column first; its CHAIN stream (high priority) then factors it and broadcasts while every rank is still
+        applying panel k to the rest of its block columns.  The records are persistent (one buffer per block column, reused
+        by later factorisations): no ring, no reshuffling copies; they are also what the replicated solver imports."""
+        ops, b, Q, nbk = self.ops, self.b, self.Q, self.nbk
+        ds = ops.diag_size
+        dsp = (ds + 31) // 32 * 32     # L and W start on 256-byte boundaries (vectorised / TMA-staged kernels read them)
+        fused = hasattr(ops, 'colblock')     # CUDA backend: diagonal block + panel in one call (single-GPU panel schedule)
+        if getattr(self, '_pan', None) is None:
+            # record of block column k: [factor data of the diagonal block | L (rows x b) | b x b scratch (W of the diagonal
+            # block's own rows) | W (rows x b)], contiguous: one broadcast
+            self._pan = [ops.empty(dsp + (2 * (nbk - 1 - k) + 1) * b * b) for k in range(nbk)]
+            self._work = ops.empty(*self.A0.shape)
+        work = self._work
+        work.copy_(self.A0)
+        self.diags, self.panels, self._pgrp = [], [], None
+        ev_look = ops.record()         # block column 0 is ready: `work` is a fresh clone made on the update stream
+        prof = [] if getattr(self, 'profile', False) else None     # per-column timing events (tools/prof_dist.py)
+        tev = (lambda: ops.record_timed()) if prof is not None else (lambda: None)
+        for k in range(nbk):
+            owner = k % Q
+            rows = (nbk - 1 - k) * b
+            buf = self._pan[k]
+            diag = buf[:ds]
+            Lk = buf[dsp:dsp + rows * b].view(rows, b) if rows else None
+            Wd = buf[dsp + rows * b:]                                   # (b + rows) x b: W of the whole block column
+            Wk = Wd[b * b:].view(rows, b) if rows else None
+            with ops.chain():
+                t0 = t1 = t2 = None
+                if owner == self.q:
+                    ops.wait(ev_look)
+                    t0 = tev()
+                    lj = k // Q
+                    if fused:
+                        ops.colblock(work[k * b:, lj * b:(lj + 1) * b], diag, Wd, chain=True)
+                        t1 = tev()
+                        if rows:
+                            Lk.copy_(work[(k + 1) * b:, lj * b:(lj + 1) * b])
+                    else:
+                        ops.factor_diag(work[k * b:(k + 1) * b, lj * b:(lj + 1) * b], diag, chain=True)
+                        t1 = tev()
+                        if rows:
+                            Bv = work[(k + 1) * b:, lj * b:(lj + 1) * b]
+                            ops.panel(Bv, diag, chain=True, out=Wk)
+                            Lk.copy_(Bv)
+                    t2 = tev()
+                tb0 = tev()
+                self._bcast(buf, self._rank_of(0, owner))
+                ev_panel = ops.record()
+                tb1 = tev()
+            self.diags.append(diag)
+            self.panels.append(Lk)
+            if not rows:
+                break
+            # trailing update of my block columns J > k:  A[J.., J] -= W[J..] L[J]^T, block column k + 1 first
+            ops.wait(ev_panel)
+            ev_look = None
+            mycols = [J for J in self.cols_blk if J > k]
+            tu0 = tev()
+            tu1 = None
+            if mycols:
+                lj0 = mycols[0] // Q
+                rest = mycols
+                if mycols[0] == k + 1:
+                    ops.update_bc(work[(k + 1) * b:, lj0 * b:(lj0 + 1) * b], Wk, Lk[:b], (1, Q), (0, self.q), k + 1, lj0)
+                    ev_look = ops.record()
+                    tu1 = tev()
+                    rest, lj0 = mycols[1:], lj0 + 1
+                if rest:
+                    if Q == 1:
+                        Lm = Lk[(rest[0] - k - 1) * b:]
+                    else:
+                        pos = np.concatenate([np.arange(b) + (J - k - 1) * b for J in rest])
+                        Lm = Lk.index_select(0, ops.index(pos))             # L rows of my block columns
+                    ops.update_bc(work[(k + 1) * b:, lj0 * b:], Wk, Lm, (1, Q), (0, self.q), k + 1, lj0)
+            if ev_look is None:
+                ev_look = ops.record()
+            if prof is not None:
+                prof.append((k, owner, t0, t1, t2, tb0, tb1, tu0, tu1, tev()))
+        ops.sync()
+        if prof is not None:
+            self.profile_events = prof
+        self.inertia = tuple(int(v) for v in ops.counts_all(self.diags))   # one synchronisation at the very end
+        self._solver = None
+        return self.inertia
+
+    def _factor_2d(self):
+        """General P x Q grid.
 
         Pipeline with look-ahead 1 on two streams.  CHAIN stream (high priority), per block column k: wait until column k
         carries every update through step k - 1; the owner of (k, k) factors the diagonal block and broadcasts its factor
@@ -339,7 +453,8 @@ class BlockCyclicLDLT(object):
     def solve_device(self, Bt, nrefine=1):
         """Bt: nrhs x n device tensor -> X (nrhs x n device tensor)."""
         if self._solver is None:
-            self.panels = self._global_panels()
+            if self._pgrp is not None:
+                self.panels = self._global_panels()
             self._solver = self.ops.make_solver(self.n, self.diags, self.panels)
         X = self._solver(Bt.clone())
         for _ in range(nrefine):
@@ -356,4 +471,6 @@ class BlockCyclicLDLT(object):
 
 
 def choose_grid(world):
-    return {1: (1, 1), 2: (1, 2), 4: (2, 2), 8: (2, 4)}.get(world, (1, world))
+    # block-column-cyclic (1 x world): one broadcast per block column and a serial chain that never leaves a GPU; the 2-D
+    # grids (2 x 2, 2 x 4) measured slower on NVSwitch, where every peer is one hop away at full bandwidth
+    return (1, world)

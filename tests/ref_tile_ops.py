@@ -46,13 +46,17 @@ class RefTileOps(object):
         b = self.b
         return diag[:b * b].view(b, b).numpy(), diag[b * b:2 * b * b].view(b, b).numpy()
 
-    def panel(self, Bblk, diag, chain=False):
+    def panel(self, Bblk, diag, chain=False, out=None):
         lu, d = self._unpack(diag)
         B = Bblk.numpy()
         W = np.linalg.solve(lu, B.T).T
         L = np.linalg.solve(d.T, W.T).T
         Bblk.copy_(torch.from_numpy(np.ascontiguousarray(L)))
-        return torch.from_numpy(np.ascontiguousarray(W))
+        Wt = torch.from_numpy(np.ascontiguousarray(W))
+        if out is not None:
+            out.copy_(Wt)
+            return out
+        return Wt
 
     def update(self, Cv, W, L):
         Cv.sub_(W @ L.t())

@@ -63,6 +63,19 @@ def test_block_cyclic_ldlt_world2_gloo(grid, tmp_path):
     assert np.max(np.abs(res['X'] - Xref)) / np.max(np.abs(Xref)) < 1e-9
 
 
+def test_block_column_cyclic_ldlt_world3_gloo(tmp_path):
+    """1 x 3 grid: eight block columns over three ranks (ragged ownership), the look-ahead owner changes every step."""
+    n, b = 64, 8
+    out = str(tmp_path / 'res.npz')
+    mp.spawn(_worker, args=(3, _free_port(), (1, 3), n, b, out), nprocs=3, join=True)
+    K, rhs = kkt_matrix(n, n // 4, 5)
+    res = np.load(out)
+    w = np.linalg.eigvalsh(K)
+    assert tuple(res['inertia']) == (int(np.sum(w > 0)), int(np.sum(w < 0)), 0)
+    Xref = np.linalg.solve(K, rhs)
+    assert np.max(np.abs(res['X'] - Xref)) / np.max(np.abs(Xref)) < 1e-9
+
+
 def test_block_cyclic_ldlt_single_rank():
     n, b = 48, 8
     K, rhs = kkt_matrix(n, 12, 9)
@@ -77,4 +90,4 @@ def test_block_cyclic_ldlt_single_rank():
 
 
 def test_choose_grid():
-    assert choose_grid(1) == (1, 1) and choose_grid(2) == (1, 2) and choose_grid(4) == (2, 2) and choose_grid(8) == (2, 4)
+    assert choose_grid(1) == (1, 1) and choose_grid(2) == (1, 2) and choose_grid(4) == (1, 4) and choose_grid(8) == (1, 8)

@@ -65,3 +65,36 @@ def test_block_cyclic_ldlt_two_ranks_nccl(tmp_path):
     assert np.max(np.abs(res['X'] - Xref)) / np.max(np.abs(Xref)) < 1e-6
     r = np.max(np.abs(K @ res['X'] - rhs)) / (np.max(np.abs(K)) * np.max(np.abs(res['X'])))
     assert r < 1e-13
+
+
+def test_pipeline_config4_size_chain_kernels_under_saturating_updates():
+    """Config-4 size (order 16384) on one rank: the look-ahead pipeline factors block column k + 1 on the high-priority chain
+    stream while the trailing update of panel k saturates every SM, so the CTAs of the chain's small kernels start at
+    different times.  Regression test of the 4-CTA mini step (its CTAs overwrite in place what their siblings read; a
+    cluster barrier now separates the loads from the stores): the scaled residual after one refinement sweep was 1e-11
+    with the race, 4e-18 without; the factor must also be reproducible run to run."""
+    import torch
+    n, m = 16384, 2048
+    nh = n - m
+    g = torch.Generator(device='cuda')
+    g.manual_seed(16384)
+    W = torch.randn(nh, nh, dtype=torch.float64, device='cuda', generator=g)
+    K = torch.zeros(n, n, dtype=torch.float64, device='cuda')
+    K[:nh, :nh] = W @ W.t() / nh
+    del W
+    K[:nh, :nh].diagonal().add_(10.0 ** (8.0 * torch.rand(nh, dtype=torch.float64, device='cuda', generator=g) - 4.0))
+    J = torch.randn(nh, m, dtype=torch.float64, device='cuda', generator=g)
+    K[:nh, nh:] = J
+    K[nh:, :nh] = J.t()
+    K[nh:, nh:].diagonal().fill_(-1e-8)
+    rhs = torch.randn(4, n, dtype=torch.float64, device='cuda', generator=g)
+    F = BlockCyclicLDLT(n, (1, 1), CudaTileOps(0), block=256)
+    F.load_device(K)
+    assert F.factor() == (nh, m, 0)
+    first = [p.clone() for p in F.panels[:8]]
+    X = F.solve_device(rhs, nrefine=1)
+    res = float((rhs - F.matvec(X)).abs().max() / (K.abs().max() * X.abs().max()))
+    assert res < 1e-15, res
+    assert F.factor() == (nh, m, 0)
+    for a, b in zip(first, F.panels[:8]):
+        assert torch.equal(a, b)
