@@ -235,10 +235,12 @@ int b200ipm_ldlt_block_panel(b200ipm_ldlt_handle h, double* B_dev, int ld, int r
 /* Block-column-cyclic driver, one call per block column: A_dev = top-left corner of the rows_total x b block column
  * (b = 256, rows_total a multiple of 64, >= b), factored with the single-GPU factorisation's panel schedule; L in place,
  * W = L D to Wb_dev (rows_total x b contiguous, row index = row of the block column), factor data of the diagonal block
- * packed into diag_dev (layout of block_factor).  The handle must have been created with order >= b.  Replaces
+ * packed into diag_dev (layout of block_factor).  The handle must have been created with order >= b.  rest_ready_event
+ * (a cudaEvent_t, or NULL): the rows below the b x b diagonal block are not touched before this event has fired -- the
+ * serial tile steps of the diagonal block overlap the tail of the previous panel's look-ahead update.  Replaces
  * block_factor + block_panel on a 1 x Q grid (sym_solve_cmp slot at config-4 size, pyipm.py:18-20). */
 int b200ipm_ldlt_colblock_factor(b200ipm_ldlt_handle h, double* A_dev, int ld, int rows_total, int b, double* diag_dev,
-                                 double* Wb_dev);
+                                 double* Wb_dev, void* rest_ready_event);
 /* y (rows) = A (rows x cols, row-major, leading dimension lda) * v: the residual's HBM-bound GEMV kernel on device pointers
  * (distributed refinement mat-vec of the block-cyclic driver); asynchronous on the handle's stream. */
 int b200ipm_ldlt_gemv(b200ipm_ldlt_handle h, const double* A_dev, int lda, int rows, int cols, const double* v_dev,

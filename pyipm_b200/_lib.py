@@ -141,7 +141,7 @@ def load():
         'b200ipm_ldlt_gemv': (i, [vp, vp, i, i, i, vp, vp]),
         'b200ipm_ldlt_block_factor': (i, [vp, vp, i, i, vp, vp]),
         'b200ipm_ldlt_block_panel': (i, [vp, vp, i, i, i, vp, vp]),
-        'b200ipm_ldlt_colblock_factor': (i, [vp, vp, i, i, i, vp, vp]),
+        'b200ipm_ldlt_colblock_factor': (i, [vp, vp, i, i, i, vp, vp, vp]),
         'b200ipm_trace_start': (i, []),
         'b200ipm_trace_dump': (i, [vp, vp, vp, vp, vp, i, ip]),
     }

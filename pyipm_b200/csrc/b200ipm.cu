@@ -2330,7 +2330,7 @@ __global__ void diag_pack_kernel(const double* __restrict__ A, int ld, int b, co
     }
 }
 int b200ipm_ldlt_colblock_factor(b200ipm_ldlt_handle h, double* A_dev, int ld, int rows_total, int b, double* diag_dev,
-                                 double* Wb_dev) {
+                                 double* Wb_dev, void* rest_ready_event) {
     if (!h || !A_dev || !diag_dev || !Wb_dev || b != NBO || rows_total < b || (rows_total % NB) != 0)
         return fail_msg("colblock_factor: bad arguments");
     if (h->F.n < b) return fail_msg("colblock_factor: the handle's order must be at least the block size");
@@ -2341,8 +2341,10 @@ int b200ipm_ldlt_colblock_factor(b200ipm_ldlt_handle h, double* A_dev, int ld, i
     double* A_save = F.A;
     const int ld_save = F.ld, n_save = F.n;
     F.A = A_dev; F.ld = ld; F.n = rows_total;
+    F.col_rest_event = reinterpret_cast<cudaEvent_t>(rest_ready_event);
     const int rc = ldlt_factor_launch(F, h->st, Wb_dev);
     F.A = A_save; F.ld = ld_save; F.n = n_save;
+    F.col_rest_event = nullptr;
     RET(rc);
     const int npad = F.nblk * NB;
     diag_pack_kernel<<<b / NB, 256, 0, h->st>>>(A_dev, ld, b, F.LinvP, F.dinfo, npad, F.kind, diag_dev);

@@ -78,6 +78,7 @@ struct LdltWs {
     int nb256 = 0;
     int solve256 = 1;          // B200IPM_SOLVE256=0: the 64-row chain (ldlt_fwd_kernel / ldlt_bwd_kernel)
     int binv_mode = 1;         // where the block inverses are built: 1 one launch at the end (default), 0 per outer panel on the bulk stream
+    cudaEvent_t col_rest_event = nullptr;   // column-block mode: rows below the diagonal block are ready once this event fires
     double pivot_u = 0.01;     // threshold of the fast (unpivoted) tile attempt: accept step j iff |d_j| >= u * max_i |T[i][j]|
 };
 
@@ -1267,6 +1268,7 @@ inline int ldlt_factor_launch(LdltWs& w, cudaStream_t st, double* Wb0 = nullptr)
                     CU(cudaStreamWaitEvent(st, w.ev_a2, 0));
                     a2_pending = false;
                 }
+                if (Wb0 && w.col_rest_event) CU(cudaStreamWaitEvent(st, w.col_rest_event, 0));
                 ldlt_panel_kernel<<<cdiv(rows, NB), 128, PANEL_SMEM, st>>>(B, ld, rows, Lk, ia + k0, ib + k0, w.kind + k0, Wt, NBO, w.counts);
                 LAUNCHED();
                 if (mcols > 0) RET(gemm_nt_sub(st, C11, ld, rows, mcols, Wt, NBO, B, ld, NB, w.counts, 0, tW, tA));
@@ -1276,6 +1278,9 @@ inline int ldlt_factor_launch(LdltWs& w, cudaStream_t st, double* Wb0 = nullptr)
                 LAUNCHED();
                 CU(cudaEventRecord(w.ev_mini, st));
                 CU(cudaStreamWaitEvent(w.upd, w.ev_tile, 0));
+                // column-block mode: tile and mini steps stay inside the 256 x 256 diagonal block; everything below it
+                // may still be receiving the look-ahead update of the previous panel
+                if (Wb0 && w.col_rest_event && k0 == c0) CU(cudaStreamWaitEvent(w.upd, w.col_rest_event, 0));
                 ldlt_panel_kernel<<<cdiv(rows - NB, NB), 128, PANEL_SMEM, w.upd>>>(B + (size_t)NB * ld, ld, rows - NB, Lk, ia + k0, ib + k0,
                                                                                    w.kind + k0, Wt + (size_t)NB * NBO, NBO, w.counts);
                 LAUNCHED();

@@ -38,7 +38,7 @@ constexpr int OZ_KMAX = 18432;               // OZ_NS * K * 2^14 < 2^31
 constexpr int OZ_KB = 32;                    // int8 elements (bytes) of K per pipeline stage = one MMA K step
 constexpr int OZ_BM = 128;                   // rows per block (UMMA M)
 constexpr int OZ_CHUNK = OZ_BM * OZ_KB;      // bytes of one slice of one row block for one k-block
-constexpr int OZ_THREADS = 192;
+constexpr int OZ_THREADS = 320;   // producer warp, MMA warp, 8 epilogue warps (two per TMEM lane quarter)
 constexpr unsigned OZ_SMEM_BUDGET = 200 * 1024;
 
 struct OzTerm { const double* A; const double* w; int lda, K, koff, sgn, vec; double alpha; };   // koff: multiple of OZ_KB; vec: 16-byte loads ok
@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzGemmArgs
             oz_mbar_init(oz_smem_u32(&bar_empty[s]), 1);
         }
         oz_mbar_init(oz_smem_u32(&bar_tfull), 1);
-        oz_mbar_init(oz_smem_u32(&bar_tempty), 4);
+        oz_mbar_init(oz_smem_u32(&bar_tempty), 8);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     for (int c = tid; c < BN; c += OZ_THREADS) s_cscale[c] = scalbn(1.0, ((col0 + c < ncol) ? rexp_c[col0 + c] : 0) - 7);
@@ -438,15 +438,20 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzGemmArgs
             __syncwarp();
         }
     } else {
-        // ===== epilogue: warp (warp & 3) owns TMEM lanes 32*(warp & 3) .. +31 = tile rows.  Per 8-column chunk: the
-        // global operands (partial sum of the higher diagonals, Cin) are prefetched one chunk ahead, the int32
-        // accumulators of the pass are read with tcgen05.ld, recombined by Horner in fp64 and scaled by exact powers of 2.
+        // ===== epilogue: warps 2..9; warp (warp & 3) owns TMEM lanes 32*(warp & 3) .. +31 = tile rows, and the two warps of
+        // a lane quarter take alternate 8-column chunks.  Per chunk: the global operands (partial sum of the higher
+        // diagonals, Cin) are prefetched ahead -- ALL of them before the accumulators are complete when the kernel has a
+        // single pass (the in-place LDL^T updates: their latency hides behind the MMA phase) --, the int32 accumulators of
+        // the pass are read with tcgen05.ld, recombined by Horner in fp64 and scaled by exact powers of 2.
         const int q4 = warp & 3;
+        const int half = (warp - 2) >> 2;
         const int rl = q4 * 32 + lane;
         const int i = row0 + rl;
         const bool rowok = i < a.n;
         const int ei = rowok ? a.rexp[i] : 0;
         const double dii = rowok ? (a.shift + (a.dadd ? a.dadd[i] : 0.0)) : 0.0;
+        constexpr int NCH = BN / 16;              // chunks per epilogue warp
+        constexpr bool PRE_ALL = (NPASS == 1) && (NCH <= 4);
 #pragma unroll
         for (int pi = 0; pi < NPASS; pi++) {
             const int d_lo = S::d_lo(pi), d_hi = S::d_hi(pi);
@@ -455,6 +460,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzGemmArgs
             const bool need_part = (pi > 0), need_cin = last && (a.Cin != nullptr);
             const double si = scalbn(1.0, ei - 7 - 8 * d_lo);
             double pre_p[8], pre_c[8];
+            double pre_all[PRE_ALL ? NCH * 8 : 1];
             auto prefetch = [&](int cb) {
 #pragma unroll
                 for (int c = 0; c < 8; c++) {
@@ -464,19 +470,21 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzGemmArgs
                     pre_c[c] = (ok && need_cin) ? a.Cin[(size_t)i * a.ldcin + j] : 0.0;
                 }
             };
-            prefetch(0);
+            if (PRE_ALL) {
+#pragma unroll
+                for (int k = 0; k < (PRE_ALL ? NCH : 0); k++)
+#pragma unroll
+                    for (int c = 0; c < 8; c++) {
+                        const int j = col0 + (half + 2 * k) * 8 + c;
+                        const bool ok = rowok && j < ncol && (a.lower ? i >= j : i <= j);
+                        pre_all[k * 8 + c] = (ok && need_cin) ? a.Cin[(size_t)i * a.ldcin + j] : 0.0;
+                    }
+            } else {
+                prefetch(half);
+            }
             oz_mbar_wait(oz_smem_u32(&bar_tfull), (uint32_t)pi & 1u, dead, a.err);
             oz_tc_fence_after();
-            for (int cb = 0; cb < BN / 8; cb++) {
-                int acc[MAXD][8];
-#pragma unroll
-                for (int dd = 0; dd < MAXD; dd++)
-                    if (dd < dn) oz_tmem_ld8(tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(dd * BN + cb * 8), acc[dd]);
-                double cur_p[8], cur_c[8];
-#pragma unroll
-                for (int c = 0; c < 8; c++) { cur_p[c] = pre_p[c]; cur_c[c] = pre_c[c]; }
-                if (cb + 1 < BN / 8) prefetch(cb + 1);
-                oz_tmem_wait_ld();
+            auto chunk = [&](int cb, const double* cur_p, const double* cur_c, int (&acc)[MAXD][8]) {
                 if (rowok) {
 #pragma unroll
                     for (int c = 0; c < 8; c++) {
@@ -497,6 +505,32 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_syrk_kernel(const OzGemmArgs
                             *cp = v;
                         }
                     }
+                }
+            };
+            if (PRE_ALL) {
+                const double zero8[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+                for (int k = 0; k < (PRE_ALL ? NCH : 0); k++) {
+                    const int cb = half + 2 * k;
+                    int acc[MAXD][8];
+#pragma unroll
+                    for (int dd = 0; dd < MAXD; dd++)
+                        if (dd < dn) oz_tmem_ld8(tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(dd * BN + cb * 8), acc[dd]);
+                    oz_tmem_wait_ld();
+                    chunk(cb, zero8, pre_all + k * 8, acc);
+                }
+            } else {
+                for (int cb = half; cb < BN / 8; cb += 2) {
+                    int acc[MAXD][8];
+#pragma unroll
+                    for (int dd = 0; dd < MAXD; dd++)
+                        if (dd < dn) oz_tmem_ld8(tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(dd * BN + cb * 8), acc[dd]);
+                    double cur_p[8], cur_c[8];
+#pragma unroll
+                    for (int c = 0; c < 8; c++) { cur_p[c] = pre_p[c]; cur_c[c] = pre_c[c]; }
+                    if (cb + 2 < BN / 8) prefetch(cb + 2);
+                    oz_tmem_wait_ld();
+                    chunk(cb, cur_p, cur_c, acc);
                 }
             }
             oz_tc_fence_before();

@@ -108,12 +108,14 @@ class CudaTileOps(object):
                                                           diag.data_ptr(), W.data_ptr()))
         return W
 
-    def colblock(self, Acol, diag, Wb, chain=True):
+    def colblock(self, Acol, diag, Wb, chain=True, rest_event=None):
         """Acol: (rows_total x b) view of a whole block column from its diagonal block down (row stride ld): factored in
-        place with the single-GPU panel schedule (one C call); Wb (rows_total x b, contiguous) <- W = L D; fills `diag`."""
+        place with the single-GPU panel schedule (one C call); Wb (rows_total x b, contiguous) <- W = L D; fills `diag`.
+        rest_event: the rows below the diagonal block are not touched before this (recorded) event has fired."""
         ctx = self.ctx_chain if chain else self.ctx
+        ev = C.c_void_p(rest_event.cuda_event) if rest_event is not None else None
         self._lib.check(self.lib.b200ipm_ldlt_colblock_factor(ctx.h, Acol.data_ptr(), Acol.stride(0), Acol.shape[0], self.b,
-                                                              diag.data_ptr(), Wb.data_ptr()))
+                                                              diag.data_ptr(), Wb.data_ptr(), ev))
 
     def update(self, Cv, W, L):
         """Cv (rows x cols view, row stride ldc) -= W (rows x b) @ L (cols x b)^T"""
@@ -277,7 +279,8 @@ class BlockCyclicLDLT(object):
         work = self._work
         work.copy_(self.A0)
         self.diags, self.panels, self._pgrp = [], [], None
-        ev_look = ops.record()         # block column 0 is ready: `work` is a fresh clone made on the update stream
+        ev_look = ops.record()         # block column 0 is ready: `work` is a fresh copy made on the update stream
+        ev_rest = None                 # ... and so are its rows below the diagonal block
         prof = [] if getattr(self, 'profile', False) else None     # per-column timing events (tools/prof_dist.py)
         tev = (lambda: ops.record_timed()) if prof is not None else (lambda: None)
         for k in range(nbk):
@@ -294,8 +297,10 @@ class BlockCyclicLDLT(object):
                     ops.wait(ev_look)
                     t0 = tev()
                     lj = k // Q
+                    if not fused:
+                        ops.wait(ev_rest)
                     if fused:
-                        ops.colblock(work[k * b:, lj * b:(lj + 1) * b], diag, Wd, chain=True)
+                        ops.colblock(work[k * b:, lj * b:(lj + 1) * b], diag, Wd, chain=True, rest_event=ev_rest)
                         t1 = tev()
                         if rows:
                             Lk.copy_(work[(k + 1) * b:, lj * b:(lj + 1) * b])
@@ -325,8 +330,15 @@ class BlockCyclicLDLT(object):
                 lj0 = mycols[0] // Q
                 rest = mycols
                 if mycols[0] == k + 1:
-                    ops.update_bc(work[(k + 1) * b:, lj0 * b:(lj0 + 1) * b], Wk, Lk[:b], (1, Q), (0, self.q), k + 1, lj0)
+                    # the next block column first, its diagonal block before the rows below it: the owner's chain stream
+                    # starts the serial tile steps as soon as the diagonal block is up to date
+                    col = work[(k + 1) * b:, lj0 * b:(lj0 + 1) * b]
+                    ops.update_bc(col[:b], Wk[:b], Lk[:b], (1, Q), (0, self.q), k + 1, lj0)
                     ev_look = ops.record()
+                    ev_rest = None
+                    if rows > b:
+                        ops.update_bc(col[b:], Wk[b:], Lk[:b], (1, Q), (0, self.q), k + 2, lj0)
+                        ev_rest = ops.record()
                     tu1 = tev()
                     rest, lj0 = mycols[1:], lj0 + 1
                 if rest:
