@@ -241,6 +241,15 @@ int b200ipm_ldlt_block_panel(b200ipm_ldlt_handle h, double* B_dev, int ld, int r
  * block_factor + block_panel on a 1 x Q grid (sym_solve_cmp slot at config-4 size, pyipm.py:18-20). */
 int b200ipm_ldlt_colblock_factor(b200ipm_ldlt_handle h, double* A_dev, int ld, int rows_total, int b, double* diag_dev,
                                  double* Wb_dev, void* rest_ready_event);
+/* tcgen05 trailing updates of the block-column-cyclic driver (int8 error-free split, 21 slice pairs, in place):
+ * oz_panel_slice -- digits of W (rows x 256) and -L (rows x 256) of the current panel, once per panel (max_rows sizes
+ * the workspace at the first call); oz_block_update -- C (n x ncols lower trapezoid, origin on the diagonal, starting
+ * row_off rows below the first sliced row; n, row_off multiples of 128) -= W L'; oz_status -- reads and clears the
+ * error word (1: non-finite operand, 4: pipeline timeout).  All asynchronous on the handle's stream but oz_status. */
+int b200ipm_oz_panel_slice(b200ipm_ldlt_handle h, int rows, const double* W_dev, int ldw, const double* L_dev, int ldl,
+                           int max_rows);
+int b200ipm_oz_block_update(b200ipm_ldlt_handle h, double* C_dev, int ldc, int n, int ncols, int row_off);
+int b200ipm_oz_status(b200ipm_ldlt_handle h, int* err_word);
 /* y (rows) = A (rows x cols, row-major, leading dimension lda) * v: the residual's HBM-bound GEMV kernel on device pointers
  * (distributed refinement mat-vec of the block-cyclic driver); asynchronous on the handle's stream. */
 int b200ipm_ldlt_gemv(b200ipm_ldlt_handle h, const double* A_dev, int lda, int rows, int cols, const double* v_dev,

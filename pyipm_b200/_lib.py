@@ -64,7 +64,7 @@ SYMBOLS = [
     'b200ipm_ldlt_create', 'b200ipm_ldlt_destroy', 'b200ipm_ldlt_factor', 'b200ipm_ldlt_solve',
     'b200ipm_ldlt_tile_factor', 'b200ipm_ldlt_panel', 'b200ipm_ldlt_import', 'b200ipm_gemm_nt_update', 'b200ipm_gemm_nt_update_bc', 'b200ipm_test_syrk', 'b200ipm_test_syrk_i8', 'b200ipm_trace_start', 'b200ipm_trace_dump',
     'b200ipm_test_gemv', 'b200ipm_lbfgs_init', 'b200ipm_lbfgs_update', 'b200ipm_lbfgs_direction', 'b200ipm_lbfgs_step',
-    'b200ipm_lbfgs_state', 'b200ipm_batch_solve_poly', 'b200ipm_soc_direction', 'b200ipm_ldlt_gemv', 'b200ipm_ldlt_block_factor', 'b200ipm_ldlt_block_panel', 'b200ipm_ldlt_colblock_factor',
+    'b200ipm_lbfgs_state', 'b200ipm_batch_solve_poly', 'b200ipm_soc_direction', 'b200ipm_ldlt_gemv', 'b200ipm_ldlt_block_factor', 'b200ipm_ldlt_block_panel', 'b200ipm_ldlt_colblock_factor', 'b200ipm_oz_panel_slice', 'b200ipm_oz_block_update', 'b200ipm_oz_status',
 ]
 
 _lib = None
@@ -142,6 +142,9 @@ def load():
         'b200ipm_ldlt_block_factor': (i, [vp, vp, i, i, vp, vp]),
         'b200ipm_ldlt_block_panel': (i, [vp, vp, i, i, i, vp, vp]),
         'b200ipm_ldlt_colblock_factor': (i, [vp, vp, i, i, i, vp, vp, vp]),
+        'b200ipm_oz_panel_slice': (i, [vp, i, vp, i, vp, i, i]),
+        'b200ipm_oz_block_update': (i, [vp, vp, i, i, i, i]),
+        'b200ipm_oz_status': (i, [vp, vp]),
         'b200ipm_trace_start': (i, []),
         'b200ipm_trace_dump': (i, [vp, vp, vp, vp, vp, i, ip]),
     }

@@ -116,6 +116,8 @@ struct b200ipm_ldlt {
     bool own_stream = false;
     bool factored = false;
     bool tile_counts_live = false;
+    OzUpdWs ozd;               // digits of the current panel for the tcgen05 trailing updates of the block-column-cyclic driver
+    int* ozd_err = nullptr;    // their device error word
 };
 
 template <typename T>
@@ -2138,6 +2140,8 @@ int b200ipm_ldlt_destroy(b200ipm_ldlt_handle h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->st);
     ldlt_free(h->F);
+    oz_upd_free(h->ozd);
+    cudaFree(h->ozd_err);
     cudaFree(h->A0); cudaFree(h->b); cudaFree(h->x); cudaFree(h->r); cudaFree(h->c);
     if (h->own_stream) cudaStreamDestroy(h->st);
     delete h;
@@ -2349,6 +2353,40 @@ int b200ipm_ldlt_colblock_factor(b200ipm_ldlt_handle h, double* A_dev, int ld, i
     const int npad = F.nblk * NB;
     diag_pack_kernel<<<b / NB, 256, 0, h->st>>>(A_dev, ld, b, F.LinvP, F.dinfo, npad, F.kind, diag_dev);
     LAUNCHED();
+    return 0;
+}
+
+// tcgen05 trailing updates for the block-column-cyclic driver (the same int8 error-free split as inside the single-GPU
+// factorisation: 21 slice pairs, in place on the lower trapezoid).  panel_slice: digits of W (rows x 256) and of -L (rows x
+// 256) of the current panel, ONCE per panel; block_update: C (n x ncols lower trapezoid with its origin on the diagonal, the
+// piece starting row_off rows below the first sliced row) -= W L' from those digits.  max_rows sizes the workspace at the
+// first call.  A non-finite operand raises the handle's error word (b200ipm_oz_status).
+int b200ipm_oz_panel_slice(b200ipm_ldlt_handle h, int rows, const double* W_dev, int ldw, const double* L_dev, int ldl, int max_rows) {
+    if (!h || !W_dev || !L_dev || rows <= 0) return fail_msg("oz_panel_slice: bad arguments");
+    CU(cudaSetDevice(h->device));
+    if (h->ozd.nmax < rows) {
+        CU(cudaStreamSynchronize(h->st));
+        oz_upd_free(h->ozd);
+        RET(oz_upd_alloc(h->ozd, std::max(rows, max_rows), NBO));
+        if (!h->ozd_err) { RET(dalloc(&h->ozd_err, 1)); CU(cudaMemset(h->ozd_err, 0, sizeof(int))); }
+    }
+    return oz_panel_slice(h->st, rows, W_dev, ldw, L_dev, ldl, NBO, h->ozd, 0, h->ozd_err, nullptr);
+}
+int b200ipm_oz_block_update(b200ipm_ldlt_handle h, double* C_dev, int ldc, int n, int ncols, int row_off) {
+    if (!h || !C_dev || n <= 0 || ncols <= 0 || (row_off % OZ_BM) != 0 || (n % OZ_BM) != 0) return fail_msg("oz_block_update: bad arguments");
+    if (h->ozd.nmax < n + row_off) return fail_msg("oz_block_update: slice the panel first");
+    CU(cudaSetDevice(h->device));
+    RET(oz_upd_tiles(h->ozd, n, ncols));
+    return oz_panel_update(h->st, C_dev, ldc, n, ncols, row_off / OZ_BM, NBO, h->ozd, 0, h->ozd_err, nullptr, 0);
+}
+int b200ipm_oz_status(b200ipm_ldlt_handle h, int* err_word) {
+    if (!h || !err_word) return fail_msg("oz_status: bad arguments");
+    *err_word = 0;
+    if (!h->ozd_err) return 0;
+    CU(cudaSetDevice(h->device));
+    CU(cudaMemcpyAsync(err_word, h->ozd_err, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    CU(cudaStreamSynchronize(h->st));
+    if (*err_word) CU(cudaMemsetAsync(h->ozd_err, 0, sizeof(int), h->st));
     return 0;
 }
 

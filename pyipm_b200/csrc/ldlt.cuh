@@ -152,6 +152,9 @@ inline int ldlt_alloc(LdltWs& w, int n, cudaStream_t st, bool background = false
         const char* e = getenv("B200IPM_LDLT_TC");
         w.tc_update = (e ? atoi(e) : 1) && n >= 2048;
         const char* c = getenv("B200IPM_LDLT_TC_CTAS");
+        // config-3 size: waves of 96 CTAs leave SMs to the chain kernels (the factorisation is chain-bound); from order 8192
+        // on the updates are the bound and every tile goes out in one launch (measured at order 16384: 63 -> 47 ms)
+        w.tc_ctas = (n >= 8192) ? 0 : 96;
         if (c) w.tc_ctas = atoi(c);
         if (w.tc_update) {
             RET(oz_upd_alloc(w.tcu, n, 256));

@@ -28,6 +28,7 @@ exercised on CPU (gloo, world_size 2) with a reference implementation (tests/tes
 from __future__ import print_function
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -116,6 +117,23 @@ class CudaTileOps(object):
         ev = C.c_void_p(rest_event.cuda_event) if rest_event is not None else None
         self._lib.check(self.lib.b200ipm_ldlt_colblock_factor(ctx.h, Acol.data_ptr(), Acol.stride(0), Acol.shape[0], self.b,
                                                               diag.data_ptr(), Wb.data_ptr(), ev))
+
+    # ---- tcgen05 trailing updates (int8 error-free split, the kernels of the single-GPU factorisation)
+    def tc_slice(self, W, L, max_rows):
+        """digits of W (rows x b) and -L (rows x b) of the current panel, once per panel"""
+        self._lib.check(self.lib.b200ipm_oz_panel_slice(self.ctx.h, W.shape[0], W.data_ptr(), W.stride(0), L.data_ptr(),
+                                                        L.stride(0), int(max_rows)))
+
+    def tc_update(self, Cv, row_off):
+        """Cv (n x ncols lower trapezoid with its origin on the diagonal; its first row is row `row_off` of the sliced
+        panel) -= W L^T, in place"""
+        self._lib.check(self.lib.b200ipm_oz_block_update(self.ctx.h, Cv.data_ptr(), Cv.stride(0), Cv.shape[0], Cv.shape[1],
+                                                         int(row_off)))
+
+    def tc_status(self):
+        err = C.c_int(0)
+        self._lib.check(self.lib.b200ipm_oz_status(self.ctx.h, C.byref(err)))
+        return err.value
 
     def update(self, Cv, W, L):
         """Cv (rows x cols view, row stride ldc) -= W (rows x b) @ L (cols x b)^T"""
@@ -271,6 +289,9 @@ class BlockCyclicLDLT(object):
         ds = ops.diag_size
         dsp = (ds + 31) // 32 * 32     # L and W start on 256-byte boundaries (vectorised / TMA-staged kernels read them)
         fused = hasattr(ops, 'colblock')     # CUDA backend: diagonal block + panel in one call (single-GPU panel schedule)
+        # ... and the trailing updates beyond the look-ahead column on tcgen05 (B200IPM_DIST_TC=0: fp64 DMMA)
+        use_tc = hasattr(ops, 'tc_slice') and os.environ.get('B200IPM_DIST_TC', '1') != '0'
+        tc_used = False
         if getattr(self, '_pan', None) is None:
             # record of block column k: [factor data of the diagonal block | L (rows x b) | b x b scratch (W of the diagonal
             # block's own rows) | W (rows x b)], contiguous: one broadcast
@@ -341,7 +362,19 @@ class BlockCyclicLDLT(object):
                         ev_rest = ops.record()
                     tu1 = tev()
                     rest, lj0 = mycols[1:], lj0 + 1
-                if rest:
+                if rest and use_tc:
+                    # digits of the panel once, then one in-place tcgen05 update per owned block column (a single launch
+                    # over the whole trailing trapezoid when this rank owns every column)
+                    ops.tc_slice(Wk, Lk, (nbk - 1) * b)
+                    tc_used = True
+                    if Q == 1:
+                        off = (rest[0] - k - 1) * b
+                        ops.tc_update(work[rest[0] * b:, rest[0] * b:], off)
+                    else:
+                        for J in rest:
+                            lj = J // Q
+                            ops.tc_update(work[J * b:, lj * b:(lj + 1) * b], (J - k - 1) * b)
+                elif rest:
                     if Q == 1:
                         Lm = Lk[(rest[0] - k - 1) * b:]
                     else:
@@ -353,6 +386,8 @@ class BlockCyclicLDLT(object):
             if prof is not None:
                 prof.append((k, owner, t0, t1, t2, tb0, tb1, tu0, tu1, tev()))
         ops.sync()
+        if tc_used and ops.tc_status():
+            raise FloatingPointError('block-column-cyclic LDL^T: non-finite entries met by the tcgen05 trailing update')
         if prof is not None:
             self.profile_events = prof
         self.inertia = tuple(int(v) for v in ops.counts_all(self.diags))   # one synchronisation at the very end
