@@ -1747,26 +1747,67 @@ int b200ipm_init_slack(b200ipm_handle h) {
 }
 // lda0 = pinv(J) df (pyipm.py:723-730): minimum-norm least squares through (J J' + eps I), iterated Tikhonov
 int b200ipm_init_lambda(b200ipm_handle h) {
+    // lda0 = pinv(J) df (pyipm.py:729-730): the minimum-norm least-squares solution of J lda = df, J = [dce | dci] (D x C),
+    // by NONSTATIONARY iterated Tikhonov on the SMALLER Gram matrix (J'J when C < D, J J' otherwise -- nonsingular whenever
+    // J has full rank, so the right-hand side of every sweep goes to zero with the residual and no null-space component is
+    // amplified by 1/t):   lda += (J'J + t I)^-1 J' (df - J lda)   resp.   lda += J' (J J' + t I)^-1 (df - J lda).
+    // A sweep contracts the component along a singular value sigma by t / (sigma^2 + t): with t = 1e-7 sigma_max^2 a
+    // well-conditioned Jacobian converges in two or three sweeps (the test below stops it); if the update is still large
+    // after six sweeps the Jacobian is ill conditioned and t drops to 1e-10, then 1e-13 (cond(J) up to ~1e6).  An update
+    // that has merely reached the rounding floor of its level (exactly dependent constraints) does NOT escalate: a smaller
+    // t would only amplify that floor.
     CU(cudaSetDevice(h->device));
     const int D = h->D, M = h->M, N = h->N, C = h->C;
     if (!C) return 0;
     RET(eval_derivs(h));
-    RET(ensure_F2(h, D));
+    const bool small = C < D;
+    const int ng = small ? C : D;
+    const double* Gop = h->J;
+    int ldg = h->ldJ, kg = C;
+    if (small) {
+        if (!h->Jt) RET(dalloc(&h->Jt, (size_t)C * rup(D, 16)));
+        ldg = (int)rup(D, 16);
+        RET(transpose(h->st, h->J, h->ldJ, D, C, h->Jt, ldg));
+        Gop = h->Jt;
+        kg = D;
+    }
+    RET(ensure_F2(h, ng));
     double scale = 0.0;
-    RET(max_row_sqnorm(h, h->J, h->ldJ, D, C, &scale));
-    const double tik = 1e-7 * (scale > 0.0 ? scale : 1.0);
-    GemmArgs a{};
-    a.C = h->F2.A; a.ldc = h->F2.ld; a.Cin = nullptr; a.dadd = nullptr; a.n = D; a.m = D; a.beta = 0.0; a.shift = tik;
-    a.mode = GEMM_UPPER_MIRROR; a.nterms = 1;
-    a.t[0] = GemmTerm{h->J, h->J, nullptr, h->ldJ, h->ldJ, C, 1.0};
-    RET(gemm_nt(h->st, a));
-    RET(ldlt_factor(h->F2));
+    RET(max_row_sqnorm(h, Gop, ldg, ng, kg, &scale));
+    if (!(scale > 0.0)) scale = 1.0;
     CU(cudaMemsetAsync(h->lam, 0, sizeof(double) * C, h->st));
-    for (int it = 0; it < 6; it++) {
-        // r = df - J lda ; u = G^-1 r ; lda += J' u
-        RET(gemv_n(h->st, h->J, h->ldJ, D, C, h->lam, h->df, 1.0, -1.0, h->wx));
-        RET(ldlt_solve(h->F2, h->wx, h->xt));
-        RET(gemv_t(h->st, h->J, h->ldJ, D, C, h->xt, h->lam, 1.0, 1.0, h->lam, h->scr));
+    static const double levels[3] = {1e-7, 1e-10, 1e-13};
+    bool done = false;
+    for (int lv = 0; lv < 3 && !done; lv++) {
+        GemmArgs a{};
+        a.C = h->F2.A; a.ldc = h->F2.ld; a.Cin = nullptr; a.dadd = nullptr; a.n = ng; a.m = ng; a.beta = 0.0;
+        a.shift = levels[lv] * scale; a.mode = GEMM_UPPER_MIRROR; a.nterms = 1;
+        a.t[0] = GemmTerm{Gop, Gop, nullptr, ldg, ldg, kg, 1.0};
+        RET(gemm_nt(h->st, a));
+        RET(ldlt_factor(h->F2));
+        const int nsweep = (lv == 2) ? 12 : 6;
+        double last = INFINITY;
+        for (int it = 0; it < nsweep; it++) {
+            RET(gemv_n(h->st, h->J, h->ldJ, D, C, h->lam, h->df, 1.0, -1.0, h->wx));              // r = df - J lda
+            double* upd = nullptr;
+            if (small) {
+                RET(gemv_t(h->st, h->J, h->ldJ, D, C, h->wx, nullptr, 0.0, 1.0, h->rho, h->scr));   // w = J' r
+                RET(ldlt_solve(h->F2, h->rho, h->ycor));                                            // u = (J'J + tI)^-1 w
+                upd = h->ycor;
+            } else {
+                RET(ldlt_solve(h->F2, h->wx, h->xt));                                               // u = (JJ' + tI)^-1 r
+                RET(gemv_t(h->st, h->J, h->ldJ, D, C, h->xt, nullptr, 0.0, 1.0, h->rho, h->scr));   // J' u
+                upd = h->rho;
+            }
+            axpby_kernel<<<cdiv(C, 256), 256, 0, h->st>>>(C, 1.0, h->lam, 1.0, upd, h->lam);
+            LAUNCHED();
+            absmax2_kernel<<<1, 1024, 0, h->st>>>(C, upd, h->lam, h->red + 12);
+            LAUNCHED();
+            RET(fetch_red(h, h->red + 12, 2));
+            last = h->h_red[0] / std::max(h->h_red[1], 1e-300);
+            if (!(last > 1e-13)) { done = true; break; }
+        }
+        if (!(last > 1e-8)) done = true;      // at the rounding floor of this level: not slow convergence, do not escalate
     }
     if (N) {
         fix_lambda_kernel<<<cdiv(N, 256), 256, 0, h->st>>>(M, N, h->p.Ktol, h->lam);

@@ -541,3 +541,36 @@ def test_config2_own_init_lambda_with_dependent_box_constraints():
     assert np.all(np.isfinite(l1)) and p1.signal in (1, 2) and p2.signal in (1, 2)
     assert np.linalg.norm(x1 - x2) <= 1e-4 * (1.0 + np.linalg.norm(x2))
     assert abs(f1 - f2) <= 1e-6 * (1.0 + abs(f2))
+
+
+@pytest.mark.parametrize('D,M,N,cond', [(80, 30, 0, 1e6), (40, 12, 50, 1e6), (64, 16, 24, 1e3), (48, 48, 0, 1e5)])
+def test_init_lambda_ill_conditioned_jacobian(D, M, N, cond):
+    """a12 / ADVICE r1: lda0 = pinv(J) df (pyipm.py:729-730) for a Jacobian [dce | dci] with singular values graded over
+    `cond` -- both Gram sides (C < D: J'J, C >= D: J J') of the nonstationary iterated-Tikhonov solve, against NumPy's
+    minimum-norm least-squares solution.  Tolerance 1e-6 relative (the fixed six sweeps at t = 1e-7 of round 1 left the
+    components below sigma_max * 3e-4 unconverged: errors of order one at cond = 1e6)."""
+    rng = np.random.default_rng(D * 1000 + M + N)
+    C = M + N
+    r = min(D, C)
+    P, _ = np.linalg.qr(rng.standard_normal((D, r)))
+    Qm, _ = np.linalg.qr(rng.standard_normal((C, r)))
+    sig = np.logspace(0.0, -np.log10(cond), r)
+    J = (P * sig) @ Qm.T                                   # D x C
+    Qh = rng.standard_normal((D, D))
+    Qh = (Qh + Qh.T) / (2.0 * np.sqrt(D))
+    x0 = rng.standard_normal(D)
+    A = J[:, :M].T.copy()
+    G = J[:, M:].T.copy() if N else None
+    prob = problems.QuadProblem(Qh, rng.standard_normal(D), 0.0, A=A, b=np.zeros(M), G=G,
+                                r=(np.abs(rng.standard_normal(N)) + 5.0) if N else None, x0=x0, name='illcond')
+    eng = make_engine(prob)
+    eng.set_state(x0, np.ones(N), np.zeros(C), 0.2, 10.0, 0.0)
+    if N:
+        eng.init_slack()
+    eng.init_lambda()
+    _, _, lda, _, _, _ = eng.get_state()
+    eng.close()
+    lref = np.linalg.lstsq(J, prob.df(x0), rcond=None)[0]
+    if N:
+        lref[M:][lref[M:] < 0] = 1e-4
+    assert relinf(lda, lref) < 1e-6, relinf(lda, lref)
