@@ -307,6 +307,16 @@ def measure_c4(world, rank, local, n, steps, warmup, fp64_peak_tf=None):
         rec['native'] = native
     else:
         rec['implementation'] = 'pyipm_b200/dist_ldlt.py block-column-cyclic pipeline over NCCL'
+    # HBM leg of the record: every triangular solve streams the factor twice (forward + backward: n^2 * 8 bytes), the
+    # refinement mat-vec streams each rank's share of the original matrix; replicated solves => per-GPU traffic
+    nsolve = 8 * 2
+    sol_bytes = nsolve * float(n) * n * 8.0 + 8 * float(n) * n * 8.0 / world
+    rec['solve_bytes_per_gpu'] = sol_bytes
+    rec['solve_gbs_per_gpu'] = sol_bytes / (rec['solve_ms_8rhs_1refine'] * 1e-3) * 1e-9
+    try:
+        rec['solve_frac_of_hbm_peak'] = rec['solve_gbs_per_gpu'] / measured_peaks()[0]
+    except Exception:
+        pass
     if fp64_peak_tf:
         rec['fp64_peak_tf_per_gpu'] = fp64_peak_tf
         rec['frac_of_aggregate_fp64_peak'] = tfl / (world * fp64_peak_tf)

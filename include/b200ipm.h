@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define B200IPM_VERSION 102
+#define B200IPM_VERSION 103
 
 typedef struct b200ipm_engine* b200ipm_handle;
 typedef struct b200ipm_ldlt*   b200ipm_ldlt_handle;

@@ -378,21 +378,16 @@ __device__ __forceinline__ void tile_fast_blocked(double* __restrict__ Tf, doubl
         for (int r = 0; r < 8; r++)
 #pragma unroll
             for (int c = 0; c <= r; c++) a[r][c] = Tf[(c0 + r) * NBP + c0 + c];
-        const double lim = 1.0 / pivot_u;
+        // (the threshold test of the block's own multipliers and the sign bookkeeping of its pivots are NOT on this
+        // thread's instruction stream: 28 otherwise idle threads test the stored multipliers in phase (1b), the signs are
+        // read off sda after the last block)
 #pragma unroll
         for (int j = 0; j < 8; j++) {
             const double d = a[j][j];
             const double dinv = (d != 0.0) ? fast_rcp(d) : 0.0;
-            if (c0 + j < nb) {
-                allpos = allpos && (d > 0.0);
-                allneg = allneg && (d < 0.0);
-            }
             double l[8];
 #pragma unroll
-            for (int r = j + 1; r < 8; r++) {
-                l[r] = a[r][j] * dinv;
-                viol |= (fabs(l[r]) > lim) ? 1 : 0;          // |d_j| >= u |T[r][j]|  <=>  |l_rj| <= 1/u
-            }
+            for (int r = j + 1; r < 8; r++) l[r] = a[r][j] * dinv;
 #pragma unroll
             for (int r = j + 1; r < 8; r++)
 #pragma unroll
@@ -491,6 +486,12 @@ __device__ __forceinline__ void tile_fast_blocked(double* __restrict__ Tf, doubl
         // eight columns; rows are independent)
         {
             const int row = c0 + 8 + (int)threadIdx.x;
+            const int e0 = (int)threadIdx.x - 64;      // threads 64 .. 91: one multiplier of the diagonal block each
+            if (e0 >= 0 && e0 < 28) {
+                int r = 1, e = e0;
+                while (e >= r) { e -= r; r++; }
+                viol |= (fabs(Tf[(c0 + r) * NBP + c0 + e]) > 1.0 / pivot_u) ? 1 : 0;   // |d_j| >= u |T[r][j]|  <=>  |l_rj| <= 1/u
+            }
             if (row < NB) {
                 double t[8], l[8];
 #pragma unroll
@@ -636,7 +637,12 @@ __global__ void __launch_bounds__(TILE_THREADS) ldlt_tile_kernel(double* __restr
         int viol = 0;
         bool allpos = true, allneg = true;
         tile_fast_blocked(Tf, Xf, sda, xscr, s_pinv, nb, lane, warp, pivot_u, viol, allpos, allneg);
-        if (tid == 0) { s_sign[0] = allpos ? 1 : 0; s_sign[1] = allneg ? 1 : 0; }   // tracked by warp 0 (lane-uniform)
+        if (warp == 0) {   // signs of the pivots, read off sda (the routine ends with a CTA barrier)
+            for (int p2 = lane; p2 < nb; p2 += 32) { allpos = allpos && (sda[p2] > 0.0); allneg = allneg && (sda[p2] < 0.0); }
+            allpos = __all_sync(0xffffffffu, allpos);
+            allneg = __all_sync(0xffffffffu, allneg);
+            if (lane == 0) { s_sign[0] = allpos ? 1 : 0; s_sign[1] = allneg ? 1 : 0; }
+        }
         const int anyviol = __syncthreads_or(viol);
         const bool ap = s_sign[0] != 0, an = s_sign[1] != 0;
         fast_ok = ((!anyviol) || ap || an) ? 1 : 0;

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     raw = ctypes.CDLL(_lib.LIB_PATH)
     for name in header_symbols():
         assert hasattr(raw, name), name
-    assert lib.b200ipm_version() == 102
+    assert lib.b200ipm_version() == 103
 
 
 def test_struct_layouts_match_header():
