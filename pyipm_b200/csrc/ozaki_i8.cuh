@@ -155,26 +155,45 @@ __global__ void __launch_bounds__(256) oz_slice_kernel(const OzSliceArgs a) {
         // so R gets the digits of -v)
         const size_t base = ((size_t)(rb * a.nkb + (cc >> 1)) * OZ_NS) * OZ_CHUNK + g * 256 + (cc & 1) * 128 + r * 16;
         unsigned wl[OZ_NS][4], wr[OZ_NS][4];
+        // fixed point: X = rint(v * 2^(55 - e)), |X| < 2^54, then balanced base-256 digits d_i in [-128, 127] (d_6 in
+        // [-64, 64]) with X = sum_i d_i 256^i.  Adding the bias 128 * 256^i at every position turns them into the ordinary
+        // base-256 digits of Y = X + 0x00808080 80808080, so ALL SEVEN digits come from one 64-bit add, and the byte that is
+        // stored (the two's complement of d_i) is byte_i(Y) ^ 0x80; digit i is slice p = 6 - i.  The bytes of four
+        // consecutive elements are gathered into one 32-bit word per slice with three PRMTs.  (2^(55-e) is applied as two
+        // exact power-of-two factors: a single one would overflow for rows whose largest entry is below 2^-968.)
+        const int sh = 55 - e, sh_a = sh / 2, sh_b = sh - sh_a;
+        const double sc_a = __longlong_as_double((long long)(1023 + sh_a) << 52);
+        const double sc_b = __longlong_as_double((long long)(1023 + sh_b) << 52);
+        const unsigned long long BIAS = 0x0080808080808080ull;
 #pragma unroll
-        for (int p = 0; p < OZ_NS; p++)
+        for (int q = 0; q < 4; q++) {
+            unsigned lo[2][4], hi[2][4];
 #pragma unroll
-            for (int q = 0; q < 4; q++) wl[p][q] = wr[p][q] = 0u;
+            for (int k = 0; k < 4; k++) {
+                const int b = 4 * q + k;
+                const long long X0 = __double2ll_rn((v[b] * sc_a) * sc_b);
+                const unsigned long long Y0 = ((unsigned long long)X0 + BIAS) ^ BIAS;
+                lo[0][k] = (unsigned)Y0;
+                hi[0][k] = (unsigned)(Y0 >> 32);
+                if (write_r) {
+                    const long long X1 = ((negmask >> b) & 1u) ? -X0 : X0;
+                    const unsigned long long Y1 = ((unsigned long long)X1 + BIAS) ^ BIAS;
+                    lo[1][k] = (unsigned)Y1;
+                    hi[1][k] = (unsigned)(Y1 >> 32);
+                }
+            }
 #pragma unroll
-        for (int b = 0; b < 16; b++) {
-            // fixed point: X = rint(v * 2^(55 - e)), |X| < 2^54; balanced base-256 digits from the bottom by integer
-            // arithmetic: t = sign-extended low byte, X = (X - t) >> 8; the last quotient is t0 in [-64, 64].  The byte
-            // stored is X & 255 itself (two's complement of t).
-            const long long X0 = __double2ll_rn(scalbn(v[b], 55 - e));
+            for (int p = 0; p < OZ_NS; p++) {
+                const int i = OZ_NS - 1 - p;                          // byte index of slice p
+                const unsigned sel = (unsigned)((i & 3) | (((i & 3) + 4) << 4));
 #pragma unroll
-            for (int side = 0; side < 2; side++) {
-                if (side == 1 && !write_r) continue;
-                long long X = (side == 1 && ((negmask >> b) & 1u)) ? -X0 : X0;
-#pragma unroll
-                for (int p = OZ_NS - 1; p >= 0; p--) {
-                    const unsigned byte = (unsigned)X & 0xffu;
-                    const unsigned word = byte << (8 * (b & 3));
-                    if (side == 0) wl[p][b >> 2] |= word; else wr[p][b >> 2] |= word;
-                    X = (X - (long long)(signed char)byte) >> 8;
+                for (int side = 0; side < 2; side++) {
+                    if (side == 1 && !write_r) continue;
+                    const unsigned* src = (i < 4) ? lo[side] : hi[side];
+                    const unsigned t01 = __byte_perm(src[0], src[1], sel);
+                    const unsigned t23 = __byte_perm(src[2], src[3], sel);
+                    const unsigned word = __byte_perm(t01, t23, 0x5410);
+                    if (side == 0) wl[p][q] = word; else wr[p][q] = word;
                 }
             }
         }
