@@ -18,7 +18,7 @@ def main(path, out):
     in_factor, fac = False, {'bytes': 0.0, 'us': 0.0, 'launches': 0}
     for r in rows.values():
         b = r.get('dram__bytes_read.sum', 0.0) + r.get('dram__bytes_write.sum', 0.0)
-        f = fam.setdefault(r['name'], {'launches': 0, 'bytes': 0.0, 'us': 0.0})
+        f = fam.setdefault(r['name'], {'launches': 0, 'bytes': 0.0, 'us': 0.0, 'first': b})
         f['launches'] += 1
         f['bytes'] += b
         f['us'] += r.get('gpu__time_duration.sum', 0.0)
@@ -32,9 +32,10 @@ def main(path, out):
             in_factor = False
     res = {'source': 'ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum over ONE steady-state Newton '
                      'step at config 3 (tools/r2_ncu_job.sh, tools/make_traffic.py); bytes = dram read + write, per launch '
-                     '(family average); ldlt_factor = all launches of the factorisation graph together'}
-    for k, f in fam.items():
-        res[k.split('<')[0] if k.split('<')[0] not in res else k] = f['bytes'] / f['launches']
+                     '(named keys: the first launch of the family in the step; per_family: averages); ldlt_factor = all launches of the '
+                     'factorisation graph together'}
+    for k, f in fam.items():     # named keys: the FIRST launch of the family in the step (residual GEMV, d2L contraction, ...)
+        res[k.split('<')[0] if k.split('<')[0] not in res else k] = f['first']
     res['ldlt_factor'] = fac['bytes']
     res['ldlt_factor_launches'] = fac['launches']
     res['per_family'] = {k: {'launches': f['launches'], 'bytes_per_launch': f['bytes'] / f['launches'],
