@@ -76,6 +76,27 @@ def test_block_column_cyclic_ldlt_world3_gloo(tmp_path):
     assert np.max(np.abs(res['X'] - Xref)) / np.max(np.abs(Xref)) < 1e-9
 
 
+def test_block_column_cyclic_deferred_bulk_update(tmp_path, monkeypatch):
+    """B200IPM_DIST_DEFER=1 (default from 8 ranks on): the owner of the next block column postpones its bulk update of
+    panel k until its own chain work is issued -- the order of updates per block column must stay the panel order."""
+    monkeypatch.setenv('B200IPM_DIST_DEFER', '1')
+    n, b = 96, 8
+    out = str(tmp_path / 'res.npz')
+    mp.spawn(_worker, args=(3, _free_port(), (1, 3), n, b, out), nprocs=3, join=True)
+    K, rhs = kkt_matrix(n, n // 4, 5)
+    res = np.load(out)
+    w = np.linalg.eigvalsh(K)
+    assert tuple(res['inertia']) == (int(np.sum(w > 0)), int(np.sum(w < 0)), 0)
+    Xref = np.linalg.solve(K, rhs)
+    assert np.max(np.abs(res['X'] - Xref)) / np.max(np.abs(Xref)) < 1e-9
+    # ... and on one rank, where deferring serialises everything but must still be right
+    F = BlockCyclicLDLT(n, (1, 1), RefTileOps(b), block=b)
+    F.load(K)
+    assert F.factor() == tuple(res['inertia'])
+    X = F.solve(rhs, nrefine=1)
+    assert np.max(np.abs(X - Xref)) / np.max(np.abs(Xref)) < 1e-9
+
+
 def test_block_cyclic_ldlt_single_rank():
     n, b = 48, 8
     K, rhs = kkt_matrix(n, 12, 9)
