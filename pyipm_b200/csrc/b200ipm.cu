@@ -75,6 +75,9 @@ struct b200ipm_engine {
     LdltWs F2;              // pseudo-inverse / second-order-correction systems (lazy)
     bool F2_ready = false;
     int F2_n = 0;
+    LdltWs F2alt;           // the previously used order of F2: init_lambda (order min(D, M+N)) and the second-order correction
+    bool F2alt_ready = false;   // (order M+N) alternate within one solve, and a workspace costs ~100 ms to create
+    int F2alt_n = 0;
     double *Jt = nullptr;   // (M+N) x D transposed Jacobian for the SOC normal equations (lazy)
     // scratch
     double *scr = nullptr, *part = nullptr, *red = nullptr, *trial = nullptr, *xt = nullptr, *st_ = nullptr;
@@ -706,7 +709,20 @@ static int merit_trials(Eng* h, double alpha0, int k0, int nb, std::vector<doubl
 // ------------------------------------------------------------------------------------------ F2 helpers
 static int ensure_F2(Eng* h, int n) {
     if (h->F2_ready && h->F2_n == n) return 0;
-    if (h->F2_ready) ldlt_free(h->F2);
+    if (h->F2alt_ready && h->F2alt_n == n) {      // back to the other order: swap instead of re-creating
+        std::swap(h->F2, h->F2alt);
+        std::swap(h->F2_ready, h->F2alt_ready);
+        std::swap(h->F2_n, h->F2alt_n);
+        return 0;
+    }
+    if (h->F2_ready) {                             // keep the current one as the alternate
+        if (h->F2alt_ready) ldlt_free(h->F2alt);
+        std::swap(h->F2, h->F2alt);
+        h->F2alt_ready = true;
+        h->F2alt_n = h->F2_n;
+        h->F2_ready = false;
+        h->F2 = LdltWs();
+    }
     RET(ldlt_alloc(h->F2, n, h->st));
     h->F2_ready = true;
     h->F2_n = n;
@@ -1381,6 +1397,7 @@ int b200ipm_destroy(b200ipm_handle h) {
     oz_free(h->oz_soc);
     oz_free(h->oz);
     if (h->F2_ready) ldlt_free(h->F2);
+    if (h->F2alt_ready) ldlt_free(h->F2alt);
     if (h->Fb_ready) {
         ldlt_free(h->Fb);
         cudaFreeHost(h->h_cntB);
