@@ -582,12 +582,14 @@ static int resolve_pending(Eng* h, b200ipm_step_info* info, bool* redo, bool* re
 
 // ------------------------------------------------------------------------------------------ solve
 // K y for the unreduced system -> rho = b - K y, returns ||rho||_inf in h->red[0] (device)
-static int kkt_residual_vec(Eng* h, const double* b, const double* y, double* rho) {
+// jt_valid: h->jt already holds J' y_x -- true right after condensed_solve() produced this very y (its expansion step needs
+// the same product: one pass over J saved, bitwise the same numbers)
+static int kkt_residual_vec(Eng* h, const double* b, const double* y, double* rho, bool jt_valid = false) {
     const int D = h->D, M = h->M, N = h->N, K = h->K;
     if (h->C) {
         RET(gemv_n(h->st, h->J, h->ldJ, D, h->C, y + D + N, nullptr, 0.0, 1.0, h->wx));           // J [y_e; y_i]
         RET(gemv_n(h->st, h->W, h->ldW, D, D, y, h->wx, 1.0, 1.0, h->wx));                        // + W dx
-        RET(gemv_t(h->st, h->J, h->ldJ, D, h->C, y, nullptr, 0.0, 1.0, h->jt, h->scr));           // J' dx
+        if (!(jt_valid && N)) RET(gemv_t(h->st, h->J, h->ldJ, D, h->C, y, nullptr, 0.0, 1.0, h->jt, h->scr));   // J' dx
     } else {
         RET(gemv_n(h->st, h->W, h->ldW, D, D, y, nullptr, 0.0, 1.0, h->wx));
     }
@@ -626,7 +628,7 @@ static int solve_direction(Eng* h, b200ipm_step_info* info) {
     for (int i = 0; i < 4; i++) bnorm = std::max(bnorm, h->last_red[i]);
     const double tol = 1e-14 * std::max(1.0, bnorm);
     for (int it = 0;; it++) {
-        RET(kkt_residual_vec(h, h->bvec, h->ycur, h->rho));
+        RET(kkt_residual_vec(h, h->bvec, h->ycur, h->rho, it == 0));
         if (it >= h->p.nrefine) break;
         RET(fetch_red(h, h->red + 8, 1));
         if (h->h_red[0] <= tol) break;
@@ -1918,7 +1920,7 @@ static int fast_step(Eng* h, b200ipm_step_info* info, double* stats, double* tri
     axpby_kernel<<<cdiv(K, 256), 256, 0, h->st>>>(K, -1.0, h->g, 0.0, nullptr, h->bvec);
     LAUNCHED();
     RET(condensed_solve(h, h->bvec, h->ycur));
-    RET(kkt_residual_vec(h, h->bvec, h->ycur, h->rho));
+    RET(kkt_residual_vec(h, h->bvec, h->ycur, h->rho, true));
     CU(cudaMemcpyAsync(h->red + 16, h->red + 8, sizeof(double), cudaMemcpyDeviceToDevice, h->st));
     RET(condensed_solve(h, h->rho, h->ycor));
     axpby_kernel<<<cdiv(K, 256), 256, 0, h->st>>>(K, 1.0, h->ycur, 1.0, h->ycor, h->ycur);
