@@ -597,7 +597,8 @@ def run_b200(args):
                                 'traffic': traffic.get('gemv_n_kernel'), 'traffic_source': traffic.get('source'),
                                 'peak_source': 'MEASURED_PEAKS.json hbm_gbs (%s)' % peak_kind,
                                 'bytes_per_launch': res['work'],
-                                'triangular_solve': {'kernel': 'ldlt_fwd_kernel + ldlt_bwd_kernel (one right-hand side)',
+                                'triangular_solve': {'kernel': 'ldlt_fwd256_kernel + ldlt_bwd256_kernel: block-256 cluster solves, one right-hand side '
+                                                               '(B200IPM_SOLVE256=0: the 64-row chain ldlt_fwd_kernel + ldlt_bwd_kernel)',
                                                      'ms': sol['ms'], 'achieved': sol['gbs'], 'frac': sol['gbs'] / hbm_gbs,
                                                      'bytes_per_launch': sol['work']}}
         line['kernels'] = kern
