@@ -69,3 +69,29 @@ def test_truncated_slice_products_against_exact_rational_arithmetic(nd, tol):
 def test_int32_accumulators_cannot_overflow_at_the_documented_k_limit():
     # worst case: every digit at -128, 7 pairs on the longest diagonal
     assert NS * 18432 * 128 * 128 < 2 ** 31
+
+
+def test_biased_add_yields_the_same_digits_as_the_recurrence():
+    """oz_slice_kernel: the seven balanced base-256 digits of X (|X| < 2^54) used to come from seven rounds of
+    `t = sign-extended low byte; X = (X - t) >> 8`; now they are the bytes of Y = X + 0x0080808080808080 with the top bit of
+    each byte flipped (stored byte = two's complement of the digit).  Same digits, bit for bit -- including the carries
+    through runs of 0x80 / 0x7f bytes and both signs."""
+    rng = np.random.default_rng(7)
+    BIAS = 0x0080808080808080
+    xs = [0, 1, -1, 127, 128, -128, -129, 255, 256, 0x7f7f7f7f7f7f, -0x7f7f7f7f7f7f, 0x808080808080, -0x808080808080,
+          (1 << 54) - 1, -(1 << 54) + 1, 0x3f80807f80ff7f, -0x3f80807f80ff7f]
+    xs += [int(v) for v in rng.integers(-(1 << 54) + 1, (1 << 54) - 1, size=20000)]
+    for X0 in xs:
+        X, ref = X0, []
+        for _ in range(7):                       # the recurrence (lowest digit first)
+            byte = X & 0xff
+            t = byte - 256 if byte >= 128 else byte
+            ref.append(byte)
+            X = (X - t) >> 8
+        assert X == 0, X0                        # seven digits suffice below 2^54 (the last one is in [-64, 64])
+        Y = ((X0 + BIAS) & 0xffffffffffffffff) ^ BIAS
+        got = [(Y >> (8 * i)) & 0xff for i in range(7)]
+        assert got == ref, (X0, got, ref)
+        assert (Y >> 56) == 0
+        digits = [b - 256 if b >= 128 else b for b in got]
+        assert sum(d << (8 * i) for i, d in enumerate(digits)) == X0
