@@ -15,8 +15,12 @@
 // Sylvester's law of inertia makes #negative eigenvalues = #negative 1x1 pivots + #2x2 blocks with det < 0
 // (+ 2 for negative-definite 2x2 blocks), which is what pyipm.py:1381,1399 tests.
 //
-// Solves are ONE launch per direction: CTA i owns block-row i, spins on per-block epoch flags published by the
-// CTAs of earlier block rows (tickets guarantee forward progress), and applies LinvP_i as a 64 x 64 GEMV.
+// Solves are ONE launch per direction.  Default ("block-256 solves", end of this file): a link of the serial chain is a
+// 256-row block handled by one thread-block cluster of eight CTAs, which polls the values published by earlier links,
+// exchanges partial results through distributed shared memory and applies the explicit inverse of the block's 256 x 256
+// diagonal part (built by ldlt_blockinv_kernel at the end of the factorisation).  B200IPM_SOLVE256=0 keeps the original
+// chain: CTA i owns 64-row block-row i, spins on the values published by the CTAs of earlier block rows (tickets
+// guarantee forward progress), and applies LinvP_i as a 64 x 64 GEMV.
 #pragma once
 #include <algorithm>
 #include <cooperative_groups.h>
